@@ -1,0 +1,204 @@
+"""ORACLE -- TEST INFRASTRUCTURE ONLY.  Second, independent restatement in NumPy.
+
+The reference Fortran is written as whole-array slice expressions; this file
+transcribes those slice expressions one-to-one (1-based inclusive Fortran
+slices -> 0-based NumPy slices on arrays of shape (ny, nz, nx)), whereas
+oracle/mpdata_oracle.hpp was written as per-cell loops.  The two were written
+separately; tests/test_oracle_cross.py requires them to agree BIT FOR BIT in
+fp32, which catches index-translation mistakes in either.  The flux limiter
+is written here in its "independent faces" form rather
+than the Fortran's carried-variable loop, which also proves that the carried
+temporaries are pure reuse -- the property the CUDA kernels rely on.
+
+PARITY UNPINNED (no reference golden vectors exist; see mpdata_oracle.hpp).
+
+Follows /root/reference/src/physics/adv_mpdata.f90 and adv_mpdata_FCT_core.f90.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+
+def flux1(l, r, U):
+    """adv_mpdata.f90:41"""
+    return ((U + np.abs(U)) * l + (U - np.abs(U)) * r) / 2
+
+
+def upwind_advection(qin, u, v, w, rho, dz, jaco):
+    """adv_mpdata.f90:44-105.  u (ny,nz,nx-1) v (ny-1,nz,nx) w (ny,nz,nx)."""
+    ny, nz, nx = qin.shape
+    q = qin.copy()
+    J = slice(1, ny - 1)                      # do i=jms+1,jme-1
+    X = slice(1, nx - 1)                      # ims+1:ime-1
+    f1 = flux1(qin[J, :, 0:nx - 1], qin[J, :, 1:nx], u[J, :, :])
+    f3 = flux1(qin[J, :, X], qin[2:ny, :, X], v[1:ny - 1, :, X])      # v(:,:,i+1)
+    f4 = flux1(qin[0:ny - 2, :, X], qin[J, :, X], v[0:ny - 2, :, X])  # v(:,:,i)
+    f5 = flux1(qin[J, 0:nz - 1, X], qin[J, 1:nz, X], w[J, 0:nz - 1, X])
+    q[J, :, X] = q[J, :, X] - ((f1[:, :, 1:nx - 1] - f1[:, :, 0:nx - 2]) + (f3 - f4)) \
+        / (jaco[J, :, X] * rho[J, :, X])
+    q[J, 1:nz - 1, X] = q[J, 1:nz - 1, X] - (f5[:, 1:nz - 1, :] - f5[:, 0:nz - 2, :]) \
+        / (dz[J, 1:nz - 1, X] * jaco[J, 1:nz - 1, X] * rho[J, 1:nz - 1, X])
+    q[J, 0, X] = q[J, 0, X] - f5[:, 0, :] / (dz[J, 0, X] * jaco[J, 0, X] * rho[J, 0, X])
+    q[J, nz - 1, X] = q[J, nz - 1, X] - (qin[J, nz - 1, X] * w[J, nz - 1, X] - f5[:, nz - 2, :]) \
+        / (dz[J, nz - 1, X] * jaco[J, nz - 1, X] * rho[J, nz - 1, X])
+    return q
+
+
+def mpdata_fluxes(q, u, v, w, G):
+    """adv_mpdata.f90:107-255; w is W_m/dz.  Loops over (j,k) like the Fortran,
+    slice expressions in x."""
+    ny, nz, nx = q.shape
+    dt = q.dtype
+    u2 = np.zeros_like(u)
+    v2 = np.zeros_like(v)
+    w2 = np.zeros_like(w)
+    quarter = dt.type(1) / dt.type(4.0)
+    half = dt.type(0.5)
+    eps = dt.type(np.float32(1e-10))
+    for i in range(ny):            # Fortran i (y)
+        for j in range(nz):        # Fortran j (z)
+            # ---- U
+            rx = q[i, j, 1:nx]
+            lx = q[i, j, 0:nx - 1]
+            denomx = rx + lx + eps
+            GG = G[i, j, 1:nx] + G[i, j, 0:nx - 1]
+            uu = u[i, j, :]
+            t = np.abs(uu) * (1 - np.abs(uu) / (half * GG))
+            t = t * (rx - lx) / denomx
+            if 0 < i < ny - 1:
+                eq = (q[i + 1, j, 1:nx] - q[i - 1, j, 1:nx] + q[i + 1, j, 0:nx - 1] - q[i - 1, j, 0:nx - 1]) / \
+                     (q[i + 1, j, 1:nx] + q[i - 1, j, 1:nx] + q[i + 1, j, 0:nx - 1] + q[i - 1, j, 0:nx - 1] + eps)
+                # v(ims+1:ime,j,i) -> compact row i-1 ; v(..,i+1) -> row i
+                ev = quarter * (v[i - 1, j, 1:nx] + v[i, j, 1:nx] + v[i - 1, j, 0:nx - 1] + v[i, j, 0:nx - 1])
+                t = t - half * uu * ev * eq / GG
+            if 0 < j < nz - 1:
+                eq = (q[i, j + 1, 1:nx] - q[i, j - 1, 1:nx] + q[i, j + 1, 0:nx - 1] - q[i, j - 1, 0:nx - 1]) / \
+                     (q[i, j + 1, 1:nx] + q[i, j - 1, 1:nx] + q[i, j + 1, 0:nx - 1] + q[i, j - 1, 0:nx - 1] + eps)
+                ev = quarter * (w[i, j, 1:nx] + w[i, j - 1, 1:nx] + w[i, j, 0:nx - 1] + w[i, j - 1, 0:nx - 1])
+                t = t - half * uu * ev * eq / GG
+            u2[i, j, :] = t
+            # ---- V  (compact row i-1 is Fortran v(:,j,i))
+            if i > 0:
+                r = q[i, j, :]
+                l = q[i - 1, j, :]
+                denom = r + l + eps
+                GG = G[i, j, :] + G[i - 1, j, :]
+                vv = v[i - 1, j, :]
+                t = np.abs(vv) * (1 - np.abs(vv) / (half * GG))
+                t = t * (r - l) / denom
+                edge_q = np.zeros(nx, dt)
+                edge_v = np.zeros(nx, dt)
+                edge_q[1:nx - 1] = (q[i - 1, j, 2:nx] - q[i, j, 0:nx - 2] + q[i, j, 2:nx] - q[i - 1, j, 0:nx - 2]) / \
+                                   (q[i, j, 2:nx] + q[i - 1, j, 2:nx] + q[i, j, 0:nx - 2] + q[i - 1, j, 0:nx - 2] + eps)
+                # u(ims+2:ime) -> compact 1:nx-1 ; u(ims+1:ime-1) -> compact 0:nx-2
+                edge_v[1:nx - 1] = quarter * (u[i, j, 1:nx - 1] + u[i - 1, j, 1:nx - 1] + u[i, j, 0:nx - 2] + u[i - 1, j, 0:nx - 2])
+                t = t - half * vv * edge_v * edge_q / GG
+                if 0 < j < nz - 1:
+                    eq = (q[i - 1, j + 1, :] - q[i, j - 1, :] + q[i, j + 1, :] - q[i - 1, j - 1, :]) / \
+                         (q[i - 1, j + 1, :] + q[i, j - 1, :] + q[i, j + 1, :] + q[i - 1, j - 1, :] + eps)
+                    ev = quarter * (w[i, j, :] + w[i, j - 1, :] + w[i - 1, j, :] + w[i - 1, j - 1, :])
+                    t = t - half * vv * ev * eq / GG
+                v2[i - 1, j, :] = t
+            # ---- W
+            if j == nz - 1:
+                w2[i, j, :] = 0
+            else:
+                r = q[i, j + 1, :]
+                l = q[i, j, :]
+                denom = r + l + eps
+                GG = G[i, j + 1, :] + G[i, j, :]
+                ww = w[i, j, :]
+                t = np.abs(ww) * (1 - np.abs(ww) / (half * GG))
+                t = t * (r - l) / denom
+                edge_q = np.zeros(nx, dt)
+                edge_v = np.zeros(nx, dt)
+                edge_q[1:nx - 1] = (q[i, j + 1, 2:nx] - q[i, j, 0:nx - 2] + q[i, j, 2:nx] - q[i, j + 1, 0:nx - 2]) / \
+                                   (q[i, j, 2:nx] + q[i, j + 1, 2:nx] + q[i, j, 0:nx - 2] + q[i, j + 1, 0:nx - 2] + eps)
+                edge_v[1:nx - 1] = quarter * (u[i, j, 1:nx - 1] + u[i, j + 1, 1:nx - 1] + u[i, j, 0:nx - 2] + u[i, j + 1, 0:nx - 2])
+                t = t - half * ww * edge_v * edge_q / GG
+                if 0 < i < ny - 1:
+                    eq = (q[i + 1, j + 1, :] - q[i - 1, j, :] + q[i + 1, j, :] - q[i - 1, j + 1, :]) / \
+                         (q[i + 1, j, :] + q[i - 1, j + 1, :] + q[i + 1, j + 1, :] + q[i - 1, j, :] + eps)
+                    # v(:,j,i)->row i-1, v(:,j+1,i)->row i-1, v(:,j,i+1)->row i, v(:,j+1,i+1)->row i
+                    ev = quarter * (v[i - 1, j, :] + v[i - 1, j + 1, :] + v[i, j, :] + v[i, j + 1, :])
+                    t = t - half * ww * ev * eq / GG
+                w2[i, j, :] = t
+    return u2, v2, w2
+
+
+def fct_lines(q1, l, U2, is_w, axis):
+    """Independent-faces form of adv_mpdata_FCT_core.f90:47-116 applied along `axis`
+    of whole arrays.  q1, l have n cells along axis; U2 has n-1 faces.  Returns limited U2."""
+    q1 = np.moveaxis(q1, axis, -1)
+    l = np.moveaxis(l, axis, -1)
+    U2 = np.moveaxis(U2, axis, -1)
+    dt = q1.dtype
+    n = q1.shape[-1]
+    f = flux1(q1[..., :n - 1], q1[..., 1:], U2)
+    hi = np.empty_like(q1)
+    lo = np.empty_like(q1)
+    m_hi = np.maximum(q1, l)
+    m_lo = np.minimum(q1, l)
+    hi[..., 1:n - 1] = np.maximum(np.maximum(m_hi[..., 0:n - 2], m_hi[..., 1:n - 1]), m_hi[..., 2:n])
+    lo[..., 1:n - 1] = np.minimum(np.minimum(m_lo[..., 0:n - 2], m_lo[..., 1:n - 1]), m_lo[..., 2:n])
+    hi[..., 0] = np.maximum(m_hi[..., 0], m_hi[..., 1])
+    lo[..., 0] = np.minimum(m_lo[..., 0], m_lo[..., 1])
+    hi[..., n - 1] = np.maximum(np.maximum(q1[..., n - 2], q1[..., n - 1]), l[..., n - 2])
+    lo[..., n - 1] = np.minimum(np.minimum(q1[..., n - 2], q1[..., n - 1]), l[..., n - 2])
+    zero = dt.type(0)
+    fin = np.zeros_like(q1)
+    fout = np.zeros_like(q1)
+    fin[..., 1:n - 1] = np.maximum(zero, f[..., 0:n - 2]) - np.minimum(zero, f[..., 1:n - 1])
+    fout[..., 1:n - 1] = np.maximum(zero, f[..., 1:n - 1]) - np.minimum(zero, f[..., 0:n - 2])
+    if is_w:
+        fin[..., 0] = zero - np.minimum(zero, f[..., 0])
+        fout[..., 0] = np.maximum(zero, f[..., 0])
+        fin[..., n - 1] = np.maximum(zero, f[..., n - 2]) - np.minimum(zero, f[..., n - 2])
+        fout[..., n - 1] = fin[..., n - 1]
+    e15 = dt.type(np.float32(1e-15))
+    one = dt.type(1)
+    with np.errstate(divide="ignore", invalid="ignore", over="ignore"):
+        beta_in = (hi - q1) / (fin + e15)
+        beta_out = (q1 - lo) / (fout + e15)
+    pos = np.minimum(np.minimum(one, beta_in[..., 1:]), beta_out[..., :n - 1]) * U2
+    neg = np.minimum(np.minimum(one, beta_in[..., :n - 1]), beta_out[..., 1:]) * U2
+    out = np.where(U2 > 0, pos, np.where(U2 < 0, neg, U2))
+    return np.moveaxis(out, -1, axis)
+
+
+def flux_limiter(q, q2, u, v, w):
+    """adv_mpdata.f90:257-354 coverage rules.  Returns new (u, v, w)."""
+    ny, nz, nx = q.shape
+    u = u.copy()
+    v = v.copy()
+    w = w.copy()
+    J = slice(1, ny - 1)
+    u[J] = fct_lines(q2[J], q[J], u[J], False, axis=2)                       # x lines, j interior, all k
+    X = slice(1, nx - 1)
+    w[J, 0:nz - 1, X] = fct_lines(q2[J, :, X], q[J, :, X], w[J, 0:nz - 1, X], True, axis=1)
+    w[J, nz - 1, X] = 0
+    v[:] = fct_lines(q2, q, v, False, axis=0)                                # y lines, ALL i, k
+    return u, v, w
+
+
+def advect3d(q, rho, jaco, dz, U_m, V_m, W_m, order=2, fct=True):
+    """adv_mpdata.f90:356-418; returns the new q."""
+    q = q.copy()
+    q2 = None
+    for iord in range(1, order + 1):
+        if iord == 1:
+            q2 = upwind_advection(q, U_m, V_m, W_m, rho, dz, jaco)
+        else:
+            u2, v2, w2 = mpdata_fluxes(q2, U_m, V_m, W_m / dz, jaco * rho)
+            u2 = u2 * q.dtype.type(0.5)
+            v2 = v2 * q.dtype.type(0.5)
+            w2 = w2 * q.dtype.type(0.5) * dz
+            if fct:
+                u2, v2, w2 = flux_limiter(q, q2, u2, v2, w2)
+            q = upwind_advection(q2, u2, v2, w2, rho, dz, jaco)
+        if iord != order:
+            if iord > 1:
+                q2 = q.copy()
+        elif iord == 1:
+            q = q2.copy()
+    return q
