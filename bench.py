@@ -1,0 +1,373 @@
+#!/usr/bin/env python
+"""bench.py -- grid-cell-updates/s of the mp + advect model step (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A "step" is one pass of the hot path (time_step.f90:512-529: mp(halo) -> halo_send ->
+mp(subset) -> halo_retrieve -> advect) over the synthetic 512x512x40 ideal hill case
+(BASELINE.json configs[1]: MPDATA order 2 + FCT, mp_simple).  One cell-update = one (i,k,j)
+cell advanced one step through the microphysics and the MPDATA of all 5 advected scalars.
+
+  value    device-resident throughput (fields already in HBM), CUDA events on the library's
+           compute stream, max over ranks.
+  e2e      the same step through icar_physics_step_host: HOST arrays in (pinned), host arrays
+           out, H2D/D2H inside the timed region.
+  roofline ALGORITHMIC bytes (128 B per cell-update for mp_simple +
+           MPDATA x 5 scalars) / measured time, against the measured HBM copy peak.
+  cpu_baseline  the oracle (CPU restatement of the reference Fortran, "port") timed on this
+           box's host cores on a bounded sample (rank 0, N=1 only).
+
+--impl reference times that CPU restatement with all host threads instead (the reference
+Fortran itself cannot be built: no Fortran compiler in the image).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "grid_cell_updates_per_s"
+UNIT = "cell-updates/s"
+B_ALG = 128.0   # bytes per cell-update, SURVEY.md section 8d (mp_simple 56 B + MPDATA S=5 72 B)
+WORKLOAD = "ideal hill 512x512x40, MPDATA order2+FCT, mp_simple (BASELINE configs[1])"
+
+
+def measured_peak():
+    """HBM copy peak from MEASURED_PEAKS.json (driver-written), else the recipe's fallback."""
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json, burst copy)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md: 6.65 TB/s)"
+
+
+class ClockSampler:
+    """Samples SM clock / throttle reasons of one GPU through NVML while the timed region runs."""
+
+    def __init__(self, index):
+        self.samples = []
+        self.reasons = set()
+        self.max_mhz = None
+        self._stop = threading.Event()
+        self._thread = None
+        self.ok = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = int(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.ok = True
+        except Exception:
+            self.ok = False
+
+    def _reasons(self):
+        nv = self.nv
+        try:
+            mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+        except Exception:
+            try:
+                mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+            except Exception:
+                return
+        names = {
+            "hw_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+            "hw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+            "sw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+            "sw_power_cap": getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4),
+            "hw_power_brake": getattr(nv, "nvmlClocksThrottleReasonHwPowerBrakeSlowdown", 0x80),
+        }
+        for n, bit in names.items():
+            if mask & bit:
+                self.reasons.add(n)
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                self.samples.append(int(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM)))
+                self._reasons()
+            except Exception:
+                pass
+            self._stop.wait(0.005)
+
+    def start(self):
+        if self.ok:
+            self._thread = threading.Thread(target=self._run, daemon=True)
+            self._thread.start()
+
+    def stop(self):
+        if self._thread:
+            self._stop.set()
+            self._thread.join()
+        return {
+            "sm_mhz": int(statistics.median(self.samples)) if self.samples else None,
+            "sm_max_mhz": self.max_mhz,
+            "reasons": sorted(self.reasons),
+            "samples": len(self.samples),
+        }
+
+
+def physical_device(local_rank):
+    vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+    if vis:
+        try:
+            return int(vis.split(",")[local_rank])
+        except Exception:
+            return local_rank
+    return local_rank
+
+
+def slab_of(st, grid):
+    """The x-slab (with ghost columns) of a global state dict for one image's grid."""
+    lo, hi = grid.ims - 1, grid.ime
+    out = {}
+    for k, v in st.items():
+        if not isinstance(v, np.ndarray):
+            out[k] = v
+        elif k in ("u", "jacobian_u"):
+            out[k] = np.ascontiguousarray(v[:, :, lo:hi + 1])
+        elif v.ndim in (2, 3):
+            out[k] = np.ascontiguousarray(v[..., lo:hi])
+        else:
+            out[k] = v
+    return out
+
+
+# --------------------------------------------------------------------------------------------
+def cpu_oracle_rate(st, dt, min_seconds, max_steps, threads=None):
+    """Times oracle.step_simple on the full workload; returns (cells/s, steps, seconds, threads)."""
+    from oracle import oracle as O
+    O.build()
+    if threads:
+        O.set_threads(threads)
+    thr = O.max_threads()
+    work = {k: (v.copy() if isinstance(v, np.ndarray) else v) for k, v in st.items()}
+    cells = work["th"].size
+    scratch = None
+    steps, t0 = 0, time.perf_counter()
+    while steps < max_steps:
+        scratch = O.step_simple(work, np.float32(dt), np.float32(dt), 2, True, scratch)
+        steps += 1
+        if time.perf_counter() - t0 >= min_seconds:
+            break
+    el = time.perf_counter() - t0
+    return cells * steps / el, steps, el, thr
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the CPU restatement of the reference Fortran on all host threads."""
+    if rank != 0:
+        return
+    from icar_b200 import ideal
+    nx, nz, ny = args.nx, args.nz, args.ny
+    # bounded sample: a y-band of the workload sized so that K+W steps end within minutes
+    st = ideal.make_ideal_case(nx=nx, nz=nz, ny=ny, perturb=True)
+    dt = float(st["dt"])
+    from oracle import oracle as O
+    O.build()
+    thr = O.max_threads()
+    probe_ny = min(ny, 32)
+    band = {k: (np.ascontiguousarray(v[:probe_ny + (1 if k in ("v", "jacobian_v") else 0)])
+                if isinstance(v, np.ndarray) and v.ndim >= 2 else v) for k, v in st.items()}
+    t0 = time.perf_counter()
+    O.step_simple(band, np.float32(dt), np.float32(dt), 2, True)
+    per_row = (time.perf_counter() - t0) / probe_ny
+    budget = 150.0 / max(1, args.steps + args.warmup)          # seconds per step
+    sample_ny = int(max(8, min(ny, budget / max(per_row, 1e-9))))
+    band = {k: (np.ascontiguousarray(v[:sample_ny + (1 if k in ("v", "jacobian_v") else 0)])
+                if isinstance(v, np.ndarray) and v.ndim >= 2 else v) for k, v in st.items()}
+    cells = nx * nz * sample_ny
+    scratch = None
+    for _ in range(args.warmup):
+        scratch = O.step_simple(band, np.float32(dt), np.float32(dt), 2, True, scratch)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        scratch = O.step_simple(band, np.float32(dt), np.float32(dt), 2, True, scratch)
+    el = time.perf_counter() - t0
+    value = cells * args.steps / el
+    sample = f"{args.steps} steps of a {nx}x{nz}x{sample_ny} y-band of the workload"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": el / args.steps * 1e3,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": WORKLOAD, "grid": [nx, nz, ny], "sample": sample,
+                   "note": "CPU restatement (oracle port) of the reference Fortran; the Fortran itself "
+                           "cannot be compiled in this image (no gfortran)"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": thr, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------
+def run_b200(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    import icar_b200
+    from icar_b200 import ideal
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    distributed = world > 1
+    if distributed and not dist.is_initialized():
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    nx, nz, ny = args.nx, args.nz, args.ny
+    halo = args.halo
+    st = ideal.make_ideal_case(nx=nx, nz=nz, ny=ny, perturb=True)
+    dt = float(st["dt"])
+    if distributed:
+        grid = icar_b200.Grid.xslab(nx, nz, ny, world, rank + 1, halo)
+        local = slab_of(st, grid)
+    else:
+        grid = icar_b200.Grid.single_image(nx, nz, ny, halo_size=1)
+        local = st
+    dom = icar_b200.Domain(grid, icar_b200.Options(dx=st["dx"]), device=local_rank)
+    dom.upload_state(local)
+    if distributed:
+        ids = [icar_b200.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(ids, src=0)
+        dom.comm_init(rank + 1, world, ids[0])
+
+    def barrier():
+        dom.synchronize()
+        if distributed:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if not distributed:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    cells_global = nx * nz * ny
+
+    # ---------------- device-resident timing
+    for _ in range(max(args.warmup, 3)):
+        dom.physics_step(dt)
+    barrier()
+    sampler = ClockSampler(physical_device(local_rank))
+    launches0 = dom.kernel_launches
+    sampler.start()
+    dom.timer_start()
+    for _ in range(args.steps):
+        dom.physics_step(dt)
+    ms = dom.timer_stop()
+    barrier()
+    clocks = sampler.stop()
+    launches = dom.kernel_launches - launches0
+    ms = max_over_ranks(ms)
+    ms_per_step = ms / args.steps
+    value = cells_global / (ms_per_step * 1e-3)
+
+    # ---------------- end-to-end timing: host arrays in, host arrays out
+    host = {k: (np.ascontiguousarray(v) if isinstance(v, np.ndarray) else v) for k, v in local.items()}
+    for k in ("th", "qv", "qc", "qr", "qs"):
+        host[k] = dom.download(k)
+    host["precipitation"] = dom.download("precipitation")
+    host["snowfall"] = dom.download("snowfall")
+    hd = dom.host_domain(host)
+    dom.host_register(hd)
+    in_keys = ("u", "v", "w", "pressure", "pii", "rho", "th", "qv", "qc", "qr", "qs", "precipitation", "snowfall")
+    out_keys = ("th", "qv", "qc", "qr", "qs", "precipitation", "snowfall")
+    h2d = int(sum(host[k].nbytes for k in in_keys))
+    d2h = int(sum(host[k].nbytes for k in out_keys))
+    e2e_steps = max(3, min(args.steps, 10))
+    for _ in range(2):
+        dom.physics_step_host(dt, hd)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        dom.physics_step_host(dt, hd)          # returns after the D2H copies completed
+    e2e_s = time.perf_counter() - t0
+    barrier()
+    dom.host_unregister(hd)
+    e2e_s = max_over_ranks(e2e_s)
+    e2e_value = cells_global / (e2e_s / e2e_steps)
+    if distributed:
+        t = torch.tensor([h2d, d2h], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t)
+        h2d, d2h = int(t[0].item()), int(t[1].item())
+    diag = dom.mp_diagnostics()
+
+    # ---------------- CPU baseline (rank 0, N=1 only)
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        rate, csteps, csec, thr = cpu_oracle_rate(st, dt, min_seconds=10.0, max_steps=5)
+        cpu = {"value": rate, "unit": UNIT, "cores": thr, "kind": "port",
+               "sample": f"{csteps} full step(s) of the same {nx}x{nz}x{ny} workload, {csec:.1f} s, "
+                         f"OpenMP over j with {thr} threads (oracle/: C++ restatement of the Fortran)"}
+
+    peak, peak_src = measured_peak()
+    achieved = value * B_ALG / 1e9 / world          # GB/s per GPU on algorithmic bytes
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "grid": [nx, nz, ny], "dt_s": dt, "advected_scalars": 5,
+                       "decomposition": (f"x-slabs over {world} GPUs, halo {halo}, NCCL send/recv" if distributed
+                                         else "single image"),
+                       "l2": "resident working set ~1.1 GB per step > 126 MB L2, no explicit flush",
+                       "mp_diagnostics": list(diag)},
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "steps": e2e_steps, "ms_per_step": e2e_s / e2e_steps * 1e3,
+                    "api": "icar_physics_step_host (pinned host arrays)"},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": None,
+                         "kernel": "whole step (all kernels of mp + advect), per GPU",
+                         "algorithmic_bytes_per_cell_update": B_ALG, "peak_source": peak_src},
+        }
+        if cpu:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line), flush=True)
+    dom.close()
+    if distributed:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--nx", type=int, default=512)
+    ap.add_argument("--nz", type=int, default=40)
+    ap.add_argument("--ny", type=int, default=512)
+    ap.add_argument("--halo", type=int, default=3, help="ghost width for N>1 (3 = decomposition-invariant)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    if world != args.gpus and world == 1 and args.gpus > 1:
+        raise SystemExit("bench.py --gpus N>1 must be launched with torch.distributed.run (one rank per GPU)")
+    run_b200(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

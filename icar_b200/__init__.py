@@ -1,0 +1,328 @@
+"""icar_b200 -- B200-native (sm_100a) MPDATA advection + cloud microphysics for ICAR.
+
+This package is a thin ctypes binding over the C ABI in include/icar_b200.h
+(libicar_b200.so, built from icar_b200/csrc by `python -c "import __graft_entry__ as g; g.build()"`).
+All compute happens in the CUDA library; there is NO CPU fallback: importing works without a
+GPU (so that symbols can be inspected), but creating a context raises IcarError.
+
+The Python surface mirrors the reference's plugin call surface:
+    advect(domain, options, dt)              src/physics/advection_driver.f90:51
+    mp(domain, options, dt, halo, subset)    src/physics/mp_driver.f90:673
+    domain%halo_send / halo_retrieve         src/objects/domain_obj.f90:104-144
+with `Domain` playing domain_t (device-resident fields) and `Options` options_t.
+
+Arrays are NumPy float32 in the reference's memory order: Fortran (i,k,j) == C-order (ny,nz,nx).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libicar_b200.so")
+
+OK, ERR_INVALID, ERR_CUDA, ERR_PHYSICS, ERR_COMM = 0, 1, 2, 3, 4
+
+# enum icar_var (include/icar_b200.h)
+VAR = dict(
+    u=0, v=1, w=2, pressure=3, exner=4, density=5, potential_temperature=6, water_vapor=7,
+    cloud_water=8, rain_in_air=9, snow_in_air=10, jacobian=11, jacobian_u=12, jacobian_v=13,
+    jacobian_w=14, advection_dz=15, dz_mass=16, precipitation=17, snowfall=18)
+# names used by icar_b200.ideal -> domain_t member names
+ALIASES = dict(th="potential_temperature", qv="water_vapor", qc="cloud_water", qr="rain_in_air",
+               qs="snow_in_air", pii="exner", rho="density")
+
+ADVECTED_SIMPLE = ("water_vapor", "cloud_water", "rain_in_air", "snow_in_air", "potential_temperature")
+
+
+class IcarError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"icar_b200 error {code}: {msg}")
+        self.code = code
+
+
+class Grid(C.Structure):
+    """grid_t: 1-based inclusive bounds (src/objects/grid_obj.f90:144-255)."""
+    _fields_ = [(n, C.c_int) for n in (
+        "ims", "ime", "kms", "kme", "jms", "jme", "its", "ite", "kts", "kte", "jts", "jte",
+        "ids", "ide", "kds", "kde", "jds", "jde", "halo_size")]
+
+    @classmethod
+    def single_image(cls, nx, nz, ny, halo_size=1):
+        """One image owning the whole domain: tile = everything but the outermost BC cell."""
+        return cls(1, nx, 1, nz, 1, ny, 2, nx - 1, 1, nz, 2, ny - 1, 1, nx, 1, nz, 1, ny, halo_size)
+
+    @classmethod
+    def xslab(cls, nx_global, nz, ny_global, nimages, image, halo_size):
+        g = cls()
+        rc = lib().icar_grid_xslab(nx_global, nz, ny_global, nimages, image, halo_size, C.byref(g))
+        if rc:
+            raise IcarError(rc, "icar_grid_xslab: invalid decomposition")
+        return g
+
+    @property
+    def nx(self): return self.ime - self.ims + 1
+    @property
+    def nz(self): return self.kme - self.kms + 1
+    @property
+    def ny(self): return self.jme - self.jms + 1
+
+
+class Options(C.Structure):
+    """The members of options_t this path reads (see icar_options in the header)."""
+    _fields_ = [("advection", C.c_int), ("microphysics", C.c_int), ("mpdata_order", C.c_int),
+                ("flux_corrected_transport", C.c_int), ("advect_density", C.c_int),
+                ("update_interval", C.c_int), ("top_mp_level", C.c_int), ("dx", C.c_float)]
+
+    def __init__(self, **kw):
+        super().__init__()
+        lib().icar_default_options(C.byref(self))
+        for k, v in kw.items():
+            if k not in dict(self._fields_):
+                raise TypeError(f"unknown option {k}")
+            setattr(self, k, v)
+
+
+class HostDomain(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in (
+        "u", "v", "w", "pressure", "exner", "density", "potential_temperature", "water_vapor",
+        "cloud_water", "rain_in_air", "snow_in_air", "accumulated_precipitation",
+        "accumulated_snowfall")]
+
+
+_lib = None
+
+# every symbol include/icar_b200.h declares
+SYMBOLS = (
+    "icar_default_options", "icar_grid_xslab", "icar_create", "icar_destroy", "icar_last_error",
+    "icar_upload", "icar_download", "icar_device_ptr", "icar_set_model_time", "icar_get_model_time",
+    "icar_advect", "icar_mp", "icar_halo_send", "icar_halo_retrieve", "icar_halo_exchange",
+    "icar_physics_step", "icar_synchronize", "icar_mp_diagnostics", "icar_kernel_launches",
+    "icar_timer_start", "icar_timer_stop",
+    "icar_comm_unique_id", "icar_comm_init", "icar_mpdata_set_winds", "icar_mpdata_advect3d",
+    "icar_mpdata_set_winds_f64", "icar_mpdata_advect3d_f64", "icar_mp_simple_driver",
+    "icar_physics_step_host", "icar_host_register", "icar_host_unregister")
+
+
+def lib() -> C.CDLL:
+    """Loads libicar_b200.so; raises loudly when the CUDA extension has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise IcarError(ERR_CUDA, f"{LIB_PATH} is missing: build it with "
+                                      "`python -c 'import __graft_entry__ as g; g.build()'` "
+                                      "(there is no CPU fallback)")
+        l = C.CDLL(LIB_PATH)
+        l.icar_last_error.restype = C.c_char_p
+        l.icar_last_error.argtypes = [C.c_void_p]
+        l.icar_kernel_launches.restype = C.c_longlong
+        l.icar_kernel_launches.argtypes = [C.c_void_p]
+        _lib = l
+    return _lib
+
+
+def _f32(a, shape=None, name="array"):
+    a = np.ascontiguousarray(a, dtype=np.float32)
+    if shape is not None and tuple(a.shape) != tuple(shape):
+        raise ValueError(f"{name}: expected shape {tuple(shape)}, got {a.shape}")
+    return a
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class Domain:
+    """domain_t for the hot path: one image's tile, fields resident on one B200."""
+
+    def __init__(self, grid: Grid, options: Options | None = None, device: int = 0):
+        self.grid = grid
+        self.options = options or Options()
+        self._h = C.c_void_p()
+        rc = lib().icar_create(int(device), C.byref(self.grid), C.byref(self.options), C.byref(self._h))
+        if rc:
+            raise IcarError(rc, lib().icar_last_error(None).decode())
+
+    # -- plumbing
+    def _check(self, rc):
+        if rc:
+            raise IcarError(rc, lib().icar_last_error(self._h).decode())
+
+    def close(self):
+        if self._h:
+            lib().icar_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _shape(self, name):
+        g = self.grid
+        if name in ("u", "jacobian_u"):
+            return (g.ny, g.nz, g.nx + 1), np.float32
+        if name in ("v", "jacobian_v"):
+            return (g.ny + 1, g.nz, g.nx), np.float32
+        if name in ("precipitation", "snowfall"):
+            return (g.ny, g.nx), np.float64
+        return (g.ny, g.nz, g.nx), np.float32
+
+    # -- resident state
+    def upload(self, name, array):
+        name = ALIASES.get(name, name)
+        shape, dt = self._shape(name)
+        a = np.ascontiguousarray(array, dtype=dt)
+        if a.shape != shape:
+            raise ValueError(f"{name}: expected shape {shape}, got {a.shape}")
+        self._check(lib().icar_upload(self._h, VAR[name], _ptr(a)))
+
+    def download(self, name):
+        name = ALIASES.get(name, name)
+        shape, dt = self._shape(name)
+        a = np.empty(shape, dt)
+        self._check(lib().icar_download(self._h, VAR[name], _ptr(a)))
+        return a
+
+    def upload_state(self, st):
+        """Uploads every member of an icar_b200.ideal state dict the device side knows."""
+        for k, v in st.items():
+            n = ALIASES.get(k, k)
+            if n in VAR and isinstance(v, np.ndarray):
+                self.upload(n, v)
+
+    def device_ptr(self, name):
+        p = C.c_void_p()
+        pitch = C.c_longlong()
+        self._check(lib().icar_device_ptr(self._h, VAR[ALIASES.get(name, name)], C.byref(p), C.byref(pitch)))
+        return p.value, pitch.value
+
+    @property
+    def model_time(self):
+        s = C.c_double()
+        self._check(lib().icar_get_model_time(self._h, C.byref(s)))
+        return s.value
+
+    @model_time.setter
+    def model_time(self, seconds):
+        self._check(lib().icar_set_model_time(self._h, C.c_double(seconds)))
+
+    # -- plugin call surface
+    def advect(self, dt):
+        self._check(lib().icar_advect(self._h, C.c_float(dt)))
+
+    def mp(self, dt, halo=None, subset=None):
+        self._check(lib().icar_mp(self._h, C.c_float(dt), -1 if halo is None else int(halo),
+                                  -1 if subset is None else int(subset)))
+
+    def halo_send(self): self._check(lib().icar_halo_send(self._h))
+    def halo_retrieve(self): self._check(lib().icar_halo_retrieve(self._h))
+    def halo_exchange(self): self._check(lib().icar_halo_exchange(self._h))
+
+    def physics_step(self, dt):
+        self._check(lib().icar_physics_step(self._h, C.c_float(dt)))
+
+    def synchronize(self):
+        self._check(lib().icar_synchronize(self._h))
+
+    def mp_diagnostics(self):
+        out = (C.c_longlong * 3)()
+        self._check(lib().icar_mp_diagnostics(self._h, out))
+        return tuple(int(x) for x in out)
+
+    @property
+    def kernel_launches(self):
+        return int(lib().icar_kernel_launches(self._h))
+
+    def timer_start(self):
+        self._check(lib().icar_timer_start(self._h))
+
+    def timer_stop(self) -> float:
+        ms = C.c_float()
+        self._check(lib().icar_timer_stop(self._h, C.byref(ms)))
+        return float(ms.value)
+
+    # -- multi-image
+    def comm_init(self, image, nimages, unique_id: bytes):
+        buf = C.create_string_buffer(unique_id, 128)
+        self._check(lib().icar_comm_init(self._h, int(image), int(nimages), buf))
+
+    # -- host-pointer leaf calls
+    def mpdata_set_winds(self, u, v, w, jac_u, jac_v, jac_w, rho, dt, dx, scheme=2):
+        dt_ = np.float64 if np.asarray(w).dtype == np.float64 else np.float32
+        arrs = [np.ascontiguousarray(a, dtype=dt_) if a is not None else None
+                for a in (u, v, w, jac_u, jac_v, jac_w, rho)]
+        if dt_ == np.float64:
+            self._check(lib().icar_mpdata_set_winds_f64(self._h, *[_ptr(a) for a in arrs],
+                                                        C.c_double(dt), C.c_double(dx), int(scheme)))
+        else:
+            self._check(lib().icar_mpdata_set_winds(self._h, *[_ptr(a) for a in arrs],
+                                                    C.c_float(dt), C.c_float(dx), int(scheme)))
+
+    def mpdata_advect3d(self, q, rho, jaco, dz, order=2, fct=True):
+        """advect3d on host arrays; returns the advected copy of q."""
+        g = self.grid
+        dt_ = np.float64 if np.asarray(q).dtype == np.float64 else np.float32
+        q = np.array(q, dtype=dt_, order="C", copy=True)
+        rho = None if rho is None else np.ascontiguousarray(rho, dtype=dt_)
+        jaco = np.ascontiguousarray(jaco, dtype=dt_)
+        dz = np.ascontiguousarray(dz, dtype=dt_)
+        fn = lib().icar_mpdata_advect3d_f64 if dt_ == np.float64 else lib().icar_mpdata_advect3d
+        self._check(fn(self._h, _ptr(q), _ptr(rho), g.ims, g.ime, g.kms, g.kme, g.jms, g.jme,
+                       _ptr(jaco), _ptr(dz), int(order), int(bool(fct))))
+        return q
+
+    def mp_simple_driver(self, pressure, th, pii, rho, qv, qc, qr, qs, rain, snow, dt, dz,
+                         its, ite, jts, jte, kts, kte):
+        """mp_simple_driver on host arrays (updated in place); bounds are Fortran 1-based."""
+        g = self.grid
+        for a in (th, qv, qc, qr, qs, rain, snow):
+            assert a.dtype == np.float32 and a.flags["C_CONTIGUOUS"]
+        self._check(lib().icar_mp_simple_driver(
+            self._h, _ptr(_f32(pressure)), _ptr(th), _ptr(_f32(pii)), _ptr(_f32(rho)), _ptr(qv),
+            _ptr(qc), _ptr(qr), _ptr(qs), _ptr(rain), _ptr(snow), C.c_float(dt), _ptr(_f32(dz)),
+            g.ims, g.ime, g.jms, g.jme, g.kms, g.kme, int(its), int(ite), int(jts), int(jte),
+            int(kts), int(kte)))
+
+    # -- host-domain step (end-to-end path)
+    def host_domain(self, st):
+        """icar_host_domain over a state dict of contiguous NumPy arrays (kept alive by caller)."""
+        hd = HostDomain()
+        m = dict(u="u", v="v", w="w", pressure="pressure", exner="pii", density="rho",
+                 potential_temperature="th", water_vapor="qv", cloud_water="qc", rain_in_air="qr",
+                 snow_in_air="qs", accumulated_precipitation="precipitation",
+                 accumulated_snowfall="snowfall")
+        for field, key in m.items():
+            a = st.get(key)
+            if a is not None:
+                assert a.flags["C_CONTIGUOUS"]
+                setattr(hd, field, a.ctypes.data)
+        return hd
+
+    def physics_step_host(self, dt, hd):
+        self._check(lib().icar_physics_step_host(self._h, C.c_float(dt), C.byref(hd)))
+
+    def host_register(self, hd): self._check(lib().icar_host_register(self._h, C.byref(hd)))
+    def host_unregister(self, hd): self._check(lib().icar_host_unregister(self._h, C.byref(hd)))
+
+
+def comm_unique_id() -> bytes:
+    buf = C.create_string_buffer(128)
+    rc = lib().icar_comm_unique_id(buf)
+    if rc:
+        raise IcarError(rc, lib().icar_last_error(None).decode())
+    return buf.raw
+
+
+# -- the reference's call surface as free functions -------------------------------------------
+def advect(domain: Domain, options: Options | None, dt: float) -> None:
+    """advect(domain, options, dt) -- advection_driver.f90:51 (options live in the domain's context)."""
+    domain.advect(dt)
+
+
+def mp(domain: Domain, options: Options | None, dt: float, halo=None, subset=None) -> None:
+    """mp(domain, options, dt_in, halo, subset) -- mp_driver.f90:673."""
+    domain.mp(dt, halo=halo, subset=subset)

@@ -1,0 +1,820 @@
+// C ABI of libicar_b200 (include/icar_b200.h): the host side that mirrors the reference's
+// advect / mp / halo_send / halo_retrieve call surface and drives the sm_100a kernels.
+//
+// Reference host logic restated here:
+//   src/physics/advection_driver.f90:51-77   advect dispatch
+//   src/physics/adv_mpdata.f90:463-524       mpdata(): winds, scalar list
+//   src/physics/mp_driver.f90:398-772        mp(): update interval, tiles, precipitation
+//   src/objects/domain_obj.f90:104-155       halo_send / halo_retrieve
+//   src/objects/grid_obj.f90:116-255         decomposition bounds
+//   src/main/time_step.f90:512-529,547       the physics part of step()
+#include "../../include/icar_b200.h"
+
+#include <dlfcn.h>
+#include <nccl.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+#include "halo.cuh"
+#include "mp_simple.cuh"
+#include "mpdata.cuh"
+
+using namespace icar;
+
+namespace {
+
+std::string g_create_error;
+
+enum Shape { CELL, USTAG, VSTAG, D2 };
+
+Shape var_shape(int var) {
+    switch (var) {
+        case ICAR_VAR_U:
+        case ICAR_VAR_JACOBIAN_U: return USTAG;
+        case ICAR_VAR_V:
+        case ICAR_VAR_JACOBIAN_V: return VSTAG;
+        case ICAR_VAR_PRECIPITATION:
+        case ICAR_VAR_SNOWFALL: return D2;
+        default: return CELL;
+    }
+}
+
+// dynamically bound NCCL (so the library loads on a host without NCCL / without a GPU)
+struct Nccl {
+    void* h = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+    bool load(std::string& err) {
+        if (h) return true;
+        const char* names[] = {"libnccl.so.2", "libnccl.so"};
+        for (const char* n : names) {
+            h = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+            if (h) break;
+        }
+        if (!h) { err = std::string("cannot dlopen libnccl: ") + dlerror(); return false; }
+#define BIND(field, sym)                                                     \
+    *(void**)(&field) = dlsym(h, sym);                                       \
+    if (!field) { err = std::string("libnccl lacks ") + sym; return false; }
+        BIND(GetUniqueId, "ncclGetUniqueId")
+        BIND(CommInitRank, "ncclCommInitRank")
+        BIND(CommDestroy, "ncclCommDestroy")
+        BIND(Send, "ncclSend")
+        BIND(Recv, "ncclRecv")
+        BIND(GroupStart, "ncclGroupStart")
+        BIND(GroupEnd, "ncclGroupEnd")
+        BIND(GetErrorString, "ncclGetErrorString")
+#undef BIND
+        return true;
+    }
+};
+Nccl g_nccl;
+
+}  // namespace
+
+struct icar_ctx {
+    int device = 0;
+    icar_grid grid{};
+    icar_options opt{};
+    Geom g{};
+    int ld2 = 0;
+    cudaStream_t stream = nullptr, comm_stream = nullptr;
+    cudaEvent_t ev_packed = nullptr, ev_comm = nullptr, ev_t0 = nullptr, ev_t1 = nullptr;
+    void* vars[ICAR_VAR_COUNT] = {};
+    bool uploaded[ICAR_VAR_COUNT] = {};
+    // module arrays of adv_mpdata (U_m, V_m, W_m) + per-call temporaries
+    float *U = nullptr, *V = nullptr, *W = nullptr, *Wn = nullptr, *G = nullptr;
+    float *qa = nullptr, *qb = nullptr, *u2 = nullptr, *v2 = nullptr, *w2 = nullptr;
+    float *rain2d = nullptr, *snow2d = nullptr;
+    unsigned long long* diag = nullptr;
+    std::vector<void*> scratch;      // leaf-call staging buffers (float or double cells)
+    std::vector<size_t> scratch_bytes;
+    double model_time = 0.0, last_model_time = -999.0;
+    long long launches = 0;
+    std::string err;
+    // multi-image
+    ncclComm_t comm = nullptr;
+    int image = 1, nimages = 1;
+    float *send_w = nullptr, *send_e = nullptr, *recv_w = nullptr, *recv_e = nullptr;
+    bool exchange_in_flight = false;
+    bool winds_f64_valid = false;
+};
+
+namespace {
+
+int fail(icar_ctx* c, int code, const std::string& msg) {
+    if (c) c->err = msg; else g_create_error = msg;
+    return code;
+}
+
+#define CU(call)                                                                         \
+    do {                                                                                 \
+        cudaError_t e__ = (call);                                                        \
+        if (e__ != cudaSuccess)                                                          \
+            return fail(ctx, ICAR_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__)); \
+    } while (0)
+
+#define NC(call)                                                                         \
+    do {                                                                                 \
+        ncclResult_t r__ = (call);                                                       \
+        if (r__ != ncclSuccess)                                                          \
+            return fail(ctx, ICAR_ERR_COMM, std::string(#call) + ": " + g_nccl.GetErrorString(r__)); \
+    } while (0)
+
+size_t elem_size(int var) { return var_shape(var) == D2 ? sizeof(double) : sizeof(float); }
+
+// rows (x-lines) and row geometry of a variable
+void var_geometry(const icar_ctx* c, int var, int* width, int* pitch, size_t* rows) {
+    const Geom& g = c->g;
+    switch (var_shape(var)) {
+        case CELL:  *width = g.nx;     *pitch = g.ld;   *rows = (size_t)g.nz * g.ny; break;
+        case USTAG: *width = g.nx + 1; *pitch = g.ldu;  *rows = (size_t)g.nz * g.ny; break;
+        case VSTAG: *width = g.nx;     *pitch = g.ld;   *rows = (size_t)g.nz * (g.ny + 1); break;
+        case D2:    *width = g.nx;     *pitch = c->ld2; *rows = (size_t)g.ny; break;
+    }
+}
+
+size_t cell_elems(const icar_ctx* c) { return (size_t)c->g.ld * c->g.nz * (c->g.ny + 1); }
+
+int alloc_cells(icar_ctx* ctx, float** p) {
+    CU(cudaMalloc((void**)p, cell_elems(ctx) * sizeof(float)));
+    CU(cudaMemsetAsync(*p, 0, cell_elems(ctx) * sizeof(float), ctx->stream));
+    return ICAR_OK;
+}
+
+// staging buffer #slot with room for one padded field of `esize`-byte elements
+int get_scratch(icar_ctx* ctx, size_t slot, size_t esize, void** out) {
+    size_t need = (size_t)ctx->g.ldu * ctx->g.nz * (ctx->g.ny + 1) * esize;
+    if (ctx->scratch.size() <= slot) { ctx->scratch.resize(slot + 1, nullptr); ctx->scratch_bytes.resize(slot + 1, 0); }
+    if (ctx->scratch_bytes[slot] < need) {
+        if (ctx->scratch[slot]) CU(cudaFree(ctx->scratch[slot]));
+        ctx->scratch[slot] = nullptr;
+        CU(cudaMalloc(&ctx->scratch[slot], need));
+        CU(cudaMemsetAsync(ctx->scratch[slot], 0, need, ctx->stream));
+        ctx->scratch_bytes[slot] = need;
+    }
+    *out = ctx->scratch[slot];
+    return ICAR_OK;
+}
+
+// host (dense, reference layout) <-> device (padded rows)
+int copy_in(icar_ctx* ctx, void* dev, const void* host, int width, int pitch, size_t rows, size_t es) {
+    CU(cudaMemcpy2DAsync(dev, (size_t)pitch * es, host, (size_t)width * es, (size_t)width * es, rows,
+                         cudaMemcpyHostToDevice, ctx->stream));
+    return ICAR_OK;
+}
+int copy_out(icar_ctx* ctx, void* host, const void* dev, int width, int pitch, size_t rows, size_t es) {
+    CU(cudaMemcpy2DAsync(host, (size_t)width * es, dev, (size_t)pitch * es, (size_t)width * es, rows,
+                         cudaMemcpyDeviceToHost, ctx->stream));
+    return ICAR_OK;
+}
+
+const int kAdvectedSimple[5] = {ICAR_VAR_WATER_VAPOR, ICAR_VAR_CLOUD_WATER, ICAR_VAR_RAIN_IN_AIR,
+                                ICAR_VAR_SNOW_IN_AIR, ICAR_VAR_POTENTIAL_TEMPERATURE};
+// order of domain%halo_send (domain_obj.f90:106-119) restricted to the allocated scalars
+const int kExchangedSimple[5] = {ICAR_VAR_WATER_VAPOR, ICAR_VAR_POTENTIAL_TEMPERATURE,
+                                 ICAR_VAR_CLOUD_WATER, ICAR_VAR_RAIN_IN_AIR, ICAR_VAR_SNOW_IN_AIR};
+
+bool check_dims(const icar_ctx* c, int ims, int ime, int kms, int kme, int jms, int jme) {
+    return (ime - ims + 1) == c->g.nx && (kme - kms + 1) == c->g.nz && (jme - jms + 1) == c->g.ny;
+}
+
+int need_uploaded(icar_ctx* ctx, std::initializer_list<int> vars, const char* who) {
+    for (int v : vars)
+        if (!ctx->uploaded[v])
+            return fail(ctx, ICAR_ERR_INVALID, std::string(who) + ": domain variable " + std::to_string(v) +
+                                                   " was never uploaded (icar_upload)");
+    return ICAR_OK;
+}
+
+// process_subdomain's scheme call (mp_driver.f90:398-607) on a 1-based inclusive tile
+int run_mp_tile(icar_ctx* ctx, float mp_dt, int its, int ite, int jts, int jte, int kts, int kte) {
+    const icar_grid& gr = ctx->grid;
+    if (ite < its || jte < jts) return ICAR_OK;
+    if (ctx->opt.microphysics == 2) {
+        float c2s = std::exp(-1.0f * (1.0f / 2000.0f) * mp_dt);    // mp_simple.f90:619
+        float c2r = std::exp(-1.0f * (1.0f / 500.0f) * mp_dt);     // mp_simple.f90:620
+        ctx->launches += mp_simple_launch(
+            ctx->g, (const float*)ctx->vars[ICAR_VAR_PRESSURE],
+            (float*)ctx->vars[ICAR_VAR_POTENTIAL_TEMPERATURE], (const float*)ctx->vars[ICAR_VAR_EXNER],
+            (const float*)ctx->vars[ICAR_VAR_DENSITY], (float*)ctx->vars[ICAR_VAR_WATER_VAPOR],
+            (float*)ctx->vars[ICAR_VAR_CLOUD_WATER], (float*)ctx->vars[ICAR_VAR_RAIN_IN_AIR],
+            (float*)ctx->vars[ICAR_VAR_SNOW_IN_AIR], ctx->rain2d, ctx->snow2d, ctx->ld2, mp_dt,
+            (const float*)ctx->vars[ICAR_VAR_DZ_MASS], its - gr.ims, ite - gr.ims, jts - gr.jms,
+            jte - gr.jms, kts - gr.kms, kte - gr.kms, c2r, c2s, ctx->diag, ctx->stream);
+        CU(cudaGetLastError());
+        return ICAR_OK;
+    }
+    return fail(ctx, ICAR_ERR_INVALID, "microphysics scheme " + std::to_string(ctx->opt.microphysics) +
+                                           " is not built (only kMP_SB04 = 2)");
+}
+
+}  // namespace
+
+// ============================================================================ lifecycle
+
+extern "C" void icar_default_options(icar_options* opt) {
+    if (!opt) return;
+    opt->advection = 2;
+    opt->microphysics = 2;
+    opt->mpdata_order = 2;
+    opt->flux_corrected_transport = 1;
+    opt->advect_density = 0;
+    opt->update_interval = 0;
+    opt->top_mp_level = 0;
+    opt->dx = 4000.0f;
+}
+
+extern "C" int icar_grid_xslab(int nx_global, int nz, int ny_global, int nimages, int image,
+                               int halo_size, icar_grid* out) {
+    if (!out || nimages < 1 || image < 1 || image > nimages || nx_global < nimages || halo_size < 1)
+        return ICAR_ERR_INVALID;
+    // my_n / my_start, grid_obj.f90:116-138 with ximages = nimages, yimages = 1
+    int base_n = nx_global / nimages, rem = nx_global % nimages;
+    int n_local = base_n + (image <= rem ? 1 : 0);
+    int start = (image - 1) * base_n + (image - 1 < rem ? image - 1 : rem) + 1;
+    bool west = (image == 1), east = (image == nimages);
+    icar_grid g;
+    g.ims = start; g.ime = start + n_local - 1;
+    g.jms = 1; g.jme = ny_global;
+    g.kms = 1; g.kme = nz; g.kts = 1; g.kte = nz;
+    g.ids = 1; g.ide = nx_global; g.jds = 1; g.jde = ny_global; g.kds = 1; g.kde = nz;
+    // update_with_halos, grid_obj.f90:209-255
+    g.ims -= west ? 0 : halo_size;
+    g.ime += east ? 0 : halo_size;
+    g.its = g.ims + (west ? 1 : halo_size);
+    g.ite = g.ime - (east ? 1 : halo_size);
+    g.jts = g.jms + 1;
+    g.jte = g.jme - 1;
+    g.halo_size = halo_size;
+    *out = g;
+    return ICAR_OK;
+}
+
+extern "C" int icar_create(int device, const icar_grid* grid, const icar_options* opt, icar_ctx** out) {
+    icar_ctx* ctx = nullptr;
+    if (!grid || !opt || !out) return fail(nullptr, ICAR_ERR_INVALID, "icar_create: null argument");
+    int nx = grid->ime - grid->ims + 1, nz = grid->kme - grid->kms + 1, ny = grid->jme - grid->jms + 1;
+    if (nx < 3 || ny < 3 || nz < 1)
+        return fail(nullptr, ICAR_ERR_INVALID, "icar_create: tile must be at least 3 x 1 x 3 cells");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(nullptr, ICAR_ERR_CUDA,
+                    std::string("icar_create: no usable CUDA device (") +
+                        (e != cudaSuccess ? cudaGetErrorString(e) : "device count 0") +
+                        "); this library has no CPU fallback");
+    if (device < 0 || device >= ndev) return fail(nullptr, ICAR_ERR_INVALID, "icar_create: bad device index");
+    CU(cudaSetDevice(device));
+    ctx = new icar_ctx();
+    ctx->device = device;
+    ctx->grid = *grid;
+    ctx->opt = *opt;
+    ctx->g.nx = nx; ctx->g.nz = nz; ctx->g.ny = ny;
+    ctx->g.ld = (nx + 31) / 32 * 32;
+    ctx->g.ldu = (nx + 1 + 31) / 32 * 32;
+    ctx->ld2 = ctx->g.ld;
+    auto bail = [&](int code) { std::string m = ctx->err; icar_destroy(ctx); g_create_error = m; return code; };
+#define CUB(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { ctx->err = std::string(#call) + ": " + cudaGetErrorString(e__); return bail(ICAR_ERR_CUDA); } } while (0)
+    CUB(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    CUB(cudaStreamCreateWithFlags(&ctx->comm_stream, cudaStreamNonBlocking));
+    CUB(cudaEventCreateWithFlags(&ctx->ev_packed, cudaEventDisableTiming));
+    CUB(cudaEventCreateWithFlags(&ctx->ev_comm, cudaEventDisableTiming));
+    CUB(cudaEventCreate(&ctx->ev_t0));
+    CUB(cudaEventCreate(&ctx->ev_t1));
+    for (int v = 0; v < ICAR_VAR_COUNT; ++v) {
+        int width, pitch; size_t rows;
+        var_geometry(ctx, v, &width, &pitch, &rows);
+        size_t bytes = (var_shape(v) == D2) ? (size_t)pitch * rows * sizeof(double)
+                       : (var_shape(v) == USTAG) ? (size_t)ctx->g.ldu * nz * ny * sizeof(float)
+                                                 : cell_elems(ctx) * sizeof(float);
+        CUB(cudaMalloc(&ctx->vars[v], bytes));
+        CUB(cudaMemsetAsync(ctx->vars[v], 0, bytes, ctx->stream));
+    }
+    float** cellbufs[] = {&ctx->U, &ctx->V, &ctx->W, &ctx->Wn, &ctx->qa, &ctx->qb, &ctx->u2, &ctx->v2, &ctx->w2};
+    for (float** p : cellbufs)
+        if (alloc_cells(ctx, p) != ICAR_OK) return bail(ICAR_ERR_CUDA);
+    if (opt->advect_density && alloc_cells(ctx, &ctx->G) != ICAR_OK) return bail(ICAR_ERR_CUDA);
+    CUB(cudaMalloc((void**)&ctx->rain2d, (size_t)ctx->ld2 * ny * sizeof(float)));
+    CUB(cudaMalloc((void**)&ctx->snow2d, (size_t)ctx->ld2 * ny * sizeof(float)));
+    CUB(cudaMalloc((void**)&ctx->diag, 3 * sizeof(unsigned long long)));
+    CUB(cudaMemsetAsync(ctx->diag, 0, 3 * sizeof(unsigned long long), ctx->stream));
+    CUB(cudaStreamSynchronize(ctx->stream));
+#undef CUB
+    *out = ctx;
+    return ICAR_OK;
+}
+
+extern "C" int icar_destroy(icar_ctx* ctx) {
+    if (!ctx) return ICAR_OK;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    if (ctx->comm_stream) cudaStreamSynchronize(ctx->comm_stream);
+    if (ctx->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(ctx->comm);
+    for (void* p : ctx->vars) if (p) cudaFree(p);
+    float* bufs[] = {ctx->U, ctx->V, ctx->W, ctx->Wn, ctx->G, ctx->qa, ctx->qb, ctx->u2, ctx->v2, ctx->w2,
+                     ctx->rain2d, ctx->snow2d, ctx->send_w, ctx->send_e, ctx->recv_w, ctx->recv_e};
+    for (float* p : bufs) if (p) cudaFree(p);
+    if (ctx->diag) cudaFree(ctx->diag);
+    for (void* p : ctx->scratch) if (p) cudaFree(p);
+    if (ctx->ev_packed) cudaEventDestroy(ctx->ev_packed);
+    if (ctx->ev_comm) cudaEventDestroy(ctx->ev_comm);
+    if (ctx->ev_t0) cudaEventDestroy(ctx->ev_t0);
+    if (ctx->ev_t1) cudaEventDestroy(ctx->ev_t1);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    if (ctx->comm_stream) cudaStreamDestroy(ctx->comm_stream);
+    delete ctx;
+    return ICAR_OK;
+}
+
+extern "C" const char* icar_last_error(const icar_ctx* ctx) {
+    return ctx ? ctx->err.c_str() : g_create_error.c_str();
+}
+
+// ============================================================================ resident state
+
+extern "C" int icar_upload(icar_ctx* ctx, int var, const void* host) {
+    if (!ctx || !host || var < 0 || var >= ICAR_VAR_COUNT) return fail(ctx, ICAR_ERR_INVALID, "icar_upload: bad argument");
+    CU(cudaSetDevice(ctx->device));
+    int width, pitch; size_t rows;
+    var_geometry(ctx, var, &width, &pitch, &rows);
+    int rc = copy_in(ctx, ctx->vars[var], host, width, pitch, rows, elem_size(var));
+    if (rc) return rc;
+    CU(cudaStreamSynchronize(ctx->stream));
+    ctx->uploaded[var] = true;
+    return ICAR_OK;
+}
+
+extern "C" int icar_download(icar_ctx* ctx, int var, void* host) {
+    if (!ctx || !host || var < 0 || var >= ICAR_VAR_COUNT) return fail(ctx, ICAR_ERR_INVALID, "icar_download: bad argument");
+    CU(cudaSetDevice(ctx->device));
+    int width, pitch; size_t rows;
+    var_geometry(ctx, var, &width, &pitch, &rows);
+    int rc = copy_out(ctx, host, ctx->vars[var], width, pitch, rows, elem_size(var));
+    if (rc) return rc;
+    CU(cudaStreamSynchronize(ctx->stream));
+    return ICAR_OK;
+}
+
+extern "C" int icar_device_ptr(icar_ctx* ctx, int var, void** dptr, long long* pitch_elems) {
+    if (!ctx || var < 0 || var >= ICAR_VAR_COUNT || !dptr) return fail(ctx, ICAR_ERR_INVALID, "icar_device_ptr: bad argument");
+    int width, pitch; size_t rows;
+    var_geometry(ctx, var, &width, &pitch, &rows);
+    *dptr = ctx->vars[var];
+    if (pitch_elems) *pitch_elems = pitch;
+    return ICAR_OK;
+}
+
+extern "C" int icar_set_model_time(icar_ctx* ctx, double seconds) {
+    if (!ctx) return ICAR_ERR_INVALID;
+    ctx->model_time = seconds;
+    return ICAR_OK;
+}
+extern "C" int icar_get_model_time(icar_ctx* ctx, double* seconds) {
+    if (!ctx || !seconds) return ICAR_ERR_INVALID;
+    *seconds = ctx->model_time;
+    return ICAR_OK;
+}
+
+extern "C" int icar_synchronize(icar_ctx* ctx) {
+    if (!ctx) return ICAR_ERR_INVALID;
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaStreamSynchronize(ctx->stream));
+    CU(cudaStreamSynchronize(ctx->comm_stream));
+    return ICAR_OK;
+}
+
+extern "C" int icar_mp_diagnostics(icar_ctx* ctx, long long out[3]) {
+    if (!ctx || !out) return ICAR_ERR_INVALID;
+    CU(cudaSetDevice(ctx->device));
+    unsigned long long h[3];
+    CU(cudaMemcpyAsync(h, ctx->diag, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    for (int i = 0; i < 3; ++i) out[i] = (long long)h[i];
+    return ICAR_OK;
+}
+
+extern "C" long long icar_kernel_launches(const icar_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+extern "C" int icar_timer_start(icar_ctx* ctx) {
+    if (!ctx) return ICAR_ERR_INVALID;
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaEventRecord(ctx->ev_t0, ctx->stream));
+    return ICAR_OK;
+}
+
+extern "C" int icar_timer_stop(icar_ctx* ctx, float* elapsed_ms) {
+    if (!ctx || !elapsed_ms) return ICAR_ERR_INVALID;
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaEventRecord(ctx->ev_t1, ctx->stream));
+    CU(cudaEventSynchronize(ctx->ev_t1));
+    CU(cudaEventElapsedTime(elapsed_ms, ctx->ev_t0, ctx->ev_t1));
+    return ICAR_OK;
+}
+
+// ============================================================================ advect
+
+extern "C" int icar_advect(icar_ctx* ctx, float dt) {
+    if (!ctx) return ICAR_ERR_INVALID;
+    CU(cudaSetDevice(ctx->device));
+    if (ctx->opt.advection != 1 && ctx->opt.advection != 2)
+        return ICAR_OK;   // advect() does nothing for other values (advection_driver.f90:67-71)
+    int rc = need_uploaded(ctx, {ICAR_VAR_U, ICAR_VAR_V, ICAR_VAR_W, ICAR_VAR_JACOBIAN, ICAR_VAR_JACOBIAN_U,
+                                 ICAR_VAR_JACOBIAN_V, ICAR_VAR_JACOBIAN_W, ICAR_VAR_ADVECTION_DZ}, "icar_advect");
+    if (rc) return rc;
+    if (ctx->opt.advect_density && (rc = need_uploaded(ctx, {ICAR_VAR_DENSITY}, "icar_advect"))) return rc;
+    const Geom& g = ctx->g;
+    const float* rho = ctx->opt.advect_density ? (const float*)ctx->vars[ICAR_VAR_DENSITY] : nullptr;
+    const float* jaco = (const float*)ctx->vars[ICAR_VAR_JACOBIAN];
+    const float* dz = (const float*)ctx->vars[ICAR_VAR_ADVECTION_DZ];
+    const bool mpdata = (ctx->opt.advection == 2);
+    // adv_mpdata.f90:500-506 / advect.f90:344-347
+    ctx->launches += staged_wind_normalise<float>(
+        g, (const float*)ctx->vars[ICAR_VAR_U], (const float*)ctx->vars[ICAR_VAR_V],
+        (const float*)ctx->vars[ICAR_VAR_W], (const float*)ctx->vars[ICAR_VAR_JACOBIAN_U],
+        (const float*)ctx->vars[ICAR_VAR_JACOBIAN_V], (const float*)ctx->vars[ICAR_VAR_JACOBIAN_W], rho, dt,
+        ctx->opt.dx, mpdata ? 2 : 1, ctx->U, ctx->V, ctx->W, ctx->stream);
+    const int order = mpdata ? ctx->opt.mpdata_order : 1;
+    const float* G = jaco;          // jaco*rho with rho == 1 is jaco itself
+    if (order > 1) {
+        ctx->launches += staged_wn_G<float>(g, ctx->W, dz, jaco, rho, ctx->Wn, rho ? ctx->G : nullptr, ctx->stream);
+        if (rho) G = ctx->G;
+    }
+    // adv_mpdata.f90:512-522: every scalar with vars_to_advect > 0 (mp_simple.f90:116-118)
+    for (int s = 0; s < 5; ++s) {
+        int var = kAdvectedSimple[s];
+        float* q = (float*)ctx->vars[var];
+        float* res = nullptr;
+        ctx->launches += staged_advect3d<float>(g, q, rho, jaco, dz, ctx->U, ctx->V, ctx->W, ctx->Wn, G, order,
+                                                ctx->opt.flux_corrected_transport != 0, ctx->qa, ctx->qb,
+                                                ctx->u2, ctx->v2, ctx->w2, &res, ctx->stream);
+        // the result buffer becomes the field; the old field buffer becomes scratch
+        if (res == ctx->qa) { ctx->qa = q; ctx->vars[var] = res; }
+        else if (res == ctx->qb) { ctx->qb = q; ctx->vars[var] = res; }
+    }
+    CU(cudaGetLastError());
+    return ICAR_OK;
+}
+
+// ============================================================================ mp
+
+extern "C" int icar_mp(icar_ctx* ctx, float dt_in, int halo, int subset) {
+    if (!ctx) return ICAR_ERR_INVALID;
+    CU(cudaSetDevice(ctx->device));
+    if (ctx->opt.microphysics == 0) return ICAR_OK;
+    int rc = need_uploaded(ctx, {ICAR_VAR_PRESSURE, ICAR_VAR_EXNER, ICAR_VAR_DENSITY, ICAR_VAR_DZ_MASS}, "icar_mp");
+    if (rc) return rc;
+    const icar_grid& gr = ctx->grid;
+    const bool has_halo = halo >= 0, has_subset = subset >= 0;
+    // mp_driver.f90:698-713
+    if (ctx->last_model_time == -999.0)
+        ctx->last_model_time = ctx->model_time - (double)std::max((float)ctx->opt.update_interval, dt_in);
+    if (((ctx->model_time + (double)dt_in) - ctx->last_model_time) >= (double)ctx->opt.update_interval) {
+        float mp_dt = (float)(ctx->model_time - ctx->last_model_time);
+        if (!has_halo) ctx->last_model_time = ctx->model_time;
+        int kte = gr.kte;
+        if (ctx->opt.top_mp_level > 0) kte = std::min(kte, ctx->opt.top_mp_level);   // :723-725
+        // process_subdomain zeroes its local precipitation arrays on entry (:411-413); the tiles
+        // of one mp() call are disjoint, so one clear + one REAL*8 accumulation serve them all
+        CU(cudaMemsetAsync(ctx->rain2d, 0, (size_t)ctx->ld2 * ctx->g.ny * sizeof(float), ctx->stream));
+        CU(cudaMemsetAsync(ctx->snow2d, 0, (size_t)ctx->ld2 * ctx->g.ny * sizeof(float), ctx->stream));
+        if (has_subset)                                                                  // :728-738
+            if ((rc = run_mp_tile(ctx, mp_dt, gr.its + subset, gr.ite - subset, gr.jts + subset,
+                                  gr.jte - subset, gr.kts, kte))) return rc;
+        if (has_halo) {                                                                  // process_halo :609-658
+            if ((rc = run_mp_tile(ctx, mp_dt, gr.its, gr.its + halo - 1, gr.jts, gr.jte, gr.kts, kte))) return rc;
+            if ((rc = run_mp_tile(ctx, mp_dt, gr.ite - halo + 1, gr.ite, gr.jts, gr.jte, gr.kts, kte))) return rc;
+            if ((rc = run_mp_tile(ctx, mp_dt, gr.its + halo, gr.ite - halo, gr.jts, gr.jts + halo - 1, gr.kts, kte))) return rc;
+            if ((rc = run_mp_tile(ctx, mp_dt, gr.its + halo, gr.ite - halo, gr.jte - halo + 1, gr.jte, gr.kts, kte))) return rc;
+        }
+        if (!has_halo && !has_subset)                                                    // :754-766
+            if ((rc = run_mp_tile(ctx, mp_dt, gr.its, gr.ite, gr.jts, gr.jte, gr.kts, kte))) return rc;
+        ctx->launches += accumulate_precip_launch(ctx->g.nx, ctx->g.ny, ctx->ld2, ctx->rain2d, ctx->snow2d,
+                                                  (double*)ctx->vars[ICAR_VAR_PRECIPITATION],
+                                                  (double*)ctx->vars[ICAR_VAR_SNOWFALL], ctx->stream);
+        CU(cudaGetLastError());
+    }
+    return ICAR_OK;
+}
+
+// ============================================================================ halo exchange
+
+extern "C" int icar_comm_unique_id(char id[128]) {
+    std::string err;
+    if (!g_nccl.load(err)) { g_create_error = err; return ICAR_ERR_COMM; }
+    ncclUniqueId uid;
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+    if (g_nccl.GetUniqueId(&uid) != ncclSuccess) { g_create_error = "ncclGetUniqueId failed"; return ICAR_ERR_COMM; }
+    std::memcpy(id, &uid, 128);
+    return ICAR_OK;
+}
+
+extern "C" int icar_comm_init(icar_ctx* ctx, int image, int nimages, const char id[128]) {
+    if (!ctx || !id || image < 1 || image > nimages) return fail(ctx, ICAR_ERR_INVALID, "icar_comm_init: bad argument");
+    CU(cudaSetDevice(ctx->device));
+    ctx->image = image;
+    ctx->nimages = nimages;
+    if (nimages == 1) return ICAR_OK;
+    std::string err;
+    if (!g_nccl.load(err)) return fail(ctx, ICAR_ERR_COMM, err);
+    ncclUniqueId uid;
+    std::memcpy(&uid, id, 128);
+    NC(g_nccl.CommInitRank(&ctx->comm, nimages, uid, image - 1));
+    size_t n = (size_t)5 * ctx->g.ny * ctx->g.nz * ctx->grid.halo_size * sizeof(float);
+    CU(cudaMalloc((void**)&ctx->send_w, n));
+    CU(cudaMalloc((void**)&ctx->send_e, n));
+    CU(cudaMalloc((void**)&ctx->recv_w, n));
+    CU(cudaMalloc((void**)&ctx->recv_e, n));
+    return ICAR_OK;
+}
+
+extern "C" int icar_halo_send(icar_ctx* ctx) {
+    if (!ctx) return ICAR_ERR_INVALID;
+    if (ctx->nimages == 1) return ICAR_OK;
+    if (!ctx->comm) return fail(ctx, ICAR_ERR_COMM, "icar_halo_send: icar_comm_init was not called");
+    CU(cudaSetDevice(ctx->device));
+    const int h = ctx->grid.halo_size, nx = ctx->g.nx;
+    const bool west = ctx->image > 1, east = ctx->image < ctx->nimages;
+    float* fields[5];
+    for (int s = 0; s < 5; ++s) fields[s] = (float*)ctx->vars[kExchangedSimple[s]];
+    const size_t count = (size_t)5 * ctx->g.ny * ctx->g.nz * h;
+    // put_west: data(start+h : start+2h-1) ; put_east: data(n-2h+1 : n-h)   (exchangeable_obj.f90:303-335)
+    if (west) ctx->launches += halo_pack_launch(ctx->g, fields, 5, h, h, ctx->send_w, ctx->stream);
+    if (east) ctx->launches += halo_pack_launch(ctx->g, fields, 5, h, nx - 2 * h, ctx->send_e, ctx->stream);
+    CU(cudaGetLastError());
+    CU(cudaEventRecord(ctx->ev_packed, ctx->stream));
+    CU(cudaStreamWaitEvent(ctx->comm_stream, ctx->ev_packed, 0));
+    NC(g_nccl.GroupStart());
+    if (west) {
+        NC(g_nccl.Send(ctx->send_w, count, ncclFloat, ctx->image - 2, ctx->comm, ctx->comm_stream));
+        NC(g_nccl.Recv(ctx->recv_w, count, ncclFloat, ctx->image - 2, ctx->comm, ctx->comm_stream));
+    }
+    if (east) {
+        NC(g_nccl.Send(ctx->send_e, count, ncclFloat, ctx->image, ctx->comm, ctx->comm_stream));
+        NC(g_nccl.Recv(ctx->recv_e, count, ncclFloat, ctx->image, ctx->comm, ctx->comm_stream));
+    }
+    NC(g_nccl.GroupEnd());
+    CU(cudaEventRecord(ctx->ev_comm, ctx->comm_stream));
+    ctx->exchange_in_flight = true;
+    return ICAR_OK;
+}
+
+extern "C" int icar_halo_retrieve(icar_ctx* ctx) {
+    if (!ctx) return ICAR_ERR_INVALID;
+    if (ctx->nimages == 1) return ICAR_OK;
+    if (!ctx->exchange_in_flight) return fail(ctx, ICAR_ERR_INVALID, "icar_halo_retrieve without icar_halo_send");
+    CU(cudaSetDevice(ctx->device));
+    const int h = ctx->grid.halo_size, nx = ctx->g.nx;
+    const bool west = ctx->image > 1, east = ctx->image < ctx->nimages;
+    float* fields[5];
+    for (int s = 0; s < 5; ++s) fields[s] = (float*)ctx->vars[kExchangedSimple[s]];
+    CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_comm, 0));     // `sync images(neighbors)`, exchangeable_obj.f90:151
+    // retrieve_west_halo: data(start : start+h-1) ; retrieve_east_halo: data(n-h+1 : n)  (:339-356)
+    if (west) ctx->launches += halo_unpack_launch(ctx->g, fields, 5, h, 0, ctx->recv_w, ctx->stream);
+    if (east) ctx->launches += halo_unpack_launch(ctx->g, fields, 5, h, nx - h, ctx->recv_e, ctx->stream);
+    CU(cudaGetLastError());
+    ctx->exchange_in_flight = false;
+    return ICAR_OK;
+}
+
+extern "C" int icar_halo_exchange(icar_ctx* ctx) {
+    int rc = icar_halo_send(ctx);
+    return rc ? rc : icar_halo_retrieve(ctx);
+}
+
+// ============================================================================ step
+
+extern "C" int icar_physics_step(icar_ctx* ctx, float dt) {
+    if (!ctx) return ICAR_ERR_INVALID;
+    int rc;
+    const int h = ctx->grid.halo_size;
+    if (dt > 1e-3f) {                                             // time_step.f90:484
+        if ((rc = icar_mp(ctx, dt, h, -1))) return rc;            // :512  mp(halo=1)
+        if ((rc = icar_halo_send(ctx))) return rc;                // :515
+        if ((rc = icar_mp(ctx, dt, -1, h))) return rc;            // :523  mp(subset=1)
+        if ((rc = icar_halo_retrieve(ctx))) return rc;            // :526
+        if ((rc = icar_advect(ctx, dt))) return rc;               // :529
+    }
+    ctx->model_time += (double)dt;                                // :547
+    return ICAR_OK;
+}
+
+// ============================================================================ host-pointer leaf calls
+
+namespace {
+
+template <class R>
+int leaf_set_winds(icar_ctx* ctx, const R* u, const R* v, const R* w, const R* ju, const R* jv, const R* jw,
+                   const R* rho, R dt, R dx, int scheme, size_t slot0) {
+    const Geom& g = ctx->g;
+    const size_t es = sizeof(R);
+    void* b[10];
+    for (int i = 0; i < 10; ++i) { int rc = get_scratch(ctx, slot0 + i, es, &b[i]); if (rc) return rc; }
+    const size_t rows = (size_t)g.nz * g.ny;
+    int rc;
+    if ((rc = copy_in(ctx, b[0], u, g.nx + 1, g.ldu, rows, es))) return rc;
+    if ((rc = copy_in(ctx, b[1], v, g.nx, g.ld, (size_t)g.nz * (g.ny + 1), es))) return rc;
+    if ((rc = copy_in(ctx, b[2], w, g.nx, g.ld, rows, es))) return rc;
+    if ((rc = copy_in(ctx, b[3], ju, g.nx + 1, g.ldu, rows, es))) return rc;
+    if ((rc = copy_in(ctx, b[4], jv, g.nx, g.ld, (size_t)g.nz * (g.ny + 1), es))) return rc;
+    if ((rc = copy_in(ctx, b[5], jw, g.nx, g.ld, rows, es))) return rc;
+    if (rho && (rc = copy_in(ctx, b[6], rho, g.nx, g.ld, rows, es))) return rc;
+    ctx->launches += staged_wind_normalise<R>(g, (R*)b[0], (R*)b[1], (R*)b[2], (R*)b[3], (R*)b[4], (R*)b[5],
+                                              rho ? (R*)b[6] : nullptr, dt, dx, scheme, (R*)b[7], (R*)b[8],
+                                              (R*)b[9], ctx->stream);
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(ctx->stream));
+    return ICAR_OK;
+}
+
+template <class R>
+int leaf_advect3d(icar_ctx* ctx, R* q, const R* rho, const R* jaco, const R* dz, int order, bool fct,
+                  size_t slot0) {
+    const Geom& g = ctx->g;
+    const size_t es = sizeof(R);
+    void* b[22];
+    for (int i = 0; i < 22; ++i) { int rc = get_scratch(ctx, slot0 + i, es, &b[i]); if (rc) return rc; }
+    R *U = (R*)b[7], *V = (R*)b[8], *W = (R*)b[9];
+    R *dq = (R*)b[10], *drho = (R*)b[11], *djaco = (R*)b[12], *ddz = (R*)b[13], *Wn = (R*)b[14], *G = (R*)b[15];
+    R *qa = (R*)b[16], *qb = (R*)b[17], *u2 = (R*)b[18], *v2 = (R*)b[19], *w2 = (R*)b[20];
+    const size_t rows = (size_t)g.nz * g.ny;
+    int rc;
+    if ((rc = copy_in(ctx, dq, q, g.nx, g.ld, rows, es))) return rc;
+    if (rho && (rc = copy_in(ctx, drho, rho, g.nx, g.ld, rows, es))) return rc;
+    if ((rc = copy_in(ctx, djaco, jaco, g.nx, g.ld, rows, es))) return rc;
+    if ((rc = copy_in(ctx, ddz, dz, g.nx, g.ld, rows, es))) return rc;
+    const R* Gp = djaco;
+    if (order > 1) {
+        ctx->launches += staged_wn_G<R>(g, W, ddz, djaco, rho ? drho : nullptr, Wn, rho ? G : nullptr, ctx->stream);
+        if (rho) Gp = G;
+    }
+    R* res = nullptr;
+    ctx->launches += staged_advect3d<R>(g, dq, rho ? drho : nullptr, djaco, ddz, U, V, W, Wn, Gp, order, fct, qa,
+                                        qb, u2, v2, w2, &res, ctx->stream);
+    CU(cudaGetLastError());
+    if ((rc = copy_out(ctx, q, res, g.nx, g.ld, rows, es))) return rc;
+    CU(cudaStreamSynchronize(ctx->stream));
+    return ICAR_OK;
+}
+
+}  // namespace
+
+// scratch slots: 0..21 float leaf calls, 32..53 double leaf calls, 64.. mp_simple leaf call
+extern "C" int icar_mpdata_set_winds(icar_ctx* ctx, const float* u, const float* v, const float* w,
+                                     const float* ju, const float* jv, const float* jw, const float* rho,
+                                     float dt, float dx, int scheme) {
+    if (!ctx || !u || !v || !w || !ju || !jv || !jw) return fail(ctx, ICAR_ERR_INVALID, "icar_mpdata_set_winds: null array");
+    CU(cudaSetDevice(ctx->device));
+    return leaf_set_winds<float>(ctx, u, v, w, ju, jv, jw, rho, dt, dx, scheme, 0);
+}
+
+extern "C" int icar_mpdata_advect3d(icar_ctx* ctx, float* q, const float* rho, int ims, int ime, int kms,
+                                    int kme, int jms, int jme, const float* jaco, const float* dz, int order,
+                                    int fct) {
+    if (!ctx || !q || !jaco || !dz) return fail(ctx, ICAR_ERR_INVALID, "icar_mpdata_advect3d: null array");
+    if (!check_dims(ctx, ims, ime, kms, kme, jms, jme)) return fail(ctx, ICAR_ERR_INVALID, "icar_mpdata_advect3d: bounds do not match the context's tile");
+    if (order < 1) return ICAR_OK;      // `do iord=1,mpdata_order` runs zero times
+    if (ctx->scratch.size() < 10 || !ctx->scratch[9]) return fail(ctx, ICAR_ERR_INVALID, "icar_mpdata_advect3d before icar_mpdata_set_winds");
+    CU(cudaSetDevice(ctx->device));
+    return leaf_advect3d<float>(ctx, q, rho, jaco, dz, order, fct != 0, 0);
+}
+
+extern "C" int icar_mpdata_set_winds_f64(icar_ctx* ctx, const double* u, const double* v, const double* w,
+                                         const double* ju, const double* jv, const double* jw,
+                                         const double* rho, double dt, double dx, int scheme) {
+    if (!ctx || !u || !v || !w || !ju || !jv || !jw) return fail(ctx, ICAR_ERR_INVALID, "icar_mpdata_set_winds_f64: null array");
+    CU(cudaSetDevice(ctx->device));
+    int rc = leaf_set_winds<double>(ctx, u, v, w, ju, jv, jw, rho, dt, dx, scheme, 32);
+    if (!rc) ctx->winds_f64_valid = true;
+    return rc;
+}
+
+extern "C" int icar_mpdata_advect3d_f64(icar_ctx* ctx, double* q, const double* rho, int ims, int ime,
+                                        int kms, int kme, int jms, int jme, const double* jaco,
+                                        const double* dz, int order, int fct) {
+    if (!ctx || !q || !jaco || !dz) return fail(ctx, ICAR_ERR_INVALID, "icar_mpdata_advect3d_f64: null array");
+    if (!check_dims(ctx, ims, ime, kms, kme, jms, jme)) return fail(ctx, ICAR_ERR_INVALID, "icar_mpdata_advect3d_f64: bounds do not match the context's tile");
+    if (order < 1) return ICAR_OK;
+    if (!ctx->winds_f64_valid) return fail(ctx, ICAR_ERR_INVALID, "icar_mpdata_advect3d_f64 before icar_mpdata_set_winds_f64");
+    CU(cudaSetDevice(ctx->device));
+    return leaf_advect3d<double>(ctx, q, rho, jaco, dz, order, fct != 0, 32);
+}
+
+extern "C" int icar_mp_simple_driver(icar_ctx* ctx, const float* pressure, float* th, const float* pii,
+                                     const float* rho, float* qv, float* qc, float* qr, float* qs,
+                                     float* rain, float* snow, float dt, const float* dz, int ims, int ime,
+                                     int jms, int jme, int kms, int kme, int its, int ite, int jts, int jte,
+                                     int kts, int kte) {
+    if (!ctx || !pressure || !th || !pii || !rho || !qv || !qc || !qr || !qs || !rain || !snow || !dz)
+        return fail(ctx, ICAR_ERR_INVALID, "icar_mp_simple_driver: null array");
+    if (!check_dims(ctx, ims, ime, kms, kme, jms, jme)) return fail(ctx, ICAR_ERR_INVALID, "icar_mp_simple_driver: bounds do not match the context's tile");
+    if (its < ims || ite > ime || jts < jms || jte > jme || kts < kms || kte > kme)
+        return fail(ctx, ICAR_ERR_INVALID, "icar_mp_simple_driver: tile outside memory bounds");
+    CU(cudaSetDevice(ctx->device));
+    const Geom& g = ctx->g;
+    void* b[11];
+    for (int i = 0; i < 11; ++i) { int rc = get_scratch(ctx, 64 + i, sizeof(float), &b[i]); if (rc) return rc; }
+    const size_t rows = (size_t)g.nz * g.ny;
+    const float* in3[9] = {pressure, th, pii, rho, qv, qc, qr, qs, dz};
+    int rc;
+    for (int i = 0; i < 9; ++i)
+        if ((rc = copy_in(ctx, b[i], in3[i], g.nx, g.ld, rows, sizeof(float)))) return rc;
+    if ((rc = copy_in(ctx, b[9], rain, g.nx, ctx->ld2, g.ny, sizeof(float)))) return rc;
+    if ((rc = copy_in(ctx, b[10], snow, g.nx, ctx->ld2, g.ny, sizeof(float)))) return rc;
+    float c2s = std::exp(-1.0f * (1.0f / 2000.0f) * dt);
+    float c2r = std::exp(-1.0f * (1.0f / 500.0f) * dt);
+    ctx->launches += mp_simple_launch(g, (float*)b[0], (float*)b[1], (float*)b[2], (float*)b[3], (float*)b[4],
+                                      (float*)b[5], (float*)b[6], (float*)b[7], (float*)b[9], (float*)b[10],
+                                      ctx->ld2, dt, (float*)b[8], its - ims, ite - ims, jts - jms, jte - jms,
+                                      kts - kms, kte - kms, c2r, c2s, ctx->diag, ctx->stream);
+    CU(cudaGetLastError());
+    float* out3[5] = {th, qv, qc, qr, qs};
+    const int idx3[5] = {1, 4, 5, 6, 7};
+    for (int i = 0; i < 5; ++i)
+        if ((rc = copy_out(ctx, out3[i], b[idx3[i]], g.nx, g.ld, rows, sizeof(float)))) return rc;
+    if ((rc = copy_out(ctx, rain, b[9], g.nx, ctx->ld2, g.ny, sizeof(float)))) return rc;
+    if ((rc = copy_out(ctx, snow, b[10], g.nx, ctx->ld2, g.ny, sizeof(float)))) return rc;
+    CU(cudaStreamSynchronize(ctx->stream));
+    return ICAR_OK;
+}
+
+// ============================================================================ host-domain step
+
+namespace {
+struct HostField { int var; const void* in; void* out; };
+
+void host_fields(const icar_host_domain* d, std::vector<HostField>& f) {
+    f = {
+        {ICAR_VAR_U, d->u, nullptr}, {ICAR_VAR_V, d->v, nullptr}, {ICAR_VAR_W, d->w, nullptr},
+        {ICAR_VAR_PRESSURE, d->pressure, nullptr}, {ICAR_VAR_EXNER, d->exner, nullptr},
+        {ICAR_VAR_DENSITY, d->density, nullptr},
+        {ICAR_VAR_POTENTIAL_TEMPERATURE, d->potential_temperature, d->potential_temperature},
+        {ICAR_VAR_WATER_VAPOR, d->water_vapor, d->water_vapor},
+        {ICAR_VAR_CLOUD_WATER, d->cloud_water, d->cloud_water},
+        {ICAR_VAR_RAIN_IN_AIR, d->rain_in_air, d->rain_in_air},
+        {ICAR_VAR_SNOW_IN_AIR, d->snow_in_air, d->snow_in_air},
+        {ICAR_VAR_PRECIPITATION, d->accumulated_precipitation, d->accumulated_precipitation},
+        {ICAR_VAR_SNOWFALL, d->accumulated_snowfall, d->accumulated_snowfall},
+    };
+}
+}  // namespace
+
+extern "C" int icar_physics_step_host(icar_ctx* ctx, float dt, const icar_host_domain* dom) {
+    if (!ctx || !dom) return fail(ctx, ICAR_ERR_INVALID, "icar_physics_step_host: null argument");
+    CU(cudaSetDevice(ctx->device));
+    std::vector<HostField> f;
+    host_fields(dom, f);
+    int rc;
+    for (const HostField& h : f) {
+        if (!h.in) continue;
+        int width, pitch; size_t rows;
+        var_geometry(ctx, h.var, &width, &pitch, &rows);
+        if ((rc = copy_in(ctx, ctx->vars[h.var], h.in, width, pitch, rows, elem_size(h.var)))) return rc;
+        ctx->uploaded[h.var] = true;
+    }
+    if ((rc = icar_physics_step(ctx, dt))) return rc;
+    for (const HostField& h : f) {
+        if (!h.out) continue;
+        int width, pitch; size_t rows;
+        var_geometry(ctx, h.var, &width, &pitch, &rows);
+        if ((rc = copy_out(ctx, h.out, ctx->vars[h.var], width, pitch, rows, elem_size(h.var)))) return rc;
+    }
+    CU(cudaStreamSynchronize(ctx->stream));
+    return ICAR_OK;
+}
+
+extern "C" int icar_host_register(icar_ctx* ctx, const icar_host_domain* dom) {
+    if (!ctx || !dom) return fail(ctx, ICAR_ERR_INVALID, "icar_host_register: null argument");
+    CU(cudaSetDevice(ctx->device));
+    std::vector<HostField> f;
+    host_fields(dom, f);
+    for (const HostField& h : f) {
+        if (!h.in) continue;
+        int width, pitch; size_t rows;
+        var_geometry(ctx, h.var, &width, &pitch, &rows);
+        CU(cudaHostRegister(const_cast<void*>(h.in), (size_t)width * rows * elem_size(h.var), cudaHostRegisterDefault));
+    }
+    return ICAR_OK;
+}
+
+extern "C" int icar_host_unregister(icar_ctx* ctx, const icar_host_domain* dom) {
+    if (!ctx || !dom) return fail(ctx, ICAR_ERR_INVALID, "icar_host_unregister: null argument");
+    CU(cudaSetDevice(ctx->device));
+    std::vector<HostField> f;
+    host_fields(dom, f);
+    for (const HostField& h : f) {
+        if (!h.in) continue;
+        CU(cudaHostUnregister(const_cast<void*>(h.in)));
+    }
+    return ICAR_OK;
+}

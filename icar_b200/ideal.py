@@ -69,6 +69,8 @@ def make_ideal_case(nx=100, nz=20, ny=100, dx=4000.0, dz_level=400.0, terrain=Tr
     if terrain:
         max_level = nz - 1                      # find_flat_model_level with flat_z_height=-1
         H = F(dzl[:max_level].sum())
+        if not H > hgt.max():
+            raise ValueError(f"terrain ({hgt.max()} m) reaches the flat level ({H} m): use more levels")
         jac[:, :max_level, :] = ((H - hgt) / H).reshape(ny, 1, nx)
     dz_interface = dzl.reshape(1, nz, 1) * jac
     dz_mass = np.empty_like(jac)

@@ -1,0 +1,231 @@
+/* icar_b200.h -- C ABI of the B200-native replacement for ICAR's advection +
+ * microphysics hot path (src/physics/advection*, src/physics/mp_*).
+ *
+ * Every entry point is `extern "C"`, takes plain pointers / sizes and returns an
+ * int status (0 = ICAR_OK); a message for the last failure is available from
+ * icar_last_error().  The reference reports errors with `stop` / `error stop`
+ * (time_step.f90:322-328, mp_simple.f90:354-356, exchangeable_obj.f90:38); the
+ * Fortran shim (icar_b200/fortran/icar_b200_mod.f90) turns a non-zero status
+ * into `error stop`.
+ *
+ * Arrays are the reference's own: Fortran column-major, 32-bit real,
+ *   3-D  (ims:ime, kms:kme, jms:jme)       x fastest, z middle, y slowest
+ *   u    (ims:ime+1, kms:kme, jms:jme)     staggered in x  (domain_obj.f90, u_grid)
+ *   v    (ims:ime, kms:kme, jms:jme+1)     staggered in y
+ *   2-D  (ims:ime, jms:jme)
+ * Index arguments are the Fortran 1-based inclusive bounds (grid_t, grid_obj.f90:144-255).
+ *
+ * Two ways in:
+ *   resident  -- a context owns device copies of the domain fields; the plugin
+ *                calls icar_mp / icar_halo_* / icar_advect operate on them.  This
+ *                is the production path (fields stay in HBM across steps).
+ *   host      -- leaf calls with host pointers that mirror the reference's leaf
+ *                subroutines one-to-one (advect3d, mp_simple_driver); each call
+ *                uploads, runs the same kernels and downloads.
+ *
+ * Threading: like the reference (one coarray image enters mp()/advect() with one
+ * thread), a context is entered by one host thread at a time.  One context = one GPU.
+ */
+#ifndef ICAR_B200_H
+#define ICAR_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ICAR_OK 0
+#define ICAR_ERR_INVALID 1   /* bad argument / call order                      */
+#define ICAR_ERR_CUDA 2      /* CUDA runtime failure (no device, OOM, launch)  */
+#define ICAR_ERR_PHYSICS 3   /* condition on which the reference would `stop`  */
+#define ICAR_ERR_COMM 4      /* NCCL / neighbour exchange failure              */
+
+typedef struct icar_ctx icar_ctx;
+
+/* grid_t (src/objects/grid_h.f90; bounds computed in grid_obj.f90:144-255). */
+typedef struct icar_grid {
+    int ims, ime, kms, kme, jms, jme; /* memory bounds of this image (incl. halo)  */
+    int its, ite, kts, kte, jts, jte; /* physics tile (excludes BC cell / halo)    */
+    int ids, ide, kds, kde, jds, jde; /* whole model domain                        */
+    int halo_size;                    /* kDEFAULT_HALO_SIZE = 1 in the reference   */
+} icar_grid;
+
+/* The members of options_t this path reads. Defaults: icar_default_options(). */
+typedef struct icar_options {
+    int advection;                /* options%physics%advection: 1 kADV_UPWIND, 2 kADV_MPDATA
+                                     (icar_constants.f90:371-372)                            */
+    int microphysics;             /* options%physics%microphysics: 0 none, 1 kMP_THOMPSON,
+                                     2 kMP_SB04 (icar_constants.f90:347-348)                 */
+    int mpdata_order;             /* adv_options%mpdata_order, default 2 (options_obj.f90:1580) */
+    int flux_corrected_transport; /* adv_options%flux_corrected_transport, default 1 (:1579)   */
+    int advect_density;           /* parameters%advect_density, default 0 (options_obj.f90:1023) */
+    int update_interval;          /* mp_options%update_interval [s], default 0 (:1282)       */
+    int top_mp_level;             /* mp_options%top_mp_level, default 0 = all (:1283)         */
+    float dx;                     /* domain%dx [m]                                           */
+} icar_options;
+
+/* kVARS-style identifiers of the domain_t members the path touches
+ * (src/objects/domain_h.f90:18-363).  3-D real unless noted. */
+enum icar_var {
+    ICAR_VAR_U = 0,                 /* domain%u%data_3d            (nx+1,nz,ny)            */
+    ICAR_VAR_V = 1,                 /* domain%v%data_3d            (nx,nz,ny+1)            */
+    ICAR_VAR_W = 2,                 /* domain%w%data_3d                                    */
+    ICAR_VAR_PRESSURE = 3,          /* domain%pressure%data_3d                             */
+    ICAR_VAR_EXNER = 4,             /* domain%exner%data_3d                                */
+    ICAR_VAR_DENSITY = 5,           /* domain%density%data_3d                              */
+    ICAR_VAR_POTENTIAL_TEMPERATURE = 6,
+    ICAR_VAR_WATER_VAPOR = 7,
+    ICAR_VAR_CLOUD_WATER = 8,
+    ICAR_VAR_RAIN_IN_AIR = 9,
+    ICAR_VAR_SNOW_IN_AIR = 10,
+    ICAR_VAR_JACOBIAN = 11,         /* domain%jacobian                                     */
+    ICAR_VAR_JACOBIAN_U = 12,       /* domain%jacobian_u           (nx+1,nz,ny)            */
+    ICAR_VAR_JACOBIAN_V = 13,       /* domain%jacobian_v           (nx,nz,ny+1)            */
+    ICAR_VAR_JACOBIAN_W = 14,       /* domain%jacobian_w                                   */
+    ICAR_VAR_ADVECTION_DZ = 15,     /* domain%advection_dz                                 */
+    ICAR_VAR_DZ_MASS = 16,          /* domain%dz_mass%data_3d                              */
+    ICAR_VAR_PRECIPITATION = 17,    /* domain%accumulated_precipitation%data_2dd (nx,ny) REAL*8 */
+    ICAR_VAR_SNOWFALL = 18,         /* domain%accumulated_snowfall%data_2dd     (nx,ny) REAL*8 */
+    ICAR_VAR_COUNT = 19
+};
+
+/* ------------------------------------------------------------------ lifecycle */
+
+/* Fills *opt with the reference's namelist defaults (options_obj.f90:1023,1259-1284,1568-1593):
+ * advection=2, microphysics=2, mpdata_order=2, FCT on, advect_density off. */
+void icar_default_options(icar_options* opt);
+
+/* grid_t%set_grid_dimensions restricted to an x-slab decomposition (ximages = nimages,
+ * yimages = 1): grid_obj.f90:116-138 (my_n / my_start) and :209-255 (update_with_halos).
+ * image is 1-based like this_image(). */
+int icar_grid_xslab(int nx_global, int nz, int ny_global, int nimages, int image, int halo_size,
+                    icar_grid* out);
+
+/* Creates a context on CUDA device `device` for one image's tile.  Replaces the allocation half
+ * of domain%init (domain_obj.f90:160-330) plus adv_init / mp_init (advection_driver.f90:24-37,
+ * mp_driver.f90:74-198) for the schemes named in `opt`.  Fails with ICAR_ERR_CUDA when no
+ * device / the CUDA build is unusable: there is no CPU fallback. */
+int icar_create(int device, const icar_grid* grid, const icar_options* opt, icar_ctx** ctx);
+int icar_destroy(icar_ctx* ctx);
+const char* icar_last_error(const icar_ctx* ctx); /* ctx may be NULL: last creation error */
+
+/* ------------------------------------------------------- resident domain state */
+
+/* Copies one domain_t member between a host array (reference layout) and its device copy.
+ * Replaces nothing in the reference (fields live in host memory there); these are the
+ * hooks output / restart use (src/io/output_obj.f90 save_file, src/io/restart.f90:11-90). */
+int icar_upload(icar_ctx* ctx, int var, const void* host);
+int icar_download(icar_ctx* ctx, int var, void* host);
+/* Device pointer and row pitch (in elements; rows are x-lines) of the current copy of `var`.
+ * Advected scalars are double-buffered: the pointer changes after every icar_advect. */
+int icar_device_ptr(icar_ctx* ctx, int var, void** dptr, long long* pitch_elems);
+
+/* domain%model_time in seconds (used by mp()'s update-interval logic, mp_driver.f90:698-713). */
+int icar_set_model_time(icar_ctx* ctx, double seconds);
+int icar_get_model_time(icar_ctx* ctx, double* seconds);
+
+/* ------------------------------------------------------------ plugin call surface */
+
+/* advect(domain, options, dt)  -- src/physics/advection_driver.f90:51-77 -> mpdata()
+ * (adv_mpdata.f90:463-524) or upwind() (advect.f90:380-418): wind normalisation, then every
+ * advected scalar (mp_simple: qv, qc, qr, qs, th) through advect3d. */
+int icar_advect(icar_ctx* ctx, float dt);
+
+/* mp(domain, options, dt_in, halo, subset) -- src/physics/mp_driver.f90:673-772.
+ * halo / subset < 0 mean "argument not present".  Implements the update_interval / mp_dt
+ * bookkeeping (:698-713), top_mp_level (:723-725), process_halo's four strips (:609-658)
+ * and the REAL*8 precipitation accumulation of process_subdomain (:587-595). */
+int icar_mp(icar_ctx* ctx, float dt_in, int halo, int subset);
+
+/* domain%halo_send / halo_retrieve / halo_exchange -- src/objects/domain_obj.f90:104-155,
+ * exchangeable_obj.f90:138-356, for an x-slab decomposition (east/west neighbours only).
+ * No-ops on a single image. */
+int icar_halo_send(icar_ctx* ctx);
+int icar_halo_retrieve(icar_ctx* ctx);
+int icar_halo_exchange(icar_ctx* ctx);
+
+/* The physics part of one pass of step()'s loop, src/main/time_step.f90:512-529 + :547:
+ * mp(halo) -> halo_send -> mp(subset) -> halo_retrieve -> advect ; model_time += dt. */
+int icar_physics_step(icar_ctx* ctx, float dt);
+
+/* Blocks until all work queued by the calls above has finished on the device. */
+int icar_synchronize(icar_ctx* ctx);
+
+/* Device-side diagnostics accumulated since creation; replaces mp_simple's print blocks
+ * (mp_simple.f90:248-278, :354-356).  out[0] = saturation iterations that hit 15,
+ * out[1] = "mp_simple ERROR" out-of-bounds events, out[2] = phase_change `stop` events. */
+int icar_mp_diagnostics(icar_ctx* ctx, long long out[3]);
+
+/* Number of CUDA kernels this context has launched since creation. */
+long long icar_kernel_launches(const icar_ctx* ctx);
+
+/* Device-side stopwatch on the context's compute stream (CUDA events): icar_timer_start queues
+ * the start mark, icar_timer_stop queues the stop mark, waits for it and returns the elapsed
+ * device time in milliseconds between the two marks.  Replaces timer_t (timer_obj.f90:13-60),
+ * which brackets physics with wall-clock timers in driver.f90:155-157. */
+int icar_timer_start(icar_ctx* ctx);
+int icar_timer_stop(icar_ctx* ctx, float* elapsed_ms);
+
+/* ------------------------------------------------- multi-image (one process per GPU) */
+
+/* ncclUniqueId bootstrap: image 1 calls icar_comm_unique_id and broadcasts the 128 bytes with
+ * whatever the host program already has (coarray co_broadcast, MPI, torch.distributed); then
+ * every image calls icar_comm_init.  Replaces exchangeable_t%set_neighbors
+ * (exchangeable_obj.f90:68-118): neighbours are image-1 (west) and image+1 (east). */
+int icar_comm_unique_id(char id[128]);
+int icar_comm_init(icar_ctx* ctx, int image, int nimages, const char id[128]);
+
+/* ------------------------------------------------- host-pointer leaf calls (stateless) */
+
+/* mpdata()'s wind normalisation, adv_mpdata.f90:500-506 (scheme 2) / setup_module_winds,
+ * advect.f90:344-347 (scheme 1).  rho may be NULL (advect_density = .false. => rho = 1).
+ * The normalised U_m, V_m, W_m stay on the device inside ctx, like the module arrays. */
+int icar_mpdata_set_winds(icar_ctx* ctx, const float* u, const float* v, const float* w,
+                          const float* jacobian_u, const float* jacobian_v,
+                          const float* jacobian_w, const float* rho, float dt, float dx,
+                          int scheme);
+
+/* advect3d(q, rho, ims,ime,kms,kme,jms,jme, jaco, dz, options) -- adv_mpdata.f90:356-418.
+ * q is updated in place.  Uses the winds of the last icar_mpdata_set_winds. */
+int icar_mpdata_advect3d(icar_ctx* ctx, float* q, const float* rho, int ims, int ime, int kms,
+                         int kme, int jms, int jme, const float* jaco, const float* dz,
+                         int mpdata_order, int flux_corrected_transport);
+/* Same in REAL*8, used for the 1e-12 mass-conservation check (no reference counterpart: the
+ * reference is built with 32-bit reals). */
+int icar_mpdata_set_winds_f64(icar_ctx* ctx, const double* u, const double* v, const double* w,
+                              const double* jacobian_u, const double* jacobian_v,
+                              const double* jacobian_w, const double* rho, double dt, double dx,
+                              int scheme);
+int icar_mpdata_advect3d_f64(icar_ctx* ctx, double* q, const double* rho, int ims, int ime,
+                             int kms, int kme, int jms, int jme, const double* jaco,
+                             const double* dz, int mpdata_order, int flux_corrected_transport);
+
+/* mp_simple_driver(pressure,th,pii,rho,qv,qc,qr,qs,rain,snow,dt,dz, ims..kme, its..kte)
+ * -- src/physics/mp_simple.f90:595-646.  th,qv,qc,qr,qs,rain,snow are updated in place. */
+int icar_mp_simple_driver(icar_ctx* ctx, const float* pressure, float* th, const float* pii,
+                          const float* rho, float* qv, float* qc, float* qr, float* qs,
+                          float* rain, float* snow, float dt, const float* dz, int ims, int ime,
+                          int jms, int jme, int kms, int kme, int its, int ite, int jts, int jte,
+                          int kts, int kte);
+
+/* Host mirror of the members of domain_t one step reads and writes.  All pointers are host
+ * arrays in the reference layout; NULL members are left untouched. */
+typedef struct icar_host_domain {
+    /* read every step */
+    const float *u, *v, *w, *pressure, *exner, *density;
+    /* read and written every step */
+    float *potential_temperature, *water_vapor, *cloud_water, *rain_in_air, *snow_in_air;
+    double *accumulated_precipitation, *accumulated_snowfall;
+} icar_host_domain;
+
+/* One physics step on HOST arrays: uploads the per-step inputs, runs icar_physics_step, and
+ * downloads the per-step outputs.  The static metric fields (jacobians, dz) must have been
+ * uploaded once with icar_upload (the reference passes `domain` to adv_init, so a shim can do
+ * that there).  icar_host_register pins the host arrays so the copies run at PCIe speed. */
+int icar_physics_step_host(icar_ctx* ctx, float dt, const icar_host_domain* dom);
+int icar_host_register(icar_ctx* ctx, const icar_host_domain* dom);
+int icar_host_unregister(icar_ctx* ctx, const icar_host_domain* dom);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ICAR_B200_H */

@@ -1,0 +1,99 @@
+"""The C-ABI library loads on a CPU-only host, exports every symbol include/icar_b200.h
+declares, its pure-host entry points behave like the reference's, and it fails loudly
+(never falls back to a CPU path) when no GPU is present."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+import icar_b200
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_functions():
+    src = open(os.path.join(ROOT, "include", "icar_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(icar_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = icar_b200.lib()
+    names = header_functions()
+    assert len(names) >= 25
+    for n in names:
+        assert hasattr(lib, n), f"libicar_b200.so does not export {n}"
+    assert sorted(icar_b200.SYMBOLS) == names
+
+
+def test_default_options_match_reference_namelist_defaults():
+    o = icar_b200.Options()
+    # options_obj.f90:1579-1581 (adv_parameters), :1023 (advect_density), :1282-1283 (mp_parameters)
+    assert (o.advection, o.microphysics, o.mpdata_order, o.flux_corrected_transport) == (2, 2, 2, 1)
+    assert (o.advect_density, o.update_interval, o.top_mp_level) == (0, 0, 0)
+
+
+def ref_xslab(nx, nz, ny, nimg, img, halo):
+    """grid_obj.f90:116-138 (my_n, my_start) + :209-255 (update_with_halos), ximages=nimg, yimages=1."""
+    base = nx // nimg
+    n = base + (1 if img <= nx % nimg else 0)
+    start = (img - 1) * base + min(img - 1, nx % nimg) + 1
+    west, east = img == 1, img == nimg
+    ims, ime = start, start + n - 1
+    ims -= 0 if west else halo
+    ime += 0 if east else halo
+    its = ims + (1 if west else halo)
+    ite = ime - (1 if east else halo)
+    return dict(ims=ims, ime=ime, its=its, ite=ite, jms=1, jme=ny, jts=2, jte=ny - 1,
+                kms=1, kme=nz, kts=1, kte=nz, ids=1, ide=nx, jds=1, jde=ny, kds=1, kde=nz)
+
+
+@pytest.mark.parametrize("nx,nimg,halo", [(512, 8, 3), (512, 8, 1), (100, 3, 1), (1024, 4, 3), (37, 5, 2)])
+def test_grid_xslab_matches_grid_obj(nx, nimg, halo):
+    owned = []
+    for img in range(1, nimg + 1):
+        g = icar_b200.Grid.xslab(nx, 20, 64, nimg, img, halo)
+        for k, v in ref_xslab(nx, 20, 64, nimg, img, halo).items():
+            assert getattr(g, k) == v, (img, k)
+        assert g.halo_size == halo
+        lo = g.ims if img == 1 else g.its
+        hi = g.ime if img == nimg else g.ite
+        owned.append((lo, hi))
+    # the owned ranges tile 1..nx exactly (test_caf_other_image_grids.f90 checks the same)
+    assert owned[0][0] == 1 and owned[-1][1] == nx
+    for (a, b), (c, d) in zip(owned, owned[1:]):
+        assert c == b + 1
+
+
+def test_grid_xslab_rejects_bad_arguments():
+    g = icar_b200.Grid()
+    lib = icar_b200.lib()
+    assert lib.icar_grid_xslab(10, 5, 10, 0, 1, 1, C.byref(g)) == icar_b200.ERR_INVALID
+    assert lib.icar_grid_xslab(10, 5, 10, 4, 5, 1, C.byref(g)) == icar_b200.ERR_INVALID
+    assert lib.icar_grid_xslab(3, 5, 10, 4, 1, 1, C.byref(g)) == icar_b200.ERR_INVALID
+
+
+def _no_gpu():
+    import torch
+    return not torch.cuda.is_available()
+
+
+@pytest.mark.skipif(not _no_gpu(), reason="only meaningful on a host without a GPU")
+def test_create_fails_loudly_without_gpu():
+    with pytest.raises(icar_b200.IcarError) as e:
+        icar_b200.Domain(icar_b200.Grid.single_image(16, 8, 16))
+    assert e.value.code == icar_b200.ERR_CUDA
+    assert "no CPU fallback" in str(e.value)
+
+
+def test_product_never_imports_the_oracle():
+    """The product path must not import, link, include or execute anything under oracle/."""
+    pkg = os.path.join(ROOT, "icar_b200")
+    pat = re.compile(r"(import|from)\s+oracle|oracle/|oracle\\.|libicar_oracle|_oracle\.hpp|oracle_api")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h", ".f90")) or f == "Makefile":
+                txt = open(os.path.join(dirpath, f), errors="ignore").read()
+                assert not pat.search(txt), (dirpath, f)
