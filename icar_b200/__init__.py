@@ -74,7 +74,8 @@ class Options(C.Structure):
     """The members of options_t this path reads (see icar_options in the header)."""
     _fields_ = [("advection", C.c_int), ("microphysics", C.c_int), ("mpdata_order", C.c_int),
                 ("flux_corrected_transport", C.c_int), ("advect_density", C.c_int),
-                ("update_interval", C.c_int), ("top_mp_level", C.c_int), ("dx", C.c_float)]
+                ("update_interval", C.c_int), ("top_mp_level", C.c_int), ("dx", C.c_float),
+                ("exact_arithmetic", C.c_int)]
 
     def __init__(self, **kw):
         super().__init__()

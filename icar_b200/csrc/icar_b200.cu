@@ -95,7 +95,16 @@ struct icar_ctx {
     // module arrays of adv_mpdata (U_m, V_m, W_m) + per-call temporaries
     float *U = nullptr, *V = nullptr, *W = nullptr, *Wn = nullptr, *G = nullptr;
     float *qa = nullptr, *qb = nullptr, *u2 = nullptr, *v2 = nullptr, *w2 = nullptr;
-    float *rain2d = nullptr, *snow2d = nullptr;
+    // fused path (mpdata_fused.cu): coefficient fields, per-scalar pass-1 scratch and output buffers
+    bool fused = false;
+    FusedCoef coef{};
+    float* fq2[5] = {};
+    float* fout[5] = {};
+    float *rain2d = nullptr, *snow2d = nullptr;      // per-call precipitation of the main-stream tile
+    float *rain2d_halo = nullptr, *snow2d_halo = nullptr;   // ... of the ring strips (aux streams)
+    cudaStream_t aux[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev_fork = nullptr, ev_aux[4] = {nullptr, nullptr, nullptr, nullptr};
+    bool aux_pending = false;        // ring strips of mp(halo) still running on the aux streams
     unsigned long long* diag = nullptr;
     std::vector<void*> scratch;      // leaf-call staging buffers (float or double cells)
     std::vector<size_t> scratch_bytes;
@@ -198,25 +207,41 @@ int need_uploaded(icar_ctx* ctx, std::initializer_list<int> vars, const char* wh
 }
 
 // process_subdomain's scheme call (mp_driver.f90:398-607) on a 1-based inclusive tile
-int run_mp_tile(icar_ctx* ctx, float mp_dt, int its, int ite, int jts, int jte, int kts, int kte) {
+int run_mp_tile(icar_ctx* ctx, float mp_dt, int its, int ite, int jts, int jte, int kts, int kte,
+                cudaStream_t st, float* rain2d, float* snow2d) {
     const icar_grid& gr = ctx->grid;
     if (ite < its || jte < jts) return ICAR_OK;
     if (ctx->opt.microphysics == 2) {
         float c2s = std::exp(-1.0f * (1.0f / 2000.0f) * mp_dt);    // mp_simple.f90:619
         float c2r = std::exp(-1.0f * (1.0f / 500.0f) * mp_dt);     // mp_simple.f90:620
-        ctx->launches += mp_simple_launch(
+        int nl = mp_simple_launch(
             ctx->g, (const float*)ctx->vars[ICAR_VAR_PRESSURE],
             (float*)ctx->vars[ICAR_VAR_POTENTIAL_TEMPERATURE], (const float*)ctx->vars[ICAR_VAR_EXNER],
             (const float*)ctx->vars[ICAR_VAR_DENSITY], (float*)ctx->vars[ICAR_VAR_WATER_VAPOR],
             (float*)ctx->vars[ICAR_VAR_CLOUD_WATER], (float*)ctx->vars[ICAR_VAR_RAIN_IN_AIR],
-            (float*)ctx->vars[ICAR_VAR_SNOW_IN_AIR], ctx->rain2d, ctx->snow2d, ctx->ld2, mp_dt,
+            (float*)ctx->vars[ICAR_VAR_SNOW_IN_AIR], rain2d, snow2d, ctx->ld2, mp_dt,
             (const float*)ctx->vars[ICAR_VAR_DZ_MASS], its - gr.ims, ite - gr.ims, jts - gr.jms,
-            jte - gr.jms, kts - gr.kms, kte - gr.kms, c2r, c2s, ctx->diag, ctx->stream);
+            jte - gr.jms, kts - gr.kms, kte - gr.kms, c2r, c2s, ctx->diag, st);
+        if (nl < 0) return fail(ctx, ICAR_ERR_INVALID, "mp_simple: more than 128 levels are not built");
+        ctx->launches += nl;
         CU(cudaGetLastError());
         return ICAR_OK;
     }
     return fail(ctx, ICAR_ERR_INVALID, "microphysics scheme " + std::to_string(ctx->opt.microphysics) +
                                            " is not built (only kMP_SB04 = 2)");
+}
+
+// Waits (on the compute stream) for the ring strips that mp(halo) left running on the aux
+// streams and folds their precipitation into the REAL*8 accumulators.
+int join_aux(icar_ctx* ctx) {
+    if (!ctx->aux_pending) return ICAR_OK;
+    for (int a = 0; a < 4; ++a) CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_aux[a], 0));
+    ctx->launches += accumulate_precip_launch(ctx->g.nx, ctx->g.ny, ctx->ld2, ctx->rain2d_halo, ctx->snow2d_halo,
+                                              (double*)ctx->vars[ICAR_VAR_PRECIPITATION],
+                                              (double*)ctx->vars[ICAR_VAR_SNOWFALL], ctx->stream);
+    CU(cudaGetLastError());
+    ctx->aux_pending = false;
+    return ICAR_OK;
 }
 
 }  // namespace
@@ -233,6 +258,7 @@ extern "C" void icar_default_options(icar_options* opt) {
     opt->update_interval = 0;
     opt->top_mp_level = 0;
     opt->dx = 4000.0f;
+    opt->exact_arithmetic = 0;
 }
 
 extern "C" int icar_grid_xslab(int nx_global, int nz, int ny_global, int nimages, int image,
@@ -305,8 +331,26 @@ extern "C" int icar_create(int device, const icar_grid* grid, const icar_options
     for (float** p : cellbufs)
         if (alloc_cells(ctx, p) != ICAR_OK) return bail(ICAR_ERR_CUDA);
     if (opt->advect_density && alloc_cells(ctx, &ctx->G) != ICAR_OK) return bail(ICAR_ERR_CUDA);
+    ctx->fused = (opt->advection == 2 && opt->mpdata_order == 2 && opt->flux_corrected_transport &&
+                  !opt->advect_density && !opt->exact_arithmetic && nz <= 64 && nz >= 2);
+    if (ctx->fused) {
+        float** cf[] = {&ctx->coef.ax, &ctx->coef.bx, &ctx->coef.cx, &ctx->coef.ay, &ctx->coef.by, &ctx->coef.cy,
+                        &ctx->coef.az, &ctx->coef.bz, &ctx->coef.cz, &ctx->coef.rj, &ctx->coef.rjz};
+        for (float** p : cf)
+            if (alloc_cells(ctx, p) != ICAR_OK) return bail(ICAR_ERR_CUDA);
+        for (int n = 0; n < 5; ++n)
+            if (alloc_cells(ctx, &ctx->fq2[n]) != ICAR_OK || alloc_cells(ctx, &ctx->fout[n]) != ICAR_OK)
+                return bail(ICAR_ERR_CUDA);
+    }
     CUB(cudaMalloc((void**)&ctx->rain2d, (size_t)ctx->ld2 * ny * sizeof(float)));
     CUB(cudaMalloc((void**)&ctx->snow2d, (size_t)ctx->ld2 * ny * sizeof(float)));
+    CUB(cudaMalloc((void**)&ctx->rain2d_halo, (size_t)ctx->ld2 * ny * sizeof(float)));
+    CUB(cudaMalloc((void**)&ctx->snow2d_halo, (size_t)ctx->ld2 * ny * sizeof(float)));
+    CUB(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
+    for (int a = 0; a < 4; ++a) {
+        CUB(cudaStreamCreateWithFlags(&ctx->aux[a], cudaStreamNonBlocking));
+        CUB(cudaEventCreateWithFlags(&ctx->ev_aux[a], cudaEventDisableTiming));
+    }
     CUB(cudaMalloc((void**)&ctx->diag, 3 * sizeof(unsigned long long)));
     CUB(cudaMemsetAsync(ctx->diag, 0, 3 * sizeof(unsigned long long), ctx->stream));
     CUB(cudaStreamSynchronize(ctx->stream));
@@ -320,13 +364,22 @@ extern "C" int icar_destroy(icar_ctx* ctx) {
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     if (ctx->comm_stream) cudaStreamSynchronize(ctx->comm_stream);
+    for (int a = 0; a < 4; ++a) if (ctx->aux[a]) cudaStreamSynchronize(ctx->aux[a]);
     if (ctx->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(ctx->comm);
     for (void* p : ctx->vars) if (p) cudaFree(p);
     float* bufs[] = {ctx->U, ctx->V, ctx->W, ctx->Wn, ctx->G, ctx->qa, ctx->qb, ctx->u2, ctx->v2, ctx->w2,
-                     ctx->rain2d, ctx->snow2d, ctx->send_w, ctx->send_e, ctx->recv_w, ctx->recv_e};
+                     ctx->rain2d, ctx->snow2d, ctx->rain2d_halo, ctx->snow2d_halo, ctx->send_w, ctx->send_e, ctx->recv_w, ctx->recv_e};
     for (float* p : bufs) if (p) cudaFree(p);
     if (ctx->diag) cudaFree(ctx->diag);
+    {
+        float* cf[] = {ctx->coef.ax, ctx->coef.bx, ctx->coef.cx, ctx->coef.ay, ctx->coef.by, ctx->coef.cy,
+                       ctx->coef.az, ctx->coef.bz, ctx->coef.cz, ctx->coef.rj, ctx->coef.rjz};
+        for (float* p : cf) if (p) cudaFree(p);
+        for (int n = 0; n < 5; ++n) { if (ctx->fq2[n]) cudaFree(ctx->fq2[n]); if (ctx->fout[n]) cudaFree(ctx->fout[n]); }
+    }
     for (void* p : ctx->scratch) if (p) cudaFree(p);
+    if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+    for (int a = 0; a < 4; ++a) { if (ctx->ev_aux[a]) cudaEventDestroy(ctx->ev_aux[a]); if (ctx->aux[a]) cudaStreamDestroy(ctx->aux[a]); }
     if (ctx->ev_packed) cudaEventDestroy(ctx->ev_packed);
     if (ctx->ev_comm) cudaEventDestroy(ctx->ev_comm);
     if (ctx->ev_t0) cudaEventDestroy(ctx->ev_t0);
@@ -346,6 +399,7 @@ extern "C" const char* icar_last_error(const icar_ctx* ctx) {
 extern "C" int icar_upload(icar_ctx* ctx, int var, const void* host) {
     if (!ctx || !host || var < 0 || var >= ICAR_VAR_COUNT) return fail(ctx, ICAR_ERR_INVALID, "icar_upload: bad argument");
     CU(cudaSetDevice(ctx->device));
+    { int jr = join_aux(ctx); if (jr) return jr; }
     int width, pitch; size_t rows;
     var_geometry(ctx, var, &width, &pitch, &rows);
     int rc = copy_in(ctx, ctx->vars[var], host, width, pitch, rows, elem_size(var));
@@ -358,6 +412,7 @@ extern "C" int icar_upload(icar_ctx* ctx, int var, const void* host) {
 extern "C" int icar_download(icar_ctx* ctx, int var, void* host) {
     if (!ctx || !host || var < 0 || var >= ICAR_VAR_COUNT) return fail(ctx, ICAR_ERR_INVALID, "icar_download: bad argument");
     CU(cudaSetDevice(ctx->device));
+    { int jr = join_aux(ctx); if (jr) return jr; }
     int width, pitch; size_t rows;
     var_geometry(ctx, var, &width, &pitch, &rows);
     int rc = copy_out(ctx, host, ctx->vars[var], width, pitch, rows, elem_size(var));
@@ -389,6 +444,7 @@ extern "C" int icar_get_model_time(icar_ctx* ctx, double* seconds) {
 extern "C" int icar_synchronize(icar_ctx* ctx) {
     if (!ctx) return ICAR_ERR_INVALID;
     CU(cudaSetDevice(ctx->device));
+    { int jr = join_aux(ctx); if (jr) return jr; }
     CU(cudaStreamSynchronize(ctx->stream));
     CU(cudaStreamSynchronize(ctx->comm_stream));
     return ICAR_OK;
@@ -397,6 +453,7 @@ extern "C" int icar_synchronize(icar_ctx* ctx) {
 extern "C" int icar_mp_diagnostics(icar_ctx* ctx, long long out[3]) {
     if (!ctx || !out) return ICAR_ERR_INVALID;
     CU(cudaSetDevice(ctx->device));
+    { int jr = join_aux(ctx); if (jr) return jr; }
     unsigned long long h[3];
     CU(cudaMemcpyAsync(h, ctx->diag, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
@@ -416,6 +473,7 @@ extern "C" int icar_timer_start(icar_ctx* ctx) {
 extern "C" int icar_timer_stop(icar_ctx* ctx, float* elapsed_ms) {
     if (!ctx || !elapsed_ms) return ICAR_ERR_INVALID;
     CU(cudaSetDevice(ctx->device));
+    { int jr = join_aux(ctx); if (jr) return jr; }
     CU(cudaEventRecord(ctx->ev_t1, ctx->stream));
     CU(cudaEventSynchronize(ctx->ev_t1));
     CU(cudaEventElapsedTime(elapsed_ms, ctx->ev_t0, ctx->ev_t1));
@@ -427,6 +485,7 @@ extern "C" int icar_timer_stop(icar_ctx* ctx, float* elapsed_ms) {
 extern "C" int icar_advect(icar_ctx* ctx, float dt) {
     if (!ctx) return ICAR_ERR_INVALID;
     CU(cudaSetDevice(ctx->device));
+    { int jr = join_aux(ctx); if (jr) return jr; }
     if (ctx->opt.advection != 1 && ctx->opt.advection != 2)
         return ICAR_OK;   // advect() does nothing for other values (advection_driver.f90:67-71)
     int rc = need_uploaded(ctx, {ICAR_VAR_U, ICAR_VAR_V, ICAR_VAR_W, ICAR_VAR_JACOBIAN, ICAR_VAR_JACOBIAN_U,
@@ -449,6 +508,25 @@ extern "C" int icar_advect(icar_ctx* ctx, float dt) {
     if (order > 1) {
         ctx->launches += staged_wn_G<float>(g, ctx->W, dz, jaco, rho, ctx->Wn, rho ? ctx->G : nullptr, ctx->stream);
         if (rho) G = ctx->G;
+    }
+    if (ctx->fused) {
+        ScalarSet ss;
+        ss.n = 5;
+        for (int n = 0; n < 5; ++n) {
+            ss.q[n] = (const float*)ctx->vars[kAdvectedSimple[n]];
+            ss.q2[n] = ctx->fq2[n];
+            ss.out[n] = ctx->fout[n];
+        }
+        const int nl = fused_advect_all(g, ss, ctx->U, ctx->V, ctx->W, ctx->Wn, jaco, dz, ctx->coef, ctx->stream);
+        if (nl < 0) return fail(ctx, ICAR_ERR_CUDA, "icar_advect: cannot set up the TMA tensor maps / shared memory of the fused MPDATA kernel");
+        ctx->launches += nl;
+        CU(cudaGetLastError());
+        for (int n = 0; n < 5; ++n) {      // the output buffer becomes the field, the old field the next output
+            float* old_field = (float*)ctx->vars[kAdvectedSimple[n]];
+            ctx->vars[kAdvectedSimple[n]] = ctx->fout[n];
+            ctx->fout[n] = old_field;
+        }
+        return ICAR_OK;
     }
     // adv_mpdata.f90:512-522: every scalar with vars_to_advect > 0 (mp_simple.f90:116-118)
     for (int s = 0; s < 5; ++s) {
@@ -484,24 +562,45 @@ extern "C" int icar_mp(icar_ctx* ctx, float dt_in, int halo, int subset) {
         if (!has_halo) ctx->last_model_time = ctx->model_time;
         int kte = gr.kte;
         if (ctx->opt.top_mp_level > 0) kte = std::min(kte, ctx->opt.top_mp_level);   // :723-725
-        // process_subdomain zeroes its local precipitation arrays on entry (:411-413); the tiles
-        // of one mp() call are disjoint, so one clear + one REAL*8 accumulation serve them all
-        CU(cudaMemsetAsync(ctx->rain2d, 0, (size_t)ctx->ld2 * ctx->g.ny * sizeof(float), ctx->stream));
-        CU(cudaMemsetAsync(ctx->snow2d, 0, (size_t)ctx->ld2 * ctx->g.ny * sizeof(float), ctx->stream));
-        if (has_subset)                                                                  // :728-738
-            if ((rc = run_mp_tile(ctx, mp_dt, gr.its + subset, gr.ite - subset, gr.jts + subset,
-                                  gr.jte - subset, gr.kts, kte))) return rc;
-        if (has_halo) {                                                                  // process_halo :609-658
-            if ((rc = run_mp_tile(ctx, mp_dt, gr.its, gr.its + halo - 1, gr.jts, gr.jte, gr.kts, kte))) return rc;
-            if ((rc = run_mp_tile(ctx, mp_dt, gr.ite - halo + 1, gr.ite, gr.jts, gr.jte, gr.kts, kte))) return rc;
-            if ((rc = run_mp_tile(ctx, mp_dt, gr.its + halo, gr.ite - halo, gr.jts, gr.jts + halo - 1, gr.kts, kte))) return rc;
-            if ((rc = run_mp_tile(ctx, mp_dt, gr.its + halo, gr.ite - halo, gr.jte - halo + 1, gr.jte, gr.kts, kte))) return rc;
+        // process_subdomain zeroes its local precipitation arrays on entry (:411-413) and adds them to
+        // the REAL*8 accumulators on exit (:587-595); tiles of one call are disjoint, so one clear
+        // and one accumulation per group of tiles is identical.
+        const size_t b2 = (size_t)ctx->ld2 * ctx->g.ny * sizeof(float);
+        if (has_halo || (!has_halo && !has_subset))
+            if ((rc = join_aux(ctx))) return rc;          // strips of an earlier call overlap these cells
+        if (has_subset || (!has_halo && !has_subset)) {
+            CU(cudaMemsetAsync(ctx->rain2d, 0, b2, ctx->stream));
+            CU(cudaMemsetAsync(ctx->snow2d, 0, b2, ctx->stream));
+            if (has_subset)                                                              // :728-738
+                rc = run_mp_tile(ctx, mp_dt, gr.its + subset, gr.ite - subset, gr.jts + subset, gr.jte - subset,
+                                 gr.kts, kte, ctx->stream, ctx->rain2d, ctx->snow2d);
+            else                                                                         // :754-766
+                rc = run_mp_tile(ctx, mp_dt, gr.its, gr.ite, gr.jts, gr.jte, gr.kts, kte, ctx->stream,
+                                 ctx->rain2d, ctx->snow2d);
+            if (rc) return rc;
+            ctx->launches += accumulate_precip_launch(ctx->g.nx, ctx->g.ny, ctx->ld2, ctx->rain2d, ctx->snow2d,
+                                                      (double*)ctx->vars[ICAR_VAR_PRECIPITATION],
+                                                      (double*)ctx->vars[ICAR_VAR_SNOWFALL], ctx->stream);
         }
-        if (!has_halo && !has_subset)                                                    // :754-766
-            if ((rc = run_mp_tile(ctx, mp_dt, gr.its, gr.ite, gr.jts, gr.jte, gr.kts, kte))) return rc;
-        ctx->launches += accumulate_precip_launch(ctx->g.nx, ctx->g.ny, ctx->ld2, ctx->rain2d, ctx->snow2d,
-                                                  (double*)ctx->vars[ICAR_VAR_PRECIPITATION],
-                                                  (double*)ctx->vars[ICAR_VAR_SNOWFALL], ctx->stream);
+        if (has_halo) {                                                                  // process_halo :609-658
+            // The four strips are thin (latency-bound) launches: they run concurrently on four aux
+            // streams and are joined lazily, so the interior tile of mp(subset) overlaps them the
+            // way time_step.f90:512-526 overlaps the halo exchange.
+            CU(cudaMemsetAsync(ctx->rain2d_halo, 0, b2, ctx->stream));
+            CU(cudaMemsetAsync(ctx->snow2d_halo, 0, b2, ctx->stream));
+            CU(cudaEventRecord(ctx->ev_fork, ctx->stream));
+            const int t[4][4] = {{gr.its, gr.its + halo - 1, gr.jts, gr.jte},
+                                 {gr.ite - halo + 1, gr.ite, gr.jts, gr.jte},
+                                 {gr.its + halo, gr.ite - halo, gr.jts, gr.jts + halo - 1},
+                                 {gr.its + halo, gr.ite - halo, gr.jte - halo + 1, gr.jte}};
+            for (int a = 0; a < 4; ++a) {
+                CU(cudaStreamWaitEvent(ctx->aux[a], ctx->ev_fork, 0));
+                if ((rc = run_mp_tile(ctx, mp_dt, t[a][0], t[a][1], t[a][2], t[a][3], gr.kts, kte, ctx->aux[a],
+                                      ctx->rain2d_halo, ctx->snow2d_halo))) return rc;
+                CU(cudaEventRecord(ctx->ev_aux[a], ctx->aux[a]));
+            }
+            ctx->aux_pending = true;
+        }
         CU(cudaGetLastError());
     }
     return ICAR_OK;
@@ -543,6 +642,7 @@ extern "C" int icar_halo_send(icar_ctx* ctx) {
     if (ctx->nimages == 1) return ICAR_OK;
     if (!ctx->comm) return fail(ctx, ICAR_ERR_COMM, "icar_halo_send: icar_comm_init was not called");
     CU(cudaSetDevice(ctx->device));
+    { int jr = join_aux(ctx); if (jr) return jr; }
     const int h = ctx->grid.halo_size, nx = ctx->g.nx;
     const bool west = ctx->image > 1, east = ctx->image < ctx->nimages;
     float* fields[5];

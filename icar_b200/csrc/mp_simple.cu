@@ -1,13 +1,25 @@
-// "Simple" (SB04) cloud microphysics, one thread per (i,j) column; a warp covers 32
-// consecutive i so every level access is one coalesced 128-byte line per field.
+// "Simple" (SB04) cloud microphysics on sm_100a.
 //
 // Reference: src/physics/mp_simple.f90 -- mp_simple_driver :595-646, mp_simple :481-566,
 // mp_conversions :381-420, cloud_conversion :198-280, cloud2hydrometeor :295-315,
 // phase_change :333-362, sediment :437-459, sat_mr :146-182.
 //
-// The column is updated in place in global memory (each thread owns its column; lines
-// stay in L1/L2 between the sweeps).  Temperature lives in the `th` array between the
-// first sweep (T = th*pii, :633) and the last (th = T/pii, :639).
+// Parallelisation.  The reference walks one column at a time; but inside a column every
+// level is independent in mp_conversions and in the re-evaporation loops, and one
+// sedimentation sub-step is level-parallel too once written per level:
+//     q_new(k) = (q_old(k) - out(k)) + in(k),   in(k) = fall*q_old(k+1)*rho(k+1)/(rho(k)*dz(k))
+// (same operation order as the Fortran's two sequential loops, :449-457).  So a CTA owns a
+// tile of 32 columns x all levels with ONE THREAD PER CELL (CPT cells per thread when
+// nz > 32): a warp is 32 consecutive i at one level, so every global access is one
+// coalesced 128-byte line, the whole column state lives in registers from the first load
+// to the last store (each field is read once and written once: the 14 field-passes of
+// SURVEY.md section 8d), and only q_old(k+1) and three column reductions go through shared
+// memory.
+//
+// Numerics: `exp` of the Fortran is glibc's expf on the reference platform; exp_glibc()
+// below evaluates the same algorithm (same table, same double-precision polynomial), so
+// together with IEEE division and -fmad=false the kernel reproduces the CPU oracle bit for
+// bit rather than to a tolerance.
 #include "common.cuh"
 #include "mp_simple.cuh"
 
@@ -24,20 +36,60 @@ constexpr float freezing_threshold = 273.15f;
 constexpr float snow_fall_rate = 1.5f;
 constexpr float rain_fall_rate = 10.0f;
 constexpr float cloud_init = 0.0001f;        // snow_cloud_init == rain_cloud_init
+constexpr int TX = 32;                       // columns per CTA (one warp = one level row)
 
-__device__ __forceinline__ float sat_mr(float t, float p) {            // :146-182
+// 2^(i/32) table of glibc's expf (sysdeps/ieee754/flt-32/e_exp2f_data.c, EXP2F_TABLE_BITS=5):
+// tab[i] = asuint64(2^(i/32)) - (i << 47).  Verified against powl() and, end to end, against
+// glibc 2.39 expf on 3.2e8 arguments.
+__device__ const unsigned long long kExp2fTab[32] = {
+    0x3ff0000000000000ULL, 0x3fefd9b0d3158574ULL, 0x3fefb5586cf9890fULL, 0x3fef9301d0125b51ULL,
+    0x3fef72b83c7d517bULL, 0x3fef54873168b9aaULL, 0x3fef387a6e756238ULL, 0x3fef1e9df51fdee1ULL,
+    0x3fef06fe0a31b715ULL, 0x3feef1a7373aa9cbULL, 0x3feedea64c123422ULL, 0x3feece086061892dULL,
+    0x3feebfdad5362a27ULL, 0x3feeb42b569d4f82ULL, 0x3feeab07dd485429ULL, 0x3feea47eb03a5585ULL,
+    0x3feea09e667f3bcdULL, 0x3fee9f75e8ec5f74ULL, 0x3feea11473eb0187ULL, 0x3feea589994cce13ULL,
+    0x3feeace5422aa0dbULL, 0x3feeb737b0cdc5e5ULL, 0x3feec49182a3f090ULL, 0x3feed503b23e255dULL,
+    0x3feee89f995ad3adULL, 0x3feeff76f2fb5e47ULL, 0x3fef199bdd85529cULL, 0x3fef3720dcef9069ULL,
+    0x3fef5818dcfba487ULL, 0x3fef7c97337b9b5fULL, 0x3fefa4afa2a490daULL, 0x3fefd0765b6e4540ULL};
+
+// glibc expf (sysdeps/ieee754/flt-32/e_expf.c): x*N/ln2 = k + r, 2^(k/N) from the table,
+// 2^(r/N) from a cubic, all in double, rounded to float once.
+__device__ __forceinline__ float exp_glibc(float x, const unsigned long long* __restrict__ tab) {
+    if (!(fabsf(x) < 87.0f)) return expf(x);           // overflow / underflow tails: not on this path
+    const double N = 32.0;
+    const double InvLn2N = 0x1.71547652b82fep+0 * N, SHIFT = 0x1.8p+52;
+    const double C0 = 0x1.c6af84b912394p-5 / N / N / N, C1 = 0x1.ebfce50fac4f3p-3 / N / N,
+                 C2 = 0x1.62e42ff0c52d6p-1 / N;
+    double z = InvLn2N * (double)x;
+    double kd = z + SHIFT;
+    unsigned long long ki = (unsigned long long)__double_as_longlong(kd);
+    kd -= SHIFT;
+    double r = z - kd;
+    unsigned long long t = tab[ki & 31ULL] + (ki << 47);
+    double s = __longlong_as_double((long long)t);
+    double p = C0 * r + C1;
+    double r2 = r * r;
+    double y = C2 * r + 1.0;
+    y = p * r2 + y;
+    return (float)(y * s);
+}
+
+struct Ctx {
+    const unsigned long long* tab;
+    unsigned long long* diag;
+    float c2r, c2s;
+};
+
+__device__ __forceinline__ float sat_mr(float t, float p, const Ctx& cx) {            // :146-182
     float a, b;
     if (t < freezing_threshold) { a = 21.8745584f; b = 7.66f; }
     else                        { a = 17.2693882f; b = 35.86f; }
-    float e_s = 610.78f * expf(a * (t - 273.16f) / (t - b));
+    float e_s = 610.78f * exp_glibc(a * (t - 273.16f) / (t - b), cx.tab);
     if ((p - e_s) <= 0.f) e_s = p * 0.99999f;
     return 0.6219907f * e_s / (p - e_s);
 }
 
-struct Diag { unsigned long long* d; };
-
 __device__ __forceinline__ void phase_change(float& t, float& q1, float qmax, float& q2,
-                                             float Lheat, float change_rate, Diag dg) {  // :333-362
+                                             float Lheat, float change_rate, const Ctx& cx) {  // :333-362
     float mass2temp = Lheat / heat_capacity;
     float delta = (qmax - q2) * change_rate;
     if (delta > q1) delta = q1;
@@ -45,7 +97,7 @@ __device__ __forceinline__ void phase_change(float& t, float& q1, float qmax, fl
     q1 = q1 - delta;
     if (q1 < 0.f) {
         if ((q1 + SMALL_VALUE) < 0.f) q1 = 0.f;
-        else atomicAdd(dg.d + 2, 1ULL);          // reference: print + stop
+        else atomicAdd(cx.diag + 2, 1ULL);         // reference: print + stop
     }
     q2 = q2 + delta;
     t = t + delta * mass2temp;
@@ -59,13 +111,12 @@ __device__ __forceinline__ void cloud2hydrometeor(float& qc, float& q, float con
 }
 
 __device__ __forceinline__ void mp_conversions(float p, float& t, float& qv, float& qc, float& qr,
-                                               float& qs, float c2r, float c2s, Diag dg) {  // :381-420
+                                               float& qs, const Ctx& cx) {                  // :381-420
     const float L_melt = -1.f * LH_liquid;
     const float L_evap = -1.f * (LH_vapor + (373.15f - t) * dLHvdt);
     const float L_subl = L_melt + L_evap;
-    // ---- cloud_conversion :198-280
     float qvsat = 0.f;
-    {
+    {   // cloud_conversion :198-280
         const float maxerr = 1e-4f;
         int iteration = 0;
         float lastqv = qv + maxerr * 2.f;
@@ -74,7 +125,7 @@ __device__ __forceinline__ void mp_conversions(float p, float& t, float& qv, flo
         while ((fabsf(lastqv - qv) > maxerr) && (iteration < 15)) {
             iteration = iteration + 1;
             lastqv = qv;
-            qvsat = sat_mr(t, p);
+            qvsat = sat_mr(t, p, cx);
             if (qv > qvsat) {
                 float excess = (qv - qvsat) * 0.5f;
                 t = t + (excess * vapor2temp);
@@ -94,138 +145,176 @@ __device__ __forceinline__ void mp_conversions(float p, float& t, float& qv, flo
             }
         }
         if (iteration == 15) {
-            qv = sat_mr(pre_t, p);
+            qv = sat_mr(pre_t, p, cx);
             t = pre_t;
             qc = pre_qc;
-            atomicAdd(dg.d + 0, 1ULL);
+            atomicAdd(cx.diag + 0, 1ULL);
         }
         qc = fmaxf(qc, 0.f);
-        if ((t > 350.f) || (qc > 0.01f) || (qvsat > 1.f)) atomicAdd(dg.d + 1, 1ULL);
+        if ((t > 350.f) || (qc > 0.01f) || (qvsat > 1.f)) atomicAdd(cx.diag + 1, 1ULL);
     }
     if ((qc + qr + qs) > SMALL_VALUE) {
         if (qc > SMALL_VALUE) {
             if (t > freezing_threshold) {
-                cloud2hydrometeor(qc, qr, c2r);
-                if (qs > SMALL_VALUE) phase_change(t, qs, 100.f, qr, L_melt, c2r, dg);
+                cloud2hydrometeor(qc, qr, cx.c2r);
+                if (qs > SMALL_VALUE) phase_change(t, qs, 100.f, qr, L_melt, cx.c2r, cx);
             } else {
-                cloud2hydrometeor(qc, qs, c2s);
+                cloud2hydrometeor(qc, qs, cx.c2s);
             }
         }
         if (qv < qvsat) {
-            if (qr > SMALL_VALUE) phase_change(t, qr, qvsat, qv, L_evap, c2r / 2.f, dg);
-            if (qs > SMALL_VALUE) phase_change(t, qs, qvsat, qv, L_subl, c2s / 2.f, dg);
+            if (qr > SMALL_VALUE) phase_change(t, qr, qvsat, qv, L_evap, cx.c2r / 2.f, cx);
+            if (qs > SMALL_VALUE) phase_change(t, qs, qvsat, qv, L_subl, cx.c2s / 2.f, cx);
         }
     }
 }
 
-// One sedimentation + re-evaporation sub-step sweep for one species (:437-459, :513-529 / :540-562).
-// q: the falling species, T lives in `th`.  Returns the mass that left the bottom level.
-template <bool SNOW>
-__device__ __forceinline__ float sediment_sweep(float* __restrict__ q, float* __restrict__ th,
-                                                float* __restrict__ qv,
-                                                const float* __restrict__ p,
-                                                const float* __restrict__ rho,
-                                                const float* __restrict__ dz, size_t base,
-                                                size_t ld, int nz, int kts, int kte, float fall,
-                                                float rate, Diag dg) {
-    const float L_melt = -1.f * LH_liquid;
+// Shared memory: two planes [nzp][TX] for q_old / rho (+1 padding level that reads as 0),
+// three column-reduction rows.
+template <int CPT>
+__global__ void __launch_bounds__(TX * 32)
+k_mp_simple(Geom g, const float* __restrict__ gp, float* __restrict__ gth,
+            const float* __restrict__ gpii, const float* __restrict__ grho,
+            float* __restrict__ gqv, float* __restrict__ gqc, float* __restrict__ gqr,
+            float* __restrict__ gqs, float* __restrict__ rain, float* __restrict__ snow, int ld2,
+            float dt, const float* __restrict__ gdz, int its, int ite, int jts, int jte, int kts,
+            int kte, float c2r, float c2s, unsigned long long* diag) {
+    extern __shared__ float sm[];
+    const int nz = g.nz;
+    const int nzt = blockDim.y;                 // z-threads; thread owns levels tz + c*nzt
+    const int tx = threadIdx.x, tz = threadIdx.y;
+    float* s_q = sm;                            // [(nz+1)][TX]
+    float* s_rho = s_q + (nz + 1) * TX;         // [(nz+1)][TX]
+    float* s_red = s_rho + (nz + 1) * TX;       // [3][TX]: max qr, max qs, max dt/dz
+    const int i = its + blockIdx.x * TX + tx;
+    const int j = jts + blockIdx.y;
+    const bool col_ok = (i <= ite);
+    const Ctx cx{kExp2fTab, diag, c2r, c2s};
     const int top = min(kte, nz - 2);
-    const int last = max(kte, top + 1);
-    size_t c = base + (size_t)kts * ld;
-    float qk = q[c], rk = rho[c], dk = dz[c];
-    const float sed = fall * qk * rk;
-    float below = 0.f;                     // flux(k-1) = v*q_old(k)*rho(k)
-    for (int k = kts; k <= last; ++k, c += ld) {
-        float nq = qk;
-        const bool moved = (k <= top + 1);
-        if (k == kts) nq = qk - (sed / dk / rk);
-        else if (moved) nq = qk - below / (rk * dk);
-        float qn = 0.f, rn = 0.f, dn = 0.f;
-        if (k + 1 < nz) { qn = q[c + ld]; rn = rho[c + ld]; dn = dz[c + ld]; }
-        if (k <= top) {
-            float flux = fall * qn * rn;
-            nq = nq + flux / (rk * dk);
-            below = flux;
+
+    float T[CPT], p[CPT], rho[CPT], dz[CPT], pii[CPT], qv[CPT], qc[CPT], qr[CPT], qs[CPT];
+    bool live[CPT];
+#pragma unroll
+    for (int c = 0; c < CPT; ++c) {
+        const int k = tz + c * nzt;
+        live[c] = col_ok && (k < nz);
+        T[c] = p[c] = rho[c] = pii[c] = 1.f; dz[c] = 1.f; qv[c] = qc[c] = qr[c] = qs[c] = 0.f;
+        if (live[c]) {
+            const size_t a = g.at(i, k, j);
+            p[c] = gp[a]; pii[c] = gpii[a]; rho[c] = grho[a]; dz[c] = gdz[a];
+            qv[c] = gqv[a]; qc[c] = gqc[a]; qr[c] = gqr[a]; qs[c] = gqs[a];
+            T[c] = gth[a] * pii[c];                                       // :633 (whole column)
+            if (k >= kts && k <= kte) mp_conversions(p[c], T[c], qv[c], qc[c], qr[c], qs[c], cx);  // :500-502
         }
-        if (k <= kte) {                    // re-evaporation / sublimation
-            float t = th[c], pk = p[c], v = qv[c];
-            float L_evap = -1.f * (LH_vapor + (373.15f - t) * dLHvdt);
-            float qvsat = sat_mr(t, pk);
-            if (v < qvsat && nq > SMALL_VALUE) {
-                phase_change(t, nq, qvsat, v, SNOW ? (L_melt + L_evap) : L_evap, rate, dg);
-                th[c] = t;
-                qv[c] = v;
+    }
+    // ---- column reductions: maxval(qr), maxval(qs), maxval(dt/dz) over the WHOLE column (:505,:511)
+    if (tz == 0) { s_q[nz * TX + tx] = 0.f; s_rho[nz * TX + tx] = 0.f; }
+#pragma unroll
+    for (int c = 0; c < CPT; ++c) {
+        const int k = tz + c * nzt;
+        if (k < nz) { s_q[k * TX + tx] = live[c] ? qr[c] : -3.4e38f; s_rho[k * TX + tx] = live[c] ? qs[c] : -3.4e38f; }
+    }
+    __syncthreads();
+    if (tz < 2) {
+        const float* src = (tz == 0) ? s_q : s_rho;
+        float m = -3.4e38f;
+        for (int k = 0; k < nz; ++k) m = fmaxf(m, src[k * TX + tx]);
+        s_red[tz * TX + tx] = m;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int c = 0; c < CPT; ++c) {
+        const int k = tz + c * nzt;
+        if (k < nz) { s_q[k * TX + tx] = live[c] ? dt / dz[c] : -3.4e38f; s_rho[k * TX + tx] = rho[c]; }
+    }
+    __syncthreads();
+    if (tz == 0) {
+        float m = -3.4e38f;
+        for (int k = 0; k < nz; ++k) m = fmaxf(m, s_q[k * TX + tx]);
+        s_red[2 * TX + tx] = m;
+    }
+    __syncthreads();
+    const float max_qr = s_red[tx], max_qs = s_red[TX + tx], max_dtdz = s_red[2 * TX + tx];
+    // rounding is monotone, so maxval(dt/dz*v) == maxval(dt/dz)*v exactly
+    int n_r = 0, n_s = 0;
+    float fall_r = 0.f, fall_s = 0.f, rate_r = 0.f, rate_s = 0.f;
+    if (col_ok && max_qr > SMALL_VALUE) {                                  // :505-513
+        float cfl = ceilf(max_dtdz * rain_fall_rate);
+        fall_r = dt * rain_fall_rate / cfl;
+        n_r = (int)lroundf(cfl);
+        rate_r = c2r / (float)(2 * n_r);
+    }
+    if (col_ok && max_qs > SMALL_VALUE) {                                  // :533-541
+        float cfl = ceilf(max_dtdz * snow_fall_rate);
+        fall_s = dt * snow_fall_rate / cfl;
+        n_s = (int)lroundf(cfl);
+        rate_s = c2s / (float)(2 * n_s);
+    }
+    const int nmax_r = __reduce_max_sync(0xffffffffu, n_r);               // same 32 columns in every warp
+    const int nmax_s = __reduce_max_sync(0xffffffffu, n_s);
+    const float L_melt = -1.f * LH_liquid;
+    // accumulated in the one thread of the column that owns level kts, in the reference's order
+    const size_t c2 = (size_t)(col_ok ? i : its) + (size_t)ld2 * (size_t)j;
+    bool owner = false;
+#pragma unroll
+    for (int c = 0; c < CPT; ++c) owner = owner || (live[c] && (tz + c * nzt) == kts);
+    float rain_acc = owner ? rain[c2] : 0.f, snow_acc = owner ? snow[c2] : 0.f;
+
+    // ---- sedimentation + re-evaporation sub-steps, rain then snow (:507-564, sediment :437-459)
+#pragma unroll
+    for (int species = 0; species < 2; ++species) {
+        const int nmax = species ? nmax_s : nmax_r;
+        const int n = species ? n_s : n_r;
+        const float fall = species ? fall_s : fall_r;
+        const float rate = species ? rate_s : rate_r;
+        for (int step = 0; step < nmax; ++step) {
+            __syncthreads();                    // previous readers of s_q are done
+#pragma unroll
+            for (int c = 0; c < CPT; ++c) {
+                const int k = tz + c * nzt;
+                if (k < nz) s_q[k * TX + tx] = species ? qs[c] : qr[c];
+            }
+            __syncthreads();
+            if (step < n) {
+#pragma unroll
+                for (int c = 0; c < CPT; ++c) {
+                    const int k = tz + c * nzt;
+                    if (!live[c] || k < kts || k > max(kte, top + 1)) continue;
+                    float& q = species ? qs[c] : qr[c];
+                    float nq = q;
+                    if (k == kts) {
+                        const float sed = fall * q * rho[c];               // :446
+                        nq = q - (sed / dz[c] / rho[c]);                   // :448
+                        if (species) { snow_acc = snow_acc + sed; rain_acc = rain_acc + sed; }   // :544-545
+                        else rain_acc = rain_acc + sed;                                           // :516
+                    } else if (k <= top + 1) {
+                        nq = q - (fall * q * rho[c]) / (rho[c] * dz[c]);   // flux(k-1), :451,:455
+                    }
+                    if (k <= top) {
+                        const float flux = fall * s_q[(k + 1) * TX + tx] * s_rho[(k + 1) * TX + tx];
+                        nq = nq + flux / (rho[c] * dz[c]);                 // :454
+                    }
+                    if (k <= kte && nq > SMALL_VALUE) {                    // :519-528 / :549-561
+                        const float L_evap = -1.f * (LH_vapor + (373.15f - T[c]) * dLHvdt);
+                        const float qvsat = sat_mr(T[c], p[c], cx);
+                        if (qv[c] < qvsat)
+                            phase_change(T[c], nq, qvsat, qv[c], species ? (L_melt + L_evap) : L_evap, rate, cx);
+                    }
+                    q = nq;
+                }
             }
         }
-        if (moved || k <= kte) q[c] = nq;
-        qk = qn; rk = rn; dk = dn;
     }
-    return sed;
-}
-
-__global__ void __launch_bounds__(128)
-k_mp_simple(Geom g, const float* __restrict__ p, float* __restrict__ th,
-            const float* __restrict__ pii, const float* __restrict__ rho, float* __restrict__ qv,
-            float* __restrict__ qc, float* __restrict__ qr, float* __restrict__ qs,
-            float* __restrict__ rain, float* __restrict__ snow, int ld2, float dt,
-            const float* __restrict__ dz, int its, int ite, int jts, int jte, int kts, int kte,
-            float c2r, float c2s, unsigned long long* diag) {
-    const int i = its + blockIdx.x * blockDim.x + threadIdx.x;
-    const int j = jts + blockIdx.y;
-    if (i > ite || j > jte) return;
-    const Diag dg{diag};
-    const size_t ld = g.ld;
-    const size_t base = g.at(i, 0, j);
-    const int nz = g.nz;
-
-    // sweep 1: T = th*pii (whole column, :633); conversions on kts..kte (:500-502);
-    // maxval(qr), maxval(qs) and maxval(dt/dz*fall_rate) over the whole column (:505,:511)
-    float max_qr = -3.4e38f, max_qs = -3.4e38f, m_r = -3.4e38f, m_s = -3.4e38f;
-    size_t c = base;
-    for (int k = 0; k < nz; ++k, c += ld) {
-        float t = th[c] * pii[c];
-        float r = qr[c], s = qs[c];
-        if (k >= kts && k <= kte) {
-            float v = qv[c], cw = qc[c];
-            mp_conversions(p[c], t, v, cw, r, s, c2r, c2s, dg);
-            qv[c] = v; qc[c] = cw; qr[c] = r; qs[c] = s;
-        }
-        th[c] = t;
-        float dtdz = dt / dz[c];
-        max_qr = fmaxf(max_qr, r);
-        max_qs = fmaxf(max_qs, s);
-        m_r = fmaxf(m_r, dtdz * rain_fall_rate);
-        m_s = fmaxf(m_s, dtdz * snow_fall_rate);
+    // ---- write back: th = T/pii for the whole column (:639)
+#pragma unroll
+    for (int c = 0; c < CPT; ++c) {
+        const int k = tz + c * nzt;
+        if (!live[c]) continue;
+        const size_t a = g.at(i, k, j);
+        gth[a] = T[c] / pii[c];
+        gqv[a] = qv[c]; gqc[a] = qc[c]; gqr[a] = qr[c]; gqs[a] = qs[c];
     }
-    const size_t c2 = (size_t)i + (size_t)ld2 * (size_t)j;
-    float rain_acc = rain[c2];
-    if (max_qr > SMALL_VALUE) {                                        // :505-530
-        float cfl = ceilf(m_r);
-        float fall = dt * rain_fall_rate / cfl;
-        int n = (int)lroundf(cfl);
-        float rate = c2r / (float)(2 * n);
-        for (int s = 0; s < n; ++s)
-            rain_acc = rain_acc + sediment_sweep<false>(qr, th, qv, p, rho, dz, base, ld, nz, kts,
-                                                        kte, fall, rate, dg);
-    }
-    if (max_qs > SMALL_VALUE) {                                        // :533-564
-        float snow_acc = snow[c2];
-        float cfl = ceilf(m_s);
-        float fall = dt * snow_fall_rate / cfl;
-        int n = (int)lroundf(cfl);
-        float rate = c2s / (float)(2 * n);
-        for (int s = 0; s < n; ++s) {
-            float f = sediment_sweep<true>(qs, th, qv, p, rho, dz, base, ld, nz, kts, kte, fall,
-                                           rate, dg);
-            snow_acc = snow_acc + f;
-            rain_acc = rain_acc + f;
-        }
-        snow[c2] = snow_acc;
-    }
-    rain[c2] = rain_acc;
-    // last sweep: th = T/pii (whole column, :639)
-    c = base;
-    for (int k = 0; k < nz; ++k, c += ld) th[c] = th[c] / pii[c];
+    if (owner && (n_r > 0 || n_s > 0)) { rain[c2] = rain_acc; snow[c2] = snow_acc; }
 }
 
 // domain%accumulated_precipitation (REAL*8) += precipitation (mp_driver.f90:587-595)
@@ -246,10 +335,22 @@ int mp_simple_launch(const Geom& g, const float* p, float* th, const float* pii,
                      float dt, const float* dz, int its, int ite, int jts, int jte, int kts,
                      int kte, float c2r, float c2s, unsigned long long* diag, cudaStream_t st) {
     if (ite < its || jte < jts) return 0;
-    dim3 block(128);
-    dim3 grid((ite - its + 1 + 127) / 128, jte - jts + 1);
-    k_mp_simple<<<grid, block, 0, st>>>(g, p, th, pii, rho, qv, qc, qr, qs, rain, snow, ld2, dt,
-                                        dz, its, ite, jts, jte, kts, kte, c2r, c2s, diag);
+    const int cpt = (g.nz + 31) / 32;                       // cells per thread
+    if (cpt > 4) return -1;                                 // nz > 128 is not built
+    const int nzt = (g.nz + cpt - 1) / cpt;
+    dim3 block(TX, nzt);
+    dim3 grid((ite - its + 1 + TX - 1) / TX, jte - jts + 1);
+    size_t smem = (size_t)(2 * (g.nz + 1) + 3) * TX * sizeof(float);
+#define LAUNCH(C)                                                                                 \
+    k_mp_simple<C><<<grid, block, smem, st>>>(g, p, th, pii, rho, qv, qc, qr, qs, rain, snow, ld2, \
+                                              dt, dz, its, ite, jts, jte, kts, kte, c2r, c2s, diag)
+    switch (cpt) {
+        case 1: LAUNCH(1); break;
+        case 2: LAUNCH(2); break;
+        case 3: LAUNCH(3); break;
+        default: LAUNCH(4); break;
+    }
+#undef LAUNCH
     return 1;
 }
 

@@ -3,7 +3,34 @@
 #pragma once
 #include "common.cuh"
 
+#define ICAR_MAX_SCALARS 12
+
 namespace icar {
+
+// the advected scalars of one advect() call: q = field before pass 1, q2 = scratch for the field
+// after pass 1, out = buffer that receives the advected field (all distinct)
+struct ScalarSet {
+    int n;
+    const float* q[ICAR_MAX_SCALARS];
+    float* q2[ICAR_MAX_SCALARS];
+    float* out[ICAR_MAX_SCALARS];
+};
+
+// per-face scalar-independent coefficients of the fused corrector (mpdata_fused.cu)
+struct FusedCoef {
+    float *ax, *bx, *cx, *ay, *by, *cy, *az, *bz, *cz, *rj, *rjz;
+};
+
+// order 2 + FCT, rho == 1, fp32: coefficients, pass 1 for all scalars, fused corrector.
+// U,V,W,Wn from staged_wind_normalise / staged_wn_G.  nz <= 64.  Returns < 0 when the TMA
+// tensor maps cannot be built (driver without cuTensorMapEncodeTiled).
+int fused_advect_all(const Geom& g, const ScalarSet& s, const float* U, const float* V, const float* W,
+                     const float* Wn, const float* jaco, const float* dz, const FusedCoef& co,
+                     cudaStream_t st);
+
+// pass 1 (adv_mpdata.f90:44-105) of every scalar in one launch; also copies the boundary ring to out
+int staged_upwind_all(const Geom& g, const ScalarSet& s, const float* U, const float* V, const float* W,
+                      const float* dz, const float* jaco, cudaStream_t st);
 
 template <class R>
 int staged_wind_normalise(const Geom& g, const R* u, const R* v, const R* w, const R* ju,

@@ -1,0 +1,560 @@
+// MPDATA order 2 + FCT, the production fp32 path: three kernels per advect() call
+//
+//   k_face_coefficients  once per call: every scalar-independent factor of the pseudo-velocity
+//                        formulas (adv_mpdata.f90:129-251, :383-385), one value per face
+//   k_upwind_all         (mpdata_staged.cu) donor-cell pass 1 (adv_mpdata.f90:44-105) for ALL
+//                        advected scalars in one launch, bit-exact
+//   k_corrector_fused    per scalar: pseudo-velocities + flux limiter (adv_mpdata.f90:257-354,
+//                        adv_mpdata_FCT_core.f90) + corrector donor-cell pass (:389) in ONE
+//                        kernel, written as a 2.5-D streaming stencil:
+//
+//   * a CTA owns a tile of 32 columns (28 outputs + 2 halo each side) x all levels and marches
+//     along y; blockIdx.x = scalar + nscalars * x-tile, so the CTAs of the 5 scalars of a tile run
+//     side by side and the 11 coefficient planes come from HBM once and from L2 four times;
+//   * every plane a CTA needs (q2, l and 11 coefficient fields: 13 boxes of 32 x nz floats) is
+//     fetched by TMA (cp.async.bulk.tensor.3d, zero fill outside the domain) into a
+//     double-buffered shared-memory stage one iteration ahead, completion on an mbarrier: no
+//     thread ever waits on a global load, and the loads cost no issue slots and no registers;
+//   * everything that couples cells along y lives in the owning thread's registers (sliding
+//     windows), x-neighbours are warp shuffles (a warp is one 32-wide row of the tile),
+//     z-neighbours between threads go through a few shared-memory rows;
+//   * each face's pseudo-velocity, each cell's limiter bounds (beta_in / beta_out) and each limited
+//     flux are computed exactly once (the staged kernels recompute them per consumer).
+//
+// Arithmetic of k_corrector_fused ("fast" mode): the same formulas as the Fortran, but
+//   * the scalar-independent factors are pre-multiplied (k_face_coefficients),
+//   * the transverse ratios use (a-b+c-d)/(a+b+c+d+eps) = (S+ - S-)/(S+ + S- + eps) with S the
+//     face pair-sums, which are shared between terms,
+//   * divisions are MUFU.RCP based (__fdividef, <= 2 ulp) and a*b+c contracts to FMA.
+// These change roundings of the ANTI-DIFFUSIVE CORRECTION only (pass 1 stays bit-exact):
+// differences of order 1e-7 of the field maximum per call; tests/test_gpu_parity.py states the
+// tolerance and also runs the bit-exact staged path (icar_options.exact_arithmetic = 1).
+#include <cuda.h>
+
+#include <cstdlib>
+#include <cstring>
+#include <unordered_map>
+
+#include "common.cuh"
+#include "mpdata.cuh"
+
+namespace icar {
+
+namespace {
+
+constexpr int TW = 32;          // tile width in columns == warp size
+constexpr int XH = 2;           // x halo columns on each side of the 28 output columns
+constexpr int TOUT = TW - 2 * XH;
+constexpr float EPS = 1e-10f;
+constexpr float E15 = 1e-15f;
+constexpr float BIG = 3.0e38f;
+constexpr int NF = 13;          // boxes per stage
+enum { F_Q2, F_L, F_AY, F_BY, F_CY, F_AX, F_BX, F_CX, F_AZ, F_BZ, F_CZ, F_RJ, F_RJZ };
+
+constexpr int FUSED_MAX_SCALARS = 9;   // keeps the kernel parameters under 4 KB (29 maps x 128 B)
+
+struct alignas(64) FusedMaps {
+    CUtensorMap q2[FUSED_MAX_SCALARS];
+    CUtensorMap l[FUSED_MAX_SCALARS];
+    CUtensorMap coef[11];       // ay by cy ax bx cx az bz cz rj rjz  (stage order F_AY..F_RJZ)
+};
+
+struct OutSet {
+    int n;
+    float* out[FUSED_MAX_SCALARS];
+};
+
+__device__ __forceinline__ float fdiv(float a, float b) { return __fdividef(a, b); }
+__device__ __forceinline__ float max3(float a, float b, float c) { return fmaxf(fmaxf(a, b), c); }
+__device__ __forceinline__ float min3(float a, float b, float c) { return fminf(fminf(a, b), c); }
+__device__ __forceinline__ float lane_lo(float v) { return __shfl_up_sync(0xffffffffu, v, 1); }    // column i-1
+__device__ __forceinline__ float lane_hi(float v) { return __shfl_down_sync(0xffffffffu, v, 1); }  // column i+1
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* b, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(b)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* b, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(b)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* b, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(b)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// one 32 x nz x 1 box of a (nx, nz, ny) field -> dense [nz][32] floats in shared memory
+__device__ __forceinline__ void tma_load_box(void* dst, const CUtensorMap* map, uint64_t* bar, int x, int z, int y) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(x), "r"(z), "r"(y)
+        : "memory");
+}
+
+// ---------------------------------------------------------------------------------------------
+// Per-face scalar-independent coefficients.  With A = (r-l)/(r+l+eps) and B, C the two
+// transverse ratios, the scaled pseudo-velocities of adv_mpdata.f90:129-251,383-385 are
+//     u2 = ax*A - bx*B - cx*C        (x-face between i-1 and i, stored at i)
+//     v2 = ay*A - by*B - cy*C        (y-face between j-1 and j, stored at j)
+//     w2 = az*A - bz*B - cz*C        (z-face above k, stored at k; includes the *0.5*dz)
+// Terms the Fortran skips at domain edges get a zero coefficient.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+k_face_coefficients(Geom g, const float* __restrict__ U, const float* __restrict__ V,
+                    const float* __restrict__ Wn, const float* __restrict__ G,
+                    const float* __restrict__ dz, FusedCoef co) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int k = blockIdx.y, j = blockIdx.z;
+    if (i >= g.nx) return;
+    const size_t ps = g.ps();
+    const int ld = g.ld;
+    const size_t c = g.at(i, k, j);
+    const bool iin = (i > 0 && i < g.nx - 1), jin = (j > 0 && j < g.ny - 1), kin = (k > 0 && k < g.nz - 1);
+    const float Gc = G[c];
+    float ax = 0.f, bx = 0.f, cx = 0.f, ay = 0.f, by = 0.f, cy = 0.f, az = 0.f, bz = 0.f, cz = 0.f;
+    if (i >= 1) {
+        const float u = U[c], GG = Gc + G[c - 1];
+        ax = 0.5f * (fabsf(u) * (1.f - fabsf(u) / (0.5f * GG)));
+        if (jin) bx = 0.5f * (0.5f * u * (0.25f * (V[c] + V[c + ps] + V[c - 1] + V[c - 1 + ps]))) / GG;
+        if (kin) cx = 0.5f * (0.5f * u * (0.25f * (Wn[c] + Wn[c - ld] + Wn[c - 1] + Wn[c - 1 - ld]))) / GG;
+    }
+    if (j >= 1) {
+        const float v = V[c], GG = Gc + G[c - ps];
+        ay = 0.5f * (fabsf(v) * (1.f - fabsf(v) / (0.5f * GG)));
+        if (iin) by = 0.5f * (0.5f * v * (0.25f * (U[c + 1] + U[c + 1 - ps] + U[c] + U[c - ps]))) / GG;
+        if (kin) cy = 0.5f * (0.5f * v * (0.25f * (Wn[c] + Wn[c - ld] + Wn[c - ps] + Wn[c - ld - ps]))) / GG;
+    }
+    if (k < g.nz - 1) {
+        const float w = Wn[c], GG = G[c + ld] + Gc, hdz = 0.5f * dz[c];
+        az = hdz * (fabsf(w) * (1.f - fabsf(w) / (0.5f * GG)));
+        if (iin) bz = hdz * (0.5f * w * (0.25f * (U[c + 1] + U[c + 1 + ld] + U[c] + U[c + ld]))) / GG;
+        if (jin) cz = hdz * (0.5f * w * (0.25f * (V[c] + V[c + ld] + V[c + ps] + V[c + ld + ps]))) / GG;
+    }
+    co.ax[c] = ax; co.bx[c] = bx; co.cx[c] = cx;
+    co.ay[c] = ay; co.by[c] = by; co.cy[c] = cy;
+    co.az[c] = az; co.bz[c] = bz; co.cz[c] = cz;
+    co.rj[c] = 1.f / Gc;                 // rho == 1 on this path (advect_density = .false.): G == jaco
+    co.rjz[c] = 1.f / (dz[c] * Gc);
+}
+
+// ---------------------------------------------------------------------------------------------
+// The fused corrector.  blockDim = (32, NZT); thread (tx, tz) owns cells (i, CPT*tz + c), c < CPT.
+// ---------------------------------------------------------------------------------------------
+template <int CPT, int MAXT>
+__global__ void __launch_bounds__(MAXT)
+k_corrector_fused(const Geom g, const OutSet outs, const __grid_constant__ FusedMaps maps, const int chunk) {
+    extern __shared__ __align__(128) unsigned char smraw[];
+    const int tx = threadIdx.x, tz = threadIdx.y, nzt = blockDim.y;
+    const int scalar = blockIdx.x % outs.n, xt = blockIdx.x / outs.n;
+    float* __restrict__ gout = outs.out[scalar];
+    const int nx = g.nx, nz = g.nz, ny = g.ny;
+    // TMA needs the box origin 16-byte aligned in the innermost dimension (scripts/probe/tma_probe.cu:
+    // x0 = -1 traps, x0 = -4 / 40 work), so tiles start at a multiple of 4 columns: 28*xt - 4
+    const int x0 = xt * TOUT - 4;                     // first column of the tile (may be negative)
+    const int i = x0 + tx;                            // output columns are tx in [XH, TW-XH)
+    const bool col = (i >= 0 && i < nx);
+    const bool ilast = (i == nx - 1);
+    const float xedge = (i == 0 || ilast) ? 0.f : 1.f;           // fin = fout = 0 at the x line ends
+    const bool has_l = (i != 0), has_r = !ilast;                  // x neighbour exists
+    const int ja = 1 + blockIdx.y * chunk;            // first output plane of this chunk
+    const int jb = min(ja + chunk, ny - 1);           // one past the last output plane
+    const int k0 = tz * CPT;
+    const int box = nz * TW;                          // floats per staged box
+
+    // ---- shared memory carve-up
+    enum { R_QLO, R_QHI, R_MHLO, R_MHHI, R_MLLO, R_MLHI, R_FZHI, R_BILO, R_BOLO, R_FLHI, R_COUNT };
+    float* rows = reinterpret_cast<float*>(smraw);
+    const int rows_floats = ((2 * R_COUNT * (nzt + 2) * TW + 31) / 32) * 32;
+    float* stage0 = rows + rows_floats;               // [2][NF][nz][32]
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(stage0 + 2 * NF * box);
+    auto row = [&](int buf, int kind, int z) -> float& { return rows[((buf * R_COUNT + kind) * (nzt + 2) + (z + 1)) * TW + tx]; };
+    const int tid = tz * TW + tx;
+    const int niter = jb - ja + 4;                    // planes ja-2 .. jb+1
+    const uint32_t stage_bytes = (uint32_t)(NF * box * sizeof(float));
+
+    auto issue = [&](int it) {                        // thread 0: fetch the 13 boxes of iteration `it`
+        const int P = ja - 2 + it, st = it & 1;
+        float* dst = stage0 + st * NF * box;
+        mbar_arrive_expect_tx(&mbar[st], stage_bytes);
+        tma_load_box(dst + F_Q2 * box, &maps.q2[scalar], &mbar[st], x0, 0, P);
+        tma_load_box(dst + F_L * box, &maps.l[scalar], &mbar[st], x0, 0, P);
+#pragma unroll
+        for (int f = 0; f < 3; ++f) tma_load_box(dst + (F_AY + f) * box, &maps.coef[f], &mbar[st], x0, 0, P);
+#pragma unroll
+        for (int f = 3; f < 11; ++f) tma_load_box(dst + (F_AY + f) * box, &maps.coef[f], &mbar[st], x0, 0, P - 2);
+    };
+
+    if (tid == 0) {
+        mbar_init(&mbar[0], 1);
+        mbar_init(&mbar[1], 1);
+        fence_barrier_init();
+    }
+    // rows of the (non-existent) threads below tz=0 and above tz=nzt-1 read as "no neighbour"
+    if (tz == 0) {
+        for (int b = 0; b < 2; ++b) {
+            row(b, R_QHI, -1) = 0.f; row(b, R_MHHI, -1) = -BIG; row(b, R_MLHI, -1) = BIG;
+            row(b, R_FZHI, -1) = 0.f; row(b, R_FLHI, -1) = 0.f;
+            row(b, R_QLO, nzt) = 0.f; row(b, R_MHLO, nzt) = -BIG; row(b, R_MLLO, nzt) = BIG;
+            row(b, R_BILO, nzt) = 0.f; row(b, R_BOLO, nzt) = 0.f;
+        }
+    }
+    __syncthreads();
+    if (tid == 0) issue(0);
+
+    // ---- per-cell register state (planes are relative to the newest loaded plane P)
+    float a[CPT][4];          // q2 at planes P-3, P-2, P-1, P
+    float sx[CPT][3];         // x-face pair sums  q2(i)+q2(i-1)   at planes P-3, P-2, P-1
+    float sz[CPT][3];         // z-face pair sums  q2(k+1)+q2(k)   at planes P-3, P-2, P-1
+    float mh[CPT][3], ml[CPT][3];   // max/min(q2, l) at planes P-2, P-1, P
+    float v2a[CPT];           // unlimited v2 at face (P-2 | P-1)
+    float fya[CPT];           // its donor flux
+    float byi[CPT], byo[CPT]; // y-limiter beta_in / beta_out of cell plane P-2
+    float fylp[CPT];          // limited y flux through face (P-3 | P-2)
+    float qab[4], qbl[4];     // q2 of the row above (k0+CPT) / below (k0-1) at planes P-3..P
+#pragma unroll
+    for (int c = 0; c < CPT; ++c) {
+#pragma unroll
+        for (int t = 0; t < 4; ++t) a[c][t] = 0.f;
+#pragma unroll
+        for (int t = 0; t < 3; ++t) { sx[c][t] = 0.f; sz[c][t] = 0.f; mh[c][t] = -BIG; ml[c][t] = BIG; }
+        v2a[c] = 0.f; fya[c] = 0.f; byi[c] = 0.f; byo[c] = 0.f; fylp[c] = 0.f;
+    }
+#pragma unroll
+    for (int t = 0; t < 4; ++t) { qab[t] = 0.f; qbl[t] = 0.f; }
+    const int cell_off = k0 * TW + tx;                // this thread's first cell inside a box
+
+    for (int it = 0; it < niter; ++it) {
+        const int P = ja - 2 + it;
+        const int buf = it & 1;
+        const bool pin = (P >= 0 && P < ny);          // plane P exists
+        const int Po = P - 2;                         // output plane of this iteration
+        const bool out_iter = (Po >= ja);
+        // every read of stage buf^1 (iteration it-1) precedes that iteration's first barrier,
+        // which this thread has passed: the stage is free to be refilled
+        if (tid == 0 && it + 1 < niter) issue(it + 1);
+        while (!mbar_try_wait(&mbar[buf], (uint32_t)((it >> 1) & 1))) {}
+        const float* __restrict__ sg = stage0 + buf * NF * box + cell_off;
+
+        // ---------------- shift the windows, take plane P from the stage
+        float cay[CPT], cby[CPT], ccy[CPT];
+#pragma unroll
+        for (int c = 0; c < CPT; ++c) {
+            a[c][0] = a[c][1]; a[c][1] = a[c][2]; a[c][2] = a[c][3];
+            mh[c][0] = mh[c][1]; mh[c][1] = mh[c][2];
+            ml[c][0] = ml[c][1]; ml[c][1] = ml[c][2];
+            const bool lev = (k0 + c < nz);
+            const bool cell = pin && col && lev;
+            const float q2v = lev ? sg[F_Q2 * box + c * TW] : 0.f;       // TMA zero-fills outside the domain
+            const float lv = lev ? sg[F_L * box + c * TW] : 0.f;
+            cay[c] = lev ? sg[F_AY * box + c * TW] : 0.f;
+            cby[c] = lev ? sg[F_BY * box + c * TW] : 0.f;
+            ccy[c] = lev ? sg[F_CY * box + c * TW] : 0.f;
+            a[c][3] = q2v;
+            mh[c][2] = cell ? fmaxf(q2v, lv) : -BIG;
+            ml[c][2] = cell ? fminf(q2v, lv) : BIG;
+        }
+        qab[0] = qab[1]; qab[1] = qab[2]; qab[2] = qab[3];
+        qbl[0] = qbl[1]; qbl[1] = qbl[2]; qbl[2] = qbl[3];
+
+        // ---------------- in-plane pseudo-velocities of plane Po = P-2 (data complete since P-1)
+        // (all shuffles are executed by every lane of every warp)
+        float u2[CPT], w2[CPT], fx[CPT], fz[CPT];
+        float rj[CPT], rjz[CPT];
+        if (out_iter) {
+            const float sx_ab = qab[1] + lane_lo(qab[1]);      // x pair sum of the row above / below
+            const float sx_bl = qbl[1] + lane_lo(qbl[1]);
+#pragma unroll
+            for (int c = 0; c < CPT; ++c) {
+                const bool lev = (k0 + c < nz);
+                const float cax = lev ? sg[F_AX * box + c * TW] : 0.f, cbx = lev ? sg[F_BX * box + c * TW] : 0.f,
+                            ccx = lev ? sg[F_CX * box + c * TW] : 0.f, caz = lev ? sg[F_AZ * box + c * TW] : 0.f,
+                            cbz = lev ? sg[F_BZ * box + c * TW] : 0.f, ccz = lev ? sg[F_CZ * box + c * TW] : 0.f;
+                rj[c] = lev ? sg[F_RJ * box + c * TW] : 0.f;
+                rjz[c] = lev ? sg[F_RJZ * box + c * TW] : 0.f;
+                const float q = a[c][1];
+                const float ql = lane_lo(q);
+                const float qu = (c + 1 < CPT) ? a[(c + 1 < CPT) ? c + 1 : c][1] : qab[1];
+                // x-face (i-1 | i)
+                const float sxc = sx[c][1];                                  // q(i)+q(i-1)
+                const float Ax = fdiv(q - ql, sxc + EPS);
+                const float sp = sx[c][2], sn = sx[c][0];                    // planes Po+1, Po-1
+                const float Bx = fdiv(sp - sn, sp + sn + EPS);
+                const float sxu = (c + 1 < CPT) ? sx[(c + 1 < CPT) ? c + 1 : c][1] : sx_ab;
+                const float sxd = (c > 0) ? sx[(c > 0) ? c - 1 : c][1] : sx_bl;
+                const float Cx = fdiv(sxu - sxd, sxu + sxd + EPS);
+                u2[c] = cax * Ax - cbx * Bx - ccx * Cx;
+                // z-face above k
+                const float szc = sz[c][1];                                  // q(k+1)+q(k)
+                const float Az = fdiv(qu - q, szc + EPS);
+                const float szr = lane_hi(szc), szl = lane_lo(szc);
+                const float Bz = fdiv(szr - szl, szr + szl + EPS);
+                const float zp = sz[c][2], zn = sz[c][0];
+                const float Cz = fdiv(zp - zn, zp + zn + EPS);
+                w2[c] = caz * Az - cbz * Bz - ccz * Cz;
+                // donor fluxes of the UNLIMITED pseudo-velocities (FCT core: f = flux1(q1(c), q1(c+1), U2))
+                fx[c] = donor(u2[c], ql, q);
+                fz[c] = donor(w2[c], q, qu);
+            }
+        }
+        // ---------------- publish rows for the z-neighbour threads
+        row(buf, R_QLO, tz) = a[0][3];
+        row(buf, R_QHI, tz) = a[CPT - 1][3];
+        if (out_iter) {
+            row(buf, R_MHLO, tz) = mh[0][0]; row(buf, R_MHHI, tz) = mh[CPT - 1][0];
+            row(buf, R_MLLO, tz) = ml[0][0]; row(buf, R_MLHI, tz) = ml[CPT - 1][0];
+            row(buf, R_FZHI, tz) = fz[CPT - 1];
+        }
+        __syncthreads();            // (no read of the TMA stage below this line)
+        qab[3] = row(buf, R_QLO, tz + 1);
+        qbl[3] = row(buf, R_QHI, tz - 1);
+
+        // ---------------- y-face (P-1 | P): unlimited v2, then beta_y of plane P-1
+        float v2b[CPT], fyb[CPT], syv[CPT];
+#pragma unroll
+        for (int c = 0; c < CPT; ++c) syv[c] = a[c][3] + a[c][2];
+        const float sy_ab = qab[3] + qab[2], sy_bl = qbl[3] + qbl[2];
+#pragma unroll
+        for (int c = 0; c < CPT; ++c) {
+            const float syr = lane_hi(syv[c]), syl = lane_lo(syv[c]);
+            const float Ay = fdiv(a[c][3] - a[c][2], syv[c] + EPS);
+            const float By = fdiv(syr - syl, syr + syl + EPS);
+            const float syu = (c + 1 < CPT) ? syv[(c + 1 < CPT) ? c + 1 : c] : sy_ab;
+            const float syd = (c > 0) ? syv[(c > 0) ? c - 1 : c] : sy_bl;
+            const float Cy = fdiv(syu - syd, syu + syd + EPS);
+            v2b[c] = cay[c] * Ay - cby[c] * By - ccy[c] * Cy;     // ay = by = cy = 0 for j = 0 (no face)
+            fyb[c] = donor(v2b[c], a[c][2], a[c][3]);            // face (P-1 | P)
+        }
+        // beta_y of cell plane Pc = P-1 (needs fy of faces (P-2|P-1), (P-1|P) and mh/ml of P-2..P)
+        float byi1[CPT], byo1[CPT];
+        {
+            const int Pc = P - 1;
+            const bool ylast = (Pc == ny - 1);
+            const float yedge = (Pc == 0 || ylast) ? 0.f : 1.f;
+#pragma unroll
+            for (int c = 0; c < CPT; ++c) {
+                const float q = a[c][2];
+                const float hi = max3(mh[c][0], ylast ? q : mh[c][1], mh[c][2]);
+                const float lo = min3(ml[c][0], ylast ? q : ml[c][1], ml[c][2]);
+                const float fin = (fmaxf(0.f, fya[c]) - fminf(0.f, fyb[c])) * yedge;
+                const float fout = (fmaxf(0.f, fyb[c]) - fminf(0.f, fya[c])) * yedge;
+                byi1[c] = fdiv(hi - q, fin + E15);
+                byo1[c] = fdiv(q - lo, fout + E15);
+            }
+        }
+        // limited y flux through face (P-2 | P-1)
+        float fyl[CPT];
+#pragma unroll
+        for (int c = 0; c < CPT; ++c) {
+            const float v = v2a[c];
+            const float lim = (v > 0.f) ? min3(1.f, byi1[c], byo[c]) : min3(1.f, byi[c], byo1[c]);
+            fyl[c] = donor(lim * v, a[c][1], a[c][2]);
+        }
+
+        // ---------------- x / z limiter and corrector update of plane Po
+        if (out_iter) {
+            const float mhb = row(buf, R_MHHI, tz - 1), mlb = row(buf, R_MLHI, tz - 1);   // row below k0
+            const float mha = row(buf, R_MHLO, tz + 1), mla = row(buf, R_MLLO, tz + 1);   // row above
+            const float fzb = row(buf, R_FZHI, tz - 1);                                   // f_z of face above k0-1
+            float bxi[CPT], bxo[CPT], bzi[CPT], bzo[CPT];
+#pragma unroll
+            for (int c = 0; c < CPT; ++c) {
+                const int k = k0 + c;
+                const float q = a[c][1];
+                const float mhc = mh[c][0], mlc = ml[c][0];
+                // x direction
+                {
+                    const float mhl = lane_lo(mhc), mhr = lane_hi(mhc), mll = lane_lo(mlc), mlr = lane_hi(mlc);
+                    const float fxp = lane_hi(fx[c]);
+                    const float hi = max3(has_l ? mhl : -BIG, ilast ? q : mhc, has_r ? mhr : -BIG);
+                    const float lo = min3(has_l ? mll : BIG, ilast ? q : mlc, has_r ? mlr : BIG);
+                    const float fin = (fmaxf(0.f, fx[c]) - fminf(0.f, fxp)) * xedge;
+                    const float fout = (fmaxf(0.f, fxp) - fminf(0.f, fx[c])) * xedge;
+                    bxi[c] = fdiv(hi - q, fin + E15);
+                    bxo[c] = fdiv(q - lo, fout + E15);
+                }
+                // z direction (flux_is_w rules at the line ends, FCT core :75-77, :92-94)
+                {
+                    const bool zlast = (k == nz - 1);
+                    const float mhd = (c > 0) ? mh[(c > 0) ? c - 1 : c][0] : mhb;
+                    const float mld = (c > 0) ? ml[(c > 0) ? c - 1 : c][0] : mlb;
+                    const float mhu = (c + 1 < CPT) ? mh[(c + 1 < CPT) ? c + 1 : c][0] : mha;
+                    const float mlu = (c + 1 < CPT) ? ml[(c + 1 < CPT) ? c + 1 : c][0] : mla;
+                    const float fzm = (c > 0) ? fz[(c > 0) ? c - 1 : c] : fzb;
+                    const float fzp = zlast ? fzm : fz[c];            // top: fin = fout = |f(nz-2)|
+                    const float hi = max3(mhd, zlast ? q : mhc, zlast ? -BIG : mhu);
+                    const float lo = min3(mld, zlast ? q : mlc, zlast ? BIG : mlu);
+                    const float fin = fmaxf(0.f, fzm) - fminf(0.f, fzp);
+                    const float fout = fmaxf(0.f, fzp) - fminf(0.f, fzm);
+                    bzi[c] = fdiv(hi - q, fin + E15);
+                    bzo[c] = fdiv(q - lo, fout + E15);
+                }
+            }
+            row(buf, R_BILO, tz) = bzi[0];
+            row(buf, R_BOLO, tz) = bzo[0];
+            __syncthreads();
+            const float bia = row(buf, R_BILO, tz + 1), boa = row(buf, R_BOLO, tz + 1);
+            float fxl[CPT], fzl[CPT];
+#pragma unroll
+            for (int c = 0; c < CPT; ++c) {
+                const float q = a[c][1];
+                // limited x flux through face (i-1 | i)
+                const float bil = lane_lo(bxi[c]), bol = lane_lo(bxo[c]);
+                const float u = u2[c];
+                const float limx = (u > 0.f) ? min3(1.f, bxi[c], bol) : min3(1.f, bil, bxo[c]);
+                fxl[c] = donor(limx * u, lane_lo(q), q);
+                // limited z flux through the face above k
+                const float biu = (c + 1 < CPT) ? bzi[(c + 1 < CPT) ? c + 1 : c] : bia;
+                const float bou = (c + 1 < CPT) ? bzo[(c + 1 < CPT) ? c + 1 : c] : boa;
+                const float w = w2[c];
+                const float limz = (w > 0.f) ? min3(1.f, biu, bzo[c]) : min3(1.f, bzi[c], bou);
+                const float qu = (c + 1 < CPT) ? a[(c + 1 < CPT) ? c + 1 : c][1] : qab[1];
+                fzl[c] = donor(limz * w, q, qu);
+            }
+            row(buf, R_FLHI, tz) = fzl[CPT - 1];
+            __syncthreads();
+            const float fzlb = row(buf, R_FLHI, tz - 1);
+            const bool store_col = col && (tx >= XH) && (tx < TW - XH) && (i >= 1) && (i <= nx - 2);
+            float* __restrict__ op = gout + g.at(col ? i : 0, k0, Po);
+#pragma unroll
+            for (int c = 0; c < CPT; ++c) {
+                const float fxr = lane_hi(fxl[c]);
+                const float fzd = (c > 0) ? fzl[(c > 0) ? c - 1 : c] : fzlb;
+                if (store_col && k0 + c < nz) {
+                    const float q = a[c][1];
+                    float val = q - ((fxr - fxl[c]) + (fyl[c] - fylp[c])) * rj[c];
+                    val = val - (fzl[c] - fzd) * rjz[c];
+                    op[c * g.ld] = val;
+                }
+            }
+        }
+        // ---------------- roll the y state forward
+#pragma unroll
+        for (int c = 0; c < CPT; ++c) {
+            fylp[c] = fyl[c];
+            v2a[c] = v2b[c];
+            fya[c] = fyb[c];
+            byi[c] = byi1[c]; byo[c] = byo1[c];
+            sx[c][0] = sx[c][1]; sx[c][1] = sx[c][2];
+            sz[c][0] = sz[c][1]; sz[c][1] = sz[c][2];
+            sx[c][2] = a[c][3] + lane_lo(a[c][3]);
+            sz[c][2] = a[c][3] + ((c + 1 < CPT) ? a[(c + 1 < CPT) ? c + 1 : c][3] : qab[3]);
+        }
+    }
+}
+
+// ---- host side: tensor maps
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+struct MapKey {
+    const void* p; int nx, nz, ny, ld;
+    bool operator==(const MapKey& o) const { return p == o.p && nx == o.nx && nz == o.nz && ny == o.ny && ld == o.ld; }
+};
+struct MapKeyHash {
+    size_t operator()(const MapKey& k) const { return std::hash<const void*>()(k.p) ^ (size_t)k.nx * 1315423911u ^ (size_t)k.ny * 2654435761u; }
+};
+
+// a (nx, nz, ny) fp32 field with row pitch ld, read in boxes of 32 x nz x 1
+bool field_map(const Geom& g, const float* ptr, CUtensorMap* out) {
+    static thread_local std::unordered_map<MapKey, CUtensorMap, MapKeyHash> cache;
+    MapKey key{ptr, g.nx, g.nz, g.ny, g.ld};
+    auto it = cache.find(key);
+    if (it != cache.end()) { *out = it->second; return true; }
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) return false;
+    cuuint64_t gdim[3] = {(cuuint64_t)g.nx, (cuuint64_t)g.nz, (cuuint64_t)g.ny};
+    cuuint64_t gstr[2] = {(cuuint64_t)g.ld * sizeof(float), (cuuint64_t)g.ld * g.nz * sizeof(float)};
+    cuuint32_t bx[3] = {(cuuint32_t)TW, (cuuint32_t)g.nz, 1u};
+    cuuint32_t es[3] = {1u, 1u, 1u};
+    CUtensorMap m;
+    CUresult r = fn(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(ptr), gdim, gstr, bx, es,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return false;
+    if (cache.size() > 4096) cache.clear();
+    cache.emplace(key, m);
+    *out = m;
+    return true;
+}
+
+int env_int(const char* name, int dflt) {
+    const char* v = std::getenv(name);
+    return v ? std::atoi(v) : dflt;
+}
+
+}  // namespace
+
+int fused_advect_all(const Geom& g, const ScalarSet& s, const float* U, const float* V, const float* W,
+                     const float* Wn, const float* jaco, const float* dz, const FusedCoef& co,
+                     cudaStream_t st) {
+    int launches = 0;
+    if (s.n > FUSED_MAX_SCALARS) return -1;
+    dim3 cgrid((g.nx + 127) / 128, g.nz, g.ny);
+    k_face_coefficients<<<cgrid, 128, 0, st>>>(g, U, V, Wn, jaco, dz, co);
+    launches += 1;
+    launches += staged_upwind_all(g, s, U, V, W, dz, jaco, st);   // also copies the boundary ring into `out`
+
+    FusedMaps maps;
+    OutSet outs;
+    outs.n = s.n;
+    const float* cf[11] = {co.ay, co.by, co.cy, co.ax, co.bx, co.cx, co.az, co.bz, co.cz, co.rj, co.rjz};
+    for (int n = 0; n < s.n; ++n) {
+        outs.out[n] = s.out[n];
+        if (!field_map(g, s.q2[n], &maps.q2[n]) || !field_map(g, s.q[n], &maps.l[n])) return -1;
+    }
+    for (int f = 0; f < 11; ++f)
+        if (!field_map(g, cf[f], &maps.coef[f])) return -1;
+
+    int cpt = env_int("ICAR_FUSED_CPT", 4);
+    if (cpt != 2 || g.nz > 40) cpt = 4;
+    const int nzt = (g.nz + cpt - 1) / cpt;
+    const int xtiles = g.nx / TOUT + 1;               // outputs of tile xt: columns 28*xt-2 .. 28*xt+25
+    // y-chunks: pick the split that wastes least (partial last wave of 148 SMs vs. the 4 warm-up
+    // planes each chunk re-reads); one CTA per SM is resident (shared-memory bound)
+    const int per_row = xtiles * s.n, planes = g.ny - 2;
+    int best = 1;
+    double best_cost = 1e30;
+    for (int cand = 1; cand <= 64 && cand <= planes; ++cand) {
+        const int len = (planes + cand - 1) / cand;
+        const int ctas = per_row * ((planes + len - 1) / len);
+        const int waves = (ctas + 147) / 148;
+        const double cost = (double)waves * (len + 4);
+        if (cost < best_cost) { best_cost = cost; best = cand; }
+    }
+    const int chunk = (planes + best - 1) / best;
+    const int chunks = (planes + chunk - 1) / chunk;
+    const int rows_floats = ((2 * 10 * (nzt + 2) * TW + 31) / 32) * 32;
+    const size_t smem = (size_t)rows_floats * sizeof(float) + (size_t)2 * NF * g.nz * TW * sizeof(float) + 16;
+    dim3 grid(xtiles * s.n, chunks);
+    dim3 block(TW, nzt);
+    if (cpt == 2) {
+        auto kern = k_corrector_fused<2, 640>;
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
+        kern<<<grid, block, smem, st>>>(g, outs, maps, chunk);
+    } else {
+        auto kern = k_corrector_fused<4, 512>;
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
+        kern<<<grid, block, smem, st>>>(g, outs, maps, chunk);
+    }
+    ++launches;
+    return launches;
+}
+
+}  // namespace icar

@@ -291,11 +291,56 @@ __global__ void k_corrector(Geom g, const R* __restrict__ l, const R* __restrict
     qout[c] = val;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Pass 1 for all scalars (same arithmetic, bit for bit, as k_upwind above; this file is built with -fmad=false).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+k_upwind_all(Geom g, ScalarSet s, const float* __restrict__ U, const float* __restrict__ V,
+             const float* __restrict__ W, const float* __restrict__ dz, const float* __restrict__ jaco) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int k = blockIdx.y, j = blockIdx.z;
+    if (i >= g.nx) return;
+    const size_t c = g.at(i, k, j);
+    if (i == 0 || i == g.nx - 1 || j == 0 || j == g.ny - 1) {
+#pragma unroll 1
+        for (int n = 0; n < s.n; ++n) { const float v = s.q[n][c]; s.q2[n][c] = v; s.out[n][c] = v; }
+        return;
+    }
+    const size_t ps = g.ps();
+    const int ld = g.ld;
+    const float uxm = U[c], uxp = U[c + 1], vym = V[c], vyp = V[c + ps];
+    const float wzp = W[c], wzm = (k > 0) ? W[c - ld] : 0.f;
+    const float jc = jaco[c];
+    const float den = dz[c] * jc;
+    const bool bottom = (k == 0), top = (k == g.nz - 1), flat = (g.nz == 1);
+#pragma unroll 1
+    for (int n = 0; n < s.n; ++n) {
+        const float* __restrict__ qin = s.q[n];
+        const float qc = qin[c];
+        const float fxm = donor(uxm, qin[c - 1], qc), fxp = donor(uxp, qc, qin[c + 1]);
+        const float fym = donor(vym, qin[c - ps], qc), fyp = donor(vyp, qc, qin[c + ps]);
+        float val = qc - ((fxp - fxm) + (fyp - fym)) / jc;
+        if (!flat) {
+            if (bottom)   val = val - donor(wzp, qc, qin[c + ld]) / den;
+            else if (top) val = val - (qc * wzp - donor(wzm, qin[c - ld], qc)) / den;
+            else          val = val - (donor(wzp, qc, qin[c + ld]) - donor(wzm, qin[c - ld], qc)) / den;
+        }
+        s.q2[n][c] = val;
+    }
+}
+
 // ---------------------------------------------------------------------------
 // launchers
 // ---------------------------------------------------------------------------
 static inline dim3 cell_grid(const Geom& g, int bx) {
     return dim3((g.nx + bx - 1) / bx, g.nz, g.ny);
+}
+
+
+int staged_upwind_all(const Geom& g, const ScalarSet& s, const float* U, const float* V, const float* W,
+                      const float* dz, const float* jaco, cudaStream_t st) {
+    k_upwind_all<<<cell_grid(g, 128), 128, 0, st>>>(g, s, U, V, W, dz, jaco);
+    return 1;
 }
 
 template <class R>

@@ -61,6 +61,12 @@ typedef struct icar_options {
     int update_interval;          /* mp_options%update_interval [s], default 0 (:1282)       */
     int top_mp_level;             /* mp_options%top_mp_level, default 0 = all (:1283)         */
     float dx;                     /* domain%dx [m]                                           */
+    int exact_arithmetic;         /* no reference counterpart.  0 (default): MPDATA order 2 + FCT runs the
+                                     fused kernel, whose anti-diffusive correction is evaluated with
+                                     pre-multiplied coefficients, shared pair sums and MUFU-based division
+                                     (differences ~1e-8 relative, tolerance 1e-6 in the tests);
+                                     1: always run the staged kernels, which keep the Fortran's operand
+                                     order and are bit-identical to the CPU oracle.                        */
 } icar_options;
 
 /* kVARS-style identifiers of the domain_t members the path touches
