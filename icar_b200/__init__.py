@@ -102,7 +102,7 @@ SYMBOLS = (
     "icar_advect", "icar_mp", "icar_halo_send", "icar_halo_retrieve", "icar_halo_exchange",
     "icar_physics_step", "icar_synchronize", "icar_mp_diagnostics", "icar_kernel_launches",
     "icar_timer_start", "icar_timer_stop",
-    "icar_comm_unique_id", "icar_comm_init", "icar_mpdata_set_winds", "icar_mpdata_advect3d",
+    "icar_halo_plan", "icar_comm_unique_id", "icar_comm_init", "icar_mpdata_set_winds", "icar_mpdata_advect3d",
     "icar_mpdata_set_winds_f64", "icar_mpdata_advect3d_f64", "icar_mp_simple_driver",
     "icar_physics_step_host", "icar_host_register", "icar_host_unregister")
 
@@ -308,6 +308,17 @@ class Domain:
 
     def host_register(self, hd): self._check(lib().icar_host_register(self._h, C.byref(hd)))
     def host_unregister(self, hd): self._check(lib().icar_host_unregister(self._h, C.byref(hd)))
+
+
+def halo_plan(grid: Grid, image: int, nimages: int):
+    """(send_west, send_east, recv_west, recv_east) first local columns (0-based) and the two
+    neighbour flags -- icar_halo_plan."""
+    plan = (C.c_int * 6)()
+    rc = lib().icar_halo_plan(C.byref(grid), int(image), int(nimages), plan)
+    if rc:
+        raise IcarError(rc, "icar_halo_plan: invalid arguments")
+    return dict(send_west=plan[0], send_east=plan[1], recv_west=plan[2], recv_east=plan[3],
+                has_west=bool(plan[4]), has_east=bool(plan[5]), width=grid.halo_size)
 
 
 def comm_unique_id() -> bytes:

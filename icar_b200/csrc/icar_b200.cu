@@ -222,7 +222,7 @@ int run_mp_tile(icar_ctx* ctx, float mp_dt, int its, int ite, int jts, int jte, 
             (float*)ctx->vars[ICAR_VAR_SNOW_IN_AIR], rain2d, snow2d, ctx->ld2, mp_dt,
             (const float*)ctx->vars[ICAR_VAR_DZ_MASS], its - gr.ims, ite - gr.ims, jts - gr.jms,
             jte - gr.jms, kts - gr.kms, kte - gr.kms, c2r, c2s, ctx->diag, st);
-        if (nl < 0) return fail(ctx, ICAR_ERR_INVALID, "mp_simple: more than 128 levels are not built");
+        if (nl < 0) return fail(ctx, ICAR_ERR_INVALID, "mp_simple: more than 80 levels are not built");
         ctx->launches += nl;
         CU(cudaGetLastError());
         return ICAR_OK;
@@ -332,7 +332,7 @@ extern "C" int icar_create(int device, const icar_grid* grid, const icar_options
         if (alloc_cells(ctx, p) != ICAR_OK) return bail(ICAR_ERR_CUDA);
     if (opt->advect_density && alloc_cells(ctx, &ctx->G) != ICAR_OK) return bail(ICAR_ERR_CUDA);
     ctx->fused = (opt->advection == 2 && opt->mpdata_order == 2 && opt->flux_corrected_transport &&
-                  !opt->advect_density && !opt->exact_arithmetic && nz <= 64 && nz >= 2);
+                  !opt->advect_density && !opt->exact_arithmetic && fused_plan(ctx->g).ok);
     if (ctx->fused) {
         float** cf[] = {&ctx->coef.ax, &ctx->coef.bx, &ctx->coef.cx, &ctx->coef.ay, &ctx->coef.by, &ctx->coef.cy,
                         &ctx->coef.az, &ctx->coef.bz, &ctx->coef.cz, &ctx->coef.rj, &ctx->coef.rjz};
@@ -502,10 +502,11 @@ extern "C" int icar_advect(icar_ctx* ctx, float dt) {
         g, (const float*)ctx->vars[ICAR_VAR_U], (const float*)ctx->vars[ICAR_VAR_V],
         (const float*)ctx->vars[ICAR_VAR_W], (const float*)ctx->vars[ICAR_VAR_JACOBIAN_U],
         (const float*)ctx->vars[ICAR_VAR_JACOBIAN_V], (const float*)ctx->vars[ICAR_VAR_JACOBIAN_W], rho, dt,
-        ctx->opt.dx, mpdata ? 2 : 1, ctx->U, ctx->V, ctx->W, ctx->stream);
+        ctx->opt.dx, mpdata ? 2 : 1, ctx->U, ctx->V, ctx->W, ctx->stream, ctx->fused ? dz : nullptr,
+        ctx->fused ? ctx->Wn : nullptr);
     const int order = mpdata ? ctx->opt.mpdata_order : 1;
     const float* G = jaco;          // jaco*rho with rho == 1 is jaco itself
-    if (order > 1) {
+    if (order > 1 && !ctx->fused) {
         ctx->launches += staged_wn_G<float>(g, ctx->W, dz, jaco, rho, ctx->Wn, rho ? ctx->G : nullptr, ctx->stream);
         if (rho) G = ctx->G;
     }
@@ -608,6 +609,19 @@ extern "C" int icar_mp(icar_ctx* ctx, float dt_in, int halo, int subset) {
 
 // ============================================================================ halo exchange
 
+extern "C" int icar_halo_plan(const icar_grid* grid, int image, int nimages, int plan[6]) {
+    if (!grid || !plan || nimages < 1 || image < 1 || image > nimages) return ICAR_ERR_INVALID;
+    const int h = grid->halo_size, nx = grid->ime - grid->ims + 1;
+    if (h < 1 || nx < 2 * h) return ICAR_ERR_INVALID;
+    plan[0] = h;               // put_west
+    plan[1] = nx - 2 * h;      // put_east
+    plan[2] = 0;               // retrieve_west_halo
+    plan[3] = nx - h;          // retrieve_east_halo
+    plan[4] = image > 1 ? 1 : 0;
+    plan[5] = image < nimages ? 1 : 0;
+    return ICAR_OK;
+}
+
 extern "C" int icar_comm_unique_id(char id[128]) {
     std::string err;
     if (!g_nccl.load(err)) { g_create_error = err; return ICAR_ERR_COMM; }
@@ -643,14 +657,15 @@ extern "C" int icar_halo_send(icar_ctx* ctx) {
     if (!ctx->comm) return fail(ctx, ICAR_ERR_COMM, "icar_halo_send: icar_comm_init was not called");
     CU(cudaSetDevice(ctx->device));
     { int jr = join_aux(ctx); if (jr) return jr; }
-    const int h = ctx->grid.halo_size, nx = ctx->g.nx;
-    const bool west = ctx->image > 1, east = ctx->image < ctx->nimages;
+    const int h = ctx->grid.halo_size;
+    int plan[6];
+    if (icar_halo_plan(&ctx->grid, ctx->image, ctx->nimages, plan)) return fail(ctx, ICAR_ERR_INVALID, "icar_halo_send: tile narrower than two halos");
+    const bool west = plan[4] != 0, east = plan[5] != 0;
     float* fields[5];
     for (int s = 0; s < 5; ++s) fields[s] = (float*)ctx->vars[kExchangedSimple[s]];
     const size_t count = (size_t)5 * ctx->g.ny * ctx->g.nz * h;
-    // put_west: data(start+h : start+2h-1) ; put_east: data(n-2h+1 : n-h)   (exchangeable_obj.f90:303-335)
-    if (west) ctx->launches += halo_pack_launch(ctx->g, fields, 5, h, h, ctx->send_w, ctx->stream);
-    if (east) ctx->launches += halo_pack_launch(ctx->g, fields, 5, h, nx - 2 * h, ctx->send_e, ctx->stream);
+    if (west) ctx->launches += halo_pack_launch(ctx->g, fields, 5, h, plan[0], ctx->send_w, ctx->stream);
+    if (east) ctx->launches += halo_pack_launch(ctx->g, fields, 5, h, plan[1], ctx->send_e, ctx->stream);
     CU(cudaGetLastError());
     CU(cudaEventRecord(ctx->ev_packed, ctx->stream));
     CU(cudaStreamWaitEvent(ctx->comm_stream, ctx->ev_packed, 0));
@@ -674,14 +689,15 @@ extern "C" int icar_halo_retrieve(icar_ctx* ctx) {
     if (ctx->nimages == 1) return ICAR_OK;
     if (!ctx->exchange_in_flight) return fail(ctx, ICAR_ERR_INVALID, "icar_halo_retrieve without icar_halo_send");
     CU(cudaSetDevice(ctx->device));
-    const int h = ctx->grid.halo_size, nx = ctx->g.nx;
-    const bool west = ctx->image > 1, east = ctx->image < ctx->nimages;
+    const int h = ctx->grid.halo_size;
+    int plan[6];
+    if (icar_halo_plan(&ctx->grid, ctx->image, ctx->nimages, plan)) return fail(ctx, ICAR_ERR_INVALID, "icar_halo_retrieve: tile narrower than two halos");
+    const bool west = plan[4] != 0, east = plan[5] != 0;
     float* fields[5];
     for (int s = 0; s < 5; ++s) fields[s] = (float*)ctx->vars[kExchangedSimple[s]];
     CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_comm, 0));     // `sync images(neighbors)`, exchangeable_obj.f90:151
-    // retrieve_west_halo: data(start : start+h-1) ; retrieve_east_halo: data(n-h+1 : n)  (:339-356)
-    if (west) ctx->launches += halo_unpack_launch(ctx->g, fields, 5, h, 0, ctx->recv_w, ctx->stream);
-    if (east) ctx->launches += halo_unpack_launch(ctx->g, fields, 5, h, nx - h, ctx->recv_e, ctx->stream);
+    if (west) ctx->launches += halo_unpack_launch(ctx->g, fields, 5, h, plan[2], ctx->recv_w, ctx->stream);
+    if (east) ctx->launches += halo_unpack_launch(ctx->g, fields, 5, h, plan[3], ctx->recv_e, ctx->stream);
     CU(cudaGetLastError());
     ctx->exchange_in_flight = false;
     return ICAR_OK;

@@ -172,7 +172,7 @@ __device__ __forceinline__ void mp_conversions(float p, float& t, float& qv, flo
 // Shared memory: two planes [nzp][TX] for q_old / rho (+1 padding level that reads as 0),
 // three column-reduction rows.
 template <int CPT>
-__global__ void __launch_bounds__(TX * 32)
+__global__ void __launch_bounds__(TX * 10, 2)
 k_mp_simple(Geom g, const float* __restrict__ gp, float* __restrict__ gth,
             const float* __restrict__ gpii, const float* __restrict__ grho,
             float* __restrict__ gqv, float* __restrict__ gqc, float* __restrict__ gqr,
@@ -193,12 +193,14 @@ k_mp_simple(Geom g, const float* __restrict__ gp, float* __restrict__ gth,
     const int top = min(kte, nz - 2);
 
     float T[CPT], p[CPT], rho[CPT], dz[CPT], pii[CPT], qv[CPT], qc[CPT], qr[CPT], qs[CPT];
+    float qvs[CPT], Tq[CPT];                   // cached sat_mr(Tq, p)
     bool live[CPT];
 #pragma unroll
     for (int c = 0; c < CPT; ++c) {
         const int k = tz + c * nzt;
         live[c] = col_ok && (k < nz);
         T[c] = p[c] = rho[c] = pii[c] = 1.f; dz[c] = 1.f; qv[c] = qc[c] = qr[c] = qs[c] = 0.f;
+        qvs[c] = 0.f; Tq[c] = -1.f;
         if (live[c]) {
             const size_t a = g.at(i, k, j);
             p[c] = gp[a]; pii[c] = gpii[a]; rho[c] = grho[a]; dz[c] = gdz[a];
@@ -207,31 +209,28 @@ k_mp_simple(Geom g, const float* __restrict__ gp, float* __restrict__ gth,
             if (k >= kts && k <= kte) mp_conversions(p[c], T[c], qv[c], qc[c], qr[c], qs[c], cx);  // :500-502
         }
     }
-    // ---- column reductions: maxval(qr), maxval(qs), maxval(dt/dz) over the WHOLE column (:505,:511)
-    if (tz == 0) { s_q[nz * TX + tx] = 0.f; s_rho[nz * TX + tx] = 0.f; }
-#pragma unroll
-    for (int c = 0; c < CPT; ++c) {
-        const int k = tz + c * nzt;
-        if (k < nz) { s_q[k * TX + tx] = live[c] ? qr[c] : -3.4e38f; s_rho[k * TX + tx] = live[c] ? qs[c] : -3.4e38f; }
-    }
-    __syncthreads();
-    if (tz < 2) {
-        const float* src = (tz == 0) ? s_q : s_rho;
-        float m = -3.4e38f;
-        for (int k = 0; k < nz; ++k) m = fmaxf(m, src[k * TX + tx]);
-        s_red[tz * TX + tx] = m;
-    }
-    __syncthreads();
-#pragma unroll
-    for (int c = 0; c < CPT; ++c) {
-        const int k = tz + c * nzt;
-        if (k < nz) { s_q[k * TX + tx] = live[c] ? dt / dz[c] : -3.4e38f; s_rho[k * TX + tx] = rho[c]; }
-    }
-    __syncthreads();
+    // ---- column reductions: maxval(qr), maxval(qs), maxval(dt/dz) over the WHOLE column (:505,:511).
+    // The first two are only compared with SMALL_VALUE > 0 and dt/dz is positive, so the maxima of
+    // max(x, 0) serve, and for non-negative floats integer order == float order: one shared-memory
+    // atomicMax per value replaces a serial walk over the levels.
+    int* s_redi = reinterpret_cast<int*>(s_red);
     if (tz == 0) {
-        float m = -3.4e38f;
-        for (int k = 0; k < nz; ++k) m = fmaxf(m, s_q[k * TX + tx]);
-        s_red[2 * TX + tx] = m;
+        s_q[nz * TX + tx] = 0.f;            // q_old / rho "above the model top"
+        s_rho[nz * TX + tx] = 0.f;
+        s_redi[tx] = 0; s_redi[TX + tx] = 0; s_redi[2 * TX + tx] = 0;
+    }
+    __syncthreads();
+    {
+        float mqr = 0.f, mqs = 0.f, mdz = 0.f;
+#pragma unroll
+        for (int c = 0; c < CPT; ++c) {
+            const int k = tz + c * nzt;
+            if (live[c]) { mqr = fmaxf(mqr, qr[c]); mqs = fmaxf(mqs, qs[c]); mdz = fmaxf(mdz, dt / dz[c]); }
+            if (k < nz) s_rho[k * TX + tx] = rho[c];
+        }
+        atomicMax(&s_redi[tx], __float_as_int(mqr));
+        atomicMax(&s_redi[TX + tx], __float_as_int(mqs));
+        atomicMax(&s_redi[2 * TX + tx], __float_as_int(mdz));
     }
     __syncthreads();
     const float max_qr = s_red[tx], max_qs = s_red[TX + tx], max_dtdz = s_red[2 * TX + tx];
@@ -296,9 +295,10 @@ k_mp_simple(Geom g, const float* __restrict__ gp, float* __restrict__ gth,
                     }
                     if (k <= kte && nq > SMALL_VALUE) {                    // :519-528 / :549-561
                         const float L_evap = -1.f * (LH_vapor + (373.15f - T[c]) * dLHvdt);
-                        const float qvsat = sat_mr(T[c], p[c], cx);
-                        if (qv[c] < qvsat)
-                            phase_change(T[c], nq, qvsat, qv[c], species ? (L_melt + L_evap) : L_evap, rate, cx);
+                        // sat_mr depends on (T, p) only: reuse the last value while T has not changed
+                        if (T[c] != Tq[c]) { qvs[c] = sat_mr(T[c], p[c], cx); Tq[c] = T[c]; }
+                        if (qv[c] < qvs[c])
+                            phase_change(T[c], nq, qvs[c], qv[c], species ? (L_melt + L_evap) : L_evap, rate, cx);
                     }
                     q = nq;
                 }
@@ -335,8 +335,8 @@ int mp_simple_launch(const Geom& g, const float* p, float* th, const float* pii,
                      float dt, const float* dz, int its, int ite, int jts, int jte, int kts,
                      int kte, float c2r, float c2s, unsigned long long* diag, cudaStream_t st) {
     if (ite < its || jte < jts) return 0;
-    const int cpt = (g.nz + 31) / 32;                       // cells per thread
-    if (cpt > 4) return -1;                                 // nz > 128 is not built
+    int cpt = (g.nz + 9) / 10;                              // cells per thread: ~10 z-threads per CTA
+    if (cpt > 8) return -1;                                 // nz > 80 is not built
     const int nzt = (g.nz + cpt - 1) / cpt;
     dim3 block(TX, nzt);
     dim3 grid((ite - its + 1 + TX - 1) / TX, jte - jts + 1);
@@ -348,7 +348,11 @@ int mp_simple_launch(const Geom& g, const float* p, float* th, const float* pii,
         case 1: LAUNCH(1); break;
         case 2: LAUNCH(2); break;
         case 3: LAUNCH(3); break;
-        default: LAUNCH(4); break;
+        case 4: LAUNCH(4); break;
+        case 5: LAUNCH(5); break;
+        case 6: LAUNCH(6); break;
+        case 7: LAUNCH(7); break;
+        default: LAUNCH(8); break;
     }
 #undef LAUNCH
     return 1;

@@ -21,6 +21,15 @@ struct FusedCoef {
     float *ax, *bx, *cx, *ay, *by, *cy, *az, *bz, *cz, *rj, *rjz;
 };
 
+// launch plan of the fused corrector for a tile; ok == false when it cannot serve this geometry
+// (more than 48 levels, or not enough opt-in shared memory): the caller then uses the staged path
+struct FusedPlan {
+    bool ok;
+    int cpt, nzp;
+    size_t smem;
+};
+FusedPlan fused_plan(const Geom& g);
+
 // order 2 + FCT, rho == 1, fp32: coefficients, pass 1 for all scalars, fused corrector.
 // U,V,W,Wn from staged_wind_normalise / staged_wn_G.  nz <= 64.  Returns < 0 when the TMA
 // tensor maps cannot be built (driver without cuTensorMapEncodeTiled).
@@ -35,7 +44,7 @@ int staged_upwind_all(const Geom& g, const ScalarSet& s, const float* U, const f
 template <class R>
 int staged_wind_normalise(const Geom& g, const R* u, const R* v, const R* w, const R* ju,
                           const R* jv, const R* jw, const R* rho, R dt, R dx, int scheme, R* U,
-                          R* V, R* W, cudaStream_t st);
+                          R* V, R* W, cudaStream_t st, const R* dz = nullptr, R* Wn = nullptr);
 
 template <class R>
 int staged_wn_G(const Geom& g, const R* W, const R* dz, const R* jaco, const R* rho, R* Wn, R* G,

@@ -117,38 +117,41 @@ k_face_coefficients(Geom g, const float* __restrict__ U, const float* __restrict
     const float Gc = G[c];
     float ax = 0.f, bx = 0.f, cx = 0.f, ay = 0.f, by = 0.f, cy = 0.f, az = 0.f, bz = 0.f, cz = 0.f;
     if (i >= 1) {
-        const float u = U[c], GG = Gc + G[c - 1];
-        ax = 0.5f * (fabsf(u) * (1.f - fabsf(u) / (0.5f * GG)));
-        if (jin) bx = 0.5f * (0.5f * u * (0.25f * (V[c] + V[c + ps] + V[c - 1] + V[c - 1 + ps]))) / GG;
-        if (kin) cx = 0.5f * (0.5f * u * (0.25f * (Wn[c] + Wn[c - ld] + Wn[c - 1] + Wn[c - 1 - ld]))) / GG;
+        const float u = U[c], GG = Gc + G[c - 1], rGG = fdiv(1.f, GG);
+        ax = 0.5f * (fabsf(u) * (1.f - fabsf(u) * (2.f * rGG)));
+        if (jin) bx = 0.5f * (0.5f * u * (0.25f * (V[c] + V[c + ps] + V[c - 1] + V[c - 1 + ps]))) * rGG;
+        if (kin) cx = 0.5f * (0.5f * u * (0.25f * (Wn[c] + Wn[c - ld] + Wn[c - 1] + Wn[c - 1 - ld]))) * rGG;
     }
     if (j >= 1) {
-        const float v = V[c], GG = Gc + G[c - ps];
-        ay = 0.5f * (fabsf(v) * (1.f - fabsf(v) / (0.5f * GG)));
-        if (iin) by = 0.5f * (0.5f * v * (0.25f * (U[c + 1] + U[c + 1 - ps] + U[c] + U[c - ps]))) / GG;
-        if (kin) cy = 0.5f * (0.5f * v * (0.25f * (Wn[c] + Wn[c - ld] + Wn[c - ps] + Wn[c - ld - ps]))) / GG;
+        const float v = V[c], GG = Gc + G[c - ps], rGG = fdiv(1.f, GG);
+        ay = 0.5f * (fabsf(v) * (1.f - fabsf(v) * (2.f * rGG)));
+        if (iin) by = 0.5f * (0.5f * v * (0.25f * (U[c + 1] + U[c + 1 - ps] + U[c] + U[c - ps]))) * rGG;
+        if (kin) cy = 0.5f * (0.5f * v * (0.25f * (Wn[c] + Wn[c - ld] + Wn[c - ps] + Wn[c - ld - ps]))) * rGG;
     }
     if (k < g.nz - 1) {
-        const float w = Wn[c], GG = G[c + ld] + Gc, hdz = 0.5f * dz[c];
-        az = hdz * (fabsf(w) * (1.f - fabsf(w) / (0.5f * GG)));
-        if (iin) bz = hdz * (0.5f * w * (0.25f * (U[c + 1] + U[c + 1 + ld] + U[c] + U[c + ld]))) / GG;
-        if (jin) cz = hdz * (0.5f * w * (0.25f * (V[c] + V[c + ld] + V[c + ps] + V[c + ld + ps]))) / GG;
+        const float w = Wn[c], GG = G[c + ld] + Gc, hdz = 0.5f * dz[c], rGG = fdiv(1.f, GG);
+        az = hdz * (fabsf(w) * (1.f - fabsf(w) * (2.f * rGG)));
+        if (iin) bz = hdz * (0.5f * w * (0.25f * (U[c + 1] + U[c + 1 + ld] + U[c] + U[c + ld]))) * rGG;
+        if (jin) cz = hdz * (0.5f * w * (0.25f * (V[c] + V[c + ld] + V[c + ps] + V[c + ld + ps]))) * rGG;
     }
     co.ax[c] = ax; co.bx[c] = bx; co.cx[c] = cx;
     co.ay[c] = ay; co.by[c] = by; co.cy[c] = cy;
     co.az[c] = az; co.bz[c] = bz; co.cz[c] = cz;
-    co.rj[c] = 1.f / Gc;                 // rho == 1 on this path (advect_density = .false.): G == jaco
-    co.rjz[c] = 1.f / (dz[c] * Gc);
+    co.rj[c] = fdiv(1.f, Gc);                 // rho == 1 on this path (advect_density = .false.): G == jaco
+    co.rjz[c] = fdiv(1.f, dz[c] * Gc);
 }
 
 // ---------------------------------------------------------------------------------------------
 // The fused corrector.  blockDim = (32, NZT); thread (tx, tz) owns cells (i, CPT*tz + c), c < CPT.
 // ---------------------------------------------------------------------------------------------
-template <int CPT, int MAXT>
-__global__ void __launch_bounds__(MAXT)
+// NZP = number of level slots per staged box (>= nz, multiple of CPT): compile-time, so that every
+// shared-memory address below is base register + immediate.
+template <int CPT, int NZP>
+__global__ void __launch_bounds__(TW * (NZP / CPT))
 k_corrector_fused(const Geom g, const OutSet outs, const __grid_constant__ FusedMaps maps, const int chunk) {
     extern __shared__ __align__(128) unsigned char smraw[];
-    const int tx = threadIdx.x, tz = threadIdx.y, nzt = blockDim.y;
+    constexpr int nzt = NZP / CPT;
+    const int tx = threadIdx.x, tz = threadIdx.y;
     const int scalar = blockIdx.x % outs.n, xt = blockIdx.x / outs.n;
     float* __restrict__ gout = outs.out[scalar];
     const int nx = g.nx, nz = g.nz, ny = g.ny;
@@ -163,18 +166,18 @@ k_corrector_fused(const Geom g, const OutSet outs, const __grid_constant__ Fused
     const int ja = 1 + blockIdx.y * chunk;            // first output plane of this chunk
     const int jb = min(ja + chunk, ny - 1);           // one past the last output plane
     const int k0 = tz * CPT;
-    const int box = nz * TW;                          // floats per staged box
+    constexpr int box = NZP * TW;                     // floats per staged box slot (TMA fills nz rows of it)
 
     // ---- shared memory carve-up
     enum { R_QLO, R_QHI, R_MHLO, R_MHHI, R_MLLO, R_MLHI, R_FZHI, R_BILO, R_BOLO, R_FLHI, R_COUNT };
     float* rows = reinterpret_cast<float*>(smraw);
-    const int rows_floats = ((2 * R_COUNT * (nzt + 2) * TW + 31) / 32) * 32;
+    constexpr int rows_floats = 2 * R_COUNT * (nzt + 2) * TW;
     float* stage0 = rows + rows_floats;               // [2][NF][nz][32]
     uint64_t* mbar = reinterpret_cast<uint64_t*>(stage0 + 2 * NF * box);
     auto row = [&](int buf, int kind, int z) -> float& { return rows[((buf * R_COUNT + kind) * (nzt + 2) + (z + 1)) * TW + tx]; };
     const int tid = tz * TW + tx;
     const int niter = jb - ja + 4;                    // planes ja-2 .. jb+1
-    const uint32_t stage_bytes = (uint32_t)(NF * box * sizeof(float));
+    const uint32_t stage_bytes = (uint32_t)(NF * nz * TW * sizeof(float));   // bytes TMA delivers per stage
 
     auto issue = [&](int it) {                        // thread 0: fetch the 13 boxes of iteration `it`
         const int P = ja - 2 + it, st = it & 1;
@@ -193,6 +196,9 @@ k_corrector_fused(const Geom g, const OutSet outs, const __grid_constant__ Fused
         mbar_init(&mbar[1], 1);
         fence_barrier_init();
     }
+    // level slots nz..NZP-1 of every box are never written by TMA: zero them once so that the
+    // (non-existent) cells above the model top read as 0 without a predicate
+    for (int t = tid; t < 2 * NF * box; t += TW * nzt) stage0[t] = 0.f;
     // rows of the (non-existent) threads below tz=0 and above tz=nzt-1 read as "no neighbour"
     if (tz == 0) {
         for (int b = 0; b < 2; ++b) {
@@ -246,13 +252,12 @@ k_corrector_fused(const Geom g, const OutSet outs, const __grid_constant__ Fused
             a[c][0] = a[c][1]; a[c][1] = a[c][2]; a[c][2] = a[c][3];
             mh[c][0] = mh[c][1]; mh[c][1] = mh[c][2];
             ml[c][0] = ml[c][1]; ml[c][1] = ml[c][2];
-            const bool lev = (k0 + c < nz);
-            const bool cell = pin && col && lev;
-            const float q2v = lev ? sg[F_Q2 * box + c * TW] : 0.f;       // TMA zero-fills outside the domain
-            const float lv = lev ? sg[F_L * box + c * TW] : 0.f;
-            cay[c] = lev ? sg[F_AY * box + c * TW] : 0.f;
-            cby[c] = lev ? sg[F_BY * box + c * TW] : 0.f;
-            ccy[c] = lev ? sg[F_CY * box + c * TW] : 0.f;
+            const bool cell = pin && col && (k0 + c < nz);
+            const float q2v = sg[F_Q2 * box + c * TW];                   // TMA zero-fills outside the domain
+            const float lv = sg[F_L * box + c * TW];
+            cay[c] = sg[F_AY * box + c * TW];
+            cby[c] = sg[F_BY * box + c * TW];
+            ccy[c] = sg[F_CY * box + c * TW];
             a[c][3] = q2v;
             mh[c][2] = cell ? fmaxf(q2v, lv) : -BIG;
             ml[c][2] = cell ? fminf(q2v, lv) : BIG;
@@ -269,12 +274,11 @@ k_corrector_fused(const Geom g, const OutSet outs, const __grid_constant__ Fused
             const float sx_bl = qbl[1] + lane_lo(qbl[1]);
 #pragma unroll
             for (int c = 0; c < CPT; ++c) {
-                const bool lev = (k0 + c < nz);
-                const float cax = lev ? sg[F_AX * box + c * TW] : 0.f, cbx = lev ? sg[F_BX * box + c * TW] : 0.f,
-                            ccx = lev ? sg[F_CX * box + c * TW] : 0.f, caz = lev ? sg[F_AZ * box + c * TW] : 0.f,
-                            cbz = lev ? sg[F_BZ * box + c * TW] : 0.f, ccz = lev ? sg[F_CZ * box + c * TW] : 0.f;
-                rj[c] = lev ? sg[F_RJ * box + c * TW] : 0.f;
-                rjz[c] = lev ? sg[F_RJZ * box + c * TW] : 0.f;
+                const float cax = sg[F_AX * box + c * TW], cbx = sg[F_BX * box + c * TW],
+                            ccx = sg[F_CX * box + c * TW], caz = sg[F_AZ * box + c * TW],
+                            cbz = sg[F_BZ * box + c * TW], ccz = sg[F_CZ * box + c * TW];
+                rj[c] = sg[F_RJ * box + c * TW];
+                rjz[c] = sg[F_RJZ * box + c * TW];
                 const float q = a[c][1];
                 const float ql = lane_lo(q);
                 const float qu = (c + 1 < CPT) ? a[(c + 1 < CPT) ? c + 1 : c][1] : qab[1];
@@ -501,6 +505,27 @@ int env_int(const char* name, int dflt) {
 
 }  // namespace
 
+// Which instantiation serves nz levels, and its dynamic shared memory: 2 x 10 exchange rows of
+// (nzt+2) x 32 floats, 2 stages of 13 boxes of NZP x 32 floats, 2 mbarriers.
+FusedPlan fused_plan(const Geom& g) {
+    FusedPlan p{};
+    if (g.nz < 2 || g.nz > 48 || g.nx < 3 || g.ny < 3) return p;
+    if (g.nz <= 20) { p.cpt = 2; p.nzp = 20; }
+    else if (g.nz <= 40) { p.cpt = 2; p.nzp = 40; }
+    else { p.cpt = 4; p.nzp = 48; }
+    if (env_int("ICAR_FUSED_CPT", 0) == 4) { p.cpt = 4; p.nzp = 48; }
+    const int nzt = p.nzp / p.cpt;
+    p.smem = (size_t)(2 * 10 * (nzt + 2) * TW + 2 * NF * p.nzp * TW) * sizeof(float) + 16;
+    int dev = 0, max_optin = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess ||
+        cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess) {
+        (void)cudaGetLastError();
+        return p;
+    }
+    p.ok = p.smem <= (size_t)max_optin;
+    return p;
+}
+
 int fused_advect_all(const Geom& g, const ScalarSet& s, const float* U, const float* V, const float* W,
                      const float* Wn, const float* jaco, const float* dz, const FusedCoef& co,
                      cudaStream_t st) {
@@ -522,9 +547,8 @@ int fused_advect_all(const Geom& g, const ScalarSet& s, const float* U, const fl
     for (int f = 0; f < 11; ++f)
         if (!field_map(g, cf[f], &maps.coef[f])) return -1;
 
-    int cpt = env_int("ICAR_FUSED_CPT", 4);
-    if (cpt != 2 || g.nz > 40) cpt = 4;
-    const int nzt = (g.nz + cpt - 1) / cpt;
+    FusedPlan plan = fused_plan(g);
+    if (!plan.ok) return -1;
     const int xtiles = g.nx / TOUT + 1;               // outputs of tile xt: columns 28*xt-2 .. 28*xt+25
     // y-chunks: pick the split that wastes least (partial last wave of 148 SMs vs. the 4 warm-up
     // planes each chunk re-reads); one CTA per SM is resident (shared-memory bound)
@@ -540,19 +564,19 @@ int fused_advect_all(const Geom& g, const ScalarSet& s, const float* U, const fl
     }
     const int chunk = (planes + best - 1) / best;
     const int chunks = (planes + chunk - 1) / chunk;
-    const int rows_floats = ((2 * 10 * (nzt + 2) * TW + 31) / 32) * 32;
-    const size_t smem = (size_t)rows_floats * sizeof(float) + (size_t)2 * NF * g.nz * TW * sizeof(float) + 16;
     dim3 grid(xtiles * s.n, chunks);
-    dim3 block(TW, nzt);
-    if (cpt == 2) {
-        auto kern = k_corrector_fused<2, 640>;
-        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
-        kern<<<grid, block, smem, st>>>(g, outs, maps, chunk);
-    } else {
-        auto kern = k_corrector_fused<4, 512>;
-        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
-        kern<<<grid, block, smem, st>>>(g, outs, maps, chunk);
+    dim3 block(TW, plan.nzp / plan.cpt);
+#define LAUNCH_FUSED(C, Z)                                                                                    \
+    {                                                                                                         \
+        auto kern = k_corrector_fused<C, Z>;                                                                  \
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem) !=        \
+            cudaSuccess) { (void)cudaGetLastError(); return -1; }                                             \
+        kern<<<grid, block, plan.smem, st>>>(g, outs, maps, chunk);                                           \
     }
+    if (plan.cpt == 2 && plan.nzp == 20) LAUNCH_FUSED(2, 20)
+    else if (plan.cpt == 2 && plan.nzp == 40) LAUNCH_FUSED(2, 40)
+    else LAUNCH_FUSED(4, 48)
+#undef LAUNCH_FUSED
     ++launches;
     return launches;
 }

@@ -23,7 +23,8 @@ __global__ void k_wind_normalise(Geom g, const R* __restrict__ u, const R* __res
                                  const R* __restrict__ w, const R* __restrict__ ju,
                                  const R* __restrict__ jv, const R* __restrict__ jw,
                                  const R* __restrict__ rho, R dt, R dx, int scheme,
-                                 R* __restrict__ U, R* __restrict__ V, R* __restrict__ W) {
+                                 R* __restrict__ U, R* __restrict__ V, R* __restrict__ W,
+                                 const R* __restrict__ dz, R* __restrict__ Wn) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     int k = blockIdx.y, j = blockIdx.z;
     if (i >= g.nx) return;
@@ -47,6 +48,7 @@ __global__ void k_wind_normalise(Geom g, const R* __restrict__ u, const R* __res
     U[c] = Uv;
     V[c] = Vv;
     W[c] = Wv;
+    if (Wn) Wn[c] = Wv / dz[c];          // the (W_m/dz) temporary of adv_mpdata.f90:379
 }
 
 // (W_m/dz) and (jaco*rho), the array temporaries of adv_mpdata.f90:379
@@ -294,6 +296,7 @@ __global__ void k_corrector(Geom g, const R* __restrict__ l, const R* __restrict
 // ---------------------------------------------------------------------------------------------
 // Pass 1 for all scalars (same arithmetic, bit for bit, as k_upwind above; this file is built with -fmad=false).
 // ---------------------------------------------------------------------------------------------
+template <int N>
 __global__ void __launch_bounds__(128)
 k_upwind_all(Geom g, ScalarSet s, const float* __restrict__ U, const float* __restrict__ V,
              const float* __restrict__ W, const float* __restrict__ dz, const float* __restrict__ jaco) {
@@ -302,28 +305,36 @@ k_upwind_all(Geom g, ScalarSet s, const float* __restrict__ U, const float* __re
     if (i >= g.nx) return;
     const size_t c = g.at(i, k, j);
     if (i == 0 || i == g.nx - 1 || j == 0 || j == g.ny - 1) {
-#pragma unroll 1
-        for (int n = 0; n < s.n; ++n) { const float v = s.q[n][c]; s.q2[n][c] = v; s.out[n][c] = v; }
+#pragma unroll
+        for (int n = 0; n < N; ++n) { const float v = s.q[n][c]; s.q2[n][c] = v; s.out[n][c] = v; }
         return;
     }
     const size_t ps = g.ps();
     const int ld = g.ld;
+    const bool bottom = (k == 0), top = (k == g.nz - 1), flat = (g.nz == 1);
+    // all loads of all scalars are issued before the first use (35 independent loads in flight)
+    float qc[N], qxm[N], qxp[N], qym[N], qyp[N], qzm[N], qzp[N];
+#pragma unroll
+    for (int n = 0; n < N; ++n) {
+        const float* __restrict__ qin = s.q[n];
+        qc[n] = qin[c]; qxm[n] = qin[c - 1]; qxp[n] = qin[c + 1];
+        qym[n] = qin[c - ps]; qyp[n] = qin[c + ps];
+        qzm[n] = bottom ? 0.f : qin[c - ld];
+        qzp[n] = top ? 0.f : qin[c + ld];
+    }
     const float uxm = U[c], uxp = U[c + 1], vym = V[c], vyp = V[c + ps];
-    const float wzp = W[c], wzm = (k > 0) ? W[c - ld] : 0.f;
+    const float wzp = W[c], wzm = bottom ? 0.f : W[c - ld];
     const float jc = jaco[c];
     const float den = dz[c] * jc;
-    const bool bottom = (k == 0), top = (k == g.nz - 1), flat = (g.nz == 1);
-#pragma unroll 1
-    for (int n = 0; n < s.n; ++n) {
-        const float* __restrict__ qin = s.q[n];
-        const float qc = qin[c];
-        const float fxm = donor(uxm, qin[c - 1], qc), fxp = donor(uxp, qc, qin[c + 1]);
-        const float fym = donor(vym, qin[c - ps], qc), fyp = donor(vyp, qc, qin[c + ps]);
-        float val = qc - ((fxp - fxm) + (fyp - fym)) / jc;
+#pragma unroll
+    for (int n = 0; n < N; ++n) {
+        const float fxm = donor(uxm, qxm[n], qc[n]), fxp = donor(uxp, qc[n], qxp[n]);
+        const float fym = donor(vym, qym[n], qc[n]), fyp = donor(vyp, qc[n], qyp[n]);
+        float val = qc[n] - ((fxp - fxm) + (fyp - fym)) / jc;
         if (!flat) {
-            if (bottom)   val = val - donor(wzp, qc, qin[c + ld]) / den;
-            else if (top) val = val - (qc * wzp - donor(wzm, qin[c - ld], qc)) / den;
-            else          val = val - (donor(wzp, qc, qin[c + ld]) - donor(wzm, qin[c - ld], qc)) / den;
+            if (bottom)   val = val - donor(wzp, qc[n], qzp[n]) / den;
+            else if (top) val = val - (qc[n] * wzp - donor(wzm, qzm[n], qc[n])) / den;
+            else          val = val - (donor(wzp, qc[n], qzp[n]) - donor(wzm, qzm[n], qc[n])) / den;
         }
         s.q2[n][c] = val;
     }
@@ -339,16 +350,31 @@ static inline dim3 cell_grid(const Geom& g, int bx) {
 
 int staged_upwind_all(const Geom& g, const ScalarSet& s, const float* U, const float* V, const float* W,
                       const float* dz, const float* jaco, cudaStream_t st) {
-    k_upwind_all<<<cell_grid(g, 128), 128, 0, st>>>(g, s, U, V, W, dz, jaco);
-    return 1;
+    dim3 grid = cell_grid(g, 128);
+    int done = 0, launches = 0;
+    while (done < s.n) {                 // batches of up to 5 scalars share the wind / metric loads
+        ScalarSet b;
+        b.n = (s.n - done >= 5) ? 5 : (s.n - done);
+        for (int n = 0; n < b.n; ++n) { b.q[n] = s.q[done + n]; b.q2[n] = s.q2[done + n]; b.out[n] = s.out[done + n]; }
+        switch (b.n) {
+            case 5: k_upwind_all<5><<<grid, 128, 0, st>>>(g, b, U, V, W, dz, jaco); break;
+            case 4: k_upwind_all<4><<<grid, 128, 0, st>>>(g, b, U, V, W, dz, jaco); break;
+            case 3: k_upwind_all<3><<<grid, 128, 0, st>>>(g, b, U, V, W, dz, jaco); break;
+            case 2: k_upwind_all<2><<<grid, 128, 0, st>>>(g, b, U, V, W, dz, jaco); break;
+            default: k_upwind_all<1><<<grid, 128, 0, st>>>(g, b, U, V, W, dz, jaco); break;
+        }
+        done += b.n;
+        ++launches;
+    }
+    return launches;
 }
 
 template <class R>
 int staged_wind_normalise(const Geom& g, const R* u, const R* v, const R* w, const R* ju,
                           const R* jv, const R* jw, const R* rho, R dt, R dx, int scheme, R* U,
-                          R* V, R* W, cudaStream_t st) {
+                          R* V, R* W, cudaStream_t st, const R* dz, R* Wn) {
     k_wind_normalise<R><<<cell_grid(g, 128), 128, 0, st>>>(g, u, v, w, ju, jv, jw, rho, dt, dx,
-                                                            scheme, U, V, W);
+                                                            scheme, U, V, W, dz, Wn);
     return 1;
 }
 
@@ -396,7 +422,7 @@ int staged_advect3d(const Geom& g, R* q, const R* rho, const R* jaco, const R* d
 #define INSTANTIATE(R)                                                                             \
     template int staged_wind_normalise<R>(const Geom&, const R*, const R*, const R*, const R*,     \
                                           const R*, const R*, const R*, R, R, int, R*, R*, R*,     \
-                                          cudaStream_t);                                           \
+                                          cudaStream_t, const R*, R*);                                           \
     template int staged_wn_G<R>(const Geom&, const R*, const R*, const R*, const R*, R*, R*,       \
                                 cudaStream_t);                                                     \
     template int staged_advect3d<R>(const Geom&, R*, const R*, const R*, const R*, const R*,       \

@@ -173,6 +173,16 @@ int icar_timer_stop(icar_ctx* ctx, float* elapsed_ms);
 
 /* ------------------------------------------------- multi-image (one process per GPU) */
 
+/* Which local columns (0-based offsets from ims) one image exchanges with its x neighbours, for
+ * `halo_size` = h columns per side -- exchangeable_obj.f90:303-356 restated as index ranges:
+ *   plan[0] first column SENT west   (put_west:           data(start+h : start+2h-1))
+ *   plan[1] first column SENT east   (put_east:           data(n-2h+1 : n-h))
+ *   plan[2] first column RECEIVED from the west (retrieve_west_halo: data(start : start+h-1))
+ *   plan[3] first column RECEIVED from the east (retrieve_east_halo: data(n-h+1 : n))
+ *   plan[4] 1 if a west neighbour exists, plan[5] 1 if an east neighbour exists.
+ * Pure host function (no GPU needed); icar_halo_send / icar_halo_retrieve use the same plan. */
+int icar_halo_plan(const icar_grid* grid, int image, int nimages, int plan[6]);
+
 /* ncclUniqueId bootstrap: image 1 calls icar_comm_unique_id and broadcasts the 128 bytes with
  * whatever the host program already has (coarray co_broadcast, MPI, torch.distributed); then
  * every image calls icar_comm_init.  Replaces exchangeable_t%set_neighbors
