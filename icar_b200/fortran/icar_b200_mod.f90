@@ -1,0 +1,274 @@
+!> ----------------------------------------------------------------------------
+!!  iso_c_binding shim over libicar_b200 (include/icar_b200.h).
+!!
+!!  Drop-in for ICAR's advection and microphysics plugins: it exports the same
+!!  three procedures per family the reference uses
+!!      adv_init / adv_var_request / advect      (src/physics/advection_driver.f90)
+!!      mp_init  / mp_var_request  / mp          (src/physics/mp_driver.f90)
+!!  so that src/main/init.f90 and src/main/time_step.f90 only have to `use` this
+!!  module instead of `advection` / `microphysics`.
+!!
+!!  NOTE: no Fortran compiler exists in the build image of this repository, so this
+!!  file is delivered as source that has NOT been compiled here; it is kept
+!!  deliberately thin (interfaces + pointer plumbing).  The C ABI it binds is
+!!  exercised from Python/ctypes with the same column-major (i,k,j) buffers.
+!!
+!!  Resident mode: fields are uploaded once (static metric terms in adv_init, state
+!!  at the first step), stay on the GPU across steps and are downloaded by
+!!  b200_sync_to_host before output / restart (driver.f90:169-195).
+!! ----------------------------------------------------------------------------
+module icar_b200_mod
+    use, intrinsic :: iso_c_binding
+    use data_structures
+    use icar_constants
+    use options_interface, only : options_t
+    use domain_interface,  only : domain_t
+    ! variable requests are unchanged: reuse the reference's own
+    use adv_upwind,        only : upwind_var_request
+    use module_mp_simple,  only : mp_simple_var_request
+    implicit none
+    private
+    public :: adv_init, adv_var_request, advect
+    public :: mp_init, mp_var_request, mp
+    public :: b200_halo_send, b200_halo_retrieve, b200_sync_to_host, b200_finalize
+
+    ! enum icar_var
+    integer(c_int), parameter :: VAR_U=0, VAR_V=1, VAR_W=2, VAR_PRESSURE=3, VAR_EXNER=4, VAR_DENSITY=5, &
+        VAR_TH=6, VAR_QV=7, VAR_QC=8, VAR_QR=9, VAR_QS=10, VAR_JACOBIAN=11, VAR_JACOBIAN_U=12,       &
+        VAR_JACOBIAN_V=13, VAR_JACOBIAN_W=14, VAR_ADVECTION_DZ=15, VAR_DZ_MASS=16, VAR_PRECIP=17,     &
+        VAR_SNOWFALL=18
+
+    type, bind(c) :: icar_grid
+        integer(c_int) :: ims, ime, kms, kme, jms, jme
+        integer(c_int) :: its, ite, kts, kte, jts, jte
+        integer(c_int) :: ids, ide, kds, kde, jds, jde
+        integer(c_int) :: halo_size
+    end type
+
+    type, bind(c) :: icar_options
+        integer(c_int) :: advection, microphysics, mpdata_order, flux_corrected_transport
+        integer(c_int) :: advect_density, update_interval, top_mp_level
+        real(c_float)  :: dx
+        integer(c_int) :: exact_arithmetic
+    end type
+
+    interface
+        subroutine icar_default_options(opt) bind(c)
+            import :: icar_options
+            type(icar_options), intent(out) :: opt
+        end subroutine
+        integer(c_int) function icar_create(device, grid, opt, ctx) bind(c)
+            import :: c_int, c_ptr, icar_grid, icar_options
+            integer(c_int), value :: device
+            type(icar_grid), intent(in) :: grid
+            type(icar_options), intent(in) :: opt
+            type(c_ptr), intent(out) :: ctx
+        end function
+        integer(c_int) function icar_destroy(ctx) bind(c)
+            import :: c_int, c_ptr
+            type(c_ptr), value :: ctx
+        end function
+        type(c_ptr) function icar_last_error(ctx) bind(c)
+            import :: c_ptr
+            type(c_ptr), value :: ctx
+        end function
+        integer(c_int) function icar_upload(ctx, var, host) bind(c)
+            import :: c_int, c_ptr
+            type(c_ptr), value :: ctx
+            integer(c_int), value :: var
+            type(c_ptr), value :: host
+        end function
+        integer(c_int) function icar_download(ctx, var, host) bind(c)
+            import :: c_int, c_ptr
+            type(c_ptr), value :: ctx
+            integer(c_int), value :: var
+            type(c_ptr), value :: host
+        end function
+        integer(c_int) function icar_set_model_time(ctx, seconds) bind(c)
+            import :: c_int, c_ptr, c_double
+            type(c_ptr), value :: ctx
+            real(c_double), value :: seconds
+        end function
+        integer(c_int) function icar_advect(ctx, dt) bind(c)
+            import :: c_int, c_ptr, c_float
+            type(c_ptr), value :: ctx
+            real(c_float), value :: dt
+        end function
+        integer(c_int) function icar_mp(ctx, dt_in, halo, subset) bind(c)
+            import :: c_int, c_ptr, c_float
+            type(c_ptr), value :: ctx
+            real(c_float), value :: dt_in
+            integer(c_int), value :: halo, subset
+        end function
+        integer(c_int) function icar_halo_send(ctx) bind(c)
+            import :: c_int, c_ptr
+            type(c_ptr), value :: ctx
+        end function
+        integer(c_int) function icar_halo_retrieve(ctx) bind(c)
+            import :: c_int, c_ptr
+            type(c_ptr), value :: ctx
+        end function
+        integer(c_int) function icar_comm_unique_id(id) bind(c)
+            import :: c_int, c_char
+            character(kind=c_char) :: id(128)
+        end function
+        integer(c_int) function icar_comm_init(ctx, image, nimages, id) bind(c)
+            import :: c_int, c_ptr, c_char
+            type(c_ptr), value :: ctx
+            integer(c_int), value :: image, nimages
+            character(kind=c_char), intent(in) :: id(128)
+        end function
+    end interface
+
+    type(c_ptr), save :: ctx = c_null_ptr
+    logical, save :: state_on_device = .false.
+
+contains
+
+    subroutine check(rc, where)
+        integer(c_int), intent(in) :: rc
+        character(len=*), intent(in) :: where
+        if (rc /= 0) then
+            write(*,*) "icar_b200 error ", rc, " in ", where
+            error stop "icar_b200"          ! the reference's own error convention (time_step.f90:322-328)
+        endif
+    end subroutine
+
+    subroutine up3(var, a)
+        integer(c_int), intent(in) :: var
+        real, intent(in), target, contiguous :: a(:,:,:)
+        call check(icar_upload(ctx, var, c_loc(a)), "icar_upload")
+    end subroutine
+
+    subroutine down3(var, a)
+        integer(c_int), intent(in) :: var
+        real, intent(inout), target, contiguous :: a(:,:,:)
+        call check(icar_download(ctx, var, c_loc(a)), "icar_download")
+    end subroutine
+
+    !> advection_driver.f90:39-49
+    subroutine adv_var_request(options)
+        type(options_t), intent(inout) :: options
+        call upwind_var_request(options)
+    end subroutine
+
+    !> advection_driver.f90:24-37: creates the GPU context for this image's tile and uploads the
+    !! static metric terms (jacobians, advection_dz, dz_mass) once.
+    subroutine adv_init(domain, options)
+        type(domain_t),  intent(in) :: domain
+        type(options_t), intent(in) :: options
+        type(icar_grid)    :: g
+        type(icar_options) :: o
+        character(kind=c_char) :: id(128)
+
+        g%ims = domain%grid%ims; g%ime = domain%grid%ime; g%kms = domain%grid%kms; g%kme = domain%grid%kme
+        g%jms = domain%grid%jms; g%jme = domain%grid%jme
+        g%its = domain%grid%its; g%ite = domain%grid%ite; g%kts = domain%grid%kts; g%kte = domain%grid%kte
+        g%jts = domain%grid%jts; g%jte = domain%grid%jte
+        g%ids = domain%grid%ids; g%ide = domain%grid%ide; g%kds = domain%grid%kds; g%kde = domain%grid%kde
+        g%jds = domain%grid%jds; g%jde = domain%grid%jde
+        g%halo_size = domain%grid%halo_size
+
+        call icar_default_options(o)
+        o%advection    = options%physics%advection
+        o%microphysics = options%physics%microphysics
+        o%mpdata_order = options%adv_options%mpdata_order
+        o%flux_corrected_transport = merge(1, 0, options%adv_options%flux_corrected_transport)
+        o%advect_density  = merge(1, 0, options%parameters%advect_density)
+        o%update_interval = options%mp_options%update_interval
+        o%top_mp_level    = options%mp_options%top_mp_level
+        o%dx = domain%dx
+
+        ! one image = one GPU of the node
+        call check(icar_create(mod(this_image()-1, 8), g, o, ctx), "icar_create")
+
+        if (num_images() > 1) then          ! x-slab decompositions only (yimages == 1)
+            if (this_image() == 1) call check(icar_comm_unique_id(id), "icar_comm_unique_id")
+            call co_broadcast(id, 1)
+            call check(icar_comm_init(ctx, this_image(), num_images(), id), "icar_comm_init")
+        endif
+
+        call up3(VAR_JACOBIAN,     domain%jacobian)
+        call up3(VAR_JACOBIAN_U,   domain%jacobian_u)
+        call up3(VAR_JACOBIAN_V,   domain%jacobian_v)
+        call up3(VAR_JACOBIAN_W,   domain%jacobian_w)
+        call up3(VAR_ADVECTION_DZ, domain%advection_dz)
+        call up3(VAR_DZ_MASS,      domain%dz_mass%data_3d)
+    end subroutine
+
+    !> mp_driver.f90:200-237 (only the schemes this library builds)
+    subroutine mp_var_request(options)
+        type(options_t), intent(inout) :: options
+        if (options%physics%microphysics == kMP_SB04) call mp_simple_var_request(options)
+    end subroutine
+
+    !> mp_driver.f90:74-198: nothing to do for mp_simple; the context exists since adv_init
+    subroutine mp_init(options)
+        type(options_t), intent(in) :: options
+    end subroutine
+
+    !> uploads the fields the host side changes between steps (diagnostic_update, apply_forcing)
+    subroutine sync_to_device(domain)
+        type(domain_t), intent(inout) :: domain
+        call up3(VAR_U, domain%u%data_3d);  call up3(VAR_V, domain%v%data_3d);  call up3(VAR_W, domain%w%data_3d)
+        call up3(VAR_PRESSURE, domain%pressure%data_3d)
+        call up3(VAR_EXNER,    domain%exner%data_3d)
+        call up3(VAR_DENSITY,  domain%density%data_3d)
+        if (.not. state_on_device) then
+            call up3(VAR_TH, domain%potential_temperature%data_3d)
+            call up3(VAR_QV, domain%water_vapor%data_3d)
+            call up3(VAR_QC, domain%cloud_water_mass%data_3d)
+            call up3(VAR_QR, domain%rain_mass%data_3d)
+            call up3(VAR_QS, domain%snow_mass%data_3d)
+            state_on_device = .true.
+        endif
+        call check(icar_set_model_time(ctx, domain%model_time%seconds()), "icar_set_model_time")
+    end subroutine
+
+    !> mp(domain, options, dt_in, halo, subset) -- mp_driver.f90:673
+    subroutine mp(domain, options, dt_in, halo, subset)
+        type(domain_t),  intent(inout) :: domain
+        type(options_t), intent(in)    :: options
+        real,            intent(in)    :: dt_in
+        integer,         intent(in), optional :: halo, subset
+        integer(c_int) :: h, s
+        h = -1; s = -1
+        if (present(halo))   h = halo
+        if (present(subset)) s = subset
+        if (present(halo) .or. (.not.present(subset))) call sync_to_device(domain)   ! first mp call of the step
+        call check(icar_mp(ctx, dt_in, h, s), "icar_mp")
+    end subroutine
+
+    !> domain%halo_send / halo_retrieve (domain_obj.f90:104-144) for the device-resident scalars
+    subroutine b200_halo_send()
+        call check(icar_halo_send(ctx), "icar_halo_send")
+    end subroutine
+    subroutine b200_halo_retrieve()
+        call check(icar_halo_retrieve(ctx), "icar_halo_retrieve")
+    end subroutine
+
+    !> advect(domain, options, dt) -- advection_driver.f90:51
+    subroutine advect(domain, options, dt)
+        type(domain_t),  intent(inout) :: domain
+        type(options_t), intent(in)    :: options
+        real,            intent(in)    :: dt
+        call check(icar_advect(ctx, dt), "icar_advect")
+    end subroutine
+
+    !> before output / restart / any host physics that reads the scalars
+    subroutine b200_sync_to_host(domain)
+        type(domain_t), intent(inout) :: domain
+        call down3(VAR_TH, domain%potential_temperature%data_3d)
+        call down3(VAR_QV, domain%water_vapor%data_3d)
+        call down3(VAR_QC, domain%cloud_water_mass%data_3d)
+        call down3(VAR_QR, domain%rain_mass%data_3d)
+        call down3(VAR_QS, domain%snow_mass%data_3d)
+        call check(icar_download(ctx, VAR_PRECIP,   c_loc(domain%accumulated_precipitation%data_2dd)), "icar_download")
+        call check(icar_download(ctx, VAR_SNOWFALL, c_loc(domain%accumulated_snowfall%data_2dd)), "icar_download")
+    end subroutine
+
+    subroutine b200_finalize()
+        if (c_associated(ctx)) call check(icar_destroy(ctx), "icar_destroy")
+        ctx = c_null_ptr
+    end subroutine
+end module icar_b200_mod

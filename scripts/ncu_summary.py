@@ -1,0 +1,71 @@
+"""Text summary of one kernel from an `ncu --set full` report: key raw metrics + SASS opcode mix.
+usage: python scripts/ncu_summary.py report.ncu-rep cells_processed > profiles/xxx.txt"""
+import collections
+import csv
+import io
+import re
+import subprocess
+import sys
+
+KEYS = [
+    "gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "launch__registers_per_thread",
+    "launch__waves_per_multiprocessor", "launch__occupancy_limit_registers", "launch__occupancy_limit_shared_mem",
+    "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
+    "sm__throughput.avg.pct_of_peak_sustained_elapsed", "sm__warps_active.avg.pct_of_peak_sustained_active",
+    "smsp__inst_executed.sum", "smsp__issue_active.avg.pct_of_peak_sustained_active",
+    "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active",
+    "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active",
+    "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active",
+    "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active",
+    "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active",
+    "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed",
+    "lts__t_sector_hit_rate.pct",
+]
+
+
+def ncu(rep, page):
+    out = subprocess.run(["ncu", "-i", rep, "--page", page, "--csv"], capture_output=True, text=True).stdout
+    return list(csv.reader(io.StringIO(out)))
+
+
+def main():
+    rep = sys.argv[1]
+    cells = float(sys.argv[2]) if len(sys.argv) > 2 else None
+    raw = ncu(rep, "raw")
+    hdr, units, vals = raw[0], raw[1], raw[2]
+    d = dict(zip(hdr, zip(vals, units)))
+    print(f"# {rep}")
+    print(f"kernel: {d.get('Kernel Name', ('?', ''))[0]}")
+    for k in KEYS:
+        if k in d:
+            print(f"{k:80s} {d[k][0]:>16s} {d[k][1]}")
+    stalls = sorted(((float(v[0]), k) for k, v in d.items()
+                     if k.startswith("smsp__average_warps_issue_stalled") and k.endswith("_per_issue_active.ratio")),
+                    reverse=True)
+    print("top warp stall reasons (warps per issue-active cycle):")
+    for v, k in stalls[:6]:
+        print(f"  {k.split('issue_stalled_')[1].split('_per_issue')[0]:28s} {v:6.2f}")
+    src = ncu(rep, "source")
+    h = src[1]
+    ia, ie = h.index("Source"), h.index("Instructions Executed")
+    ops = collections.Counter()
+    for r in src[2:]:
+        if len(r) <= ie:
+            continue
+        m = re.match(r"(@!?U?P\d+\s+)?([A-Z0-9_.]+)", r[ia].strip())
+        if m:
+            ops[m.group(2).split(".")[0]] += int(r[ie] or 0)
+    tot = sum(ops.values())
+    print(f"SASS warp-instructions executed: {tot}")
+    if cells:
+        print(f"lane-instructions per cell: {tot * 32 / cells:.1f}")
+    print("opcode mix:")
+    for op, n in ops.most_common(16):
+        print(f"  {op:10s} {n / tot * 100:5.1f}%")
+    tma = [op for op in ops if op.startswith("UTMA") or op.startswith("SYNCS")]
+    if tma:
+        print("TMA / mbarrier opcodes present:", ", ".join(f"{t} x{ops[t]}" for t in tma))
+
+
+if __name__ == "__main__":
+    main()
