@@ -13,6 +13,7 @@
 #include <dlfcn.h>
 #include <nccl.h>
 
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -163,7 +164,7 @@ int alloc_cells(icar_ctx* ctx, float** p) {
 
 // staging buffer #slot with room for one padded field of `esize`-byte elements
 int get_scratch(icar_ctx* ctx, size_t slot, size_t esize, void** out) {
-    size_t need = (size_t)ctx->g.ldu * ctx->g.nz * (ctx->g.ny + 1) * esize;
+    size_t need = (size_t)std::max(ctx->g.ldu, ctx->g.ld) * ctx->g.nz * (ctx->g.ny + 1) * esize;
     if (ctx->scratch.size() <= slot) { ctx->scratch.resize(slot + 1, nullptr); ctx->scratch_bytes.resize(slot + 1, 0); }
     if (ctx->scratch_bytes[slot] < need) {
         if (ctx->scratch[slot]) CU(cudaFree(ctx->scratch[slot]));
@@ -177,14 +178,22 @@ int get_scratch(icar_ctx* ctx, size_t slot, size_t esize, void** out) {
 }
 
 // host (dense, reference layout) <-> device (padded rows)
+// (a dense field -- pitch == width, e.g. nx = 512 -- goes as ONE linear copy: a 2-D copy of 2 KB rows
+// runs at pageable-memory speed even from pinned memory)
 int copy_in(icar_ctx* ctx, void* dev, const void* host, int width, int pitch, size_t rows, size_t es) {
-    CU(cudaMemcpy2DAsync(dev, (size_t)pitch * es, host, (size_t)width * es, (size_t)width * es, rows,
-                         cudaMemcpyHostToDevice, ctx->stream));
+    if (pitch == width)
+        CU(cudaMemcpyAsync(dev, host, (size_t)width * es * rows, cudaMemcpyHostToDevice, ctx->stream));
+    else
+        CU(cudaMemcpy2DAsync(dev, (size_t)pitch * es, host, (size_t)width * es, (size_t)width * es, rows,
+                             cudaMemcpyHostToDevice, ctx->stream));
     return ICAR_OK;
 }
 int copy_out(icar_ctx* ctx, void* host, const void* dev, int width, int pitch, size_t rows, size_t es) {
-    CU(cudaMemcpy2DAsync(host, (size_t)width * es, dev, (size_t)pitch * es, (size_t)width * es, rows,
-                         cudaMemcpyDeviceToHost, ctx->stream));
+    if (pitch == width)
+        CU(cudaMemcpyAsync(host, dev, (size_t)width * es * rows, cudaMemcpyDeviceToHost, ctx->stream));
+    else
+        CU(cudaMemcpy2DAsync(host, (size_t)width * es, dev, (size_t)pitch * es, (size_t)width * es, rows,
+                             cudaMemcpyDeviceToHost, ctx->stream));
     return ICAR_OK;
 }
 
@@ -308,7 +317,7 @@ extern "C" int icar_create(int device, const icar_grid* grid, const icar_options
     ctx->opt = *opt;
     ctx->g.nx = nx; ctx->g.nz = nz; ctx->g.ny = ny;
     ctx->g.ld = (nx + 31) / 32 * 32;
-    ctx->g.ldu = (nx + 1 + 31) / 32 * 32;
+    ctx->g.ldu = nx + 1;                       // staggered rows are dense: one linear H2D copy
     ctx->ld2 = ctx->g.ld;
     auto bail = [&](int code) { std::string m = ctx->err; icar_destroy(ctx); g_create_error = m; return code; };
 #define CUB(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { ctx->err = std::string(#call) + ": " + cudaGetErrorString(e__); return bail(ICAR_ERR_CUDA); } } while (0)

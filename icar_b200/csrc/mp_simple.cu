@@ -20,6 +20,8 @@
 // below evaluates the same algorithm (same table, same double-precision polynomial), so
 // together with IEEE division and -fmad=false the kernel reproduces the CPU oracle bit for
 // bit rather than to a tolerance.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "mp_simple.cuh"
 
@@ -336,6 +338,7 @@ int mp_simple_launch(const Geom& g, const float* p, float* th, const float* pii,
                      int kte, float c2r, float c2s, unsigned long long* diag, cudaStream_t st) {
     if (ite < its || jte < jts) return 0;
     int cpt = (g.nz + 9) / 10;                              // cells per thread: ~10 z-threads per CTA
+    if (const char* e = std::getenv("ICAR_MP_CPT")) { int v = std::atoi(e); if (v >= 1 && v <= 8 && v * 10 >= g.nz) cpt = v; }
     if (cpt > 8) return -1;                                 // nz > 80 is not built
     const int nzt = (g.nz + cpt - 1) / cpt;
     dim3 block(TX, nzt);

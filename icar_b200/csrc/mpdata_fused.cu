@@ -103,13 +103,13 @@ __device__ __forceinline__ void tma_load_box(void* dst, const CUtensorMap* map, 
 //     w2 = az*A - bz*B - cz*C        (z-face above k, stored at k; includes the *0.5*dz)
 // Terms the Fortran skips at domain edges get a zero coefficient.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(512)
 k_face_coefficients(Geom g, const float* __restrict__ U, const float* __restrict__ V,
                     const float* __restrict__ Wn, const float* __restrict__ G,
                     const float* __restrict__ dz, FusedCoef co) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    const int k = blockIdx.y, j = blockIdx.z;
-    if (i >= g.nx) return;
+    const int k = blockIdx.y * blockDim.y + threadIdx.y, j = blockIdx.z * blockDim.z + threadIdx.z;
+    if (i >= g.nx || k >= g.nz || j >= g.ny) return;
     const size_t ps = g.ps();
     const int ld = g.ld;
     const size_t c = g.at(i, k, j);
@@ -162,7 +162,6 @@ k_corrector_fused(const Geom g, const OutSet outs, const __grid_constant__ Fused
     const bool col = (i >= 0 && i < nx);
     const bool ilast = (i == nx - 1);
     const float xedge = (i == 0 || ilast) ? 0.f : 1.f;           // fin = fout = 0 at the x line ends
-    const bool has_l = (i != 0), has_r = !ilast;                  // x neighbour exists
     const int ja = 1 + blockIdx.y * chunk;            // first output plane of this chunk
     const int jb = min(ja + chunk, ny - 1);           // one past the last output plane
     const int k0 = tz * CPT;
@@ -355,7 +354,7 @@ k_corrector_fused(const Geom g, const OutSet outs, const __grid_constant__ Fused
         for (int c = 0; c < CPT; ++c) {
             const float v = v2a[c];
             const float lim = (v > 0.f) ? min3(1.f, byi1[c], byo[c]) : min3(1.f, byi[c], byo1[c]);
-            fyl[c] = donor(lim * v, a[c][1], a[c][2]);
+            fyl[c] = lim * fya[c];                 // same donor cell as the unlimited flux: donor(lim*v) == lim*f
         }
 
         // ---------------- x / z limiter and corrector update of plane Po
@@ -373,8 +372,8 @@ k_corrector_fused(const Geom g, const OutSet outs, const __grid_constant__ Fused
                 {
                     const float mhl = lane_lo(mhc), mhr = lane_hi(mhc), mll = lane_lo(mlc), mlr = lane_hi(mlc);
                     const float fxp = lane_hi(fx[c]);
-                    const float hi = max3(has_l ? mhl : -BIG, ilast ? q : mhc, has_r ? mhr : -BIG);
-                    const float lo = min3(has_l ? mll : BIG, ilast ? q : mlc, has_r ? mlr : BIG);
+                    const float hi = max3(mhl, ilast ? q : mhc, mhr);       // lanes outside the domain hold -BIG
+                    const float lo = min3(mll, ilast ? q : mlc, mlr);
                     const float fin = (fmaxf(0.f, fx[c]) - fminf(0.f, fxp)) * xedge;
                     const float fout = (fmaxf(0.f, fxp) - fminf(0.f, fx[c])) * xedge;
                     bxi[c] = fdiv(hi - q, fin + E15);
@@ -389,8 +388,8 @@ k_corrector_fused(const Geom g, const OutSet outs, const __grid_constant__ Fused
                     const float mlu = (c + 1 < CPT) ? ml[(c + 1 < CPT) ? c + 1 : c][0] : mla;
                     const float fzm = (c > 0) ? fz[(c > 0) ? c - 1 : c] : fzb;
                     const float fzp = zlast ? fzm : fz[c];            // top: fin = fout = |f(nz-2)|
-                    const float hi = max3(mhd, zlast ? q : mhc, zlast ? -BIG : mhu);
-                    const float lo = min3(mld, zlast ? q : mlc, zlast ? BIG : mlu);
+                    const float hi = max3(mhd, zlast ? q : mhc, mhu);     // the slot above the top level holds -BIG
+                    const float lo = min3(mld, zlast ? q : mlc, mlu);
                     const float fin = fmaxf(0.f, fzm) - fminf(0.f, fzp);
                     const float fout = fmaxf(0.f, fzp) - fminf(0.f, fzm);
                     bzi[c] = fdiv(hi - q, fin + E15);
@@ -404,19 +403,17 @@ k_corrector_fused(const Geom g, const OutSet outs, const __grid_constant__ Fused
             float fxl[CPT], fzl[CPT];
 #pragma unroll
             for (int c = 0; c < CPT; ++c) {
-                const float q = a[c][1];
                 // limited x flux through face (i-1 | i)
                 const float bil = lane_lo(bxi[c]), bol = lane_lo(bxo[c]);
                 const float u = u2[c];
                 const float limx = (u > 0.f) ? min3(1.f, bxi[c], bol) : min3(1.f, bil, bxo[c]);
-                fxl[c] = donor(limx * u, lane_lo(q), q);
+                fxl[c] = limx * fx[c];
                 // limited z flux through the face above k
                 const float biu = (c + 1 < CPT) ? bzi[(c + 1 < CPT) ? c + 1 : c] : bia;
                 const float bou = (c + 1 < CPT) ? bzo[(c + 1 < CPT) ? c + 1 : c] : boa;
                 const float w = w2[c];
                 const float limz = (w > 0.f) ? min3(1.f, biu, bzo[c]) : min3(1.f, bzi[c], bou);
-                const float qu = (c + 1 < CPT) ? a[(c + 1 < CPT) ? c + 1 : c][1] : qab[1];
-                fzl[c] = donor(limz * w, q, qu);
+                fzl[c] = limz * fz[c];
             }
             row(buf, R_FLHI, tz) = fzl[CPT - 1];
             __syncthreads();
@@ -531,8 +528,8 @@ int fused_advect_all(const Geom& g, const ScalarSet& s, const float* U, const fl
                      cudaStream_t st) {
     int launches = 0;
     if (s.n > FUSED_MAX_SCALARS) return -1;
-    dim3 cgrid((g.nx + 127) / 128, g.nz, g.ny);
-    k_face_coefficients<<<cgrid, 128, 0, st>>>(g, U, V, Wn, jaco, dz, co);
+    dim3 cgrid((g.nx + 31) / 32, (g.nz + 3) / 4, (g.ny + 3) / 4);
+    k_face_coefficients<<<cgrid, dim3(32, 4, 4), 0, st>>>(g, U, V, Wn, jaco, dz, co);
     launches += 1;
     launches += staged_upwind_all(g, s, U, V, W, dz, jaco, st);   // also copies the boundary ring into `out`
 

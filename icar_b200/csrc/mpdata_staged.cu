@@ -25,9 +25,9 @@ __global__ void k_wind_normalise(Geom g, const R* __restrict__ u, const R* __res
                                  const R* __restrict__ rho, R dt, R dx, int scheme,
                                  R* __restrict__ U, R* __restrict__ V, R* __restrict__ W,
                                  const R* __restrict__ dz, R* __restrict__ Wn) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    int k = blockIdx.y, j = blockIdx.z;
-    if (i >= g.nx) return;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int k = blockIdx.y * blockDim.y + threadIdx.y, j = blockIdx.z * blockDim.z + threadIdx.z;
+    if (i >= g.nx || k >= g.nz || j >= g.ny) return;
     size_t c = g.at(i, k, j);
     R r0 = rho ? rho[c] : R(1);
     R Uv = R(0), Vv = R(0);
@@ -56,9 +56,10 @@ template <class R>
 __global__ void k_wn_G(Geom g, const R* __restrict__ W, const R* __restrict__ dz,
                        const R* __restrict__ jaco, const R* __restrict__ rho,
                        R* __restrict__ Wn, R* __restrict__ G) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= g.nx) return;
-    size_t c = g.at(i, blockIdx.y, blockIdx.z);
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int k = blockIdx.y * blockDim.y + threadIdx.y, j = blockIdx.z * blockDim.z + threadIdx.z;
+    if (i >= g.nx || k >= g.nz || j >= g.ny) return;
+    size_t c = g.at(i, k, j);
     Wn[c] = W[c] / dz[c];
     if (G) G[c] = jaco[c] * rho[c];     // rho == 1: jaco*rho is jaco itself, no copy needed
 }
@@ -71,9 +72,9 @@ __global__ void k_upwind(Geom g, const R* __restrict__ qin, const R* __restrict_
                          const R* __restrict__ V, const R* __restrict__ W,
                          const R* __restrict__ rho, const R* __restrict__ dz,
                          const R* __restrict__ jaco, R* __restrict__ qout) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    int k = blockIdx.y, j = blockIdx.z;
-    if (i >= g.nx) return;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int k = blockIdx.y * blockDim.y + threadIdx.y, j = blockIdx.z * blockDim.z + threadIdx.z;
+    if (i >= g.nx || k >= g.nz || j >= g.ny) return;
     size_t c = g.at(i, k, j);
     R qc = qin[c];
     if (i == 0 || i == g.nx - 1 || j == 0 || j == g.ny - 1) { qout[c] = qc; return; }
@@ -108,9 +109,9 @@ __global__ void k_pseudo_velocities(Geom g, const R* __restrict__ q, const R* __
                                     const R* __restrict__ V, const R* __restrict__ Wn,
                                     const R* __restrict__ G, const R* __restrict__ dz,
                                     R* __restrict__ u2, R* __restrict__ v2, R* __restrict__ w2) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    int k = blockIdx.y, j = blockIdx.z;
-    if (i >= g.nx) return;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int k = blockIdx.y * blockDim.y + threadIdx.y, j = blockIdx.z * blockDim.z + threadIdx.z;
+    if (i >= g.nx || k >= g.nz || j >= g.ny) return;
     const size_t ps = g.ps();
     const int ld = g.ld;
     const R eps = R(1e-10f);
@@ -246,9 +247,9 @@ __global__ void k_corrector(Geom g, const R* __restrict__ l, const R* __restrict
                             const R* __restrict__ w2, const R* __restrict__ rho,
                             const R* __restrict__ dz, const R* __restrict__ jaco,
                             R* __restrict__ qout) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    int k = blockIdx.y, j = blockIdx.z;
-    if (i >= g.nx) return;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int k = blockIdx.y * blockDim.y + threadIdx.y, j = blockIdx.z * blockDim.z + threadIdx.z;
+    if (i >= g.nx || k >= g.nz || j >= g.ny) return;
     const size_t ps = g.ps();
     const int ld = g.ld;
     size_t c = g.at(i, k, j);
@@ -301,8 +302,8 @@ __global__ void __launch_bounds__(128)
 k_upwind_all(Geom g, ScalarSet s, const float* __restrict__ U, const float* __restrict__ V,
              const float* __restrict__ W, const float* __restrict__ dz, const float* __restrict__ jaco) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    const int k = blockIdx.y, j = blockIdx.z;
-    if (i >= g.nx) return;
+    const int k = blockIdx.y * blockDim.y + threadIdx.y, j = blockIdx.z * blockDim.z + threadIdx.z;
+    if (i >= g.nx || k >= g.nz || j >= g.ny) return;
     const size_t c = g.at(i, k, j);
     if (i == 0 || i == g.nx - 1 || j == 0 || j == g.ny - 1) {
 #pragma unroll
@@ -343,25 +344,28 @@ k_upwind_all(Geom g, ScalarSet s, const float* __restrict__ U, const float* __re
 // ---------------------------------------------------------------------------
 // launchers
 // ---------------------------------------------------------------------------
-static inline dim3 cell_grid(const Geom& g, int bx) {
-    return dim3((g.nx + bx - 1) / bx, g.nz, g.ny);
+// cell-wise kernels: one CTA = 128 consecutive x of one (k, j) row (measured faster than (32,4,4)
+// blocks for the pass-1 and wind kernels: 212 vs 273 us and 116 vs 128 us at 512x512x40)
+static inline dim3 cell_block() { return dim3(128, 1, 1); }
+static inline dim3 cell_grid(const Geom& g) {
+    return dim3((g.nx + 127) / 128, g.nz, g.ny);
 }
 
 
 int staged_upwind_all(const Geom& g, const ScalarSet& s, const float* U, const float* V, const float* W,
                       const float* dz, const float* jaco, cudaStream_t st) {
-    dim3 grid = cell_grid(g, 128);
+    dim3 grid = cell_grid(g);
     int done = 0, launches = 0;
     while (done < s.n) {                 // batches of up to 5 scalars share the wind / metric loads
         ScalarSet b;
         b.n = (s.n - done >= 5) ? 5 : (s.n - done);
         for (int n = 0; n < b.n; ++n) { b.q[n] = s.q[done + n]; b.q2[n] = s.q2[done + n]; b.out[n] = s.out[done + n]; }
         switch (b.n) {
-            case 5: k_upwind_all<5><<<grid, 128, 0, st>>>(g, b, U, V, W, dz, jaco); break;
-            case 4: k_upwind_all<4><<<grid, 128, 0, st>>>(g, b, U, V, W, dz, jaco); break;
-            case 3: k_upwind_all<3><<<grid, 128, 0, st>>>(g, b, U, V, W, dz, jaco); break;
-            case 2: k_upwind_all<2><<<grid, 128, 0, st>>>(g, b, U, V, W, dz, jaco); break;
-            default: k_upwind_all<1><<<grid, 128, 0, st>>>(g, b, U, V, W, dz, jaco); break;
+            case 5: k_upwind_all<5><<<grid, cell_block(), 0, st>>>(g, b, U, V, W, dz, jaco); break;
+            case 4: k_upwind_all<4><<<grid, cell_block(), 0, st>>>(g, b, U, V, W, dz, jaco); break;
+            case 3: k_upwind_all<3><<<grid, cell_block(), 0, st>>>(g, b, U, V, W, dz, jaco); break;
+            case 2: k_upwind_all<2><<<grid, cell_block(), 0, st>>>(g, b, U, V, W, dz, jaco); break;
+            default: k_upwind_all<1><<<grid, cell_block(), 0, st>>>(g, b, U, V, W, dz, jaco); break;
         }
         done += b.n;
         ++launches;
@@ -373,7 +377,7 @@ template <class R>
 int staged_wind_normalise(const Geom& g, const R* u, const R* v, const R* w, const R* ju,
                           const R* jv, const R* jw, const R* rho, R dt, R dx, int scheme, R* U,
                           R* V, R* W, cudaStream_t st, const R* dz, R* Wn) {
-    k_wind_normalise<R><<<cell_grid(g, 128), 128, 0, st>>>(g, u, v, w, ju, jv, jw, rho, dt, dx,
+    k_wind_normalise<R><<<cell_grid(g), cell_block(), 0, st>>>(g, u, v, w, ju, jv, jw, rho, dt, dx,
                                                             scheme, U, V, W, dz, Wn);
     return 1;
 }
@@ -381,7 +385,7 @@ int staged_wind_normalise(const Geom& g, const R* u, const R* v, const R* w, con
 template <class R>
 int staged_wn_G(const Geom& g, const R* W, const R* dz, const R* jaco, const R* rho, R* Wn, R* G,
                 cudaStream_t st) {
-    k_wn_G<R><<<cell_grid(g, 128), 128, 0, st>>>(g, W, dz, jaco, rho, Wn, G);
+    k_wn_G<R><<<cell_grid(g), cell_block(), 0, st>>>(g, W, dz, jaco, rho, Wn, G);
     return 1;
 }
 
@@ -392,18 +396,18 @@ int staged_advect3d(const Geom& g, R* q, const R* rho, const R* jaco, const R* d
                     const R* V, const R* W, const R* Wn, const R* G, int order, bool fct, R* qa,
                     R* qb, R* u2, R* v2, R* w2, R** result, cudaStream_t st) {
     int launches = 0;
-    dim3 grid = cell_grid(g, 128);
+    dim3 grid = cell_grid(g);
     // iord = 1: q2 = upwind(q)
-    k_upwind<R><<<grid, 128, 0, st>>>(g, q, U, V, W, rho, dz, jaco, qa);
+    k_upwind<R><<<grid, cell_block(), 0, st>>>(g, q, U, V, W, rho, dz, jaco, qa);
     ++launches;
     if (order <= 1) { *result = qa; return launches; }
     R* lfield = q;     // "q"  in the Fortran: field before the previous pass
     R* q2 = qa;        // "q2" in the Fortran: field after the previous pass
     R* out = qb;
     for (int iord = 2; iord <= order; ++iord) {
-        k_pseudo_velocities<R><<<grid, 128, 0, st>>>(g, q2, U, V, Wn, G, dz, u2, v2, w2);
-        if (fct) k_corrector<R, true><<<grid, 128, 0, st>>>(g, lfield, q2, u2, v2, w2, rho, dz, jaco, out);
-        else     k_corrector<R, false><<<grid, 128, 0, st>>>(g, lfield, q2, u2, v2, w2, rho, dz, jaco, out);
+        k_pseudo_velocities<R><<<grid, cell_block(), 0, st>>>(g, q2, U, V, Wn, G, dz, u2, v2, w2);
+        if (fct) k_corrector<R, true><<<grid, cell_block(), 0, st>>>(g, lfield, q2, u2, v2, w2, rho, dz, jaco, out);
+        else     k_corrector<R, false><<<grid, cell_block(), 0, st>>>(g, lfield, q2, u2, v2, w2, rho, dz, jaco, out);
         launches += 2;
         if (iord != order) {
             // adv_mpdata.f90:393-401: q2 = q ; the next limiter then sees l == q1 == this result

@@ -1,0 +1,5 @@
+python -c "import __graft_entry__ as g; g.build(); g.smoke()" 2>&1 | tail -1
+timeout 300 python -m pytest tests/test_gpu_parity.py -m gpu -q 2>&1 | tail -3
+timeout 300 python bench.py --steps 30 --warmup 5 --no-cpu-baseline 2>&1 | tail -1 | python -c "import sys,json; d=json.loads(sys.stdin.read()); print({k:d[k] for k in ('value','ms_per_step','e2e','gpu_launches')}, d['roofline']['frac'])"
+timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -s 55 -c 22 --csv --log-file gpurun_out/launches_v6.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_b.log 2>&1
+python scripts/launch_summary.py gpurun_out/launches_v6.csv
