@@ -129,22 +129,6 @@ def physical_device(local_rank):
     return local_rank
 
 
-def slab_of(st, grid):
-    """The x-slab (with ghost columns) of a global state dict for one image's grid."""
-    lo, hi = grid.ims - 1, grid.ime
-    out = {}
-    for k, v in st.items():
-        if not isinstance(v, np.ndarray):
-            out[k] = v
-        elif k in ("u", "jacobian_u"):
-            out[k] = np.ascontiguousarray(v[:, :, lo:hi + 1])
-        elif v.ndim in (2, 3):
-            out[k] = np.ascontiguousarray(v[..., lo:hi])
-        else:
-            out[k] = v
-    return out
-
-
 # --------------------------------------------------------------------------------------------
 def cpu_oracle_rate(st, dt, min_seconds, max_steps, threads=None):
     """Times oracle.step_simple on the full workload; returns (cells/s, steps, seconds, threads)."""
@@ -232,8 +216,8 @@ def run_b200(args, rank, world, local_rank):
     st = ideal.make_ideal_case(nx=nx, nz=nz, ny=ny, perturb=True)
     dt = float(st["dt"])
     if distributed:
-        grid = icar_b200.Grid.xslab(nx, nz, ny, world, rank + 1, halo)
-        local = slab_of(st, grid)
+        grid = (icar_b200.Grid.xslab if args.slabs == "x" else icar_b200.Grid.yslab)(nx, nz, ny, world, rank + 1, halo)
+        local = ideal.slab_of(st, grid)
     else:
         grid = icar_b200.Grid.single_image(nx, nz, ny, halo_size=1)
         local = st
@@ -323,7 +307,7 @@ def run_b200(args, rank, world, local_rank):
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "grid": [nx, nz, ny], "dt_s": dt, "advected_scalars": 5,
-                       "decomposition": (f"x-slabs over {world} GPUs, halo {halo}, NCCL send/recv" if distributed
+                       "decomposition": (f"{args.slabs}-slabs over {world} GPUs, halo {halo}, NCCL send/recv" if distributed
                                          else "single image"),
                        "l2": "resident working set ~1.1 GB per step > 126 MB L2, no explicit flush",
                        "mp_diagnostics": list(diag)},
@@ -356,6 +340,8 @@ def main():
     ap.add_argument("--nz", type=int, default=40)
     ap.add_argument("--ny", type=int, default=512)
     ap.add_argument("--halo", type=int, default=3, help="ghost width for N>1 (3 = decomposition-invariant)")
+    ap.add_argument("--slabs", default="y", choices=["x", "y"],
+                    help="decomposition axis for N>1 (y keeps full-width rows and contiguous halo planes)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

@@ -62,6 +62,14 @@ class Grid(C.Structure):
             raise IcarError(rc, "icar_grid_xslab: invalid decomposition")
         return g
 
+    @classmethod
+    def yslab(cls, nx_global, nz, ny_global, nimages, image, halo_size):
+        g = cls()
+        rc = lib().icar_grid_yslab(nx_global, nz, ny_global, nimages, image, halo_size, C.byref(g))
+        if rc:
+            raise IcarError(rc, "icar_grid_yslab: invalid decomposition")
+        return g
+
     @property
     def nx(self): return self.ime - self.ims + 1
     @property
@@ -97,7 +105,7 @@ _lib = None
 
 # every symbol include/icar_b200.h declares
 SYMBOLS = (
-    "icar_default_options", "icar_grid_xslab", "icar_create", "icar_destroy", "icar_last_error",
+    "icar_default_options", "icar_grid_xslab", "icar_grid_yslab", "icar_create", "icar_destroy", "icar_last_error",
     "icar_upload", "icar_download", "icar_device_ptr", "icar_set_model_time", "icar_get_model_time",
     "icar_advect", "icar_mp", "icar_halo_send", "icar_halo_retrieve", "icar_halo_exchange",
     "icar_physics_step", "icar_synchronize", "icar_mp_diagnostics", "icar_kernel_launches",
@@ -311,14 +319,14 @@ class Domain:
 
 
 def halo_plan(grid: Grid, image: int, nimages: int):
-    """(send_west, send_east, recv_west, recv_east) first local columns (0-based) and the two
-    neighbour flags -- icar_halo_plan."""
-    plan = (C.c_int * 6)()
+    """icar_halo_plan: first local indices (0-based, along the exchange axis) sent to / received
+    from the lower (west/south) and upper (east/north) neighbour."""
+    plan = (C.c_int * 8)()
     rc = lib().icar_halo_plan(C.byref(grid), int(image), int(nimages), plan)
     if rc:
         raise IcarError(rc, "icar_halo_plan: invalid arguments")
-    return dict(send_west=plan[0], send_east=plan[1], recv_west=plan[2], recv_east=plan[3],
-                has_west=bool(plan[4]), has_east=bool(plan[5]), width=grid.halo_size)
+    return dict(send_lo=plan[0], send_hi=plan[1], recv_lo=plan[2], recv_hi=plan[3],
+                has_lo=bool(plan[4]), has_hi=bool(plan[5]), axis=("x", "y")[plan[6]], width=plan[7])
 
 
 def comm_unique_id() -> bytes:

@@ -6,10 +6,11 @@
 
 namespace icar {
 
-// Gathers columns [x0, x0+h) of `nfields` cell fields into buf[s][j][k][h] / scatters them back.
-int halo_pack_launch(const Geom& g, float* const* fields, int nfields, int h, int x0, float* buf,
-                     cudaStream_t st);
-int halo_unpack_launch(const Geom& g, float* const* fields, int nfields, int h, int x0,
-                       const float* buf, cudaStream_t st);
+// Gathers columns [x0[i], x0[i]+h) of `nfields` cell fields into buf[i][s][j][k][h] / scatters them
+// back, for one or two strips (west and east) in a single launch.
+int halo_pack_launch(const Geom& g, float* const* fields, int nfields, int h, int nsides, const int* x0,
+                     float* const* buf, cudaStream_t st);
+int halo_unpack_launch(const Geom& g, float* const* fields, int nfields, int h, int nsides, const int* x0,
+                       float* const* buf, cudaStream_t st);
 
 }  // namespace icar

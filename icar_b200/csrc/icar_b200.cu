@@ -101,11 +101,12 @@ struct icar_ctx {
     FusedCoef coef{};
     float* fq2[5] = {};
     float* fout[5] = {};
-    float *rain2d = nullptr, *snow2d = nullptr;      // per-call precipitation of the main-stream tile
-    float *rain2d_halo = nullptr, *snow2d_halo = nullptr;   // ... of the ring strips (aux streams)
-    cudaStream_t aux[4] = {nullptr, nullptr, nullptr, nullptr};
-    cudaEvent_t ev_fork = nullptr, ev_aux[4] = {nullptr, nullptr, nullptr, nullptr};
-    bool aux_pending = false;        // ring strips of mp(halo) still running on the aux streams
+    // per-call REAL*4 precipitation: [rain | snow] of the main-stream tile and of the ring strips
+    float *rain2d = nullptr, *snow2d = nullptr, *rain2d_halo = nullptr, *snow2d_halo = nullptr;
+    cudaStream_t aux = nullptr;      // the ring strips of mp(halo) run here, next to mp(subset)
+    cudaEvent_t ev_fork = nullptr, ev_aux = nullptr;
+    bool aux_pending = false;        // ring strips still running on the aux stream
+    bool main_acc_pending = false;   // rain2d / snow2d not yet folded into the REAL*8 accumulators
     unsigned long long* diag = nullptr;
     std::vector<void*> scratch;      // leaf-call staging buffers (float or double cells)
     std::vector<size_t> scratch_bytes;
@@ -215,12 +216,21 @@ int need_uploaded(icar_ctx* ctx, std::initializer_list<int> vars, const char* wh
     return ICAR_OK;
 }
 
-// process_subdomain's scheme call (mp_driver.f90:398-607) on a 1-based inclusive tile
-int run_mp_tile(icar_ctx* ctx, float mp_dt, int its, int ite, int jts, int jte, int kts, int kte,
-                cudaStream_t st, float* rain2d, float* snow2d) {
+// process_subdomain's scheme call (mp_driver.f90:398-607) on up to four 1-based inclusive tiles
+// {its, ite, jts, jte}, one launch
+int run_mp_tiles(icar_ctx* ctx, float mp_dt, const int (*t)[4], int ntiles, int kts, int kte, cudaStream_t st,
+                 float* rain2d, float* snow2d) {
     const icar_grid& gr = ctx->grid;
-    if (ite < its || jte < jts) return ICAR_OK;
     if (ctx->opt.microphysics == 2) {
+        MpTiles tiles;
+        tiles.n = 0;
+        for (int a = 0; a < ntiles; ++a) {
+            if (t[a][1] < t[a][0] || t[a][3] < t[a][2]) continue;
+            tiles.its[tiles.n] = t[a][0] - gr.ims; tiles.ite[tiles.n] = t[a][1] - gr.ims;
+            tiles.jts[tiles.n] = t[a][2] - gr.jms; tiles.jte[tiles.n] = t[a][3] - gr.jms;
+            ++tiles.n;
+        }
+        if (tiles.n == 0) return ICAR_OK;
         float c2s = std::exp(-1.0f * (1.0f / 2000.0f) * mp_dt);    // mp_simple.f90:619
         float c2r = std::exp(-1.0f * (1.0f / 500.0f) * mp_dt);     // mp_simple.f90:620
         int nl = mp_simple_launch(
@@ -229,8 +239,7 @@ int run_mp_tile(icar_ctx* ctx, float mp_dt, int its, int ite, int jts, int jte, 
             (const float*)ctx->vars[ICAR_VAR_DENSITY], (float*)ctx->vars[ICAR_VAR_WATER_VAPOR],
             (float*)ctx->vars[ICAR_VAR_CLOUD_WATER], (float*)ctx->vars[ICAR_VAR_RAIN_IN_AIR],
             (float*)ctx->vars[ICAR_VAR_SNOW_IN_AIR], rain2d, snow2d, ctx->ld2, mp_dt,
-            (const float*)ctx->vars[ICAR_VAR_DZ_MASS], its - gr.ims, ite - gr.ims, jts - gr.jms,
-            jte - gr.jms, kts - gr.kms, kte - gr.kms, c2r, c2s, ctx->diag, st);
+            (const float*)ctx->vars[ICAR_VAR_DZ_MASS], tiles, kts - gr.kms, kte - gr.kms, c2r, c2s, ctx->diag, st);
         if (nl < 0) return fail(ctx, ICAR_ERR_INVALID, "mp_simple: more than 80 levels are not built");
         ctx->launches += nl;
         CU(cudaGetLastError());
@@ -240,16 +249,20 @@ int run_mp_tile(icar_ctx* ctx, float mp_dt, int its, int ite, int jts, int jte, 
                                            " is not built (only kMP_SB04 = 2)");
 }
 
-// Waits (on the compute stream) for the ring strips that mp(halo) left running on the aux
-// streams and folds their precipitation into the REAL*8 accumulators.
+// Waits (on the compute stream) for the ring strips that mp(halo) left running on the aux stream and
+// folds the pending per-call precipitation (interior tile and/or strips: disjoint cells, so one pass
+// in any order equals the reference's two `+=`) into the REAL*8 accumulators.
 int join_aux(icar_ctx* ctx) {
-    if (!ctx->aux_pending) return ICAR_OK;
-    for (int a = 0; a < 4; ++a) CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_aux[a], 0));
-    ctx->launches += accumulate_precip_launch(ctx->g.nx, ctx->g.ny, ctx->ld2, ctx->rain2d_halo, ctx->snow2d_halo,
-                                              (double*)ctx->vars[ICAR_VAR_PRECIPITATION],
-                                              (double*)ctx->vars[ICAR_VAR_SNOWFALL], ctx->stream);
+    if (!ctx->aux_pending && !ctx->main_acc_pending) return ICAR_OK;
+    if (ctx->aux_pending) CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_aux, 0));
+    ctx->launches += accumulate_precip_launch(
+        ctx->g.nx, ctx->g.ny, ctx->ld2, ctx->main_acc_pending ? ctx->rain2d : nullptr,
+        ctx->main_acc_pending ? ctx->snow2d : nullptr, ctx->aux_pending ? ctx->rain2d_halo : nullptr,
+        ctx->aux_pending ? ctx->snow2d_halo : nullptr, (double*)ctx->vars[ICAR_VAR_PRECIPITATION],
+        (double*)ctx->vars[ICAR_VAR_SNOWFALL], ctx->stream);
     CU(cudaGetLastError());
     ctx->aux_pending = false;
+    ctx->main_acc_pending = false;
     return ICAR_OK;
 }
 
@@ -291,6 +304,31 @@ extern "C" int icar_grid_xslab(int nx_global, int nz, int ny_global, int nimages
     g.ite = g.ime - (east ? 1 : halo_size);
     g.jts = g.jms + 1;
     g.jte = g.jme - 1;
+    g.halo_size = halo_size;
+    *out = g;
+    return ICAR_OK;
+}
+
+extern "C" int icar_grid_yslab(int nx_global, int nz, int ny_global, int nimages, int image,
+                               int halo_size, icar_grid* out) {
+    if (!out || nimages < 1 || image < 1 || image > nimages || ny_global < nimages || halo_size < 1)
+        return ICAR_ERR_INVALID;
+    // my_n / my_start, grid_obj.f90:116-138 with ximages = 1, yimages = nimages
+    int base_n = ny_global / nimages, rem = ny_global % nimages;
+    int n_local = base_n + (image <= rem ? 1 : 0);
+    int start = (image - 1) * base_n + (image - 1 < rem ? image - 1 : rem) + 1;
+    bool south = (image == 1), north = (image == nimages);
+    icar_grid g;
+    g.jms = start; g.jme = start + n_local - 1;
+    g.ims = 1; g.ime = nx_global;
+    g.kms = 1; g.kme = nz; g.kts = 1; g.kte = nz;
+    g.ids = 1; g.ide = nx_global; g.jds = 1; g.jde = ny_global; g.kds = 1; g.kde = nz;
+    g.jms -= south ? 0 : halo_size;                  // update_with_halos, grid_obj.f90:209-255
+    g.jme += north ? 0 : halo_size;
+    g.jts = g.jms + (south ? 1 : halo_size);
+    g.jte = g.jme - (north ? 1 : halo_size);
+    g.its = g.ims + 1;
+    g.ite = g.ime - 1;
     g.halo_size = halo_size;
     *out = g;
     return ICAR_OK;
@@ -351,15 +389,13 @@ extern "C" int icar_create(int device, const icar_grid* grid, const icar_options
             if (alloc_cells(ctx, &ctx->fq2[n]) != ICAR_OK || alloc_cells(ctx, &ctx->fout[n]) != ICAR_OK)
                 return bail(ICAR_ERR_CUDA);
     }
-    CUB(cudaMalloc((void**)&ctx->rain2d, (size_t)ctx->ld2 * ny * sizeof(float)));
-    CUB(cudaMalloc((void**)&ctx->snow2d, (size_t)ctx->ld2 * ny * sizeof(float)));
-    CUB(cudaMalloc((void**)&ctx->rain2d_halo, (size_t)ctx->ld2 * ny * sizeof(float)));
-    CUB(cudaMalloc((void**)&ctx->snow2d_halo, (size_t)ctx->ld2 * ny * sizeof(float)));
+    CUB(cudaMalloc((void**)&ctx->rain2d, (size_t)4 * ctx->ld2 * ny * sizeof(float)));   // 4 planes, one block
+    ctx->snow2d = ctx->rain2d + (size_t)ctx->ld2 * ny;
+    ctx->rain2d_halo = ctx->snow2d + (size_t)ctx->ld2 * ny;
+    ctx->snow2d_halo = ctx->rain2d_halo + (size_t)ctx->ld2 * ny;
     CUB(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
-    for (int a = 0; a < 4; ++a) {
-        CUB(cudaStreamCreateWithFlags(&ctx->aux[a], cudaStreamNonBlocking));
-        CUB(cudaEventCreateWithFlags(&ctx->ev_aux[a], cudaEventDisableTiming));
-    }
+    CUB(cudaStreamCreateWithFlags(&ctx->aux, cudaStreamNonBlocking));
+    CUB(cudaEventCreateWithFlags(&ctx->ev_aux, cudaEventDisableTiming));
     CUB(cudaMalloc((void**)&ctx->diag, 3 * sizeof(unsigned long long)));
     CUB(cudaMemsetAsync(ctx->diag, 0, 3 * sizeof(unsigned long long), ctx->stream));
     CUB(cudaStreamSynchronize(ctx->stream));
@@ -373,11 +409,11 @@ extern "C" int icar_destroy(icar_ctx* ctx) {
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     if (ctx->comm_stream) cudaStreamSynchronize(ctx->comm_stream);
-    for (int a = 0; a < 4; ++a) if (ctx->aux[a]) cudaStreamSynchronize(ctx->aux[a]);
+    if (ctx->aux) cudaStreamSynchronize(ctx->aux);
     if (ctx->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(ctx->comm);
     for (void* p : ctx->vars) if (p) cudaFree(p);
     float* bufs[] = {ctx->U, ctx->V, ctx->W, ctx->Wn, ctx->G, ctx->qa, ctx->qb, ctx->u2, ctx->v2, ctx->w2,
-                     ctx->rain2d, ctx->snow2d, ctx->rain2d_halo, ctx->snow2d_halo, ctx->send_w, ctx->send_e, ctx->recv_w, ctx->recv_e};
+                     ctx->rain2d, ctx->send_w, ctx->send_e, ctx->recv_w, ctx->recv_e};
     for (float* p : bufs) if (p) cudaFree(p);
     if (ctx->diag) cudaFree(ctx->diag);
     {
@@ -388,7 +424,8 @@ extern "C" int icar_destroy(icar_ctx* ctx) {
     }
     for (void* p : ctx->scratch) if (p) cudaFree(p);
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
-    for (int a = 0; a < 4; ++a) { if (ctx->ev_aux[a]) cudaEventDestroy(ctx->ev_aux[a]); if (ctx->aux[a]) cudaStreamDestroy(ctx->aux[a]); }
+    if (ctx->ev_aux) cudaEventDestroy(ctx->ev_aux);
+    if (ctx->aux) cudaStreamDestroy(ctx->aux);
     if (ctx->ev_packed) cudaEventDestroy(ctx->ev_packed);
     if (ctx->ev_comm) cudaEventDestroy(ctx->ev_comm);
     if (ctx->ev_t0) cudaEventDestroy(ctx->ev_t0);
@@ -575,40 +612,29 @@ extern "C" int icar_mp(icar_ctx* ctx, float dt_in, int halo, int subset) {
         // process_subdomain zeroes its local precipitation arrays on entry (:411-413) and adds them to
         // the REAL*8 accumulators on exit (:587-595); tiles of one call are disjoint, so one clear
         // and one accumulation per group of tiles is identical.
-        const size_t b2 = (size_t)ctx->ld2 * ctx->g.ny * sizeof(float);
-        if (has_halo || (!has_halo && !has_subset))
-            if ((rc = join_aux(ctx))) return rc;          // strips of an earlier call overlap these cells
+        const size_t b2 = (size_t)2 * ctx->ld2 * ctx->g.ny * sizeof(float);     // rain + snow plane
+        if (has_halo || (!has_halo && !has_subset) || ctx->main_acc_pending)
+            if ((rc = join_aux(ctx))) return rc;          // earlier tiles overlap these cells / buffers
         if (has_subset || (!has_halo && !has_subset)) {
             CU(cudaMemsetAsync(ctx->rain2d, 0, b2, ctx->stream));
-            CU(cudaMemsetAsync(ctx->snow2d, 0, b2, ctx->stream));
-            if (has_subset)                                                              // :728-738
-                rc = run_mp_tile(ctx, mp_dt, gr.its + subset, gr.ite - subset, gr.jts + subset, gr.jte - subset,
-                                 gr.kts, kte, ctx->stream, ctx->rain2d, ctx->snow2d);
-            else                                                                         // :754-766
-                rc = run_mp_tile(ctx, mp_dt, gr.its, gr.ite, gr.jts, gr.jte, gr.kts, kte, ctx->stream,
-                                 ctx->rain2d, ctx->snow2d);
-            if (rc) return rc;
-            ctx->launches += accumulate_precip_launch(ctx->g.nx, ctx->g.ny, ctx->ld2, ctx->rain2d, ctx->snow2d,
-                                                      (double*)ctx->vars[ICAR_VAR_PRECIPITATION],
-                                                      (double*)ctx->vars[ICAR_VAR_SNOWFALL], ctx->stream);
+            const int sub = has_subset ? subset : 0;                                     // :728-738 / :754-766
+            const int t[1][4] = {{gr.its + sub, gr.ite - sub, gr.jts + sub, gr.jte - sub}};
+            if ((rc = run_mp_tiles(ctx, mp_dt, t, 1, gr.kts, kte, ctx->stream, ctx->rain2d, ctx->snow2d))) return rc;
+            ctx->main_acc_pending = true;
         }
         if (has_halo) {                                                                  // process_halo :609-658
-            // The four strips are thin (latency-bound) launches: they run concurrently on four aux
-            // streams and are joined lazily, so the interior tile of mp(subset) overlaps them the
-            // way time_step.f90:512-526 overlaps the halo exchange.
+            // The four strips are thin (latency-bound): they share ONE launch on an auxiliary stream
+            // and are joined lazily, so the interior tile of mp(subset) overlaps them the way
+            // time_step.f90:512-526 overlaps the halo exchange.
             CU(cudaMemsetAsync(ctx->rain2d_halo, 0, b2, ctx->stream));
-            CU(cudaMemsetAsync(ctx->snow2d_halo, 0, b2, ctx->stream));
             CU(cudaEventRecord(ctx->ev_fork, ctx->stream));
             const int t[4][4] = {{gr.its, gr.its + halo - 1, gr.jts, gr.jte},
                                  {gr.ite - halo + 1, gr.ite, gr.jts, gr.jte},
                                  {gr.its + halo, gr.ite - halo, gr.jts, gr.jts + halo - 1},
                                  {gr.its + halo, gr.ite - halo, gr.jte - halo + 1, gr.jte}};
-            for (int a = 0; a < 4; ++a) {
-                CU(cudaStreamWaitEvent(ctx->aux[a], ctx->ev_fork, 0));
-                if ((rc = run_mp_tile(ctx, mp_dt, t[a][0], t[a][1], t[a][2], t[a][3], gr.kts, kte, ctx->aux[a],
-                                      ctx->rain2d_halo, ctx->snow2d_halo))) return rc;
-                CU(cudaEventRecord(ctx->ev_aux[a], ctx->aux[a]));
-            }
+            CU(cudaStreamWaitEvent(ctx->aux, ctx->ev_fork, 0));
+            if ((rc = run_mp_tiles(ctx, mp_dt, t, 4, gr.kts, kte, ctx->aux, ctx->rain2d_halo, ctx->snow2d_halo))) return rc;
+            CU(cudaEventRecord(ctx->ev_aux, ctx->aux));
             ctx->aux_pending = true;
         }
         CU(cudaGetLastError());
@@ -618,16 +644,23 @@ extern "C" int icar_mp(icar_ctx* ctx, float dt_in, int halo, int subset) {
 
 // ============================================================================ halo exchange
 
-extern "C" int icar_halo_plan(const icar_grid* grid, int image, int nimages, int plan[6]) {
+extern "C" int icar_halo_plan(const icar_grid* grid, int image, int nimages, int plan[8]) {
     if (!grid || !plan || nimages < 1 || image < 1 || image > nimages) return ICAR_ERR_INVALID;
-    const int h = grid->halo_size, nx = grid->ime - grid->ims + 1;
-    if (h < 1 || nx < 2 * h) return ICAR_ERR_INVALID;
-    plan[0] = h;               // put_west
-    plan[1] = nx - 2 * h;      // put_east
-    plan[2] = 0;               // retrieve_west_halo
-    plan[3] = nx - h;          // retrieve_east_halo
+    const int h = grid->halo_size;
+    const bool xcut = (grid->ims > grid->ids) || (grid->ime < grid->ide);
+    const bool ycut = (grid->jms > grid->jds) || (grid->jme < grid->jde);
+    if (xcut && ycut) return ICAR_ERR_INVALID;       // 2-D tilings are not supported (slabs only)
+    const int axis = ycut ? 1 : 0;
+    const int n = axis ? (grid->jme - grid->jms + 1) : (grid->ime - grid->ims + 1);
+    if (h < 1 || n < 2 * h) return ICAR_ERR_INVALID;
+    plan[0] = h;               // put_west / put_south
+    plan[1] = n - 2 * h;       // put_east / put_north
+    plan[2] = 0;               // retrieve_west_halo / retrieve_south_halo
+    plan[3] = n - h;           // retrieve_east_halo / retrieve_north_halo
     plan[4] = image > 1 ? 1 : 0;
     plan[5] = image < nimages ? 1 : 0;
+    plan[6] = axis;
+    plan[7] = h;
     return ICAR_OK;
 }
 
@@ -666,28 +699,52 @@ extern "C" int icar_halo_send(icar_ctx* ctx) {
     if (!ctx->comm) return fail(ctx, ICAR_ERR_COMM, "icar_halo_send: icar_comm_init was not called");
     CU(cudaSetDevice(ctx->device));
     { int jr = join_aux(ctx); if (jr) return jr; }
-    const int h = ctx->grid.halo_size;
-    int plan[6];
-    if (icar_halo_plan(&ctx->grid, ctx->image, ctx->nimages, plan)) return fail(ctx, ICAR_ERR_INVALID, "icar_halo_send: tile narrower than two halos");
-    const bool west = plan[4] != 0, east = plan[5] != 0;
+    int plan[8];
+    if (icar_halo_plan(&ctx->grid, ctx->image, ctx->nimages, plan)) return fail(ctx, ICAR_ERR_INVALID, "icar_halo_send: tile narrower than two halos, or not a slab decomposition");
+    const int h = plan[7];
+    const bool lower = plan[4] != 0, upper = plan[5] != 0;
     float* fields[5];
     for (int s = 0; s < 5; ++s) fields[s] = (float*)ctx->vars[kExchangedSimple[s]];
-    const size_t count = (size_t)5 * ctx->g.ny * ctx->g.nz * h;
-    if (west) ctx->launches += halo_pack_launch(ctx->g, fields, 5, h, plan[0], ctx->send_w, ctx->stream);
-    if (east) ctx->launches += halo_pack_launch(ctx->g, fields, 5, h, plan[1], ctx->send_e, ctx->stream);
-    CU(cudaGetLastError());
-    CU(cudaEventRecord(ctx->ev_packed, ctx->stream));
-    CU(cudaStreamWaitEvent(ctx->comm_stream, ctx->ev_packed, 0));
-    NC(g_nccl.GroupStart());
-    if (west) {
-        NC(g_nccl.Send(ctx->send_w, count, ncclFloat, ctx->image - 2, ctx->comm, ctx->comm_stream));
-        NC(g_nccl.Recv(ctx->recv_w, count, ncclFloat, ctx->image - 2, ctx->comm, ctx->comm_stream));
+    if (plan[6] == 0) {
+        // x-slabs: faces are ny*nz runs of h floats -> gather all fields into one buffer per side
+        const size_t count = (size_t)5 * ctx->g.ny * ctx->g.nz * h;
+        int x0[2], ns = 0;
+        float* bufs[2];
+        if (lower) { x0[ns] = plan[0]; bufs[ns++] = ctx->send_w; }
+        if (upper) { x0[ns] = plan[1]; bufs[ns++] = ctx->send_e; }
+        ctx->launches += halo_pack_launch(ctx->g, fields, 5, h, ns, x0, bufs, ctx->stream);
+        CU(cudaGetLastError());
+        CU(cudaEventRecord(ctx->ev_packed, ctx->stream));
+        CU(cudaStreamWaitEvent(ctx->comm_stream, ctx->ev_packed, 0));
+        NC(g_nccl.GroupStart());
+        if (lower) {
+            NC(g_nccl.Send(ctx->send_w, count, ncclFloat, ctx->image - 2, ctx->comm, ctx->comm_stream));
+            NC(g_nccl.Recv(ctx->recv_w, count, ncclFloat, ctx->image - 2, ctx->comm, ctx->comm_stream));
+        }
+        if (upper) {
+            NC(g_nccl.Send(ctx->send_e, count, ncclFloat, ctx->image, ctx->comm, ctx->comm_stream));
+            NC(g_nccl.Recv(ctx->recv_e, count, ncclFloat, ctx->image, ctx->comm, ctx->comm_stream));
+        }
+        NC(g_nccl.GroupEnd());
+    } else {
+        // y-slabs: a face of one field is h contiguous planes -> send straight from the field and
+        // receive straight into the ghost planes (mp(subset) does not touch either while this runs)
+        const size_t ps = ctx->g.ps(), count = (size_t)h * ps;
+        CU(cudaEventRecord(ctx->ev_packed, ctx->stream));
+        CU(cudaStreamWaitEvent(ctx->comm_stream, ctx->ev_packed, 0));
+        NC(g_nccl.GroupStart());
+        for (int s = 0; s < 5; ++s) {
+            if (lower) {
+                NC(g_nccl.Send(fields[s] + (size_t)plan[0] * ps, count, ncclFloat, ctx->image - 2, ctx->comm, ctx->comm_stream));
+                NC(g_nccl.Recv(fields[s] + (size_t)plan[2] * ps, count, ncclFloat, ctx->image - 2, ctx->comm, ctx->comm_stream));
+            }
+            if (upper) {
+                NC(g_nccl.Send(fields[s] + (size_t)plan[1] * ps, count, ncclFloat, ctx->image, ctx->comm, ctx->comm_stream));
+                NC(g_nccl.Recv(fields[s] + (size_t)plan[3] * ps, count, ncclFloat, ctx->image, ctx->comm, ctx->comm_stream));
+            }
+        }
+        NC(g_nccl.GroupEnd());
     }
-    if (east) {
-        NC(g_nccl.Send(ctx->send_e, count, ncclFloat, ctx->image, ctx->comm, ctx->comm_stream));
-        NC(g_nccl.Recv(ctx->recv_e, count, ncclFloat, ctx->image, ctx->comm, ctx->comm_stream));
-    }
-    NC(g_nccl.GroupEnd());
     CU(cudaEventRecord(ctx->ev_comm, ctx->comm_stream));
     ctx->exchange_in_flight = true;
     return ICAR_OK;
@@ -698,16 +755,21 @@ extern "C" int icar_halo_retrieve(icar_ctx* ctx) {
     if (ctx->nimages == 1) return ICAR_OK;
     if (!ctx->exchange_in_flight) return fail(ctx, ICAR_ERR_INVALID, "icar_halo_retrieve without icar_halo_send");
     CU(cudaSetDevice(ctx->device));
-    const int h = ctx->grid.halo_size;
-    int plan[6];
+    int plan[8];
     if (icar_halo_plan(&ctx->grid, ctx->image, ctx->nimages, plan)) return fail(ctx, ICAR_ERR_INVALID, "icar_halo_retrieve: tile narrower than two halos");
-    const bool west = plan[4] != 0, east = plan[5] != 0;
-    float* fields[5];
-    for (int s = 0; s < 5; ++s) fields[s] = (float*)ctx->vars[kExchangedSimple[s]];
+    const int h = plan[7];
+    const bool lower = plan[4] != 0, upper = plan[5] != 0;
     CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_comm, 0));     // `sync images(neighbors)`, exchangeable_obj.f90:151
-    if (west) ctx->launches += halo_unpack_launch(ctx->g, fields, 5, h, plan[2], ctx->recv_w, ctx->stream);
-    if (east) ctx->launches += halo_unpack_launch(ctx->g, fields, 5, h, plan[3], ctx->recv_e, ctx->stream);
-    CU(cudaGetLastError());
+    if (plan[6] == 0) {
+        float* fields[5];
+        for (int s = 0; s < 5; ++s) fields[s] = (float*)ctx->vars[kExchangedSimple[s]];
+        int x0[2], ns = 0;
+        float* bufs[2];
+        if (lower) { x0[ns] = plan[2]; bufs[ns++] = ctx->recv_w; }
+        if (upper) { x0[ns] = plan[3]; bufs[ns++] = ctx->recv_e; }
+        ctx->launches += halo_unpack_launch(ctx->g, fields, 5, h, ns, x0, bufs, ctx->stream);
+        CU(cudaGetLastError());
+    }
     ctx->exchange_in_flight = false;
     return ICAR_OK;
 }
@@ -858,10 +920,16 @@ extern "C" int icar_mp_simple_driver(icar_ctx* ctx, const float* pressure, float
     if ((rc = copy_in(ctx, b[10], snow, g.nx, ctx->ld2, g.ny, sizeof(float)))) return rc;
     float c2s = std::exp(-1.0f * (1.0f / 2000.0f) * dt);
     float c2r = std::exp(-1.0f * (1.0f / 500.0f) * dt);
-    ctx->launches += mp_simple_launch(g, (float*)b[0], (float*)b[1], (float*)b[2], (float*)b[3], (float*)b[4],
-                                      (float*)b[5], (float*)b[6], (float*)b[7], (float*)b[9], (float*)b[10],
-                                      ctx->ld2, dt, (float*)b[8], its - ims, ite - ims, jts - jms, jte - jms,
-                                      kts - kms, kte - kms, c2r, c2s, ctx->diag, ctx->stream);
+    MpTiles tiles;
+    tiles.n = 1;
+    tiles.its[0] = its - ims; tiles.ite[0] = ite - ims; tiles.jts[0] = jts - jms; tiles.jte[0] = jte - jms;
+    {
+        int nl = mp_simple_launch(g, (float*)b[0], (float*)b[1], (float*)b[2], (float*)b[3], (float*)b[4],
+                                  (float*)b[5], (float*)b[6], (float*)b[7], (float*)b[9], (float*)b[10], ctx->ld2, dt,
+                                  (float*)b[8], tiles, kts - kms, kte - kms, c2r, c2s, ctx->diag, ctx->stream);
+        if (nl < 0) return fail(ctx, ICAR_ERR_INVALID, "mp_simple: more than 80 levels are not built");
+        ctx->launches += nl;
+    }
     CU(cudaGetLastError());
     float* out3[5] = {th, qv, qc, qr, qs};
     const int idx3[5] = {1, 4, 5, 6, 7};

@@ -20,6 +20,7 @@
 // below evaluates the same algorithm (same table, same double-precision polynomial), so
 // together with IEEE division and -fmad=false the kernel reproduces the CPU oracle bit for
 // bit rather than to a tolerance.
+#include <algorithm>
 #include <cstdlib>
 
 #include "common.cuh"
@@ -77,7 +78,7 @@ __device__ __forceinline__ float exp_glibc(float x, const unsigned long long* __
 
 struct Ctx {
     const unsigned long long* tab;
-    unsigned long long* diag;
+    unsigned* flags;          // per-thread diagnostic bits, flushed with one atomic per set bit at the end
     float c2r, c2s;
 };
 
@@ -99,7 +100,7 @@ __device__ __forceinline__ void phase_change(float& t, float& q1, float qmax, fl
     q1 = q1 - delta;
     if (q1 < 0.f) {
         if ((q1 + SMALL_VALUE) < 0.f) q1 = 0.f;
-        else atomicAdd(cx.diag + 2, 1ULL);         // reference: print + stop
+        else *cx.flags |= 4u;                      // reference: print + stop
     }
     q2 = q2 + delta;
     t = t + delta * mass2temp;
@@ -150,10 +151,10 @@ __device__ __forceinline__ void mp_conversions(float p, float& t, float& qv, flo
             qv = sat_mr(pre_t, p, cx);
             t = pre_t;
             qc = pre_qc;
-            atomicAdd(cx.diag + 0, 1ULL);
+            *cx.flags |= 1u;
         }
         qc = fmaxf(qc, 0.f);
-        if ((t > 350.f) || (qc > 0.01f) || (qvsat > 1.f)) atomicAdd(cx.diag + 1, 1ULL);
+        if ((t > 350.f) || (qc > 0.01f) || (qvsat > 1.f)) *cx.flags |= 2u;
     }
     if ((qc + qr + qs) > SMALL_VALUE) {
         if (qc > SMALL_VALUE) {
@@ -179,8 +180,12 @@ k_mp_simple(Geom g, const float* __restrict__ gp, float* __restrict__ gth,
             const float* __restrict__ gpii, const float* __restrict__ grho,
             float* __restrict__ gqv, float* __restrict__ gqc, float* __restrict__ gqr,
             float* __restrict__ gqs, float* __restrict__ rain, float* __restrict__ snow, int ld2,
-            float dt, const float* __restrict__ gdz, int its, int ite, int jts, int jte, int kts,
+            float dt, const float* __restrict__ gdz, MpTiles tiles, int kts,
             int kte, float c2r, float c2s, unsigned long long* diag) {
+    // blockIdx.z selects one of up to 4 disjoint tiles (the ring strips of process_halo share a launch)
+    const int its = tiles.its[blockIdx.z], ite = tiles.ite[blockIdx.z];
+    const int jts = tiles.jts[blockIdx.z], jte = tiles.jte[blockIdx.z];
+    if (its + (int)blockIdx.x * TX > ite || jts + (int)blockIdx.y > jte) return;
     extern __shared__ float sm[];
     const int nz = g.nz;
     const int nzt = blockDim.y;                 // z-threads; thread owns levels tz + c*nzt
@@ -191,7 +196,8 @@ k_mp_simple(Geom g, const float* __restrict__ gp, float* __restrict__ gth,
     const int i = its + blockIdx.x * TX + tx;
     const int j = jts + blockIdx.y;
     const bool col_ok = (i <= ite);
-    const Ctx cx{kExp2fTab, diag, c2r, c2s};
+    unsigned dflags = 0u;
+    const Ctx cx{kExp2fTab, &dflags, c2r, c2s};
     const int top = min(kte, nz - 2);
 
     float T[CPT], p[CPT], rho[CPT], dz[CPT], pii[CPT], qv[CPT], qc[CPT], qr[CPT], qs[CPT];
@@ -317,36 +323,52 @@ k_mp_simple(Geom g, const float* __restrict__ gp, float* __restrict__ gth,
         gqv[a] = qv[c]; gqc[a] = qc[c]; gqr[a] = qr[c]; gqs[a] = qs[c];
     }
     if (owner && (n_r > 0 || n_s > 0)) { rain[c2] = rain_acc; snow[c2] = snow_acc; }
+    if (dflags) {                // events, not cells: the counters say "how many threads saw it"
+        if (dflags & 1u) atomicAdd(diag + 0, 1ULL);
+        if (dflags & 2u) atomicAdd(diag + 1, 1ULL);
+        if (dflags & 4u) atomicAdd(diag + 2, 1ULL);
+    }
 }
 
-// domain%accumulated_precipitation (REAL*8) += precipitation (mp_driver.f90:587-595)
+// domain%accumulated_precipitation (REAL*8) += precipitation (mp_driver.f90:587-595); up to two
+// per-call REAL*4 pairs (interior tile and ring strips, disjoint cells) in one pass
 __global__ void k_accumulate_precip(int nx, int ny, int ld2, const float* __restrict__ rain,
-                                    const float* __restrict__ snow, double* __restrict__ acc_rain,
+                                    const float* __restrict__ snow, const float* __restrict__ rain_b,
+                                    const float* __restrict__ snow_b, double* __restrict__ acc_rain,
                                     double* __restrict__ acc_snow) {
     int i = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y;
     if (i >= nx || j >= ny) return;
     size_t c = (size_t)i + (size_t)ld2 * j;
-    if (acc_rain) acc_rain[c] = acc_rain[c] + (double)rain[c];
-    if (acc_snow) acc_snow[c] = acc_snow[c] + (double)snow[c];
+    double r = acc_rain[c], s = acc_snow[c];
+    if (rain) { r = r + (double)rain[c]; s = s + (double)snow[c]; }
+    if (rain_b) { r = r + (double)rain_b[c]; s = s + (double)snow_b[c]; }
+    acc_rain[c] = r;
+    acc_snow[c] = s;
 }
 
 }  // namespace
 
 int mp_simple_launch(const Geom& g, const float* p, float* th, const float* pii, const float* rho,
                      float* qv, float* qc, float* qr, float* qs, float* rain, float* snow, int ld2,
-                     float dt, const float* dz, int its, int ite, int jts, int jte, int kts,
-                     int kte, float c2r, float c2s, unsigned long long* diag, cudaStream_t st) {
-    if (ite < its || jte < jts) return 0;
+                     float dt, const float* dz, const MpTiles& tiles, int kts, int kte, float c2r,
+                     float c2s, unsigned long long* diag, cudaStream_t st) {
+    int gx = 0, gy = 0;
+    for (int t = 0; t < tiles.n; ++t) {
+        if (tiles.ite[t] < tiles.its[t] || tiles.jte[t] < tiles.jts[t]) continue;
+        gx = std::max(gx, (tiles.ite[t] - tiles.its[t] + 1 + TX - 1) / TX);
+        gy = std::max(gy, tiles.jte[t] - tiles.jts[t] + 1);
+    }
+    if (gx == 0 || gy == 0) return 0;
     int cpt = (g.nz + 9) / 10;                              // cells per thread: ~10 z-threads per CTA
     if (const char* e = std::getenv("ICAR_MP_CPT")) { int v = std::atoi(e); if (v >= 1 && v <= 8 && v * 10 >= g.nz) cpt = v; }
     if (cpt > 8) return -1;                                 // nz > 80 is not built
     const int nzt = (g.nz + cpt - 1) / cpt;
     dim3 block(TX, nzt);
-    dim3 grid((ite - its + 1 + TX - 1) / TX, jte - jts + 1);
+    dim3 grid(gx, gy, tiles.n);
     size_t smem = (size_t)(2 * (g.nz + 1) + 3) * TX * sizeof(float);
 #define LAUNCH(C)                                                                                 \
     k_mp_simple<C><<<grid, block, smem, st>>>(g, p, th, pii, rho, qv, qc, qr, qs, rain, snow, ld2, \
-                                              dt, dz, its, ite, jts, jte, kts, kte, c2r, c2s, diag)
+                                              dt, dz, tiles, kts, kte, c2r, c2s, diag)
     switch (cpt) {
         case 1: LAUNCH(1); break;
         case 2: LAUNCH(2); break;
@@ -362,10 +384,11 @@ int mp_simple_launch(const Geom& g, const float* p, float* th, const float* pii,
 }
 
 int accumulate_precip_launch(int nx, int ny, int ld2, const float* rain, const float* snow,
-                             double* acc_rain, double* acc_snow, cudaStream_t st) {
+                             const float* rain_b, const float* snow_b, double* acc_rain,
+                             double* acc_snow, cudaStream_t st) {
     dim3 block(128);
     dim3 grid((nx + 127) / 128, ny);
-    k_accumulate_precip<<<grid, block, 0, st>>>(nx, ny, ld2, rain, snow, acc_rain, acc_snow);
+    k_accumulate_precip<<<grid, block, 0, st>>>(nx, ny, ld2, rain, snow, rain_b, snow_b, acc_rain, acc_snow);
     return 1;
 }
 

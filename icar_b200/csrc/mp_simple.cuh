@@ -4,17 +4,24 @@
 
 namespace icar {
 
+// up to 4 disjoint 0-based inclusive tiles processed by one launch
+struct MpTiles {
+    int n;
+    int its[4], ite[4], jts[4], jte[4];
+};
+
 // mp_simple_driver (mp_simple.f90:595-646) on the 0-based inclusive tile its..ite, jts..jte,
 // kts..kte.  rain/snow are (nx,ny) REAL*4 with row pitch ld2.  c2r/c2s = cloud2rain/cloud2snow
 // (:619-620), diag = 3 device counters (see icar_mp_diagnostics).
 int mp_simple_launch(const Geom& g, const float* p, float* th, const float* pii, const float* rho,
                      float* qv, float* qc, float* qr, float* qs, float* rain, float* snow, int ld2,
-                     float dt, const float* dz, int its, int ite, int jts, int jte, int kts,
-                     int kte, float c2r, float c2s, unsigned long long* diag, cudaStream_t st);
+                     float dt, const float* dz, const MpTiles& tiles, int kts, int kte, float c2r,
+                     float c2s, unsigned long long* diag, cudaStream_t st);
 
 // accumulated_precipitation / accumulated_snowfall (REAL*8) += the step's REAL*4 totals
 // (mp_driver.f90:587-595)
 int accumulate_precip_launch(int nx, int ny, int ld2, const float* rain, const float* snow,
-                             double* acc_rain, double* acc_snow, cudaStream_t st);
+                             const float* rain_b, const float* snow_b, double* acc_rain,
+                             double* acc_snow, cudaStream_t st);
 
 }  // namespace icar

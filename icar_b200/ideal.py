@@ -130,3 +130,23 @@ def make_ideal_case(nx=100, nz=20, ny=100, dx=4000.0, dz_level=400.0, terrain=Tr
 
 def copy_state(st):
     return {k: (v.copy() if isinstance(v, np.ndarray) else v) for k, v in st.items()}
+
+
+def slab_of(st, grid):
+    """The part of a global state dict one image holds (ghost cells included) for a slab `grid`
+    (x-slab or y-slab: whichever of ims..ime / jms..jme is narrower than the domain)."""
+    ilo, ihi = grid.ims - 1, grid.ime
+    jlo, jhi = grid.jms - 1, grid.jme
+    out = {}
+    for k, v in st.items():
+        if not isinstance(v, np.ndarray) or v.ndim < 2:
+            out[k] = v
+        elif v.ndim == 2:                                   # (ny, nx)
+            out[k] = np.ascontiguousarray(v[jlo:jhi, ilo:ihi])
+        elif k in ("u", "jacobian_u"):                      # (ny, nz, nx+1)
+            out[k] = np.ascontiguousarray(v[jlo:jhi, :, ilo:ihi + 1])
+        elif k in ("v", "jacobian_v"):                      # (ny+1, nz, nx)
+            out[k] = np.ascontiguousarray(v[jlo:jhi + 1, :, ilo:ihi])
+        else:
+            out[k] = np.ascontiguousarray(v[jlo:jhi, :, ilo:ihi])
+    return out

@@ -173,15 +173,26 @@ int icar_timer_stop(icar_ctx* ctx, float* elapsed_ms);
 
 /* ------------------------------------------------- multi-image (one process per GPU) */
 
-/* Which local columns (0-based offsets from ims) one image exchanges with its x neighbours, for
- * `halo_size` = h columns per side -- exchangeable_obj.f90:303-356 restated as index ranges:
- *   plan[0] first column SENT west   (put_west:           data(start+h : start+2h-1))
- *   plan[1] first column SENT east   (put_east:           data(n-2h+1 : n-h))
- *   plan[2] first column RECEIVED from the west (retrieve_west_halo: data(start : start+h-1))
- *   plan[3] first column RECEIVED from the east (retrieve_east_halo: data(n-h+1 : n))
- *   plan[4] 1 if a west neighbour exists, plan[5] 1 if an east neighbour exists.
+/* Same for a y-slab decomposition (ximages = 1, yimages = nimages): every image keeps full x-rows,
+ * which keeps all kernels at full SIMD width and makes the exchanged faces contiguous planes (no
+ * pack / unpack kernels: ncclSend / ncclRecv go straight from / into the fields).  This is what
+ * bench.py uses for N > 1; x-slabs remain supported. */
+int icar_grid_yslab(int nx_global, int nz, int ny_global, int nimages, int image, int halo_size,
+                    icar_grid* out);
+
+/* Which local columns (x-slabs) or planes (y-slabs), as 0-based offsets from ims / jms, one image
+ * exchanges with its two neighbours for `halo_size` = h -- exchangeable_obj.f90:249-356 restated
+ * as index ranges (put_west/put_south send data(start+h : start+2h-1), put_east/put_north send
+ * data(n-2h+1 : n-h); retrieve_* fill data(start : start+h-1) and data(n-h+1 : n)):
+ *   plan[0] first index SENT to the lower neighbour (west / south)
+ *   plan[1] first index SENT to the upper neighbour (east / north)
+ *   plan[2] first index RECEIVED from the lower neighbour
+ *   plan[3] first index RECEIVED from the upper neighbour
+ *   plan[4] 1 if a lower neighbour exists, plan[5] 1 if an upper neighbour exists
+ *   plan[6] exchange axis: 0 = x (columns), 1 = y (planes);  plan[7] = h
+ * The axis is read off the grid (which of ims/ime or jms/jme stops short of the domain bounds).
  * Pure host function (no GPU needed); icar_halo_send / icar_halo_retrieve use the same plan. */
-int icar_halo_plan(const icar_grid* grid, int image, int nimages, int plan[6]);
+int icar_halo_plan(const icar_grid* grid, int image, int nimages, int plan[8]);
 
 /* ncclUniqueId bootstrap: image 1 calls icar_comm_unique_id and broadcasts the 128 bytes with
  * whatever the host program already has (coarray co_broadcast, MPI, torch.distributed); then

@@ -67,6 +67,23 @@ def test_grid_xslab_matches_grid_obj(nx, nimg, halo):
         assert c == b + 1
 
 
+def test_grid_yslab_mirrors_xslab():
+    for img in (1, 2, 3):
+        gx = icar_b200.Grid.xslab(100, 20, 64, 3, img, 3)
+        gy = icar_b200.Grid.yslab(64, 20, 100, 3, img, 3)
+        assert (gx.ims, gx.ime, gx.its, gx.ite) == (gy.jms, gy.jme, gy.jts, gy.jte)
+        assert (gy.ims, gy.ime, gy.its, gy.ite) == (1, 64, 2, 63)
+        px, py = icar_b200.halo_plan(gx, img, 3), icar_b200.halo_plan(gy, img, 3)
+        assert px["axis"] == "x" and py["axis"] == "y"
+        for k in ("send_lo", "send_hi", "recv_lo", "recv_hi", "has_lo", "has_hi", "width"):
+            assert px[k] == py[k]
+    # exchangeable_obj.f90:303-356: send the h owned columns next to the ghost zone, fill the ghost zone
+    g = icar_b200.Grid.xslab(100, 20, 64, 3, 2, 3)
+    p = icar_b200.halo_plan(g, 2, 3)
+    n = g.nx
+    assert (p["send_lo"], p["send_hi"], p["recv_lo"], p["recv_hi"]) == (3, n - 6, 0, n - 3)
+
+
 def test_grid_xslab_rejects_bad_arguments():
     g = icar_b200.Grid()
     lib = icar_b200.lib()

@@ -28,22 +28,7 @@ def _free_port():
     return p
 
 
-def _slab(st, g):
-    lo, hi = g.ims - 1, g.ime
-    out = {}
-    for k, v in st.items():
-        if not isinstance(v, np.ndarray):
-            out[k] = v
-        elif k in ("u", "jacobian_u"):
-            out[k] = np.ascontiguousarray(v[:, :, lo:hi + 1])
-        elif v.ndim in (2, 3):
-            out[k] = np.ascontiguousarray(v[..., lo:hi])
-        else:
-            out[k] = v
-    return out
-
-
-def _worker(rank, world, port, halo, steps, nx, nz, ny, result_dir):
+def _worker(rank, world, port, halo, axis, steps, nx, nz, ny, result_dir):
     sys.path.insert(0, ROOT)
     import torch
     import torch.distributed as dist
@@ -56,10 +41,14 @@ def _worker(rank, world, port, halo, steps, nx, nz, ny, result_dir):
     st = ideal.make_ideal_case(nx=nx, nz=nz, ny=ny, perturb=True)
     st["qv"] *= np.float32(3.0)
     dt = np.float32(st["dt"])
-    grid = icar_b200.Grid.xslab(nx, nz, ny, world, rank + 1, halo)
+    grid = (icar_b200.Grid.xslab if axis == "x" else icar_b200.Grid.yslab)(nx, nz, ny, world, rank + 1, halo)
     plan = icar_b200.halo_plan(grid, rank + 1, world)
-    loc = _slab(st, grid)
-    nxl = grid.nx
+    assert plan["axis"] == axis
+    loc = ideal.slab_of(st, grid)
+    ax = 2 if axis == "x" else 0                      # NumPy axis of the exchange direction
+
+    def strip(a, first, width):
+        return a[:, :, first:first + width] if ax == 2 else a[first:first + width]
     U = V = W = None
     for _ in range(steps):
         # mp on the physics tile of this image (its..ite, jts..jte)  [time_step.f90:512,523]
@@ -69,11 +58,11 @@ def _worker(rank, world, port, halo, steps, nx, nz, ny, result_dir):
         # halo_send / halo_retrieve [time_step.f90:515,526]: one message per neighbour, all fields
         h = plan["width"]
         reqs, recv = [], {}
-        for side, peer, has in (("west", rank - 1, plan["has_west"]), ("east", rank + 1, plan["has_east"])):
+        for side, peer, has in (("lo", rank - 1, plan["has_lo"]), ("hi", rank + 1, plan["has_hi"])):
             if not has:
                 continue
             s0 = plan["send_" + side]
-            out = torch.from_numpy(np.stack([loc[k][:, :, s0:s0 + h] for k in FIELDS]).copy())
+            out = torch.from_numpy(np.stack([strip(loc[k], s0, h) for k in FIELDS]).copy())
             buf = torch.empty_like(out)
             recv[side] = buf
             reqs.append(dist.isend(out, peer))
@@ -83,28 +72,33 @@ def _worker(rank, world, port, halo, steps, nx, nz, ny, result_dir):
         for side, buf in recv.items():
             r0 = plan["recv_" + side]
             for n, k in enumerate(FIELDS):
-                loc[k][:, :, r0:r0 + h] = buf[n].numpy()
+                strip(loc[k], r0, h)[...] = buf[n].numpy()
         # advect on the whole local array [time_step.f90:529]
         U, V, W = O.wind_normalise(loc["u"], loc["v"], loc["w"], loc["jacobian_u"], loc["jacobian_v"],
                                    loc["jacobian_w"], None, dt, st["dx"])
         for k in ("qv", "qc", "qr", "qs", "th"):
             O.advect3d(loc[k], None, loc["jacobian"], loc["advection_dz"], U, V, W, 2, True)
-    lo = 0 if rank == 0 else grid.its - grid.ims
-    hi = nxl if rank == world - 1 else grid.ite - grid.ims + 1
-    g0 = grid.ims - 1 + lo
-    np.savez(os.path.join(result_dir, f"rank{rank}.npz"), g0=g0, **{k: loc[k][:, :, lo:hi] for k in FIELDS})
+    if axis == "x":
+        lo = 0 if rank == 0 else grid.its - grid.ims
+        hi = grid.nx if rank == world - 1 else grid.ite - grid.ims + 1
+        g0 = grid.ims - 1 + lo
+    else:
+        lo = 0 if rank == 0 else grid.jts - grid.jms
+        hi = grid.ny if rank == world - 1 else grid.jte - grid.jms + 1
+        g0 = grid.jms - 1 + lo
+    np.savez(os.path.join(result_dir, f"rank{rank}.npz"), g0=g0, **{k: strip(loc[k], lo, hi - lo) for k in FIELDS})
     dist.barrier()
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("halo", [3, 1])
-def test_two_rank_xslab_matches_single_image(tmp_path, oracle, halo):
+@pytest.mark.parametrize("axis,halo", [("x", 3), ("y", 3), ("x", 1)])
+def test_two_rank_slabs_match_single_image(tmp_path, oracle, axis, halo):
     import torch.multiprocessing as mp
     from icar_b200 import ideal
 
-    nx, nz, ny, steps, world = 40, 8, 12, 3, 2
+    nx, nz, ny, steps, world = (40, 8, 12, 3, 2) if axis == "x" else (14, 8, 36, 3, 2)
     port = _free_port()
-    mp.spawn(_worker, args=(world, port, halo, steps, nx, nz, ny, str(tmp_path)), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, port, halo, axis, steps, nx, nz, ny, str(tmp_path)), nprocs=world, join=True)
     # single-image reference run
     st = ideal.make_ideal_case(nx=nx, nz=nz, ny=ny, perturb=True)
     st["qv"] *= np.float32(3.0)
@@ -112,18 +106,18 @@ def test_two_rank_xslab_matches_single_image(tmp_path, oracle, halo):
     for _ in range(steps):
         oracle.step_simple(st, dt, dt, 2, True)
     worst = 0.0
-    covered = np.zeros(nx, bool)
+    covered = np.zeros(nx if axis == "x" else ny, bool)
     for r in range(world):
         d = np.load(os.path.join(tmp_path, f"rank{r}.npz"))
         g0 = int(d["g0"])
         for k in FIELDS:
             part = d[k]
-            ref = st[k][:, :, g0:g0 + part.shape[2]]
+            ref = st[k][:, :, g0:g0 + part.shape[2]] if axis == "x" else st[k][g0:g0 + part.shape[0]]
             if halo == 3:
                 assert np.array_equal(part, ref), (r, k)
             else:
                 worst = max(worst, float(np.abs(part - ref).max() / max(float(np.abs(ref).max()), 1e-30)))
-        covered[g0:g0 + d[FIELDS[0]].shape[2]] = True
+        covered[g0:g0 + d[FIELDS[0]].shape[2 if axis == "x" else 0]] = True
     assert covered.all()
     if halo == 1:
         # the reference's 1-cell halo is refreshed once per step, short of MPDATA's 3-cell
