@@ -228,6 +228,8 @@ int run_mp_tiles(icar_ctx* ctx, float mp_dt, const int (*t)[4], int ntiles, int 
             if (t[a][1] < t[a][0] || t[a][3] < t[a][2]) continue;
             tiles.its[tiles.n] = t[a][0] - gr.ims; tiles.ite[tiles.n] = t[a][1] - gr.ims;
             tiles.jts[tiles.n] = t[a][2] - gr.jms; tiles.jte[tiles.n] = t[a][3] - gr.jms;
+            // strips narrower than a warp in x but long in y: run the lanes along y
+            tiles.along_y[tiles.n] = ((t[a][1] - t[a][0] + 1) < 16 && (t[a][3] - t[a][2] + 1) > (t[a][1] - t[a][0] + 1)) ? 1 : 0;
             ++tiles.n;
         }
         if (tiles.n == 0) return ICAR_OK;
@@ -593,6 +595,14 @@ extern "C" int icar_advect(icar_ctx* ctx, float dt) {
 
 // ============================================================================ mp
 
+// mp() as step() needs it, without the reference's fixed ring geometry.  The only purpose of the
+// mp(halo) / mp(subset) pair in time_step.f90:512-526 is to finish the cells a neighbour needs before
+// the exchange starts; which cells those are depends on the decomposition:
+//   phase 0 ("halo")   : the h rows/columns next to each ghost zone of the exchange axis
+//   phase 1 ("subset") : every other cell of the physics tile
+// Both phases together cover the tile exactly once, like process_halo + process_subdomain(subset).
+int mp_phase(icar_ctx* ctx, float dt_in, int phase, int axis, int h);
+
 extern "C" int icar_mp(icar_ctx* ctx, float dt_in, int halo, int subset) {
     if (!ctx) return ICAR_ERR_INVALID;
     CU(cudaSetDevice(ctx->device));
@@ -638,6 +648,43 @@ extern "C" int icar_mp(icar_ctx* ctx, float dt_in, int halo, int subset) {
             ctx->aux_pending = true;
         }
         CU(cudaGetLastError());
+    }
+    return ICAR_OK;
+}
+
+int mp_phase(icar_ctx* ctx, float dt_in, int phase, int axis, int h) {
+    int rc = need_uploaded(ctx, {ICAR_VAR_PRESSURE, ICAR_VAR_EXNER, ICAR_VAR_DENSITY, ICAR_VAR_DZ_MASS}, "icar_physics_step");
+    if (rc) return rc;
+    if (ctx->opt.microphysics == 0) return ICAR_OK;
+    const icar_grid& gr = ctx->grid;
+    if (ctx->last_model_time == -999.0)                                                   // mp_driver.f90:698-700
+        ctx->last_model_time = ctx->model_time - (double)std::max((float)ctx->opt.update_interval, dt_in);
+    if (!(((ctx->model_time + (double)dt_in) - ctx->last_model_time) >= (double)ctx->opt.update_interval)) return ICAR_OK;
+    const float mp_dt = (float)(ctx->model_time - ctx->last_model_time);
+    if (phase == 1) ctx->last_model_time = ctx->model_time;                               // :711-713
+    int kte = gr.kte;
+    if (ctx->opt.top_mp_level > 0) kte = std::min(kte, ctx->opt.top_mp_level);
+    const size_t b2 = (size_t)2 * ctx->ld2 * ctx->g.ny * sizeof(float);
+    // strips exist only next to a ghost zone (an interior edge of the decomposition)
+    const bool lo = axis ? (gr.jms > gr.jds) : (gr.ims > gr.ids);
+    const bool hi = axis ? (gr.jme < gr.jde) : (gr.ime < gr.ide);
+    const int a0 = axis ? gr.jts : gr.its, a1 = axis ? gr.jte : gr.ite;
+    const int in0 = lo ? a0 + h : a0, in1 = hi ? a1 - h : a1;
+    if (phase == 0) {
+        if ((rc = join_aux(ctx))) return rc;
+        CU(cudaMemsetAsync(ctx->rain2d_halo, 0, b2, ctx->stream));
+        int t[2][4], n = 0;
+        if (lo) { t[n][0] = axis ? gr.its : a0; t[n][1] = axis ? gr.ite : a0 + h - 1; t[n][2] = axis ? a0 : gr.jts; t[n][3] = axis ? a0 + h - 1 : gr.jte; ++n; }
+        if (hi) { t[n][0] = axis ? gr.its : a1 - h + 1; t[n][1] = axis ? gr.ite : a1; t[n][2] = axis ? a1 - h + 1 : gr.jts; t[n][3] = axis ? a1 : gr.jte; ++n; }
+        if ((rc = run_mp_tiles(ctx, mp_dt, t, n, gr.kts, kte, ctx->stream, ctx->rain2d_halo, ctx->snow2d_halo))) return rc;
+        CU(cudaEventRecord(ctx->ev_aux, ctx->stream));
+        ctx->aux_pending = true;      // (recorded on the compute stream: join_aux's wait is then a no-op)
+    } else {
+        if (ctx->main_acc_pending && (rc = join_aux(ctx))) return rc;
+        CU(cudaMemsetAsync(ctx->rain2d, 0, b2, ctx->stream));
+        const int t[1][4] = {{axis ? gr.its : in0, axis ? gr.ite : in1, axis ? in0 : gr.jts, axis ? in1 : gr.jte}};
+        if ((rc = run_mp_tiles(ctx, mp_dt, t, 1, gr.kts, kte, ctx->stream, ctx->rain2d, ctx->snow2d))) return rc;
+        ctx->main_acc_pending = true;
     }
     return ICAR_OK;
 }
@@ -786,10 +833,17 @@ extern "C" int icar_physics_step(icar_ctx* ctx, float dt) {
     int rc;
     const int h = ctx->grid.halo_size;
     if (dt > 1e-3f) {                                             // time_step.f90:484
-        if ((rc = icar_mp(ctx, dt, h, -1))) return rc;            // :512  mp(halo=1)
-        if ((rc = icar_halo_send(ctx))) return rc;                // :515
-        if ((rc = icar_mp(ctx, dt, -1, h))) return rc;            // :523  mp(subset=1)
-        if ((rc = icar_halo_retrieve(ctx))) return rc;            // :526
+        if (ctx->nimages == 1) {
+            // nothing to exchange: mp(halo=1) + mp(subset=1) of :512,:523 is one whole-tile call
+            if ((rc = icar_mp(ctx, dt, -1, -1))) return rc;
+        } else {
+            int plan[8];
+            if (icar_halo_plan(&ctx->grid, ctx->image, ctx->nimages, plan)) return fail(ctx, ICAR_ERR_INVALID, "icar_physics_step: not a slab decomposition");
+            if ((rc = mp_phase(ctx, dt, 0, plan[6], h))) return rc;   // :512  the cells the neighbours need
+            if ((rc = icar_halo_send(ctx))) return rc;                // :515
+            if ((rc = mp_phase(ctx, dt, 1, plan[6], h))) return rc;   // :523  everything else, overlapping the exchange
+            if ((rc = icar_halo_retrieve(ctx))) return rc;            // :526
+        }
         if ((rc = icar_advect(ctx, dt))) return rc;               // :529
     }
     ctx->model_time += (double)dt;                                // :547
@@ -923,6 +977,7 @@ extern "C" int icar_mp_simple_driver(icar_ctx* ctx, const float* pressure, float
     MpTiles tiles;
     tiles.n = 1;
     tiles.its[0] = its - ims; tiles.ite[0] = ite - ims; tiles.jts[0] = jts - jms; tiles.jte[0] = jte - jms;
+    tiles.along_y[0] = 0;
     {
         int nl = mp_simple_launch(g, (float*)b[0], (float*)b[1], (float*)b[2], (float*)b[3], (float*)b[4],
                                   (float*)b[5], (float*)b[6], (float*)b[7], (float*)b[9], (float*)b[10], ctx->ld2, dt,

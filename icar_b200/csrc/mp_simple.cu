@@ -185,7 +185,10 @@ k_mp_simple(Geom g, const float* __restrict__ gp, float* __restrict__ gth,
     // blockIdx.z selects one of up to 4 disjoint tiles (the ring strips of process_halo share a launch)
     const int its = tiles.its[blockIdx.z], ite = tiles.ite[blockIdx.z];
     const int jts = tiles.jts[blockIdx.z], jte = tiles.jte[blockIdx.z];
-    if (its + (int)blockIdx.x * TX > ite || jts + (int)blockIdx.y > jte) return;
+    const bool along_y = tiles.along_y[blockIdx.z] != 0;
+    // lanes run along x (coalesced rows) or, for strips a few columns wide, along y
+    const int lane0 = (int)blockIdx.x * TX, row = (int)blockIdx.y;
+    if (along_y ? (jts + lane0 > jte || its + row > ite) : (its + lane0 > ite || jts + row > jte)) return;
     extern __shared__ float sm[];
     const int nz = g.nz;
     const int nzt = blockDim.y;                 // z-threads; thread owns levels tz + c*nzt
@@ -193,9 +196,9 @@ k_mp_simple(Geom g, const float* __restrict__ gp, float* __restrict__ gth,
     float* s_q = sm;                            // [(nz+1)][TX]
     float* s_rho = s_q + (nz + 1) * TX;         // [(nz+1)][TX]
     float* s_red = s_rho + (nz + 1) * TX;       // [3][TX]: max qr, max qs, max dt/dz
-    const int i = its + blockIdx.x * TX + tx;
-    const int j = jts + blockIdx.y;
-    const bool col_ok = (i <= ite);
+    const int i = along_y ? its + row : its + lane0 + tx;
+    const int j = along_y ? jts + lane0 + tx : jts + row;
+    const bool col_ok = (i <= ite) && (j <= jte);
     unsigned dflags = 0u;
     const Ctx cx{kExp2fTab, &dflags, c2r, c2s};
     const int top = min(kte, nz - 2);
@@ -261,7 +264,7 @@ k_mp_simple(Geom g, const float* __restrict__ gp, float* __restrict__ gth,
     const int nmax_s = __reduce_max_sync(0xffffffffu, n_s);
     const float L_melt = -1.f * LH_liquid;
     // accumulated in the one thread of the column that owns level kts, in the reference's order
-    const size_t c2 = (size_t)(col_ok ? i : its) + (size_t)ld2 * (size_t)j;
+    const size_t c2 = (size_t)(col_ok ? i : its) + (size_t)ld2 * (size_t)(col_ok ? j : jts);
     bool owner = false;
 #pragma unroll
     for (int c = 0; c < CPT; ++c) owner = owner || (live[c] && (tz + c * nzt) == kts);
@@ -355,8 +358,9 @@ int mp_simple_launch(const Geom& g, const float* p, float* th, const float* pii,
     int gx = 0, gy = 0;
     for (int t = 0; t < tiles.n; ++t) {
         if (tiles.ite[t] < tiles.its[t] || tiles.jte[t] < tiles.jts[t]) continue;
-        gx = std::max(gx, (tiles.ite[t] - tiles.its[t] + 1 + TX - 1) / TX);
-        gy = std::max(gy, tiles.jte[t] - tiles.jts[t] + 1);
+        const int w = tiles.ite[t] - tiles.its[t] + 1, h = tiles.jte[t] - tiles.jts[t] + 1;
+        gx = std::max(gx, ((tiles.along_y[t] ? h : w) + TX - 1) / TX);
+        gy = std::max(gy, tiles.along_y[t] ? w : h);
     }
     if (gx == 0 || gy == 0) return 0;
     int cpt = (g.nz + 9) / 10;                              // cells per thread: ~10 z-threads per CTA

@@ -8,6 +8,7 @@ namespace icar {
 struct MpTiles {
     int n;
     int its[4], ite[4], jts[4], jte[4];
+    int along_y[4];     // 1: the 32 lanes of a warp run along j (for strips only a few columns wide)
 };
 
 // mp_simple_driver (mp_simple.f90:595-646) on the 0-based inclusive tile its..ite, jts..jte,
