@@ -28,34 +28,25 @@ def ncu(rep, page):
     return list(csv.reader(io.StringIO(out)))
 
 
-def main():
-    rep = sys.argv[1]
-    cells = float(sys.argv[2]) if len(sys.argv) > 2 else None
-    raw = ncu(rep, "raw")
-    hdr, units, vals = raw[0], raw[1], raw[2]
-    d = dict(zip(hdr, zip(vals, units)))
-    print(f"# {rep}")
-    print(f"kernel: {d.get('Kernel Name', ('?', ''))[0]}")
-    for k in KEYS:
-        if k in d:
-            print(f"{k:80s} {d[k][0]:>16s} {d[k][1]}")
-    stalls = sorted(((float(v[0]), k) for k, v in d.items()
-                     if k.startswith("smsp__average_warps_issue_stalled") and k.endswith("_per_issue_active.ratio")),
-                    reverse=True)
-    print("top warp stall reasons (warps per issue-active cycle):")
-    for v, k in stalls[:6]:
-        print(f"  {k.split('issue_stalled_')[1].split('_per_issue')[0]:28s} {v:6.2f}")
-    src = ncu(rep, "source")
-    h = src[1]
+def source_mix(rep, kernel_id, cells):
+    out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--kernel-id", f":::{kernel_id}"],
+                         capture_output=True, text=True).stdout
+    src = list(csv.reader(io.StringIO(out)))
+    hi = next((n for n, r in enumerate(src) if "Source" in r and "Instructions Executed" in r), None)
+    if hi is None:
+        return
+    h = src[hi]
     ia, ie = h.index("Source"), h.index("Instructions Executed")
     ops = collections.Counter()
-    for r in src[2:]:
-        if len(r) <= ie:
+    for r in src[hi + 1:]:
+        if len(r) <= ie or not (r[ie] or "0").isdigit():
             continue
         m = re.match(r"(@!?U?P\d+\s+)?([A-Z0-9_.]+)", r[ia].strip())
         if m:
             ops[m.group(2).split(".")[0]] += int(r[ie] or 0)
     tot = sum(ops.values())
+    if not tot:
+        return
     print(f"SASS warp-instructions executed: {tot}")
     if cells:
         print(f"lane-instructions per cell: {tot * 32 / cells:.1f}")
@@ -65,6 +56,27 @@ def main():
     tma = [op for op in ops if op.startswith("UTMA") or op.startswith("SYNCS")]
     if tma:
         print("TMA / mbarrier opcodes present:", ", ".join(f"{t} x{ops[t]}" for t in tma))
+
+
+def main():
+    rep = sys.argv[1]
+    cells = float(sys.argv[2]) if len(sys.argv) > 2 else None
+    raw = ncu(rep, "raw")
+    hdr, units = raw[0], raw[1]
+    print(f"# {rep}")
+    for n, vals in enumerate(raw[2:], 1):
+        d = dict(zip(hdr, zip(vals, units)))
+        print(f"\n== launch {n}: {d.get('Kernel Name', ('?', ''))[0][:100]}")
+        for k in KEYS:
+            if k in d:
+                print(f"{k:80s} {d[k][0]:>16s} {d[k][1]}")
+        stalls = sorted(((float(v[0]), k) for k, v in d.items()
+                         if k.startswith("smsp__average_warps_issue_stalled") and k.endswith("_per_issue_active.ratio")),
+                        reverse=True)
+        print("top warp stall reasons (warps per issue-active cycle):")
+        for v, k in stalls[:6]:
+            print(f"  {k.split('issue_stalled_')[1].split('_per_issue')[0]:28s} {v:6.2f}")
+        source_mix(rep, n, cells)
 
 
 if __name__ == "__main__":
