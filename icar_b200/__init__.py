@@ -29,10 +29,12 @@ OK, ERR_INVALID, ERR_CUDA, ERR_PHYSICS, ERR_COMM = 0, 1, 2, 3, 4
 VAR = dict(
     u=0, v=1, w=2, pressure=3, exner=4, density=5, potential_temperature=6, water_vapor=7,
     cloud_water=8, rain_in_air=9, snow_in_air=10, jacobian=11, jacobian_u=12, jacobian_v=13,
-    jacobian_w=14, advection_dz=15, dz_mass=16, precipitation=17, snowfall=18)
+    jacobian_w=14, advection_dz=15, dz_mass=16, precipitation=17, snowfall=18,
+    cloud_ice=19, ice_number=20, rain_number=21, graupel_in_air=22, graupel=23)
 # names used by icar_b200.ideal -> domain_t member names
 ALIASES = dict(th="potential_temperature", qv="water_vapor", qc="cloud_water", qr="rain_in_air",
-               qs="snow_in_air", pii="exner", rho="density")
+               qs="snow_in_air", pii="exner", rho="density", qi="cloud_ice", ni="ice_number",
+               nr="rain_number", qg="graupel_in_air")
 
 ADVECTED_SIMPLE = ("water_vapor", "cloud_water", "rain_in_air", "snow_in_air", "potential_temperature")
 
@@ -94,6 +96,38 @@ class Options(C.Structure):
             setattr(self, k, v)
 
 
+class MpOptions(C.Structure):
+    """mp_options_type (src/objects/opt_types.f90:31-45); defaults options_obj.f90:1259-1280."""
+    _fields_ = [(n, C.c_float) for n in (
+        "Nt_c", "TNO", "am_s", "rho_g", "av_s", "bv_s", "fv_s", "av_i", "av_g", "bv_g",
+        "Ef_si", "Ef_rs", "Ef_rg", "Ef_ri", "C_cubes", "C_sqrd", "mu_r", "t_adjust")] + \
+        [("Ef_rw_l", C.c_int), ("Ef_sw_l", C.c_int)]
+
+    def __init__(self, **kw):
+        super().__init__()
+        lib().icar_default_mp_options(C.byref(self))
+        for k, v in kw.items():
+            if k not in dict(self._fields_):
+                raise TypeError(f"unknown mp option {k}")
+            setattr(self, k, v)
+
+
+# lookup tables in the allocation order of thompson_init (mp_thompson.f90:353-390) + Fortran shapes
+THOMPSON_TABLES = (
+    "tcg_racg", "tmr_racg", "tcr_gacr", "tmg_gacr", "tnr_racg", "tnr_gacr",
+    "tcs_racs1", "tmr_racs1", "tcs_racs2", "tmr_racs2", "tcr_sacr1", "tms_sacr1",
+    "tcr_sacr2", "tms_sacr2", "tnr_racs1", "tnr_racs2", "tnr_sacr1", "tnr_sacr2",
+    "tpi_qcfz", "tni_qcfz", "tpi_qrfz", "tpg_qrfz", "tni_qrfz", "tnr_qrfz",
+    "tps_iaus", "tni_iaus", "tpi_ide", "t_Efrw", "t_Efsw")
+THOMPSON_SHAPES = dict(
+    [(n, (28, 28, 37, 37)) for n in THOMPSON_TABLES[0:6]] +
+    [(n, (28, 9, 37, 37)) for n in THOMPSON_TABLES[6:18]] +
+    [(n, (37, 45)) for n in THOMPSON_TABLES[18:20]] +
+    [(n, (37, 37, 45)) for n in THOMPSON_TABLES[20:24]] +
+    [(n, (64, 55)) for n in THOMPSON_TABLES[24:27]] +
+    [(n, (100, 100)) for n in THOMPSON_TABLES[27:29]])
+
+
 class HostDomain(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in (
         "u", "v", "w", "pressure", "exner", "density", "potential_temperature", "water_vapor",
@@ -112,7 +146,8 @@ SYMBOLS = (
     "icar_timer_start", "icar_timer_stop",
     "icar_halo_plan", "icar_comm_unique_id", "icar_comm_init", "icar_mpdata_set_winds", "icar_mpdata_advect3d",
     "icar_mpdata_set_winds_f64", "icar_mpdata_advect3d_f64", "icar_mp_simple_driver",
-    "icar_physics_step_host", "icar_host_register", "icar_host_unregister")
+    "icar_physics_step_host", "icar_host_register", "icar_host_unregister",
+    "icar_default_mp_options", "icar_thompson_init", "icar_thompson_table", "icar_mp_gt_driver")
 
 
 def lib() -> C.CDLL:
@@ -176,7 +211,7 @@ class Domain:
             return (g.ny, g.nz, g.nx + 1), np.float32
         if name in ("v", "jacobian_v"):
             return (g.ny + 1, g.nz, g.nx), np.float32
-        if name in ("precipitation", "snowfall"):
+        if name in ("precipitation", "snowfall", "graupel"):
             return (g.ny, g.nx), np.float64
         return (g.ny, g.nz, g.nx), np.float32
 
@@ -295,6 +330,37 @@ class Domain:
             _ptr(qc), _ptr(qr), _ptr(qs), _ptr(rain), _ptr(snow), C.c_float(dt), _ptr(_f32(dz)),
             g.ims, g.ime, g.jms, g.jme, g.kms, g.kme, int(its), int(ite), int(jts), int(jte),
             int(kts), int(kte)))
+
+    # -- Thompson microphysics
+    def thompson_init(self, mp_options: "MpOptions | None" = None):
+        """thompson_init(mp_options), mp_thompson.f90:342 -- builds the lookup tables on the device."""
+        self._check(lib().icar_thompson_init(self._h, C.byref(mp_options) if mp_options is not None else None))
+
+    def thompson_table(self, name):
+        """One lookup table as float64, C-order view of the Fortran array (reversed shape)."""
+        n = C.c_longlong()
+        tid = THOMPSON_TABLES.index(name)
+        self._check(lib().icar_thompson_table(self._h, tid, None, C.byref(n)))
+        a = np.empty(n.value, np.float64)
+        self._check(lib().icar_thompson_table(self._h, tid, _ptr(a), C.byref(n)))
+        return a.reshape(THOMPSON_SHAPES[name][::-1])
+
+    def mp_gt_driver(self, st, dt, its, ite, jts, jte, kts, kte, ide=None, jde=None):
+        """mp_gt_driver on host arrays of a state dict (updated in place); bounds are Fortran
+        1-based.  st: th, qv, qc, qr, qi, qs, qg, ni, nr, pii, pressure, dz_mass (3-D float32) and
+        rainnc, sr [, rainncv, snownc, snowncv, graupelnc, graupelncv] (2-D float32)."""
+        g = self.grid
+        for k in ("qv", "qc", "qr", "qi", "qs", "qg", "ni", "nr", "th", "rainnc", "sr"):
+            assert st[k].dtype == np.float32 and st[k].flags["C_CONTIGUOUS"], k
+        o = lambda k: _ptr(st[k]) if st.get(k) is not None else None
+        self._check(lib().icar_mp_gt_driver(
+            self._h, _ptr(st["qv"]), _ptr(st["qc"]), _ptr(st["qr"]), _ptr(st["qi"]), _ptr(st["qs"]),
+            _ptr(st["qg"]), _ptr(st["ni"]), _ptr(st["nr"]), _ptr(st["th"]), _ptr(_f32(st["pii"])),
+            _ptr(_f32(st["pressure"])), _ptr(_f32(st["dz_mass"])), C.c_float(dt), 1,
+            _ptr(st["rainnc"]), o("rainncv"), o("snownc"), o("snowncv"), o("graupelnc"), o("graupelncv"),
+            _ptr(st["sr"]), g.ids, g.ide if ide is None else ide, g.jds, g.jde if jde is None else jde,
+            g.kds, g.kde, g.ims, g.ime, g.jms, g.jme, g.kms, g.kme,
+            int(its), int(ite), int(jts), int(jte), int(kts), int(kte)))
 
     # -- host-domain step (end-to-end path)
     def host_domain(self, st):

@@ -23,6 +23,7 @@
 #include "common.cuh"
 #include "halo.cuh"
 #include "mp_simple.cuh"
+#include "mp_thompson.cuh"
 #include "mpdata.cuh"
 
 using namespace icar;
@@ -40,7 +41,8 @@ Shape var_shape(int var) {
         case ICAR_VAR_V:
         case ICAR_VAR_JACOBIAN_V: return VSTAG;
         case ICAR_VAR_PRECIPITATION:
-        case ICAR_VAR_SNOWFALL: return D2;
+        case ICAR_VAR_SNOWFALL:
+        case ICAR_VAR_GRAUPEL: return D2;
         default: return CELL;
     }
 }
@@ -99,8 +101,14 @@ struct icar_ctx {
     // fused path (mpdata_fused.cu): coefficient fields, per-scalar pass-1 scratch and output buffers
     bool fused = false;
     FusedCoef coef{};
-    float* fq2[5] = {};
-    float* fout[5] = {};
+    float* fq2[ICAR_MAX_SCALARS] = {};
+    float* fout[ICAR_MAX_SCALARS] = {};
+    // scalars advect() moves (adv_mpdata.f90:512-522 order) and halo_send exchanges (domain_obj.f90:106-119
+    // order), as requested by the microphysics scheme's *_var_request (mp_simple.f90:116-118, mp_driver.f90:128-131)
+    int nadv = 0, adv[ICAR_MAX_SCALARS] = {};
+    int nexch = 0, exch[ICAR_MAX_EXCHANGED] = {};
+    // Thompson per-call REAL*4 graupel [tile | ring strips] and the module array SR (mp_driver.f90:411-413,440)
+    float *graupel2d = nullptr, *graupel2d_halo = nullptr, *sr2d = nullptr;
     // per-call REAL*4 precipitation: [rain | snow] of the main-stream tile and of the ring strips
     float *rain2d = nullptr, *snow2d = nullptr, *rain2d_halo = nullptr, *snow2d_halo = nullptr;
     cudaStream_t aux = nullptr;      // the ring strips of mp(halo) run here, next to mp(subset)
@@ -119,6 +127,13 @@ struct icar_ctx {
     float *send_w = nullptr, *send_e = nullptr, *recv_w = nullptr, *recv_e = nullptr;
     bool exchange_in_flight = false;
     bool winds_f64_valid = false;
+    // module state of mp_thompson (constants + the 29 lookup tables), filled by icar_thompson_init
+    bool th_ready = false;
+    ThConst thc{};
+    ThTables tht{};
+    double* th_tab[TH_NTABLES] = {};
+    double *th_bins = nullptr, *th_aux = nullptr;
+    unsigned long long* th_diag = nullptr;     // [0] columns that took the no_micro exit
 };
 
 namespace {
@@ -198,11 +213,18 @@ int copy_out(icar_ctx* ctx, void* host, const void* dev, int width, int pitch, s
     return ICAR_OK;
 }
 
+// advect(): the order of adv_mpdata.f90:512-522 restricted to options%vars_to_advect
 const int kAdvectedSimple[5] = {ICAR_VAR_WATER_VAPOR, ICAR_VAR_CLOUD_WATER, ICAR_VAR_RAIN_IN_AIR,
                                 ICAR_VAR_SNOW_IN_AIR, ICAR_VAR_POTENTIAL_TEMPERATURE};
+const int kAdvectedThompson[9] = {ICAR_VAR_WATER_VAPOR, ICAR_VAR_CLOUD_WATER, ICAR_VAR_RAIN_IN_AIR,
+                                  ICAR_VAR_SNOW_IN_AIR, ICAR_VAR_POTENTIAL_TEMPERATURE, ICAR_VAR_CLOUD_ICE,
+                                  ICAR_VAR_GRAUPEL_IN_AIR, ICAR_VAR_ICE_NUMBER, ICAR_VAR_RAIN_NUMBER};
 // order of domain%halo_send (domain_obj.f90:106-119) restricted to the allocated scalars
 const int kExchangedSimple[5] = {ICAR_VAR_WATER_VAPOR, ICAR_VAR_POTENTIAL_TEMPERATURE,
                                  ICAR_VAR_CLOUD_WATER, ICAR_VAR_RAIN_IN_AIR, ICAR_VAR_SNOW_IN_AIR};
+const int kExchangedThompson[9] = {ICAR_VAR_WATER_VAPOR, ICAR_VAR_POTENTIAL_TEMPERATURE, ICAR_VAR_CLOUD_WATER,
+                                   ICAR_VAR_CLOUD_ICE, ICAR_VAR_ICE_NUMBER, ICAR_VAR_RAIN_IN_AIR,
+                                   ICAR_VAR_RAIN_NUMBER, ICAR_VAR_SNOW_IN_AIR, ICAR_VAR_GRAUPEL_IN_AIR};
 
 bool check_dims(const icar_ctx* c, int ims, int ime, int kms, int kme, int jms, int jme) {
     return (ime - ims + 1) == c->g.nx && (kme - kms + 1) == c->g.nz && (jme - jms + 1) == c->g.ny;
@@ -219,20 +241,41 @@ int need_uploaded(icar_ctx* ctx, std::initializer_list<int> vars, const char* wh
 // process_subdomain's scheme call (mp_driver.f90:398-607) on up to four 1-based inclusive tiles
 // {its, ite, jts, jte}, one launch
 int run_mp_tiles(icar_ctx* ctx, float mp_dt, const int (*t)[4], int ntiles, int kts, int kte, cudaStream_t st,
-                 float* rain2d, float* snow2d) {
+                 float* rain2d, float* snow2d, float* graupel2d) {
     const icar_grid& gr = ctx->grid;
-    if (ctx->opt.microphysics == 2) {
-        MpTiles tiles;
-        tiles.n = 0;
-        for (int a = 0; a < ntiles; ++a) {
-            if (t[a][1] < t[a][0] || t[a][3] < t[a][2]) continue;
-            tiles.its[tiles.n] = t[a][0] - gr.ims; tiles.ite[tiles.n] = t[a][1] - gr.ims;
-            tiles.jts[tiles.n] = t[a][2] - gr.jms; tiles.jte[tiles.n] = t[a][3] - gr.jms;
-            // strips narrower than a warp in x but long in y: run the lanes along y
-            tiles.along_y[tiles.n] = ((t[a][1] - t[a][0] + 1) < 16 && (t[a][3] - t[a][2] + 1) > (t[a][1] - t[a][0] + 1)) ? 1 : 0;
-            ++tiles.n;
+    MpTiles tiles;
+    tiles.n = 0;
+    for (int a = 0; a < ntiles; ++a) {
+        if (t[a][1] < t[a][0] || t[a][3] < t[a][2]) continue;
+        tiles.its[tiles.n] = t[a][0] - gr.ims; tiles.ite[tiles.n] = t[a][1] - gr.ims;
+        tiles.jts[tiles.n] = t[a][2] - gr.jms; tiles.jte[tiles.n] = t[a][3] - gr.jms;
+        // strips narrower than a warp in x but long in y: run the lanes along y
+        tiles.along_y[tiles.n] = ((t[a][1] - t[a][0] + 1) < 16 && (t[a][3] - t[a][2] + 1) > (t[a][1] - t[a][0] + 1)) ? 1 : 0;
+        ++tiles.n;
+    }
+    if (tiles.n == 0) return ICAR_OK;
+    if (ctx->opt.microphysics == 1) {              // process_subdomain's mp_gt_driver call, mp_driver.f90:415-440
+        if (!ctx->th_ready) return fail(ctx, ICAR_ERR_INVALID, "icar_mp: thompson_init has not run");
+        for (int a = 0; a < tiles.n; ++a) {        // i_end = MIN(ite, ide-1), j_end = MIN(jte, jde-1)  (mp_thompson.f90:821-822)
+            tiles.ite[a] = std::min(tiles.ite[a], gr.ide - 1 - gr.ims);
+            tiles.jte[a] = std::min(tiles.jte[a], gr.jde - 1 - gr.jms);
+            tiles.along_y[a] = ((tiles.ite[a] - tiles.its[a] + 1) < 4 && (tiles.jte[a] - tiles.jts[a]) > (tiles.ite[a] - tiles.its[a])) ? 1 : 0;
         }
-        if (tiles.n == 0) return ICAR_OK;
+        int nl = th_driver_launch(
+            ctx->g, ctx->thc, ctx->tht, (float*)ctx->vars[ICAR_VAR_WATER_VAPOR], (float*)ctx->vars[ICAR_VAR_CLOUD_WATER],
+            (float*)ctx->vars[ICAR_VAR_RAIN_IN_AIR], (float*)ctx->vars[ICAR_VAR_CLOUD_ICE],
+            (float*)ctx->vars[ICAR_VAR_SNOW_IN_AIR], (float*)ctx->vars[ICAR_VAR_GRAUPEL_IN_AIR],
+            (float*)ctx->vars[ICAR_VAR_ICE_NUMBER], (float*)ctx->vars[ICAR_VAR_RAIN_NUMBER],
+            (float*)ctx->vars[ICAR_VAR_POTENTIAL_TEMPERATURE], (const float*)ctx->vars[ICAR_VAR_EXNER],
+            (const float*)ctx->vars[ICAR_VAR_PRESSURE], (const float*)ctx->vars[ICAR_VAR_DZ_MASS], mp_dt, rain2d,
+            /*RAINNCV = this_precip: never written by the reference*/ nullptr, snow2d, nullptr, graupel2d, nullptr,
+            ctx->sr2d, ctx->ld2, tiles, kts - gr.kms, kte - gr.kms, ctx->th_diag, st);
+        if (nl < 0) return fail(ctx, ICAR_ERR_INVALID, "mp_thompson: more than 64 levels are not built");
+        ctx->launches += nl;
+        CU(cudaGetLastError());
+        return ICAR_OK;
+    }
+    if (ctx->opt.microphysics == 2) {
         float c2s = std::exp(-1.0f * (1.0f / 2000.0f) * mp_dt);    // mp_simple.f90:619
         float c2r = std::exp(-1.0f * (1.0f / 500.0f) * mp_dt);     // mp_simple.f90:620
         int nl = mp_simple_launch(
@@ -248,7 +291,7 @@ int run_mp_tiles(icar_ctx* ctx, float mp_dt, const int (*t)[4], int ntiles, int 
         return ICAR_OK;
     }
     return fail(ctx, ICAR_ERR_INVALID, "microphysics scheme " + std::to_string(ctx->opt.microphysics) +
-                                           " is not built (only kMP_SB04 = 2)");
+                                           " is not built (kMP_THOMPSON = 1 and kMP_SB04 = 2 are)");
 }
 
 // Waits (on the compute stream) for the ring strips that mp(halo) left running on the aux stream and
@@ -262,6 +305,11 @@ int join_aux(icar_ctx* ctx) {
         ctx->main_acc_pending ? ctx->snow2d : nullptr, ctx->aux_pending ? ctx->rain2d_halo : nullptr,
         ctx->aux_pending ? ctx->snow2d_halo : nullptr, (double*)ctx->vars[ICAR_VAR_PRECIPITATION],
         (double*)ctx->vars[ICAR_VAR_SNOWFALL], ctx->stream);
+    if (ctx->opt.microphysics == 1)        // domain%graupel += graupel (mp_driver.f90:590-592): same kernel, graupel in both slots
+        ctx->launches += accumulate_precip_launch(
+            ctx->g.nx, ctx->g.ny, ctx->ld2, ctx->main_acc_pending ? ctx->graupel2d : nullptr, nullptr,
+            ctx->aux_pending ? ctx->graupel2d_halo : nullptr, nullptr, (double*)ctx->vars[ICAR_VAR_GRAUPEL], nullptr,
+            ctx->stream);
     CU(cudaGetLastError());
     ctx->aux_pending = false;
     ctx->main_acc_pending = false;
@@ -382,12 +430,19 @@ extern "C" int icar_create(int device, const icar_grid* grid, const icar_options
     if (opt->advect_density && alloc_cells(ctx, &ctx->G) != ICAR_OK) return bail(ICAR_ERR_CUDA);
     ctx->fused = (opt->advection == 2 && opt->mpdata_order == 2 && opt->flux_corrected_transport &&
                   !opt->advect_density && !opt->exact_arithmetic && fused_plan(ctx->g).ok);
+    if (opt->microphysics == 1) {
+        ctx->nadv = 9; std::copy(kAdvectedThompson, kAdvectedThompson + 9, ctx->adv);
+        ctx->nexch = 9; std::copy(kExchangedThompson, kExchangedThompson + 9, ctx->exch);
+    } else {
+        ctx->nadv = 5; std::copy(kAdvectedSimple, kAdvectedSimple + 5, ctx->adv);
+        ctx->nexch = 5; std::copy(kExchangedSimple, kExchangedSimple + 5, ctx->exch);
+    }
     if (ctx->fused) {
         float** cf[] = {&ctx->coef.ax, &ctx->coef.bx, &ctx->coef.cx, &ctx->coef.ay, &ctx->coef.by, &ctx->coef.cy,
                         &ctx->coef.az, &ctx->coef.bz, &ctx->coef.cz, &ctx->coef.rj, &ctx->coef.rjz};
         for (float** p : cf)
             if (alloc_cells(ctx, p) != ICAR_OK) return bail(ICAR_ERR_CUDA);
-        for (int n = 0; n < 5; ++n)
+        for (int n = 0; n < ctx->nadv; ++n)
             if (alloc_cells(ctx, &ctx->fq2[n]) != ICAR_OK || alloc_cells(ctx, &ctx->fout[n]) != ICAR_OK)
                 return bail(ICAR_ERR_CUDA);
     }
@@ -395,6 +450,10 @@ extern "C" int icar_create(int device, const icar_grid* grid, const icar_options
     ctx->snow2d = ctx->rain2d + (size_t)ctx->ld2 * ny;
     ctx->rain2d_halo = ctx->snow2d + (size_t)ctx->ld2 * ny;
     ctx->snow2d_halo = ctx->rain2d_halo + (size_t)ctx->ld2 * ny;
+    CUB(cudaMalloc((void**)&ctx->graupel2d, (size_t)3 * ctx->ld2 * ny * sizeof(float)));
+    CUB(cudaMemsetAsync(ctx->graupel2d, 0, (size_t)3 * ctx->ld2 * ny * sizeof(float), ctx->stream));
+    ctx->graupel2d_halo = ctx->graupel2d + (size_t)ctx->ld2 * ny;
+    ctx->sr2d = ctx->graupel2d_halo + (size_t)ctx->ld2 * ny;
     CUB(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
     CUB(cudaStreamCreateWithFlags(&ctx->aux, cudaStreamNonBlocking));
     CUB(cudaEventCreateWithFlags(&ctx->ev_aux, cudaEventDisableTiming));
@@ -402,6 +461,10 @@ extern "C" int icar_create(int device, const icar_grid* grid, const icar_options
     CUB(cudaMemsetAsync(ctx->diag, 0, 3 * sizeof(unsigned long long), ctx->stream));
     CUB(cudaStreamSynchronize(ctx->stream));
 #undef CUB
+    if (opt->microphysics == 1) {          // mp_init -> thompson_init(options%mp_options), mp_driver.f90:80-83
+        int rc = icar_thompson_init(ctx, nullptr);
+        if (rc) return bail(rc);
+    }
     *out = ctx;
     return ICAR_OK;
 }
@@ -415,14 +478,18 @@ extern "C" int icar_destroy(icar_ctx* ctx) {
     if (ctx->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(ctx->comm);
     for (void* p : ctx->vars) if (p) cudaFree(p);
     float* bufs[] = {ctx->U, ctx->V, ctx->W, ctx->Wn, ctx->G, ctx->qa, ctx->qb, ctx->u2, ctx->v2, ctx->w2,
-                     ctx->rain2d, ctx->send_w, ctx->send_e, ctx->recv_w, ctx->recv_e};
+                     ctx->rain2d, ctx->graupel2d, ctx->send_w, ctx->send_e, ctx->recv_w, ctx->recv_e};
     for (float* p : bufs) if (p) cudaFree(p);
     if (ctx->diag) cudaFree(ctx->diag);
+    for (double* t : ctx->th_tab) if (t) cudaFree(t);
+    if (ctx->th_bins) cudaFree(ctx->th_bins);
+    if (ctx->th_aux) cudaFree(ctx->th_aux);
+    if (ctx->th_diag) cudaFree(ctx->th_diag);
     {
         float* cf[] = {ctx->coef.ax, ctx->coef.bx, ctx->coef.cx, ctx->coef.ay, ctx->coef.by, ctx->coef.cy,
                        ctx->coef.az, ctx->coef.bz, ctx->coef.cz, ctx->coef.rj, ctx->coef.rjz};
         for (float* p : cf) if (p) cudaFree(p);
-        for (int n = 0; n < 5; ++n) { if (ctx->fq2[n]) cudaFree(ctx->fq2[n]); if (ctx->fout[n]) cudaFree(ctx->fout[n]); }
+        for (int n = 0; n < ICAR_MAX_SCALARS; ++n) { if (ctx->fq2[n]) cudaFree(ctx->fq2[n]); if (ctx->fout[n]) cudaFree(ctx->fout[n]); }
     }
     for (void* p : ctx->scratch) if (p) cudaFree(p);
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
@@ -560,9 +627,9 @@ extern "C" int icar_advect(icar_ctx* ctx, float dt) {
     }
     if (ctx->fused) {
         ScalarSet ss;
-        ss.n = 5;
-        for (int n = 0; n < 5; ++n) {
-            ss.q[n] = (const float*)ctx->vars[kAdvectedSimple[n]];
+        ss.n = ctx->nadv;
+        for (int n = 0; n < ctx->nadv; ++n) {
+            ss.q[n] = (const float*)ctx->vars[ctx->adv[n]];
             ss.q2[n] = ctx->fq2[n];
             ss.out[n] = ctx->fout[n];
         }
@@ -570,16 +637,16 @@ extern "C" int icar_advect(icar_ctx* ctx, float dt) {
         if (nl < 0) return fail(ctx, ICAR_ERR_CUDA, "icar_advect: cannot set up the TMA tensor maps / shared memory of the fused MPDATA kernel");
         ctx->launches += nl;
         CU(cudaGetLastError());
-        for (int n = 0; n < 5; ++n) {      // the output buffer becomes the field, the old field the next output
-            float* old_field = (float*)ctx->vars[kAdvectedSimple[n]];
-            ctx->vars[kAdvectedSimple[n]] = ctx->fout[n];
+        for (int n = 0; n < ctx->nadv; ++n) {      // the output buffer becomes the field, the old field the next output
+            float* old_field = (float*)ctx->vars[ctx->adv[n]];
+            ctx->vars[ctx->adv[n]] = ctx->fout[n];
             ctx->fout[n] = old_field;
         }
         return ICAR_OK;
     }
     // adv_mpdata.f90:512-522: every scalar with vars_to_advect > 0 (mp_simple.f90:116-118)
-    for (int s = 0; s < 5; ++s) {
-        int var = kAdvectedSimple[s];
+    for (int s = 0; s < ctx->nadv; ++s) {
+        int var = ctx->adv[s];
         float* q = (float*)ctx->vars[var];
         float* res = nullptr;
         ctx->launches += staged_advect3d<float>(g, q, rho, jaco, dz, ctx->U, ctx->V, ctx->W, ctx->Wn, G, order,
@@ -627,9 +694,10 @@ extern "C" int icar_mp(icar_ctx* ctx, float dt_in, int halo, int subset) {
             if ((rc = join_aux(ctx))) return rc;          // earlier tiles overlap these cells / buffers
         if (has_subset || (!has_halo && !has_subset)) {
             CU(cudaMemsetAsync(ctx->rain2d, 0, b2, ctx->stream));
+            CU(cudaMemsetAsync(ctx->graupel2d, 0, b2 / 2, ctx->stream));
             const int sub = has_subset ? subset : 0;                                     // :728-738 / :754-766
             const int t[1][4] = {{gr.its + sub, gr.ite - sub, gr.jts + sub, gr.jte - sub}};
-            if ((rc = run_mp_tiles(ctx, mp_dt, t, 1, gr.kts, kte, ctx->stream, ctx->rain2d, ctx->snow2d))) return rc;
+            if ((rc = run_mp_tiles(ctx, mp_dt, t, 1, gr.kts, kte, ctx->stream, ctx->rain2d, ctx->snow2d, ctx->graupel2d))) return rc;
             ctx->main_acc_pending = true;
         }
         if (has_halo) {                                                                  // process_halo :609-658
@@ -637,13 +705,14 @@ extern "C" int icar_mp(icar_ctx* ctx, float dt_in, int halo, int subset) {
             // and are joined lazily, so the interior tile of mp(subset) overlaps them the way
             // time_step.f90:512-526 overlaps the halo exchange.
             CU(cudaMemsetAsync(ctx->rain2d_halo, 0, b2, ctx->stream));
+            CU(cudaMemsetAsync(ctx->graupel2d_halo, 0, b2 / 2, ctx->stream));
             CU(cudaEventRecord(ctx->ev_fork, ctx->stream));
             const int t[4][4] = {{gr.its, gr.its + halo - 1, gr.jts, gr.jte},
                                  {gr.ite - halo + 1, gr.ite, gr.jts, gr.jte},
                                  {gr.its + halo, gr.ite - halo, gr.jts, gr.jts + halo - 1},
                                  {gr.its + halo, gr.ite - halo, gr.jte - halo + 1, gr.jte}};
             CU(cudaStreamWaitEvent(ctx->aux, ctx->ev_fork, 0));
-            if ((rc = run_mp_tiles(ctx, mp_dt, t, 4, gr.kts, kte, ctx->aux, ctx->rain2d_halo, ctx->snow2d_halo))) return rc;
+            if ((rc = run_mp_tiles(ctx, mp_dt, t, 4, gr.kts, kte, ctx->aux, ctx->rain2d_halo, ctx->snow2d_halo, ctx->graupel2d_halo))) return rc;
             CU(cudaEventRecord(ctx->ev_aux, ctx->aux));
             ctx->aux_pending = true;
         }
@@ -673,17 +742,19 @@ int mp_phase(icar_ctx* ctx, float dt_in, int phase, int axis, int h) {
     if (phase == 0) {
         if ((rc = join_aux(ctx))) return rc;
         CU(cudaMemsetAsync(ctx->rain2d_halo, 0, b2, ctx->stream));
+        CU(cudaMemsetAsync(ctx->graupel2d_halo, 0, b2 / 2, ctx->stream));
         int t[2][4], n = 0;
         if (lo) { t[n][0] = axis ? gr.its : a0; t[n][1] = axis ? gr.ite : a0 + h - 1; t[n][2] = axis ? a0 : gr.jts; t[n][3] = axis ? a0 + h - 1 : gr.jte; ++n; }
         if (hi) { t[n][0] = axis ? gr.its : a1 - h + 1; t[n][1] = axis ? gr.ite : a1; t[n][2] = axis ? a1 - h + 1 : gr.jts; t[n][3] = axis ? a1 : gr.jte; ++n; }
-        if ((rc = run_mp_tiles(ctx, mp_dt, t, n, gr.kts, kte, ctx->stream, ctx->rain2d_halo, ctx->snow2d_halo))) return rc;
+        if ((rc = run_mp_tiles(ctx, mp_dt, t, n, gr.kts, kte, ctx->stream, ctx->rain2d_halo, ctx->snow2d_halo, ctx->graupel2d_halo))) return rc;
         CU(cudaEventRecord(ctx->ev_aux, ctx->stream));
         ctx->aux_pending = true;      // (recorded on the compute stream: join_aux's wait is then a no-op)
     } else {
         if (ctx->main_acc_pending && (rc = join_aux(ctx))) return rc;
         CU(cudaMemsetAsync(ctx->rain2d, 0, b2, ctx->stream));
+        CU(cudaMemsetAsync(ctx->graupel2d, 0, b2 / 2, ctx->stream));
         const int t[1][4] = {{axis ? gr.its : in0, axis ? gr.ite : in1, axis ? in0 : gr.jts, axis ? in1 : gr.jte}};
-        if ((rc = run_mp_tiles(ctx, mp_dt, t, 1, gr.kts, kte, ctx->stream, ctx->rain2d, ctx->snow2d))) return rc;
+        if ((rc = run_mp_tiles(ctx, mp_dt, t, 1, gr.kts, kte, ctx->stream, ctx->rain2d, ctx->snow2d, ctx->graupel2d))) return rc;
         ctx->main_acc_pending = true;
     }
     return ICAR_OK;
@@ -732,7 +803,7 @@ extern "C" int icar_comm_init(icar_ctx* ctx, int image, int nimages, const char 
     ncclUniqueId uid;
     std::memcpy(&uid, id, 128);
     NC(g_nccl.CommInitRank(&ctx->comm, nimages, uid, image - 1));
-    size_t n = (size_t)5 * ctx->g.ny * ctx->g.nz * ctx->grid.halo_size * sizeof(float);
+    size_t n = (size_t)ctx->nexch * ctx->g.ny * ctx->g.nz * ctx->grid.halo_size * sizeof(float);
     CU(cudaMalloc((void**)&ctx->send_w, n));
     CU(cudaMalloc((void**)&ctx->send_e, n));
     CU(cudaMalloc((void**)&ctx->recv_w, n));
@@ -750,16 +821,17 @@ extern "C" int icar_halo_send(icar_ctx* ctx) {
     if (icar_halo_plan(&ctx->grid, ctx->image, ctx->nimages, plan)) return fail(ctx, ICAR_ERR_INVALID, "icar_halo_send: tile narrower than two halos, or not a slab decomposition");
     const int h = plan[7];
     const bool lower = plan[4] != 0, upper = plan[5] != 0;
-    float* fields[5];
-    for (int s = 0; s < 5; ++s) fields[s] = (float*)ctx->vars[kExchangedSimple[s]];
+    const int nf = ctx->nexch;
+    float* fields[ICAR_MAX_EXCHANGED];
+    for (int s = 0; s < nf; ++s) fields[s] = (float*)ctx->vars[ctx->exch[s]];
     if (plan[6] == 0) {
         // x-slabs: faces are ny*nz runs of h floats -> gather all fields into one buffer per side
-        const size_t count = (size_t)5 * ctx->g.ny * ctx->g.nz * h;
+        const size_t count = (size_t)nf * ctx->g.ny * ctx->g.nz * h;
         int x0[2], ns = 0;
         float* bufs[2];
         if (lower) { x0[ns] = plan[0]; bufs[ns++] = ctx->send_w; }
         if (upper) { x0[ns] = plan[1]; bufs[ns++] = ctx->send_e; }
-        ctx->launches += halo_pack_launch(ctx->g, fields, 5, h, ns, x0, bufs, ctx->stream);
+        ctx->launches += halo_pack_launch(ctx->g, fields, nf, h, ns, x0, bufs, ctx->stream);
         CU(cudaGetLastError());
         CU(cudaEventRecord(ctx->ev_packed, ctx->stream));
         CU(cudaStreamWaitEvent(ctx->comm_stream, ctx->ev_packed, 0));
@@ -780,7 +852,7 @@ extern "C" int icar_halo_send(icar_ctx* ctx) {
         CU(cudaEventRecord(ctx->ev_packed, ctx->stream));
         CU(cudaStreamWaitEvent(ctx->comm_stream, ctx->ev_packed, 0));
         NC(g_nccl.GroupStart());
-        for (int s = 0; s < 5; ++s) {
+        for (int s = 0; s < nf; ++s) {
             if (lower) {
                 NC(g_nccl.Send(fields[s] + (size_t)plan[0] * ps, count, ncclFloat, ctx->image - 2, ctx->comm, ctx->comm_stream));
                 NC(g_nccl.Recv(fields[s] + (size_t)plan[2] * ps, count, ncclFloat, ctx->image - 2, ctx->comm, ctx->comm_stream));
@@ -808,13 +880,14 @@ extern "C" int icar_halo_retrieve(icar_ctx* ctx) {
     const bool lower = plan[4] != 0, upper = plan[5] != 0;
     CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_comm, 0));     // `sync images(neighbors)`, exchangeable_obj.f90:151
     if (plan[6] == 0) {
-        float* fields[5];
-        for (int s = 0; s < 5; ++s) fields[s] = (float*)ctx->vars[kExchangedSimple[s]];
+        const int nf = ctx->nexch;
+        float* fields[ICAR_MAX_EXCHANGED];
+        for (int s = 0; s < nf; ++s) fields[s] = (float*)ctx->vars[ctx->exch[s]];
         int x0[2], ns = 0;
         float* bufs[2];
         if (lower) { x0[ns] = plan[2]; bufs[ns++] = ctx->recv_w; }
         if (upper) { x0[ns] = plan[3]; bufs[ns++] = ctx->recv_e; }
-        ctx->launches += halo_unpack_launch(ctx->g, fields, 5, h, ns, x0, bufs, ctx->stream);
+        ctx->launches += halo_unpack_launch(ctx->g, fields, nf, h, ns, x0, bufs, ctx->stream);
         CU(cudaGetLastError());
     }
     ctx->exchange_in_flight = false;
@@ -1064,5 +1137,110 @@ extern "C" int icar_host_unregister(icar_ctx* ctx, const icar_host_domain* dom) 
         if (!h.in) continue;
         CU(cudaHostUnregister(const_cast<void*>(h.in)));
     }
+    return ICAR_OK;
+}
+
+// ============================================================================ Thompson (mp = 1)
+
+extern "C" void icar_default_mp_options(icar_mp_options* o) {
+    if (!o) return;
+    // options_obj.f90:1259-1280
+    o->Nt_c = 100.e6f; o->TNO = 5.0f; o->am_s = 0.069f; o->rho_g = 500.0f;
+    o->av_s = 40.0f; o->bv_s = 0.55f; o->fv_s = 100.0f; o->av_i = 1847.5f;
+    o->av_g = 442.0f; o->bv_g = 0.89f;
+    o->Ef_si = 0.05f; o->Ef_rs = 0.95f; o->Ef_rg = 0.75f; o->Ef_ri = 0.95f;
+    o->C_cubes = 0.5f; o->C_sqrd = 0.3f; o->mu_r = 0.f; o->t_adjust = 0.f;
+    o->Ef_rw_l = 0; o->Ef_sw_l = 0;
+}
+
+extern "C" int icar_thompson_init(icar_ctx* ctx, const icar_mp_options* opt) {
+    if (!ctx) return ICAR_ERR_INVALID;
+    CU(cudaSetDevice(ctx->device));
+    icar_mp_options d;
+    icar_default_mp_options(&d);
+    if (opt) d = *opt;
+    static_assert(sizeof(icar_mp_options) == sizeof(ThOptions), "icar_mp_options and ThOptions must match");
+    ThOptions o;
+    std::memcpy(&o, &d, sizeof(o));
+    if (!(o.Nt_c > 0.f) || !(o.am_s > 0.f) || !(o.rho_g > 0.f))
+        return fail(ctx, ICAR_ERR_INVALID, "icar_thompson_init: Nt_c, am_s and rho_g must be positive");
+    std::vector<double> bins(1000);
+    th_make_constants(o, &ctx->thc, bins.data());
+    if (!ctx->th_bins) CU(cudaMalloc((void**)&ctx->th_bins, 1000 * sizeof(double)));
+    if (!ctx->th_aux) CU(cudaMalloc((void**)&ctx->th_aux, 800 * sizeof(double)));
+    if (!ctx->th_diag) {
+        CU(cudaMalloc((void**)&ctx->th_diag, sizeof(unsigned long long)));
+        CU(cudaMemsetAsync(ctx->th_diag, 0, sizeof(unsigned long long), ctx->stream));
+    }
+    for (int t = 0; t < TH_NTABLES; ++t) {
+        if (!ctx->th_tab[t]) CU(cudaMalloc((void**)&ctx->th_tab[t], th_table_elems(t) * sizeof(double)));
+        CU(cudaMemsetAsync(ctx->th_tab[t], 0, th_table_elems(t) * sizeof(double), ctx->stream));   // :640-714
+        ctx->tht.t[t] = ctx->th_tab[t];
+    }
+    CU(cudaMemcpyAsync(ctx->th_bins, bins.data(), 1000 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    ctx->launches += th_build_tables(ctx->thc, ctx->th_bins, ctx->th_aux, ctx->th_tab, ctx->stream);
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(ctx->stream));
+    ctx->th_ready = true;
+    return ICAR_OK;
+}
+
+extern "C" int icar_thompson_table(icar_ctx* ctx, int id, double* host, long long* count) {
+    if (!ctx || id < 0 || id >= TH_NTABLES) return fail(ctx, ICAR_ERR_INVALID, "icar_thompson_table: bad table id");
+    if (count) *count = (long long)th_table_elems(id);
+    if (!host) return ICAR_OK;
+    if (!ctx->th_ready) return fail(ctx, ICAR_ERR_INVALID, "icar_thompson_table before icar_thompson_init");
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaMemcpyAsync(host, ctx->th_tab[id], th_table_elems(id) * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return ICAR_OK;
+}
+
+extern "C" int icar_mp_gt_driver(icar_ctx* ctx, float* qv, float* qc, float* qr, float* qi, float* qs, float* qg,
+                                 float* ni, float* nr, float* th, const float* pii, const float* p, const float* dz,
+                                 float dt_in, int itimestep, float* RAINNC, const float* RAINNCV, float* SNOWNC,
+                                 float* SNOWNCV, float* GRAUPELNC, float* GRAUPELNCV, float* SR, int ids, int ide,
+                                 int jds, int jde, int kds, int kde, int ims, int ime, int jms, int jme, int kms,
+                                 int kme, int its, int ite, int jts, int jte, int kts, int kte) {
+    (void)itimestep; (void)ids; (void)jds; (void)kds; (void)kde;      // unused by the reference too
+    if (!ctx || !qv || !qc || !qr || !qi || !qs || !qg || !ni || !nr || !th || !pii || !p || !dz || !RAINNC || !SR)
+        return fail(ctx, ICAR_ERR_INVALID, "icar_mp_gt_driver: null array");
+    if (!check_dims(ctx, ims, ime, kms, kme, jms, jme)) return fail(ctx, ICAR_ERR_INVALID, "icar_mp_gt_driver: bounds do not match the context's tile");
+    if (its < ims || ite > ime || jts < jms || jte > jme || kts < kms || kte > kme)
+        return fail(ctx, ICAR_ERR_INVALID, "icar_mp_gt_driver: tile outside memory bounds");
+    if (!ctx->th_ready) return fail(ctx, ICAR_ERR_INVALID, "icar_mp_gt_driver before icar_thompson_init");
+    CU(cudaSetDevice(ctx->device));
+    const Geom& g = ctx->g;
+    void* b[19];
+    for (int i = 0; i < 19; ++i) { int rc = get_scratch(ctx, 80 + i, sizeof(float), &b[i]); if (rc) return rc; }
+    const size_t rows = (size_t)g.nz * g.ny;
+    const float* in3[12] = {qv, qc, qr, qi, qs, qg, ni, nr, th, pii, p, dz};
+    int rc;
+    for (int i = 0; i < 12; ++i)
+        if ((rc = copy_in(ctx, b[i], in3[i], g.nx, g.ld, rows, sizeof(float)))) return rc;
+    const float* in2[7] = {RAINNC, RAINNCV, SNOWNC, SNOWNCV, GRAUPELNC, GRAUPELNCV, SR};
+    for (int i = 0; i < 7; ++i)
+        if (in2[i] && (rc = copy_in(ctx, b[12 + i], in2[i], g.nx, ctx->ld2, g.ny, sizeof(float)))) return rc;
+    MpTiles tiles;
+    tiles.n = 1;
+    // i_end = MIN(ite, ide-1), j_end = MIN(jte, jde-1)  (:821-822)
+    tiles.its[0] = its - ims; tiles.ite[0] = std::min(ite, ide - 1) - ims;
+    tiles.jts[0] = jts - jms; tiles.jte[0] = std::min(jte, jde - 1) - jms;
+    tiles.along_y[0] = 0;
+    auto d2 = [&](int i) { return in2[i] ? (float*)b[12 + i] : nullptr; };
+    int nl = th_driver_launch(g, ctx->thc, ctx->tht, (float*)b[0], (float*)b[1], (float*)b[2], (float*)b[3], (float*)b[4],
+                              (float*)b[5], (float*)b[6], (float*)b[7], (float*)b[8], (float*)b[9], (float*)b[10],
+                              (float*)b[11], dt_in, d2(0), d2(1), d2(2), d2(3), d2(4), d2(5), d2(6), ctx->ld2, tiles,
+                              kts - kms, kte - kms, ctx->th_diag, ctx->stream);
+    if (nl < 0) return fail(ctx, ICAR_ERR_INVALID, "mp_thompson: more than 64 levels are not built");
+    ctx->launches += nl;
+    CU(cudaGetLastError());
+    float* out3[9] = {qv, qc, qr, qi, qs, qg, ni, nr, th};
+    for (int i = 0; i < 9; ++i)
+        if ((rc = copy_out(ctx, out3[i], b[i], g.nx, g.ld, rows, sizeof(float)))) return rc;
+    float* out2[7] = {RAINNC, nullptr, SNOWNC, SNOWNCV, GRAUPELNC, GRAUPELNCV, SR};
+    for (int i = 0; i < 7; ++i)
+        if (out2[i] && (rc = copy_out(ctx, out2[i], b[12 + i], g.nx, ctx->ld2, g.ny, sizeof(float)))) return rc;
+    CU(cudaStreamSynchronize(ctx->stream));
     return ICAR_OK;
 }

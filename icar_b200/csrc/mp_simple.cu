@@ -342,11 +342,16 @@ __global__ void k_accumulate_precip(int nx, int ny, int ld2, const float* __rest
     int i = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y;
     if (i >= nx || j >= ny) return;
     size_t c = (size_t)i + (size_t)ld2 * j;
-    double r = acc_rain[c], s = acc_snow[c];
-    if (rain) { r = r + (double)rain[c]; s = s + (double)snow[c]; }
-    if (rain_b) { r = r + (double)rain_b[c]; s = s + (double)snow_b[c]; }
+    double r = acc_rain[c];
+    if (rain) r = r + (double)rain[c];
+    if (rain_b) r = r + (double)rain_b[c];
     acc_rain[c] = r;
-    acc_snow[c] = s;
+    if (acc_snow) {                       // (null when a single accumulator is updated: Thompson's graupel)
+        double s = acc_snow[c];
+        if (rain) s = s + (double)snow[c];
+        if (rain_b) s = s + (double)snow_b[c];
+        acc_snow[c] = s;
+    }
 }
 
 }  // namespace

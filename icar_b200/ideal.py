@@ -128,6 +128,19 @@ def make_ideal_case(nx=100, nz=20, ny=100, dx=4000.0, dz_level=400.0, terrain=Tr
     return st
 
 
+def add_thompson_fields(st, moisten=1.0):
+    """Adds the extra Thompson species (qi, qg, ni, nr = 0) and the 2-D per-call precipitation arrays of
+    mp_gt_driver to an ideal state; `moisten` scales qv (3.0 makes every process of the scheme fire
+    within a few steps)."""
+    if moisten != 1.0:
+        st["qv"] = (st["qv"] * F(moisten)).astype(np.float32)
+    for k in ("qi", "qg", "ni", "nr"):
+        st[k] = np.zeros_like(st["qv"])
+    for k in ("rainnc", "rainncv", "snownc", "snowncv", "graupelnc", "graupelncv", "sr"):
+        st[k] = np.zeros(st["rain"].shape, np.float32)
+    return st
+
+
 def copy_state(st):
     return {k: (v.copy() if isinstance(v, np.ndarray) else v) for k, v in st.items()}
 

@@ -91,8 +91,28 @@ enum icar_var {
     ICAR_VAR_DZ_MASS = 16,          /* domain%dz_mass%data_3d                              */
     ICAR_VAR_PRECIPITATION = 17,    /* domain%accumulated_precipitation%data_2dd (nx,ny) REAL*8 */
     ICAR_VAR_SNOWFALL = 18,         /* domain%accumulated_snowfall%data_2dd     (nx,ny) REAL*8 */
-    ICAR_VAR_COUNT = 19
+    /* Thompson (kMP_THOMPSON) only -- mp_driver.f90:128-131, 415-424 */
+    ICAR_VAR_CLOUD_ICE = 19,        /* domain%cloud_ice_mass%data_3d                       */
+    ICAR_VAR_ICE_NUMBER = 20,       /* domain%cloud_ice_number%data_3d                     */
+    ICAR_VAR_RAIN_NUMBER = 21,      /* domain%rain_number%data_3d                          */
+    ICAR_VAR_GRAUPEL_IN_AIR = 22,   /* domain%graupel_mass%data_3d                         */
+    ICAR_VAR_GRAUPEL = 23,          /* domain%graupel%data_2dd                 (nx,ny) REAL*8 */
+    ICAR_VAR_COUNT = 24
 };
+
+/* mp_options_type (src/objects/opt_types.f90:31-45): the Thompson sensitivity parameters that
+ * thompson_init copies into its module variables (mp_thompson.f90:397-417).  Defaults:
+ * icar_default_mp_options() = options_obj.f90:1259-1280. */
+typedef struct icar_mp_options {
+    float Nt_c, TNO, am_s, rho_g;
+    float av_s, bv_s, fv_s, av_i;
+    float av_g, bv_g;
+    float Ef_si, Ef_rs, Ef_rg, Ef_ri;
+    float C_cubes, C_sqrd;
+    float mu_r;
+    float t_adjust;
+    int Ef_rw_l, Ef_sw_l;
+} icar_mp_options;
 
 /* ------------------------------------------------------------------ lifecycle */
 
@@ -170,6 +190,37 @@ long long icar_kernel_launches(const icar_ctx* ctx);
  * which brackets physics with wall-clock timers in driver.f90:155-157. */
 int icar_timer_start(icar_ctx* ctx);
 int icar_timer_stop(icar_ctx* ctx, float* elapsed_ms);
+
+/* ------------------------------------------------- Thompson microphysics (microphysics = 1) */
+
+void icar_default_mp_options(icar_mp_options* opt);
+
+/* thompson_init(mp_options) -- src/physics/mp_thompson.f90:342-766: derives the gamma-function
+ * constants and builds the 29 REAL*8 lookup tables (qr_acr_qg :2853, qr_acr_qs :3014, freezeH2O :3273,
+ * qi_aut_qs :3413, table_Efrw :3464, table_Efsw :3533) ON THE DEVICE (about 0.2 s; the reference
+ * spends minutes and therefore caches them in *_mpt.dat files).  opt may be NULL (defaults).
+ * icar_mp with microphysics = 1 calls this with the defaults if the caller has not. */
+int icar_thompson_init(icar_ctx* ctx, const icar_mp_options* opt);
+
+/* Copies lookup table `table_id` (0..28, in the allocation order of mp_thompson.f90:353-390:
+ * tcg_racg, tmr_racg, tcr_gacr, tmg_gacr, tnr_racg, tnr_gacr, tcs_racs1, tmr_racs1, tcs_racs2,
+ * tmr_racs2, tcr_sacr1, tms_sacr1, tcr_sacr2, tms_sacr2, tnr_racs1, tnr_racs2, tnr_sacr1, tnr_sacr2,
+ * tpi_qcfz, tni_qcfz, tpi_qrfz, tpg_qrfz, tni_qrfz, tnr_qrfz, tps_iaus, tni_iaus, tpi_ide, t_Efrw,
+ * t_Efsw) to `host` in the Fortran's column-major order -- the record layout of the reference's
+ * qr_acr_qg_mpt.dat / qr_acr_qs_mpt.dat / freezeH2O_mpt.dat.  *count receives the element count;
+ * host may be NULL to query it. */
+int icar_thompson_table(icar_ctx* ctx, int table_id, double* host, long long* count);
+
+/* mp_gt_driver(qv,qc,qr,qi,qs,qg,ni,nr,th,pii,p,dz,dt_in,itimestep, RAINNC,RAINNCV, SNOWNC,SNOWNCV,
+ * GRAUPELNC,GRAUPELNCV,SR, ids..kde, ims..kme, its..kte) -- src/physics/mp_thompson.f90:772-1044, on host
+ * arrays; same argument order.  SNOWNC, SNOWNCV, GRAUPELNC, GRAUPELNCV are OPTIONAL in the Fortran and
+ * may be NULL; RAINNCV is only read (for SR, :915) and may be NULL (read as 0). */
+int icar_mp_gt_driver(icar_ctx* ctx, float* qv, float* qc, float* qr, float* qi, float* qs, float* qg,
+                      float* ni, float* nr, float* th, const float* pii, const float* p, const float* dz,
+                      float dt_in, int itimestep, float* RAINNC, const float* RAINNCV, float* SNOWNC,
+                      float* SNOWNCV, float* GRAUPELNC, float* GRAUPELNCV, float* SR, int ids, int ide,
+                      int jds, int jde, int kds, int kde, int ims, int ime, int jms, int jme, int kms,
+                      int kme, int its, int ite, int jts, int jte, int kts, int kte);
 
 /* ------------------------------------------------- multi-image (one process per GPU) */
 

@@ -24,7 +24,8 @@ _SO = os.path.join(_HERE, "_build", "libicar_oracle.so")
 def build(force: bool = False) -> str:
     """Compile the C++ restatement (g++ -O2 -ffp-contract=off -fopenmp)."""
     srcs = [os.path.join(_HERE, f) for f in
-            ("oracle_api.cpp", "mpdata_oracle.hpp", "mp_simple_oracle.hpp", "Makefile")]
+            ("oracle_api.cpp", "mpdata_oracle.hpp", "mp_simple_oracle.hpp", "mp_thompson_oracle.hpp",
+             "Makefile")]
     stale = (not os.path.exists(_SO)) or any(
         os.path.getmtime(s) > os.path.getmtime(_SO) for s in srcs)
     if force or stale:
@@ -161,3 +162,117 @@ def step_simple(st, mp_dt, dt, order=2, fct=True, scratch=None):
         f(st["dx"]), nx, nz, ny, int(order), int(bool(fct)), _p(scratch[0]), _p(scratch[1]),
         _p(scratch[2]))
     return scratch
+
+
+# ------------------------------------------------------------------ Thompson (mp = 1)
+class ThompsonOptions(C.Structure):
+    """mp_options_type (src/objects/opt_types.f90:31-45), defaults of options_obj.f90:1259-1280."""
+    _fields_ = [(n, C.c_float) for n in (
+        "Nt_c", "TNO", "am_s", "rho_g", "av_s", "bv_s", "fv_s", "av_i", "av_g", "bv_g",
+        "Ef_si", "Ef_rs", "Ef_rg", "Ef_ri", "C_cubes", "C_sqrd", "mu_r", "t_adjust")] + \
+        [("Ef_rw_l", C.c_int), ("Ef_sw_l", C.c_int)]
+
+    def __init__(self, **kw):
+        super().__init__(100.e6, 5.0, 0.069, 500.0, 40.0, 0.55, 100.0, 1847.5, 442.0, 0.89,
+                         0.05, 0.95, 0.75, 0.95, 0.5, 0.3, 0.0, 0.0, 0, 0)
+        for k, v in kw.items():
+            setattr(self, k, v)
+
+
+# order of oracle_thompson_table ids == allocation order in thompson_init (mp_thompson.f90:353-390)
+THOMPSON_TABLES = (
+    "tcg_racg", "tmr_racg", "tcr_gacr", "tmg_gacr", "tnr_racg", "tnr_gacr",
+    "tcs_racs1", "tmr_racs1", "tcs_racs2", "tmr_racs2", "tcr_sacr1", "tms_sacr1",
+    "tcr_sacr2", "tms_sacr2", "tnr_racs1", "tnr_racs2", "tnr_sacr1", "tnr_sacr2",
+    "tpi_qcfz", "tni_qcfz", "tpi_qrfz", "tpg_qrfz", "tni_qrfz", "tnr_qrfz",
+    "tps_iaus", "tni_iaus", "tpi_ide", "t_Efrw", "t_Efsw")
+# Fortran shapes (column-major); numpy views are the reversed shape in C order
+THOMPSON_SHAPES = dict(
+    [(n, (28, 28, 37, 37)) for n in THOMPSON_TABLES[0:6]] +
+    [(n, (28, 9, 37, 37)) for n in THOMPSON_TABLES[6:18]] +
+    [(n, (37, 45)) for n in THOMPSON_TABLES[18:20]] +
+    [(n, (37, 37, 45)) for n in THOMPSON_TABLES[20:24]] +
+    [(n, (64, 55)) for n in THOMPSON_TABLES[24:27]] +
+    [(n, (100, 100)) for n in THOMPSON_TABLES[27:29]])
+
+
+class Thompson:
+    """thompson_init + mp_gt_driver of the CPU restatement (oracle/mp_thompson_oracle.hpp).
+    big_tables=False skips qr_acr_qg / qr_acr_qs (1.4e10 inner iterations); single (k,m) slabs of
+    them can then be filled with big_slab()."""
+
+    def __init__(self, options: ThompsonOptions | None = None, big_tables: bool = True):
+        l = lib()
+        l.oracle_thompson_create.restype = C.c_void_p
+        l.oracle_thompson_table.restype = C.c_longlong
+        l.oracle_thompson_driver.restype = C.c_longlong
+        self.options = options or ThompsonOptions()
+        self._h = C.c_void_p(l.oracle_thompson_create(C.byref(self.options), int(big_tables)))
+
+    def __del__(self):
+        try:
+            lib().oracle_thompson_destroy(self._h)
+        except Exception:
+            pass
+
+    def table(self, name):
+        """numpy VIEW (C order, reversed Fortran shape) on the oracle's table."""
+        p = C.POINTER(C.c_double)()
+        n = lib().oracle_thompson_table(self._h, THOMPSON_TABLES.index(name), C.byref(p))
+        return np.ctypeslib.as_array(p, (n,)).reshape(THOMPSON_SHAPES[name][::-1])
+
+    def big_slab(self, which, km, ij0=0, ij1=None):
+        """Fill cells [ij0, ij1) of slab km = (m-1)*37 + (k-1) of qr_acr_qg (0) or qr_acr_qs (1)."""
+        if ij1 is None:
+            ij1 = 28 * 28 if which == 0 else 28 * 9
+        lib().oracle_thompson_big_slab(self._h, int(which), int(km), int(ij0), int(ij1))
+
+    def constants(self):
+        out = (C.c_float * 256)()
+        n = lib().oracle_thompson_constants(self._h, out)
+        return np.array(out[:n], np.float32)
+
+    def bins(self):
+        out = np.empty((5, 100), np.float64)
+        lib().oracle_thompson_bins(self._h, _p(out))
+        return dict(zip(("Dc", "Di", "Dr", "Ds", "Dg"), out))
+
+    def driver(self, st, dt, its, ite, jts, jte, kts, kte, ide0=None, jde0=None):
+        """mp_gt_driver in place on a state dict with th, qv, qc, qr, qi, qs, qg, ni, nr, pii,
+        pressure, dz_mass and 2-D rainnc, snownc, graupelnc, sr (float32).  0-based inclusive bounds.
+        Returns the number of columns that took the no_micro early exit."""
+        nx, nz, ny = _dims(st["th"])
+        ide0 = nx - 1 if ide0 is None else ide0
+        jde0 = ny - 1 if jde0 is None else jde0
+        return int(lib().oracle_thompson_driver(
+            self._h, _p(st["qv"]), _p(st["qc"]), _p(st["qr"]), _p(st["qi"]), _p(st["qs"]), _p(st["qg"]),
+            _p(st["ni"]), _p(st["nr"]), _p(st["th"]), _p(st["pii"]), _p(st["pressure"]), _p(st["dz_mass"]),
+            C.c_float(dt), _p(st["rainnc"]), _p(st.get("rainncv")), _p(st.get("snownc")),
+            _p(st.get("graupelnc")), _p(st.get("sr")), nx, nz, ny, int(its), int(ite), int(jts), int(jte),
+            int(kts), int(kte), int(ide0), int(jde0)))
+
+    def column(self, col, dt):
+        """mp_thompson on one column dict (qv,qc,qi,qr,qs,qg,ni,nr,T,p,dz float32 1-D); returns
+        (no_micro, ppt[rain, snow, graupel, ice])."""
+        ppt = np.zeros(4, np.float32)
+        nk = col["T"].shape[0]
+        r = lib().oracle_thompson_column(
+            self._h, _p(col["qv"]), _p(col["qc"]), _p(col["qi"]), _p(col["qr"]), _p(col["qs"]), _p(col["qg"]),
+            _p(col["ni"]), _p(col["nr"]), _p(col["T"]), _p(col["p"]), _p(col["dz"]), _p(ppt), nk, C.c_float(dt))
+        return bool(r), ppt
+
+    def step(self, st, mp_dt, dt, order=2, fct=True, scratch=None):
+        """One Thompson + MPDATA model step on a state dict (the CPU baseline for BASELINE configs[2]).
+        st needs the 9 scalars, the metric / wind fields and float64 precipitation, snowfall, graupel."""
+        nx, nz, ny = _dims(st["th"])
+        if scratch is None:
+            scratch = (np.empty((ny, nz, nx - 1), np.float32), np.empty((ny - 1, nz, nx), np.float32),
+                       np.empty((ny, nz, nx), np.float32))
+        f = C.c_float
+        lib().oracle_step_thompson_f32(
+            self._h, _p(st["pressure"]), _p(st["th"]), _p(st["pii"]), _p(st["qv"]), _p(st["qc"]), _p(st["qr"]),
+            _p(st["qi"]), _p(st["qs"]), _p(st["qg"]), _p(st["ni"]), _p(st["nr"]), _p(st["precipitation"]),
+            _p(st["snowfall"]), _p(st["graupel"]), _p(st["sr"]), _p(st["dz_mass"]), _p(st["u"]), _p(st["v"]),
+            _p(st["w"]), _p(st["jacobian_u"]), _p(st["jacobian_v"]), _p(st["jacobian_w"]), _p(st["jacobian"]),
+            _p(st["advection_dz"]), f(mp_dt), f(dt), f(st["dx"]), nx, nz, ny, int(order), int(bool(fct)),
+            _p(scratch[0]), _p(scratch[1]), _p(scratch[2]))

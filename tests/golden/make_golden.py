@@ -77,6 +77,33 @@ def hill_case(nx=24, nz=10, ny=20, steps=3):
     return {k: st[k] for k in ("th", "qv", "qc", "qr", "qs", "rain", "snow")}, float(dt)
 
 
+def thompson_column_case(nz=24, ncall=12, dt=60.0):
+    """A single moist column (the ideal sounding, qv x 3) pushed through mp_thompson `ncall` times:
+    cloud -> ice -> snow -> graupel -> rain all fire.  Frozen from the oracle (parity unpinned)."""
+    st = ideal.add_thompson_fields(ideal.make_ideal_case(nx=3, nz=nz, ny=3), moisten=3.0)
+    T = O.Thompson(big_tables=True)
+    out = []
+    for _ in range(ncall):
+        T.driver(st, dt, 1, 1, 1, 1, 0, nz - 1)
+        out.append(np.stack([st[k][1, :, 1] for k in ("th", "qv", "qc", "qr", "qi", "qs", "qg", "ni", "nr")]))
+    ppt = np.array([st[k][1, 1] for k in ("rainnc", "snownc", "graupelnc")], np.float32)
+    return np.array(out, np.float32), ppt
+
+
+def thompson_table_samples():
+    """A fixed sample of entries of every lookup table (the full tables are 88 MB)."""
+    T = O.Thompson(big_tables=True)
+    rng = np.random.default_rng(7)
+    out = {}
+    for name in O.THOMPSON_TABLES:
+        flat = T.table(name).ravel()
+        idx = rng.choice(flat.size, size=min(64, flat.size), replace=False)
+        out[name + "_idx"] = idx
+        out[name] = flat[idx].copy()
+    out["constants"] = T.constants()
+    return out
+
+
 if __name__ == "__main__":
     O.build()
     rows, line = mpdata_scenario()
@@ -84,4 +111,7 @@ if __name__ == "__main__":
     np.savez_compressed(os.path.join(HERE, "mp_simple_scenario_f32.npz"), table=mp_simple_scenario())
     fields, dt = hill_case()
     np.savez_compressed(os.path.join(HERE, "hill_24x10x20_3steps_f32.npz"), dt=dt, **fields)
+    cols, ppt = thompson_column_case()
+    np.savez_compressed(os.path.join(HERE, "thompson_column_f32.npz"), columns=cols, ppt=ppt)
+    np.savez_compressed(os.path.join(HERE, "thompson_table_samples.npz"), **thompson_table_samples())
     print("written")
