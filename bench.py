@@ -39,8 +39,44 @@ if ROOT not in sys.path:
 
 METRIC = "grid_cell_updates_per_s"
 UNIT = "cell-updates/s"
-B_ALG = 128.0   # bytes per cell-update, SURVEY.md section 8d (mp_simple 56 B + MPDATA S=5 72 B)
-WORKLOAD = "ideal hill 512x512x40, MPDATA order2+FCT, mp_simple (BASELINE configs[1])"
+# bytes per cell-update, SURVEY.md section 8d: mp_simple 56 B + MPDATA S=5 72 B; Thompson 84 B + MPDATA S=9 104 B
+# Algorithmic bytes per cell and launch of each kernel family (distinct fields read + written
+# once, 4 B each; S = advected scalars) and the DRAM traffic one launch moved at 512x512x40 in the committed
+# `ncu --set full` captures (profiles/r1_v8_top_kernels.txt, profiles/r1_thompson_v1.txt), in bytes.
+KERNEL_BYTES = {
+    "k_mp_simple": lambda S: 56.0, "k_mp_thompson": lambda S: 84.0, "k_wind_normalise": lambda S: 44.0,
+    "k_face_coefficients": lambda S: 64.0, "k_upwind_all": lambda S: 20.0 + 8.0 * S,
+    "k_corrector_fused": lambda S: 44.0 + 12.0 * S,
+}
+NCU_TRAFFIC_512 = {("k_corrector_fused", 5): 1138.8e6, ("k_mp_simple", 5): 546.1e6, ("k_upwind_all", 5): 619.3e6,
+                   ("k_mp_thompson", 9): 847.4e6}
+SCHEMES = {
+    "simple": dict(mp=2, b_alg=128.0, scalars=("th", "qv", "qc", "qr", "qs"), acc=("precipitation", "snowfall"),
+                   workload="ideal hill {nx}x{ny}x{nz}, MPDATA order2+FCT, mp_simple (BASELINE configs[1])"),
+    "thompson": dict(mp=1, b_alg=188.0, scalars=("th", "qv", "qc", "qr", "qs", "qi", "qg", "ni", "nr"),
+                     acc=("precipitation", "snowfall", "graupel"),
+                     workload="ideal hill {nx}x{ny}x{nz}, MPDATA order2+FCT, Thompson microphysics (BASELINE configs[2])"),
+}
+
+
+def make_state(args):
+    from icar_b200 import ideal
+    st = ideal.make_ideal_case(nx=args.nx, nz=args.nz, ny=args.ny, perturb=True)
+    if args.mp == "thompson":
+        ideal.add_thompson_fields(st)
+    for k in SCHEMES[args.mp]["acc"]:
+        st[k] = np.zeros((args.ny, args.nx), np.float64)
+    return st
+
+
+def oracle_stepper(args):
+    """step(state, dt, scratch) -> scratch for the scheme's CPU restatement."""
+    from oracle import oracle as O
+    O.build()
+    if args.mp == "thompson":
+        T = O.Thompson(big_tables=True)
+        return O, lambda w, dt, scr: T.step(w, np.float32(dt), np.float32(dt), 2, True, scr)
+    return O, lambda w, dt, scr: O.step_simple(w, np.float32(dt), np.float32(dt), 2, True, scr)
 
 
 def measured_peak():
@@ -130,19 +166,20 @@ def physical_device(local_rank):
 
 
 # --------------------------------------------------------------------------------------------
-def cpu_oracle_rate(st, dt, min_seconds, max_steps, threads=None):
-    """Times oracle.step_simple on the full workload; returns (cells/s, steps, seconds, threads)."""
-    from oracle import oracle as O
-    O.build()
+def cpu_oracle_rate(args, st, dt, min_seconds, max_steps, threads=None):
+    """Times the oracle step on the full workload; returns (cells/s, steps, seconds, threads)."""
+    O, step = oracle_stepper(args)
     if threads:
         O.set_threads(threads)
     thr = O.max_threads()
     work = {k: (v.copy() if isinstance(v, np.ndarray) else v) for k, v in st.items()}
     cells = work["th"].size
-    scratch = None
+    ny, nz, nx = work["th"].shape
+    scratch = (np.empty((ny, nz, nx - 1), np.float32), np.empty((ny - 1, nz, nx), np.float32),
+               np.empty((ny, nz, nx), np.float32))
     steps, t0 = 0, time.perf_counter()
     while steps < max_steps:
-        scratch = O.step_simple(work, np.float32(dt), np.float32(dt), 2, True, scratch)
+        step(work, dt, scratch)
         steps += 1
         if time.perf_counter() - t0 >= min_seconds:
             break
@@ -154,31 +191,35 @@ def run_reference(args, rank, world):
     """--impl reference: the CPU restatement of the reference Fortran on all host threads."""
     if rank != 0:
         return
-    from icar_b200 import ideal
     nx, nz, ny = args.nx, args.nz, args.ny
     # bounded sample: a y-band of the workload sized so that K+W steps end within minutes
-    st = ideal.make_ideal_case(nx=nx, nz=nz, ny=ny, perturb=True)
+    st = make_state(args)
     dt = float(st["dt"])
-    from oracle import oracle as O
-    O.build()
+    O, step = oracle_stepper(args)
     thr = O.max_threads()
+
+    def scratch_for(b):
+        n = b["th"].shape[0]
+        return (np.empty((n, nz, nx - 1), np.float32), np.empty((n - 1, nz, nx), np.float32),
+                np.empty((n, nz, nx), np.float32))
+
     probe_ny = min(ny, 32)
     band = {k: (np.ascontiguousarray(v[:probe_ny + (1 if k in ("v", "jacobian_v") else 0)])
                 if isinstance(v, np.ndarray) and v.ndim >= 2 else v) for k, v in st.items()}
     t0 = time.perf_counter()
-    O.step_simple(band, np.float32(dt), np.float32(dt), 2, True)
+    step(band, dt, scratch_for(band))
     per_row = (time.perf_counter() - t0) / probe_ny
     budget = 150.0 / max(1, args.steps + args.warmup)          # seconds per step
     sample_ny = int(max(8, min(ny, budget / max(per_row, 1e-9))))
     band = {k: (np.ascontiguousarray(v[:sample_ny + (1 if k in ("v", "jacobian_v") else 0)])
                 if isinstance(v, np.ndarray) and v.ndim >= 2 else v) for k, v in st.items()}
     cells = nx * nz * sample_ny
-    scratch = None
+    scratch = scratch_for(band)
     for _ in range(args.warmup):
-        scratch = O.step_simple(band, np.float32(dt), np.float32(dt), 2, True, scratch)
+        step(band, dt, scratch)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        scratch = O.step_simple(band, np.float32(dt), np.float32(dt), 2, True, scratch)
+        step(band, dt, scratch)
     el = time.perf_counter() - t0
     value = cells * args.steps / el
     sample = f"{args.steps} steps of a {nx}x{nz}x{sample_ny} y-band of the workload"
@@ -187,7 +228,7 @@ def run_reference(args, rank, world):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": el / args.steps * 1e3,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
-        "config": {"workload": WORKLOAD, "grid": [nx, nz, ny], "sample": sample,
+        "config": {"workload": SCHEMES[args.mp]["workload"].format(nx=nx, ny=ny, nz=nz), "grid": [nx, nz, ny], "sample": sample,
                    "note": "CPU restatement (oracle port) of the reference Fortran; the Fortran itself "
                            "cannot be compiled in this image (no gfortran)"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": thr, "kind": "port", "sample": sample},
@@ -213,7 +254,8 @@ def run_b200(args, rank, world, local_rank):
 
     nx, nz, ny = args.nx, args.nz, args.ny
     halo = args.halo
-    st = ideal.make_ideal_case(nx=nx, nz=nz, ny=ny, perturb=True)
+    scheme = SCHEMES[args.mp]
+    st = make_state(args)
     dt = float(st["dt"])
     if distributed:
         grid = (icar_b200.Grid.xslab if args.slabs == "x" else icar_b200.Grid.yslab)(nx, nz, ny, world, rank + 1, halo)
@@ -221,7 +263,7 @@ def run_b200(args, rank, world, local_rank):
     else:
         grid = icar_b200.Grid.single_image(nx, nz, ny, halo_size=1)
         local = st
-    dom = icar_b200.Domain(grid, icar_b200.Options(dx=st["dx"]), device=local_rank)
+    dom = icar_b200.Domain(grid, icar_b200.Options(dx=st["dx"], microphysics=scheme["mp"]), device=local_rank)
     dom.upload_state(local)
     if distributed:
         ids = [icar_b200.comm_unique_id() if rank == 0 else None]
@@ -261,16 +303,24 @@ def run_b200(args, rank, world, local_rank):
     ms_per_step = ms / args.steps
     value = cells_global / (ms_per_step * 1e-3)
 
+    # ---------------- per-kernel timing (CUDA events around every launch, on the launching stream) for the
+    # roofline of the dominant kernel; a separate pass of the same steps so that the events do not sit
+    # inside the timed region above
+    dom.profile_enable(True)
+    for _ in range(args.steps):
+        dom.physics_step(dt)
+    prof = dom.profile_read()
+    dom.profile_enable(False)
+    barrier()
+
     # ---------------- end-to-end timing: host arrays in, host arrays out
     host = {k: (np.ascontiguousarray(v) if isinstance(v, np.ndarray) else v) for k, v in local.items()}
-    for k in ("th", "qv", "qc", "qr", "qs"):
+    for k in scheme["scalars"] + scheme["acc"]:
         host[k] = dom.download(k)
-    host["precipitation"] = dom.download("precipitation")
-    host["snowfall"] = dom.download("snowfall")
     hd = dom.host_domain(host)
     dom.host_register(hd)
-    in_keys = ("u", "v", "w", "pressure", "pii", "rho", "th", "qv", "qc", "qr", "qs", "precipitation", "snowfall")
-    out_keys = ("th", "qv", "qc", "qr", "qs", "precipitation", "snowfall")
+    in_keys = ("u", "v", "w", "pressure", "pii", "rho") + scheme["scalars"] + scheme["acc"]
+    out_keys = scheme["scalars"] + scheme["acc"]
     h2d = int(sum(host[k].nbytes for k in in_keys))
     d2h = int(sum(host[k].nbytes for k in out_keys))
     e2e_steps = max(3, min(args.steps, 10))
@@ -294,19 +344,33 @@ def run_b200(args, rank, world, local_rank):
     # ---------------- CPU baseline (rank 0, N=1 only)
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        rate, csteps, csec, thr = cpu_oracle_rate(st, dt, min_seconds=10.0, max_steps=5)
+        rate, csteps, csec, thr = cpu_oracle_rate(args, st, dt, min_seconds=10.0, max_steps=5)
         cpu = {"value": rate, "unit": UNIT, "cores": thr, "kind": "port",
                "sample": f"{csteps} full step(s) of the same {nx}x{nz}x{ny} workload, {csec:.1f} s, "
                          f"OpenMP over j with {thr} threads (oracle/: C++ restatement of the Fortran)"}
 
     peak, peak_src = measured_peak()
+    B_ALG = scheme["b_alg"]
     achieved = value * B_ALG / 1e9 / world          # GB/s per GPU on algorithmic bytes
+    S = len(scheme["scalars"])
+    cells_local = grid.nx * grid.nz * grid.ny
+    kernels = {}
+    for name, (kms, kn) in prof.items():
+        e = {"ms_per_step": kms / args.steps, "launches_per_step": kn / args.steps, "avg_us": kms / max(kn, 1) * 1e3}
+        if name in KERNEL_BYTES:
+            # one launch of a family covers the tile once (mp strips + interior together do)
+            per_step_bytes = KERNEL_BYTES[name](S) * cells_local
+            e["algorithmic_bytes_per_cell"] = KERNEL_BYTES[name](S)
+            e["achieved_gbs"] = per_step_bytes / (kms / args.steps * 1e-3) / 1e9
+        kernels[name] = e
+    dominant = max(kernels, key=lambda k: kernels[k]["ms_per_step"]) if kernels else None
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "grid": [nx, nz, ny], "dt_s": dt, "advected_scalars": 5,
+            "config": {"workload": scheme["workload"].format(nx=nx, ny=ny, nz=nz), "grid": [nx, nz, ny], "dt_s": dt,
+                       "advected_scalars": len(scheme["scalars"]),
                        "decomposition": (f"{args.slabs}-slabs over {world} GPUs, halo {halo}, NCCL send/recv" if distributed
                                          else "single image"),
                        "l2": "resident working set ~1.1 GB per step > 126 MB L2, no explicit flush",
@@ -316,10 +380,23 @@ def run_b200(args, rank, world, local_rank):
                     "steps": e2e_steps, "ms_per_step": e2e_s / e2e_steps * 1e3,
                     "api": "icar_physics_step_host (pinned host arrays)"},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None,
-                         "kernel": "whole step (all kernels of mp + advect), per GPU",
-                         "algorithmic_bytes_per_cell_update": B_ALG, "peak_source": peak_src},
+            # the dominant kernel, timed live with CUDA events (rank 0's tile); `traffic` = DRAM bytes of one
+            # launch from the committed ncu --set full capture (only known for the default 512x512x40 tile)
+            "roofline": ({"bound": "hbm", "kernel": dominant, "achieved": kernels[dominant].get("achieved_gbs"),
+                          "peak": peak, "unit": "GB/s",
+                          "frac": (kernels[dominant]["achieved_gbs"] / peak) if "achieved_gbs" in kernels[dominant] else None,
+                          "traffic": (NCU_TRAFFIC_512.get((dominant, S)) if (grid.nx, grid.nz, grid.ny) == (512, 40, 512) else None),
+                          "algorithmic_bytes_per_launch": kernels[dominant].get("algorithmic_bytes_per_cell", 0) * cells_local,
+                          "avg_launch_us": kernels[dominant]["ms_per_step"] * 1e3,
+                          "share_of_step": kernels[dominant]["ms_per_step"] / sum(k["ms_per_step"] for k in kernels.values()),
+                          "peak_source": peak_src,
+                          "note": "issue-bound, not HBM-bound: see DESIGN.md section 3 (instruction counts per cell)"}
+                         if dominant else None),
+            # the BASELINE metric's own figure: whole step on the algorithmic bytes of SURVEY.md section 8d
+            "step_roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                              "kernel": "whole step (all kernels of mp + advect), per GPU",
+                              "algorithmic_bytes_per_cell_update": B_ALG},
+            "kernels": kernels,
         }
         if cpu:
             line["cpu_baseline"] = cpu
@@ -343,6 +420,8 @@ def main():
     ap.add_argument("--slabs", default="y", choices=["x", "y"],
                     help="decomposition axis for N>1 (y keeps full-width rows and contiguous halo planes)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--mp", default="simple", choices=["simple", "thompson"],
+                    help="microphysics scheme: simple = BASELINE configs[1] (the headline), thompson = configs[2]")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -132,7 +132,8 @@ class HostDomain(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in (
         "u", "v", "w", "pressure", "exner", "density", "potential_temperature", "water_vapor",
         "cloud_water", "rain_in_air", "snow_in_air", "accumulated_precipitation",
-        "accumulated_snowfall")]
+        "accumulated_snowfall", "cloud_ice", "ice_number", "rain_number", "graupel_in_air",
+        "accumulated_graupel")]
 
 
 _lib = None
@@ -147,7 +148,8 @@ SYMBOLS = (
     "icar_halo_plan", "icar_comm_unique_id", "icar_comm_init", "icar_mpdata_set_winds", "icar_mpdata_advect3d",
     "icar_mpdata_set_winds_f64", "icar_mpdata_advect3d_f64", "icar_mp_simple_driver",
     "icar_physics_step_host", "icar_host_register", "icar_host_unregister",
-    "icar_default_mp_options", "icar_thompson_init", "icar_thompson_table", "icar_mp_gt_driver")
+    "icar_default_mp_options", "icar_thompson_init", "icar_thompson_table", "icar_mp_gt_driver",
+    "icar_profile_enable", "icar_profile_read")
 
 
 def lib() -> C.CDLL:
@@ -289,6 +291,18 @@ class Domain:
         self._check(lib().icar_timer_stop(self._h, C.byref(ms)))
         return float(ms.value)
 
+    def profile_enable(self, on=True):
+        self._check(lib().icar_profile_enable(self._h, int(bool(on))))
+
+    def profile_read(self):
+        """{kernel family: (milliseconds, launches)} since the last read (CUDA events per launch)."""
+        names = ((C.c_char * 32) * 16)()
+        ms = (C.c_float * 16)()
+        n_l = (C.c_longlong * 16)()
+        n = C.c_int()
+        self._check(lib().icar_profile_read(self._h, 16, names, ms, n_l, C.byref(n)))
+        return {names[i].value.decode(): (float(ms[i]), int(n_l[i])) for i in range(n.value)}
+
     # -- multi-image
     def comm_init(self, image, nimages, unique_id: bytes):
         buf = C.create_string_buffer(unique_id, 128)
@@ -369,7 +383,8 @@ class Domain:
         m = dict(u="u", v="v", w="w", pressure="pressure", exner="pii", density="rho",
                  potential_temperature="th", water_vapor="qv", cloud_water="qc", rain_in_air="qr",
                  snow_in_air="qs", accumulated_precipitation="precipitation",
-                 accumulated_snowfall="snowfall")
+                 accumulated_snowfall="snowfall", cloud_ice="qi", ice_number="ni", rain_number="nr",
+                 graupel_in_air="qg", accumulated_graupel="graupel")
         for field, key in m.items():
             a = st.get(key)
             if a is not None:

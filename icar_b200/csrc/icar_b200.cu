@@ -127,6 +127,13 @@ struct icar_ctx {
     float *send_w = nullptr, *send_e = nullptr, *recv_w = nullptr, *recv_e = nullptr;
     bool exchange_in_flight = false;
     bool winds_f64_valid = false;
+    // per-kernel profile (icar_profile_enable / icar_profile_read): event pairs queued on the launching stream
+    bool prof_on = false;
+    struct ProfRec { int kid; cudaEvent_t a, b; };
+    std::vector<ProfRec> prof_pending;
+    std::vector<cudaEvent_t> prof_pool;
+    double prof_ms[16] = {};
+    long long prof_n[16] = {};
     // module state of mp_thompson (constants + the 29 lookup tables), filled by icar_thompson_init
     bool th_ready = false;
     ThConst thc{};
@@ -142,6 +149,30 @@ int fail(icar_ctx* c, int code, const std::string& msg) {
     if (c) c->err = msg; else g_create_error = msg;
     return code;
 }
+
+// kernel families of the per-kernel profile
+enum ProfKid { K_MP_SIMPLE = 0, K_MP_THOMPSON, K_ACCUMULATE, K_WIND_NORMALISE, K_FACE_COEF, K_UPWIND_PASS1, K_CORRECTOR,
+               K_STAGED_ADVECT3D, K_HALO_PACK, K_HALO_UNPACK, K_COUNT };
+const char* const kProfNames[K_COUNT] = {"k_mp_simple", "k_mp_thompson", "k_accumulate_precip", "k_wind_normalise",
+                                         "k_face_coefficients", "k_upwind_all", "k_corrector_fused",
+                                         "staged_advect3d", "k_halo_pack", "k_halo_unpack"};
+
+cudaEvent_t prof_event(icar_ctx* c) {
+    if (!c->prof_pool.empty()) { cudaEvent_t e = c->prof_pool.back(); c->prof_pool.pop_back(); return e; }
+    cudaEvent_t e = nullptr;
+    cudaEventCreate(&e);
+    return e;
+}
+// brackets the launches queued on `st` between construction and destruction
+struct ProfScope {
+    icar_ctx* c; int kid; cudaStream_t st; cudaEvent_t a = nullptr;
+    ProfScope(icar_ctx* c_, int kid_, cudaStream_t st_) : c(c_), kid(kid_), st(st_) {
+        if (c->prof_on) { a = prof_event(c); cudaEventRecord(a, st); }
+    }
+    ~ProfScope() {
+        if (a) { cudaEvent_t b = prof_event(c); cudaEventRecord(b, st); c->prof_pending.push_back({kid, a, b}); }
+    }
+};
 
 #define CU(call)                                                                         \
     do {                                                                                 \
@@ -261,6 +292,7 @@ int run_mp_tiles(icar_ctx* ctx, float mp_dt, const int (*t)[4], int ntiles, int 
             tiles.jte[a] = std::min(tiles.jte[a], gr.jde - 1 - gr.jms);
             tiles.along_y[a] = ((tiles.ite[a] - tiles.its[a] + 1) < 4 && (tiles.jte[a] - tiles.jts[a]) > (tiles.ite[a] - tiles.its[a])) ? 1 : 0;
         }
+        ProfScope ps(ctx, K_MP_THOMPSON, st);
         int nl = th_driver_launch(
             ctx->g, ctx->thc, ctx->tht, (float*)ctx->vars[ICAR_VAR_WATER_VAPOR], (float*)ctx->vars[ICAR_VAR_CLOUD_WATER],
             (float*)ctx->vars[ICAR_VAR_RAIN_IN_AIR], (float*)ctx->vars[ICAR_VAR_CLOUD_ICE],
@@ -278,6 +310,7 @@ int run_mp_tiles(icar_ctx* ctx, float mp_dt, const int (*t)[4], int ntiles, int 
     if (ctx->opt.microphysics == 2) {
         float c2s = std::exp(-1.0f * (1.0f / 2000.0f) * mp_dt);    // mp_simple.f90:619
         float c2r = std::exp(-1.0f * (1.0f / 500.0f) * mp_dt);     // mp_simple.f90:620
+        ProfScope ps(ctx, K_MP_SIMPLE, st);
         int nl = mp_simple_launch(
             ctx->g, (const float*)ctx->vars[ICAR_VAR_PRESSURE],
             (float*)ctx->vars[ICAR_VAR_POTENTIAL_TEMPERATURE], (const float*)ctx->vars[ICAR_VAR_EXNER],
@@ -300,6 +333,7 @@ int run_mp_tiles(icar_ctx* ctx, float mp_dt, const int (*t)[4], int ntiles, int 
 int join_aux(icar_ctx* ctx) {
     if (!ctx->aux_pending && !ctx->main_acc_pending) return ICAR_OK;
     if (ctx->aux_pending) CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_aux, 0));
+    ProfScope ps(ctx, K_ACCUMULATE, ctx->stream);
     ctx->launches += accumulate_precip_launch(
         ctx->g.nx, ctx->g.ny, ctx->ld2, ctx->main_acc_pending ? ctx->rain2d : nullptr,
         ctx->main_acc_pending ? ctx->snow2d : nullptr, ctx->aux_pending ? ctx->rain2d_halo : nullptr,
@@ -492,6 +526,8 @@ extern "C" int icar_destroy(icar_ctx* ctx) {
         for (int n = 0; n < ICAR_MAX_SCALARS; ++n) { if (ctx->fq2[n]) cudaFree(ctx->fq2[n]); if (ctx->fout[n]) cudaFree(ctx->fout[n]); }
     }
     for (void* p : ctx->scratch) if (p) cudaFree(p);
+    for (auto& r : ctx->prof_pending) { if (r.kid >= 0) cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+    for (cudaEvent_t e : ctx->prof_pool) cudaEventDestroy(e);
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
     if (ctx->ev_aux) cudaEventDestroy(ctx->ev_aux);
     if (ctx->aux) cudaStreamDestroy(ctx->aux);
@@ -613,12 +649,15 @@ extern "C" int icar_advect(icar_ctx* ctx, float dt) {
     const float* dz = (const float*)ctx->vars[ICAR_VAR_ADVECTION_DZ];
     const bool mpdata = (ctx->opt.advection == 2);
     // adv_mpdata.f90:500-506 / advect.f90:344-347
-    ctx->launches += staged_wind_normalise<float>(
-        g, (const float*)ctx->vars[ICAR_VAR_U], (const float*)ctx->vars[ICAR_VAR_V],
-        (const float*)ctx->vars[ICAR_VAR_W], (const float*)ctx->vars[ICAR_VAR_JACOBIAN_U],
-        (const float*)ctx->vars[ICAR_VAR_JACOBIAN_V], (const float*)ctx->vars[ICAR_VAR_JACOBIAN_W], rho, dt,
-        ctx->opt.dx, mpdata ? 2 : 1, ctx->U, ctx->V, ctx->W, ctx->stream, ctx->fused ? dz : nullptr,
-        ctx->fused ? ctx->Wn : nullptr);
+    {
+        ProfScope ps(ctx, K_WIND_NORMALISE, ctx->stream);
+        ctx->launches += staged_wind_normalise<float>(
+            g, (const float*)ctx->vars[ICAR_VAR_U], (const float*)ctx->vars[ICAR_VAR_V],
+            (const float*)ctx->vars[ICAR_VAR_W], (const float*)ctx->vars[ICAR_VAR_JACOBIAN_U],
+            (const float*)ctx->vars[ICAR_VAR_JACOBIAN_V], (const float*)ctx->vars[ICAR_VAR_JACOBIAN_W], rho, dt,
+            ctx->opt.dx, mpdata ? 2 : 1, ctx->U, ctx->V, ctx->W, ctx->stream, ctx->fused ? dz : nullptr,
+            ctx->fused ? ctx->Wn : nullptr);
+    }
     const int order = mpdata ? ctx->opt.mpdata_order : 1;
     const float* G = jaco;          // jaco*rho with rho == 1 is jaco itself
     if (order > 1 && !ctx->fused) {
@@ -633,7 +672,15 @@ extern "C" int icar_advect(icar_ctx* ctx, float dt) {
             ss.q2[n] = ctx->fq2[n];
             ss.out[n] = ctx->fout[n];
         }
-        const int nl = fused_advect_all(g, ss, ctx->U, ctx->V, ctx->W, ctx->Wn, jaco, dz, ctx->coef, ctx->stream);
+        cudaEvent_t marks[4];
+        if (ctx->prof_on) for (cudaEvent_t& m : marks) m = prof_event(ctx);
+        const int nl = fused_advect_all(g, ss, ctx->U, ctx->V, ctx->W, ctx->Wn, jaco, dz, ctx->coef, ctx->stream,
+                                        ctx->prof_on ? marks : nullptr);
+        if (ctx->prof_on) {      // consecutive marks delimit the three kernels
+            ctx->prof_pending.push_back({K_FACE_COEF, marks[0], marks[1]});
+            ctx->prof_pending.push_back({-K_UPWIND_PASS1 - 100, marks[1], marks[2]});    // negative id: the start event is the
+            ctx->prof_pending.push_back({-K_CORRECTOR - 100, marks[2], marks[3]});       // previous record's stop event
+        }
         if (nl < 0) return fail(ctx, ICAR_ERR_CUDA, "icar_advect: cannot set up the TMA tensor maps / shared memory of the fused MPDATA kernel");
         ctx->launches += nl;
         CU(cudaGetLastError());
@@ -645,6 +692,7 @@ extern "C" int icar_advect(icar_ctx* ctx, float dt) {
         return ICAR_OK;
     }
     // adv_mpdata.f90:512-522: every scalar with vars_to_advect > 0 (mp_simple.f90:116-118)
+    ProfScope ps_staged(ctx, K_STAGED_ADVECT3D, ctx->stream);
     for (int s = 0; s < ctx->nadv; ++s) {
         int var = ctx->adv[s];
         float* q = (float*)ctx->vars[var];
@@ -831,7 +879,8 @@ extern "C" int icar_halo_send(icar_ctx* ctx) {
         float* bufs[2];
         if (lower) { x0[ns] = plan[0]; bufs[ns++] = ctx->send_w; }
         if (upper) { x0[ns] = plan[1]; bufs[ns++] = ctx->send_e; }
-        ctx->launches += halo_pack_launch(ctx->g, fields, nf, h, ns, x0, bufs, ctx->stream);
+        { ProfScope ps(ctx, K_HALO_PACK, ctx->stream);
+          ctx->launches += halo_pack_launch(ctx->g, fields, nf, h, ns, x0, bufs, ctx->stream); }
         CU(cudaGetLastError());
         CU(cudaEventRecord(ctx->ev_packed, ctx->stream));
         CU(cudaStreamWaitEvent(ctx->comm_stream, ctx->ev_packed, 0));
@@ -887,7 +936,8 @@ extern "C" int icar_halo_retrieve(icar_ctx* ctx) {
         float* bufs[2];
         if (lower) { x0[ns] = plan[2]; bufs[ns++] = ctx->recv_w; }
         if (upper) { x0[ns] = plan[3]; bufs[ns++] = ctx->recv_e; }
-        ctx->launches += halo_unpack_launch(ctx->g, fields, nf, h, ns, x0, bufs, ctx->stream);
+        { ProfScope ps(ctx, K_HALO_UNPACK, ctx->stream);
+          ctx->launches += halo_unpack_launch(ctx->g, fields, nf, h, ns, x0, bufs, ctx->stream); }
         CU(cudaGetLastError());
     }
     ctx->exchange_in_flight = false;
@@ -1086,6 +1136,11 @@ void host_fields(const icar_host_domain* d, std::vector<HostField>& f) {
         {ICAR_VAR_SNOW_IN_AIR, d->snow_in_air, d->snow_in_air},
         {ICAR_VAR_PRECIPITATION, d->accumulated_precipitation, d->accumulated_precipitation},
         {ICAR_VAR_SNOWFALL, d->accumulated_snowfall, d->accumulated_snowfall},
+        {ICAR_VAR_CLOUD_ICE, d->cloud_ice, d->cloud_ice},
+        {ICAR_VAR_ICE_NUMBER, d->ice_number, d->ice_number},
+        {ICAR_VAR_RAIN_NUMBER, d->rain_number, d->rain_number},
+        {ICAR_VAR_GRAUPEL_IN_AIR, d->graupel_in_air, d->graupel_in_air},
+        {ICAR_VAR_GRAUPEL, d->accumulated_graupel, d->accumulated_graupel},
     };
 }
 }  // namespace
@@ -1242,5 +1297,48 @@ extern "C" int icar_mp_gt_driver(icar_ctx* ctx, float* qv, float* qc, float* qr,
     for (int i = 0; i < 7; ++i)
         if (out2[i] && (rc = copy_out(ctx, out2[i], b[12 + i], g.nx, ctx->ld2, g.ny, sizeof(float)))) return rc;
     CU(cudaStreamSynchronize(ctx->stream));
+    return ICAR_OK;
+}
+
+// ============================================================================ per-kernel profile
+
+extern "C" int icar_profile_enable(icar_ctx* ctx, int on) {
+    if (!ctx) return ICAR_ERR_INVALID;
+    CU(cudaSetDevice(ctx->device));
+    { int jr = join_aux(ctx); if (jr) return jr; }
+    CU(cudaStreamSynchronize(ctx->stream));
+    CU(cudaStreamSynchronize(ctx->aux));
+    for (auto& r : ctx->prof_pending) { if (r.kid >= 0) ctx->prof_pool.push_back(r.a); ctx->prof_pool.push_back(r.b); }
+    ctx->prof_pending.clear();
+    for (int k = 0; k < 16; ++k) { ctx->prof_ms[k] = 0.0; ctx->prof_n[k] = 0; }
+    ctx->prof_on = on != 0;
+    return ICAR_OK;
+}
+
+extern "C" int icar_profile_read(icar_ctx* ctx, int max_entries, char (*names)[32], float* ms, long long* launches,
+                                 int* n_out) {
+    if (!ctx || !names || !ms || !launches || !n_out) return fail(ctx, ICAR_ERR_INVALID, "icar_profile_read: null argument");
+    CU(cudaSetDevice(ctx->device));
+    { int jr = join_aux(ctx); if (jr) return jr; }
+    CU(cudaStreamSynchronize(ctx->stream));
+    CU(cudaStreamSynchronize(ctx->aux));
+    for (auto& r : ctx->prof_pending) {
+        const int kid = r.kid >= 0 ? r.kid : -(r.kid + 100);
+        float t = 0.f;
+        if (cudaEventElapsedTime(&t, r.a, r.b) == cudaSuccess) { ctx->prof_ms[kid] += t; ctx->prof_n[kid] += 1; }
+        if (r.kid >= 0) ctx->prof_pool.push_back(r.a);      // shared start events belong to the previous record
+        ctx->prof_pool.push_back(r.b);
+    }
+    ctx->prof_pending.clear();
+    int n = 0;
+    for (int k = 0; k < K_COUNT && n < max_entries; ++k) {
+        if (!ctx->prof_n[k]) continue;
+        std::snprintf(names[n], 32, "%s", kProfNames[k]);
+        ms[n] = (float)ctx->prof_ms[k];
+        launches[n] = ctx->prof_n[k];
+        ++n;
+    }
+    *n_out = n;
+    for (int k = 0; k < 16; ++k) { ctx->prof_ms[k] = 0.0; ctx->prof_n[k] = 0; }
     return ICAR_OK;
 }

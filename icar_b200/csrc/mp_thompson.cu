@@ -21,6 +21,7 @@
 // Typing follows the Fortran: REAL -> float, DOUBLE PRECISION -> double, mixed expressions promote
 // where the Fortran's do.  -fmad=false (see Makefile): no contraction.
 #include <algorithm>
+#include <cstdlib>
 
 #include "mp_thompson.cuh"
 
@@ -59,6 +60,31 @@ __device__ __forceinline__ float rsif(float P, float T) {                  // :3
     const float X = fmaxf(-80.f, T - 273.16f);
     const float ESI = C0 + X * (C1 + X * (C2 + X * (C3 + X * (C4 + X * (C5 + X * (C6 + X * (C7 + X * C8)))))));
     return .622f * ESI / (P - ESI);
+}
+
+// x**y in REAL*8.  The exponents are run-time constants of the scheme (gamma-distribution shape
+// parameters: cre(), cge(), bm_r ...) and for the default options most are small integers -- x**1,
+// x**3, (lamr+fv_r)**(-5) ... -- which a few multiplications evaluate to within a few ulp(double) of pow()
+// (also quarter-integer exponents such as oge1 = 1/4, cre(12) = 2.5, cre(7) = 3.5, through sqrt);
+// the general case stays a call (not inlined: ~250 instructions each, the kernel has 40 call sites).
+__device__ __noinline__ double dpow_general(double x, double y) { return pow(x, y); }
+__device__ __forceinline__ double dpow(double x, double y) {
+    const double y4 = 4.0 * y;
+    if (y4 == rint(y4) && fabs(y) <= 8.0) {        // uniform across the grid: y is a constant
+        // y = n + f/4: x**n by multiplication, x**(1/2) and x**(1/4) by (correctly rounded) square roots
+        const double ay = fabs(y);
+        int n = (int)ay;
+        const int f = (int)(4.0 * (ay - (double)n));      // 0..3
+        double p = 1.0, b = x;
+        while (n) { if (n & 1) p *= b; b *= b; n >>= 1; }
+        if (f) {
+            const double r2 = sqrt(x);
+            if (f & 2) p *= r2;
+            if (f & 1) p *= sqrt(r2);
+        }
+        return y < 0.0 ? 1.0 / p : p;
+    }
+    return dpow_general(x, y);
 }
 
 // 10.**n for integer n the way gfortran evaluates it (libgcc __powisf2)
@@ -117,12 +143,12 @@ __device__ __forceinline__ float rain_balance(const ThConst& c, float rr, float&
     if (mvd > 2.5E-3f) {
         mvd = 2.5E-3f;
         lamr = (3.0f + c.o.mu_r + 0.672f) / mvd;
-        nr = (float)(c.crg[1] * c.org3 * rr * pow(lamr, (double)bm_r) / c.am_r);
+        nr = (float)(c.crg[1] * c.org3 * rr * dpow(lamr, (double)bm_r) / c.am_r);
         clamped = true;
     } else if (mvd < D0r * 0.75f) {
         mvd = D0r * 0.75f;
         lamr = (3.0f + c.o.mu_r + 0.672f) / mvd;
-        nr = (float)(c.crg[1] * c.org3 * rr * pow(lamr, (double)bm_r) / c.am_r);
+        nr = (float)(c.crg[1] * c.org3 * rr * dpow(lamr, (double)bm_r) / c.am_r);
         clamped = true;
     }
     return mvd;
@@ -136,7 +162,8 @@ struct Args {
 };
 
 // Shared memory (doubles first): s_n0[nz][TX] double | s_f[7][(nz+1)][TX] float | s_i[10][TX] int
-__global__ void __launch_bounds__(TX * 64)
+template <int MAXT, int MINB>
+__global__ void __launch_bounds__(MAXT, MINB)
 k_mp_thompson(Geom g, ThConst c, ThTables tb, Args A, int ld2, float dt, MpTiles tiles, int kts, int kte,
               unsigned long long* diag) {
     const int its = tiles.its[blockIdx.z], ite = tiles.ite[blockIdx.z];
@@ -189,10 +216,10 @@ k_mp_thompson(Geom g, ThConst c, ThTables tb, Args A, int ld2, float dt, MpTiles
         const float xDi = (float)((bm_i + mu_i + 1.f) * ilami);
         if (xDi < 20.E-6f) {
             lami = c.cie[1] / 20.E-6f;
-            ni = (float)fmin(250.E3, c.cig[0] * c.oig2 * ri / c.am_i * pow(lami, (double)bm_i));
+            ni = (float)fmin(250.E3, c.cig[0] * c.oig2 * ri / c.am_i * dpow(lami, (double)bm_i));
         } else if (xDi > 300.E-6f) {
             lami = c.cie[1] / 300.E-6f;
-            ni = (float)(c.cig[0] * c.oig2 * ri / c.am_i * pow(lami, (double)bm_i));
+            ni = (float)(c.cig[0] * c.oig2 * ri / c.am_i * dpow(lami, (double)bm_i));
         }
     } else { qi1d = 0.0f; ni1d = 0.0f; ri = R1; ni = R2; L_qi = false; }
     if (qr1d > R1) {
@@ -289,14 +316,14 @@ k_mp_thompson(Geom g, ThConst c, ThTables tb, Args A, int ld2, float dt, MpTiles
             double N0_min = gonv_max;
             for (int q = kk; q < nk; ++q) N0_min = fmin(s_n0[q * TX + tx], N0_min);
             N0_exp = N0_min;
-            const double lam_exp = pow((N0_exp * c.am_g * c.cgg[0] / rg), (double)c.oge1);
+            const double lam_exp = dpow((N0_exp * c.am_g * c.cgg[0] / rg), (double)c.oge1);
             const double lamg = lam_exp * powf((c.cgg[2] * c.ogg2 * c.ogg1), c.obmg);
             ilamg = 1. / lamg;
-            N0_g = N0_exp / (c.cgg[1] * lam_exp) * pow(lamg, (double)c.cge[1]);
+            N0_g = N0_exp / (c.cgg[1] * lam_exp) * dpow(lamg, (double)c.cge[1]);
             const double lamr = powf((c.am_r * c.crg[2] * c.org2 * nr / rr), c.obmr);
             ilamr = 1. / lamr;
             mvd_r = (float)((3.0f + c.o.mu_r + 0.672f) / lamr);
-            N0_r = nr * c.org2 * pow(lamr, (double)c.cre[1]);
+            N0_r = nr * c.org2 * dpow(lamr, (double)c.cre[1]);
         }
     };
     graupel_rain_slopes();
@@ -330,7 +357,7 @@ k_mp_thompson(Geom g, ThConst c, ThTables tb, Args A, int ld2, float dt, MpTiles
                 idx = min(idx, nbins);
                 const int jc = min((int)(mvd_c * 1.E6f), nbins);          // (upper clamp: memory safety only)
                 const float Ef_rw = (float)tb.t[T_Efrw][(idx - 1) + nbins * (jc - 1)];
-                prr_rcw = rhof * c.t1_qr_qc * Ef_rw * rc * N0_r * (pow((lamr + fv_r), (double)(-c.cre[8])));
+                prr_rcw = rhof * c.t1_qr_qc * Ef_rw * rc * N0_r * (dpow((lamr + fv_r), (double)(-c.cre[8])));
                 prr_rcw = fmin((double)(rc * odts), prr_rcw);
             }
         }
@@ -350,7 +377,7 @@ k_mp_thompson(Geom g, ThConst c, ThTables tb, Args A, int ld2, float dt, MpTiles
             idx_r = decade_index(rr, c.nir2, ntb_r);
             const double lamr = 1. / ilamr;
             const double lam_exp = lamr * powf((c.crg[2] * c.org2 * c.org1), bm_r);
-            const double N0_exp = c.org1 * rr / c.am_r * pow(lam_exp, (double)c.cre[0]);
+            const double N0_exp = c.org1 * rr / c.am_r * dpow(lam_exp, (double)c.cre[0]);
             idx_r1 = decade_index_d(N0_exp, c.nir3, ntb_r1);
         }
         const int idx_s = (rs > 1.e-5f) ? decade_index(rs, c.nis2, ntb_s) : 1;
@@ -358,7 +385,7 @@ k_mp_thompson(Geom g, ThConst c, ThTables tb, Args A, int ld2, float dt, MpTiles
             idx_g = decade_index(rg, c.nig2, ntb_g);
             const double lamg = 1. / ilamg;
             const double lam_exp = lamg * powf((c.cgg[2] * c.ogg2 * c.ogg1), bm_g);
-            const double N0_exp = c.ogg1 * rg / c.am_g * pow(lam_exp, (double)c.cge[0]);
+            const double N0_exp = c.ogg1 * rg / c.am_g * dpow(lam_exp, (double)c.cge[0]);
             idx_g1 = decade_index_d(N0_exp, c.nig3, ntb_g1);
         }
 
@@ -389,14 +416,14 @@ k_mp_thompson(Geom g, ThConst c, ThTables tb, Args A, int ld2, float dt, MpTiles
             }
             if (rg >= 1.e-5f && mvd_c > D0c) {
                 const float xDg = (float)((bm_g + mu_g + 1.f) * ilamg);
-                const float vtg = (float)(rhof * c.o.av_g * c.cgg[5] * c.ogg3 * pow(ilamg, (double)c.o.bv_g));
+                const float vtg = (float)(rhof * c.o.av_g * c.cgg[5] * c.ogg3 * dpow(ilamg, (double)c.o.bv_g));
                 const float stoke_g = mvd_c * mvd_c * vtg * rho_w / (9.f * visco * xDg);
                 if (xDg > D0g) {
                     float Ef_gw = 0.f;
                     if (stoke_g >= 0.4f && stoke_g <= 10.f) Ef_gw = 0.55f * log10f(2.51f * stoke_g);
                     else if (stoke_g < 0.4f) Ef_gw = 0.0f;
                     else if (stoke_g > 10.f) Ef_gw = 0.77f;
-                    prg_gcw = rhof * c.t1_qg_qc * Ef_gw * rc * N0_g * pow(ilamg, (double)c.cge[8]);
+                    prg_gcw = rhof * c.t1_qg_qc * Ef_gw * rc * N0_g * dpow(ilamg, (double)c.cge[8]);
                 }
             }
         }
@@ -510,7 +537,7 @@ k_mp_thompson(Geom g, ThConst c, ThTables tb, Args A, int ld2, float dt, MpTiles
             }
             if (L_qg && ssati < -eps) {                                      // :1884-1893
                 prg_gde = C_cube * t1_subl * diffu * ssati * rvs * N0_g *
-                          (c.t1_qg_sd * pow(ilamg, (double)c.cge[9]) + c.t2_qg_sd * vsc2 * rhof2 * pow(ilamg, (double)c.cge[10]));
+                          (c.t1_qg_sd * dpow(ilamg, (double)c.cge[9]) + c.t2_qg_sd * vsc2 * rhof2 * dpow(ilamg, (double)c.cge[10]));
                 if (prg_gde < 0.) prg_gde = fmax(fmax((double)(-rg * odts), prg_gde), (double)rate_max);
                 else prg_gde = fmin(prg_gde, (double)rate_max);
             }
@@ -526,10 +553,10 @@ k_mp_thompson(Geom g, ThConst c, ThTables tb, Args A, int ld2, float dt, MpTiles
                 }
                 if (rr >= 1.e-6f && mvd_r > 4.f * xDi) {
                     const double lamr = 1. / ilamr;
-                    pri_rci = rhof * c.t1_qr_qi * c.o.Ef_ri * ri * N0_r * (pow((lamr + fv_r), (double)(-c.cre[8])));
-                    pnr_rci = rhof * c.t1_qr_qi * c.o.Ef_ri * ni * N0_r * (pow((lamr + fv_r), (double)(-c.cre[8])));
+                    pri_rci = rhof * c.t1_qr_qi * c.o.Ef_ri * ri * N0_r * (dpow((lamr + fv_r), (double)(-c.cre[8])));
+                    pnr_rci = rhof * c.t1_qr_qi * c.o.Ef_ri * ni * N0_r * (dpow((lamr + fv_r), (double)(-c.cre[8])));
                     pni_rci = pri_rci * oxmi;
-                    prr_rci = rhof * c.t2_qr_qi * c.o.Ef_ri * ni * N0_r * (pow((lamr + fv_r), (double)(-c.cre[7])));
+                    prr_rci = rhof * c.t2_qr_qi * c.o.Ef_ri * ni * N0_r * (dpow((lamr + fv_r), (double)(-c.cre[7])));
                     prr_rci = fmin((double)(rr * odts), prr_rci);
                     prg_rci = pri_rci + prr_rci;
                 }
@@ -565,13 +592,13 @@ k_mp_thompson(Geom g, ThConst c, ThTables tb, Args A, int ld2, float dt, MpTiles
             }
             if (L_qg) {
                 prr_gml = (tempc * tcond - lvap0 * diffu * delQvs) * N0_g *
-                          (c.t1_qg_me * pow(ilamg, (double)c.cge[9]) + c.t2_qg_me * rhof2 * vsc2 * pow(ilamg, (double)c.cge[10]));
+                          (c.t1_qg_me * dpow(ilamg, (double)c.cge[9]) + c.t2_qg_me * rhof2 * vsc2 * dpow(ilamg, (double)c.cge[10]));
                 prr_gml = fmin((double)(rg * odts), fmax(0., prr_gml));
-                pnr_gml = N0_g * c.cgg[1] * pow(ilamg, (double)c.cge[1]) / rg * prr_gml * powf(10.0f, (-1.5f * tempc));
+                pnr_gml = N0_g * c.cgg[1] * dpow(ilamg, (double)c.cge[1]) / rg * prr_gml * powf(10.0f, (-1.5f * tempc));
                 if (tempc > 7.5f || rg < 0.005E-3f) pnr_gml = 0.0;
                 if (ssati < 0.f) {
                     prg_gde = C_cube * t1_subl * diffu * ssati * rvs * N0_g *
-                              (c.t1_qg_sd * pow(ilamg, (double)c.cge[9]) + c.t2_qg_sd * vsc2 * rhof2 * pow(ilamg, (double)c.cge[10]));
+                              (c.t1_qg_sd * dpow(ilamg, (double)c.cge[9]) + c.t2_qg_sd * vsc2 * rhof2 * dpow(ilamg, (double)c.cge[10]));
                     prg_gde = fmax((double)(-rg * odts), prg_gde);
                 }
             }
@@ -646,11 +673,11 @@ k_mp_thompson(Geom g, ThConst c, ThTables tb, Args A, int ld2, float dt, MpTiles
                 const float xDi = (float)((bm_i + mu_i + 1.f) * ilami);
                 if (xDi < 20.E-6f) {
                     lami = c.cie[1] / 20.E-6f;
-                    xni = (float)fmin(250.E3, c.cig[0] * c.oig2 * xri / c.am_i * pow(lami, (double)bm_i));
+                    xni = (float)fmin(250.E3, c.cig[0] * c.oig2 * xri / c.am_i * dpow(lami, (double)bm_i));
                     niten = (xni - ni1d * rho) * odts * orho;
                 } else if (xDi > 300.E-6f) {
                     lami = c.cie[1] / 300.E-6f;
-                    xni = (float)(c.cig[0] * c.oig2 * xri / c.am_i * pow(lami, (double)bm_i));
+                    xni = (float)(c.cig[0] * c.oig2 * xri / c.am_i * dpow(lami, (double)bm_i));
                     niten = (xni - ni1d * rho) * odts * orho;
                 }
             } else {
@@ -784,7 +811,7 @@ k_mp_thompson(Geom g, ThConst c, ThTables tb, Args A, int ld2, float dt, MpTiles
                 prv_rev = rr / rho * odts;
             } else {
                 prv_rev = t1_evap * diffu * (-ssatw) * N0_r * rvs *
-                          (c.t1_qr_ev * pow(ilamr, (double)c.cre[9]) + c.t2_qr_ev * vsc2 * rhof2 * (pow((lamr + 0.5f * fv_r), (double)(-c.cre[10]))));
+                          (c.t1_qr_ev * dpow(ilamr, (double)c.cre[9]) + c.t2_qr_ev * vsc2 * rhof2 * (dpow((lamr + 0.5f * fv_r), (double)(-c.cre[10]))));
                 const float rate_max = fminf((rr / rho * odts), (qvs - qv) * odts);
                 prv_rev = fmin((double)rate_max, prv_rev / rho);
             }
@@ -810,14 +837,14 @@ k_mp_thompson(Geom g, ThConst c, ThTables tb, Args A, int ld2, float dt, MpTiles
         rhof = sqrtf(c.rho_not / rho);
         if (rr > R1) {
             const double lamr = powf((c.am_r * c.crg[2] * c.org2 * nr / rr), c.obmr);
-            vtrk = (float)(rhof * av_r * c.crg[5] * c.org3 * pow(lamr, (double)c.cre[2]) * (pow((lamr + fv_r), (double)(-c.cre[5]))));
-            vtnrk = (float)(rhof * av_r * c.crg[6] / c.crg[11] * pow(lamr, (double)c.cre[11]) * (pow((lamr + fv_r), (double)(-c.cre[6]))));
+            vtrk = (float)(rhof * av_r * c.crg[5] * c.org3 * dpow(lamr, (double)c.cre[2]) * (dpow((lamr + fv_r), (double)(-c.cre[5]))));
+            vtnrk = (float)(rhof * av_r * c.crg[6] / c.crg[11] * dpow(lamr, (double)c.cre[11]) * (dpow((lamr + fv_r), (double)(-c.cre[6]))));
         }
         if (ri > R1) {
             const double lami = powf((c.am_i * c.cig[1] * c.oig1 * ni / ri), c.obmi);
             const double ilami = 1. / lami;
-            vtik = (float)(rhof * c.o.av_i * c.cig[2] * c.oig2 * pow(ilami, (double)bv_i));
-            vtnik = (float)(rhof * c.o.av_i * c.cig[5] / c.cig[6] * pow(ilami, (double)bv_i));
+            vtik = (float)(rhof * c.o.av_i * c.cig[2] * c.oig2 * dpow(ilami, (double)bv_i));
+            vtnik = (float)(rhof * c.o.av_i * c.cig[5] / c.cig[6] * dpow(ilami, (double)bv_i));
         }
     }
     __syncthreads();
@@ -853,7 +880,7 @@ k_mp_thompson(Geom g, ThConst c, ThTables tb, Args A, int ld2, float dt, MpTiles
             vtsk = (temp > T_0) ? fmaxf(vts * vts_boost, vtrk) : vts * vts_boost;
         }
         if (rg > R1) {                                                       // :2631-2637
-            const float vtg = (float)(rhof * c.o.av_g * c.cgg[5] * c.ogg3 * pow(ilamg, (double)c.o.bv_g));
+            const float vtg = (float)(rhof * c.o.av_g * c.cgg[5] * c.ogg3 * dpow(ilamg, (double)c.o.bv_g));
             vtgk = (temp > T_0) ? fmaxf(vtg, vtrk) : vtg;
         }
     }
@@ -961,7 +988,7 @@ k_mp_thompson(Geom g, ThConst c, ThTables tb, Args A, int ld2, float dt, MpTiles
             const float xDi = (float)((bm_i + mu_i + 1.f) * ilami);
             if (xDi < 20.E-6f) lami = c.cie[1] / 20.E-6f;
             else if (xDi > 300.E-6f) lami = c.cie[1] / 300.E-6f;
-            ni1d = (float)fmin(c.cig[0] * c.oig2 * qi1d / c.am_i * pow(lami, (double)bm_i), 250.E3 / rho);
+            ni1d = (float)fmin(c.cig[0] * c.oig2 * qi1d / c.am_i * dpow(lami, (double)bm_i), 250.E3 / rho);
         }
         qr1d = qr1d + qrten * dt;
         nr1d = fmaxf(R2 / rho, nr1d + nrten * dt);
@@ -972,7 +999,7 @@ k_mp_thompson(Geom g, ThConst c, ThTables tb, Args A, int ld2, float dt, MpTiles
             if (mv > 2.5E-3f) mv = 2.5E-3f;
             else if (mv < D0r * 0.75f) mv = D0r * 0.75f;
             lamr = (3.0f + c.o.mu_r + 0.672f) / mv;
-            nr1d = (float)(c.crg[1] * c.org3 * qr1d * pow(lamr, (double)bm_r) / c.am_r);
+            nr1d = (float)(c.crg[1] * c.org3 * qr1d * dpow(lamr, (double)bm_r) / c.am_r);
         }
         qs1d = qs1d + qsten * dt;
         if (qs1d <= R1) qs1d = 0.0f;
@@ -1020,7 +1047,17 @@ int th_driver_launch(const Geom& g, const ThConst& c, const ThTables& tb, float*
     Args A{qv, qc, qr, qi, qs, qg, ni, nr, th, pii, p, dz, rainnc, snownc, snowncv, graupelnc, graupelncv, sr, rainncv};
     dim3 block(TX, nkt), grid(gx, gy, tiles.n);
     const size_t smem = (size_t)nk * TX * sizeof(double) + (size_t)7 * (nk + 1) * TX * sizeof(float) + (size_t)10 * TX * sizeof(int);
-    k_mp_thompson<<<grid, block, smem, st>>>(g, c, tb, A, ld2, dt, tiles, kts, kte, diag);
+    static const bool occ1 = std::getenv("ICAR_TH_OCC1") != nullptr;      // (tuning aid)
+    static bool carved = false;
+    if (!carved) {       // (tuning aid) shared-memory carve-out in percent; default: the driver's choice
+        if (const char* e = std::getenv("ICAR_TH_CARVEOUT")) {
+            cudaFuncSetAttribute(k_mp_thompson<320, 2>, cudaFuncAttributePreferredSharedMemoryCarveout, std::atoi(e));
+            cudaFuncSetAttribute(k_mp_thompson<TX * 64, 1>, cudaFuncAttributePreferredSharedMemoryCarveout, std::atoi(e));
+        }
+        carved = true;
+    }
+    if (TX * nkt <= 320 && !occ1) k_mp_thompson<320, 2><<<grid, block, smem, st>>>(g, c, tb, A, ld2, dt, tiles, kts, kte, diag);
+    else k_mp_thompson<TX * 64, 1><<<grid, block, smem, st>>>(g, c, tb, A, ld2, dt, tiles, kts, kte, diag);
     return 1;
 }
 

@@ -33,9 +33,11 @@ FusedPlan fused_plan(const Geom& g);
 // order 2 + FCT, rho == 1, fp32: coefficients, pass 1 for all scalars, fused corrector.
 // U,V,W,Wn from staged_wind_normalise / staged_wn_G.  nz <= 64.  Returns < 0 when the TMA
 // tensor maps cannot be built (driver without cuTensorMapEncodeTiled).
+// marks (optional): 4 events recorded on `st` before the coefficient kernel and after each of the three
+// kernels, for the per-kernel profile (icar_profile_read).
 int fused_advect_all(const Geom& g, const ScalarSet& s, const float* U, const float* V, const float* W,
                      const float* Wn, const float* jaco, const float* dz, const FusedCoef& co,
-                     cudaStream_t st);
+                     cudaStream_t st, cudaEvent_t* marks = nullptr);
 
 // pass 1 (adv_mpdata.f90:44-105) of every scalar in one launch; also copies the boundary ring to out
 int staged_upwind_all(const Geom& g, const ScalarSet& s, const float* U, const float* V, const float* W,

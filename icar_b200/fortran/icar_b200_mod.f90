@@ -26,6 +26,7 @@ module icar_b200_mod
     ! variable requests are unchanged: reuse the reference's own
     use adv_upwind,        only : upwind_var_request
     use module_mp_simple,  only : mp_simple_var_request
+    use microphysics,      only : reference_mp_var_request => mp_var_request   ! Thompson's request list (mp_driver.f90:118-145)
     implicit none
     private
     public :: adv_init, adv_var_request, advect
@@ -36,7 +37,7 @@ module icar_b200_mod
     integer(c_int), parameter :: VAR_U=0, VAR_V=1, VAR_W=2, VAR_PRESSURE=3, VAR_EXNER=4, VAR_DENSITY=5, &
         VAR_TH=6, VAR_QV=7, VAR_QC=8, VAR_QR=9, VAR_QS=10, VAR_JACOBIAN=11, VAR_JACOBIAN_U=12,       &
         VAR_JACOBIAN_V=13, VAR_JACOBIAN_W=14, VAR_ADVECTION_DZ=15, VAR_DZ_MASS=16, VAR_PRECIP=17,     &
-        VAR_SNOWFALL=18
+        VAR_SNOWFALL=18, VAR_QI=19, VAR_NI=20, VAR_NR=21, VAR_QG=22, VAR_GRAUPEL=23
 
     type, bind(c) :: icar_grid
         integer(c_int) :: ims, ime, kms, kme, jms, jme
@@ -52,7 +53,24 @@ module icar_b200_mod
         integer(c_int) :: exact_arithmetic
     end type
 
+    !> icar_mp_options == mp_options_type (opt_types.f90:31-45) up to the two logicals, which are C ints
+    type, bind(c) :: icar_mp_options
+        real(c_float)  :: Nt_c, TNO, am_s, rho_g
+        real(c_float)  :: av_s, bv_s, fv_s, av_i
+        real(c_float)  :: av_g, bv_g
+        real(c_float)  :: Ef_si, Ef_rs, Ef_rg, Ef_ri
+        real(c_float)  :: C_cubes, C_sqrd
+        real(c_float)  :: mu_r
+        real(c_float)  :: t_adjust
+        integer(c_int) :: Ef_rw_l, Ef_sw_l
+    end type
+
     interface
+        integer(c_int) function icar_thompson_init(ctx, opt) bind(c)
+            import :: c_int, c_ptr, icar_mp_options
+            type(c_ptr), value :: ctx
+            type(icar_mp_options), intent(in) :: opt
+        end function
         subroutine icar_default_options(opt) bind(c)
             import :: icar_options
             type(icar_options), intent(out) :: opt
@@ -122,6 +140,8 @@ module icar_b200_mod
 
     type(c_ptr), save :: ctx = c_null_ptr
     logical, save :: state_on_device = .false.
+    type(icar_mp_options), save :: mpo
+    logical, save :: have_mpo = .false., thompson = .false.
 
 contains
 
@@ -194,17 +214,38 @@ contains
         call up3(VAR_JACOBIAN_W,   domain%jacobian_w)
         call up3(VAR_ADVECTION_DZ, domain%advection_dz)
         call up3(VAR_DZ_MASS,      domain%dz_mass%data_3d)
+        thompson = (options%physics%microphysics == kMP_THOMPSON)
+        if (thompson .and. have_mpo) call check(icar_thompson_init(ctx, mpo), "icar_thompson_init")
     end subroutine
 
     !> mp_driver.f90:200-237 (only the schemes this library builds)
     subroutine mp_var_request(options)
         type(options_t), intent(inout) :: options
         if (options%physics%microphysics == kMP_SB04) call mp_simple_var_request(options)
+        if (options%physics%microphysics == kMP_THOMPSON) call reference_mp_var_request(options)
     end subroutine
 
-    !> mp_driver.f90:74-198: nothing to do for mp_simple; the context exists since adv_init
+    !> mp_driver.f90:74-198.  mp_simple needs nothing; for Thompson this is thompson_init(options%mp_options)
+    !! (mp_thompson.f90:342): the lookup tables are built on the GPU (no *_mpt.dat cache files).
+    !! icar_create already ran it with the namelist defaults; this call passes the user's mp_parameters.
+    !! init_physics calls mp_init BEFORE adv_init (init.f90:136,146), so when the context does not exist
+    !! yet the options are kept and applied at the end of adv_init.
     subroutine mp_init(options)
         type(options_t), intent(in) :: options
+        if (options%physics%microphysics /= kMP_THOMPSON) return
+        mpo%Nt_c = options%mp_options%Nt_c;   mpo%TNO = options%mp_options%TNO
+        mpo%am_s = options%mp_options%am_s;   mpo%rho_g = options%mp_options%rho_g
+        mpo%av_s = options%mp_options%av_s;   mpo%bv_s = options%mp_options%bv_s
+        mpo%fv_s = options%mp_options%fv_s;   mpo%av_i = options%mp_options%av_i
+        mpo%av_g = options%mp_options%av_g;   mpo%bv_g = options%mp_options%bv_g
+        mpo%Ef_si = options%mp_options%Ef_si; mpo%Ef_rs = options%mp_options%Ef_rs
+        mpo%Ef_rg = options%mp_options%Ef_rg; mpo%Ef_ri = options%mp_options%Ef_ri
+        mpo%C_cubes = options%mp_options%C_cubes; mpo%C_sqrd = options%mp_options%C_sqrd
+        mpo%mu_r = options%mp_options%mu_r;   mpo%t_adjust = options%mp_options%t_adjust
+        mpo%Ef_rw_l = merge(1, 0, options%mp_options%Ef_rw_l)
+        mpo%Ef_sw_l = merge(1, 0, options%mp_options%Ef_sw_l)
+        have_mpo = .true.
+        if (c_associated(ctx)) call check(icar_thompson_init(ctx, mpo), "icar_thompson_init")
     end subroutine
 
     !> uploads the fields the host side changes between steps (diagnostic_update, apply_forcing)
@@ -220,6 +261,10 @@ contains
             call up3(VAR_QC, domain%cloud_water_mass%data_3d)
             call up3(VAR_QR, domain%rain_mass%data_3d)
             call up3(VAR_QS, domain%snow_mass%data_3d)
+            if (thompson) then
+                call up3(VAR_QI, domain%cloud_ice_mass%data_3d);  call up3(VAR_NI, domain%cloud_ice_number%data_3d)
+                call up3(VAR_NR, domain%rain_number%data_3d);     call up3(VAR_QG, domain%graupel_mass%data_3d)
+            endif
             state_on_device = .true.
         endif
         call check(icar_set_model_time(ctx, domain%model_time%seconds()), "icar_set_model_time")
@@ -265,6 +310,11 @@ contains
         call down3(VAR_QS, domain%snow_mass%data_3d)
         call check(icar_download(ctx, VAR_PRECIP,   c_loc(domain%accumulated_precipitation%data_2dd)), "icar_download")
         call check(icar_download(ctx, VAR_SNOWFALL, c_loc(domain%accumulated_snowfall%data_2dd)), "icar_download")
+        if (thompson) then
+            call down3(VAR_QI, domain%cloud_ice_mass%data_3d);  call down3(VAR_NI, domain%cloud_ice_number%data_3d)
+            call down3(VAR_NR, domain%rain_number%data_3d);     call down3(VAR_QG, domain%graupel_mass%data_3d)
+            call check(icar_download(ctx, VAR_GRAUPEL, c_loc(domain%graupel%data_2dd)), "icar_download")
+        endif
     end subroutine
 
     subroutine b200_finalize()

@@ -191,6 +191,15 @@ long long icar_kernel_launches(const icar_ctx* ctx);
 int icar_timer_start(icar_ctx* ctx);
 int icar_timer_stop(icar_ctx* ctx, float* elapsed_ms);
 
+/* Per-kernel device timing, for the roofline of the dominant kernel.  While enabled, every kernel family
+ * the context launches is bracketed by CUDA events on the stream it is launched on (timer_t brackets
+ * only whole phases, timer_obj.f90:13-60; the reference has no per-kernel timers).  icar_profile_read
+ * waits for the queued work, returns per family the summed milliseconds and the number of launches
+ * since the last read, and resets the sums.  names = max_entries x char[32]. */
+int icar_profile_enable(icar_ctx* ctx, int on);
+int icar_profile_read(icar_ctx* ctx, int max_entries, char (*names)[32], float* ms, long long* launches,
+                      int* n_out);
+
 /* ------------------------------------------------- Thompson microphysics (microphysics = 1) */
 
 void icar_default_mp_options(icar_mp_options* opt);
@@ -293,6 +302,9 @@ typedef struct icar_host_domain {
     /* read and written every step */
     float *potential_temperature, *water_vapor, *cloud_water, *rain_in_air, *snow_in_air;
     double *accumulated_precipitation, *accumulated_snowfall;
+    /* Thompson only (NULL otherwise): read and written every step */
+    float *cloud_ice, *ice_number, *rain_number, *graupel_in_air;
+    double *accumulated_graupel;
 } icar_host_domain;
 
 /* One physics step on HOST arrays: uploads the per-step inputs, runs icar_physics_step, and

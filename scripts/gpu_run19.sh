@@ -1,0 +1,5 @@
+python -c "import __graft_entry__ as g; g.build()" 2>&1 | tail -1
+timeout 900 python -m pytest tests/test_gpu_thompson.py -m gpu -q 2>&1 | tail -5
+P='import sys,json; d=json.loads(sys.stdin.read()); print({k:d[k] for k in ("value","ms_per_step","gpu_launches")}, d["e2e"]["ms_per_step"], d["roofline"]["frac"])'
+timeout 300 python bench.py --mp thompson --steps 20 --warmup 5 --no-cpu-baseline 2>&1 | tail -1 | python -c "$P"
+ICAR_TH_OCC1=1 timeout 300 python bench.py --mp thompson --steps 20 --warmup 5 --no-cpu-baseline 2>&1 | tail -1 | python -c "$P"
