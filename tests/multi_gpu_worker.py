@@ -19,15 +19,18 @@ def main():
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     nx, nz, ny, steps, halo = (int(a) for a in sys.argv[1:6])
     axis = sys.argv[6] if len(sys.argv) > 6 else "x"
+    mp = int(sys.argv[7]) if len(sys.argv) > 7 else 2      # 2 = mp_simple (5 scalars), 1 = Thompson (9 scalars)
     torch.cuda.set_device(local)
     dist.init_process_group("gloo")          # plumbing only: id broadcast + barrier
     st = ideal.make_ideal_case(nx=nx, nz=nz, ny=ny, perturb=True)
     st["qv"] *= np.float32(3.0)
+    if mp == 1:
+        ideal.add_thompson_fields(st)
     dt = float(st["dt"])
-    one = icar_b200.Domain(icar_b200.Grid.single_image(nx, nz, ny), icar_b200.Options(dx=st["dx"]), device=local)
+    one = icar_b200.Domain(icar_b200.Grid.single_image(nx, nz, ny), icar_b200.Options(dx=st["dx"], microphysics=mp), device=local)
     one.upload_state(st)
     grid = (icar_b200.Grid.xslab if axis == "x" else icar_b200.Grid.yslab)(nx, nz, ny, world, rank + 1, halo)
-    dom = icar_b200.Domain(grid, icar_b200.Options(dx=st["dx"]), device=local)
+    dom = icar_b200.Domain(grid, icar_b200.Options(dx=st["dx"], microphysics=mp), device=local)
     dom.upload_state(ideal.slab_of(st, grid))
     ids = [icar_b200.comm_unique_id() if rank == 0 else None]
     dist.broadcast_object_list(ids, src=0)
@@ -49,11 +52,12 @@ def main():
         own = lambda a: a[lo:hi]
         ref = lambda a: a[g0:g0 + (hi - lo)]
     bad = []
-    for k in ("th", "qv", "qc", "qr", "qs", "precipitation"):
+    fields = ("th", "qv", "qc", "qr", "qs", "precipitation") + (("qi", "qg", "ni", "nr", "snowfall", "graupel") if mp == 1 else ())
+    for k in fields:
         a, b = own(dom.download(k)), ref(one.download(k))
         if not np.array_equal(a, b):
             bad.append((k, float(np.abs(a - b).max())))
-    print(f"rank {rank}: axis {axis}, owned {g0}..{g0 + hi - lo - 1}, mismatching fields: {bad}", flush=True)
+    print(f"rank {rank}: mp {mp}, axis {axis}, owned {g0}..{g0 + hi - lo - 1}, mismatching fields: {bad}", flush=True)
     dist.barrier()
     dom.close(); one.close()
     dist.destroy_process_group()

@@ -16,13 +16,13 @@ def _ngpu():
     return torch.cuda.device_count()
 
 
-@pytest.mark.parametrize("world,axis", [(2, "x"), (2, "y"), (4, "y")])
-def test_nccl_slabs_equal_single_image(world, axis):
+@pytest.mark.parametrize("world,axis,mp", [(2, "x", 2), (2, "y", 2), (4, "y", 2), (2, "x", 1), (2, "y", 1)])
+def test_nccl_slabs_equal_single_image(world, axis, mp):
     if _ngpu() < world:
         pytest.skip(f"needs {world} GPUs")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
            "--master-addr", "127.0.0.1", "--master-port", "29611",
-           os.path.join(ROOT, "tests", "multi_gpu_worker.py"), "96", "12", "96", "4", "3", axis]
+           os.path.join(ROOT, "tests", "multi_gpu_worker.py"), "96", "12", "96", "4", "3", axis, str(mp)]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     sys.stdout.write(r.stdout[-2000:])
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
