@@ -39,7 +39,10 @@ constexpr float freezing_threshold = 273.15f;
 constexpr float snow_fall_rate = 1.5f;
 constexpr float rain_fall_rate = 10.0f;
 constexpr float cloud_init = 0.0001f;        // snow_cloud_init == rain_cloud_init
-constexpr int TX = 32;                       // columns per CTA (one warp = one level row)
+#ifndef ICAR_MP_TX
+#define ICAR_MP_TX 32
+#endif
+constexpr int TX = ICAR_MP_TX;               // columns per CTA (one warp = 32/TX level rows)
 
 // 2^(i/32) table of glibc's expf (sysdeps/ieee754/flt-32/e_exp2f_data.c, EXP2F_TABLE_BITS=5):
 // tab[i] = asuint64(2^(i/32)) - (i << 47).  Verified against powl() and, end to end, against

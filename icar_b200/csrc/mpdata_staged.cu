@@ -10,6 +10,9 @@
 // Device layout of the staggered winds (differs from the Fortran module arrays, which are
 // compact): U[i] is the x-face between cells i-1 and i (i>=1), V[j] the y-face between rows
 // j-1 and j (j>=1), W[k] the z-face above cell k; all share the cell pitch `ld`.
+#include <algorithm>
+#include <cstdlib>
+
 #include "common.cuh"
 #include "mpdata.cuh"
 
@@ -297,7 +300,20 @@ __global__ void k_corrector(Geom g, const R* __restrict__ l, const R* __restrict
 // ---------------------------------------------------------------------------------------------
 // Pass 1 for all scalars (same arithmetic, bit for bit, as k_upwind above; this file is built with -fmad=false).
 // ---------------------------------------------------------------------------------------------
-template <int N>
+// Both divisors of a cell (J and dz*J) are shared by all N scalars, so each quotient is formed from ONE
+// correctly rounded reciprocal per divisor, y = RN(1/b), as  q0 = RN(a*y), r = a - b*q0 (exact, FMA),
+// q = RN(q0 + r*y)  -- Markstein's correction: q is the IEEE quotient RN(a/b), bit for bit (outside the
+// subnormal range), for 3 instructions instead of the ~10 of a full division with its slow-path check.
+// MARKSTEIN = false keeps the plain `/` (test hook: tests/test_gpu_parity.py compares the two bitwise).
+template <bool MARKSTEIN>
+__device__ __forceinline__ float div_shared(float a, float b, float y) {
+    if (!MARKSTEIN) return a / b;
+    const float q0 = a * y;
+    const float r = fmaf(-b, q0, a);
+    return fmaf(r, y, q0);
+}
+
+template <int N, bool MARKSTEIN>
 __global__ void __launch_bounds__(128)
 k_upwind_all(Geom g, ScalarSet s, const float* __restrict__ U, const float* __restrict__ V,
              const float* __restrict__ W, const float* __restrict__ dz, const float* __restrict__ jaco) {
@@ -327,15 +343,18 @@ k_upwind_all(Geom g, ScalarSet s, const float* __restrict__ U, const float* __re
     const float wzp = W[c], wzm = bottom ? 0.f : W[c - ld];
     const float jc = jaco[c];
     const float den = dz[c] * jc;
+    const float rj = MARKSTEIN ? __frcp_rn(jc) : 0.f, rden = MARKSTEIN ? __frcp_rn(den) : 0.f;
 #pragma unroll
     for (int n = 0; n < N; ++n) {
         const float fxm = donor(uxm, qxm[n], qc[n]), fxp = donor(uxp, qc[n], qxp[n]);
         const float fym = donor(vym, qym[n], qc[n]), fyp = donor(vyp, qc[n], qyp[n]);
-        float val = qc[n] - ((fxp - fxm) + (fyp - fym)) / jc;
+        float val = qc[n] - div_shared<MARKSTEIN>((fxp - fxm) + (fyp - fym), jc, rj);
         if (!flat) {
-            if (bottom)   val = val - donor(wzp, qc[n], qzp[n]) / den;
-            else if (top) val = val - (qc[n] * wzp - donor(wzm, qzm[n], qc[n])) / den;
-            else          val = val - (donor(wzp, qc[n], qzp[n]) - donor(wzm, qzm[n], qc[n])) / den;
+            float vert;
+            if (bottom)   vert = donor(wzp, qc[n], qzp[n]);
+            else if (top) vert = qc[n] * wzp - donor(wzm, qzm[n], qc[n]);
+            else          vert = donor(wzp, qc[n], qzp[n]) - donor(wzm, qzm[n], qc[n]);
+            val = val - div_shared<MARKSTEIN>(vert, den, rden);
         }
         s.q2[n][c] = val;
     }
@@ -354,19 +373,24 @@ static inline dim3 cell_grid(const Geom& g) {
 
 int staged_upwind_all(const Geom& g, const ScalarSet& s, const float* U, const float* V, const float* W,
                       const float* dz, const float* jaco, cudaStream_t st) {
+    const bool ieee = std::getenv("ICAR_UPWIND_IEEE_DIV") != nullptr;     // test hook, see div_shared
     dim3 grid = cell_grid(g);
     int done = 0, launches = 0;
     while (done < s.n) {                 // batches of up to 5 scalars share the wind / metric loads
         ScalarSet b;
         b.n = (s.n - done >= 5) ? 5 : (s.n - done);
         for (int n = 0; n < b.n; ++n) { b.q[n] = s.q[done + n]; b.q2[n] = s.q2[done + n]; b.out[n] = s.out[done + n]; }
+#define UPWIND_ALL(NN)                                                                                     \
+    if (ieee) k_upwind_all<NN, false><<<grid, cell_block(), 0, st>>>(g, b, U, V, W, dz, jaco);             \
+    else k_upwind_all<NN, true><<<grid, cell_block(), 0, st>>>(g, b, U, V, W, dz, jaco)
         switch (b.n) {
-            case 5: k_upwind_all<5><<<grid, cell_block(), 0, st>>>(g, b, U, V, W, dz, jaco); break;
-            case 4: k_upwind_all<4><<<grid, cell_block(), 0, st>>>(g, b, U, V, W, dz, jaco); break;
-            case 3: k_upwind_all<3><<<grid, cell_block(), 0, st>>>(g, b, U, V, W, dz, jaco); break;
-            case 2: k_upwind_all<2><<<grid, cell_block(), 0, st>>>(g, b, U, V, W, dz, jaco); break;
-            default: k_upwind_all<1><<<grid, cell_block(), 0, st>>>(g, b, U, V, W, dz, jaco); break;
+            case 5: UPWIND_ALL(5); break;
+            case 4: UPWIND_ALL(4); break;
+            case 3: UPWIND_ALL(3); break;
+            case 2: UPWIND_ALL(2); break;
+            default: UPWIND_ALL(1); break;
         }
+#undef UPWIND_ALL
         done += b.n;
         ++launches;
     }
