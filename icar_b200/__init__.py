@@ -149,7 +149,7 @@ SYMBOLS = (
     "icar_mpdata_set_winds_f64", "icar_mpdata_advect3d_f64", "icar_mp_simple_driver",
     "icar_physics_step_host", "icar_host_register", "icar_host_unregister",
     "icar_default_mp_options", "icar_thompson_init", "icar_thompson_table", "icar_mp_gt_driver",
-    "icar_profile_enable", "icar_profile_read")
+    "icar_profile_enable", "icar_profile_read", "icar_diagnostic_update", "icar_compute_dt", "icar_enforce_limits")
 
 
 def lib() -> C.CDLL:
@@ -270,6 +270,23 @@ class Domain:
 
     def physics_step(self, dt):
         self._check(lib().icar_physics_step(self._h, C.c_float(dt)))
+
+    # -- the rest of step()'s loop body
+    def diagnostic_update(self):
+        """exner and density from pressure and potential temperature (time_step.f90:85-101)."""
+        self._check(lib().icar_diagnostic_update(self._h))
+
+    def compute_dt(self, dz_levels, cfl_reduction_factor=0.9, cfl_strictness=3):
+        """update_dt (time_step.f90:375-423): CFL time step, min over images, capped at 120 s."""
+        dz = _f32(dz_levels, (self.grid.nz,), "dz_levels")
+        out = C.c_double()
+        self._check(lib().icar_compute_dt(self._h, _ptr(dz), C.c_float(cfl_reduction_factor), int(cfl_strictness),
+                                          C.byref(out)))
+        return out.value
+
+    def enforce_limits(self):
+        """domain%enforce_limits (domain_obj.f90:2228-2243)."""
+        self._check(lib().icar_enforce_limits(self._h))
 
     def synchronize(self):
         self._check(lib().icar_synchronize(self._h))

@@ -25,6 +25,7 @@
 #include "mp_simple.cuh"
 #include "mp_thompson.cuh"
 #include "mpdata.cuh"
+#include "step_loop.cuh"
 
 using namespace icar;
 
@@ -55,6 +56,7 @@ struct Nccl {
     ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
     ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*GroupStart)() = nullptr;
     ncclResult_t (*GroupEnd)() = nullptr;
     const char* (*GetErrorString)(ncclResult_t) = nullptr;
@@ -74,6 +76,7 @@ struct Nccl {
         BIND(CommDestroy, "ncclCommDestroy")
         BIND(Send, "ncclSend")
         BIND(Recv, "ncclRecv")
+        BIND(AllReduce, "ncclAllReduce")
         BIND(GroupStart, "ncclGroupStart")
         BIND(GroupEnd, "ncclGroupEnd")
         BIND(GetErrorString, "ncclGetErrorString")
@@ -141,6 +144,10 @@ struct icar_ctx {
     double* th_tab[TH_NTABLES] = {};
     double *th_bins = nullptr, *th_aux = nullptr;
     unsigned long long* th_diag = nullptr;     // [0] columns that took the no_micro exit
+    // compute_dt: 4 maxima (uint images of floats) | 1 double for the co_min | nz dz_levels
+    unsigned* cfl_max = nullptr;
+    double* cfl_dt = nullptr;
+    float* cfl_dz = nullptr;
 };
 
 namespace {
@@ -519,6 +526,9 @@ extern "C" int icar_destroy(icar_ctx* ctx) {
     if (ctx->th_bins) cudaFree(ctx->th_bins);
     if (ctx->th_aux) cudaFree(ctx->th_aux);
     if (ctx->th_diag) cudaFree(ctx->th_diag);
+    if (ctx->cfl_max) cudaFree(ctx->cfl_max);
+    if (ctx->cfl_dt) cudaFree(ctx->cfl_dt);
+    if (ctx->cfl_dz) cudaFree(ctx->cfl_dz);
     {
         float* cf[] = {ctx->coef.ax, ctx->coef.bx, ctx->coef.cx, ctx->coef.ay, ctx->coef.by, ctx->coef.cy,
                        ctx->coef.az, ctx->coef.bz, ctx->coef.cz, ctx->coef.rj, ctx->coef.rjz};
@@ -1340,5 +1350,93 @@ extern "C" int icar_profile_read(icar_ctx* ctx, int max_entries, char (*names)[3
     }
     *n_out = n;
     for (int k = 0; k < 16; ++k) { ctx->prof_ms[k] = 0.0; ctx->prof_n[k] = 0; }
+    return ICAR_OK;
+}
+
+// ============================================================================ rest of the step loop
+
+extern "C" int icar_diagnostic_update(icar_ctx* ctx) {
+    if (!ctx) return ICAR_ERR_INVALID;
+    CU(cudaSetDevice(ctx->device));
+    int rc = need_uploaded(ctx, {ICAR_VAR_PRESSURE, ICAR_VAR_POTENTIAL_TEMPERATURE}, "icar_diagnostic_update");
+    if (rc) return rc;
+    { int jr = join_aux(ctx); if (jr) return jr; }
+    ctx->launches += diagnostic_update_launch(ctx->g, (const float*)ctx->vars[ICAR_VAR_PRESSURE],
+                                              (const float*)ctx->vars[ICAR_VAR_POTENTIAL_TEMPERATURE],
+                                              (float*)ctx->vars[ICAR_VAR_EXNER], (float*)ctx->vars[ICAR_VAR_DENSITY],
+                                              ctx->stream);
+    CU(cudaGetLastError());
+    ctx->uploaded[ICAR_VAR_EXNER] = true;
+    ctx->uploaded[ICAR_VAR_DENSITY] = true;
+    return ICAR_OK;
+}
+
+extern "C" int icar_compute_dt(icar_ctx* ctx, const float* dz_levels, float cfl, int strictness, double* dt_seconds) {
+    if (!ctx || !dz_levels || !dt_seconds) return fail(ctx, ICAR_ERR_INVALID, "icar_compute_dt: null argument");
+    if (strictness < 1 || strictness > 5) return fail(ctx, ICAR_ERR_INVALID, "icar_compute_dt: cfl_strictness must be 1..5");
+    CU(cudaSetDevice(ctx->device));
+    int rc = need_uploaded(ctx, {ICAR_VAR_U, ICAR_VAR_V, ICAR_VAR_W}, "icar_compute_dt");
+    if (rc) return rc;
+    const Geom& g = ctx->g;
+    if (!ctx->cfl_max) {
+        CU(cudaMalloc((void**)&ctx->cfl_max, 4 * sizeof(unsigned)));
+        CU(cudaMalloc((void**)&ctx->cfl_dt, sizeof(double)));
+        CU(cudaMalloc((void**)&ctx->cfl_dz, (size_t)g.nz * sizeof(float)));
+    }
+    CU(cudaMemcpyAsync(ctx->cfl_dz, dz_levels, (size_t)g.nz * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemsetAsync(ctx->cfl_max, 0, 4 * sizeof(unsigned), ctx->stream));
+    ctx->launches += cfl_maxima_launch(g, (const float*)ctx->vars[ICAR_VAR_U], (const float*)ctx->vars[ICAR_VAR_V],
+                                       (const float*)ctx->vars[ICAR_VAR_W], ctx->cfl_dz, ctx->opt.dx, ctx->cfl_max,
+                                       ctx->stream);
+    CU(cudaGetLastError());
+    unsigned bits[4];
+    CU(cudaMemcpyAsync(bits, ctx->cfl_max, sizeof(bits), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    float m[4];
+    std::memcpy(m, bits, sizeof(m));
+    // time_step.f90:234-318 (REAL arithmetic)
+    const float sqrt3 = std::sqrt(3.0f) * 1.001f, three_d_cfl = 0.577350269f;
+    float maxwind3d = 0.f, maxwind1d = 0.f;
+    if (strictness == 1) {
+        maxwind1d = std::max(std::max(m[1], m[2]), m[3]);
+        maxwind3d = maxwind1d * sqrt3;
+    } else if (strictness == 5) {
+        maxwind3d = m[1] + m[2] + m[3];
+    } else {
+        maxwind3d = m[0];
+        if (strictness == 2) {
+            maxwind3d = maxwind3d * three_d_cfl;
+            maxwind1d = std::max(std::max(m[1], m[2]), m[3]);
+            maxwind3d = std::max(maxwind1d, maxwind3d);
+        } else if (strictness == 4) {
+            maxwind3d = maxwind3d * sqrt3;
+        }
+    }
+    const float dt = cfl / maxwind3d;
+    if (dt < 1e-1f) {
+        char msg[200];
+        std::snprintf(msg, sizeof msg, "ERROR time step too small: dt = %g, Umax = %g, Vmax = %g, Wmax = %g", dt, m[1], m[2], m[3]);
+        return fail(ctx, ICAR_ERR_PHYSICS, msg);
+    }
+    double seconds = (double)dt;
+    if (ctx->nimages > 1) {                                     // call co_min(seconds), :413
+        if (!ctx->comm) return fail(ctx, ICAR_ERR_COMM, "icar_compute_dt: icar_comm_init was not called");
+        CU(cudaMemcpyAsync(ctx->cfl_dt, &seconds, sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        NC(g_nccl.AllReduce(ctx->cfl_dt, ctx->cfl_dt, 1, ncclDouble, ncclMin, ctx->comm, ctx->stream));
+        CU(cudaMemcpyAsync(&seconds, ctx->cfl_dt, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+    }
+    *dt_seconds = std::min(seconds, 120.0);                     // :421
+    return ICAR_OK;
+}
+
+extern "C" int icar_enforce_limits(icar_ctx* ctx) {
+    if (!ctx) return ICAR_ERR_INVALID;
+    CU(cudaSetDevice(ctx->device));
+    { int jr = join_aux(ctx); if (jr) return jr; }
+    float* fields[ICAR_MAX_EXCHANGED];
+    for (int s = 0; s < ctx->nexch; ++s) fields[s] = (float*)ctx->vars[ctx->exch[s]];
+    ctx->launches += enforce_limits_launch(ctx->g, fields, ctx->nexch, ctx->stream);
+    CU(cudaGetLastError());
     return ICAR_OK;
 }

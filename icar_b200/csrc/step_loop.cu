@@ -1,0 +1,87 @@
+// See step_loop.cuh.  All three kernels are plain HBM streams (one pass over the fields they name).
+#include "step_loop.cuh"
+
+namespace icar {
+
+namespace {
+
+constexpr float Rd = 287.058f, cp = 1012.0f;       // src/constants/icar_constants.f90:391-393
+
+__global__ void __launch_bounds__(128)
+k_diagnostic_update(Geom g, const float* __restrict__ p, const float* __restrict__ th, float* __restrict__ exner,
+                    float* __restrict__ rho) {
+    const int i = blockIdx.x * 128 + threadIdx.x, k = blockIdx.y, j = blockIdx.z;
+    if (i >= g.nx) return;
+    const size_t c = g.at(i, k, j);
+    const float pr = p[c];
+    const float ex = powf(pr / 100000.f, Rd / cp);            // exner_function, atm_utilities.f90:687-688
+    const float t = th[c] * ex;                               // time_step.f90:96
+    exner[c] = ex;
+    rho[c] = pr / (Rd * t);                                   // time_step.f90:101
+}
+
+__global__ void __launch_bounds__(128)
+k_cfl_maxima(Geom g, const float* __restrict__ u, const float* __restrict__ v, const float* __restrict__ w,
+             const float* __restrict__ dzl, float dx, unsigned* __restrict__ out) {
+    const int i = blockIdx.x * 128 + threadIdx.x, k = blockIdx.y, j = blockIdx.z;
+    float m3 = 0.f, mu = 0.f, mv = 0.f, mw = 0.f;
+    if (i < g.nx) {
+        const size_t c = g.at(i, k, j), cu = g.atu(i, k, j);
+        const float u0 = fabsf(u[cu]), u1 = fabsf(u[cu + 1]);
+        const float v0 = fabsf(v[c]), v1 = fabsf(v[c + g.ps()]);
+        const float w0 = fabsf(w[c]), wl = (k == 0) ? w0 : fabsf(w[c - g.ld]);       // zoffset, :267-271
+        m3 = fmaxf(u0, u1) / dx + fmaxf(v0, v1) / dx + fmaxf(w0, wl) / dzl[k];      // :282-284
+        mu = fmaxf(u0, u1); mv = fmaxf(v0, v1); mw = w0;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        m3 = fmaxf(m3, __shfl_xor_sync(0xffffffffu, m3, o));
+        mu = fmaxf(mu, __shfl_xor_sync(0xffffffffu, mu, o));
+        mv = fmaxf(mv, __shfl_xor_sync(0xffffffffu, mv, o));
+        mw = fmaxf(mw, __shfl_xor_sync(0xffffffffu, mw, o));
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicMax(out + 0, __float_as_uint(m3));
+        atomicMax(out + 1, __float_as_uint(mu));
+        atomicMax(out + 2, __float_as_uint(mv));
+        atomicMax(out + 3, __float_as_uint(mw));
+    }
+}
+
+struct FieldPtrs { float* p[12]; };
+
+__global__ void __launch_bounds__(128)
+k_enforce_limits(Geom g, FieldPtrs f, int nf) {
+    const int i = blockIdx.x * 128 + threadIdx.x, k = blockIdx.y, j = blockIdx.z;
+    if (i >= g.nx) return;
+    const size_t c = g.at(i, k, j);
+    for (int n = 0; n < nf; ++n) {
+        const float v = f.p[n][c];
+        if (v < 0.f) f.p[n][c] = 0.f;
+    }
+}
+
+dim3 row_grid(const Geom& g) { return dim3((g.nx + 127) / 128, g.nz, g.ny); }
+
+}  // namespace
+
+int diagnostic_update_launch(const Geom& g, const float* pressure, const float* th, float* exner, float* density,
+                             cudaStream_t st) {
+    k_diagnostic_update<<<row_grid(g), 128, 0, st>>>(g, pressure, th, exner, density);
+    return 1;
+}
+
+int cfl_maxima_launch(const Geom& g, const float* u, const float* v, const float* w, const float* dz_levels,
+                      float dx, unsigned* out4, cudaStream_t st) {
+    k_cfl_maxima<<<row_grid(g), 128, 0, st>>>(g, u, v, w, dz_levels, dx, out4);
+    return 1;
+}
+
+int enforce_limits_launch(const Geom& g, float* const* fields, int nfields, cudaStream_t st) {
+    FieldPtrs f{};
+    for (int n = 0; n < nfields && n < 12; ++n) f.p[n] = fields[n];
+    k_enforce_limits<<<row_grid(g), 128, 0, st>>>(g, f, nfields);
+    return 1;
+}
+
+}  // namespace icar

@@ -1,0 +1,24 @@
+// The cheap parts of step()'s loop body around mp / advect (src/main/time_step.f90:464-547), so that a
+// device-resident step loop needs no host round trip: diagnostic_update's exner / density (:85-101),
+// compute_dt's CFL maxima (:217-330) and domain%enforce_limits (domain_obj.f90:2228-2243).
+#pragma once
+#include "common.cuh"
+
+namespace icar {
+
+// exner = (pressure / 100000) ** (Rd/cp); density = pressure / (Rd * potential_temperature * exner)
+// (time_step.f90:85,96,101; atm_utilities.f90:682-691; Rd = 287.058, cp = 1012, icar_constants.f90:391-393)
+int diagnostic_update_launch(const Geom& g, const float* pressure, const float* th, float* exner, float* density,
+                             cudaStream_t st);
+
+// compute_dt's four maxima over this image's tile (time_step.f90:234-289, use_density = .false.):
+//   out[0] = max over cells of  max|u|/dx + max|v|/dx + max|w|/dz(k)   (the strictness 2/3/4 loop)
+//   out[1..3] = maxval(abs(u)), maxval(abs(v)), maxval(abs(w))
+// stored as the bit patterns of non-negative floats (integer order == float order); out must be zeroed.
+int cfl_maxima_launch(const Geom& g, const float* u, const float* v, const float* w, const float* dz_levels,
+                      float dx, unsigned* out4, cudaStream_t st);
+
+// where (q < 0) q = 0 for every listed field (domain_obj.f90:2228-2243)
+int enforce_limits_launch(const Geom& g, float* const* fields, int nfields, cudaStream_t st);
+
+}  // namespace icar

@@ -173,6 +173,25 @@ int icar_halo_exchange(icar_ctx* ctx);
  * mp(halo) -> halo_send -> mp(subset) -> halo_retrieve -> advect ; model_time += dt. */
 int icar_physics_step(icar_ctx* ctx, float dt);
 
+/* ---- the rest of step()'s loop body, so that the loop can run without host round trips ("next" rows) */
+
+/* The part of diagnostic_update (src/main/time_step.f90:49-198) that mp / advect read:
+ * exner = exner_function(pressure) (:85, atm_utilities.f90:682-691) and
+ * density = pressure / (Rd * potential_temperature * exner) (:96,:101), on the device copies. */
+int icar_diagnostic_update(icar_ctx* ctx);
+
+/* update_dt / compute_dt (src/main/time_step.f90:217-330, 375-423) on the device-resident winds:
+ * the CFL maxima for cfl_strictness 1..5 (use_density = .false.), dt = cfl_reduction_factor / maxwind,
+ * `co_min` over the images of the communicator (:413; ncclAllReduce(min) of one double) and the
+ * 120 s cap (:421).  dz_levels = options%parameters%dz_levels(kms:kme).  Returns ICAR_ERR_PHYSICS where
+ * the reference stops with "ERROR time step too small" (dt < 0.1 s, :322-328). */
+int icar_compute_dt(icar_ctx* ctx, const float* dz_levels, float cfl_reduction_factor, int cfl_strictness,
+                    double* dt_seconds);
+
+/* domain%enforce_limits (src/objects/domain_obj.f90:2228-2243): where (q < 0) q = 0 on every scalar the
+ * microphysics scheme allocates. */
+int icar_enforce_limits(icar_ctx* ctx);
+
 /* Blocks until all work queued by the calls above has finished on the device. */
 int icar_synchronize(icar_ctx* ctx);
 

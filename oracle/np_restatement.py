@@ -202,3 +202,54 @@ def advect3d(q, rho, jaco, dz, U_m, V_m, W_m, order=2, fct=True):
         elif iord == 1:
             q = q2.copy()
     return q
+
+
+# ------------------------------------------------------------------ the rest of step()'s loop body
+RD = np.float32(287.058)     # src/constants/icar_constants.f90:391
+CP = np.float32(1012.0)      # src/constants/icar_constants.f90:393
+
+
+def diagnostic_update_np(pressure, th):
+    """exner and density as diagnostic_update computes them (src/main/time_step.f90:85,96,101;
+    exner_function, src/utilities/atm_utilities.f90:682-691).  float32 throughout."""
+    exner = (pressure / np.float32(100000)) ** (RD / CP)
+    temperature = th * exner
+    density = pressure / (RD * temperature)
+    return exner.astype(np.float32), density.astype(np.float32)
+
+
+def compute_dt_np(dx, u, v, w, dz_levels, cfl, cfl_strictness):
+    """compute_dt (src/main/time_step.f90:217-330) with use_density = .false., then update_dt's 120 s cap
+    (:421).  u (ny,nz,nx+1), v (ny+1,nz,nx), w (ny,nz,nx); REAL arithmetic.  Raises where the reference
+    stops ("ERROR time step too small")."""
+    f = np.float32
+    au, av, aw = np.abs(u), np.abs(v), np.abs(w)
+    sqrt3 = f(np.sqrt(f(3.0))) * f(1.001)
+    three_d_cfl = f(0.577350269)
+    if cfl_strictness == 1:
+        maxwind1d = max(au.max(), av.max(), aw.max())
+        maxwind3d = f(maxwind1d) * sqrt3
+    elif cfl_strictness == 5:
+        maxwind3d = f(au.max()) + f(av.max()) + f(aw.max())
+    else:
+        wl = aw.copy()
+        wl[:, 1:, :] = np.maximum(aw[:, 1:, :], aw[:, :-1, :])          # zoffset = -1 for k > 1
+        cur = (np.maximum(au[:, :, :-1], au[:, :, 1:]) / f(dx)
+               + np.maximum(av[:-1], av[1:]) / f(dx)
+               + wl / np.asarray(dz_levels, f).reshape(1, -1, 1))
+        maxwind3d = f(cur.max())
+        if cfl_strictness == 2:
+            maxwind3d = maxwind3d * three_d_cfl
+            maxwind3d = max(f(max(au.max(), av.max(), aw.max())), maxwind3d)
+        elif cfl_strictness == 4:
+            maxwind3d = maxwind3d * sqrt3
+    dt = f(cfl) / f(maxwind3d)
+    if dt < f(1e-1):
+        raise FloatingPointError("ERROR time step too small")
+    return min(float(dt), 120.0)
+
+
+def enforce_limits_np(fields):
+    """domain%enforce_limits (src/objects/domain_obj.f90:2228-2243), in place."""
+    for a in fields:
+        a[a < 0] = 0

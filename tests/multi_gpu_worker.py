@@ -35,6 +35,11 @@ def main():
     ids = [icar_b200.comm_unique_id() if rank == 0 else None]
     dist.broadcast_object_list(ids, src=0)
     dom.comm_init(rank + 1, world, ids[0])
+    # update_dt: the CFL time step of the slab, `co_min` over the images (ncclAllReduce), must equal the
+    # single-image value (the per-cell maxima partition exactly)
+    dt_one = one.compute_dt(st["dz_levels"])
+    dt_all = dom.compute_dt(st["dz_levels"])
+    assert dt_one == dt_all == min(dt, 120.0), (dt_one, dt_all, dt)
     for _ in range(steps):
         one.physics_step(dt)
         dom.physics_step(dt)

@@ -1,0 +1,106 @@
+"""The "next" rows around the hot path: diagnostic_update's exner / density,
+update_dt / compute_dt and enforce_limits on the device-resident fields, against the NumPy restatement."""
+import numpy as np
+import pytest
+
+from icar_b200 import ideal
+from oracle import np_restatement as NP
+
+pytestmark = pytest.mark.gpu
+
+
+def make(gpu_lib, st, **opt):
+    nx, nz, ny = st["nx"], st["nz"], st["ny"]
+    dom = gpu_lib.Domain(gpu_lib.Grid.single_image(nx, nz, ny), gpu_lib.Options(dx=st["dx"], **opt))
+    dom.upload_state(st)
+    return dom
+
+
+def test_diagnostic_update_matches_time_step_f90(gpu_lib):
+    st = ideal.make_ideal_case(nx=70, nz=15, ny=11, perturb=True)
+    dom = make(gpu_lib, st)
+    dom.upload("exner", np.zeros_like(st["pii"]))
+    dom.upload("density", np.zeros_like(st["rho"]))
+    dom.diagnostic_update()
+    ex, rho = NP.diagnostic_update_np(st["pressure"], st["th"])
+    # powf of the device vs glibc: <= 2 ulp
+    np.testing.assert_allclose(dom.download("exner"), ex, rtol=3e-7)
+    np.testing.assert_allclose(dom.download("density"), rho, rtol=5e-7)
+    # and the ideal-case generator agrees with both
+    np.testing.assert_allclose(ex, st["pii"], rtol=3e-7)
+
+
+@pytest.mark.parametrize("strictness", [1, 2, 3, 4, 5])
+@pytest.mark.parametrize("scale", [1.0, 0.01])
+def test_compute_dt_all_strictness_levels(gpu_lib, strictness, scale):
+    """cfl_strictness 1, 5 (and the 1-D branch of 2) divide the CFL factor by a wind SPEED, not by
+    speed/dx (time_step.f90:241-258,296-305), so with ordinary winds the reference stops with "time step
+    too small"; the library must fail the same way, and agree exactly where the reference succeeds."""
+    st = ideal.make_ideal_case(nx=53, nz=12, ny=17, perturb=True)
+    rng = np.random.default_rng(strictness)
+    st["u"] = (st["u"] * rng.uniform(0.2, 1.5, st["u"].shape) * scale).astype(np.float32)
+    st["v"] = (st["v"] * scale).astype(np.float32)
+    st["w"] = (rng.uniform(-2, 2, st["w"].shape) * scale).astype(np.float32)
+    dom = make(gpu_lib, st)
+    try:
+        want = NP.compute_dt_np(st["dx"], st["u"], st["v"], st["w"], st["dz_levels"], 0.9, strictness)
+    except FloatingPointError:
+        with pytest.raises(gpu_lib.IcarError) as e:
+            dom.compute_dt(st["dz_levels"], 0.9, strictness)
+        assert e.value.code == gpu_lib.ERR_PHYSICS
+        return
+    got = dom.compute_dt(st["dz_levels"], 0.9, strictness)
+    assert got == want, (got, want)          # maxima are exact, the arithmetic is the same REAL sequence
+
+
+def test_compute_dt_cap_and_failure(gpu_lib):
+    st = ideal.make_ideal_case(nx=20, nz=8, ny=9)
+    st["u"][:] = np.float32(0.5); st["v"][:] = 0; st["w"][:] = 0
+    dom = make(gpu_lib, st)
+    assert dom.compute_dt(st["dz_levels"]) == 120.0                      # min(seconds, 120), time_step.f90:421
+    st["u"][:] = np.float32(5e5)
+    dom.upload("u", st["u"])
+    with pytest.raises(gpu_lib.IcarError) as e:                          # "ERROR time step too small", :322-328
+        dom.compute_dt(st["dz_levels"])
+    assert e.value.code == gpu_lib.ERR_PHYSICS and "time step too small" in str(e.value)
+
+
+@pytest.mark.parametrize("mp", [2, 1])
+def test_enforce_limits_clamps_every_scheme_scalar(gpu_lib, mp):
+    st = ideal.make_ideal_case(nx=40, nz=8, ny=10, perturb=True)
+    names = ["th", "qv", "qc", "qr", "qs"]
+    if mp == 1:
+        ideal.add_thompson_fields(st)
+        names += ["qi", "qg", "ni", "nr"]
+    rng = np.random.default_rng(0)
+    for k in names:
+        st[k] = (st[k] + rng.normal(0, 1e-3, st[k].shape)).astype(np.float32) if k != "th" else st[k]
+        st[k][rng.random(st[k].shape) < 0.2] *= np.float32(-1)
+    dom = make(gpu_lib, st, microphysics=mp)
+    dom.enforce_limits()
+    want = [st[k].copy() for k in names]
+    NP.enforce_limits_np(want)
+    for k, w in zip(names, want):
+        np.testing.assert_array_equal(dom.download(k), w, err_msg=k)
+
+
+def test_device_resident_loop_body(gpu_lib, oracle):
+    """update_dt -> diagnostic_update -> mp -> advect -> enforce_limits entirely on the device, a few
+    steps, against the same sequence on the CPU (exact arithmetic mode)."""
+    st = ideal.make_ideal_case(nx=48, nz=16, ny=20, perturb=True)
+    st["qv"] *= np.float32(3.0)
+    ref = ideal.copy_state(st)
+    dom = make(gpu_lib, st, exact_arithmetic=1)
+    for _ in range(3):
+        dt = dom.compute_dt(st["dz_levels"])
+        dom.diagnostic_update()
+        dom.physics_step(dt)
+        dom.enforce_limits()
+        dt_ref = NP.compute_dt_np(ref["dx"], ref["u"], ref["v"], ref["w"], ref["dz_levels"], 0.9, 3)
+        assert dt == dt_ref
+        ref["pii"], ref["rho"] = NP.diagnostic_update_np(ref["pressure"], ref["th"])
+        oracle.step_simple(ref, np.float32(dt_ref), np.float32(dt_ref), 2, True)
+        NP.enforce_limits_np([ref[k] for k in ("th", "qv", "qc", "qr", "qs")])
+    for k in ("th", "qv", "qc", "qr", "qs"):
+        a, b = dom.download(k).astype(np.float64), ref[k].astype(np.float64)
+        assert np.abs(a - b).max() <= 1e-5 * np.abs(b).max(), k         # exner via device powf feeds mp_simple

@@ -107,3 +107,21 @@ def test_mp_simple_water_budget(oracle):
     assert np.abs(lhs - w0[1:-1, 1:-1]).max() / w0.max() < 2e-5
     # boundary-condition ring is never processed (its = ims+1 ..., grid_obj.f90:241-250)
     assert np.array_equal(st["th"][0], th0[0]) and np.array_equal(st["th"][:, :, 0], th0[:, :, 0])
+
+
+def test_compute_dt_restatement_matches_the_ideal_case_generator():
+    """oracle/np_restatement.compute_dt_np (time_step.f90:217-330, all strictness levels) against the
+    strictness-3 formula icar_b200.ideal uses to pick the benchmark's dt."""
+    from oracle import np_restatement as NP
+    st = ideal.make_ideal_case(nx=30, nz=10, ny=12, perturb=True)
+    want = ideal.compute_dt(st["u"], st["v"], st["w"], st["dx"], st["dz_levels"])
+    assert NP.compute_dt_np(st["dx"], st["u"], st["v"], st["w"], st["dz_levels"], 0.9, 3) == pytest.approx(want, rel=1e-7)
+    # strictness 4 = strictness 3 / (sqrt(3) * 1.001); 2 <= 3 (mean instead of sum, but at least the 1-D limit)
+    d3 = NP.compute_dt_np(st["dx"], st["u"] * 1e-3, st["v"] * 1e-3, st["w"] * 1e-3, st["dz_levels"], 0.9, 3)
+    d4 = NP.compute_dt_np(st["dx"], st["u"] * 1e-3, st["v"] * 1e-3, st["w"] * 1e-3, st["dz_levels"], 0.9, 4)
+    assert d3 == 120.0 and d4 == 120.0          # capped (time_step.f90:421)
+    with pytest.raises(FloatingPointError):     # strictness 1 divides by a speed, not speed/dx (:241-249)
+        NP.compute_dt_np(st["dx"], st["u"], st["v"], st["w"], st["dz_levels"], 0.9, 1)
+    ex, rho = NP.diagnostic_update_np(st["pressure"], st["th"])
+    np.testing.assert_allclose(ex, st["pii"], rtol=3e-7)
+    np.testing.assert_allclose(rho, st["rho"], rtol=5e-7)
