@@ -110,14 +110,11 @@ struct icar_ctx {
     // order), as requested by the microphysics scheme's *_var_request (mp_simple.f90:116-118, mp_driver.f90:128-131)
     int nadv = 0, adv[ICAR_MAX_SCALARS] = {};
     int nexch = 0, exch[ICAR_MAX_EXCHANGED] = {};
-    // Thompson per-call REAL*4 graupel [tile | ring strips] and the module array SR (mp_driver.f90:411-413,440)
-    float *graupel2d = nullptr, *graupel2d_halo = nullptr, *sr2d = nullptr;
-    // per-call REAL*4 precipitation: [rain | snow] of the main-stream tile and of the ring strips
-    float *rain2d = nullptr, *snow2d = nullptr, *rain2d_halo = nullptr, *snow2d_halo = nullptr;
+    // Thompson's module array SR (mp_driver.f90:440)
+    float* sr2d = nullptr;
     cudaStream_t aux = nullptr;      // the ring strips of mp(halo) run here, next to mp(subset)
     cudaEvent_t ev_fork = nullptr, ev_aux = nullptr;
     bool aux_pending = false;        // ring strips still running on the aux stream
-    bool main_acc_pending = false;   // rain2d / snow2d not yet folded into the REAL*8 accumulators
     unsigned long long* diag = nullptr;
     std::vector<void*> scratch;      // leaf-call staging buffers (float or double cells)
     std::vector<size_t> scratch_bytes;
@@ -158,9 +155,9 @@ int fail(icar_ctx* c, int code, const std::string& msg) {
 }
 
 // kernel families of the per-kernel profile
-enum ProfKid { K_MP_SIMPLE = 0, K_MP_THOMPSON, K_ACCUMULATE, K_WIND_NORMALISE, K_FACE_COEF, K_UPWIND_PASS1, K_CORRECTOR,
+enum ProfKid { K_MP_SIMPLE = 0, K_MP_THOMPSON, K_WIND_NORMALISE, K_FACE_COEF, K_UPWIND_PASS1, K_CORRECTOR,
                K_STAGED_ADVECT3D, K_HALO_PACK, K_HALO_UNPACK, K_COUNT };
-const char* const kProfNames[K_COUNT] = {"k_mp_simple", "k_mp_thompson", "k_accumulate_precip", "k_wind_normalise",
+const char* const kProfNames[K_COUNT] = {"k_mp_simple", "k_mp_thompson", "k_wind_normalise",
                                          "k_face_coefficients", "k_upwind_all", "k_corrector_fused",
                                          "staged_advect3d", "k_halo_pack", "k_halo_unpack"};
 
@@ -278,8 +275,9 @@ int need_uploaded(icar_ctx* ctx, std::initializer_list<int> vars, const char* wh
 
 // process_subdomain's scheme call (mp_driver.f90:398-607) on up to four 1-based inclusive tiles
 // {its, ite, jts, jte}, one launch
-int run_mp_tiles(icar_ctx* ctx, float mp_dt, const int (*t)[4], int ntiles, int kts, int kte, cudaStream_t st,
-                 float* rain2d, float* snow2d, float* graupel2d) {
+int run_mp_tiles(icar_ctx* ctx, float mp_dt, const int (*t)[4], int ntiles, int kts, int kte, cudaStream_t st) {
+    double* acc_rain = (double*)ctx->vars[ICAR_VAR_PRECIPITATION];
+    double* acc_snow = (double*)ctx->vars[ICAR_VAR_SNOWFALL];
     const icar_grid& gr = ctx->grid;
     MpTiles tiles;
     tiles.n = 0;
@@ -306,9 +304,10 @@ int run_mp_tiles(icar_ctx* ctx, float mp_dt, const int (*t)[4], int ntiles, int 
             (float*)ctx->vars[ICAR_VAR_SNOW_IN_AIR], (float*)ctx->vars[ICAR_VAR_GRAUPEL_IN_AIR],
             (float*)ctx->vars[ICAR_VAR_ICE_NUMBER], (float*)ctx->vars[ICAR_VAR_RAIN_NUMBER],
             (float*)ctx->vars[ICAR_VAR_POTENTIAL_TEMPERATURE], (const float*)ctx->vars[ICAR_VAR_EXNER],
-            (const float*)ctx->vars[ICAR_VAR_PRESSURE], (const float*)ctx->vars[ICAR_VAR_DZ_MASS], mp_dt, rain2d,
-            /*RAINNCV = this_precip: never written by the reference*/ nullptr, snow2d, nullptr, graupel2d, nullptr,
-            ctx->sr2d, ctx->ld2, tiles, kts - gr.kms, kte - gr.kms, ctx->th_diag, st);
+            (const float*)ctx->vars[ICAR_VAR_PRESSURE], (const float*)ctx->vars[ICAR_VAR_DZ_MASS], mp_dt, nullptr,
+            /*RAINNCV = this_precip: never written by the reference*/ nullptr, nullptr, nullptr, nullptr, nullptr,
+            ctx->sr2d, ctx->ld2, tiles, kts - gr.kms, kte - gr.kms, ctx->th_diag, st, acc_rain, acc_snow,
+            (double*)ctx->vars[ICAR_VAR_GRAUPEL]);
         if (nl < 0) return fail(ctx, ICAR_ERR_INVALID, "mp_thompson: more than 64 levels are not built");
         ctx->launches += nl;
         CU(cudaGetLastError());
@@ -323,8 +322,9 @@ int run_mp_tiles(icar_ctx* ctx, float mp_dt, const int (*t)[4], int ntiles, int 
             (float*)ctx->vars[ICAR_VAR_POTENTIAL_TEMPERATURE], (const float*)ctx->vars[ICAR_VAR_EXNER],
             (const float*)ctx->vars[ICAR_VAR_DENSITY], (float*)ctx->vars[ICAR_VAR_WATER_VAPOR],
             (float*)ctx->vars[ICAR_VAR_CLOUD_WATER], (float*)ctx->vars[ICAR_VAR_RAIN_IN_AIR],
-            (float*)ctx->vars[ICAR_VAR_SNOW_IN_AIR], rain2d, snow2d, ctx->ld2, mp_dt,
-            (const float*)ctx->vars[ICAR_VAR_DZ_MASS], tiles, kts - gr.kms, kte - gr.kms, c2r, c2s, ctx->diag, st);
+            (float*)ctx->vars[ICAR_VAR_SNOW_IN_AIR], nullptr, nullptr, ctx->ld2, mp_dt,
+            (const float*)ctx->vars[ICAR_VAR_DZ_MASS], tiles, kts - gr.kms, kte - gr.kms, c2r, c2s, ctx->diag, st,
+            acc_rain, acc_snow);
         if (nl < 0) return fail(ctx, ICAR_ERR_INVALID, "mp_simple: more than 80 levels are not built");
         ctx->launches += nl;
         CU(cudaGetLastError());
@@ -334,26 +334,13 @@ int run_mp_tiles(icar_ctx* ctx, float mp_dt, const int (*t)[4], int ntiles, int 
                                            " is not built (kMP_THOMPSON = 1 and kMP_SB04 = 2 are)");
 }
 
-// Waits (on the compute stream) for the ring strips that mp(halo) left running on the aux stream and
-// folds the pending per-call precipitation (interior tile and/or strips: disjoint cells, so one pass
-// in any order equals the reference's two `+=`) into the REAL*8 accumulators.
+// Makes the compute stream wait for the strips that mp(halo) / the multi-image step left running on the
+// auxiliary stream.  (The per-call precipitation needs no joining: the mp kernels add it to the REAL*8
+// accumulators themselves, the strips and the interior tile own disjoint columns.)
 int join_aux(icar_ctx* ctx) {
-    if (!ctx->aux_pending && !ctx->main_acc_pending) return ICAR_OK;
-    if (ctx->aux_pending) CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_aux, 0));
-    ProfScope ps(ctx, K_ACCUMULATE, ctx->stream);
-    ctx->launches += accumulate_precip_launch(
-        ctx->g.nx, ctx->g.ny, ctx->ld2, ctx->main_acc_pending ? ctx->rain2d : nullptr,
-        ctx->main_acc_pending ? ctx->snow2d : nullptr, ctx->aux_pending ? ctx->rain2d_halo : nullptr,
-        ctx->aux_pending ? ctx->snow2d_halo : nullptr, (double*)ctx->vars[ICAR_VAR_PRECIPITATION],
-        (double*)ctx->vars[ICAR_VAR_SNOWFALL], ctx->stream);
-    if (ctx->opt.microphysics == 1)        // domain%graupel += graupel (mp_driver.f90:590-592): same kernel, graupel in both slots
-        ctx->launches += accumulate_precip_launch(
-            ctx->g.nx, ctx->g.ny, ctx->ld2, ctx->main_acc_pending ? ctx->graupel2d : nullptr, nullptr,
-            ctx->aux_pending ? ctx->graupel2d_halo : nullptr, nullptr, (double*)ctx->vars[ICAR_VAR_GRAUPEL], nullptr,
-            ctx->stream);
-    CU(cudaGetLastError());
+    if (!ctx->aux_pending) return ICAR_OK;
+    CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_aux, 0));
     ctx->aux_pending = false;
-    ctx->main_acc_pending = false;
     return ICAR_OK;
 }
 
@@ -487,14 +474,8 @@ extern "C" int icar_create(int device, const icar_grid* grid, const icar_options
             if (alloc_cells(ctx, &ctx->fq2[n]) != ICAR_OK || alloc_cells(ctx, &ctx->fout[n]) != ICAR_OK)
                 return bail(ICAR_ERR_CUDA);
     }
-    CUB(cudaMalloc((void**)&ctx->rain2d, (size_t)4 * ctx->ld2 * ny * sizeof(float)));   // 4 planes, one block
-    ctx->snow2d = ctx->rain2d + (size_t)ctx->ld2 * ny;
-    ctx->rain2d_halo = ctx->snow2d + (size_t)ctx->ld2 * ny;
-    ctx->snow2d_halo = ctx->rain2d_halo + (size_t)ctx->ld2 * ny;
-    CUB(cudaMalloc((void**)&ctx->graupel2d, (size_t)3 * ctx->ld2 * ny * sizeof(float)));
-    CUB(cudaMemsetAsync(ctx->graupel2d, 0, (size_t)3 * ctx->ld2 * ny * sizeof(float), ctx->stream));
-    ctx->graupel2d_halo = ctx->graupel2d + (size_t)ctx->ld2 * ny;
-    ctx->sr2d = ctx->graupel2d_halo + (size_t)ctx->ld2 * ny;
+    CUB(cudaMalloc((void**)&ctx->sr2d, (size_t)ctx->ld2 * ny * sizeof(float)));
+    CUB(cudaMemsetAsync(ctx->sr2d, 0, (size_t)ctx->ld2 * ny * sizeof(float), ctx->stream));
     CUB(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
     CUB(cudaStreamCreateWithFlags(&ctx->aux, cudaStreamNonBlocking));
     CUB(cudaEventCreateWithFlags(&ctx->ev_aux, cudaEventDisableTiming));
@@ -519,7 +500,7 @@ extern "C" int icar_destroy(icar_ctx* ctx) {
     if (ctx->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(ctx->comm);
     for (void* p : ctx->vars) if (p) cudaFree(p);
     float* bufs[] = {ctx->U, ctx->V, ctx->W, ctx->Wn, ctx->G, ctx->qa, ctx->qb, ctx->u2, ctx->v2, ctx->w2,
-                     ctx->rain2d, ctx->graupel2d, ctx->send_w, ctx->send_e, ctx->recv_w, ctx->recv_e};
+                     ctx->sr2d, ctx->send_w, ctx->send_e, ctx->recv_w, ctx->recv_e};
     for (float* p : bufs) if (p) cudaFree(p);
     if (ctx->diag) cudaFree(ctx->diag);
     for (double* t : ctx->th_tab) if (t) cudaFree(t);
@@ -727,6 +708,7 @@ extern "C" int icar_advect(icar_ctx* ctx, float dt) {
 //   phase 1 ("subset") : every other cell of the physics tile
 // Both phases together cover the tile exactly once, like process_halo + process_subdomain(subset).
 int mp_phase(icar_ctx* ctx, float dt_in, int phase, int axis, int h);
+int halo_send_from(icar_ctx* ctx, cudaStream_t producer);
 
 extern "C" int icar_mp(icar_ctx* ctx, float dt_in, int halo, int subset) {
     if (!ctx) return ICAR_ERR_INVALID;
@@ -744,33 +726,25 @@ extern "C" int icar_mp(icar_ctx* ctx, float dt_in, int halo, int subset) {
         if (!has_halo) ctx->last_model_time = ctx->model_time;
         int kte = gr.kte;
         if (ctx->opt.top_mp_level > 0) kte = std::min(kte, ctx->opt.top_mp_level);   // :723-725
-        // process_subdomain zeroes its local precipitation arrays on entry (:411-413) and adds them to
-        // the REAL*8 accumulators on exit (:587-595); tiles of one call are disjoint, so one clear
-        // and one accumulation per group of tiles is identical.
-        const size_t b2 = (size_t)2 * ctx->ld2 * ctx->g.ny * sizeof(float);     // rain + snow plane
-        if (has_halo || (!has_halo && !has_subset) || ctx->main_acc_pending)
-            if ((rc = join_aux(ctx))) return rc;          // earlier tiles overlap these cells / buffers
+        // process_subdomain's local precipitation arrays (:411-413, :587-595) are folded into the kernels
+        if (has_halo || (!has_halo && !has_subset))
+            if ((rc = join_aux(ctx))) return rc;          // earlier strips overlap these cells
         if (has_subset || (!has_halo && !has_subset)) {
-            CU(cudaMemsetAsync(ctx->rain2d, 0, b2, ctx->stream));
-            CU(cudaMemsetAsync(ctx->graupel2d, 0, b2 / 2, ctx->stream));
             const int sub = has_subset ? subset : 0;                                     // :728-738 / :754-766
             const int t[1][4] = {{gr.its + sub, gr.ite - sub, gr.jts + sub, gr.jte - sub}};
-            if ((rc = run_mp_tiles(ctx, mp_dt, t, 1, gr.kts, kte, ctx->stream, ctx->rain2d, ctx->snow2d, ctx->graupel2d))) return rc;
-            ctx->main_acc_pending = true;
+            if ((rc = run_mp_tiles(ctx, mp_dt, t, 1, gr.kts, kte, ctx->stream))) return rc;
         }
         if (has_halo) {                                                                  // process_halo :609-658
             // The four strips are thin (latency-bound): they share ONE launch on an auxiliary stream
             // and are joined lazily, so the interior tile of mp(subset) overlaps them the way
             // time_step.f90:512-526 overlaps the halo exchange.
-            CU(cudaMemsetAsync(ctx->rain2d_halo, 0, b2, ctx->stream));
-            CU(cudaMemsetAsync(ctx->graupel2d_halo, 0, b2 / 2, ctx->stream));
             CU(cudaEventRecord(ctx->ev_fork, ctx->stream));
             const int t[4][4] = {{gr.its, gr.its + halo - 1, gr.jts, gr.jte},
                                  {gr.ite - halo + 1, gr.ite, gr.jts, gr.jte},
                                  {gr.its + halo, gr.ite - halo, gr.jts, gr.jts + halo - 1},
                                  {gr.its + halo, gr.ite - halo, gr.jte - halo + 1, gr.jte}};
             CU(cudaStreamWaitEvent(ctx->aux, ctx->ev_fork, 0));
-            if ((rc = run_mp_tiles(ctx, mp_dt, t, 4, gr.kts, kte, ctx->aux, ctx->rain2d_halo, ctx->snow2d_halo, ctx->graupel2d_halo))) return rc;
+            if ((rc = run_mp_tiles(ctx, mp_dt, t, 4, gr.kts, kte, ctx->aux))) return rc;
             CU(cudaEventRecord(ctx->ev_aux, ctx->aux));
             ctx->aux_pending = true;
         }
@@ -791,29 +765,26 @@ int mp_phase(icar_ctx* ctx, float dt_in, int phase, int axis, int h) {
     if (phase == 1) ctx->last_model_time = ctx->model_time;                               // :711-713
     int kte = gr.kte;
     if (ctx->opt.top_mp_level > 0) kte = std::min(kte, ctx->opt.top_mp_level);
-    const size_t b2 = (size_t)2 * ctx->ld2 * ctx->g.ny * sizeof(float);
     // strips exist only next to a ghost zone (an interior edge of the decomposition)
     const bool lo = axis ? (gr.jms > gr.jds) : (gr.ims > gr.ids);
     const bool hi = axis ? (gr.jme < gr.jde) : (gr.ime < gr.ide);
     const int a0 = axis ? gr.jts : gr.its, a1 = axis ? gr.jte : gr.ite;
     const int in0 = lo ? a0 + h : a0, in1 = hi ? a1 - h : a1;
     if (phase == 0) {
+        // the strips run on the auxiliary stream: the exchange waits for them only, and the interior tile
+        // (phase 1, compute stream) runs next to both
         if ((rc = join_aux(ctx))) return rc;
-        CU(cudaMemsetAsync(ctx->rain2d_halo, 0, b2, ctx->stream));
-        CU(cudaMemsetAsync(ctx->graupel2d_halo, 0, b2 / 2, ctx->stream));
+        CU(cudaEventRecord(ctx->ev_fork, ctx->stream));
+        CU(cudaStreamWaitEvent(ctx->aux, ctx->ev_fork, 0));
         int t[2][4], n = 0;
         if (lo) { t[n][0] = axis ? gr.its : a0; t[n][1] = axis ? gr.ite : a0 + h - 1; t[n][2] = axis ? a0 : gr.jts; t[n][3] = axis ? a0 + h - 1 : gr.jte; ++n; }
         if (hi) { t[n][0] = axis ? gr.its : a1 - h + 1; t[n][1] = axis ? gr.ite : a1; t[n][2] = axis ? a1 - h + 1 : gr.jts; t[n][3] = axis ? a1 : gr.jte; ++n; }
-        if ((rc = run_mp_tiles(ctx, mp_dt, t, n, gr.kts, kte, ctx->stream, ctx->rain2d_halo, ctx->snow2d_halo, ctx->graupel2d_halo))) return rc;
-        CU(cudaEventRecord(ctx->ev_aux, ctx->stream));
-        ctx->aux_pending = true;      // (recorded on the compute stream: join_aux's wait is then a no-op)
+        if ((rc = run_mp_tiles(ctx, mp_dt, t, n, gr.kts, kte, ctx->aux))) return rc;
+        CU(cudaEventRecord(ctx->ev_aux, ctx->aux));
+        ctx->aux_pending = true;
     } else {
-        if (ctx->main_acc_pending && (rc = join_aux(ctx))) return rc;
-        CU(cudaMemsetAsync(ctx->rain2d, 0, b2, ctx->stream));
-        CU(cudaMemsetAsync(ctx->graupel2d, 0, b2 / 2, ctx->stream));
         const int t[1][4] = {{axis ? gr.its : in0, axis ? gr.ite : in1, axis ? in0 : gr.jts, axis ? in1 : gr.jte}};
-        if ((rc = run_mp_tiles(ctx, mp_dt, t, 1, gr.kts, kte, ctx->stream, ctx->rain2d, ctx->snow2d, ctx->graupel2d))) return rc;
-        ctx->main_acc_pending = true;
+        if ((rc = run_mp_tiles(ctx, mp_dt, t, 1, gr.kts, kte, ctx->stream))) return rc;
     }
     return ICAR_OK;
 }
@@ -869,12 +840,20 @@ extern "C" int icar_comm_init(icar_ctx* ctx, int image, int nimages, const char 
     return ICAR_OK;
 }
 
+// halo_send with the stream that produced the cells to be sent: the exchange (and, for x-slabs, the pack
+// kernel) is ordered after the work queued on `producer` only
+int halo_send_from(icar_ctx* ctx, cudaStream_t producer);
+
 extern "C" int icar_halo_send(icar_ctx* ctx) {
     if (!ctx) return ICAR_ERR_INVALID;
     if (ctx->nimages == 1) return ICAR_OK;
-    if (!ctx->comm) return fail(ctx, ICAR_ERR_COMM, "icar_halo_send: icar_comm_init was not called");
     CU(cudaSetDevice(ctx->device));
     { int jr = join_aux(ctx); if (jr) return jr; }
+    return halo_send_from(ctx, ctx->stream);
+}
+
+int halo_send_from(icar_ctx* ctx, cudaStream_t producer) {
+    if (!ctx->comm) return fail(ctx, ICAR_ERR_COMM, "icar_halo_send: icar_comm_init was not called");
     int plan[8];
     if (icar_halo_plan(&ctx->grid, ctx->image, ctx->nimages, plan)) return fail(ctx, ICAR_ERR_INVALID, "icar_halo_send: tile narrower than two halos, or not a slab decomposition");
     const int h = plan[7];
@@ -889,10 +868,10 @@ extern "C" int icar_halo_send(icar_ctx* ctx) {
         float* bufs[2];
         if (lower) { x0[ns] = plan[0]; bufs[ns++] = ctx->send_w; }
         if (upper) { x0[ns] = plan[1]; bufs[ns++] = ctx->send_e; }
-        { ProfScope ps(ctx, K_HALO_PACK, ctx->stream);
-          ctx->launches += halo_pack_launch(ctx->g, fields, nf, h, ns, x0, bufs, ctx->stream); }
+        { ProfScope ps(ctx, K_HALO_PACK, producer);
+          ctx->launches += halo_pack_launch(ctx->g, fields, nf, h, ns, x0, bufs, producer); }
         CU(cudaGetLastError());
-        CU(cudaEventRecord(ctx->ev_packed, ctx->stream));
+        CU(cudaEventRecord(ctx->ev_packed, producer));
         CU(cudaStreamWaitEvent(ctx->comm_stream, ctx->ev_packed, 0));
         NC(g_nccl.GroupStart());
         if (lower) {
@@ -908,7 +887,7 @@ extern "C" int icar_halo_send(icar_ctx* ctx) {
         // y-slabs: a face of one field is h contiguous planes -> send straight from the field and
         // receive straight into the ghost planes (mp(subset) does not touch either while this runs)
         const size_t ps = ctx->g.ps(), count = (size_t)h * ps;
-        CU(cudaEventRecord(ctx->ev_packed, ctx->stream));
+        CU(cudaEventRecord(ctx->ev_packed, producer));
         CU(cudaStreamWaitEvent(ctx->comm_stream, ctx->ev_packed, 0));
         NC(g_nccl.GroupStart());
         for (int s = 0; s < nf; ++s) {
@@ -972,8 +951,8 @@ extern "C" int icar_physics_step(icar_ctx* ctx, float dt) {
         } else {
             int plan[8];
             if (icar_halo_plan(&ctx->grid, ctx->image, ctx->nimages, plan)) return fail(ctx, ICAR_ERR_INVALID, "icar_physics_step: not a slab decomposition");
-            if ((rc = mp_phase(ctx, dt, 0, plan[6], h))) return rc;   // :512  the cells the neighbours need
-            if ((rc = icar_halo_send(ctx))) return rc;                // :515
+            if ((rc = mp_phase(ctx, dt, 0, plan[6], h))) return rc;   // :512  the cells the neighbours need (aux stream)
+            if ((rc = halo_send_from(ctx, ctx->aux))) return rc;      // :515  ordered after the strips only
             if ((rc = mp_phase(ctx, dt, 1, plan[6], h))) return rc;   // :523  everything else, overlapping the exchange
             if ((rc = icar_halo_retrieve(ctx))) return rc;            // :526
         }

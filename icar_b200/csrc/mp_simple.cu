@@ -184,7 +184,8 @@ k_mp_simple(Geom g, const float* __restrict__ gp, float* __restrict__ gth,
             float* __restrict__ gqv, float* __restrict__ gqc, float* __restrict__ gqr,
             float* __restrict__ gqs, float* __restrict__ rain, float* __restrict__ snow, int ld2,
             float dt, const float* __restrict__ gdz, MpTiles tiles, int kts,
-            int kte, float c2r, float c2s, unsigned long long* diag) {
+            int kte, float c2r, float c2s, unsigned long long* diag, double* __restrict__ acc_rain,
+            double* __restrict__ acc_snow) {
     // blockIdx.z selects one of up to 4 disjoint tiles (the ring strips of process_halo share a launch)
     const int its = tiles.its[blockIdx.z], ite = tiles.ite[blockIdx.z];
     const int jts = tiles.jts[blockIdx.z], jte = tiles.jte[blockIdx.z];
@@ -271,7 +272,12 @@ k_mp_simple(Geom g, const float* __restrict__ gp, float* __restrict__ gth,
     bool owner = false;
 #pragma unroll
     for (int c = 0; c < CPT; ++c) owner = owner || (live[c] && (tz + c * nzt) == kts);
-    float rain_acc = owner ? rain[c2] : 0.f, snow_acc = owner ? snow[c2] : 0.f;
+    // resident mode (acc_rain != null): the per-call REAL*4 precipitation array of process_subdomain starts
+    // at zero (mp_driver.f90:411-413) and is added to the REAL*8 accumulator at the end (:587-595) -- done
+    // here by the owning thread, which saves the clear and the separate accumulation pass
+    float rain_acc = (owner && !acc_rain) ? rain[c2] : 0.f, snow_acc = (owner && !acc_rain) ? snow[c2] : 0.f;
+    // (accumulators are read here, not at the end: a dependent load in a CTA's last instructions is exposed)
+    const double acc_r0 = (owner && acc_rain) ? acc_rain[c2] : 0.0, acc_s0 = (owner && acc_rain) ? acc_snow[c2] : 0.0;
 
     // ---- sedimentation + re-evaporation sub-steps, rain then snow (:507-564, sediment :437-459)
 #pragma unroll
@@ -328,32 +334,18 @@ k_mp_simple(Geom g, const float* __restrict__ gp, float* __restrict__ gth,
         gth[a] = T[c] / pii[c];
         gqv[a] = qv[c]; gqc[a] = qc[c]; gqr[a] = qr[c]; gqs[a] = qs[c];
     }
-    if (owner && (n_r > 0 || n_s > 0)) { rain[c2] = rain_acc; snow[c2] = snow_acc; }
+    if (owner && (n_r > 0 || n_s > 0)) {
+        if (acc_rain) {
+            acc_rain[c2] = acc_r0 + (double)rain_acc;
+            acc_snow[c2] = acc_s0 + (double)snow_acc;
+        } else {
+            rain[c2] = rain_acc; snow[c2] = snow_acc;
+        }
+    }
     if (dflags) {                // events, not cells: the counters say "how many threads saw it"
         if (dflags & 1u) atomicAdd(diag + 0, 1ULL);
         if (dflags & 2u) atomicAdd(diag + 1, 1ULL);
         if (dflags & 4u) atomicAdd(diag + 2, 1ULL);
-    }
-}
-
-// domain%accumulated_precipitation (REAL*8) += precipitation (mp_driver.f90:587-595); up to two
-// per-call REAL*4 pairs (interior tile and ring strips, disjoint cells) in one pass
-__global__ void k_accumulate_precip(int nx, int ny, int ld2, const float* __restrict__ rain,
-                                    const float* __restrict__ snow, const float* __restrict__ rain_b,
-                                    const float* __restrict__ snow_b, double* __restrict__ acc_rain,
-                                    double* __restrict__ acc_snow) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y;
-    if (i >= nx || j >= ny) return;
-    size_t c = (size_t)i + (size_t)ld2 * j;
-    double r = acc_rain[c];
-    if (rain) r = r + (double)rain[c];
-    if (rain_b) r = r + (double)rain_b[c];
-    acc_rain[c] = r;
-    if (acc_snow) {                       // (null when a single accumulator is updated: Thompson's graupel)
-        double s = acc_snow[c];
-        if (rain) s = s + (double)snow[c];
-        if (rain_b) s = s + (double)snow_b[c];
-        acc_snow[c] = s;
     }
 }
 
@@ -362,7 +354,7 @@ __global__ void k_accumulate_precip(int nx, int ny, int ld2, const float* __rest
 int mp_simple_launch(const Geom& g, const float* p, float* th, const float* pii, const float* rho,
                      float* qv, float* qc, float* qr, float* qs, float* rain, float* snow, int ld2,
                      float dt, const float* dz, const MpTiles& tiles, int kts, int kte, float c2r,
-                     float c2s, unsigned long long* diag, cudaStream_t st) {
+                     float c2s, unsigned long long* diag, cudaStream_t st, double* acc_rain, double* acc_snow) {
     int gx = 0, gy = 0;
     for (int t = 0; t < tiles.n; ++t) {
         if (tiles.ite[t] < tiles.its[t] || tiles.jte[t] < tiles.jts[t]) continue;
@@ -380,7 +372,7 @@ int mp_simple_launch(const Geom& g, const float* p, float* th, const float* pii,
     size_t smem = (size_t)(2 * (g.nz + 1) + 3) * TX * sizeof(float);
 #define LAUNCH(C)                                                                                 \
     k_mp_simple<C><<<grid, block, smem, st>>>(g, p, th, pii, rho, qv, qc, qr, qs, rain, snow, ld2, \
-                                              dt, dz, tiles, kts, kte, c2r, c2s, diag)
+                                              dt, dz, tiles, kts, kte, c2r, c2s, diag, acc_rain, acc_snow)
     switch (cpt) {
         case 1: LAUNCH(1); break;
         case 2: LAUNCH(2); break;
@@ -392,15 +384,6 @@ int mp_simple_launch(const Geom& g, const float* p, float* th, const float* pii,
         default: LAUNCH(8); break;
     }
 #undef LAUNCH
-    return 1;
-}
-
-int accumulate_precip_launch(int nx, int ny, int ld2, const float* rain, const float* snow,
-                             const float* rain_b, const float* snow_b, double* acc_rain,
-                             double* acc_snow, cudaStream_t st) {
-    dim3 block(128);
-    dim3 grid((nx + 127) / 128, ny);
-    k_accumulate_precip<<<grid, block, 0, st>>>(nx, ny, ld2, rain, snow, rain_b, snow_b, acc_rain, acc_snow);
     return 1;
 }
 

@@ -17,12 +17,9 @@ struct MpTiles {
 int mp_simple_launch(const Geom& g, const float* p, float* th, const float* pii, const float* rho,
                      float* qv, float* qc, float* qr, float* qs, float* rain, float* snow, int ld2,
                      float dt, const float* dz, const MpTiles& tiles, int kts, int kte, float c2r,
-                     float c2s, unsigned long long* diag, cudaStream_t st);
-
-// accumulated_precipitation / accumulated_snowfall (REAL*8) += the step's REAL*4 totals
-// (mp_driver.f90:587-595)
-int accumulate_precip_launch(int nx, int ny, int ld2, const float* rain, const float* snow,
-                             const float* rain_b, const float* snow_b, double* acc_rain,
-                             double* acc_snow, cudaStream_t st);
+                     float c2s, unsigned long long* diag, cudaStream_t st, double* acc_rain = nullptr,
+                     double* acc_snow = nullptr);
+// (acc_rain / acc_snow non-null: resident mode -- rain / snow are ignored and the call's precipitation is
+//  added straight to domain%accumulated_precipitation / accumulated_snowfall, REAL*8, mp_driver.f90:587-595)
 
 }  // namespace icar

@@ -159,6 +159,7 @@ struct Args {
     const float *pii, *p, *dz;
     float *rainnc, *snownc, *snowncv, *graupelnc, *graupelncv, *sr;
     const float* rainncv;
+    double *acc_precip, *acc_snow, *acc_graupel;      // resident mode: REAL*8 accumulators (mp_driver.f90:587-595)
 };
 
 // Shared memory (doubles first): s_n0[nz][TX] double | s_f[7][(nz+1)][TX] float | s_i[10][TX] int
@@ -195,6 +196,12 @@ k_mp_thompson(Geom g, ThConst c, ThTables tb, Args A, int ld2, float dt, MpTiles
         ni1d = A.ni[a]; nr1d = A.nr[a];
     }
     if (kk == 0) { for (int n = 0; n < 10; ++n) s_i[n * TX + tx] = 0; }
+    // (accumulators are read here, not at the end: a dependent load in a CTA's last instructions is exposed)
+    double acc0[3] = {0.0, 0.0, 0.0};
+    if (live && kk == 0 && A.acc_precip) {
+        const size_t a2 = (size_t)i + (size_t)ld2 * (size_t)j;
+        acc0[0] = A.acc_precip[a2]; acc0[1] = A.acc_snow[a2]; acc0[2] = A.acc_graupel[a2];
+    }
     __syncthreads();
 
     const float dtsave = dt, odt = 1.f / dt, odts = 1.f / dtsave;
@@ -1016,6 +1023,11 @@ k_mp_thompson(Geom g, ThConst c, ThTables tb, Args A, int ld2, float dt, MpTiles
         if (kk == 0) {
             const float pptrain = ppt[0], pptice = ppt[1], pptsnow = ppt[2], pptgraul = ppt[3];
             const size_t a2 = (size_t)i + (size_t)ld2 * (size_t)j;
+            if (A.acc_precip) {        // the per-call arrays start at zero (mp_driver.f90:411-413): 0 + ppt..., then REAL*8 +=
+                A.acc_precip[a2] = acc0[0] + (double)(0.f + pptrain + pptsnow + pptgraul + pptice);
+                A.acc_snow[a2] = acc0[1] + (double)(0.f + pptsnow + pptice);
+                A.acc_graupel[a2] = acc0[2] + (double)(0.f + pptgraul);
+            }
             if (A.rainnc) A.rainnc[a2] = A.rainnc[a2] + pptrain + pptsnow + pptgraul + pptice;
             if (A.snownc) A.snownc[a2] = A.snownc[a2] + pptsnow + pptice;
             if (A.snowncv) A.snowncv[a2] = pptsnow + pptice;
@@ -1032,7 +1044,8 @@ int th_driver_launch(const Geom& g, const ThConst& c, const ThTables& tb, float*
                      float* qs, float* qg, float* ni, float* nr, float* th, const float* pii, const float* p,
                      const float* dz, float dt, float* rainnc, const float* rainncv, float* snownc, float* snowncv,
                      float* graupelnc, float* graupelncv, float* sr, int ld2, const MpTiles& tiles, int kts, int kte,
-                     unsigned long long* diag, cudaStream_t st) {
+                     unsigned long long* diag, cudaStream_t st, double* acc_precip, double* acc_snow,
+                     double* acc_graupel) {
     int gx = 0, gy = 0;
     for (int t = 0; t < tiles.n; ++t) {
         if (tiles.ite[t] < tiles.its[t] || tiles.jte[t] < tiles.jts[t]) continue;
@@ -1044,7 +1057,8 @@ int th_driver_launch(const Geom& g, const ThConst& c, const ThTables& tb, float*
     const int nk = kte - kts + 1;
     if (nk < 1 || nk > 64) return -1;                       // one thread per level, at most 64 levels
     const int nkt = (nk * TX + 31) / 32 * 32 / TX;          // whole warps
-    Args A{qv, qc, qr, qi, qs, qg, ni, nr, th, pii, p, dz, rainnc, snownc, snowncv, graupelnc, graupelncv, sr, rainncv};
+    Args A{qv, qc, qr, qi, qs, qg, ni, nr, th, pii, p, dz, rainnc, snownc, snowncv, graupelnc, graupelncv, sr, rainncv,
+           acc_precip, acc_snow, acc_graupel};
     dim3 block(TX, nkt), grid(gx, gy, tiles.n);
     const size_t smem = (size_t)nk * TX * sizeof(double) + (size_t)7 * (nk + 1) * TX * sizeof(float) + (size_t)10 * TX * sizeof(int);
     static const bool occ1 = std::getenv("ICAR_TH_OCC1") != nullptr;      // (tuning aid)

@@ -65,6 +65,9 @@ int th_driver_launch(const Geom& g, const ThConst& c, const ThTables& tb, float*
                      float* qs, float* qg, float* ni, float* nr, float* th, const float* pii, const float* p,
                      const float* dz, float dt, float* rainnc, const float* rainncv, float* snownc, float* snowncv,
                      float* graupelnc, float* graupelncv, float* sr, int ld2, const MpTiles& tiles, int kts, int kte,
-                     unsigned long long* diag, cudaStream_t st);
+                     unsigned long long* diag, cudaStream_t st, double* acc_precip = nullptr, double* acc_snow = nullptr,
+                     double* acc_graupel = nullptr);
+// (acc_* non-null: resident mode -- the call's precipitation / snowfall / graupel are added straight to the
+//  REAL*8 accumulators of domain_t, mp_driver.f90:587-595; rainnc / snownc / graupelnc are then null)
 
 }  // namespace icar
