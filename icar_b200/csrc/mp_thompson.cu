@@ -29,7 +29,10 @@ namespace icar {
 
 namespace {
 
-constexpr int TX = 8;      // columns per CTA: 8 floats = one 32-byte sector per level row
+#ifndef ICAR_TH_TX
+#define ICAR_TH_TX 8
+#endif
+constexpr int TX = ICAR_TH_TX;      // columns per CTA: 8 floats = one 32-byte sector per level row
 
 constexpr float T_0 = 273.15f, PI2 = 3.1415926536f;
 constexpr float rho_w = 1000.0f;
@@ -45,7 +48,7 @@ __device__ const float k_sa[10] = {5.065339f, -0.062659f, -3.032362f, 0.029469f,
 __device__ const float k_sb[10] = {0.476221f, -0.015896f, 0.165977f, 0.007468f, -0.000141f,
                                    0.060366f, 0.000079f, 0.000594f, 0.0f, -0.003577f};
 
-__device__ __forceinline__ float rslf(float P, float T) {                  // :3776-3805
+__device__ __noinline__ float rslf(float P, float T) {                  // :3776-3805
     const float C0 = .611583699E03f, C1 = .444606896E02f, C2 = .143177157E01f, C3 = .264224321E-1f,
                 C4 = .299291081E-3f, C5 = .203154182E-5f, C6 = .702620698E-8f, C7 = .379534310E-11f,
                 C8 = -.321582393E-13f;
@@ -53,7 +56,7 @@ __device__ __forceinline__ float rslf(float P, float T) {                  // :3
     const float ESL = C0 + X * (C1 + X * (C2 + X * (C3 + X * (C4 + X * (C5 + X * (C6 + X * (C7 + X * C8)))))));
     return .622f * ESL / (P - ESL);
 }
-__device__ __forceinline__ float rsif(float P, float T) {                  // :3810-3835
+__device__ __noinline__ float rsif(float P, float T) {                  // :3810-3835
     const float C0 = .609868993E03f, C1 = .499320233E02f, C2 = .184672631E01f, C3 = .402737184E-1f,
                 C4 = .565392987E-3f, C5 = .521693933E-5f, C6 = .307839583E-7f, C7 = .105785160E-9f,
                 C8 = .161444444E-12f;
@@ -67,8 +70,16 @@ __device__ __forceinline__ float rsif(float P, float T) {                  // :3
 // x**3, (lamr+fv_r)**(-5) ... -- which a few multiplications evaluate to within a few ulp(double) of pow()
 // (also quarter-integer exponents such as oge1 = 1/4, cre(12) = 2.5, cre(7) = 3.5, through sqrt);
 // the general case stays a call (not inlined: ~250 instructions each, the kernel has 40 call sites).
+// Code size matters here: with every helper inlined the kernel was 17 000 SASS instructions (272 KB) and
+// "no instruction" (instruction-cache misses) was the top warp stall, 6.8 warps per issue slot.  The
+// transcendental functions and the helpers that contain them are therefore real calls.
 __device__ __noinline__ double dpow_general(double x, double y) { return pow(x, y); }
-__device__ __forceinline__ double dpow(double x, double y) {
+__device__ __noinline__ float fpow(float x, float y) { return powf(x, y); }
+__device__ __noinline__ float fexp(float x) { return expf(x); }
+__device__ __noinline__ float flog10(float x) { return log10f(x); }
+__device__ __noinline__ double dlog(double x) { return log(x); }
+__device__ __noinline__ int nint_f(float x) { return (int)lroundf(x); }
+__device__ __noinline__ double dpow(double x, double y) {
     const double y4 = 4.0 * y;
     if (y4 == rint(y4) && fabs(y) <= 8.0) {        // uniform across the grid: y is a constant
         // y = n + f/4: x**n by multiplication, x**(1/2) and x**(1/4) by (correctly rounded) square roots
@@ -88,15 +99,15 @@ __device__ __forceinline__ double dpow(double x, double y) {
 }
 
 // 10.**n for integer n the way gfortran evaluates it (libgcc __powisf2)
-__device__ __forceinline__ float pow10i(int m) {
+__device__ __noinline__ float pow10i(int m) {
     unsigned n = m < 0 ? 0u - (unsigned)m : (unsigned)m;
     float x = 10.f, y = (n & 1u) ? x : 1.f;
     while (n >>= 1) { x = x * x; if (n & 1u) y *= x; }
     return m < 0 ? 1.f / y : y;
 }
 // index into a decade table, :1562-1676
-__device__ __forceinline__ int decade_index(float x, int n2, int ntb) {
-    const int nic = (int)lroundf(log10f(x));
+__device__ __noinline__ int decade_index(float x, int n2, int ntb) {
+    const int nic = (int)lroundf(flog10(x));
     int n = nic - 1;
     for (int nn = nic - 1; nn <= nic + 1; ++nn) {
         n = nn;
@@ -106,7 +117,7 @@ __device__ __forceinline__ int decade_index(float x, int n2, int ntb) {
     const int idx = (int)(x / pow10i(n)) + 10 * (n - n2) - (n - n2);
     return max(1, min(idx, ntb));
 }
-__device__ __forceinline__ int decade_index_d(double x, int n2, int ntb) {
+__device__ __noinline__ int decade_index_d(double x, int n2, int ntb) {
     const int nic = (int)lround(log10(x));
     int n = nic - 1;
     for (int nn = nic - 1; nn <= nic + 1; ++nn) {
@@ -123,11 +134,11 @@ __device__ __forceinline__ float sa_poly(const float* s, float tc0, float x) {
            s[7] * tc0 * x * x + s[8] * tc0 * tc0 * tc0 + s[9] * x * x * x;
 }
 // a_ * smo2**b_ for the `x`-th moment (e.g. :1413-1423)
-__device__ __forceinline__ float snow_moment(float tc0, float x, float smo2) {
+__device__ __noinline__ float snow_moment(float tc0, float x, float smo2) {
     const float loga_ = sa_poly(k_sa, tc0, x);
-    const float a_ = powf(10.0f, loga_);
+    const float a_ = fpow(10.0f, loga_);
     const float b_ = sa_poly(k_sb, tc0, x);
-    return a_ * powf(smo2, b_);
+    return a_ * fpow(smo2, b_);
 }
 
 __device__ __forceinline__ size_t t4(int i, int j, int k, int m, int n1, int n2, int n3) {   // 1-based, column-major
@@ -136,8 +147,8 @@ __device__ __forceinline__ size_t t4(int i, int j, int k, int m, int n1, int n2,
 
 // rain mass/number balance (:1283-1293, :2185-2197, :2286-2296): returns mvd_r; in the two clamped
 // branches nr is recomputed and `clamped` set
-__device__ __forceinline__ float rain_balance(const ThConst& c, float rr, float& nr, bool& clamped) {
-    double lamr = powf((c.am_r * c.crg[2] * c.org2 * nr / rr), c.obmr);
+__device__ __noinline__ float rain_balance(const ThConst& c, float rr, float& nr, bool& clamped) {
+    double lamr = fpow((c.am_r * c.crg[2] * c.org2 * nr / rr), c.obmr);
     float mvd = (float)((3.0f + c.o.mu_r + 0.672f) / lamr);
     clamped = false;
     if (mvd > 2.5E-3f) {
@@ -218,7 +229,7 @@ k_mp_thompson(Geom g, ThConst c, ThTables tb, Args A, int ld2, float dt, MpTiles
         ri = qi1d * rho;
         ni = fmaxf(R2, ni1d * rho);
         L_qi = true;
-        double lami = powf((c.am_i * c.cig[1] * c.oig1 * ni / ri), c.obmi);
+        double lami = fpow((c.am_i * c.cig[1] * c.oig1 * ni / ri), c.obmi);
         const double ilami = 1. / lami;
         const float xDi = (float)((bm_i + mu_i + 1.f) * ilami);
         if (xDi < 20.E-6f) {
@@ -252,7 +263,7 @@ k_mp_thompson(Geom g, ThConst c, ThTables tb, Args A, int ld2, float dt, MpTiles
     if (fabsf(ssatw) < eps) ssatw = 0.0f;
     if (fabsf(ssati) < eps) ssati = 0.0f;
     if (ssati > 0.0f) micro = true;
-    float diffu = 2.11E-5f * powf((temp / 273.15f), 1.94f) * (101325.f / pres);
+    float diffu = 2.11E-5f * fpow((temp / 273.15f), 1.94f) * (101325.f / pres);
     float visco = (tempc >= 0.0f) ? (1.718f + 0.0049f * tempc) * 1.0E-5f
                                   : (1.718f + 0.0049f * tempc - 1.2E-5f * tempc * tempc) * 1.0E-5f;
     float ocp = 1.f / (Cp2 * (1.f + 0.887f * qv));
@@ -282,22 +293,22 @@ k_mp_thompson(Geom g, ThConst c, ThTables tb, Args A, int ld2, float dt, MpTiles
         smob = rs * c.oams;
         if (bm_s > (2.0f - 1.e-3f) && bm_s < (2.0f + 1.e-3f)) smo2 = smob;
         else {
-            const float loga_ = sa_poly(k_sa, tc0, bm_s), a_ = powf(10.0f, loga_), b_ = sa_poly(k_sb, tc0, bm_s);
-            smo2 = powf((smob / a_), (1.f / b_));
+            const float loga_ = sa_poly(k_sa, tc0, bm_s), a_ = fpow(10.0f, loga_), b_ = sa_poly(k_sb, tc0, bm_s);
+            smo2 = fpow((smob / a_), (1.f / b_));
         }
         {   // 0th moment :1394-1397
             const float loga_ = k_sa[0] + k_sa[1] * tc0 + k_sa[4] * tc0 * tc0 + k_sa[8] * tc0 * tc0 * tc0;
-            const float a_ = powf(10.0f, loga_);
+            const float a_ = fpow(10.0f, loga_);
             const float b_ = k_sb[0] + k_sb[1] * tc0 + k_sb[4] * tc0 * tc0 + k_sb[8] * tc0 * tc0 * tc0;
-            smo0 = a_ * powf(smo2, b_);
+            smo0 = a_ * fpow(smo2, b_);
         }
         {   // 1st moment :1400-1410
             const float loga_ = k_sa[0] + k_sa[1] * tc0 + k_sa[2] + k_sa[3] * tc0 + k_sa[4] * tc0 * tc0 + k_sa[5] +
                                 k_sa[6] * tc0 * tc0 + k_sa[7] * tc0 + k_sa[8] * tc0 * tc0 * tc0 + k_sa[9];
-            const float a_ = powf(10.0f, loga_);
+            const float a_ = fpow(10.0f, loga_);
             const float b_ = k_sb[0] + k_sb[1] * tc0 + k_sb[2] + k_sb[3] * tc0 + k_sb[4] * tc0 * tc0 + k_sb[5] +
                              k_sb[6] * tc0 * tc0 + k_sb[7] * tc0 + k_sb[8] * tc0 * tc0 * tc0 + k_sb[9];
-            smo1 = a_ * powf(smo2, b_);
+            smo1 = a_ * fpow(smo2, b_);
         }
         smoc = snow_moment(tc0, c.cse[0], smo2);
         smoe = snow_moment(tc0, c.cse[12], smo2);
@@ -310,10 +321,10 @@ k_mp_thompson(Geom g, ThConst c, ThTables tb, Args A, int ld2, float dt, MpTiles
     auto graupel_rain_slopes = [&]() {
         double N0_exp = 0.0;
         if (active) {
-            const float xslw1 = (temp < 270.65f && L_qr && mvd_r > 100.E-6f) ? 4.01f + log10f(mvd_r) : 0.01f;
-            const float ygra1 = 4.31f + log10f(fmaxf(5.E-5f, rg));
+            const float xslw1 = (temp < 270.65f && L_qr && mvd_r > 100.E-6f) ? 4.01f + flog10(mvd_r) : 0.01f;
+            const float ygra1 = 4.31f + flog10(fmaxf(5.E-5f, rg));
             const float zans1 = 3.1f + (100.f / (300.f * xslw1 * ygra1 / (10.f / xslw1 + 1.f + 0.25f * ygra1) + 30.f + 10.f * ygra1));
-            N0_exp = powf(10.f, (zans1));
+            N0_exp = fpow(10.f, (zans1));
             N0_exp = fmax((double)gonv_min, fmin(N0_exp, (double)gonv_max));
         }
         __syncthreads();                       // previous readers of s_n0 are done
@@ -321,13 +332,14 @@ k_mp_thompson(Geom g, ThConst c, ThTables tb, Args A, int ld2, float dt, MpTiles
         __syncthreads();
         if (active) {
             double N0_min = gonv_max;
+#pragma unroll 1
             for (int q = kk; q < nk; ++q) N0_min = fmin(s_n0[q * TX + tx], N0_min);
             N0_exp = N0_min;
             const double lam_exp = dpow((N0_exp * c.am_g * c.cgg[0] / rg), (double)c.oge1);
-            const double lamg = lam_exp * powf((c.cgg[2] * c.ogg2 * c.ogg1), c.obmg);
+            const double lamg = lam_exp * fpow((c.cgg[2] * c.ogg2 * c.ogg1), c.obmg);
             ilamg = 1. / lamg;
             N0_g = N0_exp / (c.cgg[1] * lam_exp) * dpow(lamg, (double)c.cge[1]);
-            const double lamr = powf((c.am_r * c.crg[2] * c.org2 * nr / rr), c.obmr);
+            const double lamr = fpow((c.am_r * c.crg[2] * c.org2 * nr / rr), c.obmr);
             ilamr = 1. / lamr;
             mvd_r = (float)((3.0f + c.o.mu_r + 0.672f) / lamr);
             N0_r = nr * c.org2 * dpow(lamr, (double)c.cre[1]);
@@ -339,17 +351,17 @@ k_mp_thompson(Geom g, ThConst c, ThTables tb, Args A, int ld2, float dt, MpTiles
     if (active) {
         // ---------------------------------------------------------- warm rain (:1500-1544)
         if (L_qr && mvd_r > D0r) {
-            const float Ef_rr = 2.0f - expf(2300.0f * (mvd_r - 1600.0E-6f));
+            const float Ef_rr = 2.0f - fexp(2300.0f * (mvd_r - 1600.0E-6f));
             pnr_rcr = Ef_rr * 4.f * nr * rr;
         }
         mvd_c = D0c;
         if (L_qc) {
-            const float xDc = fmaxf(D0c * 1.E6f, (powf((rc / (c.am_r * c.o.Nt_c)), c.obmr)) * 1.E6f);
-            const double lamc = powf((c.o.Nt_c * c.am_r * c.ccg[1] * c.ocg1 / rc), c.obmr);
+            const float xDc = fmaxf(D0c * 1.E6f, (fpow((rc / (c.am_r * c.o.Nt_c)), c.obmr)) * 1.E6f);
+            const double lamc = fpow((c.o.Nt_c * c.am_r * c.ccg[1] * c.ocg1 / rc), c.obmr);
             mvd_c = (float)((3.0f + c.mu_c + 0.672f) / lamc);
             if (rc > 0.01e-3f) {
-                const float Dc_g = (float)((powf((c.ccg[2] * c.ocg2), c.obmr) / lamc) * 1.E6f);
-                const float Dc_b = powf((xDc * xDc * xDc * Dc_g * Dc_g * Dc_g - xDc * xDc * xDc * xDc * xDc * xDc), (1.f / 6.f));
+                const float Dc_g = (float)((fpow((c.ccg[2] * c.ocg2), c.obmr) / lamc) * 1.E6f);
+                const float Dc_b = fpow((xDc * xDc * xDc * Dc_g * Dc_g * Dc_g - xDc * xDc * xDc * xDc * xDc * xDc), (1.f / 6.f));
                 const float zeta1 = 0.5f * ((6.25E-6f * xDc * Dc_b * Dc_b * Dc_b - 0.4f) + fabsf(6.25E-6f * xDc * Dc_b * Dc_b * Dc_b - 0.4f));
                 const float zeta = 0.027f * rc * zeta1;
                 const float taud = 0.5f * ((0.5f * Dc_b - 7.5f) + fabsf(0.5f * Dc_b - 7.5f)) + R1;
@@ -360,7 +372,7 @@ k_mp_thompson(Geom g, ThConst c, ThTables tb, Args A, int ld2, float dt, MpTiles
             }
             if (L_qr && mvd_r > D0r && mvd_c > D0c) {
                 const double lamr = 1. / ilamr;
-                int idx = 1 + (int)(nbins * log(mvd_r / c.Dr1) / log(c.Drn / c.Dr1));
+                int idx = 1 + (int)(nbins * dlog(mvd_r / c.Dr1) / dlog(c.Drn / c.Dr1));
                 idx = min(idx, nbins);
                 const int jc = min((int)(mvd_c * 1.E6f), nbins);          // (upper clamp: memory safety only)
                 const float Ef_rw = (float)tb.t[T_Efrw][(idx - 1) + nbins * (jc - 1)];
@@ -372,7 +384,7 @@ k_mp_thompson(Geom g, ThConst c, ThTables tb, Args A, int ld2, float dt, MpTiles
         // ---------------------------------------------------------- frozen species (:1550-2009)
         vts_boost = 1.5f;
         tempc = temp - 273.15f;
-        const int idx_tc = max(1, min((int)lroundf(-tempc), 45));
+        const int idx_tc = max(1, min(nint_f(-tempc), 45));
         int idx_t = (int)((tempc - 2.5f) / 5.f) - 1;
         idx_t = max(1, -idx_t);
         idx_t = min(idx_t, ntb_t);
@@ -383,7 +395,7 @@ k_mp_thompson(Geom g, ThConst c, ThTables tb, Args A, int ld2, float dt, MpTiles
         if (rr > 1.e-6f) {
             idx_r = decade_index(rr, c.nir2, ntb_r);
             const double lamr = 1. / ilamr;
-            const double lam_exp = lamr * powf((c.crg[2] * c.org2 * c.org1), bm_r);
+            const double lam_exp = lamr * fpow((c.crg[2] * c.org2 * c.org1), bm_r);
             const double N0_exp = c.org1 * rr / c.am_r * dpow(lam_exp, (double)c.cre[0]);
             idx_r1 = decade_index_d(N0_exp, c.nir3, ntb_r1);
         }
@@ -391,7 +403,7 @@ k_mp_thompson(Geom g, ThConst c, ThTables tb, Args A, int ld2, float dt, MpTiles
         if (rg > 1.e-5f) {
             idx_g = decade_index(rg, c.nig2, ntb_g);
             const double lamg = 1. / ilamg;
-            const double lam_exp = lamg * powf((c.cgg[2] * c.ogg2 * c.ogg1), bm_g);
+            const double lam_exp = lamg * fpow((c.cgg[2] * c.ogg2 * c.ogg1), bm_g);
             const double N0_exp = c.ogg1 * rg / c.am_g * dpow(lam_exp, (double)c.cge[0]);
             idx_g1 = decade_index_d(N0_exp, c.nig3, ntb_g1);
         }
@@ -415,7 +427,7 @@ k_mp_thompson(Geom g, ThConst c, ThTables tb, Args A, int ld2, float dt, MpTiles
             float xDs = 0.0f;
             if (L_qs) xDs = smoc / smob;
             if (xDs > D0s) {
-                int idx = 1 + (int)(nbins * log(xDs / c.Ds1) / log(c.Dsn / c.Ds1));
+                int idx = 1 + (int)(nbins * dlog(xDs / c.Ds1) / dlog(c.Dsn / c.Ds1));
                 idx = min(idx, nbins);
                 const int jc = min((int)(mvd_c * 1.E6f), nbins);
                 const float Ef_sw = (float)tb.t[T_Efsw][(idx - 1) + nbins * (jc - 1)];
@@ -427,7 +439,7 @@ k_mp_thompson(Geom g, ThConst c, ThTables tb, Args A, int ld2, float dt, MpTiles
                 const float stoke_g = mvd_c * mvd_c * vtg * rho_w / (9.f * visco * xDg);
                 if (xDg > D0g) {
                     float Ef_gw = 0.f;
-                    if (stoke_g >= 0.4f && stoke_g <= 10.f) Ef_gw = 0.55f * log10f(2.51f * stoke_g);
+                    if (stoke_g >= 0.4f && stoke_g <= 10.f) Ef_gw = 0.55f * flog10(2.51f * stoke_g);
                     else if (stoke_g < 0.4f) Ef_gw = 0.0f;
                     else if (stoke_g > 10.f) Ef_gw = 0.77f;
                     prg_gcw = rhof * c.t1_qg_qc * Ef_gw * rc * N0_g * dpow(ilamg, (double)c.cge[8]);
@@ -499,17 +511,17 @@ k_mp_thompson(Geom g, ThConst c, ThTables tb, Args A, int ld2, float dt, MpTiles
                 pni_wfz = fmin(fmin((double)(c.o.Nt_c * odts), pri_wfz / (2.f * xm0i)), pni_wfz);
             }
             if ((ssati >= 0.25f) || (ssatw > eps && temp < 261.15f)) {       // :1820-1827
-                const float xnc = fminf(250.E3f, c.o.TNO * expf(ATO * (T_0 - temp)));
+                const float xnc = fminf(250.E3f, c.o.TNO * fexp(ATO * (T_0 - temp)));
                 const float xni = (float)(ni + (pni_rfz + pni_wfz) * dtsave);
                 pni_inu = 0.5f * (xnc - xni + fabsf(xnc - xni)) * odts;
                 pri_inu = fmin((double)rate_max, xm0i * pni_inu);
                 pni_inu = pri_inu / xm0i;
             }
             if (L_qi) {                                                      // :1830-1863
-                const double lami = powf((c.am_i * c.cig[1] * c.oig1 * ni / ri), c.obmi);
+                const double lami = fpow((c.am_i * c.cig[1] * c.oig1 * ni / ri), c.obmi);
                 const double ilami = 1. / lami;
                 const float xDi = (float)fmax((double)c.D0i, (bm_i + mu_i + 1.f) * ilami);
-                const float xmi = c.am_i * powf(xDi, bm_i);
+                const float xmi = c.am_i * fpow(xDi, bm_i);
                 const float oxmi = 1.f / xmi;
                 pri_ide = C_cube * t1_subl * diffu * ssati * rvs * c.oig1 * c.cig[4] * ni * ilami;
                 const size_t q = (size_t)(idx_i - 1) + (size_t)ntb_i * (size_t)(idx_i1 - 1);
@@ -549,10 +561,10 @@ k_mp_thompson(Geom g, ThConst c, ThTables tb, Args A, int ld2, float dt, MpTiles
                 else prg_gde = fmin(prg_gde, (double)rate_max);
             }
             if (L_qi) {                                                      // :1896-1920
-                const double lami = powf((c.am_i * c.cig[1] * c.oig1 * ni / ri), c.obmi);
+                const double lami = fpow((c.am_i * c.cig[1] * c.oig1 * ni / ri), c.obmi);
                 const double ilami = 1. / lami;
                 const float xDi = (float)fmax((double)c.D0i, (bm_i + mu_i + 1.f) * ilami);
-                const float xmi = c.am_i * powf(xDi, bm_i);
+                const float xmi = c.am_i * fpow(xDi, bm_i);
                 const float oxmi = 1.f / xmi;
                 if (rs >= 1.e-5f) {
                     prs_sci = c.t1_qs_qi * rhof * c.o.Ef_si * ri * smoe;
@@ -589,7 +601,7 @@ k_mp_thompson(Geom g, ThConst c, ThTables tb, Args A, int ld2, float dt, MpTiles
                 prr_sml = (tempc * tcond - lvap0 * diffu * delQvs) * (c.t1_qs_me * smo1 + c.t2_qs_me * rhof2 * vsc2 * smof);
                 prr_sml = prr_sml + 4218.f * c.olfus * tempc * (prr_rcs + prs_scw);
                 prr_sml = fmin((double)(rs * odts), fmax(0., prr_sml));
-                pnr_sml = smo0 / rs * prr_sml * powf(10.0f, (-0.75f * tempc));
+                pnr_sml = smo0 / rs * prr_sml * fpow(10.0f, (-0.75f * tempc));
                 pnr_sml = fmin((double)(smo0 * odts), pnr_sml);
                 if (tempc > 3.5f || rs < 0.005E-3f) pnr_sml = 0.0;
                 if (ssati < 0.f) {
@@ -601,7 +613,7 @@ k_mp_thompson(Geom g, ThConst c, ThTables tb, Args A, int ld2, float dt, MpTiles
                 prr_gml = (tempc * tcond - lvap0 * diffu * delQvs) * N0_g *
                           (c.t1_qg_me * dpow(ilamg, (double)c.cge[9]) + c.t2_qg_me * rhof2 * vsc2 * dpow(ilamg, (double)c.cge[10]));
                 prr_gml = fmin((double)(rg * odts), fmax(0., prr_gml));
-                pnr_gml = N0_g * c.cgg[1] * dpow(ilamg, (double)c.cge[1]) / rg * prr_gml * powf(10.0f, (-1.5f * tempc));
+                pnr_gml = N0_g * c.cgg[1] * dpow(ilamg, (double)c.cge[1]) / rg * prr_gml * fpow(10.0f, (-1.5f * tempc));
                 if (tempc > 7.5f || rg < 0.005E-3f) pnr_gml = 0.0;
                 if (ssati < 0.f) {
                     prg_gde = C_cube * t1_subl * diffu * ssati * rvs * N0_g *
@@ -675,7 +687,7 @@ k_mp_thompson(Geom g, ThConst c, ThTables tb, Args A, int ld2, float dt, MpTiles
             const float xri = fmaxf(R1, (qi1d + qiten * dtsave) * rho);
             float xni = fmaxf(R2, (ni1d + niten * dtsave) * rho);
             if (xri > R1) {
-                double lami = powf((c.am_i * c.cig[1] * c.oig1 * xni / xri), c.obmi);
+                double lami = fpow((c.am_i * c.cig[1] * c.oig1 * xni / xri), c.obmi);
                 const double ilami = 1. / lami;
                 const float xDi = (float)((bm_i + mu_i + 1.f) * ilami);
                 if (xDi < 20.E-6f) {
@@ -730,7 +742,7 @@ k_mp_thompson(Geom g, ThConst c, ThTables tb, Args A, int ld2, float dt, MpTiles
         qvs = rslf(pres, temp);
         ssatw = qv / qvs - 1.f;
         if (fabsf(ssatw) < eps) ssatw = 0.0f;
-        diffu = 2.11E-5f * powf((temp / 273.15f), 1.94f) * (101325.f / pres);
+        diffu = 2.11E-5f * fpow((temp / 273.15f), 1.94f) * (101325.f / pres);
         visco = (tempc >= 0.0f) ? (1.718f + 0.0049f * tempc) * 1.0E-5f
                                 : (1.718f + 0.0049f * tempc - 1.2E-5f * tempc * tempc) * 1.0E-5f;
         vsc2 = sqrtf(rho / visco);
@@ -759,8 +771,8 @@ k_mp_thompson(Geom g, ThConst c, ThTables tb, Args A, int ld2, float dt, MpTiles
             smob = rs * c.oams;
             if (bm_s > (2.0f - 1.e-3f) && bm_s < (2.0f + 1.e-3f)) smo2 = smob;
             else {
-                const float loga_ = sa_poly(k_sa, tc0, bm_s), a_ = powf(10.0f, loga_), b_ = sa_poly(k_sb, tc0, bm_s);
-                smo2 = powf((smob / a_), (1.f / b_));
+                const float loga_ = sa_poly(k_sa, tc0, bm_s), a_ = fpow(10.0f, loga_), b_ = sa_poly(k_sb, tc0, bm_s);
+                smo2 = fpow((smob / a_), (1.f / b_));
             }
             smoc = snow_moment(tc0, c.cse[0], smo2);
             smod = snow_moment(tc0, c.cse[13], smo2);
@@ -773,8 +785,8 @@ k_mp_thompson(Geom g, ThConst c, ThTables tb, Args A, int ld2, float dt, MpTiles
         if ((ssatw > eps) || (ssatw < -eps && L_qc)) {
             float clap = (qv - qvs) / (1.f + lvt2 * qvs);
             for (int n = 1; n <= 3; ++n) {
-                const float fcd = qvs * expf(lvt2 * clap) - qv + clap;
-                const float dfcd = qvs * lvt2 * expf(lvt2 * clap) + 1.f;
+                const float fcd = qvs * fexp(lvt2 * clap) - qv + clap;
+                const float dfcd = qvs * lvt2 * fexp(lvt2 * clap) + 1.f;
                 clap = clap - fcd / dfcd;
             }
             const float xrc = rc + clap;
@@ -796,7 +808,7 @@ k_mp_thompson(Geom g, ThConst c, ThTables tb, Args A, int ld2, float dt, MpTiles
             const float otemp = 1.f / temp;
             rhof = sqrtf(c.rho_not / rho);
             rhof2 = sqrtf(rhof);
-            diffu = 2.11E-5f * powf((temp / 273.15f), 1.94f) * (101325.f / pres);
+            diffu = 2.11E-5f * fpow((temp / 273.15f), 1.94f) * (101325.f / pres);
             visco = (tempc >= 0.0f) ? (1.718f + 0.0049f * tempc) * 1.0E-5f
                                     : (1.718f + 0.0049f * tempc - 1.2E-5f * tempc * tempc) * 1.0E-5f;
             vsc2 = sqrtf(rho / visco);
@@ -843,12 +855,12 @@ k_mp_thompson(Geom g, ThConst c, ThTables tb, Args A, int ld2, float dt, MpTiles
     if (active) {
         rhof = sqrtf(c.rho_not / rho);
         if (rr > R1) {
-            const double lamr = powf((c.am_r * c.crg[2] * c.org2 * nr / rr), c.obmr);
+            const double lamr = fpow((c.am_r * c.crg[2] * c.org2 * nr / rr), c.obmr);
             vtrk = (float)(rhof * av_r * c.crg[5] * c.org3 * dpow(lamr, (double)c.cre[2]) * (dpow((lamr + fv_r), (double)(-c.cre[5]))));
             vtnrk = (float)(rhof * av_r * c.crg[6] / c.crg[11] * dpow(lamr, (double)c.cre[11]) * (dpow((lamr + fv_r), (double)(-c.cre[6]))));
         }
         if (ri > R1) {
-            const double lami = powf((c.am_i * c.cig[1] * c.oig1 * ni / ri), c.obmi);
+            const double lami = fpow((c.am_i * c.cig[1] * c.oig1 * ni / ri), c.obmi);
             const double ilami = 1. / lami;
             vtik = (float)(rhof * c.o.av_i * c.cig[2] * c.oig2 * dpow(ilami, (double)bv_i));
             vtnik = (float)(rhof * c.o.av_i * c.cig[5] / c.cig[6] * dpow(ilami, (double)bv_i));
@@ -865,6 +877,7 @@ k_mp_thompson(Geom g, ThConst c, ThTables tb, Args A, int ld2, float dt, MpTiles
     __syncthreads();
     // a level without the species takes the value of the nearest level above that has it (else 0)
     auto inherit = [&](int plane, unsigned bit, float own) -> float {
+#pragma unroll 1
         for (int q = kk; q < nk; ++q)
             if (__float_as_uint(s_f[6 * PL + q * TX + tx]) & bit) return (q == kk) ? own : s_f[plane * PL + q * TX + tx];
         return 0.f;
@@ -877,12 +890,12 @@ k_mp_thompson(Geom g, ThConst c, ThTables tb, Args A, int ld2, float dt, MpTiles
             const float Mrat = 1.f / xDs;
             float ils1 = 1.f / (Mrat * Lam0 + c.o.fv_s);
             float ils2 = 1.f / (Mrat * Lam1 + c.o.fv_s);
-            const float t1_vts = Kap0 * c.csg[3] * powf(ils1, c.cse[3]);
-            const float t2_vts = Kap1 * powf(Mrat, mu_s) * c.csg[9] * powf(ils2, c.cse[9]);
+            const float t1_vts = Kap0 * c.csg[3] * fpow(ils1, c.cse[3]);
+            const float t2_vts = Kap1 * fpow(Mrat, mu_s) * c.csg[9] * fpow(ils2, c.cse[9]);
             ils1 = 1.f / (Mrat * Lam0);
             ils2 = 1.f / (Mrat * Lam1);
-            const float t3_vts = Kap0 * c.csg[0] * powf(ils1, c.cse[0]);
-            const float t4_vts = Kap1 * powf(Mrat, mu_s) * c.csg[6] * powf(ils2, c.cse[6]);
+            const float t3_vts = Kap0 * c.csg[0] * fpow(ils1, c.cse[0]);
+            const float t4_vts = Kap1 * fpow(Mrat, mu_s) * c.csg[6] * fpow(ils2, c.cse[6]);
             const float vts = rhof * c.o.av_s * (t1_vts + t2_vts) / (t3_vts + t4_vts);
             vtsk = (temp > T_0) ? fmaxf(vts * vts_boost, vtrk) : vts * vts_boost;
         }
@@ -917,12 +930,12 @@ k_mp_thompson(Geom g, ThConst c, ThTables tb, Args A, int ld2, float dt, MpTiles
     for (int s = 0; s < 4; ++s) {
         const int ns = s_i[(1 + s) * TX + tx];
         onstep[s] = (ns > 0) ? 1.f / (float)ns : 1.0f;
-        nstep[s] = active ? (int)lroundf(1.f / onstep[s]) : 0;
+        nstep[s] = active ? nint_f(1.f / onstep[s]) : 0;
         int ks = max(1, s_i[(5 + s) * TX + tx]);
         if (ks == nk) ks = nk - 1;
         ksed1[s] = ks;
         // uniform trip count for the CTA: the largest sub-step count of its columns
-        int m = col_ok && (s_i[tx] != 0) ? (int)lroundf(1.f / onstep[s]) : 0;
+        int m = col_ok && (s_i[tx] != 0) ? nint_f(1.f / onstep[s]) : 0;
         m = __reduce_max_sync(0xffffffffu, m);             // every warp holds all TX columns (TX divides 32)
         nmax[s] = m;
     }
@@ -990,7 +1003,7 @@ k_mp_thompson(Geom g, ThConst c, ThTables tb, Args A, int ld2, float dt, MpTiles
         ni1d = fmaxf(R2 / rho, ni1d + niten * dt);
         if (qi1d <= R1) { qi1d = 0.0f; ni1d = 0.0f; }
         else {
-            double lami = powf((c.am_i * c.cig[1] * c.oig1 * ni1d / qi1d), c.obmi);
+            double lami = fpow((c.am_i * c.cig[1] * c.oig1 * ni1d / qi1d), c.obmi);
             const double ilami = 1. / lami;
             const float xDi = (float)((bm_i + mu_i + 1.f) * ilami);
             if (xDi < 20.E-6f) lami = c.cie[1] / 20.E-6f;
@@ -1001,7 +1014,7 @@ k_mp_thompson(Geom g, ThConst c, ThTables tb, Args A, int ld2, float dt, MpTiles
         nr1d = fmaxf(R2 / rho, nr1d + nrten * dt);
         if (qr1d <= R1) { qr1d = 0.0f; nr1d = 0.0f; }
         else {
-            double lamr = powf((c.am_r * c.crg[2] * c.org2 * nr1d / qr1d), c.obmr);
+            double lamr = fpow((c.am_r * c.crg[2] * c.org2 * nr1d / qr1d), c.obmr);
             float mv = (float)((3.0f + c.o.mu_r + 0.672f) / lamr);
             if (mv > 2.5E-3f) mv = 2.5E-3f;
             else if (mv < D0r * 0.75f) mv = D0r * 0.75f;
@@ -1055,23 +1068,18 @@ int th_driver_launch(const Geom& g, const ThConst& c, const ThTables& tb, float*
     }
     if (gx == 0 || gy == 0) return 0;
     const int nk = kte - kts + 1;
-    if (nk < 1 || nk > 64) return -1;                       // one thread per level, at most 64 levels
+    if (nk < 1 || nk * TX > 1024) return -1;                // one thread per level
     const int nkt = (nk * TX + 31) / 32 * 32 / TX;          // whole warps
     Args A{qv, qc, qr, qi, qs, qg, ni, nr, th, pii, p, dz, rainnc, snownc, snowncv, graupelnc, graupelncv, sr, rainncv,
            acc_precip, acc_snow, acc_graupel};
     dim3 block(TX, nkt), grid(gx, gy, tiles.n);
     const size_t smem = (size_t)nk * TX * sizeof(double) + (size_t)7 * (nk + 1) * TX * sizeof(float) + (size_t)10 * TX * sizeof(int);
-    static const bool occ1 = std::getenv("ICAR_TH_OCC1") != nullptr;      // (tuning aid)
-    static bool carved = false;
-    if (!carved) {       // (tuning aid) shared-memory carve-out in percent; default: the driver's choice
-        if (const char* e = std::getenv("ICAR_TH_CARVEOUT")) {
-            cudaFuncSetAttribute(k_mp_thompson<320, 2>, cudaFuncAttributePreferredSharedMemoryCarveout, std::atoi(e));
-            cudaFuncSetAttribute(k_mp_thompson<TX * 64, 1>, cudaFuncAttributePreferredSharedMemoryCarveout, std::atoi(e));
-        }
-        carved = true;
-    }
-    if (TX * nkt <= 320 && !occ1) k_mp_thompson<320, 2><<<grid, block, smem, st>>>(g, c, tb, A, ld2, dt, tiles, kts, kte, diag);
-    else k_mp_thompson<TX * 64, 1><<<grid, block, smem, st>>>(g, c, tb, A, ld2, dt, tiles, kts, kte, diag);
+    const int nthreads = TX * nkt;
+#define TH_LAUNCH(MAXT, MINB) k_mp_thompson<MAXT, MINB><<<grid, block, smem, st>>>(g, c, tb, A, ld2, dt, tiles, kts, kte, diag)
+    if (nthreads <= 320) TH_LAUNCH(320, 2);
+    else if (nthreads <= 640) TH_LAUNCH(640, 1);
+    else TH_LAUNCH(1024, 1);
+#undef TH_LAUNCH
     return 1;
 }
 
