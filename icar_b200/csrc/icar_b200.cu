@@ -437,8 +437,12 @@ extern "C" int icar_create(int device, const icar_grid* grid, const icar_options
     ctx->ld2 = ctx->g.ld;
     auto bail = [&](int code) { std::string m = ctx->err; icar_destroy(ctx); g_create_error = m; return code; };
 #define CUB(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { ctx->err = std::string(#call) + ": " + cudaGetErrorString(e__); return bail(ICAR_ERR_CUDA); } } while (0)
+    // the exchange and the boundary strips are short and on the critical path of a multi-image step: they get
+    // the highest stream priority so that their CTAs are scheduled ahead of the interior tile's
+    int prio_lo = 0, prio_hi = 0;
+    CUB(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
     CUB(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
-    CUB(cudaStreamCreateWithFlags(&ctx->comm_stream, cudaStreamNonBlocking));
+    CUB(cudaStreamCreateWithPriority(&ctx->comm_stream, cudaStreamNonBlocking, prio_hi));
     CUB(cudaEventCreateWithFlags(&ctx->ev_packed, cudaEventDisableTiming));
     CUB(cudaEventCreateWithFlags(&ctx->ev_comm, cudaEventDisableTiming));
     CUB(cudaEventCreate(&ctx->ev_t0));
@@ -477,7 +481,7 @@ extern "C" int icar_create(int device, const icar_grid* grid, const icar_options
     CUB(cudaMalloc((void**)&ctx->sr2d, (size_t)ctx->ld2 * ny * sizeof(float)));
     CUB(cudaMemsetAsync(ctx->sr2d, 0, (size_t)ctx->ld2 * ny * sizeof(float), ctx->stream));
     CUB(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
-    CUB(cudaStreamCreateWithFlags(&ctx->aux, cudaStreamNonBlocking));
+    CUB(cudaStreamCreateWithPriority(&ctx->aux, cudaStreamNonBlocking, prio_hi));
     CUB(cudaEventCreateWithFlags(&ctx->ev_aux, cudaEventDisableTiming));
     CUB(cudaMalloc((void**)&ctx->diag, 3 * sizeof(unsigned long long)));
     CUB(cudaMemsetAsync(ctx->diag, 0, 3 * sizeof(unsigned long long), ctx->stream));
@@ -624,10 +628,12 @@ extern "C" int icar_timer_stop(icar_ctx* ctx, float* elapsed_ms) {
 
 // ============================================================================ advect
 
-extern "C" int icar_advect(icar_ctx* ctx, float dt) {
+// part 0: the whole advect(); part 1: what depends on the winds only (wind normalisation, face
+// coefficients) -- a multi-image step queues it before it waits for the halo exchange; part 2: the scalars.
+int advect_impl(icar_ctx* ctx, float dt, int part) {
     if (!ctx) return ICAR_ERR_INVALID;
     CU(cudaSetDevice(ctx->device));
-    { int jr = join_aux(ctx); if (jr) return jr; }
+    if (part != 1) { int jr = join_aux(ctx); if (jr) return jr; }
     if (ctx->opt.advection != 1 && ctx->opt.advection != 2)
         return ICAR_OK;   // advect() does nothing for other values (advection_driver.f90:67-71)
     int rc = need_uploaded(ctx, {ICAR_VAR_U, ICAR_VAR_V, ICAR_VAR_W, ICAR_VAR_JACOBIAN, ICAR_VAR_JACOBIAN_U,
@@ -640,7 +646,7 @@ extern "C" int icar_advect(icar_ctx* ctx, float dt) {
     const float* dz = (const float*)ctx->vars[ICAR_VAR_ADVECTION_DZ];
     const bool mpdata = (ctx->opt.advection == 2);
     // adv_mpdata.f90:500-506 / advect.f90:344-347
-    {
+    if (part != 2) {
         ProfScope ps(ctx, K_WIND_NORMALISE, ctx->stream);
         ctx->launches += staged_wind_normalise<float>(
             g, (const float*)ctx->vars[ICAR_VAR_U], (const float*)ctx->vars[ICAR_VAR_V],
@@ -652,7 +658,7 @@ extern "C" int icar_advect(icar_ctx* ctx, float dt) {
     const int order = mpdata ? ctx->opt.mpdata_order : 1;
     const float* G = jaco;          // jaco*rho with rho == 1 is jaco itself
     if (order > 1 && !ctx->fused) {
-        ctx->launches += staged_wn_G<float>(g, ctx->W, dz, jaco, rho, ctx->Wn, rho ? ctx->G : nullptr, ctx->stream);
+        if (part != 2) ctx->launches += staged_wn_G<float>(g, ctx->W, dz, jaco, rho, ctx->Wn, rho ? ctx->G : nullptr, ctx->stream);
         if (rho) G = ctx->G;
     }
     if (ctx->fused) {
@@ -666,15 +672,25 @@ extern "C" int icar_advect(icar_ctx* ctx, float dt) {
         cudaEvent_t marks[4];
         if (ctx->prof_on) for (cudaEvent_t& m : marks) m = prof_event(ctx);
         const int nl = fused_advect_all(g, ss, ctx->U, ctx->V, ctx->W, ctx->Wn, jaco, dz, ctx->coef, ctx->stream,
-                                        ctx->prof_on ? marks : nullptr);
+                                        ctx->prof_on ? marks : nullptr, part);
         if (ctx->prof_on) {      // consecutive marks delimit the three kernels
-            ctx->prof_pending.push_back({K_FACE_COEF, marks[0], marks[1]});
-            ctx->prof_pending.push_back({-K_UPWIND_PASS1 - 100, marks[1], marks[2]});    // negative id: the start event is the
-            ctx->prof_pending.push_back({-K_CORRECTOR - 100, marks[2], marks[3]});       // previous record's stop event
+            if (part == 1) {
+                ctx->prof_pending.push_back({K_FACE_COEF, marks[0], marks[1]});
+                ctx->prof_pool.push_back(marks[2]); ctx->prof_pool.push_back(marks[3]);
+            } else if (part == 2) {
+                ctx->prof_pool.push_back(marks[0]);
+                ctx->prof_pending.push_back({K_UPWIND_PASS1, marks[1], marks[2]});
+                ctx->prof_pending.push_back({-K_CORRECTOR - 100, marks[2], marks[3]});
+            } else {
+                ctx->prof_pending.push_back({K_FACE_COEF, marks[0], marks[1]});
+                ctx->prof_pending.push_back({-K_UPWIND_PASS1 - 100, marks[1], marks[2]});    // negative id: the start event is the
+                ctx->prof_pending.push_back({-K_CORRECTOR - 100, marks[2], marks[3]});       // previous record's stop event
+            }
         }
         if (nl < 0) return fail(ctx, ICAR_ERR_CUDA, "icar_advect: cannot set up the TMA tensor maps / shared memory of the fused MPDATA kernel");
         ctx->launches += nl;
         CU(cudaGetLastError());
+        if (part == 1) return ICAR_OK;
         for (int n = 0; n < ctx->nadv; ++n) {      // the output buffer becomes the field, the old field the next output
             float* old_field = (float*)ctx->vars[ctx->adv[n]];
             ctx->vars[ctx->adv[n]] = ctx->fout[n];
@@ -682,6 +698,7 @@ extern "C" int icar_advect(icar_ctx* ctx, float dt) {
         }
         return ICAR_OK;
     }
+    if (part == 1) return ICAR_OK;
     // adv_mpdata.f90:512-522: every scalar with vars_to_advect > 0 (mp_simple.f90:116-118)
     ProfScope ps_staged(ctx, K_STAGED_ADVECT3D, ctx->stream);
     for (int s = 0; s < ctx->nadv; ++s) {
@@ -699,6 +716,8 @@ extern "C" int icar_advect(icar_ctx* ctx, float dt) {
     return ICAR_OK;
 }
 
+extern "C" int icar_advect(icar_ctx* ctx, float dt) { return advect_impl(ctx, dt, 0); }
+
 // ============================================================================ mp
 
 // mp() as step() needs it, without the reference's fixed ring geometry.  The only purpose of the
@@ -709,6 +728,7 @@ extern "C" int icar_advect(icar_ctx* ctx, float dt) {
 // Both phases together cover the tile exactly once, like process_halo + process_subdomain(subset).
 int mp_phase(icar_ctx* ctx, float dt_in, int phase, int axis, int h);
 int halo_send_from(icar_ctx* ctx, cudaStream_t producer);
+int advect_impl(icar_ctx* ctx, float dt, int part);
 
 extern "C" int icar_mp(icar_ctx* ctx, float dt_in, int halo, int subset) {
     if (!ctx) return ICAR_ERR_INVALID;
@@ -954,7 +974,11 @@ extern "C" int icar_physics_step(icar_ctx* ctx, float dt) {
             if ((rc = mp_phase(ctx, dt, 0, plan[6], h))) return rc;   // :512  the cells the neighbours need (aux stream)
             if ((rc = halo_send_from(ctx, ctx->aux))) return rc;      // :515  ordered after the strips only
             if ((rc = mp_phase(ctx, dt, 1, plan[6], h))) return rc;   // :523  everything else, overlapping the exchange
+            if ((rc = advect_impl(ctx, dt, 1))) return rc;            // the wind-only part of advect() needs no halo
             if ((rc = icar_halo_retrieve(ctx))) return rc;            // :526
+            if ((rc = advect_impl(ctx, dt, 2))) return rc;            // :529
+            ctx->model_time += (double)dt;                            // :547
+            return ICAR_OK;
         }
         if ((rc = icar_advect(ctx, dt))) return rc;               // :529
     }

@@ -37,7 +37,9 @@ FusedPlan fused_plan(const Geom& g);
 // kernels, for the per-kernel profile (icar_profile_read).
 int fused_advect_all(const Geom& g, const ScalarSet& s, const float* U, const float* V, const float* W,
                      const float* Wn, const float* jaco, const float* dz, const FusedCoef& co,
-                     cudaStream_t st, cudaEvent_t* marks = nullptr);
+                     cudaStream_t st, cudaEvent_t* marks = nullptr, int part = 0);
+// part: 0 = everything; 1 = k_face_coefficients only (depends on the winds, not on the scalars); 2 = pass 1 +
+// corrector only.  A multi-image step queues part 1 before it waits for the halo exchange.
 
 // pass 1 (adv_mpdata.f90:44-105) of every scalar in one launch; also copies the boundary ring to out
 int staged_upwind_all(const Geom& g, const ScalarSet& s, const float* U, const float* V, const float* W,

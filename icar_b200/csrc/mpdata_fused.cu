@@ -532,14 +532,17 @@ FusedPlan fused_plan(const Geom& g) {
 
 int fused_advect_all(const Geom& g, const ScalarSet& s, const float* U, const float* V, const float* W,
                      const float* Wn, const float* jaco, const float* dz, const FusedCoef& co,
-                     cudaStream_t st, cudaEvent_t* marks) {
+                     cudaStream_t st, cudaEvent_t* marks, int part) {
     int launches = 0;
     if (s.n > FUSED_MAX_SCALARS) return -1;
     dim3 cgrid((g.nx + 31) / 32, (g.nz + 3) / 4, (g.ny + 3) / 4);
     if (marks) cudaEventRecord(marks[0], st);
-    k_face_coefficients<<<cgrid, dim3(32, 4, 4), 0, st>>>(g, U, V, Wn, jaco, dz, co);
-    launches += 1;
+    if (part != 2) {
+        k_face_coefficients<<<cgrid, dim3(32, 4, 4), 0, st>>>(g, U, V, Wn, jaco, dz, co);
+        launches += 1;
+    }
     if (marks) cudaEventRecord(marks[1], st);
+    if (part == 1) return launches;
     launches += staged_upwind_all(g, s, U, V, W, dz, jaco, st);   // also copies the boundary ring into `out`
     if (marks) cudaEventRecord(marks[2], st);
 
