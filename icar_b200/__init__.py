@@ -149,7 +149,8 @@ SYMBOLS = (
     "icar_mpdata_set_winds_f64", "icar_mpdata_advect3d_f64", "icar_mp_simple_driver",
     "icar_physics_step_host", "icar_host_register", "icar_host_unregister",
     "icar_default_mp_options", "icar_thompson_init", "icar_thompson_table", "icar_mp_gt_driver",
-    "icar_profile_enable", "icar_profile_read", "icar_diagnostic_update", "icar_compute_dt", "icar_enforce_limits")
+    "icar_profile_enable", "icar_profile_read", "icar_diagnostic_update", "icar_compute_dt", "icar_enforce_limits",
+    "icar_upload_tendency", "icar_apply_forcing")
 
 
 def lib() -> C.CDLL:
@@ -283,6 +284,16 @@ class Domain:
         self._check(lib().icar_compute_dt(self._h, _ptr(dz), C.c_float(cfl_reduction_factor), int(cfl_strictness),
                                           C.byref(out)))
         return out.value
+
+    def upload_tendency(self, name, dqdt):
+        """var%dqdt_3d of a forced variable (per second), same shape as the variable."""
+        name = ALIASES.get(name, name)
+        shape, _ = self._shape(name)
+        self._check(lib().icar_upload_tendency(self._h, VAR[name], _ptr(_f32(dqdt, shape, name))))
+
+    def apply_forcing(self, dt_seconds):
+        """domain%apply_forcing(dt), domain_obj.f90:2383-2448."""
+        self._check(lib().icar_apply_forcing(self._h, C.c_double(dt_seconds)))
 
     def enforce_limits(self):
         """domain%enforce_limits (domain_obj.f90:2228-2243)."""

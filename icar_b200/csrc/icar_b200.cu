@@ -141,6 +141,7 @@ struct icar_ctx {
     double* th_tab[TH_NTABLES] = {};
     double *th_bins = nullptr, *th_aux = nullptr;
     unsigned long long* th_diag = nullptr;     // [0] columns that took the no_micro exit
+    float* dqdt[ICAR_VAR_COUNT] = {};          // var%dqdt_3d of the forced variables (icar_upload_tendency)
     // compute_dt: 4 maxima (uint images of floats) | 1 double for the co_min | nz dz_levels
     unsigned* cfl_max = nullptr;
     double* cfl_dt = nullptr;
@@ -511,6 +512,7 @@ extern "C" int icar_destroy(icar_ctx* ctx) {
     if (ctx->th_bins) cudaFree(ctx->th_bins);
     if (ctx->th_aux) cudaFree(ctx->th_aux);
     if (ctx->th_diag) cudaFree(ctx->th_diag);
+    for (float* t : ctx->dqdt) if (t) cudaFree(t);
     if (ctx->cfl_max) cudaFree(ctx->cfl_max);
     if (ctx->cfl_dt) cudaFree(ctx->cfl_dt);
     if (ctx->cfl_dz) cudaFree(ctx->cfl_dz);
@@ -1440,6 +1442,43 @@ extern "C" int icar_enforce_limits(icar_ctx* ctx) {
     float* fields[ICAR_MAX_EXCHANGED];
     for (int s = 0; s < ctx->nexch; ++s) fields[s] = (float*)ctx->vars[ctx->exch[s]];
     ctx->launches += enforce_limits_launch(ctx->g, fields, ctx->nexch, ctx->stream);
+    CU(cudaGetLastError());
+    return ICAR_OK;
+}
+
+extern "C" int icar_upload_tendency(icar_ctx* ctx, int var, const float* host) {
+    if (!ctx || !host || var < 0 || var >= ICAR_VAR_COUNT || var_shape(var) == D2)
+        return fail(ctx, ICAR_ERR_INVALID, "icar_upload_tendency: bad argument (3-D REAL variables only)");
+    CU(cudaSetDevice(ctx->device));
+    int width, pitch; size_t rows;
+    var_geometry(ctx, var, &width, &pitch, &rows);
+    if (!ctx->dqdt[var]) {
+        const size_t bytes = (var_shape(var) == USTAG) ? (size_t)ctx->g.ldu * ctx->g.nz * ctx->g.ny * sizeof(float)
+                                                       : cell_elems(ctx) * sizeof(float);
+        CU(cudaMalloc((void**)&ctx->dqdt[var], bytes));
+        CU(cudaMemsetAsync(ctx->dqdt[var], 0, bytes, ctx->stream));
+    }
+    int rc = copy_in(ctx, ctx->dqdt[var], host, width, pitch, rows, sizeof(float));
+    if (rc) return rc;
+    CU(cudaStreamSynchronize(ctx->stream));
+    return ICAR_OK;
+}
+
+extern "C" int icar_apply_forcing(icar_ctx* ctx, double dt_seconds) {
+    if (!ctx) return ICAR_ERR_INVALID;
+    CU(cudaSetDevice(ctx->device));
+    { int jr = join_aux(ctx); if (jr) return jr; }
+    const icar_grid& gr = ctx->grid;
+    // this%west_boundary = (ximg == 1) ... (domain_obj.f90:2211-2214): the tile touches that domain edge
+    const bool edges[4] = {gr.ims == gr.ids, gr.ime == gr.ide, gr.jms == gr.jds, gr.jme == gr.jde};
+    for (int var = 0; var < ICAR_VAR_COUNT; ++var) {
+        if (!ctx->dqdt[var]) continue;
+        const bool diagnosed = (var == ICAR_VAR_U || var == ICAR_VAR_V || var == ICAR_VAR_W || var == ICAR_VAR_PRESSURE);
+        int width, pitch; size_t rows;
+        var_geometry(ctx, var, &width, &pitch, &rows);
+        ctx->launches += apply_forcing_launch((float*)ctx->vars[var], ctx->dqdt[var], width, ctx->g.nz,
+                                              (int)(rows / ctx->g.nz), pitch, dt_seconds, !diagnosed, edges, ctx->stream);
+    }
     CU(cudaGetLastError());
     return ICAR_OK;
 }

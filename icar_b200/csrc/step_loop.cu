@@ -48,6 +48,20 @@ k_cfl_maxima(Geom g, const float* __restrict__ u, const float* __restrict__ v, c
     }
 }
 
+__global__ void __launch_bounds__(128)
+k_apply_forcing(float* __restrict__ q, const float* __restrict__ dqdt, int width, int nz, int rows_y, int pitch,
+                double seconds, int boundaries_only, int west, int east, int south, int north) {
+    const int i = blockIdx.x * 128 + threadIdx.x, k = blockIdx.y, j = blockIdx.z;
+    if (i >= width) return;
+    if (boundaries_only) {
+        const bool on_sn = (south && j == 0) || (north && j == rows_y - 1);
+        const bool on_we = ((west && i == 0) || (east && i == width - 1)) && j > 0 && j < rows_y - 1;
+        if (!on_sn && !on_we) return;
+    }
+    const size_t c = (size_t)i + (size_t)pitch * ((size_t)k + (size_t)nz * (size_t)j);
+    q[c] = (float)((double)q[c] + ((double)dqdt[c] * seconds));
+}
+
 struct FieldPtrs { float* p[12]; };
 
 __global__ void __launch_bounds__(128)
@@ -74,6 +88,14 @@ int diagnostic_update_launch(const Geom& g, const float* pressure, const float* 
 int cfl_maxima_launch(const Geom& g, const float* u, const float* v, const float* w, const float* dz_levels,
                       float dx, unsigned* out4, cudaStream_t st) {
     k_cfl_maxima<<<row_grid(g), 128, 0, st>>>(g, u, v, w, dz_levels, dx, out4);
+    return 1;
+}
+
+int apply_forcing_launch(float* q, const float* dqdt, int width, int nz, int rows_y, int pitch, double seconds,
+                         bool boundaries_only, const bool edges[4], cudaStream_t st) {
+    k_apply_forcing<<<dim3((width + 127) / 128, nz, rows_y), 128, 0, st>>>(q, dqdt, width, nz, rows_y, pitch, seconds,
+                                                                          boundaries_only ? 1 : 0, edges[0], edges[1],
+                                                                          edges[2], edges[3]);
     return 1;
 }
 

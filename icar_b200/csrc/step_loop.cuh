@@ -18,6 +18,14 @@ int diagnostic_update_launch(const Geom& g, const float* pressure, const float* 
 int cfl_maxima_launch(const Geom& g, const float* u, const float* v, const float* w, const float* dz_levels,
                       float dx, unsigned* out4, cudaStream_t st);
 
+// domain%apply_forcing (domain_obj.f90:2383-2448) for one 3-D REAL variable: q = q + dqdt * dt%seconds()
+// (the product and the sum are REAL*8, rounded once on assignment).  boundaries_only: force_boundaries =
+// .True. variables (advected scalars) are forced on the domain edges this image owns -- west/east columns
+// for rows jms+1..jme-1 (:2409-2414), whole south/north rows (:2415-2420); edges[4] = {west, east, south, north}.
+// width = nx (+1 for u), rows_y = ny (+1 for v), pitch = row pitch of the variable.
+int apply_forcing_launch(float* q, const float* dqdt, int width, int nz, int rows_y, int pitch, double seconds,
+                         bool boundaries_only, const bool edges[4], cudaStream_t st);
+
 // where (q < 0) q = 0 for every listed field (domain_obj.f90:2228-2243)
 int enforce_limits_launch(const Geom& g, float* const* fields, int nfields, cudaStream_t st);
 

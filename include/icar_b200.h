@@ -188,6 +188,16 @@ int icar_diagnostic_update(icar_ctx* ctx);
 int icar_compute_dt(icar_ctx* ctx, const float* dz_levels, float cfl_reduction_factor, int cfl_strictness,
                     double* dt_seconds);
 
+/* domain%apply_forcing(dt) (src/objects/domain_obj.f90:2383-2448) for the 3-D variables of this path.
+ * icar_upload_tendency stores var%dqdt_3d (the per-second change update_delta_fields derives from two
+ * forcing time steps; same shape as the variable) on the device; icar_apply_forcing then does, for every
+ * variable with a tendency,  q = q + dqdt * dt_seconds  (REAL*8 product and sum, rounded once):
+ * throughout the tile for the diagnosed fields (u, v, w, pressure: force_boundaries = .False.,
+ * domain_obj.f90:178-184, and :2431-2434 for w), on the domain edges this image owns for the advected
+ * scalars (force_boundaries = .True., :2404-2421). */
+int icar_upload_tendency(icar_ctx* ctx, int var, const float* host);
+int icar_apply_forcing(icar_ctx* ctx, double dt_seconds);
+
 /* domain%enforce_limits (src/objects/domain_obj.f90:2228-2243): where (q < 0) q = 0 on every scalar the
  * microphysics scheme allocates. */
 int icar_enforce_limits(icar_ctx* ctx);

@@ -253,3 +253,20 @@ def enforce_limits_np(fields):
     """domain%enforce_limits (src/objects/domain_obj.f90:2228-2243), in place."""
     for a in fields:
         a[a < 0] = 0
+
+
+def apply_forcing_np(q, dqdt, seconds, boundaries_only, west=True, east=True, south=True, north=True):
+    """domain%apply_forcing for one 3-D variable (src/objects/domain_obj.f90:2404-2426), in place:
+    q = q + dqdt * dt%seconds() with the product and sum in REAL*8, rounded once on assignment."""
+    new = (q.astype(np.float64) + dqdt.astype(np.float64) * float(seconds)).astype(np.float32)
+    if not boundaries_only:
+        q[...] = new
+        return
+    if west:
+        q[1:-1, :, 0] = new[1:-1, :, 0]
+    if east:
+        q[1:-1, :, -1] = new[1:-1, :, -1]
+    if south:
+        q[0] = new[0]
+    if north:
+        q[-1] = new[-1]

@@ -84,22 +84,54 @@ def test_enforce_limits_clamps_every_scheme_scalar(gpu_lib, mp):
         np.testing.assert_array_equal(dom.download(k), w, err_msg=k)
 
 
+def test_apply_forcing_diagnosed_fields_and_scalar_boundaries(gpu_lib):
+    st = ideal.make_ideal_case(nx=37, nz=9, ny=13, perturb=True)
+    rng = np.random.default_rng(5)
+    dom = make(gpu_lib, st)
+    names = ("u", "v", "w", "pressure", "th", "qv")
+    tend = {k: (rng.normal(0, 1, st[k].shape) * np.abs(st[k]).max() * 1e-4).astype(np.float32) for k in names}
+    for k in names:
+        dom.upload_tendency(k, tend[k])
+    want = {k: st[k].copy() for k in names}
+    for seconds in (117.3, 36.0):
+        dom.apply_forcing(seconds)
+        for k in names:
+            NP.apply_forcing_np(want[k], tend[k], seconds, boundaries_only=k in ("th", "qv"))
+    for k in names:
+        np.testing.assert_array_equal(dom.download(k), want[k], err_msg=k)
+    # interior of a boundary-forced scalar is untouched, its edges are not
+    assert np.array_equal(want["qv"][1:-1, :, 1:-1], st["qv"][1:-1, :, 1:-1])
+    assert not np.array_equal(want["qv"][0], st["qv"][0])
+    # a scalar without a tendency is left alone
+    np.testing.assert_array_equal(dom.download("qc"), st["qc"])
+
+
 def test_device_resident_loop_body(gpu_lib, oracle):
-    """update_dt -> diagnostic_update -> mp -> advect -> enforce_limits entirely on the device, a few
-    steps, against the same sequence on the CPU (exact arithmetic mode)."""
+    """The loop body of step() (time_step.f90:464-547 with rad/lsm/pbl off): update_dt -> diagnostic_update ->
+    mp -> advect -> apply_forcing -> enforce_limits entirely on the device, a few steps, against the same
+    sequence on the CPU (exact arithmetic mode)."""
     st = ideal.make_ideal_case(nx=48, nz=16, ny=20, perturb=True)
     st["qv"] *= np.float32(3.0)
     ref = ideal.copy_state(st)
     dom = make(gpu_lib, st, exact_arithmetic=1)
+    rng = np.random.default_rng(11)
+    tend = {"u": (rng.normal(0, 2e-3, st["u"].shape)).astype(np.float32),
+            "pressure": (rng.normal(0, 1e-2, st["pressure"].shape)).astype(np.float32),
+            "th": (rng.normal(0, 1e-4, st["th"].shape)).astype(np.float32)}
+    for k, v in tend.items():
+        dom.upload_tendency(k, v)
     for _ in range(3):
         dt = dom.compute_dt(st["dz_levels"])
         dom.diagnostic_update()
         dom.physics_step(dt)
+        dom.apply_forcing(dt)
         dom.enforce_limits()
         dt_ref = NP.compute_dt_np(ref["dx"], ref["u"], ref["v"], ref["w"], ref["dz_levels"], 0.9, 3)
         assert dt == dt_ref
         ref["pii"], ref["rho"] = NP.diagnostic_update_np(ref["pressure"], ref["th"])
         oracle.step_simple(ref, np.float32(dt_ref), np.float32(dt_ref), 2, True)
+        for k, v in tend.items():
+            NP.apply_forcing_np(ref[k], v, dt_ref, boundaries_only=(k == "th"))
         NP.enforce_limits_np([ref[k] for k in ("th", "qv", "qc", "qr", "qs")])
     for k in ("th", "qv", "qc", "qr", "qs"):
         a, b = dom.download(k).astype(np.float64), ref[k].astype(np.float64)
