@@ -178,7 +178,10 @@ __device__ __forceinline__ void mp_conversions(float p, float& t, float& qv, flo
 // Shared memory: two planes [nzp][TX] for q_old / rho (+1 padding level that reads as 0),
 // three column-reduction rows.
 template <int CPT>
-__global__ void __launch_bounds__(TX * 10, 2)
+#ifndef ICAR_MP_MINB
+#define ICAR_MP_MINB 3
+#endif
+__global__ void __launch_bounds__(TX * 10, ICAR_MP_MINB)
 k_mp_simple(Geom g, const float* __restrict__ gp, float* __restrict__ gth,
             const float* __restrict__ gpii, const float* __restrict__ grho,
             float* __restrict__ gqv, float* __restrict__ gqc, float* __restrict__ gqr,

@@ -148,6 +148,84 @@ k_face_coefficients(Geom g, const float* __restrict__ U, const float* __restrict
     co.rjz[c] = fdiv(1.f, dz[c] * Gc);
 }
 
+// The same coefficients, four consecutive cells per thread: every row the stencil touches is fetched as one
+// 16-byte load (+ one scalar for the i-1 / i+4 neighbour), the eleven outputs leave as 16-byte stores.
+// Same expressions as k_face_coefficients (which stays as the reference form, ICAR_COEF_SCALAR=1 selects it).
+struct Row5 { float m, v[4], p; };       // values at i0-1, i0..i0+3, i0+4 of one x-row (0 outside the row)
+__device__ __forceinline__ Row5 load_row(const float* __restrict__ a, size_t c, int i0, int nx, bool need_m, bool need_p) {
+    Row5 r;
+    const float4 q = *reinterpret_cast<const float4*>(a + c);
+    r.v[0] = q.x; r.v[1] = q.y; r.v[2] = q.z; r.v[3] = q.w;
+    r.m = (need_m && i0 > 0) ? a[c - 1] : 0.f;
+    r.p = (need_p && i0 + 4 < nx) ? a[c + 4] : 0.f;
+    return r;
+}
+__device__ __forceinline__ float at5(const Row5& r, int e) { return e < 0 ? r.m : (e > 3 ? r.p : r.v[e]); }
+
+__global__ void __launch_bounds__(128)
+k_face_coefficients_v4(Geom g, const float* __restrict__ U, const float* __restrict__ V,
+                       const float* __restrict__ Wn, const float* __restrict__ G,
+                       const float* __restrict__ dz, FusedCoef co) {
+    const int i0 = 4 * (blockIdx.x * 128 + threadIdx.x), k = blockIdx.y, j = blockIdx.z;
+    if (i0 >= g.ld) return;
+    const size_t ps = g.ps();
+    const int ld = g.ld, nx = g.nx;
+    const size_t c = g.at(i0, k, j);
+    const bool jin = (j > 0 && j < g.ny - 1), kin = (k > 0 && k < g.nz - 1), jlo = j >= 1, kup = k < g.nz - 1;
+    const Row5 zero{0.f, {0.f, 0.f, 0.f, 0.f}, 0.f};
+    // rows: U needs i..i+1, V / Wn / G need i-1..i
+    const Row5 u00 = load_row(U, c, i0, nx, false, true);
+    const Row5 u0m = jlo ? load_row(U, c - ps, i0, nx, false, true) : zero;          // (k, j-1)
+    const Row5 up0 = kup ? load_row(U, c + ld, i0, nx, false, true) : zero;          // (k+1, j)
+    const Row5 v00 = load_row(V, c, i0, nx, true, false);
+    const Row5 v0p = load_row(V, c + ps, i0, nx, true, false);                       // (k, j+1): V has ny+1 planes
+    const Row5 vp0 = kup ? load_row(V, c + ld, i0, nx, false, false) : zero;         // (k+1, j)
+    const Row5 vpp = kup ? load_row(V, c + ld + ps, i0, nx, false, false) : zero;    // (k+1, j+1)
+    const Row5 w00 = load_row(Wn, c, i0, nx, true, false);
+    const Row5 wm0 = (k > 0) ? load_row(Wn, c - ld, i0, nx, true, false) : zero;     // (k-1, j)
+    const Row5 w0m = jlo ? load_row(Wn, c - ps, i0, nx, false, false) : zero;        // (k, j-1)
+    const Row5 wmm = (jlo && k > 0) ? load_row(Wn, c - ld - ps, i0, nx, false, false) : zero;
+    const Row5 g00 = load_row(G, c, i0, nx, true, false);
+    const Row5 g0m = jlo ? load_row(G, c - ps, i0, nx, false, false) : zero;
+    const Row5 gp0 = kup ? load_row(G, c + ld, i0, nx, false, false) : zero;
+    const float4 dz4 = *reinterpret_cast<const float4*>(dz + c);
+    const float dzz[4] = {dz4.x, dz4.y, dz4.z, dz4.w};
+    float o[11][4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        const int i = i0 + e;
+        const bool in = i < nx, iin = (i > 0 && i < nx - 1);
+        const float Gc = g00.v[e];
+        float ax = 0.f, bx = 0.f, cx = 0.f, ay = 0.f, by = 0.f, cy = 0.f, az = 0.f, bz = 0.f, cz = 0.f;
+        if (in && i >= 1) {
+            const float u = u00.v[e], GG = Gc + at5(g00, e - 1), rGG = fdiv(1.f, GG);
+            ax = 0.5f * (fabsf(u) * (1.f - fabsf(u) * (2.f * rGG)));
+            if (jin) bx = 0.5f * (0.5f * u * (0.25f * (v00.v[e] + v0p.v[e] + at5(v00, e - 1) + at5(v0p, e - 1)))) * rGG;
+            if (kin) cx = 0.5f * (0.5f * u * (0.25f * (w00.v[e] + wm0.v[e] + at5(w00, e - 1) + at5(wm0, e - 1)))) * rGG;
+        }
+        if (in && jlo) {
+            const float v = v00.v[e], GG = Gc + g0m.v[e], rGG = fdiv(1.f, GG);
+            ay = 0.5f * (fabsf(v) * (1.f - fabsf(v) * (2.f * rGG)));
+            if (iin) by = 0.5f * (0.5f * v * (0.25f * (at5(u00, e + 1) + at5(u0m, e + 1) + u00.v[e] + u0m.v[e]))) * rGG;
+            if (kin) cy = 0.5f * (0.5f * v * (0.25f * (w00.v[e] + wm0.v[e] + w0m.v[e] + wmm.v[e]))) * rGG;
+        }
+        if (in && kup) {
+            const float w = w00.v[e], GG = gp0.v[e] + Gc, hdz = 0.5f * dzz[e], rGG = fdiv(1.f, GG);
+            az = hdz * (fabsf(w) * (1.f - fabsf(w) * (2.f * rGG)));
+            if (iin) bz = hdz * (0.5f * w * (0.25f * (at5(u00, e + 1) + at5(up0, e + 1) + u00.v[e] + up0.v[e]))) * rGG;
+            if (jin) cz = hdz * (0.5f * w * (0.25f * (v00.v[e] + vp0.v[e] + v0p.v[e] + vpp.v[e]))) * rGG;
+        }
+        o[0][e] = ax; o[1][e] = bx; o[2][e] = cx; o[3][e] = ay; o[4][e] = by; o[5][e] = cy;
+        o[6][e] = az; o[7][e] = bz; o[8][e] = cz;
+        o[9][e] = in ? fdiv(1.f, Gc) : 0.f;
+        o[10][e] = in ? fdiv(1.f, dzz[e] * Gc) : 0.f;
+    }
+    float* const outp[11] = {co.ax, co.bx, co.cx, co.ay, co.by, co.cy, co.az, co.bz, co.cz, co.rj, co.rjz};
+#pragma unroll
+    for (int f = 0; f < 11; ++f)
+        *reinterpret_cast<float4*>(outp[f] + c) = make_float4(o[f][0], o[f][1], o[f][2], o[f][3]);
+}
+
 // ---------------------------------------------------------------------------------------------
 // The fused corrector.  blockDim = (32, NZT); thread (tx, tz) owns cells (i, CPT*tz + c), c < CPT.
 // ---------------------------------------------------------------------------------------------
@@ -538,7 +616,10 @@ int fused_advect_all(const Geom& g, const ScalarSet& s, const float* U, const fl
     dim3 cgrid((g.nx + 31) / 32, (g.nz + 3) / 4, (g.ny + 3) / 4);
     if (marks) cudaEventRecord(marks[0], st);
     if (part != 2) {
-        k_face_coefficients<<<cgrid, dim3(32, 4, 4), 0, st>>>(g, U, V, Wn, jaco, dz, co);
+        if (g.ld % 4 == 0 && !std::getenv("ICAR_COEF_SCALAR"))
+            k_face_coefficients_v4<<<dim3((g.ld / 4 + 127) / 128, g.nz, g.ny), 128, 0, st>>>(g, U, V, Wn, jaco, dz, co);
+        else
+            k_face_coefficients<<<cgrid, dim3(32, 4, 4), 0, st>>>(g, U, V, Wn, jaco, dz, co);
         launches += 1;
     }
     if (marks) cudaEventRecord(marks[1], st);

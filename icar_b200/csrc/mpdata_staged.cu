@@ -54,6 +54,42 @@ __global__ void k_wind_normalise(Geom g, const R* __restrict__ u, const R* __res
     if (Wn) Wn[c] = Wv / dz[c];          // the (W_m/dz) temporary of adv_mpdata.f90:379
 }
 
+// The resident fp32 path (rho == 1, MPDATA operand order, W_m/dz wanted): four consecutive cells per
+// thread with 16-byte loads and stores of the cell-pitched fields (rows start on 128-byte lines; u and
+// jacobian_u rows are nx+1 long and stay scalar).  Same expressions as k_wind_normalise, bit for bit;
+// a pure HBM stream (7 fields in, 4 out).
+__global__ void __launch_bounds__(128)
+k_wind_normalise_v4(Geom g, const float* __restrict__ u, const float* __restrict__ v, const float* __restrict__ w,
+                    const float* __restrict__ ju, const float* __restrict__ jv, const float* __restrict__ jw,
+                    float dt, float dx, float* __restrict__ U, float* __restrict__ V, float* __restrict__ W,
+                    const float* __restrict__ dz, float* __restrict__ Wn) {
+    const int i0 = 4 * (blockIdx.x * 128 + threadIdx.x), k = blockIdx.y, j = blockIdx.z;
+    if (i0 >= g.ld) return;                                   // ld is a multiple of 32: whole float4s
+    const size_t c = g.at(i0, k, j), cu = g.atu(i0, k, j);
+    const float4 v4 = *reinterpret_cast<const float4*>(v + c), jv4 = *reinterpret_cast<const float4*>(jv + c);
+    const float4 w4 = *reinterpret_cast<const float4*>(w + c), jw4 = *reinterpret_cast<const float4*>(jw + c);
+    const float4 dz4 = *reinterpret_cast<const float4*>(dz + c);
+    const float vv[4] = {v4.x, v4.y, v4.z, v4.w}, jvv[4] = {jv4.x, jv4.y, jv4.z, jv4.w};
+    const float ww[4] = {w4.x, w4.y, w4.z, w4.w}, jww[4] = {jw4.x, jw4.y, jw4.z, jw4.w};
+    const float dzz[4] = {dz4.x, dz4.y, dz4.z, dz4.w};
+    float Uo[4], Vo[4], Wo[4], Wno[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        const int i = i0 + e;
+        const bool in = i < g.nx;
+        const float rs = 1.f + 1.f;
+        Uo[e] = (in && i >= 1) ? (u[cu + e] * dt * rs * 0.5f * ju[cu + e] / dx) : 0.f;
+        Vo[e] = (in && j >= 1) ? (vv[e] * dt * rs * 0.5f * jvv[e] / dx) : 0.f;
+        Wo[e] = (k < g.nz - 1) ? (ww[e] * dt * jww[e] * (1.f + 1.f) * 0.5f) : (ww[e] * dt * jww[e] * 1.f);
+        Wno[e] = Wo[e] / dzz[e];
+        if (!in) { Wo[e] = 0.f; Wno[e] = 0.f; }               // row padding: keep it finite
+    }
+    *reinterpret_cast<float4*>(U + c) = make_float4(Uo[0], Uo[1], Uo[2], Uo[3]);
+    *reinterpret_cast<float4*>(V + c) = make_float4(Vo[0], Vo[1], Vo[2], Vo[3]);
+    *reinterpret_cast<float4*>(W + c) = make_float4(Wo[0], Wo[1], Wo[2], Wo[3]);
+    *reinterpret_cast<float4*>(Wn + c) = make_float4(Wno[0], Wno[1], Wno[2], Wno[3]);
+}
+
 // (W_m/dz) and (jaco*rho), the array temporaries of adv_mpdata.f90:379
 template <class R>
 __global__ void k_wn_G(Geom g, const R* __restrict__ W, const R* __restrict__ dz,
@@ -401,6 +437,14 @@ template <class R>
 int staged_wind_normalise(const Geom& g, const R* u, const R* v, const R* w, const R* ju,
                           const R* jv, const R* jw, const R* rho, R dt, R dx, int scheme, R* U,
                           R* V, R* W, cudaStream_t st, const R* dz, R* Wn) {
+    if constexpr (sizeof(R) == 4) {
+        if (!rho && scheme == 2 && Wn && dz && g.ld % 4 == 0 && !std::getenv("ICAR_WIND_SCALAR")) {
+            k_wind_normalise_v4<<<dim3((g.ld / 4 + 127) / 128, g.nz, g.ny), 128, 0, st>>>(
+                g, (const float*)u, (const float*)v, (const float*)w, (const float*)ju, (const float*)jv,
+                (const float*)jw, (float)dt, (float)dx, (float*)U, (float*)V, (float*)W, (const float*)dz, (float*)Wn);
+            return 1;
+        }
+    }
     k_wind_normalise<R><<<cell_grid(g), cell_block(), 0, st>>>(g, u, v, w, ju, jv, jw, rho, dt, dx,
                                                             scheme, U, V, W, dz, Wn);
     return 1;
