@@ -396,6 +396,82 @@ k_upwind_all(Geom g, ScalarSet s, const float* __restrict__ U, const float* __re
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Pass 1 for all scalars, four consecutive cells per thread: every x-row of the 7-point stencil is one
+// 16-byte load (+ the i-1 / i+4 neighbours of the centre row), a quarter of the load and address
+// instructions of k_upwind_all, which was issue-bound on exactly those.  Same expressions, bit for bit.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void ld4(const float* __restrict__ p, float (&o)[4]) {
+    const float4 q = *reinterpret_cast<const float4*>(p);
+    o[0] = q.x; o[1] = q.y; o[2] = q.z; o[3] = q.w;
+}
+
+template <int N, bool MARKSTEIN>
+__global__ void __launch_bounds__(128)
+k_upwind_all_v4(Geom g, ScalarSet s, const float* __restrict__ U, const float* __restrict__ V,
+                const float* __restrict__ W, const float* __restrict__ dz, const float* __restrict__ jaco) {
+    const int i0 = 4 * (blockIdx.x * 128 + threadIdx.x), k = blockIdx.y, j = blockIdx.z;
+    if (i0 >= g.nx) return;
+    const int nx = g.nx, ld = g.ld;
+    const size_t ps = g.ps();
+    const size_t c = g.at(i0, k, j);
+    const bool jring = (j == 0 || j == g.ny - 1);
+    const bool bottom = (k == 0), top = (k == g.nz - 1), flat = (g.nz == 1);
+    float uc[4], vm[4], vp[4], wp[4], wm[4] = {0.f, 0.f, 0.f, 0.f}, jc[4], dzc[4];
+    ld4(U + c, uc);
+    const float u_hi = (i0 + 4 < nx) ? U[c + 4] : 0.f;
+    ld4(V + c, vm); ld4(V + c + ps, vp); ld4(W + c, wp);
+    if (!bottom) ld4(W + c - ld, wm);
+    ld4(jaco + c, jc); ld4(dz + c, dzc);
+    float rj[4], rden[4], den[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        den[e] = dzc[e] * jc[e];
+        rj[e] = MARKSTEIN ? __frcp_rn(jc[e]) : 0.f;
+        rden[e] = MARKSTEIN ? __frcp_rn(den[e]) : 0.f;
+    }
+#pragma unroll
+    for (int n = 0; n < N; ++n) {
+        const float* __restrict__ qin = s.q[n];
+        float qc[4], qym[4] = {0.f, 0.f, 0.f, 0.f}, qyp[4] = {0.f, 0.f, 0.f, 0.f}, qzm[4] = {0.f, 0.f, 0.f, 0.f},
+              qzp[4] = {0.f, 0.f, 0.f, 0.f};
+        ld4(qin + c, qc);
+        if (!jring) { ld4(qin + c - ps, qym); ld4(qin + c + ps, qyp); }
+        if (!bottom) ld4(qin + c - ld, qzm);
+        if (!top) ld4(qin + c + ld, qzp);
+        const float q_lo = (i0 > 0) ? qin[c - 1] : 0.f, q_hi = (i0 + 4 < nx) ? qin[c + 4] : 0.f;
+        float val[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int i = i0 + e;
+            if (jring || i == 0 || i >= nx - 1) { val[e] = qc[e]; continue; }      // boundary ring: copied through
+            const float qxm = (e == 0) ? q_lo : qc[e > 0 ? e - 1 : 0], qxp = (e == 3) ? q_hi : qc[e < 3 ? e + 1 : 3];
+            const float uxp = (e == 3) ? u_hi : uc[e < 3 ? e + 1 : 3];
+            const float fxm = donor(uc[e], qxm, qc[e]), fxp = donor(uxp, qc[e], qxp);
+            const float fym = donor(vm[e], qym[e], qc[e]), fyp = donor(vp[e], qc[e], qyp[e]);
+            float v = qc[e] - div_shared<MARKSTEIN>((fxp - fxm) + (fyp - fym), jc[e], rj[e]);
+            if (!flat) {
+                float vert;
+                if (bottom)   vert = donor(wp[e], qc[e], qzp[e]);
+                else if (top) vert = qc[e] * wp[e] - donor(wm[e], qzm[e], qc[e]);
+                else          vert = donor(wp[e], qc[e], qzp[e]) - donor(wm[e], qzm[e], qc[e]);
+                v = v - div_shared<MARKSTEIN>(vert, den[e], rden[e]);
+            }
+            val[e] = v;
+        }
+        // rows are padded to a multiple of 32 floats: the whole float4 is storable; padding gets q's padding back
+        *reinterpret_cast<float4*>(s.q2[n] + c) = make_float4(val[0], val[1], val[2], val[3]);
+        if (jring || i0 == 0 || i0 + 4 >= nx - 1 + 1) {
+            // the boundary ring also goes to `out` (the corrector only writes interior cells)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int i = i0 + e;
+                if (i < nx && (jring || i == 0 || i == nx - 1)) s.out[n][c + e] = qc[e];
+            }
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------
 // launchers
 // ---------------------------------------------------------------------------
@@ -410,6 +486,7 @@ static inline dim3 cell_grid(const Geom& g) {
 int staged_upwind_all(const Geom& g, const ScalarSet& s, const float* U, const float* V, const float* W,
                       const float* dz, const float* jaco, cudaStream_t st) {
     const bool ieee = std::getenv("ICAR_UPWIND_IEEE_DIV") != nullptr;     // test hook, see div_shared
+    const bool scalar_form = std::getenv("ICAR_UPWIND_SCALAR") != nullptr || g.ld % 4 != 0;   // test hook: one cell per thread
     dim3 grid = cell_grid(g);
     int done = 0, launches = 0;
     while (done < s.n) {                 // batches of up to 5 scalars share the wind / metric loads
@@ -418,7 +495,8 @@ int staged_upwind_all(const Geom& g, const ScalarSet& s, const float* U, const f
         for (int n = 0; n < b.n; ++n) { b.q[n] = s.q[done + n]; b.q2[n] = s.q2[done + n]; b.out[n] = s.out[done + n]; }
 #define UPWIND_ALL(NN)                                                                                     \
     if (ieee) k_upwind_all<NN, false><<<grid, cell_block(), 0, st>>>(g, b, U, V, W, dz, jaco);             \
-    else k_upwind_all<NN, true><<<grid, cell_block(), 0, st>>>(g, b, U, V, W, dz, jaco)
+    else if (scalar_form) k_upwind_all<NN, true><<<grid, cell_block(), 0, st>>>(g, b, U, V, W, dz, jaco);  \
+    else k_upwind_all_v4<NN, true><<<dim3((g.ld / 4 + 127) / 128, g.nz, g.ny), 128, 0, st>>>(g, b, U, V, W, dz, jaco)
         switch (b.n) {
             case 5: UPWIND_ALL(5); break;
             case 4: UPWIND_ALL(4); break;
