@@ -42,14 +42,16 @@ UNIT = "cell-updates/s"
 # bytes per cell-update, SURVEY.md section 8d: mp_simple 56 B + MPDATA S=5 72 B; Thompson 84 B + MPDATA S=9 104 B
 # Algorithmic bytes per cell and launch of each kernel family (distinct fields read + written
 # once, 4 B each; S = advected scalars) and the DRAM traffic one launch moved at 512x512x40 in the committed
-# `ncu --set full` captures (profiles/r1_v8_top_kernels.txt, profiles/r1_thompson_v1.txt), in bytes.
+# `ncu --set full` captures (profiles/r1_v11_top_kernels.txt, profiles/r1_thompson_v3.txt), in bytes.
 KERNEL_BYTES = {
     "k_mp_simple": lambda S: 56.0, "k_mp_thompson": lambda S: 84.0, "k_wind_normalise": lambda S: 44.0,
     "k_face_coefficients": lambda S: 64.0, "k_upwind_all": lambda S: 20.0 + 8.0 * S,
     "k_corrector_fused": lambda S: 44.0 + 12.0 * S,
 }
-NCU_TRAFFIC_512 = {("k_corrector_fused", 5): 1138.8e6, ("k_mp_simple", 5): 546.1e6, ("k_upwind_all", 5): 619.3e6,
-                   ("k_mp_thompson", 9): 847.4e6}
+NCU_TRAFFIC_512 = {("k_corrector_fused", 5): 1142.5e6, ("k_mp_simple", 5): 620.0e6, ("k_upwind_all", 5): 620.0e6,
+                   # Thompson: 0.68 GB of field reads + 11.4 GB of writes, almost all of it register spills around
+                   # the out-of-line math calls (profiles/r1_thompson_v3.txt)
+                   ("k_mp_thompson", 9): 12056.0e6}
 SCHEMES = {
     "simple": dict(mp=2, b_alg=128.0, scalars=("th", "qv", "qc", "qr", "qs"), acc=("precipitation", "snowfall"),
                    workload="ideal hill {nx}x{ny}x{nz}, MPDATA order2+FCT, mp_simple (BASELINE configs[1])"),
