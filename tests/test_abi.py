@@ -114,3 +114,88 @@ def test_product_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h", ".f90")) or f == "Makefile":
                 txt = open(os.path.join(dirpath, f), errors="ignore").read()
                 assert not pat.search(txt), (dirpath, f)
+
+
+# ------------------------------------------------------------------ the Fortran shim against the C header
+def _fortran_shim():
+    return open(os.path.join(ROOT, "icar_b200", "fortran", "icar_b200_mod.f90")).read()
+
+
+def _c_prototypes():
+    """{name: number of parameters} for every function the header declares."""
+    src = open(os.path.join(ROOT, "include", "icar_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    protos = {}
+    for m in re.finditer(r"\b(icar_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", src, flags=re.S):
+        args = m.group(2).strip()
+        # function-pointer-free header: a plain comma count is the parameter count
+        protos[m.group(1)] = 0 if args in ("", "void") else args.count(",") + 1
+    return protos
+
+
+def test_fortran_shim_binds_existing_symbols_with_matching_arity():
+    """No Fortran compiler exists in the image, so the iso_c_binding interfaces are checked textually:
+    every `bind(c)` interface must name an exported symbol and take as many dummies as the C prototype."""
+    lib = icar_b200.lib()
+    protos = _c_prototypes()
+    found = re.findall(r"(?:function|subroutine)\s+(icar_[a-z0-9_]+)\s*\(([^)]*)\)\s*bind\(c\)", _fortran_shim(), flags=re.I)
+    assert len(found) >= 12
+    for name, args in found:
+        assert hasattr(lib, name), f"Fortran shim binds {name}, which libicar_b200.so does not export"
+        nargs = 0 if not args.strip() else args.count(",") + 1
+        assert nargs == protos[name], f"{name}: {nargs} dummies in the shim, {protos[name]} parameters in the header"
+
+
+def test_fortran_shim_enum_and_struct_layouts_match_the_header():
+    hdr = open(os.path.join(ROOT, "include", "icar_b200.h")).read()
+    shim = _fortran_shim()
+    enum = dict((k, int(v)) for k, v in re.findall(r"(ICAR_VAR_[A-Z_]+)\s*=\s*(\d+)", hdr))
+    alias = dict(VAR_TH="ICAR_VAR_POTENTIAL_TEMPERATURE", VAR_QV="ICAR_VAR_WATER_VAPOR", VAR_QC="ICAR_VAR_CLOUD_WATER",
+                 VAR_QR="ICAR_VAR_RAIN_IN_AIR", VAR_QS="ICAR_VAR_SNOW_IN_AIR", VAR_PRECIP="ICAR_VAR_PRECIPITATION",
+                 VAR_QI="ICAR_VAR_CLOUD_ICE", VAR_NI="ICAR_VAR_ICE_NUMBER", VAR_NR="ICAR_VAR_RAIN_NUMBER",
+                 VAR_QG="ICAR_VAR_GRAUPEL_IN_AIR")
+    fvars = dict((k, int(v)) for k, v in re.findall(r"\b(VAR_[A-Z_0-9]+)\s*=\s*(\d+)", shim))
+    assert len(fvars) >= 20
+    for k, v in fvars.items():
+        assert enum[alias.get(k, "ICAR_" + k)] == v, k
+    # member order of the bind(c) derived types == member order of the C structs
+    def c_members(struct):
+        body = re.search(r"typedef struct %s \{(.*?)\} %s;" % (struct, struct), re.sub(r"/\*.*?\*/", "", hdr, flags=re.S), flags=re.S).group(1)
+        names = []
+        for decl in body.split(";"):
+            decl = decl.strip()
+            if decl:
+                names += [n.strip(" *") for n in re.sub(r"^(const\s+)?\w+\s+", "", decl).split(",")]
+        return [n.lower() for n in names]
+
+    def f_members(t):
+        body = re.search(r"type, bind\(c\) :: %s\n(.*?)end type" % t, shim, flags=re.S | re.I).group(1)
+        names = []
+        for line in body.splitlines():
+            if "::" in line:
+                names += [n.strip().lower() for n in line.split("::")[1].split("!")[0].split(",")]
+        return names
+
+    for t in ("icar_grid", "icar_options", "icar_mp_options"):
+        assert f_members(t) == c_members(t), t
+
+
+def test_ctypes_structs_match_the_header_member_order():
+    hdr = re.sub(r"/\*.*?\*/", "", open(os.path.join(ROOT, "include", "icar_b200.h")).read(), flags=re.S)
+
+    def c_members(struct):
+        body = re.search(r"typedef struct %s \{(.*?)\} %s;" % (struct, struct), hdr, flags=re.S).group(1)
+        names = []
+        for decl in body.split(";"):
+            decl = decl.strip()
+            if decl:
+                names += [n.strip(" *") for n in re.sub(r"^(const\s+)?\w+\s+", "", decl).split(",")]
+        return names
+
+    assert [n for n, _ in icar_b200.Grid._fields_] == c_members("icar_grid")
+    assert [n for n, _ in icar_b200.Options._fields_] == c_members("icar_options")
+    assert [n for n, _ in icar_b200.MpOptions._fields_] == c_members("icar_mp_options")
+    assert [n for n, _ in icar_b200.HostDomain._fields_] == c_members("icar_host_domain")
+    enum = dict((k, int(v)) for k, v in re.findall(r"(ICAR_VAR_[A-Z_]+)\s*=\s*(\d+)", hdr))
+    for name, idx in icar_b200.VAR.items():
+        assert enum["ICAR_VAR_" + name.upper()] == idx, name
