@@ -150,7 +150,7 @@ SYMBOLS = (
     "icar_physics_step_host", "icar_host_register", "icar_host_unregister",
     "icar_default_mp_options", "icar_thompson_init", "icar_thompson_table", "icar_mp_gt_driver",
     "icar_profile_enable", "icar_profile_read", "icar_diagnostic_update", "icar_compute_dt", "icar_enforce_limits",
-    "icar_upload_tendency", "icar_apply_forcing")
+    "icar_upload_tendency", "icar_apply_forcing", "icar_balance_uvw")
 
 
 def lib() -> C.CDLL:
@@ -294,6 +294,10 @@ class Domain:
     def apply_forcing(self, dt_seconds):
         """domain%apply_forcing(dt), domain_obj.f90:2383-2448."""
         self._check(lib().icar_apply_forcing(self._h, C.c_double(dt_seconds)))
+
+    def balance_uvw(self):
+        """balance_uvw (wind.f90:81-172): w from the horizontal divergence of the resident u, v."""
+        self._check(lib().icar_balance_uvw(self._h))
 
     def enforce_limits(self):
         """domain%enforce_limits (domain_obj.f90:2228-2243)."""

@@ -1482,3 +1482,19 @@ extern "C" int icar_apply_forcing(icar_ctx* ctx, double dt_seconds) {
     CU(cudaGetLastError());
     return ICAR_OK;
 }
+
+extern "C" int icar_balance_uvw(icar_ctx* ctx) {
+    if (!ctx) return ICAR_ERR_INVALID;
+    CU(cudaSetDevice(ctx->device));
+    int rc = need_uploaded(ctx, {ICAR_VAR_U, ICAR_VAR_V, ICAR_VAR_JACOBIAN_U, ICAR_VAR_JACOBIAN_V, ICAR_VAR_JACOBIAN_W,
+                                 ICAR_VAR_ADVECTION_DZ}, "icar_balance_uvw");
+    if (rc) return rc;
+    ctx->launches += balance_uvw_launch(ctx->g, (const float*)ctx->vars[ICAR_VAR_U], (const float*)ctx->vars[ICAR_VAR_V],
+                                        (float*)ctx->vars[ICAR_VAR_W], (const float*)ctx->vars[ICAR_VAR_JACOBIAN_U],
+                                        (const float*)ctx->vars[ICAR_VAR_JACOBIAN_V],
+                                        (const float*)ctx->vars[ICAR_VAR_JACOBIAN_W],
+                                        (const float*)ctx->vars[ICAR_VAR_ADVECTION_DZ], ctx->opt.dx, ctx->stream);
+    CU(cudaGetLastError());
+    ctx->uploaded[ICAR_VAR_W] = true;
+    return ICAR_OK;
+}

@@ -348,6 +348,7 @@ k_mp_thompson(Geom g, ThConst c, ThTables tb, Args A, int ld2, float dt, MpTiles
     graupel_rain_slopes();
 
     float rvs = 0.f, t1_subl = 0.f;
+    double lamr_fv9 = -1.0;        // (lamr + fv_r)**(-cre(9)) once it has been evaluated (it is positive)
     if (active) {
         // ---------------------------------------------------------- warm rain (:1500-1544)
         if (L_qr && mvd_r > D0r) {
@@ -376,7 +377,8 @@ k_mp_thompson(Geom g, ThConst c, ThTables tb, Args A, int ld2, float dt, MpTiles
                 idx = min(idx, nbins);
                 const int jc = min((int)(mvd_c * 1.E6f), nbins);          // (upper clamp: memory safety only)
                 const float Ef_rw = (float)tb.t[T_Efrw][(idx - 1) + nbins * (jc - 1)];
-                prr_rcw = rhof * c.t1_qr_qc * Ef_rw * rc * N0_r * (dpow((lamr + fv_r), (double)(-c.cre[8])));
+                lamr_fv9 = dpow((lamr + fv_r), (double)(-c.cre[8]));          // reused by pri_rci / pnr_rci (same ilamr)
+                prr_rcw = rhof * c.t1_qr_qc * Ef_rw * rc * N0_r * (lamr_fv9);
                 prr_rcw = fmin((double)(rc * odts), prr_rcw);
             }
         }
@@ -517,12 +519,17 @@ k_mp_thompson(Geom g, ThConst c, ThTables tb, Args A, int ld2, float dt, MpTiles
                 pri_inu = fmin((double)rate_max, xm0i * pni_inu);
                 pni_inu = pri_inu / xm0i;
             }
-            if (L_qi) {                                                      // :1830-1863
+            // (the Fortran evaluates lami, xDi, xmi twice from the same ni, ri -- :1831-1835 and :1897-1901 -- once here)
+            double ilami = 0.0;
+            float xDi = 0.f, oxmi = 0.f;
+            if (L_qi) {
                 const double lami = fpow((c.am_i * c.cig[1] * c.oig1 * ni / ri), c.obmi);
-                const double ilami = 1. / lami;
-                const float xDi = (float)fmax((double)c.D0i, (bm_i + mu_i + 1.f) * ilami);
+                ilami = 1. / lami;
+                xDi = (float)fmax((double)c.D0i, (bm_i + mu_i + 1.f) * ilami);
                 const float xmi = c.am_i * fpow(xDi, bm_i);
-                const float oxmi = 1.f / xmi;
+                oxmi = 1.f / xmi;
+            }
+            if (L_qi) {                                                      // :1830-1863
                 pri_ide = C_cube * t1_subl * diffu * ssati * rvs * c.oig1 * c.cig[4] * ni * ilami;
                 const size_t q = (size_t)(idx_i - 1) + (size_t)ntb_i * (size_t)(idx_i1 - 1);
                 if (pri_ide < 0.0) {
@@ -561,19 +568,15 @@ k_mp_thompson(Geom g, ThConst c, ThTables tb, Args A, int ld2, float dt, MpTiles
                 else prg_gde = fmin(prg_gde, (double)rate_max);
             }
             if (L_qi) {                                                      // :1896-1920
-                const double lami = fpow((c.am_i * c.cig[1] * c.oig1 * ni / ri), c.obmi);
-                const double ilami = 1. / lami;
-                const float xDi = (float)fmax((double)c.D0i, (bm_i + mu_i + 1.f) * ilami);
-                const float xmi = c.am_i * fpow(xDi, bm_i);
-                const float oxmi = 1.f / xmi;
                 if (rs >= 1.e-5f) {
                     prs_sci = c.t1_qs_qi * rhof * c.o.Ef_si * ri * smoe;
                     pni_sci = prs_sci * oxmi;
                 }
                 if (rr >= 1.e-6f && mvd_r > 4.f * xDi) {
                     const double lamr = 1. / ilamr;
-                    pri_rci = rhof * c.t1_qr_qi * c.o.Ef_ri * ri * N0_r * (dpow((lamr + fv_r), (double)(-c.cre[8])));
-                    pnr_rci = rhof * c.t1_qr_qi * c.o.Ef_ri * ni * N0_r * (dpow((lamr + fv_r), (double)(-c.cre[8])));
+                    const double lf9 = (lamr_fv9 >= 0.0) ? lamr_fv9 : dpow((lamr + fv_r), (double)(-c.cre[8]));
+                    pri_rci = rhof * c.t1_qr_qi * c.o.Ef_ri * ri * N0_r * (lf9);
+                    pnr_rci = rhof * c.t1_qr_qi * c.o.Ef_ri * ni * N0_r * (lf9);
                     pni_rci = pri_rci * oxmi;
                     prr_rci = rhof * c.t2_qr_qi * c.o.Ef_ri * ni * N0_r * (dpow((lamr + fv_r), (double)(-c.cre[7])));
                     prr_rci = fmin((double)(rr * odts), prr_rci);
@@ -610,14 +613,15 @@ k_mp_thompson(Geom g, ThConst c, ThTables tb, Args A, int ld2, float dt, MpTiles
                 }
             }
             if (L_qg) {
+                const double ig10 = dpow(ilamg, (double)c.cge[9]), ig11 = dpow(ilamg, (double)c.cge[10]);
                 prr_gml = (tempc * tcond - lvap0 * diffu * delQvs) * N0_g *
-                          (c.t1_qg_me * dpow(ilamg, (double)c.cge[9]) + c.t2_qg_me * rhof2 * vsc2 * dpow(ilamg, (double)c.cge[10]));
+                          (c.t1_qg_me * ig10 + c.t2_qg_me * rhof2 * vsc2 * ig11);
                 prr_gml = fmin((double)(rg * odts), fmax(0., prr_gml));
                 pnr_gml = N0_g * c.cgg[1] * dpow(ilamg, (double)c.cge[1]) / rg * prr_gml * fpow(10.0f, (-1.5f * tempc));
                 if (tempc > 7.5f || rg < 0.005E-3f) pnr_gml = 0.0;
                 if (ssati < 0.f) {
                     prg_gde = C_cube * t1_subl * diffu * ssati * rvs * N0_g *
-                              (c.t1_qg_sd * dpow(ilamg, (double)c.cge[9]) + c.t2_qg_sd * vsc2 * rhof2 * dpow(ilamg, (double)c.cge[10]));
+                              (c.t1_qg_sd * ig10 + c.t2_qg_sd * vsc2 * rhof2 * ig11);
                     prg_gde = fmax((double)(-rg * odts), prg_gde);
                 }
             }

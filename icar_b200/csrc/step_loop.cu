@@ -62,6 +62,28 @@ k_apply_forcing(float* __restrict__ q, const float* __restrict__ dqdt, int width
     q[c] = (float)((double)q[c] + ((double)dqdt[c] * seconds));
 }
 
+__global__ void __launch_bounds__(128)
+k_balance_uvw(Geom g, const float* __restrict__ u, const float* __restrict__ v, float* __restrict__ w,
+              const float* __restrict__ ju, const float* __restrict__ jv, const float* __restrict__ jw,
+              const float* __restrict__ dz, float dx) {
+    const int i = blockIdx.x * 128 + threadIdx.x, j = blockIdx.y;
+    if (i >= g.nx) return;
+    float w_below = 0.f, jw_below = 1.f;
+    for (int k = 0; k < g.nz; ++k) {
+        const size_t c = g.at(i, k, j), cu = g.atu(i, k, j);
+        // calc_divergence, horz_only: u_met = u*jaco_u, v_met = v*jaco_v; div = (diff_U + diff_V)/dx   (:209-216)
+        const float diff_U = u[cu + 1] * ju[cu + 1] - u[cu] * ju[cu];
+        const float diff_V = v[c + g.ps()] * jv[c + g.ps()] - v[c] * jv[c];
+        const float div = (diff_U + diff_V) / dx;
+        const float jwc = jw[c];
+        float wk;
+        if (k == 0) wk = 0.f - div * dz[c] / jwc;                              // :142
+        else        wk = (w_below * jw_below - div * dz[c]) / jwc;            // :144
+        w[c] = wk;
+        w_below = wk; jw_below = jwc;
+    }
+}
+
 struct FieldPtrs { float* p[12]; };
 
 __global__ void __launch_bounds__(128)
@@ -96,6 +118,12 @@ int apply_forcing_launch(float* q, const float* dqdt, int width, int nz, int row
     k_apply_forcing<<<dim3((width + 127) / 128, nz, rows_y), 128, 0, st>>>(q, dqdt, width, nz, rows_y, pitch, seconds,
                                                                           boundaries_only ? 1 : 0, edges[0], edges[1],
                                                                           edges[2], edges[3]);
+    return 1;
+}
+
+int balance_uvw_launch(const Geom& g, const float* u, const float* v, float* w, const float* ju, const float* jv,
+                       const float* jw, const float* dz, float dx, cudaStream_t st) {
+    k_balance_uvw<<<dim3((g.nx + 127) / 128, g.ny), 128, 0, st>>>(g, u, v, w, ju, jv, jw, dz, dx);
     return 1;
 }
 

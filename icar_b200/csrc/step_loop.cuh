@@ -26,6 +26,12 @@ int cfl_maxima_launch(const Geom& g, const float* u, const float* v, const float
 int apply_forcing_launch(float* q, const float* dqdt, int width, int nz, int rows_y, int pitch, double seconds,
                          bool boundaries_only, const bool edges[4], cudaStream_t st);
 
+// balance_uvw (src/physics/wind.f90:81-172) with calc_divergence(horz_only) (:175-228): the w that balances
+// the horizontal divergence of u*jacobian_u, v*jacobian_v, integrated upward from w = 0 at the ground.
+// One thread per column (the level loop carries w(k-1)); lanes run along x.
+int balance_uvw_launch(const Geom& g, const float* u, const float* v, float* w, const float* ju, const float* jv,
+                       const float* jw, const float* dz, float dx, cudaStream_t st);
+
 // where (q < 0) q = 0 for every listed field (domain_obj.f90:2228-2243)
 int enforce_limits_launch(const Geom& g, float* const* fields, int nfields, cudaStream_t st);
 

@@ -198,6 +198,12 @@ int icar_compute_dt(icar_ctx* ctx, const float* dz_levels, float cfl_reduction_f
 int icar_upload_tendency(icar_ctx* ctx, int var, const float* host);
 int icar_apply_forcing(icar_ctx* ctx, double dt_seconds);
 
+/* balance_uvw(u, v, w, jaco_u, jaco_v, jaco_w, dz, dx, jaco, options) (src/physics/wind.f90:81-172, with
+ * calc_divergence(horz_only=.True.), :175-228) on the device-resident winds: w is replaced by the vertical
+ * wind that balances du/dx + dv/dy, integrated upward from the ground; dz = domain%advection_dz as at the
+ * call sites wind.f90:330-332.  update_winds runs this once per forcing interval ("next" rank 3). */
+int icar_balance_uvw(icar_ctx* ctx);
+
 /* domain%enforce_limits (src/objects/domain_obj.f90:2228-2243): where (q < 0) q = 0 on every scalar the
  * microphysics scheme allocates. */
 int icar_enforce_limits(icar_ctx* ctx);

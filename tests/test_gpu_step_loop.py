@@ -106,6 +106,22 @@ def test_apply_forcing_diagnosed_fields_and_scalar_boundaries(gpu_lib):
     np.testing.assert_array_equal(dom.download("qc"), st["qc"])
 
 
+def test_balance_uvw_matches_wind_f90(gpu_lib):
+    """icar_balance_uvw against the NumPy restatement of wind.f90:81-228 the ideal-case generator uses."""
+    st = ideal.make_ideal_case(nx=45, nz=14, ny=11, perturb=True)
+    rng = np.random.default_rng(2)
+    st["u"] = (st["u"] * rng.uniform(0.5, 1.5, st["u"].shape)).astype(np.float32)
+    st["v"] = (st["v"] * rng.uniform(0.5, 1.5, st["v"].shape)).astype(np.float32)
+    dom = make(gpu_lib, st)
+    dom.upload("w", np.full_like(st["w"], 7.0))            # balance_uvw starts from w = 0 (:104)
+    dom.balance_uvw()
+    want = ideal.balance_uvw(st["u"], st["v"], st["jacobian_u"], st["jacobian_v"], st["jacobian_w"],
+                             st["advection_dz"], st["dx"])
+    got = dom.download("w")
+    # same REAL operations in the same order; -fmad=false on the device, NumPy does not contract either
+    np.testing.assert_array_equal(got, want)
+
+
 def test_device_resident_loop_body(gpu_lib, oracle):
     """The loop body of step() (time_step.f90:464-547 with rad/lsm/pbl off): update_dt -> diagnostic_update ->
     mp -> advect -> apply_forcing -> enforce_limits entirely on the device, a few steps, against the same
