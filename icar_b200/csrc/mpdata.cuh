@@ -22,10 +22,10 @@ struct FusedCoef {
 };
 
 // launch plan of the fused corrector for a tile; ok == false when it cannot serve this geometry
-// (more than 48 levels, or not enough opt-in shared memory): the caller then uses the staged path
+// (more than 64 levels, or not enough opt-in shared memory): the caller then uses the staged path
 struct FusedPlan {
     bool ok;
-    int cpt, nzp;
+    int cpt, nzp, stages;
     size_t smem;
 };
 FusedPlan fused_plan(const Geom& g);

@@ -231,7 +231,10 @@ k_face_coefficients_v4(Geom g, const float* __restrict__ U, const float* __restr
 // ---------------------------------------------------------------------------------------------
 // NZP = number of level slots per staged box (>= nz, multiple of CPT): compile-time, so that every
 // shared-memory address below is base register + immediate.
-template <int CPT, int NZP>
+// STAGES = 2: the TMA stage is double-buffered (the boxes of plane P+1 land while plane P is computed);
+// STAGES = 1 (50 < nz <= 64 levels, where two stages of 13 boxes no longer fit 227 KB of shared memory):
+// one stage, refilled at the top of every iteration -- the load latency is then exposed once per plane.
+template <int CPT, int NZP, int STAGES>
 __global__ void __launch_bounds__(TW * (NZP / CPT))
 k_corrector_fused(const Geom g, const OutSet outs, const __grid_constant__ FusedMaps maps, const int chunk) {
     extern __shared__ __align__(128) unsigned char smraw[];
@@ -256,15 +259,15 @@ k_corrector_fused(const Geom g, const OutSet outs, const __grid_constant__ Fused
     enum { R_QLO, R_QHI, R_MHLO, R_MHHI, R_MLLO, R_MLHI, R_FZHI, R_BILO, R_BOLO, R_FLHI, R_COUNT };
     float* rows = reinterpret_cast<float*>(smraw);
     constexpr int rows_floats = 2 * R_COUNT * (nzt + 2) * TW;
-    float* stage0 = rows + rows_floats;               // [2][NF][nz][32]
-    uint64_t* mbar = reinterpret_cast<uint64_t*>(stage0 + 2 * NF * box);
+    float* stage0 = rows + rows_floats;               // [STAGES][NF][nz][32]
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(stage0 + STAGES * NF * box);
     auto row = [&](int buf, int kind, int z) -> float& { return rows[((buf * R_COUNT + kind) * (nzt + 2) + (z + 1)) * TW + tx]; };
     const int tid = tz * TW + tx;
     const int niter = jb - ja + 4;                    // planes ja-2 .. jb+1
     const uint32_t stage_bytes = (uint32_t)(NF * nz * TW * sizeof(float));   // bytes TMA delivers per stage
 
     auto issue = [&](int it) {                        // thread 0: fetch the 13 boxes of iteration `it`
-        const int P = ja - 2 + it, st = it & 1;
+        const int P = ja - 2 + it, st = (STAGES == 2) ? (it & 1) : 0;
         float* dst = stage0 + st * NF * box;
         mbar_arrive_expect_tx(&mbar[st], stage_bytes);
         tma_load_box(dst + F_Q2 * box, &maps.q2[scalar], &mbar[st], x0, 0, P);
@@ -282,7 +285,7 @@ k_corrector_fused(const Geom g, const OutSet outs, const __grid_constant__ Fused
     }
     // level slots nz..NZP-1 of every box are never written by TMA: zero them once so that the
     // (non-existent) cells above the model top read as 0 without a predicate
-    for (int t = tid; t < 2 * NF * box; t += TW * nzt) stage0[t] = 0.f;
+    for (int t = tid; t < STAGES * NF * box; t += TW * nzt) stage0[t] = 0.f;
     // rows of the (non-existent) threads below tz=0 and above tz=nzt-1 read as "no neighbour"
     if (tz == 0) {
         for (int b = 0; b < 2; ++b) {
@@ -325,9 +328,11 @@ k_corrector_fused(const Geom g, const OutSet outs, const __grid_constant__ Fused
         const bool out_iter = (Po >= ja);
         // every read of stage buf^1 (iteration it-1) precedes that iteration's first barrier,
         // which this thread has passed: the stage is free to be refilled
-        if (tid == 0 && it + 1 < niter) issue(it + 1);
-        while (!mbar_try_wait(&mbar[buf], (uint32_t)((it >> 1) & 1))) {}
-        const float* __restrict__ sg = stage0 + buf * NF * box + cell_off;
+        if (STAGES == 2) { if (tid == 0 && it + 1 < niter) issue(it + 1); }
+        else             { if (tid == 0 && it > 0) issue(it); }
+        const int st = (STAGES == 2) ? buf : 0;
+        while (!mbar_try_wait(&mbar[st], (uint32_t)((STAGES == 2) ? ((it >> 1) & 1) : (it & 1)))) {}
+        const float* __restrict__ sg = stage0 + st * NF * box + cell_off;
 
         // ---------------- shift the windows, take plane P from the stage
         float cay[CPT], cby[CPT], ccy[CPT];
@@ -588,16 +593,18 @@ int env_int(const char* name, int dflt) {
 }  // namespace
 
 // Which instantiation serves nz levels, and its dynamic shared memory: 2 x 10 exchange rows of
-// (nzt+2) x 32 floats, 2 stages of 13 boxes of NZP x 32 floats, 2 mbarriers.
+// (nzt+2) x 32 floats, 1 or 2 stages of 13 boxes of NZP x 32 floats, 2 mbarriers.
 FusedPlan fused_plan(const Geom& g) {
     FusedPlan p{};
-    if (g.nz < 2 || g.nz > 48 || g.nx < 3 || g.ny < 3) return p;
+    if (g.nz < 2 || g.nz > 64 || g.nx < 3 || g.ny < 3) return p;
+    p.stages = 2;
     if (g.nz <= 20) { p.cpt = 2; p.nzp = 20; }
     else if (g.nz <= 40) { p.cpt = 2; p.nzp = 40; }
-    else { p.cpt = 4; p.nzp = 48; }
-    if (env_int("ICAR_FUSED_CPT", 0) == 4) { p.cpt = 4; p.nzp = 48; }
+    else if (g.nz <= 48) { p.cpt = 4; p.nzp = 48; }
+    else { p.cpt = 4; p.nzp = 64; p.stages = 1; }
+    if (env_int("ICAR_FUSED_CPT", 0) == 4 && g.nz <= 48) { p.cpt = 4; p.nzp = 48; }
     const int nzt = p.nzp / p.cpt;
-    p.smem = (size_t)(2 * 10 * (nzt + 2) * TW + 2 * NF * p.nzp * TW) * sizeof(float) + 16;
+    p.smem = (size_t)(2 * 10 * (nzt + 2) * TW + p.stages * NF * p.nzp * TW) * sizeof(float) + 16;
     int dev = 0, max_optin = 0;
     if (cudaGetDevice(&dev) != cudaSuccess ||
         cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess) {
@@ -657,16 +664,17 @@ int fused_advect_all(const Geom& g, const ScalarSet& s, const float* U, const fl
     const int chunks = (planes + chunk - 1) / chunk;
     dim3 grid(xtiles * s.n, chunks);
     dim3 block(TW, plan.nzp / plan.cpt);
-#define LAUNCH_FUSED(C, Z)                                                                                    \
+#define LAUNCH_FUSED(C, Z, S)                                                                                 \
     {                                                                                                         \
-        auto kern = k_corrector_fused<C, Z>;                                                                  \
+        auto kern = k_corrector_fused<C, Z, S>;                                                               \
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem) !=        \
             cudaSuccess) { (void)cudaGetLastError(); return -1; }                                             \
         kern<<<grid, block, plan.smem, st>>>(g, outs, maps, chunk);                                           \
     }
-    if (plan.cpt == 2 && plan.nzp == 20) LAUNCH_FUSED(2, 20)
-    else if (plan.cpt == 2 && plan.nzp == 40) LAUNCH_FUSED(2, 40)
-    else LAUNCH_FUSED(4, 48)
+    if (plan.cpt == 2 && plan.nzp == 20) LAUNCH_FUSED(2, 20, 2)
+    else if (plan.cpt == 2 && plan.nzp == 40) LAUNCH_FUSED(2, 40, 2)
+    else if (plan.nzp == 48) LAUNCH_FUSED(4, 48, 2)
+    else LAUNCH_FUSED(4, 64, 1)
 #undef LAUNCH_FUSED
     ++launches;
     if (marks) cudaEventRecord(marks[3], st);
