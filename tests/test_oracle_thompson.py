@@ -4,6 +4,7 @@ NumPy evaluation of lookup-table entries, and physical invariants of the column 
 PARITY UNPINNED: the reference has no expected values for mp_thompson and cannot be compiled here;
 these tests pin the restatement against regressions and against a second, independent evaluation
 of the table integrals (mp_thompson.f90:2917-2975, :3093-3220, :3323-3381, :3425-3454)."""
+import math
 import os
 
 import numpy as np
@@ -198,3 +199,140 @@ def test_driver_clips_tile_to_domain_edge(thompson_full):
     for k in ("th", "qv", "qc"):
         np.testing.assert_array_equal(st[k][:, :, -1], before[k][:, :, -1])
         np.testing.assert_array_equal(st[k][-1], before[k][-1])
+
+
+# ------------------------------------------------------------------ more independent table evaluations
+def _snow_dsd(th, i, j):
+    """N_s(n) of table cell (r_s(i), Tc(j)) in float64, Field et al. (2005) as in mp_thompson.f90:3111-3150."""
+    c = th.constants().astype(np.float64)
+    f = lambda x: np.float64(np.float32(x))
+    sa = [f(v) for v in (5.065339, -0.062659, -3.032362, 0.029469, -0.000285, 0.31255, 0.000204, 0.003199, 0.0, -0.015952)]
+    sb = [f(v) for v in (0.476221, -0.015896, 0.165977, 0.007468, -0.000141, 0.060366, 0.000079, 0.000594, 0.0, -0.003577)]
+    Tc = f((-0.01, -5., -10., -15., -20., -25., -30., -35., -40.)[j])
+    am_s = f(0.069)
+    rs = float(np.float32(f"{i % 9 + 1}e{i // 9 - 5}"))
+
+    def poly(s, x):       # evaluated in REAL by the Fortran; float64 here (differences ~1e-7 relative)
+        return (s[0] + s[1] * Tc + s[2] * x + s[3] * Tc * x + s[4] * Tc * Tc + s[5] * x * x + s[6] * Tc * Tc * x
+                + s[7] * Tc * x * x + s[8] * Tc ** 3 + s[9] * x ** 3)
+
+    M2 = rs / am_s
+    second = (M2 / 10.0 ** poly(sa, 2.0)) ** (1.0 / poly(sb, 2.0))          # the bm_s ~ 2 branch (:3112-3124)
+    M3 = 10.0 ** poly(sa, 3.0) * second ** poly(sb, 3.0)
+    r = M2 / M3
+    Mrat, M0, slam1, slam2 = M2 * r ** 3, r ** f(0.6357), r * f(20.78), r * f(3.29)
+    Ds = th.bins()["Ds"]
+    return Mrat * (f(490.6) * np.exp(-slam1 * Ds) + f(17.46) * M0 * Ds ** f(0.6357) * np.exp(-slam2 * Ds)) * _dt_of(Ds, 200e-6, 2e-2)
+
+
+@pytest.mark.parametrize("k,m,i,j", [(3, 4, 0, 0), (20, 18, 14, 4), (36, 36, 27, 8), (9, 30, 22, 2)])
+def test_qr_acr_qs_against_numpy(thompson, k, m, i, j):
+    """The twelve rain-snow tables (mp_thompson.f90:3093-3220), including the massr > 1.5 masss split."""
+    th = thompson
+    th.big_slab(1, m * 37 + k)
+    c = th.constants().astype(np.float64)
+    am_r = c[5]
+    b = th.bins()
+    N_r, rr = _rain_dsd(th, k, m)
+    N_s = _snow_dsd(th, i, j)
+    Dr, Ds = b["Dr"], b["Ds"]
+    f = lambda x: np.float64(np.float32(x))
+    vr = f(-0.1021) + f(4.932E3) * Dr - f(0.9551E6) * Dr ** 2 + f(0.07934E9) * Dr ** 3 - f(0.002362E12) * Dr ** 4
+    vs = f(np.float32(1.5) * np.float32(40.0)) * Ds ** f(0.55) * np.exp(-f(100.0) * Ds)
+    dvs = np.maximum(vr[:, None] - vs[None, :], 0)
+    dvr = np.maximum(vs[None, :] - vr[:, None], 0)
+    kern = f(PI2 * np.float32(.25) * np.float32(0.95)) * (Ds[None, :] + Dr[:, None]) ** 2 * N_s[None, :] * N_r[:, None]
+    massr, masss = (am_r * Dr ** 3)[:, None], (f(0.069) * Ds ** 2)[None, :]
+    big = massr > f(1.5) * masss
+    want = dict(
+        tcs_racs1=(kern * dvs * masss)[big].sum(), tmr_racs1=min((kern * dvs * massr)[big].sum(), rr),
+        tcs_racs2=(kern * dvs * masss)[~big].sum(), tmr_racs2=(kern * dvs * massr)[~big].sum(),
+        tcr_sacr1=(kern * dvr * massr)[big].sum(), tms_sacr1=(kern * dvr * masss)[big].sum(),
+        tcr_sacr2=(kern * dvr * massr)[~big].sum(), tms_sacr2=(kern * dvr * masss)[~big].sum(),
+        tnr_racs1=(kern * dvs)[big].sum(), tnr_racs2=(kern * dvs)[~big].sum(),
+        tnr_sacr1=(kern * dvr)[big].sum(), tnr_sacr2=(kern * dvr)[~big].sum())
+    for name, w in want.items():
+        got = th.table(name)[m, k, j, i]
+        # the snow-moment regression is REAL arithmetic in the Fortran (and the oracle), float64 here
+        assert abs(got - w) <= 2e-4 * abs(w) + 1e-300, (name, got, w)
+
+
+def test_freezeH2O_against_numpy(thompson):
+    """Bigg (1953) freezing tables (mp_thompson.f90:3323-3381) with the largest-drop-first early EXIT."""
+    th = thompson
+    c = th.constants().astype(np.float64)
+    am_r, xm0g = c[5], c[4]
+    b = th.bins()
+    Dr, Dc = b["Dr"], b["Dc"]
+    massr, massc = am_r * Dr ** 3, am_r * Dc ** 3
+    rng = np.random.default_rng(1)
+    for _ in range(40):
+        i, j, k = int(rng.integers(37)), int(rng.integers(37)), int(rng.integers(1, 46))
+        Texp = np.exp(float(k)) - 1.0
+        N_r, rr = _rain_dsd(th, j, i)
+        prob = np.maximum(1.0 - np.exp(-120.0 * (massr / 1000.0) * 5.2e-4 * Texp), 0.0)
+        s1 = s2 = n1 = n2 = 0.0
+        for n in range(99, -1, -1):
+            if massr[n] < xm0g:
+                n1 += prob[n] * N_r[n]; s1 += prob[n] * N_r[n] * massr[n]
+            else:
+                n2 += prob[n] * N_r[n]; s2 += prob[n] * N_r[n] * massr[n]
+            if s1 + s2 >= rr:
+                break
+        got = [th.table(t)[k - 1, j, i] for t in ("tpi_qrfz", "tni_qrfz", "tpg_qrfz", "tnr_qrfz")]
+        np.testing.assert_allclose(got, [s1, n1, s2, n2], rtol=2e-5, atol=1e-300)
+    # cloud water: all 45 temperatures of a few r_c entries
+    mu_c, Nt_c = c[0], 100.e6
+    o = 8
+    cce, ccg = c[o:o + 3], c[o + 3:o + 6]
+    for i in (0, 12, 36):
+        rc = float(np.float32(f"{i % 9 + 1}e{i // 9 - 6}"))
+        lamc = 1e-6 * (Nt_c * am_r * ccg[1] / ccg[0] / rc) ** (1 / 3)
+        N0_c = 1e-18 * Nt_c / ccg[0] * lamc ** cce[0]
+        y = Dc * 1e6
+        N_c = 1e24 * N0_c * y ** mu_c * np.exp(-lamc * y) * 1e-6          # dtc = 1e-6 (D0c for the first bin too)
+        for k in (1, 7, 20, 45):
+            # at k = 1 the exponent is below 1e-16 for the small bins, so 1 - exp(-x) is pure rounding of exp:
+            # libm's exp (what the Fortran and the oracle call), not NumPy's vector one
+            x = -120.0 * (massc / 1000.0) * 5.2e-4 * (math.exp(float(k)) - 1.0)
+            prob = np.maximum(1.0 - np.array([math.exp(v) for v in x]), 0.0)
+            s1 = sn = 0.0
+            for n in range(99, -1, -1):
+                sn += prob[n] * N_c[n]; s1 += prob[n] * N_c[n] * massc[n]
+                if s1 >= rc:
+                    break
+            np.testing.assert_allclose([th.table("tpi_qcfz")[k - 1, i], th.table("tni_qcfz")[k - 1, i]], [s1, sn], rtol=2e-5)
+
+
+def test_qi_aut_qs_against_scipy(thompson):
+    """Ice -> snow conversion tables (mp_thompson.f90:3425-3454): the incomplete gamma function and the bin sums."""
+    th = thompson
+    c = th.constants().astype(np.float64)
+    am_i, D0i = c[6], c[2]
+    Di = th.bins()["Di"]
+    x = np.exp(np.arange(101) / 100 * np.log(5.0 * float(np.float32(200e-6)) / D0i) + np.log(D0i))
+    np.testing.assert_allclose(np.sqrt(x[:-1] * x[1:]), Di, rtol=1e-12)
+    dti = np.diff(x)
+    D0s = float(np.float32(200e-6))
+    rng = np.random.default_rng(2)
+    checked = 0
+    for _ in range(200):
+        i, j = int(rng.integers(64)), int(rng.integers(55))
+        ri = float(np.float32(f"{i % 9 + 1}e{i // 9 - 10}"))
+        Nt = float(10.0 ** (j // 9) * (j % 9 + 1))
+        lami = (am_i * 6.0 * Nt / ri) ** (1 / 3)          # cig(2) = gamma(4) = 6, oig1 = 1
+        Dm = 4.0 / lami
+        got = [th.table(t)[j, i] for t in ("tps_iaus", "tni_iaus", "tpi_ide")]
+        if Dm > 5.0 * D0s * (1 + 1e-5):
+            want = [ri, Nt, 0.0]
+        elif Dm < D0i * (1 - 1e-5):
+            want = [0.0, 0.0, 1.0]
+        elif abs(Dm / (5.0 * D0s) - 1) < 1e-5 or abs(Dm / D0i - 1) < 1e-5:
+            continue                                       # on a branch boundary in REAL arithmetic
+        else:
+            N_i = Nt * lami * np.exp(-lami * Di) * dti
+            big = Di >= D0s
+            want = [(N_i * am_i * Di ** 3)[big].sum(), N_i[big].sum(), special.gammainc(2.0, lami * D0s)]
+        np.testing.assert_allclose(got, want, rtol=3e-5, atol=1e-300)
+        checked += 1
+    assert checked > 150
