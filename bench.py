@@ -290,13 +290,18 @@ def run_b200(args, rank, world, local_rank):
     # ---------------- device-resident timing
     for _ in range(max(args.warmup, 3)):
         dom.physics_step(dt)
+    if args.graph:
+        dom.physics_steps(dt, 2, graph=True)               # capture outside the timed region
     barrier()
     sampler = ClockSampler(physical_device(local_rank))
     launches0 = dom.kernel_launches
     sampler.start()
     dom.timer_start()
-    for _ in range(args.steps):
-        dom.physics_step(dt)
+    if args.graph:
+        dom.physics_steps(dt, args.steps, graph=True)      # pairs of steps replayed from a CUDA graph
+    else:
+        for _ in range(args.steps):
+            dom.physics_step(dt)
     ms = dom.timer_stop()
     barrier()
     clocks = sampler.stop()
@@ -376,7 +381,8 @@ def run_b200(args, rank, world, local_rank):
                        "decomposition": (f"{args.slabs}-slabs over {world} GPUs, halo {halo}, NCCL send/recv" if distributed
                                          else "single image"),
                        "l2": "resident working set ~1.1 GB per step > 126 MB L2, no explicit flush",
-                       "mp_diagnostics": list(diag)},
+                       "mp_diagnostics": list(diag),
+                       "stepping": "icar_physics_steps (CUDA graph replay)" if args.graph else "icar_physics_step per step"},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": e2e_steps, "ms_per_step": e2e_s / e2e_steps * 1e3,
@@ -422,6 +428,9 @@ def main():
     ap.add_argument("--slabs", default="y", choices=["x", "y"],
                     help="decomposition axis for N>1 (y keeps full-width rows and contiguous halo planes)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--graph", action="store_true",
+                    help="run the timed steps through icar_physics_steps (CUDA-graph replay) instead of one "
+                         "icar_physics_step call per step")
     ap.add_argument("--mp", default="simple", choices=["simple", "thompson"],
                     help="microphysics scheme: simple = BASELINE configs[1] (the headline), thompson = configs[2]")
     args = ap.parse_args()

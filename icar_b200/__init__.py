@@ -143,7 +143,7 @@ SYMBOLS = (
     "icar_default_options", "icar_grid_xslab", "icar_grid_yslab", "icar_create", "icar_destroy", "icar_last_error",
     "icar_upload", "icar_download", "icar_device_ptr", "icar_set_model_time", "icar_get_model_time",
     "icar_advect", "icar_mp", "icar_halo_send", "icar_halo_retrieve", "icar_halo_exchange",
-    "icar_physics_step", "icar_synchronize", "icar_mp_diagnostics", "icar_kernel_launches",
+    "icar_physics_step", "icar_physics_steps", "icar_synchronize", "icar_mp_diagnostics", "icar_kernel_launches",
     "icar_timer_start", "icar_timer_stop",
     "icar_halo_plan", "icar_comm_unique_id", "icar_comm_init", "icar_mpdata_set_winds", "icar_mpdata_advect3d",
     "icar_mpdata_set_winds_f64", "icar_mpdata_advect3d_f64", "icar_mp_simple_driver",
@@ -271,6 +271,11 @@ class Domain:
 
     def physics_step(self, dt):
         self._check(lib().icar_physics_step(self._h, C.c_float(dt)))
+
+    def physics_steps(self, dt, nsteps, graph=True):
+        """nsteps passes of step()'s loop body at a fixed dt (time_step.f90:464-549); graph=True replays
+        pairs of steps from a CUDA graph, with results identical to nsteps physics_step calls."""
+        self._check(lib().icar_physics_steps(self._h, C.c_float(dt), int(nsteps), 1 if graph else 0))
 
     # -- the rest of step()'s loop body
     def diagnostic_update(self):

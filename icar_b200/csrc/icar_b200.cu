@@ -146,6 +146,18 @@ struct icar_ctx {
     unsigned* cfl_max = nullptr;
     double* cfl_dt = nullptr;
     float* cfl_dz = nullptr;
+    // icar_physics_steps: two consecutive steps captured as one CUDA graph (two, because advect() swaps each
+    // field with its output buffer, so the pointer state has period 2)
+    struct StepGraph {
+        cudaGraphExec_t exec = nullptr;
+        float dt = 0.f;
+        bool runs[2] = {false, false};       // does mp() run in step A / B (update_interval, mp_driver.f90:703)
+        float mp_dt[2] = {0.f, 0.f};         // and with which mp_dt (:704)
+        void* vars[ICAR_VAR_COUNT] = {};     // the buffer each variable lived in when the pair was captured
+        long long launches = 0;              // kernels of this library inside the pair
+        bool unsupported = false;            // pointer state did not return after two steps: stay eager
+    } sgraph;
+    long long eager_steps = 0;               // completed icar_physics_step calls with dt > 1e-3 (lazy allocations done)
 };
 
 namespace {
@@ -502,6 +514,7 @@ extern "C" int icar_destroy(icar_ctx* ctx) {
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     if (ctx->comm_stream) cudaStreamSynchronize(ctx->comm_stream);
     if (ctx->aux) cudaStreamSynchronize(ctx->aux);
+    if (ctx->sgraph.exec) cudaGraphExecDestroy(ctx->sgraph.exec);
     if (ctx->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(ctx->comm);
     for (void* p : ctx->vars) if (p) cudaFree(p);
     float* bufs[] = {ctx->U, ctx->V, ctx->W, ctx->Wn, ctx->G, ctx->qa, ctx->qb, ctx->u2, ctx->v2, ctx->w2,
@@ -973,6 +986,19 @@ extern "C" int icar_physics_step(icar_ctx* ctx, float dt) {
         } else {
             int plan[8];
             if (icar_halo_plan(&ctx->grid, ctx->image, ctx->nimages, plan)) return fail(ctx, ICAR_ERR_INVALID, "icar_physics_step: not a slab decomposition");
+            bool due = ctx->opt.microphysics != 0;
+            if (due) {                                                // mp_driver.f90:698-703
+                const double last = ctx->last_model_time == -999.0
+                    ? ctx->model_time - (double)std::max((float)ctx->opt.update_interval, dt) : ctx->last_model_time;
+                due = ((ctx->model_time + (double)dt) - last) >= (double)ctx->opt.update_interval;
+            }
+            if (!due) {
+                // no strips this step: the auxiliary stream carries the halo pack alone, which still has to
+                // start after everything queued on the compute stream
+                if ((rc = join_aux(ctx))) return rc;
+                CU(cudaEventRecord(ctx->ev_fork, ctx->stream));
+                CU(cudaStreamWaitEvent(ctx->aux, ctx->ev_fork, 0));
+            }
             if ((rc = mp_phase(ctx, dt, 0, plan[6], h))) return rc;   // :512  the cells the neighbours need (aux stream)
             if ((rc = halo_send_from(ctx, ctx->aux))) return rc;      // :515  ordered after the strips only
             if ((rc = mp_phase(ctx, dt, 1, plan[6], h))) return rc;   // :523  everything else, overlapping the exchange
@@ -980,11 +1006,119 @@ extern "C" int icar_physics_step(icar_ctx* ctx, float dt) {
             if ((rc = icar_halo_retrieve(ctx))) return rc;            // :526
             if ((rc = advect_impl(ctx, dt, 2))) return rc;            // :529
             ctx->model_time += (double)dt;                            // :547
+            ++ctx->eager_steps;
             return ICAR_OK;
         }
         if ((rc = icar_advect(ctx, dt))) return rc;               // :529
+        ++ctx->eager_steps;
     }
     ctx->model_time += (double)dt;                                // :547
+    return ICAR_OK;
+}
+
+// ---------------------------------------------------------------------------- several steps, as a CUDA graph
+
+namespace {
+
+// What mp() would decide at `model_time` (mp_driver.f90:698-713), without running anything.
+void mp_schedule(const icar_ctx* ctx, double model_time, double last, float dt, bool* runs, float* mp_dt, double* new_last) {
+    *runs = false; *mp_dt = 0.f; *new_last = last;
+    if (ctx->opt.microphysics == 0) return;
+    if (((model_time + (double)dt) - last) >= (double)ctx->opt.update_interval) {
+        *runs = true;
+        *mp_dt = (float)(model_time - last);
+        *new_last = model_time;
+    }
+}
+
+void drop_step_graph(icar_ctx* ctx) {
+    if (ctx->sgraph.exec) cudaGraphExecDestroy(ctx->sgraph.exec);
+    ctx->sgraph.exec = nullptr;
+}
+
+// Runs steps A and B of a pair through the captured graph when that is valid; *ran says whether it did.
+int graph_pair(icar_ctx* ctx, float dt, bool* ran) {
+    *ran = false;
+    icar_ctx::StepGraph& sg = ctx->sgraph;
+    // the eager path has to have run first: it does the lazy allocations and sets the mp_dt lag up
+    if (sg.unsupported || ctx->prof_on || ctx->eager_steps < 2 || ctx->last_model_time == -999.0 ||
+        ctx->aux_pending || ctx->exchange_in_flight)
+        return ICAR_OK;
+    bool runs[2]; float mp_dt[2]; double last = ctx->last_model_time, t = ctx->model_time;
+    mp_schedule(ctx, t, last, dt, &runs[0], &mp_dt[0], &last);
+    mp_schedule(ctx, t + (double)dt, last, dt, &runs[1], &mp_dt[1], &last);
+    const double t_end = (t + (double)dt) + (double)dt;
+    bool match = sg.exec && sg.dt == dt && std::memcmp(sg.vars, ctx->vars, sizeof(sg.vars)) == 0;
+    for (int a = 0; a < 2 && match; ++a) match = sg.runs[a] == runs[a] && (!runs[a] || sg.mp_dt[a] == mp_dt[a]);
+    if (!match) {
+        drop_step_graph(ctx);
+        // Capture queues nothing on the GPU, but the two calls advance the host-side state (clock, launch
+        // counter, buffer roles): snapshot, capture, and put it back.
+        const double t0 = ctx->model_time, last0 = ctx->last_model_time;
+        const long long launches0 = ctx->launches, eager0 = ctx->eager_steps;
+        void* vars0[ICAR_VAR_COUNT]; std::memcpy(vars0, ctx->vars, sizeof(vars0));
+        float* fout0[ICAR_MAX_SCALARS]; std::memcpy(fout0, ctx->fout, sizeof(fout0));
+        float *qa0 = ctx->qa, *qb0 = ctx->qb;
+        CU(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeRelaxed));
+        int rc = icar_physics_step(ctx, dt);
+        if (!rc) rc = icar_physics_step(ctx, dt);
+        if (!rc) rc = join_aux(ctx);
+        cudaGraph_t graph = nullptr;
+        const cudaError_t ce = cudaStreamEndCapture(ctx->stream, &graph);      // always: leaves capture mode
+        const long long pair_launches = ctx->launches - launches0;
+        const bool same_buffers = std::memcmp(vars0, ctx->vars, sizeof(vars0)) == 0 &&
+                                  std::memcmp(fout0, ctx->fout, sizeof(fout0)) == 0 && qa0 == ctx->qa && qb0 == ctx->qb;
+        ctx->model_time = t0; ctx->last_model_time = last0; ctx->launches = launches0; ctx->eager_steps = eager0;
+        std::memcpy(ctx->vars, vars0, sizeof(vars0)); std::memcpy(ctx->fout, fout0, sizeof(fout0));
+        ctx->qa = qa0; ctx->qb = qb0;
+        ctx->aux_pending = false; ctx->exchange_in_flight = false;
+        if (rc || ce != cudaSuccess || !graph) {
+            if (graph) cudaGraphDestroy(graph);
+            cudaGetLastError();
+            sg.unsupported = true;
+            if (rc) return rc;
+            return fail(ctx, ICAR_ERR_CUDA, std::string("icar_physics_steps: stream capture failed: ") + cudaGetErrorString(ce));
+        }
+        if (!same_buffers) {             // the buffer roles have a longer period than two steps: no graph
+            cudaGraphDestroy(graph);
+            sg.unsupported = true;
+            return ICAR_OK;
+        }
+        const cudaError_t ie = cudaGraphInstantiate(&sg.exec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (ie != cudaSuccess) {
+            sg.exec = nullptr; sg.unsupported = true;
+            return fail(ctx, ICAR_ERR_CUDA, std::string("icar_physics_steps: cudaGraphInstantiate: ") + cudaGetErrorString(ie));
+        }
+        sg.dt = dt;
+        for (int a = 0; a < 2; ++a) { sg.runs[a] = runs[a]; sg.mp_dt[a] = mp_dt[a]; }
+        std::memcpy(sg.vars, ctx->vars, sizeof(sg.vars));
+        sg.launches = pair_launches;
+    }
+    CU(cudaGraphLaunch(sg.exec, ctx->stream));
+    ctx->model_time = t_end;
+    ctx->last_model_time = last;
+    ctx->launches += sg.launches;
+    ctx->eager_steps += 2;
+    *ran = true;
+    return ICAR_OK;
+}
+
+}  // namespace
+
+extern "C" int icar_physics_steps(icar_ctx* ctx, float dt, int nsteps, int use_graph) {
+    if (!ctx || nsteps < 0) return fail(ctx, ICAR_ERR_INVALID, "icar_physics_steps: bad argument");
+    CU(cudaSetDevice(ctx->device));
+    int done = 0, rc;
+    while (done < nsteps) {
+        if (use_graph && nsteps - done >= 2 && dt > 1e-3f) {
+            bool ran = false;
+            if ((rc = graph_pair(ctx, dt, &ran))) return rc;
+            if (ran) { done += 2; continue; }
+        }
+        if ((rc = icar_physics_step(ctx, dt))) return rc;
+        ++done;
+    }
     return ICAR_OK;
 }
 
@@ -1252,6 +1386,7 @@ extern "C" int icar_thompson_init(icar_ctx* ctx, const icar_mp_options* opt) {
     CU(cudaGetLastError());
     CU(cudaStreamSynchronize(ctx->stream));
     ctx->th_ready = true;
+    drop_step_graph(ctx);      // the constants are kernel parameters of a captured step
     return ICAR_OK;
 }
 

@@ -31,7 +31,7 @@ module icar_b200_mod
     private
     public :: adv_init, adv_var_request, advect
     public :: mp_init, mp_var_request, mp
-    public :: b200_halo_send, b200_halo_retrieve, b200_sync_to_host, b200_finalize
+    public :: b200_halo_send, b200_halo_retrieve, b200_sync_to_host, b200_finalize, b200_physics_steps
 
     ! enum icar_var
     integer(c_int), parameter :: VAR_U=0, VAR_V=1, VAR_W=2, VAR_PRESSURE=3, VAR_EXNER=4, VAR_DENSITY=5, &
@@ -117,6 +117,12 @@ module icar_b200_mod
             type(c_ptr), value :: ctx
             real(c_float), value :: dt_in
             integer(c_int), value :: halo, subset
+        end function
+        integer(c_int) function icar_physics_steps(ctx, dt, nsteps, use_graph) bind(c)
+            import :: c_int, c_ptr, c_float
+            type(c_ptr), value :: ctx
+            real(c_float), value :: dt
+            integer(c_int), value :: nsteps, use_graph
         end function
         integer(c_int) function icar_halo_send(ctx) bind(c)
             import :: c_int, c_ptr
@@ -290,6 +296,15 @@ contains
     end subroutine
     subroutine b200_halo_retrieve()
         call check(icar_halo_retrieve(ctx), "icar_halo_retrieve")
+    end subroutine
+
+    !> n passes of mp(halo) -> halo_send -> mp(subset) -> halo_retrieve -> advect at a fixed dt, replayed from
+    !> a CUDA graph: what the `do while` loop of step() (time_step.f90:464-549) does between two dt changes
+    !> when microphysics and advection are the only physics switched on
+    subroutine b200_physics_steps(dt, n)
+        real,    intent(in) :: dt
+        integer, intent(in) :: n
+        call check(icar_physics_steps(ctx, dt, int(n, c_int), 1_c_int), "icar_physics_steps")
     end subroutine
 
     !> advect(domain, options, dt) -- advection_driver.f90:51

@@ -173,6 +173,15 @@ int icar_halo_exchange(icar_ctx* ctx);
  * mp(halo) -> halo_send -> mp(subset) -> halo_retrieve -> advect ; model_time += dt. */
 int icar_physics_step(icar_ctx* ctx, float dt);
 
+/* `nsteps` passes of that loop body at a fixed dt -- the `do while (domain%model_time < end_time)` loop of
+ * step(), src/main/time_step.f90:464-549, between two update_dt changes (the caller shortens the last
+ * step itself, :469-471, with one icar_physics_step).  use_graph != 0: pairs of steps are replayed from a
+ * CUDA graph captured on first use (a pair, because advect() swaps every field with its output buffer),
+ * which removes the per-launch host cost; the results are those of nsteps icar_physics_step calls, bit for
+ * bit.  The first two steps of a context, odd remainders, and steps taken while the per-kernel profile is
+ * on always run eagerly. */
+int icar_physics_steps(icar_ctx* ctx, float dt, int nsteps, int use_graph);
+
 /* ---- the rest of step()'s loop body, so that the loop can run without host round trips ("next" rows) */
 
 /* The part of diagnostic_update (src/main/time_step.f90:49-198) that mp / advect read:

@@ -40,9 +40,15 @@ def main():
     dt_one = one.compute_dt(st["dz_levels"])
     dt_all = dom.compute_dt(st["dz_levels"])
     assert dt_one == dt_all == min(dt, 120.0), (dt_one, dt_all, dt)
+    # ICAR_TEST_GRAPH_MULTI=1: the images step through icar_physics_steps (CUDA-graph replay with the NCCL
+    # exchange inside the captured pair) -- not yet validated on hardware, hence opt-in
+    graph = os.environ.get("ICAR_TEST_GRAPH_MULTI", "0") == "1"
     for _ in range(steps):
         one.physics_step(dt)
-        dom.physics_step(dt)
+        if not graph:
+            dom.physics_step(dt)
+    if graph:
+        dom.physics_steps(dt, steps, graph=True)
     dom.synchronize()
     if axis == "x":
         lo = 0 if rank == 0 else grid.its - grid.ims
