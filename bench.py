@@ -74,6 +74,20 @@ def make_state(args):
 _THOMPSON = None
 
 
+def host_cpu():
+    """(model name, logical cores) of the box the CPU baseline runs on."""
+    model = "unknown"
+    try:
+        with open("/proc/cpuinfo") as f:
+            for ln in f:
+                if ln.lower().startswith("model name"):
+                    model = ln.split(":", 1)[1].strip()
+                    break
+    except OSError:
+        pass
+    return model, os.cpu_count() or 1
+
+
 def oracle_stepper(args):
     """step(state, dt, scratch) -> scratch for the scheme's CPU restatement."""
     from oracle import oracle as O
@@ -261,7 +275,8 @@ def run_reference(args, rank, world):
         "config": {"workload": SCHEMES[args.mp]["workload"].format(nx=nx, ny=ny, nz=nz), "grid": [nx, nz, ny], "sample": sample,
                    "note": "CPU restatement (oracle port) of the reference Fortran; the Fortran itself "
                            "cannot be compiled in this image (no gfortran)"},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": thr, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": thr, "kind": "port", "sample": sample,
+                         "cpu_model": host_cpu()[0], "host_logical_cores": host_cpu()[1]},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -383,6 +398,7 @@ def run_b200(args, rank, world, local_rank):
         cpu = {"value": rate, "unit": UNIT, "cores": thr, "kind": "port",
                "sample": f"{csteps} full step(s) of the same {nx}x{nz}x{ny} workload, {csec:.1f} s, "
                          f"OpenMP over j with {thr} threads (oracle/: C++ restatement of the Fortran)"}
+        cpu["cpu_model"], cpu["host_logical_cores"] = host_cpu()
         r1, rows1, sec1 = cpu_oracle_rate_one_thread(args, st, dt)
         cpu["one_thread"] = {"value": r1, "unit": UNIT, "cores": 1,
                              "sample": f"one step of a {nx}x{nz}x{rows1} y-band of the workload, {sec1:.1f} s "
