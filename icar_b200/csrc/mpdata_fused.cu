@@ -537,6 +537,263 @@ k_corrector_fused(const Geom g, const OutSet outs, const __grid_constant__ Fused
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// The same kernel for CPT = 2 with the two cells of a thread carried as one f32x2 pair: sm_100 has
+// packed FADD2 / FMUL2 / FFMA2 (add / sub / mul / fma .f32x2), one issue slot for both cells.  The kernel
+// is issue-bound, and 166 of the 489 instructions of one plane iteration are
+// FADD / FMUL / FFMA that come in such pairs.  Comparisons, selects, min/max, MUFU.RCP and shuffles
+// stay per component.  Each f32x2 operation rounds its two halves like the scalar instruction, so the
+// results are those of k_corrector_fused<2, NZP, 2> up to where the compiler contracts a*b+c there.
+// The plane loop is unrolled by four: the register windows (3 and 4 planes deep) then rotate by
+// renaming instead of 42 moves per iteration.
+// ---------------------------------------------------------------------------------------------
+struct f2 { float x, y; };
+typedef unsigned long long u64;
+__device__ __forceinline__ u64 pk(f2 a) { u64 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a.x), "f"(a.y)); return r; }
+__device__ __forceinline__ f2 up(u64 v) { f2 r; asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v)); return r; }
+__device__ __forceinline__ f2 operator+(f2 a, f2 b) { u64 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(pk(a)), "l"(pk(b))); return up(r); }
+__device__ __forceinline__ f2 operator-(f2 a, f2 b) { u64 r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(pk(a)), "l"(pk(b))); return up(r); }
+__device__ __forceinline__ f2 operator*(f2 a, f2 b) { u64 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(pk(a)), "l"(pk(b))); return up(r); }
+__device__ __forceinline__ f2 fma2(f2 a, f2 b, f2 c) { u64 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(pk(a)), "l"(pk(b)), "l"(pk(c))); return up(r); }
+__device__ __forceinline__ f2 neg2(f2 a) { return f2{-a.x, -a.y}; }
+__device__ __forceinline__ f2 splat(float v) { return f2{v, v}; }
+__device__ __forceinline__ f2 rcp2(f2 a) {
+    f2 r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r.x) : "f"(a.x));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r.y) : "f"(a.y));
+    return r;
+}
+__device__ __forceinline__ f2 div2(f2 a, f2 b) { return a * rcp2(b); }
+__device__ __forceinline__ f2 lane_lo2(f2 v) { return f2{lane_lo(v.x), lane_lo(v.y)}; }
+__device__ __forceinline__ f2 lane_hi2(f2 v) { return f2{lane_hi(v.x), lane_hi(v.y)}; }
+__device__ __forceinline__ f2 donor2(f2 U, f2 l, f2 r) { return U * f2{U.x > 0.f ? l.x : r.x, U.y > 0.f ? l.y : r.y}; }
+__device__ __forceinline__ f2 pos2(f2 v) { return f2{fmaxf(0.f, v.x), fmaxf(0.f, v.y)}; }     // max(0, v)
+__device__ __forceinline__ f2 npos2(f2 v) { return f2{fminf(0.f, v.x), fminf(0.f, v.y)}; }    // min(0, v)
+
+template <int NZP>
+__global__ void __launch_bounds__(TW * (NZP / 2))
+k_corrector_fused_p2(const Geom g, const OutSet outs, const __grid_constant__ FusedMaps maps, const int chunk) {
+    extern __shared__ __align__(128) unsigned char smraw[];
+    constexpr int nzt = NZP / 2;
+    const int tx = threadIdx.x, tz = threadIdx.y;
+    const int scalar = blockIdx.x % outs.n, xt = blockIdx.x / outs.n;
+    float* __restrict__ gout = outs.out[scalar];
+    const int nx = g.nx, nz = g.nz, ny = g.ny;
+    const int x0 = xt * TOUT - 4;
+    const int i = x0 + tx;
+    const bool col = (i >= 0 && i < nx);
+    const bool ilast = (i == nx - 1);
+    const f2 xedge = splat((i == 0 || ilast) ? 0.f : 1.f);
+    const int ja = 1 + blockIdx.y * chunk;
+    const int jb = min(ja + chunk, ny - 1);
+    const int k0 = tz * 2;
+    constexpr int box = NZP * TW;
+    const f2 eps = splat(EPS), e15 = splat(E15);
+
+    enum { R_QLO, R_QHI, R_MHLO, R_MHHI, R_MLLO, R_MLHI, R_FZHI, R_BILO, R_BOLO, R_FLHI, R_COUNT };
+    float* rows = reinterpret_cast<float*>(smraw);
+    constexpr int rows_floats = 2 * R_COUNT * (nzt + 2) * TW;
+    float* stage0 = rows + rows_floats;
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(stage0 + 2 * NF * box);
+    auto row = [&](int buf, int kind, int z) -> float& { return rows[((buf * R_COUNT + kind) * (nzt + 2) + (z + 1)) * TW + tx]; };
+    const int tid = tz * TW + tx;
+    const int niter = jb - ja + 4;
+    const uint32_t stage_bytes = (uint32_t)(NF * nz * TW * sizeof(float));
+
+    auto issue = [&](int it) {
+        const int P = ja - 2 + it, st = it & 1;
+        float* dst = stage0 + st * NF * box;
+        mbar_arrive_expect_tx(&mbar[st], stage_bytes);
+        tma_load_box(dst + F_Q2 * box, &maps.q2[scalar], &mbar[st], x0, 0, P);
+        tma_load_box(dst + F_L * box, &maps.l[scalar], &mbar[st], x0, 0, P);
+#pragma unroll
+        for (int f = 0; f < 3; ++f) tma_load_box(dst + (F_AY + f) * box, &maps.coef[f], &mbar[st], x0, 0, P);
+#pragma unroll
+        for (int f = 3; f < 11; ++f) tma_load_box(dst + (F_AY + f) * box, &maps.coef[f], &mbar[st], x0, 0, P - 2);
+    };
+
+    if (tid == 0) {
+        mbar_init(&mbar[0], 1);
+        mbar_init(&mbar[1], 1);
+        fence_barrier_init();
+    }
+    for (int t = tid; t < 2 * NF * box; t += TW * nzt) stage0[t] = 0.f;
+    if (tz == 0) {
+        for (int b = 0; b < 2; ++b) {
+            row(b, R_QHI, -1) = 0.f; row(b, R_MHHI, -1) = -BIG; row(b, R_MLHI, -1) = BIG;
+            row(b, R_FZHI, -1) = 0.f; row(b, R_FLHI, -1) = 0.f;
+            row(b, R_QLO, nzt) = 0.f; row(b, R_MHLO, nzt) = -BIG; row(b, R_MLLO, nzt) = BIG;
+            row(b, R_BILO, nzt) = 0.f; row(b, R_BOLO, nzt) = 0.f;
+        }
+    }
+    __syncthreads();
+    if (tid == 0) issue(0);
+
+    // per-pair register state; .x = level k0, .y = level k0 + 1 (the windows are those of k_corrector_fused)
+    f2 a0 = splat(0.f), a1 = a0, a2 = a0, a3 = a0;                  // q2 at planes P-3, P-2, P-1, P
+    f2 sx0 = a0, sx1 = a0, sx2 = a0;                                // x-face pair sums at planes P-3, P-2, P-1
+    f2 sz0 = a0, sz1 = a0, sz2 = a0;                                // z-face pair sums
+    f2 mh0 = splat(-BIG), mh1 = mh0, mh2 = mh0;                     // max(q2, l) at planes P-2, P-1, P
+    f2 ml0 = splat(BIG), ml1 = ml0, ml2 = ml0;                      // min(q2, l)
+    f2 v2a = a0, fya = a0, byi = a0, byo = a0, fylp = a0;
+    float qab0 = 0.f, qab1 = 0.f, qab2 = 0.f, qab3 = 0.f;           // q2 of the row above (k0+2) at planes P-3..P
+    float qbl0 = 0.f, qbl1 = 0.f, qbl2 = 0.f, qbl3 = 0.f;           // q2 of the row below (k0-1)
+    const int cell_off = k0 * TW + tx;
+    const bool lev0 = col && (k0 < nz), lev1 = col && (k0 + 1 < nz);
+
+#pragma unroll 4
+    for (int it = 0; it < niter; ++it) {
+        const int P = ja - 2 + it;
+        const int buf = it & 1;
+        const bool pin = (P >= 0 && P < ny);
+        const int Po = P - 2;
+        const bool out_iter = (Po >= ja);
+        if (tid == 0 && it + 1 < niter) issue(it + 1);
+        while (!mbar_try_wait(&mbar[buf], (uint32_t)((it >> 1) & 1))) {}
+        const float* __restrict__ sg = stage0 + buf * NF * box + cell_off;
+        auto ld2 = [&](int f) { return f2{sg[f * box], sg[f * box + TW]}; };
+
+        // ---------------- shift the windows, take plane P from the stage
+        a0 = a1; a1 = a2; a2 = a3;
+        mh0 = mh1; mh1 = mh2;
+        ml0 = ml1; ml1 = ml2;
+        const f2 q2v = ld2(F_Q2), lv = ld2(F_L);
+        const f2 cay = ld2(F_AY), cby = ld2(F_BY), ccy = ld2(F_CY);
+        a3 = q2v;
+        mh2 = f2{(pin && lev0) ? fmaxf(q2v.x, lv.x) : -BIG, (pin && lev1) ? fmaxf(q2v.y, lv.y) : -BIG};
+        ml2 = f2{(pin && lev0) ? fminf(q2v.x, lv.x) : BIG, (pin && lev1) ? fminf(q2v.y, lv.y) : BIG};
+        qab0 = qab1; qab1 = qab2; qab2 = qab3;
+        qbl0 = qbl1; qbl1 = qbl2; qbl2 = qbl3;
+
+        // ---------------- in-plane pseudo-velocities of plane Po = P-2
+        f2 u2 = splat(0.f), w2 = u2, fx = u2, fz = u2, rj = u2, rjz = u2;
+        if (out_iter) {
+            const float sx_ab = qab1 + lane_lo(qab1);
+            const float sx_bl = qbl1 + lane_lo(qbl1);
+            const f2 cax = ld2(F_AX), cbx = ld2(F_BX), ccx = ld2(F_CX), caz = ld2(F_AZ), cbz = ld2(F_BZ), ccz = ld2(F_CZ);
+            rj = ld2(F_RJ);
+            rjz = ld2(F_RJZ);
+            const f2 q = a1;
+            const f2 ql = lane_lo2(q);
+            const f2 qu = f2{a1.y, qab1};
+            // x-face (i-1 | i)
+            const f2 Ax = div2(q - ql, sx1 + eps);
+            const f2 Bx = div2(sx2 - sx0, sx2 + sx0 + eps);
+            const f2 sxu = f2{sx1.y, sx_ab}, sxd = f2{sx_bl, sx1.x};
+            const f2 Cx = div2(sxu - sxd, sxu + sxd + eps);
+            u2 = fma2(neg2(ccx), Cx, fma2(neg2(cbx), Bx, cax * Ax));
+            // z-face above k
+            const f2 Az = div2(qu - q, sz1 + eps);
+            const f2 szr = lane_hi2(sz1), szl = lane_lo2(sz1);
+            const f2 Bz = div2(szr - szl, szr + szl + eps);
+            const f2 Cz = div2(sz2 - sz0, sz2 + sz0 + eps);
+            w2 = fma2(neg2(ccz), Cz, fma2(neg2(cbz), Bz, caz * Az));
+            fx = donor2(u2, ql, q);
+            fz = donor2(w2, q, qu);
+        }
+        // ---------------- publish rows for the z-neighbour threads
+        row(buf, R_QLO, tz) = a3.x;
+        row(buf, R_QHI, tz) = a3.y;
+        if (out_iter) {
+            row(buf, R_MHLO, tz) = mh0.x; row(buf, R_MHHI, tz) = mh0.y;
+            row(buf, R_MLLO, tz) = ml0.x; row(buf, R_MLHI, tz) = ml0.y;
+            row(buf, R_FZHI, tz) = fz.y;
+        }
+        __syncthreads();            // (no read of the TMA stage below this line)
+        qab3 = row(buf, R_QLO, tz + 1);
+        qbl3 = row(buf, R_QHI, tz - 1);
+
+        // ---------------- y-face (P-1 | P): unlimited v2, then beta_y of plane P-1
+        const f2 syv = a3 + a2;
+        const float sy_ab = qab3 + qab2, sy_bl = qbl3 + qbl2;
+        const f2 syr = lane_hi2(syv), syl = lane_lo2(syv);
+        const f2 Ay = div2(a3 - a2, syv + eps);
+        const f2 By = div2(syr - syl, syr + syl + eps);
+        const f2 syu = f2{syv.y, sy_ab}, syd = f2{sy_bl, syv.x};
+        const f2 Cy = div2(syu - syd, syu + syd + eps);
+        const f2 v2b = fma2(neg2(ccy), Cy, fma2(neg2(cby), By, cay * Ay));
+        const f2 fyb = donor2(v2b, a2, a3);                    // face (P-1 | P)
+        // beta_y of cell plane Pc = P-1
+        f2 byi1, byo1;
+        {
+            const int Pc = P - 1;
+            const bool ylast = (Pc == ny - 1);
+            const f2 yedge = splat((Pc == 0 || ylast) ? 0.f : 1.f);
+            const f2 q = a2;
+            const f2 hi = f2{max3(mh0.x, ylast ? q.x : mh1.x, mh2.x), max3(mh0.y, ylast ? q.y : mh1.y, mh2.y)};
+            const f2 lo = f2{min3(ml0.x, ylast ? q.x : ml1.x, ml2.x), min3(ml0.y, ylast ? q.y : ml1.y, ml2.y)};
+            const f2 fin = (pos2(fya) - npos2(fyb)) * yedge;
+            const f2 fout = (pos2(fyb) - npos2(fya)) * yedge;
+            byi1 = div2(hi - q, fin + e15);
+            byo1 = div2(q - lo, fout + e15);
+        }
+        // limited y flux through face (P-2 | P-1)
+        const f2 limy = f2{(v2a.x > 0.f) ? min3(1.f, byi1.x, byo.x) : min3(1.f, byi.x, byo1.x),
+                           (v2a.y > 0.f) ? min3(1.f, byi1.y, byo.y) : min3(1.f, byi.y, byo1.y)};
+        const f2 fyl = limy * fya;
+
+        // ---------------- x / z limiter and corrector update of plane Po
+        if (out_iter) {
+            const float mhb = row(buf, R_MHHI, tz - 1), mlb = row(buf, R_MLHI, tz - 1);
+            const float mha = row(buf, R_MHLO, tz + 1), mla = row(buf, R_MLLO, tz + 1);
+            const float fzb = row(buf, R_FZHI, tz - 1);
+            const f2 q = a1;
+            // x direction
+            const f2 mhl = lane_lo2(mh0), mhr = lane_hi2(mh0), mll = lane_lo2(ml0), mlr = lane_hi2(ml0);
+            const f2 fxp = lane_hi2(fx);
+            const f2 hix = f2{max3(mhl.x, ilast ? q.x : mh0.x, mhr.x), max3(mhl.y, ilast ? q.y : mh0.y, mhr.y)};
+            const f2 lox = f2{min3(mll.x, ilast ? q.x : ml0.x, mlr.x), min3(mll.y, ilast ? q.y : ml0.y, mlr.y)};
+            const f2 finx = (pos2(fx) - npos2(fxp)) * xedge;
+            const f2 foutx = (pos2(fxp) - npos2(fx)) * xedge;
+            const f2 bxi = div2(hix - q, finx + e15);
+            const f2 bxo = div2(q - lox, foutx + e15);
+            // z direction (flux_is_w rules at the line ends, FCT core :75-77, :92-94)
+            const bool zlast0 = (k0 == nz - 1), zlast1 = (k0 + 1 == nz - 1);
+            const f2 fzm = f2{fzb, fz.x};
+            const f2 fzp = f2{zlast0 ? fzm.x : fz.x, zlast1 ? fzm.y : fz.y};
+            const f2 hiz = f2{max3(mhb, zlast0 ? q.x : mh0.x, mh0.y), max3(mh0.x, zlast1 ? q.y : mh0.y, mha)};
+            const f2 loz = f2{min3(mlb, zlast0 ? q.x : ml0.x, ml0.y), min3(ml0.x, zlast1 ? q.y : ml0.y, mla)};
+            const f2 finz = pos2(fzm) - npos2(fzp);
+            const f2 foutz = pos2(fzp) - npos2(fzm);
+            const f2 bzi = div2(hiz - q, finz + e15);
+            const f2 bzo = div2(q - loz, foutz + e15);
+            row(buf, R_BILO, tz) = bzi.x;
+            row(buf, R_BOLO, tz) = bzo.x;
+            __syncthreads();
+            const float bia = row(buf, R_BILO, tz + 1), boa = row(buf, R_BOLO, tz + 1);
+            // limited x flux through face (i-1 | i)
+            const f2 bil = lane_lo2(bxi), bol = lane_lo2(bxo);
+            const f2 limx = f2{(u2.x > 0.f) ? min3(1.f, bxi.x, bol.x) : min3(1.f, bil.x, bxo.x),
+                               (u2.y > 0.f) ? min3(1.f, bxi.y, bol.y) : min3(1.f, bil.y, bxo.y)};
+            const f2 fxl = limx * fx;
+            // limited z flux through the face above k
+            const f2 limz = f2{(w2.x > 0.f) ? min3(1.f, bzi.y, bzo.x) : min3(1.f, bzi.x, bzo.y),
+                               (w2.y > 0.f) ? min3(1.f, bia, bzo.y) : min3(1.f, bzi.y, boa)};
+            const f2 fzl = limz * fz;
+            row(buf, R_FLHI, tz) = fzl.y;
+            __syncthreads();
+            const float fzlb = row(buf, R_FLHI, tz - 1);
+            const bool store_col = col && (tx >= XH) && (tx < TW - XH) && (i >= 1) && (i <= nx - 2);
+            float* __restrict__ op = gout + g.at(col ? i : 0, k0, Po);
+            const f2 fxr = lane_hi2(fxl);
+            const f2 fzd = f2{fzlb, fzl.x};
+            f2 val = fma2(neg2((fxr - fxl) + (fyl - fylp)), rj, q);
+            val = fma2(neg2(fzl - fzd), rjz, val);
+            if (store_col && k0 < nz) op[0] = val.x;
+            if (store_col && k0 + 1 < nz) op[g.ld] = val.y;
+        }
+        // ---------------- roll the y state forward
+        fylp = fyl;
+        v2a = v2b;
+        fya = fyb;
+        byi = byi1; byo = byo1;
+        sx0 = sx1; sx1 = sx2;
+        sz0 = sz1; sz1 = sz2;
+        sx2 = a3 + lane_lo2(a3);
+        sz2 = a3 + f2{a3.y, qab3};
+    }
+}
+
 // ---- host side: tensor maps
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -671,11 +928,23 @@ int fused_advect_all(const Geom& g, const ScalarSet& s, const float* U, const fl
             cudaSuccess) { (void)cudaGetLastError(); return -1; }                                             \
         kern<<<grid, block, plan.smem, st>>>(g, outs, maps, chunk);                                           \
     }
-    if (plan.cpt == 2 && plan.nzp == 20) LAUNCH_FUSED(2, 20, 2)
+    // CPT = 2: the f32x2 form of the kernel (ICAR_CORR_SCALAR=1 selects the scalar one, the reference form)
+    const bool packed = plan.cpt == 2 && !std::getenv("ICAR_CORR_SCALAR");
+#define LAUNCH_PACKED(Z)                                                                                      \
+    {                                                                                                         \
+        auto kern = k_corrector_fused_p2<Z>;                                                                  \
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem) !=        \
+            cudaSuccess) { (void)cudaGetLastError(); return -1; }                                             \
+        kern<<<grid, block, plan.smem, st>>>(g, outs, maps, chunk);                                           \
+    }
+    if (packed && plan.nzp == 20) LAUNCH_PACKED(20)
+    else if (packed && plan.nzp == 40) LAUNCH_PACKED(40)
+    else if (plan.cpt == 2 && plan.nzp == 20) LAUNCH_FUSED(2, 20, 2)
     else if (plan.cpt == 2 && plan.nzp == 40) LAUNCH_FUSED(2, 40, 2)
     else if (plan.nzp == 48) LAUNCH_FUSED(4, 48, 2)
     else LAUNCH_FUSED(4, 64, 1)
 #undef LAUNCH_FUSED
+#undef LAUNCH_PACKED
     ++launches;
     if (marks) cudaEventRecord(marks[3], st);
     return launches;
