@@ -860,6 +860,9 @@ FusedPlan fused_plan(const Geom& g) {
     else if (g.nz <= 48) { p.cpt = 4; p.nzp = 48; }
     else { p.cpt = 4; p.nzp = 64; p.stages = 1; }
     if (env_int("ICAR_FUSED_CPT", 0) == 4 && g.nz <= 48) { p.cpt = 4; p.nzp = 48; }
+    // opt-in until it has run on hardware: 49..52 levels (BASELINE configs[3] has 50) still fit TWO stages
+    // (2 x 13 x 52 x 128 B + rows = 211 KB), so the TMA loads stay one plane ahead instead of being exposed
+    if (env_int("ICAR_FUSED_NZP52", 0) == 1 && g.nz > 48 && g.nz <= 52) { p.cpt = 4; p.nzp = 52; p.stages = 2; }
     const int nzt = p.nzp / p.cpt;
     p.smem = (size_t)(2 * 10 * (nzt + 2) * TW + p.stages * NF * p.nzp * TW) * sizeof(float) + 16;
     int dev = 0, max_optin = 0;
@@ -942,6 +945,7 @@ int fused_advect_all(const Geom& g, const ScalarSet& s, const float* U, const fl
     else if (plan.cpt == 2 && plan.nzp == 20) LAUNCH_FUSED(2, 20, 2)
     else if (plan.cpt == 2 && plan.nzp == 40) LAUNCH_FUSED(2, 40, 2)
     else if (plan.nzp == 48) LAUNCH_FUSED(4, 48, 2)
+    else if (plan.nzp == 52) LAUNCH_FUSED(4, 52, 2)
     else LAUNCH_FUSED(4, 64, 1)
 #undef LAUNCH_FUSED
 #undef LAUNCH_PACKED
