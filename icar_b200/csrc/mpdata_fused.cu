@@ -794,6 +794,290 @@ k_corrector_fused_p2(const Geom g, const OutSet outs, const __grid_constant__ Fu
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// The packed form for NP pairs per thread (ICAR_CORR_V2=1; NOT the default: it has not run on hardware
+// yet).  NP = 2 is what 41..64 levels need (four levels per thread): static count 182 instructions per cell
+// and plane against 225 of k_corrector_fused<4, ..>.  NP = 1 exists to check this kernel against
+// k_corrector_fused_p2, with which it must agree bit for bit.
+// One difference in form, none in value: max(0, f) and min(0, f) of the limiter's in/out flux sums are
+// taken as (f + |f|) and (f - |f|) -- exactly twice the value -- on packed pairs (FADD2 takes |x| and
+// -|x| operands), the factor 0.5 folded into the edge mask and the "+ 1e-15" into one FFMA2.  (For NP = 1
+// that trades 24 FMNMX for packed adds and moves and comes out even: 370 against 369 per plane.)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ f2 abs2(f2 a) { return f2{fabsf(a.x), fabsf(a.y)}; }
+__device__ __forceinline__ f2 twice_pos(f2 f) { return f + abs2(f); }      // 2 max(0, f)
+__device__ __forceinline__ f2 twice_neg(f2 f) { return f - abs2(f); }      // 2 min(0, f)
+
+template <int NP, int NZP, int STAGES>
+__global__ void __launch_bounds__(TW * (NZP / (2 * NP)))
+k_corrector_fused_pk(const Geom g, const OutSet outs, const __grid_constant__ FusedMaps maps, const int chunk) {
+    extern __shared__ __align__(128) unsigned char smraw[];
+    constexpr int CPT = 2 * NP;
+    constexpr int nzt = NZP / CPT;
+    const int tx = threadIdx.x, tz = threadIdx.y;
+    const int scalar = blockIdx.x % outs.n, xt = blockIdx.x / outs.n;
+    float* __restrict__ gout = outs.out[scalar];
+    const int nx = g.nx, nz = g.nz, ny = g.ny;
+    const int x0 = xt * TOUT - 4;
+    const int i = x0 + tx;
+    const bool col = (i >= 0 && i < nx);
+    const bool ilast = (i == nx - 1);
+    const f2 xedge_half = splat((i == 0 || ilast) ? 0.f : 0.5f);
+    const int ja = 1 + blockIdx.y * chunk;
+    const int jb = min(ja + chunk, ny - 1);
+    const int k0 = tz * CPT;
+    constexpr int box = NZP * TW;
+    const f2 eps = splat(EPS), e15 = splat(E15), half = splat(0.5f);
+
+    enum { R_QLO, R_QHI, R_MHLO, R_MHHI, R_MLLO, R_MLHI, R_FZHI, R_BILO, R_BOLO, R_FLHI, R_COUNT };
+    float* rows = reinterpret_cast<float*>(smraw);
+    constexpr int rows_floats = 2 * R_COUNT * (nzt + 2) * TW;
+    float* stage0 = rows + rows_floats;
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(stage0 + STAGES * NF * box);
+    auto row = [&](int buf, int kind, int z) -> float& { return rows[((buf * R_COUNT + kind) * (nzt + 2) + (z + 1)) * TW + tx]; };
+    const int tid = tz * TW + tx;
+    const int niter = jb - ja + 4;
+    const uint32_t stage_bytes = (uint32_t)(NF * nz * TW * sizeof(float));
+
+    auto issue = [&](int it) {
+        const int P = ja - 2 + it, st = (STAGES == 2) ? (it & 1) : 0;
+        float* dst = stage0 + st * NF * box;
+        mbar_arrive_expect_tx(&mbar[st], stage_bytes);
+        tma_load_box(dst + F_Q2 * box, &maps.q2[scalar], &mbar[st], x0, 0, P);
+        tma_load_box(dst + F_L * box, &maps.l[scalar], &mbar[st], x0, 0, P);
+#pragma unroll
+        for (int f = 0; f < 3; ++f) tma_load_box(dst + (F_AY + f) * box, &maps.coef[f], &mbar[st], x0, 0, P);
+#pragma unroll
+        for (int f = 3; f < 11; ++f) tma_load_box(dst + (F_AY + f) * box, &maps.coef[f], &mbar[st], x0, 0, P - 2);
+    };
+
+    if (tid == 0) {
+        mbar_init(&mbar[0], 1);
+        mbar_init(&mbar[1], 1);
+        fence_barrier_init();
+    }
+    for (int t = tid; t < STAGES * NF * box; t += TW * nzt) stage0[t] = 0.f;
+    if (tz == 0) {
+        for (int b = 0; b < 2; ++b) {
+            row(b, R_QHI, -1) = 0.f; row(b, R_MHHI, -1) = -BIG; row(b, R_MLHI, -1) = BIG;
+            row(b, R_FZHI, -1) = 0.f; row(b, R_FLHI, -1) = 0.f;
+            row(b, R_QLO, nzt) = 0.f; row(b, R_MHLO, nzt) = -BIG; row(b, R_MLLO, nzt) = BIG;
+            row(b, R_BILO, nzt) = 0.f; row(b, R_BOLO, nzt) = 0.f;
+        }
+    }
+    __syncthreads();
+    if (tid == 0) issue(0);
+
+    // pair p of a thread holds levels k0 + 2p (.x) and k0 + 2p + 1 (.y)
+    f2 a0[NP], a1[NP], a2[NP], a3[NP];          // q2 at planes P-3, P-2, P-1, P
+    f2 sx0[NP], sx1[NP], sx2[NP];               // x-face pair sums at planes P-3, P-2, P-1
+    f2 sz0[NP], sz1[NP], sz2[NP];               // z-face pair sums
+    f2 mh0[NP], mh1[NP], mh2[NP];               // max(q2, l) at planes P-2, P-1, P
+    f2 ml0[NP], ml1[NP], ml2[NP];               // min(q2, l)
+    f2 v2a[NP], fya[NP], byi[NP], byo[NP], fylp[NP];
+    bool lev[NP][2];
+#pragma unroll
+    for (int p = 0; p < NP; ++p) {
+        a0[p] = a1[p] = a2[p] = a3[p] = splat(0.f);
+        sx0[p] = sx1[p] = sx2[p] = sz0[p] = sz1[p] = sz2[p] = splat(0.f);
+        mh0[p] = mh1[p] = mh2[p] = splat(-BIG);
+        ml0[p] = ml1[p] = ml2[p] = splat(BIG);
+        v2a[p] = fya[p] = byi[p] = byo[p] = fylp[p] = splat(0.f);
+        lev[p][0] = col && (k0 + 2 * p < nz);
+        lev[p][1] = col && (k0 + 2 * p + 1 < nz);
+    }
+    float qab0 = 0.f, qab1 = 0.f, qab2 = 0.f, qab3 = 0.f;           // q2 of the row above (k0+CPT) at planes P-3..P
+    float qbl0 = 0.f, qbl1 = 0.f, qbl2 = 0.f, qbl3 = 0.f;           // q2 of the row below (k0-1)
+    const int cell_off = k0 * TW + tx;
+    // {v[p].y, v[p+1].x} with `above` after the last pair; {v[p-1].y, v[p].x} with `below` before the first
+    auto up_of = [&](const f2 (&v)[NP], int p, float above) { return f2{v[p].y, (p + 1 < NP) ? v[(p + 1 < NP) ? p + 1 : p].x : above}; };
+    auto dn_of = [&](const f2 (&v)[NP], int p, float below) { return f2{(p > 0) ? v[(p > 0) ? p - 1 : p].y : below, v[p].x}; };
+
+#pragma unroll(NP == 1 ? 4 : 2)
+    for (int it = 0; it < niter; ++it) {
+        const int P = ja - 2 + it;
+        const int buf = it & 1;
+        const bool pin = (P >= 0 && P < ny);
+        const int Po = P - 2;
+        const bool out_iter = (Po >= ja);
+        if (STAGES == 2) { if (tid == 0 && it + 1 < niter) issue(it + 1); }
+        else             { if (tid == 0 && it > 0) issue(it); }
+        const int st = (STAGES == 2) ? buf : 0;
+        while (!mbar_try_wait(&mbar[st], (uint32_t)((STAGES == 2) ? ((it >> 1) & 1) : (it & 1)))) {}
+        const float* __restrict__ sg = stage0 + st * NF * box + cell_off;
+        auto ld2 = [&](int f, int p) { return f2{sg[f * box + (2 * p) * TW], sg[f * box + (2 * p + 1) * TW]}; };
+
+        // ---------------- shift the windows, take plane P from the stage
+        f2 cay[NP], cby[NP], ccy[NP];
+#pragma unroll
+        for (int p = 0; p < NP; ++p) {
+            a0[p] = a1[p]; a1[p] = a2[p]; a2[p] = a3[p];
+            mh0[p] = mh1[p]; mh1[p] = mh2[p];
+            ml0[p] = ml1[p]; ml1[p] = ml2[p];
+            const f2 q2v = ld2(F_Q2, p), lv = ld2(F_L, p);
+            cay[p] = ld2(F_AY, p); cby[p] = ld2(F_BY, p); ccy[p] = ld2(F_CY, p);
+            a3[p] = q2v;
+            mh2[p] = f2{(pin && lev[p][0]) ? fmaxf(q2v.x, lv.x) : -BIG, (pin && lev[p][1]) ? fmaxf(q2v.y, lv.y) : -BIG};
+            ml2[p] = f2{(pin && lev[p][0]) ? fminf(q2v.x, lv.x) : BIG, (pin && lev[p][1]) ? fminf(q2v.y, lv.y) : BIG};
+        }
+        qab0 = qab1; qab1 = qab2; qab2 = qab3;
+        qbl0 = qbl1; qbl1 = qbl2; qbl2 = qbl3;
+
+        // ---------------- in-plane pseudo-velocities of plane Po = P-2
+        f2 u2[NP], w2[NP], fx[NP], fz[NP], rj[NP], rjz[NP];
+#pragma unroll
+        for (int p = 0; p < NP; ++p) u2[p] = w2[p] = fx[p] = fz[p] = rj[p] = rjz[p] = splat(0.f);
+        if (out_iter) {
+            const float sx_ab = qab1 + lane_lo(qab1);
+            const float sx_bl = qbl1 + lane_lo(qbl1);
+#pragma unroll
+            for (int p = 0; p < NP; ++p) {
+                const f2 cax = ld2(F_AX, p), cbx = ld2(F_BX, p), ccx = ld2(F_CX, p), caz = ld2(F_AZ, p),
+                         cbz = ld2(F_BZ, p), ccz = ld2(F_CZ, p);
+                rj[p] = ld2(F_RJ, p);
+                rjz[p] = ld2(F_RJZ, p);
+                const f2 q = a1[p];
+                const f2 ql = lane_lo2(q);
+                const f2 qu = up_of(a1, p, qab1);
+                // x-face (i-1 | i)
+                const f2 Ax = div2(q - ql, sx1[p] + eps);
+                const f2 Bx = div2(sx2[p] - sx0[p], sx2[p] + sx0[p] + eps);
+                const f2 sxu = up_of(sx1, p, sx_ab), sxd = dn_of(sx1, p, sx_bl);
+                const f2 Cx = div2(sxu - sxd, sxu + sxd + eps);
+                u2[p] = fma2(neg2(ccx), Cx, fma2(neg2(cbx), Bx, cax * Ax));
+                // z-face above k
+                const f2 Az = div2(qu - q, sz1[p] + eps);
+                const f2 szr = lane_hi2(sz1[p]), szl = lane_lo2(sz1[p]);
+                const f2 Bz = div2(szr - szl, szr + szl + eps);
+                const f2 Cz = div2(sz2[p] - sz0[p], sz2[p] + sz0[p] + eps);
+                w2[p] = fma2(neg2(ccz), Cz, fma2(neg2(cbz), Bz, caz * Az));
+                fx[p] = donor2(u2[p], ql, q);
+                fz[p] = donor2(w2[p], q, qu);
+            }
+        }
+        // ---------------- publish rows for the z-neighbour threads
+        row(buf, R_QLO, tz) = a3[0].x;
+        row(buf, R_QHI, tz) = a3[NP - 1].y;
+        if (out_iter) {
+            row(buf, R_MHLO, tz) = mh0[0].x; row(buf, R_MHHI, tz) = mh0[NP - 1].y;
+            row(buf, R_MLLO, tz) = ml0[0].x; row(buf, R_MLHI, tz) = ml0[NP - 1].y;
+            row(buf, R_FZHI, tz) = fz[NP - 1].y;
+        }
+        __syncthreads();            // (no read of the TMA stage below this line)
+        qab3 = row(buf, R_QLO, tz + 1);
+        qbl3 = row(buf, R_QHI, tz - 1);
+
+        // ---------------- y-face (P-1 | P): unlimited v2, then beta_y of plane P-1, then the limited flux
+        f2 v2b[NP], fyb[NP], syv[NP], byi1[NP], byo1[NP], fyl[NP];
+#pragma unroll
+        for (int p = 0; p < NP; ++p) syv[p] = a3[p] + a2[p];
+        const float sy_ab = qab3 + qab2, sy_bl = qbl3 + qbl2;
+        const int Pc = P - 1;
+        const bool ylast = (Pc == ny - 1);
+        const f2 yedge_half = splat((Pc == 0 || ylast) ? 0.f : 0.5f);
+#pragma unroll
+        for (int p = 0; p < NP; ++p) {
+            const f2 syr = lane_hi2(syv[p]), syl = lane_lo2(syv[p]);
+            const f2 Ay = div2(a3[p] - a2[p], syv[p] + eps);
+            const f2 By = div2(syr - syl, syr + syl + eps);
+            const f2 syu = up_of(syv, p, sy_ab), syd = dn_of(syv, p, sy_bl);
+            const f2 Cy = div2(syu - syd, syu + syd + eps);
+            v2b[p] = fma2(neg2(ccy[p]), Cy, fma2(neg2(cby[p]), By, cay[p] * Ay));
+            fyb[p] = donor2(v2b[p], a2[p], a3[p]);                    // face (P-1 | P)
+            // beta_y of cell plane Pc = P-1
+            const f2 q = a2[p];
+            const f2 hi = f2{max3(mh0[p].x, ylast ? q.x : mh1[p].x, mh2[p].x), max3(mh0[p].y, ylast ? q.y : mh1[p].y, mh2[p].y)};
+            const f2 lo = f2{min3(ml0[p].x, ylast ? q.x : ml1[p].x, ml2[p].x), min3(ml0[p].y, ylast ? q.y : ml1[p].y, ml2[p].y)};
+            const f2 fin2 = twice_pos(fya[p]) - twice_neg(fyb[p]);
+            const f2 fout2 = twice_pos(fyb[p]) - twice_neg(fya[p]);
+            byi1[p] = div2(hi - q, fma2(fin2, yedge_half, e15));
+            byo1[p] = div2(q - lo, fma2(fout2, yedge_half, e15));
+            // limited y flux through face (P-2 | P-1)
+            const f2 limy = f2{(v2a[p].x > 0.f) ? min3(1.f, byi1[p].x, byo[p].x) : min3(1.f, byi[p].x, byo1[p].x),
+                               (v2a[p].y > 0.f) ? min3(1.f, byi1[p].y, byo[p].y) : min3(1.f, byi[p].y, byo1[p].y)};
+            fyl[p] = limy * fya[p];
+        }
+
+        // ---------------- x / z limiter and corrector update of plane Po
+        if (out_iter) {
+            const float mhb = row(buf, R_MHHI, tz - 1), mlb = row(buf, R_MLHI, tz - 1);
+            const float mha = row(buf, R_MHLO, tz + 1), mla = row(buf, R_MLLO, tz + 1);
+            const float fzb = row(buf, R_FZHI, tz - 1);
+            f2 bxi[NP], bxo[NP], bzi[NP], bzo[NP];
+#pragma unroll
+            for (int p = 0; p < NP; ++p) {
+                const f2 q = a1[p];
+                // x direction
+                const f2 mhl = lane_lo2(mh0[p]), mhr = lane_hi2(mh0[p]), mll = lane_lo2(ml0[p]), mlr = lane_hi2(ml0[p]);
+                const f2 fxp = lane_hi2(fx[p]);
+                const f2 hix = f2{max3(mhl.x, ilast ? q.x : mh0[p].x, mhr.x), max3(mhl.y, ilast ? q.y : mh0[p].y, mhr.y)};
+                const f2 lox = f2{min3(mll.x, ilast ? q.x : ml0[p].x, mlr.x), min3(mll.y, ilast ? q.y : ml0[p].y, mlr.y)};
+                const f2 finx2 = twice_pos(fx[p]) - twice_neg(fxp);
+                const f2 foutx2 = twice_pos(fxp) - twice_neg(fx[p]);
+                bxi[p] = div2(hix - q, fma2(finx2, xedge_half, e15));
+                bxo[p] = div2(q - lox, fma2(foutx2, xedge_half, e15));
+                // z direction (flux_is_w rules at the line ends, FCT core :75-77, :92-94)
+                const bool zlast0 = (k0 + 2 * p == nz - 1), zlast1 = (k0 + 2 * p + 1 == nz - 1);
+                const f2 mhd = dn_of(mh0, p, mhb), mhu = up_of(mh0, p, mha);
+                const f2 mld = dn_of(ml0, p, mlb), mlu = up_of(ml0, p, mla);
+                const f2 fzm = dn_of(fz, p, fzb);
+                const f2 fzp = f2{zlast0 ? fzm.x : fz[p].x, zlast1 ? fzm.y : fz[p].y};
+                const f2 hiz = f2{max3(mhd.x, zlast0 ? q.x : mh0[p].x, mhu.x), max3(mhd.y, zlast1 ? q.y : mh0[p].y, mhu.y)};
+                const f2 loz = f2{min3(mld.x, zlast0 ? q.x : ml0[p].x, mlu.x), min3(mld.y, zlast1 ? q.y : ml0[p].y, mlu.y)};
+                const f2 finz2 = twice_pos(fzm) - twice_neg(fzp);
+                const f2 foutz2 = twice_pos(fzp) - twice_neg(fzm);
+                bzi[p] = div2(hiz - q, fma2(finz2, half, e15));
+                bzo[p] = div2(q - loz, fma2(foutz2, half, e15));
+            }
+            row(buf, R_BILO, tz) = bzi[0].x;
+            row(buf, R_BOLO, tz) = bzo[0].x;
+            __syncthreads();
+            const float bia = row(buf, R_BILO, tz + 1), boa = row(buf, R_BOLO, tz + 1);
+            f2 fxl[NP], fzl[NP];
+#pragma unroll
+            for (int p = 0; p < NP; ++p) {
+                // limited x flux through face (i-1 | i)
+                const f2 bil = lane_lo2(bxi[p]), bol = lane_lo2(bxo[p]);
+                const f2 limx = f2{(u2[p].x > 0.f) ? min3(1.f, bxi[p].x, bol.x) : min3(1.f, bil.x, bxo[p].x),
+                                   (u2[p].y > 0.f) ? min3(1.f, bxi[p].y, bol.y) : min3(1.f, bil.y, bxo[p].y)};
+                fxl[p] = limx * fx[p];
+                // limited z flux through the face above k
+                const f2 biu = up_of(bzi, p, bia), bou = up_of(bzo, p, boa);
+                const f2 limz = f2{(w2[p].x > 0.f) ? min3(1.f, biu.x, bzo[p].x) : min3(1.f, bzi[p].x, bou.x),
+                                   (w2[p].y > 0.f) ? min3(1.f, biu.y, bzo[p].y) : min3(1.f, bzi[p].y, bou.y)};
+                fzl[p] = limz * fz[p];
+            }
+            row(buf, R_FLHI, tz) = fzl[NP - 1].y;
+            __syncthreads();
+            const float fzlb = row(buf, R_FLHI, tz - 1);
+            const bool store_col = col && (tx >= XH) && (tx < TW - XH) && (i >= 1) && (i <= nx - 2);
+            float* __restrict__ op = gout + g.at(col ? i : 0, k0, Po);
+#pragma unroll
+            for (int p = 0; p < NP; ++p) {
+                const f2 fxr = lane_hi2(fxl[p]);
+                const f2 fzd = dn_of(fzl, p, fzlb);
+                f2 val = fma2(neg2((fxr - fxl[p]) + (fyl[p] - fylp[p])), rj[p], a1[p]);
+                val = fma2(neg2(fzl[p] - fzd), rjz[p], val);
+                if (store_col && k0 + 2 * p < nz) op[(2 * p) * g.ld] = val.x;
+                if (store_col && k0 + 2 * p + 1 < nz) op[(2 * p + 1) * g.ld] = val.y;
+            }
+        }
+        // ---------------- roll the y state forward
+#pragma unroll
+        for (int p = 0; p < NP; ++p) {
+            fylp[p] = fyl[p];
+            v2a[p] = v2b[p];
+            fya[p] = fyb[p];
+            byi[p] = byi1[p]; byo[p] = byo1[p];
+            sx0[p] = sx1[p]; sx1[p] = sx2[p];
+            sz0[p] = sz1[p]; sz1[p] = sz2[p];
+            sx2[p] = a3[p] + lane_lo2(a3[p]);
+        }
+#pragma unroll
+        for (int p = 0; p < NP; ++p) sz2[p] = a3[p] + up_of(a3, p, qab3);
+    }
+}
+
 // ---- host side: tensor maps
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -940,7 +1224,21 @@ int fused_advect_all(const Geom& g, const ScalarSet& s, const float* U, const fl
             cudaSuccess) { (void)cudaGetLastError(); return -1; }                                             \
         kern<<<grid, block, plan.smem, st>>>(g, outs, maps, chunk);                                           \
     }
-    if (packed && plan.nzp == 20) LAUNCH_PACKED(20)
+    // candidate form of the packed kernel, opt-in until it has been validated on hardware
+    const bool v2 = env_int("ICAR_CORR_V2", 0) == 1;
+#define LAUNCH_PK(NPAIRS, Z, S)                                                                               \
+    {                                                                                                         \
+        auto kern = k_corrector_fused_pk<NPAIRS, Z, S>;                                                       \
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem) !=        \
+            cudaSuccess) { (void)cudaGetLastError(); return -1; }                                             \
+        kern<<<grid, block, plan.smem, st>>>(g, outs, maps, chunk);                                           \
+    }
+    if (v2 && plan.cpt == 2 && plan.nzp == 20) LAUNCH_PK(1, 20, 2)
+    else if (v2 && plan.cpt == 2 && plan.nzp == 40) LAUNCH_PK(1, 40, 2)
+    else if (v2 && plan.nzp == 48) LAUNCH_PK(2, 48, 2)
+    else if (v2 && plan.nzp == 52) LAUNCH_PK(2, 52, 2)
+    else if (v2 && plan.nzp == 64) LAUNCH_PK(2, 64, 1)
+    else if (packed && plan.nzp == 20) LAUNCH_PACKED(20)
     else if (packed && plan.nzp == 40) LAUNCH_PACKED(40)
     else if (plan.cpt == 2 && plan.nzp == 20) LAUNCH_FUSED(2, 20, 2)
     else if (plan.cpt == 2 && plan.nzp == 40) LAUNCH_FUSED(2, 40, 2)
@@ -949,6 +1247,7 @@ int fused_advect_all(const Geom& g, const ScalarSet& s, const float* U, const fl
     else LAUNCH_FUSED(4, 64, 1)
 #undef LAUNCH_FUSED
 #undef LAUNCH_PACKED
+#undef LAUNCH_PK
     ++launches;
     if (marks) cudaEventRecord(marks[3], st);
     return launches;
