@@ -36,6 +36,7 @@
 #include <unordered_map>
 
 #include "common.cuh"
+#include "f32x2.cuh"
 #include "mpdata.cuh"
 
 namespace icar {
@@ -547,23 +548,6 @@ k_corrector_fused(const Geom g, const OutSet outs, const __grid_constant__ Fused
 // The plane loop is unrolled by four: the register windows (3 and 4 planes deep) then rotate by
 // renaming instead of 42 moves per iteration.
 // ---------------------------------------------------------------------------------------------
-struct f2 { float x, y; };
-typedef unsigned long long u64;
-__device__ __forceinline__ u64 pk(f2 a) { u64 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a.x), "f"(a.y)); return r; }
-__device__ __forceinline__ f2 up(u64 v) { f2 r; asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v)); return r; }
-__device__ __forceinline__ f2 operator+(f2 a, f2 b) { u64 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(pk(a)), "l"(pk(b))); return up(r); }
-__device__ __forceinline__ f2 operator-(f2 a, f2 b) { u64 r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(pk(a)), "l"(pk(b))); return up(r); }
-__device__ __forceinline__ f2 operator*(f2 a, f2 b) { u64 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(pk(a)), "l"(pk(b))); return up(r); }
-__device__ __forceinline__ f2 fma2(f2 a, f2 b, f2 c) { u64 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(pk(a)), "l"(pk(b)), "l"(pk(c))); return up(r); }
-__device__ __forceinline__ f2 neg2(f2 a) { return f2{-a.x, -a.y}; }
-__device__ __forceinline__ f2 splat(float v) { return f2{v, v}; }
-__device__ __forceinline__ f2 rcp2(f2 a) {
-    f2 r;
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r.x) : "f"(a.x));
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r.y) : "f"(a.y));
-    return r;
-}
-__device__ __forceinline__ f2 div2(f2 a, f2 b) { return a * rcp2(b); }
 __device__ __forceinline__ f2 lane_lo2(f2 v) { return f2{lane_lo(v.x), lane_lo(v.y)}; }
 __device__ __forceinline__ f2 lane_hi2(f2 v) { return f2{lane_hi(v.x), lane_hi(v.y)}; }
 __device__ __forceinline__ f2 donor2(f2 U, f2 l, f2 r) { return U * f2{U.x > 0.f ? l.x : r.x, U.y > 0.f ? l.y : r.y}; }
