@@ -1318,6 +1318,37 @@ extern "C" int icar_physics_step_host(icar_ctx* ctx, float dt, const icar_host_d
     return ICAR_OK;
 }
 
+// diagnostic_update + the physics step on host arrays: exner and density are not uploaded but taken on the
+// device from the pressure and potential temperature just uploaded (time_step.f90:85-101), which is what
+// step()'s loop does before the physics and saves two of the thirteen per-step input fields on the PCIe side.
+extern "C" int icar_step_host(icar_ctx* ctx, float dt, const icar_host_domain* dom) {
+    if (!ctx || !dom) return fail(ctx, ICAR_ERR_INVALID, "icar_step_host: null argument");
+    if (dom->exner || dom->density)
+        return fail(ctx, ICAR_ERR_INVALID, "icar_step_host: exner and density are derived on the device; pass them as NULL "
+                                           "(icar_physics_step_host takes them from the host)");
+    CU(cudaSetDevice(ctx->device));
+    std::vector<HostField> f;
+    host_fields(dom, f);
+    int rc;
+    for (const HostField& h : f) {
+        if (!h.in) continue;
+        int width, pitch; size_t rows;
+        var_geometry(ctx, h.var, &width, &pitch, &rows);
+        if ((rc = copy_in(ctx, ctx->vars[h.var], h.in, width, pitch, rows, elem_size(h.var)))) return rc;
+        ctx->uploaded[h.var] = true;
+    }
+    if ((rc = icar_diagnostic_update(ctx))) return rc;
+    if ((rc = icar_physics_step(ctx, dt))) return rc;
+    for (const HostField& h : f) {
+        if (!h.out) continue;
+        int width, pitch; size_t rows;
+        var_geometry(ctx, h.var, &width, &pitch, &rows);
+        if ((rc = copy_out(ctx, h.out, ctx->vars[h.var], width, pitch, rows, elem_size(h.var)))) return rc;
+    }
+    CU(cudaStreamSynchronize(ctx->stream));
+    return ICAR_OK;
+}
+
 extern "C" int icar_host_register(icar_ctx* ctx, const icar_host_domain* dom) {
     if (!ctx || !dom) return fail(ctx, ICAR_ERR_INVALID, "icar_host_register: null argument");
     CU(cudaSetDevice(ctx->device));

@@ -356,6 +356,10 @@ typedef struct icar_host_domain {
  * uploaded once with icar_upload (the reference passes `domain` to adv_init, so a shim can do
  * that there).  icar_host_register pins the host arrays so the copies run at PCIe speed. */
 int icar_physics_step_host(icar_ctx* ctx, float dt, const icar_host_domain* dom);
+/* The same with diagnostic_update's exner / density (src/main/time_step.f90:85-101) taken on the device from the
+ * pressure and potential temperature of this call: dom->exner and dom->density must be NULL.  Two of the
+ * thirteen per-step input fields do not cross PCIe. */
+int icar_step_host(icar_ctx* ctx, float dt, const icar_host_domain* dom);
 int icar_host_register(icar_ctx* ctx, const icar_host_domain* dom);
 int icar_host_unregister(icar_ctx* ctx, const icar_host_domain* dom);
 
