@@ -1349,6 +1349,44 @@ extern "C" int icar_step_host(icar_ctx* ctx, float dt, const icar_host_domain* d
     return ICAR_OK;
 }
 
+// The host step with separate input and output arrays and a row range for the outputs: what a caller needs
+// to pipeline one model step over several contexts that each hold a band of rows (icar_b200/pipeline.py).
+// `in`: every non-NULL member is uploaded (the whole tile).  `out`: every non-NULL output member receives the
+// tile's rows row0..row1 (0-based y index, inclusive); the pointer addresses the tile's row 0.
+extern "C" int icar_physics_step_host_io(icar_ctx* ctx, float dt, const icar_host_domain* in, const icar_host_domain* out,
+                                         int row0, int row1, int derive_diagnostics) {
+    if (!ctx || !in || !out) return fail(ctx, ICAR_ERR_INVALID, "icar_physics_step_host_io: null argument");
+    if (row0 < 0 || row1 >= ctx->g.ny || row1 < row0) return fail(ctx, ICAR_ERR_INVALID, "icar_physics_step_host_io: bad row range");
+    if (derive_diagnostics && (in->exner || in->density))
+        return fail(ctx, ICAR_ERR_INVALID, "icar_physics_step_host_io: exner and density are derived on the device; pass them as NULL");
+    CU(cudaSetDevice(ctx->device));
+    std::vector<HostField> fi, fo;
+    host_fields(in, fi);
+    host_fields(out, fo);
+    int rc;
+    for (const HostField& h : fi) {
+        if (!h.in) continue;
+        int width, pitch; size_t rows;
+        var_geometry(ctx, h.var, &width, &pitch, &rows);
+        if ((rc = copy_in(ctx, ctx->vars[h.var], h.in, width, pitch, rows, elem_size(h.var)))) return rc;
+        ctx->uploaded[h.var] = true;
+    }
+    if (derive_diagnostics && (rc = icar_diagnostic_update(ctx))) return rc;
+    if ((rc = icar_physics_step(ctx, dt))) return rc;
+    for (const HostField& h : fo) {
+        if (!h.out) continue;
+        int width, pitch; size_t rows;
+        var_geometry(ctx, h.var, &width, &pitch, &rows);
+        const size_t es = elem_size(h.var);
+        const size_t lines_per_row = (var_shape(h.var) == D2) ? 1 : (size_t)ctx->g.nz;       // x-lines per y index
+        const size_t first = lines_per_row * (size_t)row0, count = lines_per_row * (size_t)(row1 - row0 + 1);
+        if ((rc = copy_out(ctx, (char*)h.out + first * (size_t)width * es,
+                           (const char*)ctx->vars[h.var] + first * (size_t)pitch * es, width, pitch, count, es))) return rc;
+    }
+    CU(cudaStreamSynchronize(ctx->stream));
+    return ICAR_OK;
+}
+
 extern "C" int icar_host_register(icar_ctx* ctx, const icar_host_domain* dom) {
     if (!ctx || !dom) return fail(ctx, ICAR_ERR_INVALID, "icar_host_register: null argument");
     CU(cudaSetDevice(ctx->device));

@@ -360,6 +360,14 @@ int icar_physics_step_host(icar_ctx* ctx, float dt, const icar_host_domain* dom)
  * pressure and potential temperature of this call: dom->exner and dom->density must be NULL.  Two of the
  * thirteen per-step input fields do not cross PCIe. */
 int icar_step_host(icar_ctx* ctx, float dt, const icar_host_domain* dom);
+/* The host step with separate input and output arrays and a row range for the outputs, so that one model
+ * step can be pipelined over several contexts that each hold a band of rows (upload of the next band,
+ * kernels of this one and download of the previous one overlap; icar_b200/pipeline.py).  Every non-NULL
+ * member of `in` is uploaded (whole tile); every non-NULL output member of `out` receives the tile's rows
+ * row0..row1 (0-based y index, inclusive) at its place in an array whose row 0 is the tile's row 0.
+ * derive_diagnostics != 0: exner / density as in icar_step_host. */
+int icar_physics_step_host_io(icar_ctx* ctx, float dt, const icar_host_domain* in, const icar_host_domain* out,
+                              int row0, int row1, int derive_diagnostics);
 int icar_host_register(icar_ctx* ctx, const icar_host_domain* dom);
 int icar_host_unregister(icar_ctx* ctx, const icar_host_domain* dom);
 

@@ -7,9 +7,9 @@ mkdir -p gpurun_out
 python -c "import __graft_entry__ as g; g.build()" 2>&1 | tail -1
 ICAR_TEST_UNVALIDATED=1 timeout 300 python -m pytest tests/test_gpu_parity.py -m gpu -q \
     -k "candidate or 52_level or packed" > gpurun_out/candidates_tests.log 2>&1
-ICAR_TEST_UNVALIDATED=1 timeout 120 python -m pytest tests/test_gpu_step_loop.py -m gpu -q -k step_host >> gpurun_out/candidates_tests.log 2>&1
+ICAR_TEST_UNVALIDATED=1 timeout 120 python -m pytest tests/test_gpu_step_loop.py -m gpu -q -k "step_host or host_pipeline" >> gpurun_out/candidates_tests.log 2>&1
 tail -15 gpurun_out/candidates_tests.log
-P='import sys,json; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print(sys.argv[1], "ms/step", round(d["ms_per_step"],4), {k:round(v["ms_per_step"],4) for k,v in d["kernels"].items()})'
+P='import sys,json; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print(sys.argv[1], "ms/step", round(d["ms_per_step"],4), "e2e ms", round(d["e2e"]["ms_per_step"],2), {k:round(v["ms_per_step"],4) for k,v in d["kernels"].items()})'
 run() {  # name, env assignments..., then -- bench arguments
     name=$1; shift
     envs=()
@@ -23,7 +23,10 @@ run default --
 run pass1_packed ICAR_UPWIND_PACKED=1 --
 run corr_scalar ICAR_CORR_SCALAR=1 --
 run graph -- --graph
-run derive_diagnostics -- --derive-diagnostics     # look at e2e in gpurun_out/cand_derive_diagnostics.json
+run derive_diagnostics -- --derive-diagnostics     # look at e2e in gpurun_out/cand_*.json for these four
+run e2e_bands4 -- --e2e-bands 4
+run e2e_bands8 -- --e2e-bands 8
+run e2e_bands8_derive -- --e2e-bands 8 --derive-diagnostics
 run nz50_default -- --nz 50
 run nz50_two_stages ICAR_FUSED_NZP52=1 -- --nz 50
 run nz50_packed ICAR_CORR_V2=1 -- --nz 50

@@ -199,3 +199,15 @@ def test_ctypes_structs_match_the_header_member_order():
     enum = dict((k, int(v)) for k, v in re.findall(r"(ICAR_VAR_[A-Z_]+)\s*=\s*(\d+)", hdr))
     for name, idx in icar_b200.VAR.items():
         assert enum["ICAR_VAR_" + name.upper()] == idx, name
+
+
+def test_pipeline_band_bounds_cover_the_domain_once():
+    """icar_b200.pipeline.band_bounds: owned rows partition 0..ny-1, held rows add the ghost rows inside the domain."""
+    from icar_b200.pipeline import band_bounds
+    for ny, bands, halo in [(512, 8, 4), (70, 3, 4), (70, 5, 4), (9, 4, 4), (64, 1, 4), (100, 64, 4)]:
+        bb = band_bounds(ny, bands, halo)
+        owned = [r for (a, b, _, _) in bb for r in range(a, b + 1)]
+        assert owned == list(range(ny)), (ny, bands)
+        for (a, b, v0, v1) in bb:
+            assert v0 == max(0, a - halo) and v1 == min(ny - 1, b + halo)
+            assert b - a + 1 >= min(ny, 2 * halo)                  # a band is never thinner than its two halos

@@ -175,3 +175,42 @@ def test_step_host_derives_exner_and_density_on_the_device(gpu_lib):
     dom.step_host(dt, dom.host_domain(host))
     for k in ("th", "qv", "qc", "qr", "qs", "precipitation"):
         np.testing.assert_array_equal(host[k], ref.download(k), err_msg=k)
+
+
+@pytest.mark.skipif(__import__("os").environ.get("ICAR_TEST_UNVALIDATED") != "1",
+                    reason="not yet run on hardware (set ICAR_TEST_UNVALIDATED=1)")
+@pytest.mark.parametrize("bands,derive", [(3, False), (5, True), (1, False)])
+def test_host_pipeline_equals_the_undivided_host_step(gpu_lib, bands, derive):
+    """icar_b200.pipeline.HostPipeline: bands of rows as stand-alone tiles with 4 ghost rows, stepped
+    concurrently -- the rows each band owns must equal the undivided domain's, bit for bit."""
+    from icar_b200.pipeline import HostPipeline
+    st = ideal.make_ideal_case(nx=64, nz=12, ny=70, perturb=True)
+    st["qv"] *= np.float32(3.0)
+    for k in ("precipitation", "snowfall"):
+        st[k] = np.zeros((st["ny"], st["nx"]), np.float64)
+    dt = float(st["dt"])
+    per_step = ("u", "v", "w", "pressure", "pii", "rho", "th", "qv", "qc", "qr", "qs", "precipitation", "snowfall")
+    out_keys = ("th", "qv", "qc", "qr", "qs", "precipitation", "snowfall")
+    # reference: one domain, in-place host arrays
+    ref_host = {k: np.ascontiguousarray(st[k].copy()) for k in per_step}
+    ref = make(gpu_lib, st)
+    hd = ref.host_domain(ref_host)
+    # pipeline: two sets of host arrays, swapped every step
+    a = {k: np.ascontiguousarray(st[k].copy()) for k in per_step}
+    b = {k: np.ascontiguousarray(st[k].copy()) for k in per_step}
+    pipe = HostPipeline(st, gpu_lib.Options(dx=st["dx"]), bands=bands, derive_diagnostics=derive)
+    for step in range(3):
+        if derive:
+            ref.upload_state({k: ref_host[k] for k in ("pressure", "th")})
+            ref.diagnostic_update()
+            ref_in = {k: v for k, v in ref_host.items() if k not in ("pii", "rho")}
+            ref.physics_step_host(dt, ref.host_domain(ref_in))
+        else:
+            ref.physics_step_host(dt, hd)
+        src, dst = (a, b) if step % 2 == 0 else (b, a)
+        pipe.step(dt, src, {k: dst[k] for k in out_keys})
+        for k in out_keys:
+            np.testing.assert_array_equal(dst[k], ref_host[k], err_msg=f"step {step} {k}")
+    with pytest.raises(ValueError):
+        pipe.step(dt, a, {k: a[k] for k in out_keys})
+    pipe.close()
