@@ -80,6 +80,9 @@ class HostPipeline:
         key = (tuple((k, v.ctypes.data) for k, v in host_in.items() if isinstance(v, np.ndarray)),
                tuple((k, v.ctypes.data) for k, v in host_out.items() if isinstance(v, np.ndarray)))
         if key not in self._views:
+            for k, v in host_out.items():               # checked once per pair of array sets, not per step
+                if isinstance(v, np.ndarray) and isinstance(host_in.get(k), np.ndarray) and np.may_share_memory(v, host_in[k]):
+                    raise ValueError(f"{k}: input and output arrays of a pipelined step must be different arrays")
             per_band = []
             for dom, (a, b, v0, v1) in zip(self.domains, self.bounds):
                 vin = {k: _rows(k, v, v0, v1) for k, v in host_in.items()
@@ -93,9 +96,6 @@ class HostPipeline:
     def step(self, dt, host_in, host_out):
         """One step: host_in (u, v, w, pressure, [pii, rho,] scalars, accumulators) -> host_out (scalars,
         accumulators).  The two must not share memory."""
-        for k, v in host_out.items():
-            if isinstance(v, np.ndarray) and k in host_in and np.shares_memory(v, host_in[k]):
-                raise ValueError(f"{k}: input and output arrays of a pipelined step must be different arrays")
         work = self._host_domains(host_in, host_out)
         futures = [self.pool.submit(dom.physics_step_host_io, dt, hin, hout, r0, r1, self.derive)
                    for dom, (hin, hout, r0, r1, _, _) in zip(self.domains, work)]
