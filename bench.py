@@ -240,6 +240,12 @@ def run_reference(args, rank, world):
     st = make_state(args)
     dt = float(st["dt"])
     O, step = oracle_stepper(args)
+    # all the host threads this process may use: torchrun exports OMP_NUM_THREADS=1 to its ranks, which would
+    # time the reference on one core
+    try:
+        O.set_threads(len(os.sched_getaffinity(0)))
+    except AttributeError:
+        O.set_threads(os.cpu_count() or 1)
     thr = O.max_threads()
 
     def scratch_for(b):
