@@ -150,7 +150,9 @@ SYMBOLS = (
     "icar_physics_step_host", "icar_step_host", "icar_physics_step_host_io", "icar_host_register", "icar_host_unregister",
     "icar_default_mp_options", "icar_thompson_init", "icar_thompson_table", "icar_mp_gt_driver",
     "icar_profile_enable", "icar_profile_read", "icar_diagnostic_update", "icar_compute_dt", "icar_enforce_limits",
-    "icar_upload_tendency", "icar_apply_forcing", "icar_balance_uvw")
+    "icar_upload_tendency", "icar_apply_forcing", "icar_balance_uvw",
+    "icar_add_buffer_topo", "icar_linear_winds_init", "icar_linear_winds_dims", "icar_linear_winds_terrain_frequency",
+    "icar_linear_perturbation", "icar_linear_perturb")
 
 
 def lib() -> C.CDLL:
@@ -303,6 +305,59 @@ class Domain:
     def balance_uvw(self):
         """balance_uvw (wind.f90:81-172): w from the horizontal divergence of the resident u, v."""
         self._check(lib().icar_balance_uvw(self._h))
+
+    # -- linear-theory winds (linear_winds.f90); 2-D arrays are (ny, nx) C-order = the Fortran (nx, ny) image
+    def linear_winds_init(self, global_terrain, buffer=50):
+        """setup_linwinds (linear_winds.f90:1180-1222): terrain_frequency on the device.  buffer: lt_parameters default 50."""
+        g = self.grid
+        t = _f32(global_terrain, (g.jde - g.jds + 1, g.ide - g.ids + 1), "global_terrain")
+        self._check(lib().icar_linear_winds_init(self._h, _ptr(t), t.shape[1], t.shape[0], int(buffer)))
+
+    def linear_winds_dims(self):
+        """(fft_nx, fft_ny, total buffer) of the buffered grid."""
+        a, b, c = C.c_int(), C.c_int(), C.c_int()
+        self._check(lib().icar_linear_winds_dims(self._h, C.byref(a), C.byref(b), C.byref(c)))
+        return a.value, b.value, c.value
+
+    def terrain_frequency(self):
+        """domain%terrain_frequency as a (fft_ny, fft_nx) complex128 array."""
+        fnx, fny, _ = self.linear_winds_dims()
+        out = np.empty((fny, fnx), np.complex128)
+        self._check(lib().icar_linear_winds_terrain_frequency(self._h, _ptr(out)))
+        return out
+
+    def linear_perturbation(self, U, V, Nsq, z_bottom, z_top, minimum_step=100.0):
+        """linear_perturbation (linear_winds.f90:239-344): scalars -> constz, (ny, nx) fields -> varyingz.
+        Returns lt_data%u_perturb, v_perturb as (fft_ny, fft_nx) complex128 arrays."""
+        fnx, fny, _ = self.linear_winds_dims()
+        u = np.empty((fny, fnx), np.complex128)
+        v = np.empty((fny, fnx), np.complex128)
+        if np.ndim(z_bottom) == 0:
+            rc = lib().icar_linear_perturbation(self._h, C.c_float(U), C.c_float(V), C.c_float(Nsq), C.c_float(z_bottom),
+                                                C.c_float(z_top), None, None, C.c_float(minimum_step), _ptr(u), _ptr(v))
+        else:
+            g = self.grid
+            shape = (g.jde - g.jds + 1, g.ide - g.ids + 1)
+            zb, zt = _f32(z_bottom, shape, "z_bottom"), _f32(z_top, shape, "z_top")
+            rc = lib().icar_linear_perturbation(self._h, C.c_float(U), C.c_float(V), C.c_float(Nsq), C.c_float(0), C.c_float(0),
+                                                _ptr(zb), _ptr(zt), C.c_float(minimum_step), _ptr(u), _ptr(v))
+        self._check(rc)
+        return u, v
+
+    def linear_perturb(self, U, V, Nsq, global_z_interface=None, global_dz_interface=None, layer_height=None,
+                       dz_levels=None, minimum_layer_size=100.0, linear_contribution=1.0, linear_update_fraction=0.2):
+        """linear_perturb (linear_winds.f90:1317-1366) evaluated directly for the background (U, V, Nsq): adds the
+        perturbation of every level to the resident u, v.  Defaults: options_obj.f90:1459-1479."""
+        g = self.grid
+        zi = dzi = lh = dz = None
+        if global_z_interface is not None:
+            shape = (g.jde - g.jds + 1, g.nz, g.ide - g.ids + 1)
+            zi, dzi = _f32(global_z_interface, shape, "global_z_interface"), _f32(global_dz_interface, shape, "global_dz_interface")
+        else:
+            lh, dz = _f32(layer_height, (g.nz,), "layer_height"), _f32(dz_levels, (g.nz,), "dz_levels")
+        self._check(lib().icar_linear_perturb(self._h, C.c_float(U), C.c_float(V), C.c_float(Nsq), _ptr(zi), _ptr(dzi),
+                                              _ptr(lh), _ptr(dz), C.c_float(minimum_layer_size),
+                                              C.c_float(linear_contribution), C.c_float(linear_update_fraction)))
 
     def enforce_limits(self):
         """domain%enforce_limits (domain_obj.f90:2228-2243)."""

@@ -22,6 +22,7 @@
 
 #include "common.cuh"
 #include "halo.cuh"
+#include "linear_winds.cuh"
 #include "mp_simple.cuh"
 #include "mp_thompson.cuh"
 #include "mpdata.cuh"
@@ -158,6 +159,7 @@ struct icar_ctx {
         bool unsupported = false;            // pointer state did not return after two steps: stay eager
     } sgraph;
     long long eager_steps = 0;               // completed icar_physics_step calls with dt > 1e-3 (lazy allocations done)
+    LinWinds* lw = nullptr;                  // module state of linear_theory_winds (icar_linear_winds_init)
 };
 
 namespace {
@@ -536,6 +538,7 @@ extern "C" int icar_destroy(icar_ctx* ctx) {
         for (int n = 0; n < ICAR_MAX_SCALARS; ++n) { if (ctx->fq2[n]) cudaFree(ctx->fq2[n]); if (ctx->fout[n]) cudaFree(ctx->fout[n]); }
     }
     for (void* p : ctx->scratch) if (p) cudaFree(p);
+    lw_destroy(ctx->lw);
     for (auto& r : ctx->prof_pending) { if (r.kid >= 0) cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
     for (cudaEvent_t e : ctx->prof_pool) cudaEventDestroy(e);
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
@@ -1700,5 +1703,104 @@ extern "C" int icar_balance_uvw(icar_ctx* ctx) {
                                         (const float*)ctx->vars[ICAR_VAR_ADVECTION_DZ], ctx->opt.dx, ctx->stream);
     CU(cudaGetLastError());
     ctx->uploaded[ICAR_VAR_W] = true;
+    return ICAR_OK;
+}
+
+// ------------------------------------------------------------------ linear-theory winds ("next" rank 3)
+
+extern "C" void icar_add_buffer_topo(const float* terrain, int nx, int ny, int smooth_window, int buffer, double* out) {
+    if (terrain && out && nx > 0 && ny > 0 && buffer >= 0) lw_add_buffer_topo(terrain, nx, ny, smooth_window, buffer, out);
+}
+
+extern "C" int icar_linear_winds_init(icar_ctx* ctx, const float* global_terrain, int nx_global, int ny_global,
+                                      int buffer) {
+    if (!ctx) return ICAR_ERR_INVALID;
+    CU(cudaSetDevice(ctx->device));
+    const icar_grid& gr = ctx->grid;
+    if (nx_global != gr.ide - gr.ids + 1 || ny_global != gr.jde - gr.jds + 1)
+        return fail(ctx, ICAR_ERR_INVALID, "icar_linear_winds_init: global_terrain must cover ids:ide x jds:jde");
+    lw_destroy(ctx->lw);
+    ctx->lw = nullptr;
+    std::string err;
+    const int rc = lw_create(&ctx->lw, global_terrain, nx_global, ny_global, buffer, ctx->opt.dx, ctx->stream, &err);
+    if (rc) return fail(ctx, rc == 1 ? ICAR_ERR_INVALID : ICAR_ERR_CUDA, "icar_linear_winds_init: " + err);
+    ctx->launches += 1;
+    return ICAR_OK;
+}
+
+extern "C" int icar_linear_winds_dims(icar_ctx* ctx, int* fft_nx, int* fft_ny, int* buffer) {
+    if (!ctx || !ctx->lw) return fail(ctx, ICAR_ERR_INVALID, "icar_linear_winds_dims: call icar_linear_winds_init first");
+    lw_dims(ctx->lw, fft_nx, fft_ny, buffer);
+    return ICAR_OK;
+}
+
+extern "C" int icar_linear_winds_terrain_frequency(icar_ctx* ctx, double* host) {
+    if (!ctx || !ctx->lw || !host)
+        return fail(ctx, ICAR_ERR_INVALID, "icar_linear_winds_terrain_frequency: call icar_linear_winds_init first");
+    CU(cudaSetDevice(ctx->device));
+    std::string err;
+    if (lw_terrain_frequency(ctx->lw, host, &err)) return fail(ctx, ICAR_ERR_CUDA, err);
+    return ICAR_OK;
+}
+
+extern "C" int icar_linear_perturbation(icar_ctx* ctx, float U, float V, float Nsq, float z_bottom, float z_top,
+                                        const float* z_bottom_2d, const float* z_top_2d, float minimum_step,
+                                        double* u_perturb, double* v_perturb) {
+    if (!ctx || !ctx->lw) return fail(ctx, ICAR_ERR_INVALID, "icar_linear_perturbation: call icar_linear_winds_init first");
+    if ((z_bottom_2d == nullptr) != (z_top_2d == nullptr))
+        return fail(ctx, ICAR_ERR_INVALID, "icar_linear_perturbation: z_bottom_2d and z_top_2d go together");
+    CU(cudaSetDevice(ctx->device));
+    std::string err;
+    const int rc = z_bottom_2d ? lw_perturbation_varyingz(ctx->lw, U, V, Nsq, z_bottom_2d, z_top_2d, minimum_step,
+                                                          &ctx->launches, &err)
+                               : lw_perturbation_constz(ctx->lw, U, V, Nsq, z_bottom, z_top, minimum_step,
+                                                        &ctx->launches, &err);
+    if (rc) return fail(ctx, rc == 1 ? ICAR_ERR_INVALID : rc == 3 ? ICAR_ERR_PHYSICS : ICAR_ERR_CUDA, "icar_linear_perturbation: " + err);
+    if (u_perturb || v_perturb)
+        if (lw_download_perturbation(ctx->lw, u_perturb, v_perturb, &err)) return fail(ctx, ICAR_ERR_CUDA, err);
+    return ICAR_OK;
+}
+
+extern "C" int icar_linear_perturb(icar_ctx* ctx, float U, float V, float Nsq, const float* global_z_interface,
+                                   const float* global_dz_interface, const float* layer_height, const float* dz_levels,
+                                   float minimum_layer_size, float linear_contribution, float linear_update_fraction) {
+    if (!ctx || !ctx->lw) return fail(ctx, ICAR_ERR_INVALID, "icar_linear_perturb: call icar_linear_winds_init first");
+    const bool varying = global_z_interface != nullptr;
+    if (varying ? !global_dz_interface : !(layer_height && dz_levels))
+        return fail(ctx, ICAR_ERR_INVALID, "icar_linear_perturb: give global_z_interface + global_dz_interface "
+                                           "(space_varying_dz) or layer_height + dz_levels");
+    CU(cudaSetDevice(ctx->device));
+    int rc = need_uploaded(ctx, {ICAR_VAR_U, ICAR_VAR_V}, "icar_linear_perturb");
+    if (rc) return rc;
+    { int jr = join_aux(ctx); if (jr) return jr; }
+    const icar_grid& gr = ctx->grid;
+    const Geom& g = ctx->g;
+    int gnx = 0, gny = 0;
+    const float* terrain = lw_terrain(ctx->lw, &gnx, &gny);
+    std::vector<float> zb, zt;
+    if (varying) { zb.resize((size_t)gnx * gny); zt.resize((size_t)gnx * gny); }
+    std::string err;
+    for (int k = 0; k < g.nz; ++k) {
+        if (varying) {
+            // z_interface(:, z, :) - terrain and ... + dz_interface(:, z, :)   (linear_winds.f90:723-726)
+            for (int j = 0; j < gny; ++j)
+                for (int i = 0; i < gnx; ++i) {
+                    const size_t c3 = (size_t)i + (size_t)gnx * ((size_t)k + (size_t)g.nz * (size_t)j);
+                    const float b = global_z_interface[c3] - terrain[(size_t)j * gnx + i];
+                    zb[(size_t)j * gnx + i] = b;
+                    zt[(size_t)j * gnx + i] = b + global_dz_interface[c3];
+                }
+            rc = lw_perturbation_varyingz(ctx->lw, U, V, Nsq, zb.data(), zt.data(), minimum_layer_size, &ctx->launches, &err);
+        } else {
+            const float half = dz_levels[k] / 2.0f;                  // :730-732
+            rc = lw_perturbation_constz(ctx->lw, U, V, Nsq, layer_height[k] - half, layer_height[k] + half,
+                                        minimum_layer_size, &ctx->launches, &err);
+        }
+        if (!rc)
+            rc = lw_apply_level(ctx->lw, g, gr.ims - gr.ids, gr.jms - gr.jds, k, (float*)ctx->vars[ICAR_VAR_U],
+                                (float*)ctx->vars[ICAR_VAR_V], linear_contribution, linear_update_fraction,
+                                &ctx->launches, &err);
+        if (rc) return fail(ctx, rc == 1 ? ICAR_ERR_INVALID : rc == 3 ? ICAR_ERR_PHYSICS : ICAR_ERR_CUDA, "icar_linear_perturb: " + err);
+    }
     return ICAR_OK;
 }

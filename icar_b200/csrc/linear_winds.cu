@@ -1,0 +1,479 @@
+// Linear-theory wind perturbation (Barstad & Gronas 2006) for sm_100a.
+//
+// Reference routines restated here (src/physics/linear_winds.f90 unless noted):
+//   :351-418    add_buffer_topo                    host, once at set-up
+//   :426-472    initialize_linear_theory_data      wavenumber grids k, l (REAL, -pi/dx .. +pi/dx inclusive)
+//   :1180-1222  setup_linwinds                     buffered terrain -> FFT / N -> fftshift = terrain_frequency
+//   :181-237    linear_perturbation_at_height      lw_math.cuh, one thread per wavenumber
+//   :239-277    linear_perturbation_constz
+//   :280-344    linear_perturbation_varyingz
+//   :756-762    the stagger of the LUT entries;  :1094-1111  the update of u, v in spatial_winds
+//   src/utilities/fftshift.f90:87-109, 217-239     the shifts (through a single-precision temporary)
+//
+// What is different from the reference, by design: there is no look-up table.  The reference tabulates the
+// perturbation for 10 speeds x 36 directions x 10 stabilities and interpolates (3600 x nx x nz x ny x 2 REALs,
+// 7 TB at 2048 x 2048 x 60); here the perturbation is evaluated for the background state it is needed for.
+// The 2-D transforms are cuFFT's (the reference calls FFTW for them), bound with dlopen like NCCL; the
+// wavenumber-space arithmetic, both shifts, the sub-layer mean, the layer-fraction weighting, the stagger and
+// the wind update are kernels of this file.  ifftshift is folded into the spectrum kernel (it writes uhat and
+// vhat at their FFT-order positions), and for a layer with constant bounds the mean over its sub-layer heights
+// is taken BEFORE the inverse transform, so such a layer costs two FFTs instead of two per sub-layer.
+#include "linear_winds.cuh"
+
+#include <cufft.h>
+#include <dlfcn.h>
+
+#include <algorithm>
+#include <cmath>
+#include <vector>
+
+#include "lw_math.cuh"
+
+namespace icar {
+
+namespace {
+
+struct Cufft {
+    void* h = nullptr;
+    cufftResult (*Plan2d)(cufftHandle*, int, int, cufftType) = nullptr;
+    cufftResult (*ExecZ2Z)(cufftHandle, cufftDoubleComplex*, cufftDoubleComplex*, int) = nullptr;
+    cufftResult (*SetStream)(cufftHandle, cudaStream_t) = nullptr;
+    cufftResult (*Destroy)(cufftHandle) = nullptr;
+    bool load(std::string* err) {
+        if (h) return true;
+        for (const char* n : {"libcufft.so.11", "libcufft.so.12", "libcufft.so"}) {
+            h = dlopen(n, RTLD_NOW | RTLD_LOCAL);
+            if (h) break;
+        }
+        if (!h) { *err = std::string("cannot dlopen libcufft: ") + dlerror(); return false; }
+#define BIND(field, sym)                                                 \
+    *(void**)(&field) = dlsym(h, sym);                                   \
+    if (!field) { *err = std::string("libcufft lacks ") + sym; h = nullptr; return false; }
+        BIND(Plan2d, "cufftPlan2d")
+        BIND(ExecZ2Z, "cufftExecZ2Z")
+        BIND(SetStream, "cufftSetStream")
+        BIND(Destroy, "cufftDestroy")
+#undef BIND
+        return true;
+    }
+};
+Cufft g_cufft;
+
+using lw::cplx;
+
+constexpr int kThreads = 128;
+inline dim3 grid2d(int nx, int ny) { return dim3((nx + kThreads - 1) / kThreads, ny); }
+
+// terrain_frequency = fftshift(FFT(terrain) / (nx ny))     (:1217-1222)
+__global__ void __launch_bounds__(kThreads)
+k_lw_shift_norm(const double2* __restrict__ in, double2* __restrict__ out, int fnx, int fny, double cells) {
+    const int i = blockIdx.x * kThreads + threadIdx.x, j = blockIdx.y;
+    if (i >= fnx) return;
+    const double2 a = in[(size_t)j * fnx + i];
+    const cplx v = lw::through_single({a.x / cells, a.y / cells});
+    out[(size_t)lw::shifted(j, fny) * fnx + lw::shifted(i, fnx)] = make_double2(v.x, v.y);
+}
+
+// uhat, vhat at their FFT-order positions (ifftshift folded in), summed over `nsteps` heights that start at z0
+// and advance by `step` in REAL arithmetic exactly as linear_perturbation_constz's loop does (:262-268)
+__global__ void __launch_bounds__(kThreads)
+k_lw_spectrum(const double2* __restrict__ tf, const float* __restrict__ kx, const float* __restrict__ ly, int fnx,
+              int fny, float U, float V, float Nsq, float z0, float step, int nsteps, double2* __restrict__ uhat,
+              double2* __restrict__ vhat) {
+    const int i = blockIdx.x * kThreads + threadIdx.x, j = blockIdx.y;
+    if (i >= fnx) return;
+    const int si = lw::shifted(i, fnx), sj = lw::shifted(j, fny);      // ifftshift reads its (i, j) from (ii, jj)
+    const double2 t = tf[(size_t)sj * fnx + si];
+    const lw::Mode q = lw::make_mode(U, V, Nsq, kx[si], ly[sj], {t.x, t.y});
+    cplx us = {0.0, 0.0}, vs = {0.0, 0.0};
+    float z = z0;
+    for (int s = 0; s < nsteps; ++s) {
+        cplx uh, vh;
+        lw::hats_at(q, z, &uh, &vh);
+        us.x += uh.x; us.y += uh.y;
+        vs.x += vh.x; vs.y += vh.y;
+        z = z + step;
+    }
+    uhat[(size_t)j * fnx + i] = make_double2(us.x, us.y);
+    vhat[(size_t)j * fnx + i] = make_double2(vs.x, vs.y);
+}
+
+// u_perturb = u_accumulator / n_steps   (:271-272)
+__global__ void __launch_bounds__(kThreads)
+k_lw_divide(double2* __restrict__ u, double2* __restrict__ v, size_t n, double by) {
+    const size_t c = (size_t)blockIdx.x * kThreads + threadIdx.x;
+    if (c >= n) return;
+    u[c] = make_double2(u[c].x / by, u[c].y / by);
+    v[c] = make_double2(v[c].x / by, v[c].y / by);
+}
+
+// internal_z_top / internal_z_bottom (:305-309): the domain's layer bounds placed at (buffer : buffer + n - 1)
+// of the FFT grid -- as written, one cell west / south of where the terrain sits -- inside their extreme values
+__global__ void __launch_bounds__(kThreads)
+k_lw_layer_bounds(const float* __restrict__ zb, const float* __restrict__ zt, int nx, int ny, int buffer, float zb_min,
+                  float zt_max, float* __restrict__ ibot, float* __restrict__ itop, int fnx, int fny) {
+    const int i = blockIdx.x * kThreads + threadIdx.x, j = blockIdx.y;
+    if (i >= fnx) return;
+    const int di = i - (buffer - 1), dj = j - (buffer - 1);
+    const bool inside = di >= 0 && di < nx && dj >= 0 && dj < ny;
+    ibot[(size_t)j * fnx + i] = inside ? zb[(size_t)dj * nx + di] : zb_min;
+    itop[(size_t)j * fnx + i] = inside ? zt[(size_t)dj * nx + di] : zt_max;
+}
+
+// one sampled height of linear_perturbation_varyingz (:326-333)
+__global__ void __launch_bounds__(kThreads)
+k_lw_accumulate(const double2* __restrict__ up, const double2* __restrict__ vp, const float* __restrict__ ibot,
+                const float* __restrict__ itop, float current_z, float step_size, double2* __restrict__ ua,
+                double2* __restrict__ va, float* __restrict__ count, size_t n) {
+    const size_t c = (size_t)blockIdx.x * kThreads + threadIdx.x;
+    if (c >= n) return;
+    const float f = lw::layer_fraction(current_z, ibot[c], itop[c], step_size);
+    const double fd = (double)f;
+    count[c] = count[c] + f;
+    ua[c] = make_double2(ua[c].x + up[c].x * fd, ua[c].y + up[c].y * fd);
+    va[c] = make_double2(va[c].x + vp[c].x * fd, va[c].y + vp[c].y * fd);
+}
+
+// u_perturb = u_accumulator / layer_count   (:338-339)
+__global__ void __launch_bounds__(kThreads)
+k_lw_divide_by_count(const double2* __restrict__ ua, const double2* __restrict__ va, const float* __restrict__ count,
+                     double2* __restrict__ up, double2* __restrict__ vp, size_t n) {
+    const size_t c = (size_t)blockIdx.x * kThreads + threadIdx.x;
+    if (c >= n) return;
+    const double d = (double)count[c];
+    up[c] = make_double2(ua[c].x / d, ua[c].y / d);
+    vp[c] = make_double2(va[c].x / d, va[c].y / d);
+}
+
+// level k of u (nx + 1 faces per row): stagger (:756-758) and update (:1094-1098)
+__global__ void __launch_bounds__(kThreads)
+k_lw_apply_u(const double2* __restrict__ up, int fnx, int buffer, Geom g, int i0, int j0, int k,
+             float* __restrict__ u3d, float* __restrict__ upert, float contribution, float fraction) {
+    const int i = blockIdx.x * kThreads + threadIdx.x, j = blockIdx.y;
+    if (i > g.nx) return;
+    const size_t row = (size_t)(buffer + j0 + j) * fnx;
+    const int col = buffer + i0 + i;
+    const float fresh = (float)(up[row + col - 1].x + up[row + col].x) / 2.0f;
+    const size_t c = g.atu(i, k, j);
+    const float keep = upert[c] * (1.0f - fraction);
+    const float p = keep + fraction * fresh;
+    upert[c] = p;
+    u3d[c] = u3d[c] + p * contribution;
+}
+
+// level k of v (ny + 1 rows): stagger (:760-762) and update (:1107-1111)
+__global__ void __launch_bounds__(kThreads)
+k_lw_apply_v(const double2* __restrict__ vp, int fnx, int buffer, Geom g, int i0, int j0, int k,
+             float* __restrict__ v3d, float* __restrict__ vpert, float contribution, float fraction) {
+    const int i = blockIdx.x * kThreads + threadIdx.x, j = blockIdx.y;
+    if (i >= g.nx) return;
+    const int col = buffer + i0 + i;
+    const size_t row = (size_t)(buffer + j0 + j) * fnx;
+    const float fresh = (float)(vp[row - fnx + col].x + vp[row + col].x) / 2.0f;
+    const size_t c = g.at(i, k, j);
+    const float keep = vpert[c] * (1.0f - fraction);
+    const float p = keep + fraction * fresh;
+    vpert[c] = p;
+    v3d[c] = v3d[c] + p * contribution;
+}
+
+}  // namespace
+
+struct LinWinds {
+    int nx = 0, ny = 0;            // the un-buffered domain (global_terrain)
+    int fnx = 0, fny = 0;          // the FFT grid
+    int buffer = 0;                // original buffer + 2
+    cudaStream_t st = nullptr;
+    cufftHandle plan = 0;
+    bool have_plan = false;
+    double2 *tf = nullptr, *uhat = nullptr, *vhat = nullptr, *up = nullptr, *vp = nullptr, *ua = nullptr, *va = nullptr;
+    float *kx = nullptr, *ly = nullptr, *ibot = nullptr, *itop = nullptr, *count = nullptr, *zb = nullptr, *zt = nullptr;
+    float *upert = nullptr, *vpert = nullptr;      // hi_u_perturbation / hi_v_perturbation of the tile (:1262-1268)
+    size_t upert_elems = 0, vpert_elems = 0;
+    bool have_perturbation = false;
+    std::vector<float> terrain;    // domain%global_terrain, kept for the layer bounds of linear_perturb
+};
+
+#define LWCU(call)                                                               \
+    do {                                                                         \
+        cudaError_t e__ = (call);                                                \
+        if (e__ != cudaSuccess) {                                                \
+            *err = std::string(#call) + ": " + cudaGetErrorString(e__);          \
+            return 2;                                                            \
+        }                                                                        \
+    } while (0)
+#define LWFFT(call)                                                              \
+    do {                                                                         \
+        cufftResult r__ = (call);                                                \
+        if (r__ != CUFFT_SUCCESS) {                                              \
+            *err = std::string(#call) + ": cufft status " + std::to_string((int)r__); \
+            return 2;                                                            \
+        }                                                                        \
+    } while (0)
+
+void lw_add_buffer_topo(const float* terrain, int nx0, int ny0, int smooth_window, int buffer, double* out) {
+    const int nx = nx0 + 2 * buffer, ny = ny0 + 2 * buffer;
+    auto re = [&](int i, int j) -> double& { return out[2 * ((size_t)j * nx + i)]; };        // 0-based (i, j)
+    auto im = [&](int i, int j) -> double& { return out[2 * ((size_t)j * nx + i) + 1]; };
+    auto T = [&](int i, int j) { return terrain[(size_t)j * nx0 + i]; };
+    float lowest = terrain[0];
+    for (size_t c = 0; c < (size_t)nx0 * ny0; ++c) lowest = std::min(lowest, terrain[c]);
+    for (int j = 0; j < ny; ++j)
+        for (int i = 0; i < nx; ++i) { re(i, j) = (double)lowest; im(i, j) = 0.0; }
+    for (int j = 0; j < ny0; ++j)
+        for (int i = 0; i < nx0; ++i) re(buffer + i, buffer + j) = (double)T(i, j);
+    // west / east rims: the first and last terrain columns blended into each other (:365-370, REAL expressions)
+    for (int s = 1; s <= buffer; ++s) {
+        const float weight = (float)s / ((float)buffer * 2.0f);
+        const int pos = buffer - s;
+        for (int j = 0; j < ny0; ++j) {
+            const float first = T(0, j), last = T(nx0 - 1, j);
+            re(pos, buffer + j) = (double)(first * (1.0f - weight) + last * weight);
+            re(nx - pos - 1, buffer + j) = (double)(first * weight + last * (1.0f - weight));
+        }
+    }
+    // south / north rims from the rows just inside them (:371-376): complex double times REAL
+    for (int s = 1; s <= buffer; ++s) {
+        const float weight = (float)s / ((float)buffer * 2.0f);
+        const double w = (double)weight, omw = (double)(1.0f - weight);
+        const int pos = buffer - s;
+        for (int i = 0; i < nx; ++i) {
+            const double lo_r = re(i, buffer), hi_r = re(i, ny - buffer - 1);
+            const double lo_i = im(i, buffer), hi_i = im(i, ny - buffer - 1);
+            re(i, pos) = lo_r * omw + hi_r * w;
+            im(i, pos) = lo_i * omw + hi_i * w;
+            re(i, ny - pos - 1) = lo_r * w + hi_r * omw;
+            im(i, ny - pos - 1) = lo_i * w + hi_i * omw;
+        }
+    }
+    if (smooth_window <= 0) return;
+    // box means over a window that grows away from the terrain, in place and in this order (:380-414)
+    auto box_mean = [&](int xs, int xe, int ys, int ye, int ti, int tj) {     // 1-based inclusive bounds and target
+        double sr = 0.0, si = 0.0;
+        for (int j = ys; j <= ye; ++j)                                         // Fortran sum(): column-major order
+            for (int i = xs; i <= xe; ++i) { sr += re(i - 1, j - 1); si += im(i - 1, j - 1); }
+        const double cells = (double)((xe - xs + 1) * (ye - ys + 1));
+        re(ti - 1, tj - 1) = sr / cells;
+        im(ti - 1, tj - 1) = si / cells;
+    };
+    for (int j = 1; j <= buffer; ++j) {
+        const int window = std::min(j, smooth_window);
+        for (int i = 1; i <= nx; ++i) {
+            const int xs = std::max(1, i - window), xe = std::min(nx, i + window);
+            int ys = std::max(1, buffer - j + 1 - window), ye = std::min(ny, buffer - j + 1 + window);
+            box_mean(xs, xe, ys, ye, i, buffer - j + 1);
+            ys = std::max(1, ny - (buffer - j) - window);
+            ye = std::min(ny, ny - (buffer - j) + window);
+            box_mean(xs, xe, ys, ye, i, ny - (buffer - j));
+        }
+        for (int i = 1; i <= ny; ++i) {
+            int xs = std::max(1, buffer - j + 1 - window), xe = std::min(nx, buffer - j + 1 + window);
+            const int ys = std::max(1, i - window), ye = std::min(ny, i + window);
+            box_mean(xs, xe, ys, ye, buffer - j + 1, i);
+            xs = std::max(1, nx - (buffer - j) - window);
+            xe = std::min(nx, nx - (buffer - j) + window);
+            box_mean(xs, xe, ys, ye, nx - (buffer - j), i);
+        }
+    }
+}
+
+void lw_destroy(LinWinds* lw) {
+    if (!lw) return;
+    if (lw->have_plan && g_cufft.Destroy) g_cufft.Destroy(lw->plan);
+    void* bufs[] = {lw->tf, lw->uhat, lw->vhat, lw->up, lw->vp, lw->ua, lw->va, lw->kx, lw->ly, lw->ibot, lw->itop,
+                    lw->count, lw->zb, lw->zt, lw->upert, lw->vpert};
+    for (void* p : bufs) if (p) cudaFree(p);
+    delete lw;
+}
+
+const float* lw_terrain(const LinWinds* lw, int* nx, int* ny) {
+    if (nx) *nx = lw->nx;
+    if (ny) *ny = lw->ny;
+    return lw->terrain.data();
+}
+
+void lw_dims(const LinWinds* lw, int* fnx, int* fny, int* buffer) {
+    if (fnx) *fnx = lw->fnx;
+    if (fny) *fny = lw->fny;
+    if (buffer) *buffer = lw->buffer;
+}
+
+int lw_create(LinWinds** out, const float* terrain, int nx, int ny, int buffer, float dx, cudaStream_t st,
+              std::string* err) {
+    *out = nullptr;
+    if (!terrain || nx < 2 || ny < 2 || buffer < 1 || !(dx > 0.f)) {
+        *err = "linear winds: need a terrain of at least 2 x 2 cells, buffer >= 1 (lt_parameters) and dx > 0";
+        return 1;
+    }
+    if (!g_cufft.load(err)) return 2;
+    // two buffering passes (:1199-1207)
+    const int n1x = nx + 2 * buffer, n1y = ny + 2 * buffer;
+    std::vector<double> first((size_t)2 * n1x * n1y);
+    lw_add_buffer_topo(terrain, nx, ny, 5, buffer, first.data());
+    std::vector<float> first_real((size_t)n1x * n1y);
+    for (size_t c = 0; c < first_real.size(); ++c) first_real[c] = (float)first[2 * c];      // real(real(...))
+    const int fnx = n1x + 4, fny = n1y + 4;
+    std::vector<double> second((size_t)2 * fnx * fny);
+    lw_add_buffer_topo(first_real.data(), n1x, n1y, 0, 2, second.data());
+
+    LinWinds* lw = new LinWinds;
+    lw->terrain.assign(terrain, terrain + (size_t)nx * ny);
+    lw->nx = nx; lw->ny = ny; lw->fnx = fnx; lw->fny = fny; lw->buffer = buffer + 2; lw->st = st;
+    auto bail = [&](int rc) { lw_destroy(lw); return rc; };
+    const size_t n = (size_t)fnx * fny;
+    for (double2** p : {&lw->tf, &lw->uhat, &lw->vhat, &lw->up, &lw->vp})
+        if (cudaMalloc((void**)p, n * sizeof(double2)) != cudaSuccess) { *err = "linear winds: cudaMalloc failed"; return bail(2); }
+    if (cudaMalloc((void**)&lw->kx, fnx * sizeof(float)) != cudaSuccess ||
+        cudaMalloc((void**)&lw->ly, fny * sizeof(float)) != cudaSuccess) { *err = "linear winds: cudaMalloc failed"; return bail(2); }
+    // k, l (:447-463): REAL arithmetic, (i-1) * gain - offset
+    const float pi = 3.1415927f;
+    const float offset = pi / dx;
+    std::vector<float> kx(fnx), ly(fny);
+    float gain = 2.0f * offset / (float)(fnx - 1);
+    for (int i = 0; i < fnx; ++i) { const float t = (float)i * gain; kx[i] = t - offset; }
+    gain = 2.0f * offset / (float)(fny - 1);
+    for (int j = 0; j < fny; ++j) { const float t = (float)j * gain; ly[j] = t - offset; }
+    cudaError_t e = cudaMemcpyAsync(lw->kx, kx.data(), fnx * sizeof(float), cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(lw->ly, ly.data(), fny * sizeof(float), cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(lw->uhat, second.data(), n * sizeof(double2), cudaMemcpyHostToDevice, st);
+    if (e != cudaSuccess) { *err = std::string("linear winds: upload: ") + cudaGetErrorString(e); return bail(2); }
+    // Fortran (fnx, fny) with the first index fastest = a C array [fny][fnx]
+    if (g_cufft.Plan2d(&lw->plan, fny, fnx, CUFFT_Z2Z) != CUFFT_SUCCESS) { *err = "linear winds: cufftPlan2d failed"; return bail(2); }
+    lw->have_plan = true;
+    if (g_cufft.SetStream(lw->plan, st) != CUFFT_SUCCESS) { *err = "linear winds: cufftSetStream failed"; return bail(2); }
+    if (g_cufft.ExecZ2Z(lw->plan, lw->uhat, lw->up, CUFFT_FORWARD) != CUFFT_SUCCESS) { *err = "linear winds: forward FFT failed"; return bail(2); }
+    k_lw_shift_norm<<<grid2d(fnx, fny), kThreads, 0, st>>>(lw->up, lw->tf, fnx, fny, (double)(fnx * fny));
+    e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);       // `second`, kx, ly go out of scope
+    if (e != cudaSuccess) { *err = std::string("linear winds: set-up: ") + cudaGetErrorString(e); return bail(2); }
+    *out = lw;
+    return 0;
+}
+
+int lw_terrain_frequency(LinWinds* lw, double* host, std::string* err) {
+    LWCU(cudaMemcpyAsync(host, lw->tf, (size_t)lw->fnx * lw->fny * sizeof(double2), cudaMemcpyDeviceToHost, lw->st));
+    LWCU(cudaStreamSynchronize(lw->st));
+    return 0;
+}
+
+int lw_download_perturbation(LinWinds* lw, double* u, double* v, std::string* err) {
+    if (!lw->have_perturbation) { *err = "linear winds: no perturbation has been computed yet"; return 1; }
+    const size_t bytes = (size_t)lw->fnx * lw->fny * sizeof(double2);
+    if (u) LWCU(cudaMemcpyAsync(u, lw->up, bytes, cudaMemcpyDeviceToHost, lw->st));
+    if (v) LWCU(cudaMemcpyAsync(v, lw->vp, bytes, cudaMemcpyDeviceToHost, lw->st));
+    LWCU(cudaStreamSynchronize(lw->st));
+    return 0;
+}
+
+static int zero_perturbation(LinWinds* lw, std::string* err) {          // U = V = 0  (:196-200)
+    const size_t bytes = (size_t)lw->fnx * lw->fny * sizeof(double2);
+    LWCU(cudaMemsetAsync(lw->up, 0, bytes, lw->st));
+    LWCU(cudaMemsetAsync(lw->vp, 0, bytes, lw->st));
+    lw->have_perturbation = true;
+    return 0;
+}
+
+int lw_perturbation_constz(LinWinds* lw, float U, float V, float Nsq, float z_bottom, float z_top,
+                           float minimum_step, long long* launches, std::string* err) {
+    if (U == 0.f && V == 0.f) return zero_perturbation(lw, err);
+    if (!(minimum_step > 0.f)) { *err = "linear winds: minimum_layer_size must be positive"; return 1; }
+    const int n_steps = std::max(1, (int)std::ceil((z_top - z_bottom) / minimum_step));       // :257
+    const float step_size = (z_top - z_bottom) / (float)n_steps;                              // :258
+    const float half = step_size / 2.0f;
+    const float z0 = z_bottom + half;                                                         // :263
+    const size_t n = (size_t)lw->fnx * lw->fny;
+    k_lw_spectrum<<<grid2d(lw->fnx, lw->fny), kThreads, 0, lw->st>>>(lw->tf, lw->kx, lw->ly, lw->fnx, lw->fny, U, V,
+                                                                     Nsq, z0, step_size, n_steps, lw->uhat, lw->vhat);
+    LWCU(cudaGetLastError());
+    LWFFT(g_cufft.ExecZ2Z(lw->plan, lw->uhat, lw->up, CUFFT_INVERSE));     // FFTW_BACKWARD: unnormalised, like cuFFT
+    LWFFT(g_cufft.ExecZ2Z(lw->plan, lw->vhat, lw->vp, CUFFT_INVERSE));
+    int mine = 1;
+    if (n_steps > 1) {
+        k_lw_divide<<<(unsigned)((n + kThreads - 1) / kThreads), kThreads, 0, lw->st>>>(lw->up, lw->vp, n, (double)n_steps);
+        LWCU(cudaGetLastError());
+        ++mine;
+    }
+    if (launches) *launches += mine;
+    lw->have_perturbation = true;
+    return 0;
+}
+
+int lw_perturbation_varyingz(LinWinds* lw, float U, float V, float Nsq, const float* z_bottom, const float* z_top,
+                             float minimum_step, long long* launches, std::string* err) {
+    if (U == 0.f && V == 0.f) return zero_perturbation(lw, err);
+    if (!z_bottom || !z_top) { *err = "linear winds: z_bottom / z_top missing"; return 1; }
+    const size_t cells = (size_t)lw->nx * lw->ny, n = (size_t)lw->fnx * lw->fny;
+    float start_z = z_bottom[0], end_z = z_top[0], thinnest = z_top[0] - z_bottom[0];
+    for (size_t c = 0; c < cells; ++c) {
+        start_z = std::min(start_z, z_bottom[c]);                      // :301
+        end_z = std::max(end_z, z_top[c]);                             // :302
+        thinnest = std::min(thinnest, z_top[c] - z_bottom[c]);
+    }
+    const float step_size = std::min(minimum_step, thinnest);          // :315
+    if (!(step_size > 0.f)) { *err = "linear winds: a layer of zero or negative thickness"; return 3; }
+    if (!lw->ua) {
+        for (double2** p : {&lw->ua, &lw->va}) LWCU(cudaMalloc((void**)p, n * sizeof(double2)));
+        for (float** p : {&lw->ibot, &lw->itop, &lw->count}) LWCU(cudaMalloc((void**)p, n * sizeof(float)));
+        for (float** p : {&lw->zb, &lw->zt}) LWCU(cudaMalloc((void**)p, cells * sizeof(float)));
+    }
+    LWCU(cudaMemcpyAsync(lw->zb, z_bottom, cells * sizeof(float), cudaMemcpyHostToDevice, lw->st));
+    LWCU(cudaMemcpyAsync(lw->zt, z_top, cells * sizeof(float), cudaMemcpyHostToDevice, lw->st));
+    LWCU(cudaMemsetAsync(lw->ua, 0, n * sizeof(double2), lw->st));
+    LWCU(cudaMemsetAsync(lw->va, 0, n * sizeof(double2), lw->st));
+    LWCU(cudaMemsetAsync(lw->count, 0, n * sizeof(float), lw->st));
+    k_lw_layer_bounds<<<grid2d(lw->fnx, lw->fny), kThreads, 0, lw->st>>>(lw->zb, lw->zt, lw->nx, lw->ny, lw->buffer, start_z,
+                                                                         end_z, lw->ibot, lw->itop, lw->fnx, lw->fny);
+    LWCU(cudaGetLastError());
+    int mine = 1;
+    const unsigned blocks = (unsigned)((n + kThreads - 1) / kThreads);
+    const float half = step_size / 2.0f;
+    float current_z = start_z + half;                                  // :320
+    while (current_z < end_z) {                                        // :325
+        k_lw_spectrum<<<grid2d(lw->fnx, lw->fny), kThreads, 0, lw->st>>>(lw->tf, lw->kx, lw->ly, lw->fnx, lw->fny, U, V,
+                                                                         Nsq, current_z, 0.f, 1, lw->uhat, lw->vhat);
+        LWFFT(g_cufft.ExecZ2Z(lw->plan, lw->uhat, lw->up, CUFFT_INVERSE));
+        LWFFT(g_cufft.ExecZ2Z(lw->plan, lw->vhat, lw->vp, CUFFT_INVERSE));
+        k_lw_accumulate<<<blocks, kThreads, 0, lw->st>>>(lw->up, lw->vp, lw->ibot, lw->itop, current_z, step_size,
+                                                         lw->ua, lw->va, lw->count, n);
+        LWCU(cudaGetLastError());
+        mine += 2;
+        current_z = current_z + step_size;                             // :335
+    }
+    k_lw_divide_by_count<<<blocks, kThreads, 0, lw->st>>>(lw->ua, lw->va, lw->count, lw->up, lw->vp, n);
+    LWCU(cudaGetLastError());
+    // z_bottom / z_top are the caller's: the uploads must have left them before we return
+    LWCU(cudaStreamSynchronize(lw->st));
+    if (launches) *launches += mine + 1;
+    lw->have_perturbation = true;
+    return 0;
+}
+
+int lw_apply_level(LinWinds* lw, const Geom& g, int i0, int j0, int k, float* u3d, float* v3d,
+                   float linear_contribution, float update_fraction, long long* launches, std::string* err) {
+    if (!lw->have_perturbation) { *err = "linear winds: no perturbation has been computed yet"; return 1; }
+    if (i0 < 0 || j0 < 0 || i0 + g.nx > lw->nx || j0 + g.ny > lw->ny || k < 0 || k >= g.nz) {
+        *err = "linear winds: the tile does not lie inside the terrain given to icar_linear_winds_init";
+        return 1;
+    }
+    const size_t ue = (size_t)g.ldu * g.nz * g.ny, ve = (size_t)g.ld * g.nz * (g.ny + 1);
+    if (!lw->upert || lw->upert_elems != ue || lw->vpert_elems != ve) {
+        if (lw->upert) cudaFree(lw->upert);
+        if (lw->vpert) cudaFree(lw->vpert);
+        lw->upert = lw->vpert = nullptr;
+        LWCU(cudaMalloc((void**)&lw->upert, ue * sizeof(float)));
+        LWCU(cudaMalloc((void**)&lw->vpert, ve * sizeof(float)));
+        LWCU(cudaMemsetAsync(lw->upert, 0, ue * sizeof(float), lw->st));       // hi_u_perturbation = 0 (:1264)
+        LWCU(cudaMemsetAsync(lw->vpert, 0, ve * sizeof(float), lw->st));
+        lw->upert_elems = ue;
+        lw->vpert_elems = ve;
+    }
+    k_lw_apply_u<<<grid2d(g.nx + 1, g.ny), kThreads, 0, lw->st>>>(lw->up, lw->fnx, lw->buffer, g, i0, j0, k, u3d, lw->upert,
+                                                                  linear_contribution, update_fraction);
+    k_lw_apply_v<<<grid2d(g.nx, g.ny + 1), kThreads, 0, lw->st>>>(lw->vp, lw->fnx, lw->buffer, g, i0, j0, k, v3d, lw->vpert,
+                                                                  linear_contribution, update_fraction);
+    LWCU(cudaGetLastError());
+    if (launches) *launches += 2;
+    return 0;
+}
+
+}  // namespace icar

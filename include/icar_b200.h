@@ -213,6 +213,48 @@ int icar_apply_forcing(icar_ctx* ctx, double dt_seconds);
  * call sites wind.f90:330-332.  update_winds runs this once per forcing interval ("next" rank 3). */
 int icar_balance_uvw(icar_ctx* ctx);
 
+/* ---- linear-theory winds (src/physics/linear_winds.f90; "next" rank 3, BASELINE configs[4]).  update_winds calls
+ * linear_perturb once per forcing interval (wind.f90:310-354), then balance_uvw.  The reference goes through a
+ * look-up table over 10 speeds x 36 directions x 10 stabilities (initialize_spatial_winds :596-830, interpolated in
+ * spatial_winds :840-1127) -- 3600 x nx x nz x ny x 2 REALs, 7 TB at 2048 x 2048 x 60.  This library evaluates the
+ * perturbation directly for the background state (U, V, N^2) the caller passes: one LUT entry, computed when it
+ * is needed, with the same routines the LUT builder calls.  2-D arrays are Fortran (nx, ny), first index fastest. */
+
+/* add_buffer_topo(terrain, buffer_topo, smooth_window, buffer) (:351-418).  out: (nx + 2 buffer, ny + 2 buffer)
+ * complex double, interleaved.  Pure host function (no GPU needed). */
+void icar_add_buffer_topo(const float* terrain, int nx, int ny, int smooth_window, int buffer, double* out);
+
+/* setup_linwinds (:1180-1222) + initialize_linear_theory_data (:426-472): the terrain buffered twice (window 5
+ * over `buffer` cells, then a rim of 2), forward FFT / N, fftshift -> domain%terrain_frequency on the device;
+ * wavenumber grids from opt.dx.  global_terrain = domain%global_terrain (ids:ide, jds:jde); every image passes the
+ * same array.  buffer = lt_options%buffer (default 50, options_obj.f90:1452). */
+int icar_linear_winds_init(icar_ctx* ctx, const float* global_terrain, int nx_global, int ny_global, int buffer);
+/* size of the buffered (FFT) grid and the total buffer (lt buffer + 2, :1207) */
+int icar_linear_winds_dims(icar_ctx* ctx, int* fft_nx, int* fft_ny, int* buffer);
+/* domain%terrain_frequency, (fft_nx, fft_ny) complex double, interleaved */
+int icar_linear_winds_terrain_frequency(icar_ctx* ctx, double* host);
+
+/* linear_perturbation(U, V, Nsq, z_bottom, z_top, minimum_step, fourier_terrain, lt_data) (:239-344), both
+ * specifics of the generic: z_bottom_2d / z_top_2d NULL -> linear_perturbation_constz with the scalar bounds;
+ * otherwise linear_perturbation_varyingz with (nx_global, ny_global) host fields.  u_perturb / v_perturb (may be
+ * NULL) receive lt_data%u_perturb / v_perturb, (fft_nx, fft_ny) complex double; they also stay on the device. */
+int icar_linear_perturbation(icar_ctx* ctx, float U, float V, float Nsq, float z_bottom, float z_top,
+                             const float* z_bottom_2d, const float* z_top_2d, float minimum_step,
+                             double* u_perturb, double* v_perturb);
+
+/* linear_perturb(domain, options, vsmooth, reverse, useDensity, update) (:1317-1366) on the resident u, v of this
+ * image's tile, for a uniform background (U, V, Nsq): for every level the layer's perturbation as the LUT builder
+ * computes it (:716-737: space_varying_dz -> bounds global_z_interface(:,z,:) - terrain and + global_dz_interface(:,z,:),
+ * both (nx_global, nz, ny_global); else layer_height(z) -+ dz_levels(z)/2 with layer_height = z(ims,:,jms) - terrain(ims,jms)),
+ * staggered to the u / v faces (:756-762), then, as spatial_winds does (:1094-1111),
+ *   u_perturbation = u_perturbation * (1 - linear_update_fraction) + linear_update_fraction * new
+ *   u = u + u_perturbation * linear_contribution                                     (v likewise).
+ * Defaults of lt_parameters: minimum_layer_size 100, linear_contribution 1, linear_update_fraction 0.2
+ * (options_obj.f90:1459-1479).  Follow with icar_balance_uvw, as update_winds does. */
+int icar_linear_perturb(icar_ctx* ctx, float U, float V, float Nsq, const float* global_z_interface,
+                        const float* global_dz_interface, const float* layer_height, const float* dz_levels,
+                        float minimum_layer_size, float linear_contribution, float linear_update_fraction);
+
 /* domain%enforce_limits (src/objects/domain_obj.f90:2228-2243): where (q < 0) q = 0 on every scalar the
  * microphysics scheme allocates. */
 int icar_enforce_limits(icar_ctx* ctx);

@@ -1,0 +1,169 @@
+"""Linear-theory winds on the device (icar_linear_winds_init / icar_linear_perturbation / icar_linear_perturb;
+SURVEY.md section 8f rank 3) against the NumPy restatement oracle/linear_winds_np.py.  PARITY UNPINNED (the
+reference holds no expected values for this path and cannot be compiled here).
+
+Tolerance: 1e-6 of the field maximum (BASELINE north_star).  The arithmetic is complex double on both sides; what
+differs is cuFFT against pocketfft (1e-15), the division formula (see tests/test_linear_winds_host.py) and, rarely,
+the single-precision rounding inside the reference's fftshift flipping for one coefficient (6e-8 of it)."""
+import os
+
+import numpy as np
+import pytest
+
+from icar_b200 import ideal
+from oracle import linear_winds_np as LW
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(os.environ.get("ICAR_TEST_UNVALIDATED") != "1",
+                                 reason="not yet run on hardware (set ICAR_TEST_UNVALIDATED=1)")]
+
+RTOL = 1e-6
+
+
+def hill(nx, ny, seed=0):
+    rng = np.random.default_rng(seed)
+    x = np.arange(nx)[:, None]; y = np.arange(ny)[None, :]
+    return (800 * np.exp(-((x - nx / 2) / 5.0) ** 2 - ((y - ny / 3) / 7.0) ** 2) + 30 * rng.random((nx, ny)) + 4 * x).astype(np.float32)
+
+
+def domain(gpu_lib, nx, nz, ny, dx=2000.0):
+    return gpu_lib.Domain(gpu_lib.Grid.single_image(nx, nz, ny), gpu_lib.Options(dx=dx))
+
+
+def close(a, b, what):
+    scale = np.abs(b).max()
+    assert scale > 0, what
+    err = np.abs(a - b).max() / scale
+    assert err <= RTOL, f"{what}: {err:.2e} of the field maximum"
+    return err
+
+
+@pytest.mark.parametrize("nx,ny,buffer", [(30, 22, 5), (64, 40, 8), (33, 47, 3)])
+def test_terrain_frequency(gpu_lib, nx, ny, buffer):
+    terrain = hill(nx, ny, seed=nx)                       # [i, j]
+    dom = domain(gpu_lib, nx, 4, ny)
+    dom.linear_winds_init(terrain.T, buffer=buffer)
+    want, total = LW.terrain_frequency(terrain, buffer)
+    assert dom.linear_winds_dims() == (want.shape[0], want.shape[1], total)
+    got = dom.terrain_frequency().T
+    assert got.dtype == np.complex128
+    assert np.array_equal(got, got.astype(np.complex64).astype(np.complex128))      # went through single precision
+    close(got, want, "terrain_frequency")
+
+
+@pytest.mark.parametrize("U,V,Nsq", [(10.0, 3.0, 1e-4), (-7.0, 2.5, 3e-5), (0.0, 6.0, 2e-4), (10.0, 0.0, -1e-4)])
+def test_layer_with_constant_bounds(gpu_lib, U, V, Nsq):
+    nx, ny, buffer = 40, 28, 6
+    terrain = hill(nx, ny, seed=2)
+    dom = domain(gpu_lib, nx, 4, ny)
+    dom.linear_winds_init(terrain.T, buffer=buffer)
+    tf, _ = LW.terrain_frequency(terrain, buffer)
+    lt = LW.LinearTheoryData(tf.shape[0], tf.shape[1], 2000.0)
+    for zb, zt in ((0.0, 90.0), (200.0, 830.0), (1500.0, 1900.0)):
+        u, v = dom.linear_perturbation(U, V, Nsq, zb, zt, minimum_step=100.0)
+        wu, wv = LW.linear_perturbation_constz(U, V, Nsq, zb, zt, 100.0, tf, lt)
+        close(u.T, wu, f"u_perturb {zb}..{zt}")
+        close(v.T, wv, f"v_perturb {zb}..{zt}")
+    u, v = dom.linear_perturbation(0.0, 0.0, Nsq, 0.0, 400.0)
+    assert not u.any() and not v.any()
+
+
+def test_layer_with_terrain_following_bounds(gpu_lib):
+    nx, ny, buffer = 36, 26, 5
+    terrain = hill(nx, ny, seed=5)
+    dom = domain(gpu_lib, nx, 4, ny)
+    dom.linear_winds_init(terrain.T, buffer=buffer)
+    tf, total = LW.terrain_frequency(terrain, buffer)
+    lt = LW.LinearTheoryData(tf.shape[0], tf.shape[1], 2000.0)
+    jac = (np.float32(6000.0) - terrain) / np.float32(6000.0)
+    zb = (np.float32(1200.0) * jac).astype(np.float32)
+    zt = (zb + np.float32(400.0) * jac).astype(np.float32)
+    u, v = dom.linear_perturbation(9.0, -2.0, 1e-4, zb.T, zt.T, minimum_step=100.0)
+    wu, wv = LW.linear_perturbation_varyingz(9.0, -2.0, 1e-4, zb, zt, 100.0, tf, lt, total)
+    ok = np.isfinite(wu)                                   # layer_count can be 0 outside every column's layer
+    assert np.array_equal(np.isfinite(u.T), ok)
+    close(np.where(ok, u.T, 0), np.where(ok, wu, 0), "u_perturb")
+    close(np.where(ok, v.T, 0), np.where(ok, wv, 0), "v_perturb")
+
+
+def stagger(field, buffer, nx, ny):
+    """initialize_spatial_winds :756-762 (0-based): u faces (nx+1, ny), v faces (nx, ny+1), REAL."""
+    f = np.float32
+    b = buffer
+    tu = (field[0][b - 1:b + nx, b:b + ny] + field[0][b:b + nx + 1, b:b + ny]).real.astype(f) / f(2)
+    tv = (field[1][b:b + nx, b - 1:b + ny] + field[1][b:b + nx, b:b + ny + 1]).real.astype(f) / f(2)
+    return tu, tv
+
+
+@pytest.mark.parametrize("varying", [False, True])
+def test_linear_perturb_updates_the_resident_winds(gpu_lib, varying):
+    st = ideal.make_ideal_case(nx=40, nz=6, ny=24, perturb=True)
+    nx, nz, ny = 40, 6, 24
+    dom = domain(gpu_lib, nx, nz, ny, dx=st["dx"])
+    dom.upload_state(st)
+    terrain = np.ascontiguousarray(st["terrain"].T)        # [i, j]
+    buffer = 7
+    dom.linear_winds_init(st["terrain"], buffer=buffer)
+    tf, total = LW.terrain_frequency(terrain, buffer)
+    lt = LW.LinearTheoryData(tf.shape[0], tf.shape[1], st["dx"])
+    U, V, Nsq, frac, contrib = 10.0, 4.0, 1e-4, np.float32(0.2), np.float32(0.7)
+    f = np.float32
+    zi = np.empty_like(st["dz_interface"])                  # (ny, nz, nx): z_interface = terrain + sum of the layers below
+    zi[:, 0, :] = st["terrain"]
+    for k in range(1, nz):
+        zi[:, k, :] = zi[:, k - 1, :] + st["dz_interface"][:, k - 1, :]
+    lh = (np.cumsum(st["dz_levels"], dtype=f) - st["dz_levels"] / f(2)).astype(f)
+    u, v = st["u"].copy(), st["v"].copy()
+    up, vp = np.zeros_like(u), np.zeros_like(v)
+    for call in range(2):                                   # the second call exercises the (1 - fraction) memory
+        if varying:
+            dom.linear_perturb(U, V, Nsq, global_z_interface=zi, global_dz_interface=st["dz_interface"],
+                               linear_contribution=float(contrib), linear_update_fraction=float(frac))
+        else:
+            dom.linear_perturb(U, V, Nsq, layer_height=lh, dz_levels=st["dz_levels"],
+                               linear_contribution=float(contrib), linear_update_fraction=float(frac))
+        for k in range(nz):
+            if varying:
+                zb = (zi[:, k, :] - st["terrain"]).T
+                zt = (zi[:, k, :] - st["terrain"] + st["dz_interface"][:, k, :]).T
+                pert = LW.linear_perturbation_varyingz(U, V, Nsq, zb, zt, 100.0, tf, lt, total)
+            else:
+                half = st["dz_levels"][k] / f(2)
+                pert = LW.linear_perturbation_constz(U, V, Nsq, lh[k] - half, lh[k] + half, 100.0, tf, lt)
+            tu, tv = stagger(pert, total, nx, ny)
+            up[:, k, :] = up[:, k, :] * (f(1) - frac) + frac * tu.T
+            vp[:, k, :] = vp[:, k, :] * (f(1) - frac) + frac * tv.T
+            u[:, k, :] += up[:, k, :] * contrib
+            v[:, k, :] += vp[:, k, :] * contrib
+    du, dv = dom.download("u") - st["u"], dom.download("v") - st["v"]
+    wu, wv = u - st["u"], v - st["v"]
+    scale = max(np.abs(wu).max(), np.abs(wv).max())
+    assert scale > 1e-3                                     # the hill does perturb a 10 m/s flow
+    assert np.abs(du - wu).max() <= 2e-6 * max(scale, 10.0) and np.abs(dv - wv).max() <= 2e-6 * max(scale, 10.0)
+    dom.balance_uvw()                                       # what update_winds does next (wind.f90:330-332)
+    assert np.isfinite(dom.download("w")).all()
+
+
+def test_full_size_plane_against_the_restatement(gpu_lib):
+    """A BASELINE-sized plane (2048 x 2048 cells, configs[4]; 2152 x 2152 with the default buffer of 50): the
+    terrain spectrum and one layer with four sub-layer heights against the restatement (about 15 s of NumPy), and
+    two properties: a ridge that is uniform in y gives a perturbation that is uniform in y, and its amplitude is
+    N h0 up to what the blended rim adds (the buffered ridge is not periodic: measured 14-19 % on the CPU)."""
+    n, buffer, h0, U, V, Nsq, waves = 2048, 50, 100.0, 10.0, 0.0, 1e-4, 64
+    x = np.arange(n, dtype=np.float64)[:, None]
+    terrain = (h0 * np.cos(2 * np.pi * waves * x / n) * np.ones((1, n))).astype(np.float32)     # [i, j]
+    dom = domain(gpu_lib, n, 2, n, dx=2000.0)
+    dom.linear_winds_init(terrain.T, buffer=buffer)
+    fnx, fny, total = dom.linear_winds_dims()
+    assert (fnx, fny, total) == (n + 2 * buffer + 4, n + 2 * buffer + 4, buffer + 2)
+    tf, _ = LW.terrain_frequency(terrain, buffer)
+    close(dom.terrain_frequency().T, tf, "terrain_frequency")
+    lt = LW.LinearTheoryData(fnx, fny, 2000.0)
+    u, v = dom.linear_perturbation(U, V, Nsq, 400.0, 800.0, minimum_step=100.0)
+    wu, wv = LW.linear_perturbation_constz(U, V, Nsq, 400.0, 800.0, 100.0, tf, lt)
+    close(u.T, wu, "u_perturb")
+    close(v.T, wv, "v_perturb")
+    ur = u.T.real
+    assert np.abs(ur - ur[:, :1]).max() <= 1e-6 * np.abs(ur).max()
+    inner = ur[total + 200:total + n - 200, total + 200:total + n - 200]
+    assert 0.9 * np.sqrt(Nsq) * h0 < np.abs(inner).max() < 1.3 * np.sqrt(Nsq) * h0
