@@ -152,7 +152,7 @@ SYMBOLS = (
     "icar_profile_enable", "icar_profile_read", "icar_diagnostic_update", "icar_compute_dt", "icar_enforce_limits",
     "icar_upload_tendency", "icar_apply_forcing", "icar_balance_uvw",
     "icar_add_buffer_topo", "icar_linear_winds_init", "icar_linear_winds_dims", "icar_linear_winds_terrain_frequency",
-    "icar_linear_perturbation", "icar_linear_perturb")
+    "icar_linear_perturbation", "icar_linear_perturb", "icar_restart_info", "icar_write_restart", "icar_read_restart")
 
 
 def lib() -> C.CDLL:
@@ -170,6 +170,16 @@ def lib() -> C.CDLL:
         l.icar_kernel_launches.argtypes = [C.c_void_p]
         _lib = l
     return _lib
+
+
+def restart_info(path):
+    """Header of a restart file without a GPU: (Grid, microphysics, model_time, [var ids])."""
+    g, mp, t, n = Grid(), C.c_int(), C.c_double(), C.c_int()
+    ids = (C.c_int * len(VAR))()
+    rc = lib().icar_restart_info(os.fsencode(path), C.byref(g), C.byref(mp), C.byref(t), C.byref(n), ids)
+    if rc:
+        raise IcarError(rc, lib().icar_last_error(None).decode())
+    return g, mp.value, t.value, list(ids[:n.value])
 
 
 def _f32(a, shape=None, name="array"):
@@ -358,6 +368,15 @@ class Domain:
         self._check(lib().icar_linear_perturb(self._h, C.c_float(U), C.c_float(V), C.c_float(Nsq), _ptr(zi), _ptr(dzi),
                                               _ptr(lh), _ptr(dz), C.c_float(minimum_layer_size),
                                               C.c_float(linear_contribution), C.c_float(linear_update_fraction)))
+
+    # -- restart / output files (src/io/output_obj.f90 save_file, src/io/restart.f90:11-90)
+    def write_restart(self, path):
+        """Every resident variable + model time to one self-describing file (format: icar_b200/restart.py)."""
+        self._check(lib().icar_write_restart(self._h, os.fsencode(path)))
+
+    def read_restart(self, path):
+        """restart_model: the variables and the model time of a file written for this tile and scheme."""
+        self._check(lib().icar_read_restart(self._h, os.fsencode(path)))
 
     def enforce_limits(self):
         """domain%enforce_limits (domain_obj.f90:2228-2243)."""

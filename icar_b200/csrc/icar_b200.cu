@@ -1804,3 +1804,186 @@ extern "C" int icar_linear_perturb(icar_ctx* ctx, float U, float V, float Nsq, c
     }
     return ICAR_OK;
 }
+
+// ------------------------------------------------------------------ restart / output files ("next" rank 4)
+//
+// One self-describing little-endian file per image (the reference writes one NetCDF file per image as well,
+// output_obj.f90; there is no NetCDF library in this image).  Layout:
+//   char magic[8] = "ICARB2RS"; int32 version = 1; int32 nvars; int32 grid[19] (icar_grid member order);
+//   int32 microphysics; double model_time; double last_model_time (mp()'s update-interval memory);
+//   nvars x { int32 var (enum icar_var); int32 elem_size; int32 dims[3] = (nx', ny', nz') in FILE order, nz' = 1
+//             for 2-D variables; int64 nbytes; data }
+// 3-D data are in the reference's file order (x, y, z) = reshape(data_3d, order=[1,3,2]) (output_obj.f90:423-426).
+
+namespace {
+
+const char kRestartMagic[8] = {'I', 'C', 'A', 'R', 'B', '2', 'R', 'S'};
+
+struct RestartHeader {
+    char magic[8];
+    int version, nvars;
+    int grid[19];
+    int microphysics;
+    double model_time, last_model_time;
+};
+struct RestartVar {
+    int var, elem_size, dims[3];
+    long long nbytes;
+};
+
+bool read_exact(FILE* f, void* p, size_t n) { return std::fread(p, 1, n, f) == n; }
+
+int read_restart_header(FILE* f, RestartHeader* h, std::string* err) {
+    if (!read_exact(f, h->magic, 8) || std::memcmp(h->magic, kRestartMagic, 8) != 0) { *err = "not an icar_b200 restart file"; return 1; }
+    if (!read_exact(f, &h->version, 4) || !read_exact(f, &h->nvars, 4) || !read_exact(f, h->grid, sizeof h->grid) ||
+        !read_exact(f, &h->microphysics, 4) || !read_exact(f, &h->model_time, 8) || !read_exact(f, &h->last_model_time, 8)) {
+        *err = "truncated restart header";
+        return 1;
+    }
+    if (h->version != 1) { *err = "restart file version " + std::to_string(h->version) + " (this library reads 1)"; return 1; }
+    if (h->nvars < 0 || h->nvars > ICAR_VAR_COUNT) { *err = "restart file: bad variable count"; return 1; }
+    return 0;
+}
+
+int read_restart_var(FILE* f, RestartVar* v, std::string* err) {
+    if (!read_exact(f, &v->var, 4) || !read_exact(f, &v->elem_size, 4) || !read_exact(f, v->dims, 12) ||
+        !read_exact(f, &v->nbytes, 8)) { *err = "truncated restart file (variable record)"; return 1; }
+    if (v->var < 0 || v->var >= ICAR_VAR_COUNT || (v->elem_size != 4 && v->elem_size != 8) ||
+        v->nbytes != (long long)v->elem_size * v->dims[0] * v->dims[1] * v->dims[2]) { *err = "corrupt restart file (variable record)"; return 1; }
+    return 0;
+}
+
+}  // namespace
+
+extern "C" int icar_restart_info(const char* path, icar_grid* grid, int* microphysics, double* model_time, int* nvars,
+                                 int* vars) {
+    if (!path) return ICAR_ERR_INVALID;
+    FILE* f = std::fopen(path, "rb");
+    if (!f) return fail(nullptr, ICAR_ERR_INVALID, std::string("icar_restart_info: cannot open ") + path);
+    RestartHeader h;
+    std::string err;
+    int rc = read_restart_header(f, &h, &err);
+    for (int n = 0; !rc && n < h.nvars; ++n) {
+        RestartVar v;
+        rc = read_restart_var(f, &v, &err);
+        if (!rc && std::fseek(f, (long)v.nbytes, SEEK_CUR) != 0) { err = "truncated restart file (data)"; rc = 1; }
+        if (!rc && vars) vars[n] = v.var;
+    }
+    if (!rc) {
+        // the data of the last variable must be there too
+        const long here = std::ftell(f);
+        std::fseek(f, 0, SEEK_END);
+        if (std::ftell(f) < here) { err = "truncated restart file (data)"; rc = 1; }
+    }
+    std::fclose(f);
+    if (rc) return fail(nullptr, ICAR_ERR_INVALID, std::string("icar_restart_info: ") + err);
+    if (grid) std::memcpy(grid, h.grid, sizeof h.grid);
+    if (microphysics) *microphysics = h.microphysics;
+    if (model_time) *model_time = h.model_time;
+    if (nvars) *nvars = h.nvars;
+    return ICAR_OK;
+}
+
+extern "C" int icar_write_restart(icar_ctx* ctx, const char* path) {
+    if (!ctx || !path) return fail(ctx, ICAR_ERR_INVALID, "icar_write_restart: bad argument");
+    static_assert(sizeof(icar_grid) == 19 * sizeof(int), "icar_grid is 19 ints");
+    CU(cudaSetDevice(ctx->device));
+    { int jr = join_aux(ctx); if (jr) return jr; }
+    FILE* f = std::fopen(path, "wb");
+    if (!f) return fail(ctx, ICAR_ERR_INVALID, std::string("icar_write_restart: cannot create ") + path);
+    // the precipitation accumulators start at zero and are only ever written by the mp kernels: always saved
+    auto saved = [&](int v) { return ctx->vars[v] && (ctx->uploaded[v] || var_shape(v) == D2); };
+    int nvars = 0;
+    for (int v = 0; v < ICAR_VAR_COUNT; ++v) nvars += saved(v) ? 1 : 0;
+    const int version = 1;
+    bool ok = std::fwrite(kRestartMagic, 1, 8, f) == 8 && std::fwrite(&version, 4, 1, f) == 1 &&
+              std::fwrite(&nvars, 4, 1, f) == 1 && std::fwrite(&ctx->grid, sizeof(icar_grid), 1, f) == 1 &&
+              std::fwrite(&ctx->opt.microphysics, 4, 1, f) == 1 && std::fwrite(&ctx->model_time, 8, 1, f) == 1 &&
+              std::fwrite(&ctx->last_model_time, 8, 1, f) == 1;
+    std::vector<char> host;
+    int rc = ICAR_OK;
+    for (int var = 0; ok && rc == ICAR_OK && var < ICAR_VAR_COUNT; ++var) {
+        if (!saved(var)) continue;
+        int width, pitch; size_t rows;
+        var_geometry(ctx, var, &width, &pitch, &rows);
+        const bool two_d = var_shape(var) == D2;
+        const int nz = two_d ? 1 : ctx->g.nz, rows_y = (int)(rows / nz);
+        RestartVar rv{var, (int)elem_size(var), {width, rows_y, nz}, (long long)elem_size(var) * width * (long long)rows};
+        host.resize((size_t)rv.nbytes);
+        if (two_d) {
+            rc = copy_out(ctx, host.data(), ctx->vars[var], width, pitch, rows, elem_size(var));
+        } else {
+            void* dense = nullptr;
+            rc = get_scratch(ctx, 0, sizeof(float), &dense);
+            if (rc == ICAR_OK) {
+                ctx->launches += output_reorder_launch((float*)ctx->vars[var], (float*)dense, width, nz, rows_y, pitch, true, ctx->stream);
+                if (cudaMemcpyAsync(host.data(), dense, (size_t)rv.nbytes, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess)
+                    rc = fail(ctx, ICAR_ERR_CUDA, "icar_write_restart: device to host copy failed");
+            }
+        }
+        if (rc == ICAR_OK && cudaStreamSynchronize(ctx->stream) != cudaSuccess)
+            rc = fail(ctx, ICAR_ERR_CUDA, std::string("icar_write_restart: ") + cudaGetErrorString(cudaGetLastError()));
+        if (rc == ICAR_OK)
+            ok = std::fwrite(&rv.var, 4, 1, f) == 1 && std::fwrite(&rv.elem_size, 4, 1, f) == 1 &&
+                 std::fwrite(rv.dims, 4, 3, f) == 3 && std::fwrite(&rv.nbytes, 8, 1, f) == 1 &&
+                 std::fwrite(host.data(), 1, (size_t)rv.nbytes, f) == (size_t)rv.nbytes;
+    }
+    ok = (std::fclose(f) == 0) && ok;
+    if (rc != ICAR_OK) return rc;
+    if (!ok) return fail(ctx, ICAR_ERR_INVALID, std::string("icar_write_restart: write to ") + path + " failed");
+    return ICAR_OK;
+}
+
+extern "C" int icar_read_restart(icar_ctx* ctx, const char* path) {
+    if (!ctx || !path) return fail(ctx, ICAR_ERR_INVALID, "icar_read_restart: bad argument");
+    CU(cudaSetDevice(ctx->device));
+    { int jr = join_aux(ctx); if (jr) return jr; }
+    FILE* f = std::fopen(path, "rb");
+    if (!f) return fail(ctx, ICAR_ERR_INVALID, std::string("icar_read_restart: cannot open ") + path);
+    RestartHeader h;
+    std::string err;
+    int bad = read_restart_header(f, &h, &err);
+    // restart_domain_error (restart.f90): the file must have been written for this tile and this scheme
+    if (!bad && std::memcmp(h.grid, &ctx->grid, sizeof h.grid) != 0) { err = "the file was written for a different grid / decomposition"; bad = 1; }
+    if (!bad && h.microphysics != ctx->opt.microphysics) { err = "the file was written with a different microphysics scheme"; bad = 1; }
+    std::vector<char> host;
+    int rc = ICAR_OK;
+    for (int n = 0; !bad && rc == ICAR_OK && n < h.nvars; ++n) {
+        RestartVar rv;
+        bad = read_restart_var(f, &rv, &err);
+        if (bad) break;
+        int width, pitch; size_t rows;
+        var_geometry(ctx, rv.var, &width, &pitch, &rows);
+        const bool two_d = var_shape(rv.var) == D2;
+        const int nz = two_d ? 1 : ctx->g.nz, rows_y = (int)(rows / nz);
+        if (!ctx->vars[rv.var] || rv.elem_size != (int)elem_size(rv.var) || rv.dims[0] != width || rv.dims[1] != rows_y || rv.dims[2] != nz) {
+            err = "variable " + std::to_string(rv.var) + " has a different shape in the file";
+            bad = 1;
+            break;
+        }
+        host.resize((size_t)rv.nbytes);
+        if (!read_exact(f, host.data(), (size_t)rv.nbytes)) { err = "truncated restart file (data)"; bad = 1; break; }
+        if (two_d) {
+            rc = copy_in(ctx, ctx->vars[rv.var], host.data(), width, pitch, rows, elem_size(rv.var));
+        } else {
+            void* dense = nullptr;
+            rc = get_scratch(ctx, 0, sizeof(float), &dense);
+            if (rc == ICAR_OK) {
+                if (cudaMemcpyAsync(dense, host.data(), (size_t)rv.nbytes, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess)
+                    rc = fail(ctx, ICAR_ERR_CUDA, "icar_read_restart: host to device copy failed");
+                else
+                    ctx->launches += output_reorder_launch((float*)ctx->vars[rv.var], (float*)dense, width, nz, rows_y, pitch, false, ctx->stream);
+            }
+        }
+        if (rc == ICAR_OK && cudaStreamSynchronize(ctx->stream) != cudaSuccess)
+            rc = fail(ctx, ICAR_ERR_CUDA, std::string("icar_read_restart: ") + cudaGetErrorString(cudaGetLastError()));
+        if (rc == ICAR_OK) ctx->uploaded[rv.var] = true;
+    }
+    std::fclose(f);
+    if (rc != ICAR_OK) return rc;
+    if (bad) return fail(ctx, ICAR_ERR_INVALID, std::string("icar_read_restart: ") + err);
+    ctx->model_time = h.model_time;
+    ctx->last_model_time = h.last_model_time;
+    ctx->winds_f64_valid = false;
+    return ICAR_OK;
+}

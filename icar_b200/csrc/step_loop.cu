@@ -99,6 +99,16 @@ k_enforce_limits(Geom g, FieldPtrs f, int nf) {
 
 dim3 row_grid(const Geom& g) { return dim3((g.nx + 127) / 128, g.nz, g.ny); }
 
+// (x, z, y) memory order <-> (x, y, z) file order of output_obj.f90:423-426 / restart.f90:57-63
+__global__ void __launch_bounds__(128)
+k_output_reorder(float* __restrict__ field, float* __restrict__ dense, int width, int nz, int rows_y, int pitch, int to_file) {
+    const int i = blockIdx.x * 128 + threadIdx.x, k = blockIdx.y, j = blockIdx.z;
+    if (i >= width) return;
+    const size_t m = (size_t)i + (size_t)pitch * ((size_t)k + (size_t)nz * (size_t)j);
+    const size_t f = (size_t)i + (size_t)width * ((size_t)j + (size_t)rows_y * (size_t)k);
+    if (to_file) dense[f] = field[m]; else field[m] = dense[f];
+}
+
 }  // namespace
 
 int diagnostic_update_launch(const Geom& g, const float* pressure, const float* th, float* exner, float* density,
@@ -124,6 +134,13 @@ int apply_forcing_launch(float* q, const float* dqdt, int width, int nz, int row
 int balance_uvw_launch(const Geom& g, const float* u, const float* v, float* w, const float* ju, const float* jv,
                        const float* jw, const float* dz, float dx, cudaStream_t st) {
     k_balance_uvw<<<dim3((g.nx + 127) / 128, g.ny), 128, 0, st>>>(g, u, v, w, ju, jv, jw, dz, dx);
+    return 1;
+}
+
+int output_reorder_launch(float* field, float* dense, int width, int nz, int rows_y, int pitch, bool to_file,
+                          cudaStream_t st) {
+    k_output_reorder<<<dim3((width + 127) / 128, nz, rows_y), 128, 0, st>>>(field, dense, width, nz, rows_y, pitch,
+                                                                           to_file ? 1 : 0);
     return 1;
 }
 

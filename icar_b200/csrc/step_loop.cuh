@@ -32,6 +32,12 @@ int apply_forcing_launch(float* q, const float* dqdt, int width, int nz, int row
 int balance_uvw_launch(const Geom& g, const float* u, const float* v, float* w, const float* ju, const float* jv,
                        const float* jw, const float* dz, float dx, cudaStream_t st);
 
+// output_t%save_data writes a 3-D variable as reshape(data_3d, order=[1,3,2]) (src/io/output_obj.f90:423-426): the file
+// holds (x, y, z), memory holds (x, z, y).  to_file: dense[(k*rows_y + j)*width + i] = field(i, k, j); otherwise the
+// reverse (read_restart_data, src/io/restart.f90:57-63).  x is the fastest index on both sides.
+int output_reorder_launch(float* field, float* dense, int width, int nz, int rows_y, int pitch, bool to_file,
+                          cudaStream_t st);
+
 // where (q < 0) q = 0 for every listed field (domain_obj.f90:2228-2243)
 int enforce_limits_launch(const Geom& g, float* const* fields, int nfields, cudaStream_t st);
 

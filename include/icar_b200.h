@@ -255,6 +255,24 @@ int icar_linear_perturb(icar_ctx* ctx, float U, float V, float Nsq, const float*
                         const float* global_dz_interface, const float* layer_height, const float* dz_levels,
                         float minimum_layer_size, float linear_contribution, float linear_update_fraction);
 
+/* ---- restart / output files ("next" rank 4).  The reference writes one NetCDF file per image (output_t%save_file,
+ * src/io/output_obj.f90:41-80, 404-458) and reads it back in restart_model (src/io/restart.f90:11-90); there is no
+ * NetCDF library here, so the file is a self-describing little-endian binary (layout: icar_b200/restart.py, which
+ * also converts it to NumPy arrays).  3-D variables are stored in the reference's FILE order (x, y, z) =
+ * reshape(data_3d, order=[1,3,2]) (output_obj.f90:423-426); the reorder runs on the device. */
+
+/* Writes every resident variable that has been uploaded or computed, the model time and mp()'s update-interval
+ * memory (mp_driver.f90:698-713) for this image's tile. */
+int icar_write_restart(icar_ctx* ctx, const char* path);
+/* restart_model / read_restart_data: the file must have been written for the same tile (grid_t bounds) and the
+ * same microphysics scheme -- otherwise ICAR_ERR_INVALID, where the reference stops in restart_domain_error.
+ * Continuing from a file is bit-identical to not having stopped. */
+int icar_read_restart(icar_ctx* ctx, const char* path);
+/* Header of a file without a GPU: grid, scheme, model time and the variable ids it holds (vars: room for
+ * ICAR_VAR_COUNT ints).  Any out pointer may be NULL.  Pure host function. */
+int icar_restart_info(const char* path, icar_grid* grid, int* microphysics, double* model_time, int* nvars,
+                      int* vars);
+
 /* domain%enforce_limits (src/objects/domain_obj.f90:2228-2243): where (q < 0) q = 0 on every scalar the
  * microphysics scheme allocates. */
 int icar_enforce_limits(icar_ctx* ctx);

@@ -9,7 +9,7 @@ ICAR_TEST_UNVALIDATED=1 timeout 300 python -m pytest tests/test_gpu_parity.py -m
     -k "candidate or 52_level or packed" > gpurun_out/candidates_tests.log 2>&1
 ICAR_TEST_UNVALIDATED=1 timeout 120 python -m pytest tests/test_gpu_step_loop.py -m gpu -q -k "step_host or host_pipeline" >> gpurun_out/candidates_tests.log 2>&1
 ICAR_TEST_UNVALIDATED=1 timeout 300 python -m pytest tests/test_cpp_host.py tests/test_gpu_step_graph.py -m gpu -q >> gpurun_out/candidates_tests.log 2>&1
-ICAR_TEST_UNVALIDATED=1 timeout 300 python -m pytest tests/test_gpu_linear_winds.py -m gpu -q >> gpurun_out/candidates_tests.log 2>&1
+ICAR_TEST_UNVALIDATED=1 timeout 400 python -m pytest tests/test_gpu_linear_winds.py tests/test_gpu_restart.py -m gpu -q >> gpurun_out/candidates_tests.log 2>&1
 tail -15 gpurun_out/candidates_tests.log
 P='import sys,json; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print(sys.argv[1], "ms/step", round(d["ms_per_step"],4), "e2e ms", round(d["e2e"]["ms_per_step"],2), {k:round(v["ms_per_step"],4) for k,v in d["kernels"].items()})'
 run() {  # name, env assignments..., then -- bench arguments
