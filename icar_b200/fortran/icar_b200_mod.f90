@@ -32,6 +32,7 @@ module icar_b200_mod
     public :: adv_init, adv_var_request, advect
     public :: mp_init, mp_var_request, mp
     public :: b200_halo_send, b200_halo_retrieve, b200_sync_to_host, b200_finalize, b200_physics_steps
+    public :: b200_linear_perturb, b200_write_restart, b200_read_restart
 
     ! enum icar_var
     integer(c_int), parameter :: VAR_U=0, VAR_V=1, VAR_W=2, VAR_PRESSURE=3, VAR_EXNER=4, VAR_DENSITY=5, &
@@ -123,6 +124,35 @@ module icar_b200_mod
             type(c_ptr), value :: ctx
             real(c_float), value :: dt
             integer(c_int), value :: nsteps, use_graph
+        end function
+        integer(c_int) function icar_linear_winds_init(ctx, global_terrain, nx_global, ny_global, buffer) bind(c)
+            import :: c_int, c_ptr
+            type(c_ptr), value :: ctx
+            type(c_ptr), value :: global_terrain
+            integer(c_int), value :: nx_global, ny_global, buffer
+        end function
+        integer(c_int) function icar_linear_perturb(ctx, U, V, Nsq, global_z_interface, global_dz_interface,   &
+                                                    layer_height, dz_levels, minimum_layer_size,              &
+                                                    linear_contribution, linear_update_fraction) bind(c)
+            import :: c_int, c_ptr, c_float
+            type(c_ptr), value :: ctx
+            real(c_float), value :: U, V, Nsq
+            type(c_ptr), value :: global_z_interface, global_dz_interface, layer_height, dz_levels
+            real(c_float), value :: minimum_layer_size, linear_contribution, linear_update_fraction
+        end function
+        integer(c_int) function icar_balance_uvw(ctx) bind(c)
+            import :: c_int, c_ptr
+            type(c_ptr), value :: ctx
+        end function
+        integer(c_int) function icar_write_restart(ctx, path) bind(c)
+            import :: c_int, c_ptr, c_char
+            type(c_ptr), value :: ctx
+            character(kind=c_char), intent(in) :: path(*)
+        end function
+        integer(c_int) function icar_read_restart(ctx, path) bind(c)
+            import :: c_int, c_ptr, c_char
+            type(c_ptr), value :: ctx
+            character(kind=c_char), intent(in) :: path(*)
         end function
         integer(c_int) function icar_halo_send(ctx) bind(c)
             import :: c_int, c_ptr
@@ -330,6 +360,42 @@ contains
             call down3(VAR_NR, domain%rain_number%data_3d);     call down3(VAR_QG, domain%graupel_mass%data_3d)
             call check(icar_download(ctx, VAR_GRAUPEL, c_loc(domain%graupel%data_2dd)), "icar_download")
         endif
+    end subroutine
+
+    !> linear_perturb(domain, options, vsmooth, reverse, useDensity, update) -- linear_winds.f90:1317-1366, as
+    !> update_winds calls it (wind.f90:310-332), for the space_varying_dz case and a uniform background state
+    !> (U, V, Nsq): the perturbation is computed on the GPU for that state instead of being interpolated from the
+    !> look-up table, added to the resident u, v, and w is re-balanced.  The caller uploads domain%u, domain%v first.
+    subroutine b200_linear_perturb(domain, options, U, V, Nsq)
+        type(domain_t),  intent(inout), target :: domain      ! global_terrain etc. are allocatable components
+        type(options_t), intent(in)    :: options
+        real,            intent(in)    :: U, V, Nsq
+        logical, save :: initialized = .false.
+        if (.not. initialized) then                 ! setup_linwinds, linear_winds.f90:1180-1222
+            call check(icar_linear_winds_init(ctx, c_loc(domain%global_terrain),                       &
+                                              int(size(domain%global_terrain, 1), c_int),              &
+                                              int(size(domain%global_terrain, 2), c_int),              &
+                                              int(options%lt_options%buffer, c_int)), "icar_linear_winds_init")
+            initialized = .true.
+        endif
+        call check(icar_linear_perturb(ctx, U, V, Nsq, c_loc(domain%global_z_interface),               &
+                                       c_loc(domain%global_dz_interface), c_null_ptr, c_null_ptr,      &
+                                       options%lt_options%minimum_layer_size,                          &
+                                       options%lt_options%linear_contribution,                         &
+                                       options%lt_options%linear_update_fraction), "icar_linear_perturb")
+        call check(icar_balance_uvw(ctx), "icar_balance_uvw")     ! wind.f90:330-332
+    end subroutine
+
+    !> output_t%save_file / restart_model (output_obj.f90:41-80, restart.f90:11-90): one binary file per image
+    subroutine b200_write_restart(filename)
+        character(len=*), intent(in) :: filename
+        call check(icar_write_restart(ctx, trim(filename)//c_null_char), "icar_write_restart")
+    end subroutine
+
+    subroutine b200_read_restart(filename)
+        character(len=*), intent(in) :: filename
+        call check(icar_read_restart(ctx, trim(filename)//c_null_char), "icar_read_restart")
+        state_on_device = .true.
     end subroutine
 
     subroutine b200_finalize()
