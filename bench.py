@@ -336,6 +336,27 @@ def run_b200(args, rank, world, local_rank):
 
     cells_global = nx * nz * ny
 
+    # ---------------- optional: what update_winds does once per forcing interval (BASELINE configs[4]: "full step incl.
+    # linear_winds"): linear-theory perturbation of u, v for the background flow, then balance_uvw; timed on its own
+    linear_winds = None
+    if args.linear_winds:
+        zi = np.empty_like(st["dz_interface"])             # global z_interface = terrain + the layers below
+        zi[:, 0, :] = st["terrain"]
+        for k in range(1, nz):
+            zi[:, k, :] = zi[:, k - 1, :] + st["dz_interface"][:, k - 1, :]
+        dom.linear_winds_init(st["terrain"], buffer=50)     # lt_parameters default (options_obj.f90:1452)
+        dom.synchronize()
+        dom.timer_start()
+        dom.linear_perturb(10.0, 5.0, 3e-5, global_z_interface=zi, global_dz_interface=st["dz_interface"],
+                           linear_update_fraction=1.0)
+        dom.balance_uvw()
+        lw_ms = max_over_ranks(dom.timer_stop())
+        dt = float(dom.compute_dt(st["dz_levels"]))          # the winds changed: update_dt (time_step.f90:375-423)
+        fnx, fny, _ = dom.linear_winds_dims()
+        linear_winds = {"ms": lw_ms, "fft_grid": [fnx, fny], "levels": nz, "dt_s_after": dt,
+                        "api": "icar_linear_perturb (space_varying_dz, N^2 = 3e-5, direct evaluation, cuFFT Z2Z) + icar_balance_uvw; "
+                               "once per forcing interval, not inside the timed steps"}
+
     # ---------------- device-resident timing
     for _ in range(max(args.warmup, 3)):
         dom.physics_step(dt)
@@ -491,6 +512,8 @@ def run_b200(args, rank, world, local_rank):
         }
         if cpu:
             line["cpu_baseline"] = cpu
+        if linear_winds:
+            line["linear_winds"] = linear_winds
         print(json.dumps(line), flush=True)
     dom.close()
     if distributed:
@@ -516,6 +539,9 @@ def main():
                          "(diagnostic_update), as step()'s loop does before the physics")
     ap.add_argument("--e2e-bands", type=int, default=1,
                     help="e2e pipelined over this many bands of rows (icar_b200/pipeline.py); 1 = the plain host step")
+    ap.add_argument("--linear-winds", action="store_true",
+                    help="before the steps, run the once-per-forcing-interval wind update (icar_linear_perturb + "
+                         "icar_balance_uvw) and report its time under `linear_winds` (not yet run on hardware)")
     ap.add_argument("--graph", action="store_true",
                     help="run the timed steps through icar_physics_steps (CUDA-graph replay) instead of one "
                          "icar_physics_step call per step")
