@@ -6,11 +6,14 @@ Tolerance: 1e-6 of the field maximum (BASELINE north_star).  The arithmetic is c
 differs is cuFFT against pocketfft (1e-15), the division formula (see tests/test_linear_winds_host.py) and, rarely,
 the single-precision rounding inside the reference's fftshift flipping for one coefficient (6e-8 of it)."""
 import os
+import sys
 
 import numpy as np
 import pytest
 
 from icar_b200 import ideal
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 from oracle import linear_winds_np as LW
 
 pytestmark = [pytest.mark.gpu,
@@ -86,55 +89,22 @@ def test_layer_with_terrain_following_bounds(gpu_lib):
     close(np.where(ok, v.T, 0), np.where(ok, wv, 0), "v_perturb")
 
 
-def stagger(field, buffer, nx, ny):
-    """initialize_spatial_winds :756-762 (0-based): u faces (nx+1, ny), v faces (nx, ny+1), REAL."""
-    f = np.float32
-    b = buffer
-    tu = (field[0][b - 1:b + nx, b:b + ny] + field[0][b:b + nx + 1, b:b + ny]).real.astype(f) / f(2)
-    tv = (field[1][b:b + nx, b - 1:b + ny] + field[1][b:b + nx, b:b + ny + 1]).real.astype(f) / f(2)
-    return tu, tv
-
-
 @pytest.mark.parametrize("varying", [False, True])
 def test_linear_perturb_updates_the_resident_winds(gpu_lib, varying):
-    st = ideal.make_ideal_case(nx=40, nz=6, ny=24, perturb=True)
-    nx, nz, ny = 40, 6, 24
-    dom = domain(gpu_lib, nx, nz, ny, dx=st["dx"])
+    from lw_expected import expected_winds
+    st = ideal.make_ideal_case(nx=40, nz=7, ny=24, perturb=True)
+    dom = domain(gpu_lib, 40, 7, 24, dx=st["dx"])
     dom.upload_state(st)
-    terrain = np.ascontiguousarray(st["terrain"].T)        # [i, j]
-    buffer = 7
+    buffer, U, V, Nsq, frac, contrib = 7, 10.0, 4.0, 1e-4, 0.2, 0.7
     dom.linear_winds_init(st["terrain"], buffer=buffer)
-    tf, total = LW.terrain_frequency(terrain, buffer)
-    lt = LW.LinearTheoryData(tf.shape[0], tf.shape[1], st["dx"])
-    U, V, Nsq, frac, contrib = 10.0, 4.0, 1e-4, np.float32(0.2), np.float32(0.7)
-    f = np.float32
-    zi = np.empty_like(st["dz_interface"])                  # (ny, nz, nx): z_interface = terrain + sum of the layers below
-    zi[:, 0, :] = st["terrain"]
-    for k in range(1, nz):
-        zi[:, k, :] = zi[:, k - 1, :] + st["dz_interface"][:, k - 1, :]
-    lh = (np.cumsum(st["dz_levels"], dtype=f) - st["dz_levels"] / f(2)).astype(f)
-    u, v = st["u"].copy(), st["v"].copy()
-    up, vp = np.zeros_like(u), np.zeros_like(v)
+    u, v, lh, zi = expected_winds(st, buffer, U, V, Nsq, frac, contrib, varying, calls=2)
     for call in range(2):                                   # the second call exercises the (1 - fraction) memory
         if varying:
             dom.linear_perturb(U, V, Nsq, global_z_interface=zi, global_dz_interface=st["dz_interface"],
-                               linear_contribution=float(contrib), linear_update_fraction=float(frac))
+                               linear_contribution=contrib, linear_update_fraction=frac)
         else:
             dom.linear_perturb(U, V, Nsq, layer_height=lh, dz_levels=st["dz_levels"],
-                               linear_contribution=float(contrib), linear_update_fraction=float(frac))
-        for k in range(nz):
-            if varying:
-                zb = (zi[:, k, :] - st["terrain"]).T
-                zt = (zi[:, k, :] - st["terrain"] + st["dz_interface"][:, k, :]).T
-                pert = LW.linear_perturbation_varyingz(U, V, Nsq, zb, zt, 100.0, tf, lt, total)
-            else:
-                half = st["dz_levels"][k] / f(2)
-                pert = LW.linear_perturbation_constz(U, V, Nsq, lh[k] - half, lh[k] + half, 100.0, tf, lt)
-            tu, tv = stagger(pert, total, nx, ny)
-            up[:, k, :] = up[:, k, :] * (f(1) - frac) + frac * tu.T
-            vp[:, k, :] = vp[:, k, :] * (f(1) - frac) + frac * tv.T
-            u[:, k, :] += up[:, k, :] * contrib
-            v[:, k, :] += vp[:, k, :] * contrib
+                               linear_contribution=contrib, linear_update_fraction=frac)
     du, dv = dom.download("u") - st["u"], dom.download("v") - st["v"]
     wu, wv = u - st["u"], v - st["v"]
     scale = max(np.abs(wu).max(), np.abs(wv).max())
