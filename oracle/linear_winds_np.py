@@ -1,6 +1,11 @@
 """TEST INFRASTRUCTURE -- NumPy restatement of the core of ICAR's linear-theory wind perturbation
-(Barstad & Gronas 2006, appendix A), the piece a cuFFT implementation will be
-checked against.  PARITY UNPINNED: the reference has no expected values for it and cannot be compiled here.
+(Barstad & Gronas 2006, appendix A), the piece the cuFFT implementation
+(icar_b200/csrc/linear_winds.cu) is checked against.
+PARITY: the Fortran cannot be compiled here and holds no expected values, but the reference ships a Python
+implementation of the same solution in its x-z form, helpers/ideal_linear.py:solve(); it is run in this container
+by tests/golden/make_linear_theory_golden.py and linear_perturbation_at_height reproduces its u_hat to 4.5e-8 of the
+field maximum (tests/test_oracle_linear_winds.py) -- so the per-height solution is PINNED; add_buffer_topo, the two
+shifts of fftshift.f90, the layer means and the 3-D (l /= 0) terms have no counterpart there and remain unpinned.
 
 Follows, function by function:
     src/utilities/fftshift.f90:87-109, 217-239      fftshift2cc / ifftshift2cc (through a SINGLE precision temporary)

@@ -264,3 +264,24 @@ def test_whole_linear_perturb_with_emulated_kernels(emu, varying, tile):
     scale = max(np.abs(wu).max(), np.abs(wv).max())
     assert scale > 1e-3
     assert np.abs(du - wu).max() <= 2e-6 * max(scale, 10.0) and np.abs(dv - wv).max() <= 2e-6 * max(scale, 10.0)
+
+
+def test_kernel_arithmetic_reproduces_the_references_python_solver(host):
+    """lw_math.cuh (what k_lw_spectrum runs per wavenumber) against u_hat of the reference's own Python solver,
+    helpers/ideal_linear.py:solve(), frozen in tests/golden/linear_theory_1d.npz: the x-z case, l = 0."""
+    g = np.load(os.path.join(ROOT, "tests", "golden", "linear_theory_1d.npz"))
+    for n in range(int(g["ncases"])):
+        Fzs, U, Nsq, dx = g[f"Fzs_{n}"], float(g[f"U_{n}"]), float(g[f"Ndsq_{n}"]), float(g["dx"])
+        Nx = Fzs.shape[0]
+        kx = np.ascontiguousarray(LW.LinearTheoryData(Nx, 2, dx).k[:, 0])
+        ly = np.zeros(1, np.float32)
+        tf = np.ascontiguousarray(Fzs.astype(np.complex128))
+        for iz, z in enumerate(g["zlevels"]):
+            uh = np.empty(Nx, np.complex128); vh = np.empty(Nx, np.complex128)
+            host.lw_host_spectrum(dptr(tf.view(np.float64)), fptr(kx), fptr(ly), Nx, 1, C.c_float(U), C.c_float(0.0),
+                                  C.c_float(Nsq), C.c_float(z), C.c_float(0.0), 1, dptr(uh.view(np.float64)),
+                                  dptr(vh.view(np.float64)))
+            u = (np.fft.ifft(uh) * Nx).real
+            want = g[f"u_hat_{n}"][iz]
+            assert np.abs(u - want).max() <= 2e-7 * np.abs(want).max(), (n, z)      # measured 4.5e-8
+            assert not vh.any()

@@ -125,3 +125,43 @@ def test_layer_means():
     zt = np.full((57, 9), 800.0, np.float32)
     uv, vv = LW.linear_perturbation_varyingz(*args, zb, zt, 100.0, ft, lt, buffer=4)
     np.testing.assert_allclose(uv, u, rtol=1e-5, atol=1e-9)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Pinned against the reference itself: tests/golden/linear_theory_1d.npz holds u_hat of the reference's own Python
+# implementation of the same solution, helpers/ideal_linear.py:solve(), run in this container by
+# tests/golden/make_linear_theory_golden.py.  It is the x-z form (l = 0) of linear_perturbation_at_height.
+
+def one_dimensional(golden, n):
+    """The case as linear_perturbation_at_height sees it: an (Nx, 1) plane with l = 0."""
+    f = np.float32
+    Fzs, U, Nsq, dx = golden[f"Fzs_{n}"], float(golden[f"U_{n}"]), float(golden[f"Ndsq_{n}"]), float(golden["dx"])
+    Nx = Fzs.shape[0]
+    lt = LW.LinearTheoryData.__new__(LW.LinearTheoryData)
+    k1 = LW.LinearTheoryData(Nx, 2, dx).k[:, :1]                     # the Fortran's REAL k grid (:447-451)
+    np.testing.assert_allclose(k1[:, 0], np.linspace(-np.pi / dx, np.pi / dx, Nx), rtol=2e-6, atol=1e-10)   # == solve()'s k
+    lt.k, lt.l = k1, np.zeros((Nx, 1), f)
+    lt.kl = (k1 ** 2).astype(f)
+    lt.kl[lt.kl == 0] = LW.SMALL_VALUE
+    lt.nx, lt.ny = Nx, 1
+    return lt, Fzs[:, None].astype(np.complex128), U, Nsq
+
+
+@pytest.fixture(scope="module")
+def golden_1d():
+    import os
+    return np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "linear_theory_1d.npz"))
+
+
+def test_restatement_reproduces_the_references_python_solver(golden_1d):
+    g = golden_1d
+    for n in range(int(g["ncases"])):
+        lt, ft, U, Nsq = one_dimensional(g, n)
+        for iz, z in enumerate(g["zlevels"]):
+            u, v = LW.linear_perturbation_at_height(U, 0.0, Nsq, z, ft, lt)
+            want = g[f"u_hat_{n}"][iz]
+            scale = np.abs(want).max()
+            assert scale > 0
+            # REAL k, sig and the single-precision temporary of ifftshift against float64 throughout in solve()
+            assert np.abs(u[:, 0].real - want).max() <= 2e-7 * scale, (n, z)        # measured 4.5e-8
+            assert not v.any()                                         # l = 0: no v'
