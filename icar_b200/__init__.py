@@ -112,6 +112,24 @@ class MpOptions(C.Structure):
             setattr(self, k, v)
 
 
+class LtOptions(C.Structure):
+    """lt_parameters as spatial_winds reads them (options_obj.f90:1401-1530); defaults :1448-1479."""
+    _fields_ = [("variable_N", C.c_int), ("smooth_nsq", C.c_int), ("vert_smooth", C.c_int), ("stability_window_size", C.c_int),
+                ("max_stability", C.c_float), ("min_stability", C.c_float), ("N_squared", C.c_float),
+                ("linear_contribution", C.c_float), ("linear_update_fraction", C.c_float),
+                ("dirmax", C.c_float), ("dirmin", C.c_float), ("spdmax", C.c_float), ("spdmin", C.c_float),
+                ("n_dir_values", C.c_int), ("n_nsq_values", C.c_int), ("n_spd_values", C.c_int),
+                ("minimum_layer_size", C.c_float)]
+
+    def __init__(self, **kw):
+        super().__init__()
+        lib().icar_default_lt_options(C.byref(self))
+        for k, v in kw.items():
+            if k not in dict(self._fields_):
+                raise TypeError(f"unknown lt option {k}")
+            setattr(self, k, v)
+
+
 # lookup tables in the allocation order of thompson_init (mp_thompson.f90:353-390) + Fortran shapes
 THOMPSON_TABLES = (
     "tcg_racg", "tmr_racg", "tcr_gacr", "tmg_gacr", "tnr_racg", "tnr_gacr",
@@ -152,7 +170,8 @@ SYMBOLS = (
     "icar_profile_enable", "icar_profile_read", "icar_diagnostic_update", "icar_compute_dt", "icar_enforce_limits",
     "icar_upload_tendency", "icar_apply_forcing", "icar_balance_uvw",
     "icar_add_buffer_topo", "icar_linear_winds_init", "icar_linear_winds_dims", "icar_linear_winds_terrain_frequency",
-    "icar_linear_perturbation", "icar_linear_perturb", "icar_restart_info", "icar_write_restart", "icar_read_restart")
+    "icar_linear_perturbation", "icar_linear_perturb", "icar_default_lt_options", "icar_linear_winds_set_z",
+    "icar_linear_perturb_spatial", "icar_restart_info", "icar_write_restart", "icar_read_restart")
 
 
 def lib() -> C.CDLL:
@@ -368,6 +387,27 @@ class Domain:
         self._check(lib().icar_linear_perturb(self._h, C.c_float(U), C.c_float(V), C.c_float(Nsq), _ptr(zi), _ptr(dzi),
                                               _ptr(lh), _ptr(dz), C.c_float(minimum_layer_size),
                                               C.c_float(linear_contribution), C.c_float(linear_update_fraction)))
+
+    def linear_winds_set_z(self, z):
+        """domain%z%data_3d of the tile, (ny, nz, nx): calc_stability reads it when variable_N."""
+        g = self.grid
+        self._check(lib().icar_linear_winds_set_z(self._h, _ptr(_f32(z, (g.ny, g.nz, g.nx), "z"))))
+
+    def linear_perturb_spatial(self, options=None, global_z_interface=None, global_dz_interface=None, layer_height=None,
+                               dz_levels=None):
+        """spatial_winds (linear_winds.f90:840-1127) with the reference's table semantics, the entries evaluated on
+        demand.  Returns the number of (entry, level) evaluations."""
+        g = self.grid
+        zi = dzi = lh = dz = None
+        if global_z_interface is not None:
+            shape = (g.jde - g.jds + 1, g.nz, g.ide - g.ids + 1)
+            zi, dzi = _f32(global_z_interface, shape, "global_z_interface"), _f32(global_dz_interface, shape, "global_dz_interface")
+        else:
+            lh, dz = _f32(layer_height, (g.nz,), "layer_height"), _f32(dz_levels, (g.nz,), "dz_levels")
+        opt = options or LtOptions()
+        n = C.c_longlong()
+        self._check(lib().icar_linear_perturb_spatial(self._h, C.byref(opt), _ptr(zi), _ptr(dzi), _ptr(lh), _ptr(dz), C.byref(n)))
+        return n.value
 
     # -- restart / output files (src/io/output_obj.f90 save_file, src/io/restart.f90:11-90)
     def write_restart(self, path):

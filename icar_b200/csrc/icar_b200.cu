@@ -1805,6 +1805,56 @@ extern "C" int icar_linear_perturb(icar_ctx* ctx, float U, float V, float Nsq, c
     return ICAR_OK;
 }
 
+extern "C" void icar_default_lt_options(icar_lt_options* o) {
+    if (!o) return;
+    // options_obj.f90:1448-1479
+    o->variable_N = 1; o->smooth_nsq = 1; o->vert_smooth = 10; o->stability_window_size = 10;
+    o->max_stability = 6e-4f; o->min_stability = 1e-7f; o->N_squared = 3e-5f;
+    o->linear_contribution = 1.f; o->linear_update_fraction = 0.2f;
+    o->dirmax = 2.f * 3.1415927f; o->dirmin = 0.f; o->spdmax = 30.f; o->spdmin = 0.f;
+    o->n_dir_values = 24; o->n_nsq_values = 5; o->n_spd_values = 6;
+    o->minimum_layer_size = 100.f;
+}
+
+extern "C" int icar_linear_winds_set_z(icar_ctx* ctx, const float* z) {
+    if (!ctx || !ctx->lw) return fail(ctx, ICAR_ERR_INVALID, "icar_linear_winds_set_z: call icar_linear_winds_init first");
+    CU(cudaSetDevice(ctx->device));
+    std::string err;
+    const int rc = lw_set_z(ctx->lw, ctx->g, z, &err);
+    if (rc) return fail(ctx, rc == 1 ? ICAR_ERR_INVALID : ICAR_ERR_CUDA, "icar_linear_winds_set_z: " + err);
+    return ICAR_OK;
+}
+
+extern "C" int icar_linear_perturb_spatial(icar_ctx* ctx, const icar_lt_options* opt, const float* global_z_interface,
+                                           const float* global_dz_interface, const float* layer_height,
+                                           const float* dz_levels, long long* entries_computed) {
+    if (!ctx || !ctx->lw) return fail(ctx, ICAR_ERR_INVALID, "icar_linear_perturb_spatial: call icar_linear_winds_init first");
+    CU(cudaSetDevice(ctx->device));
+    int rc = need_uploaded(ctx, {ICAR_VAR_U, ICAR_VAR_V, ICAR_VAR_POTENTIAL_TEMPERATURE, ICAR_VAR_EXNER, ICAR_VAR_WATER_VAPOR},
+                           "icar_linear_perturb_spatial");
+    if (rc) return rc;
+    { int jr = join_aux(ctx); if (jr) return jr; }
+    icar_lt_options d;
+    icar_default_lt_options(&d);
+    if (opt) d = *opt;
+    static_assert(sizeof(icar_lt_options) == sizeof(LtOptions), "icar_lt_options and LtOptions must match");
+    LtOptions o;
+    std::memcpy(&o, &d, sizeof(o));
+    auto have = [&](int v) -> const float* { return ctx->uploaded[v] ? (const float*)ctx->vars[v] : nullptr; };
+    // hydrometeors = cloud water + cloud ice + rain + snow, whichever are associated (:905-913)
+    LtFields f{(const float*)ctx->vars[ICAR_VAR_POTENTIAL_TEMPERATURE], (const float*)ctx->vars[ICAR_VAR_EXNER],
+               (const float*)ctx->vars[ICAR_VAR_WATER_VAPOR], have(ICAR_VAR_CLOUD_WATER),
+               ctx->opt.microphysics == 1 ? have(ICAR_VAR_CLOUD_ICE) : nullptr, have(ICAR_VAR_RAIN_IN_AIR),
+               have(ICAR_VAR_SNOW_IN_AIR)};
+    const icar_grid& gr = ctx->grid;
+    std::string err;
+    rc = lw_spatial_winds(ctx->lw, ctx->g, gr.ims - gr.ids, gr.jms - gr.jds, f, o, (float*)ctx->vars[ICAR_VAR_U],
+                          (float*)ctx->vars[ICAR_VAR_V], global_z_interface, global_dz_interface, layer_height, dz_levels,
+                          entries_computed, &ctx->launches, &err);
+    if (rc) return fail(ctx, rc == 1 ? ICAR_ERR_INVALID : rc == 3 ? ICAR_ERR_PHYSICS : ICAR_ERR_CUDA, "icar_linear_perturb_spatial: " + err);
+    return ICAR_OK;
+}
+
 // ------------------------------------------------------------------ restart / output files ("next" rank 4)
 //
 // One self-describing little-endian file per image (the reference writes one NetCDF file per image as well,

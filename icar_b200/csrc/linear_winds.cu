@@ -77,6 +77,13 @@ struct LinWinds {
     size_t upert_elems = 0, vpert_elems = 0;
     bool have_perturbation = false;
     std::vector<float> terrain;    // domain%global_terrain, kept for the layer bounds of linear_perturb
+    // spatial_winds
+    float *z = nullptr, *nsq = nullptr, *u1d = nullptr, *v1d = nullptr, *planes_u = nullptr, *planes_v = nullptr;
+    double* rowmeans = nullptr;
+    unsigned* bitmap = nullptr;
+    int* slot_of = nullptr;
+    size_t cell_elems = 0;
+    int plane_slots = 0;
 };
 
 #define LWCU(call)                                                               \
@@ -166,7 +173,8 @@ void lw_destroy(LinWinds* lw) {
     if (!lw) return;
     if (lw->have_plan && g_cufft.Destroy) g_cufft.Destroy(lw->plan);
     void* bufs[] = {lw->tf, lw->uhat, lw->vhat, lw->up, lw->vp, lw->ua, lw->va, lw->kx, lw->ly, lw->ibot, lw->itop,
-                    lw->count, lw->zb, lw->zt, lw->upert, lw->vpert};
+                    lw->count, lw->zb, lw->zt, lw->upert, lw->vpert, lw->z, lw->nsq, lw->u1d, lw->v1d, lw->planes_u,
+                    lw->planes_v, lw->rowmeans, lw->bitmap, lw->slot_of};
     for (void* p : bufs) if (p) cudaFree(p);
     delete lw;
 }
@@ -333,6 +341,8 @@ int lw_perturbation_varyingz(LinWinds* lw, float U, float V, float Nsq, const fl
     return 0;
 }
 
+int ensure_perturbation_state(LinWinds* lw, const Geom& g, std::string* err);
+
 int lw_apply_level(LinWinds* lw, const Geom& g, int i0, int j0, int k, float* u3d, float* v3d,
                    float linear_contribution, float update_fraction, long long* launches, std::string* err) {
     if (!lw->have_perturbation) { *err = "linear winds: no perturbation has been computed yet"; return 1; }
@@ -340,6 +350,18 @@ int lw_apply_level(LinWinds* lw, const Geom& g, int i0, int j0, int k, float* u3
         *err = "linear winds: the tile does not lie inside the terrain given to icar_linear_winds_init";
         return 1;
     }
+    if (int rc = ensure_perturbation_state(lw, g, err)) return rc;
+    k_lw_apply_u<<<grid2d(g.nx + 1, g.ny), kThreads, 0, lw->st>>>(lw->up, lw->fnx, lw->buffer, g.nx, g.nz, g.ldu, i0, j0, k, u3d, lw->upert,
+                                                                  linear_contribution, update_fraction);
+    k_lw_apply_v<<<grid2d(g.nx, g.ny + 1), kThreads, 0, lw->st>>>(lw->vp, lw->fnx, lw->buffer, g.nx, g.nz, g.ld, i0, j0, k, v3d, lw->vpert,
+                                                                  linear_contribution, update_fraction);
+    LWCU(cudaGetLastError());
+    if (launches) *launches += 2;
+    return 0;
+}
+
+// hi_u_perturbation / hi_v_perturbation of the tile, zero on first use (:1262-1268)
+int ensure_perturbation_state(LinWinds* lw, const Geom& g, std::string* err) {
     const size_t ue = (size_t)g.ldu * g.nz * g.ny, ve = (size_t)g.ld * g.nz * (g.ny + 1);
     if (!lw->upert || lw->upert_elems != ue || lw->vpert_elems != ve) {
         if (lw->upert) cudaFree(lw->upert);
@@ -352,12 +374,159 @@ int lw_apply_level(LinWinds* lw, const Geom& g, int i0, int j0, int k, float* u3
         lw->upert_elems = ue;
         lw->vpert_elems = ve;
     }
-    k_lw_apply_u<<<grid2d(g.nx + 1, g.ny), kThreads, 0, lw->st>>>(lw->up, lw->fnx, lw->buffer, g.nx, g.nz, g.ldu, i0, j0, k, u3d, lw->upert,
-                                                                  linear_contribution, update_fraction);
-    k_lw_apply_v<<<grid2d(g.nx, g.ny + 1), kThreads, 0, lw->st>>>(lw->vp, lw->fnx, lw->buffer, g.nx, g.nz, g.ld, i0, j0, k, v3d, lw->vpert,
-                                                                  linear_contribution, update_fraction);
+    return 0;
+}
+
+int lw_set_z(LinWinds* lw, const Geom& g, const float* z_host, std::string* err) {
+    if (!z_host) { *err = "linear winds: z missing"; return 1; }
+    const size_t elems = (size_t)g.ld * g.nz * g.ny;
+    if (!lw->z || lw->cell_elems != elems) {
+        if (lw->z) cudaFree(lw->z);
+        lw->z = nullptr;
+        LWCU(cudaMalloc((void**)&lw->z, elems * sizeof(float)));
+        LWCU(cudaMemsetAsync(lw->z, 0, elems * sizeof(float), lw->st));
+    }
+    LWCU(cudaMemcpy2DAsync(lw->z, (size_t)g.ld * sizeof(float), z_host, (size_t)g.nx * sizeof(float),
+                           (size_t)g.nx * sizeof(float), (size_t)g.nz * g.ny, cudaMemcpyHostToDevice, lw->st));
+    LWCU(cudaStreamSynchronize(lw->st));
+    lw->cell_elems = elems;
+    return 0;
+}
+
+// linear_space (array_utilities.f90:233-235): (i - 1.0) / real(n - 1.0) * (max - min) + min
+static void linear_space(float* out, float lo, float hi, int n) {
+    for (int i = 0; i < n; ++i) {
+        const float t = (float)i / (float)(n - 1);
+        const float s = t * (hi - lo);
+        out[i] = s + lo;
+    }
+}
+
+int lw_spatial_winds(LinWinds* lw, const Geom& g, int i0, int j0, const LtFields& f, const LtOptions& o, float* u3d,
+                     float* v3d, const float* global_z_interface, const float* global_dz_interface,
+                     const float* layer_height, const float* dz_levels, long long* entries_computed,
+                     long long* launches, std::string* err) {
+    const bool varying = global_z_interface != nullptr;
+    if (varying ? !global_dz_interface : !(layer_height && dz_levels)) { *err = "linear winds: layer bounds missing"; return 1; }
+    if (i0 < 0 || j0 < 0 || i0 + g.nx > lw->nx || j0 + g.ny > lw->ny) { *err = "linear winds: the tile does not lie inside the terrain"; return 1; }
+    if (o.n_dir_values < 2 || o.n_dir_values > 64 || o.n_nsq_values < 2 || o.n_nsq_values > 32 || o.n_spd_values < 2 || o.n_spd_values > 32) {
+        *err = "linear winds: table sizes must be 2..64 directions, 2..32 speeds and stabilities";
+        return 1;
+    }
+    if (o.smooth_nsq && (g.nx <= o.stability_window_size)) {
+        *err = "linear winds: stability_window_size must be smaller than the tile (smooth_array reads rowmeans(2:windowsize))";
+        return 1;
+    }
+    if (o.variable_N && (!lw->z || lw->cell_elems != (size_t)g.ld * g.nz * g.ny)) { *err = "linear winds: variable_N needs domain%z (icar_linear_winds_set_z)"; return 1; }
+    if (int rc = ensure_perturbation_state(lw, g, err)) return rc;
+
+    LutAxes ax{};
+    ax.n_dir = o.n_dir_values; ax.n_nsq = o.n_nsq_values; ax.n_spd = o.n_spd_values;
+    linear_space(ax.dir, o.dirmin, o.dirmax, ax.n_dir);                       // :657-661
+    linear_space(ax.nsq, logf(o.min_stability), logf(o.max_stability), ax.n_nsq);   // nsqmin / nsqmax, options_obj.f90:1472-1473
+    linear_space(ax.spd, o.spdmin, o.spdmax, ax.n_spd);
+    SpatialOpts so{o.variable_N, o.smooth_nsq, o.vert_smooth, o.stability_window_size, o.min_stability, o.max_stability,
+                   o.N_squared, o.linear_contribution, o.linear_update_fraction};
+    const int n_entries = ax.n_dir * ax.n_nsq * ax.n_spd, words = (n_entries + 31) / 32;
+    const size_t cells = (size_t)g.ld * g.nz * g.ny, nx1 = (size_t)g.nx + 1;
+    if (!lw->nsq) {
+        LWCU(cudaMalloc((void**)&lw->nsq, cells * sizeof(float)));
+        LWCU(cudaMalloc((void**)&lw->rowmeans, cells * sizeof(double)));
+        LWCU(cudaMalloc((void**)&lw->u1d, nx1 * (g.ny + 1) * sizeof(float)));
+        LWCU(cudaMalloc((void**)&lw->v1d, nx1 * (g.ny + 1) * sizeof(float)));
+        LWCU(cudaMalloc((void**)&lw->bitmap, 2048 * sizeof(unsigned)));       // 64 x 32 x 32 entries at most
+        LWCU(cudaMalloc((void**)&lw->slot_of, 2048 * 32 * sizeof(int)));
+        LWCU(cudaMemsetAsync(lw->nsq, 0, cells * sizeof(float), lw->st));
+    }
+    long long mine = 0, evaluated = 0;
+
+    // log N^2, vertical running mean, horizontal box mean (:898-959)
+    CellFields cf{f.th, f.pii, lw->z, f.qv, f.qc, f.qi, f.qr, f.qs};
+    k_lw_nsq_column<<<grid2d(g.nx, g.ny), kThreads, 0, lw->st>>>(g.nx, g.nz, g.ld, cf, so, lw->nsq);
+    ++mine;
+    if (o.smooth_nsq) {
+        const dim3 grid((g.nx + kThreads - 1) / kThreads, g.nz, g.ny);
+        k_lw_smooth_y<<<grid, kThreads, 0, lw->st>>>(lw->nsq, lw->rowmeans, g.nx, g.nz, g.ny, g.ld, o.stability_window_size);
+        k_lw_smooth_x<<<grid, kThreads, 0, lw->st>>>(lw->rowmeans, lw->nsq, g.nx, g.nz, g.ny, g.ld, o.stability_window_size);
+        mine += 2;
+    }
     LWCU(cudaGetLastError());
-    if (launches) *launches += 2;
+
+    const size_t stride_u = (size_t)(lw->nx + 1) * lw->ny, stride_v = (size_t)lw->nx * (lw->ny + 1);
+    std::vector<float> zb, zt;
+    if (varying) { zb.resize((size_t)lw->nx * lw->ny); zt.resize(zb.size()); }
+    std::vector<unsigned> bits(words);
+    std::vector<int> slot_of(n_entries);
+
+    // rows 0 .. ny-1 carry u and v; row ny (the extra v row) is looked up with the column means of the UPDATED u of
+    // row ny-1, because the reference walks the rows in order (:961-973 inside `do k = 1, nyv`)
+    for (int phase = 0; phase < 2; ++phase) {
+        const int row0 = phase == 0 ? 0 : g.ny, nrows = phase == 0 ? g.ny : 1;
+        k_lw_colmean<<<grid2d(g.nx + 1, nrows), kThreads, 0, lw->st>>>(u3d, v3d, g.nx, g.nz, g.ny, g.ld, g.ldu, row0, lw->u1d, lw->v1d);
+        ++mine;
+        for (int j = 0; j < g.nz; ++j) {
+            LWCU(cudaMemsetAsync(lw->bitmap, 0, words * sizeof(unsigned), lw->st));
+            k_lw_mark_entries<<<grid2d(g.nx + 1, nrows), kThreads, 0, lw->st>>>(ax, lw->u1d, lw->v1d, lw->nsq, g.nx, g.nz, g.ny, g.ld, j,
+                                                                              o.stability_window_size, row0, lw->bitmap);
+            ++mine;
+            LWCU(cudaGetLastError());
+            LWCU(cudaMemcpyAsync(bits.data(), lw->bitmap, words * sizeof(unsigned), cudaMemcpyDeviceToHost, lw->st));
+            LWCU(cudaStreamSynchronize(lw->st));
+            int used = 0;
+            for (int e = 0; e < n_entries; ++e) slot_of[e] = ((bits[e >> 5] >> (e & 31)) & 1u) ? used++ : 0;
+            if (used > lw->plane_slots) {
+                if (lw->planes_u) cudaFree(lw->planes_u);
+                if (lw->planes_v) cudaFree(lw->planes_v);
+                lw->planes_u = lw->planes_v = nullptr;
+                lw->plane_slots = 0;
+                LWCU(cudaMalloc((void**)&lw->planes_u, (size_t)used * stride_u * sizeof(float)));
+                LWCU(cudaMalloc((void**)&lw->planes_v, (size_t)used * stride_v * sizeof(float)));
+                lw->plane_slots = used;
+            }
+            if (varying)       // z_interface(:, z, :) - terrain and ... + dz_interface(:, z, :)   (:723-726)
+                for (int y = 0; y < lw->ny; ++y)
+                    for (int x = 0; x < lw->nx; ++x) {
+                        const size_t c3 = (size_t)x + (size_t)lw->nx * ((size_t)j + (size_t)g.nz * (size_t)y);
+                        const float b = global_z_interface[c3] - lw->terrain[(size_t)y * lw->nx + x];
+                        zb[(size_t)y * lw->nx + x] = b;
+                        zt[(size_t)y * lw->nx + x] = b + global_dz_interface[c3];
+                    }
+            for (int e = 0; e < n_entries; ++e) {
+                if (!((bits[e >> 5] >> (e & 31)) & 1u)) continue;
+                const int in = e % ax.n_nsq, is = (e / ax.n_nsq) % ax.n_spd, id = e / (ax.n_nsq * ax.n_spd);
+                const float U = sinf(ax.dir[id]) * ax.spd[is];           // calc_u / calc_v (atm_utilities.f90:373-391)
+                const float V = cosf(ax.dir[id]) * ax.spd[is];
+                const float N2 = expf(ax.nsq[in]);                       // :712
+                int rc;
+                if (varying) {
+                    rc = lw_perturbation_varyingz(lw, U, V, N2, zb.data(), zt.data(), o.minimum_layer_size, &mine, err);
+                } else {
+                    const float half = dz_levels[j] / 2.0f;              // :730-732
+                    rc = lw_perturbation_constz(lw, U, V, N2, layer_height[j] - half, layer_height[j] + half,
+                                                o.minimum_layer_size, &mine, err);
+                }
+                if (rc) return rc;
+                k_lw_stagger<<<grid2d(lw->nx + 1, lw->ny + 1), kThreads, 0, lw->st>>>(
+                    lw->up, lw->vp, lw->fnx, lw->buffer, lw->nx, lw->ny, lw->planes_u + (size_t)slot_of[e] * stride_u,
+                    lw->planes_v + (size_t)slot_of[e] * stride_v);
+                ++mine;
+                ++evaluated;
+            }
+            LWCU(cudaMemcpyAsync(lw->slot_of, slot_of.data(), n_entries * sizeof(int), cudaMemcpyHostToDevice, lw->st));
+            if (phase == 0)
+                k_lw_interp<<<grid2d(g.nx + 1, g.ny), kThreads, 0, lw->st>>>(ax, so, lw->u1d, lw->v1d, lw->nsq, g.nx, g.nz, g.ny, g.ld, g.ldu,
+                                                                           j, 0, 0, lw->slot_of, lw->planes_u, stride_u, lw->nx, i0, j0,
+                                                                           u3d, lw->upert);
+            k_lw_interp<<<grid2d(g.nx, nrows), kThreads, 0, lw->st>>>(ax, so, lw->u1d, lw->v1d, lw->nsq, g.nx, g.nz, g.ny, g.ld, g.ld, j,
+                                                                     row0, 1, lw->slot_of, lw->planes_v, stride_v, lw->nx, i0, j0, v3d,
+                                                                     lw->vpert);
+            mine += phase == 0 ? 2 : 1;
+            LWCU(cudaGetLastError());
+            LWCU(cudaStreamSynchronize(lw->st));                         // slot_of (host) is rewritten for the next level
+        }
+    }
+    if (launches) *launches += mine;
+    if (entries_computed) *entries_computed = evaluated;
     return 0;
 }
 

@@ -48,4 +48,30 @@ int lw_download_perturbation(LinWinds* lw, double* u, double* v, std::string* er
 int lw_apply_level(LinWinds* lw, const Geom& g, int i0, int j0, int k, float* u3d, float* v3d,
                    float linear_contribution, float update_fraction, long long* launches, std::string* err);
 
+
+// lt_parameters as spatial_winds reads them (include/icar_b200.h: icar_lt_options has the same members)
+struct LtOptions {
+    int variable_N, smooth_nsq, vert_smooth, stability_window_size;
+    float max_stability, min_stability, N_squared, linear_contribution, linear_update_fraction;
+    float dirmax, dirmin, spdmax, spdmin;
+    int n_dir_values, n_nsq_values, n_spd_values;
+    float minimum_layer_size;
+};
+struct LtFields {          // resident fields of the tile (device, cell layout); hydrometeors may be null
+    const float *th, *pii, *qv, *qc, *qi, *qr, *qs;
+};
+
+// domain%z%data_3d of the tile (host, (nx, nz, ny) dense): read by calc_stability; kept on the device
+int lw_set_z(LinWinds* lw, const Geom& g, const float* z_host, std::string* err);
+
+// spatial_winds (:840-1127), reverse = .False.: stability field and its smoothing, column-mean background wind, table
+// positions, the table entries the tile needs (each computed when first needed, level by level, with the routines
+// the reference's table builder calls, :700-762), trilinear interpolation, relaxation, update of u3d / v3d.
+// Layer bounds: global_z_interface + global_dz_interface (space_varying_dz, host, (gnx, nz, gny)) or layer_height +
+// dz_levels (host, nz).  entries_computed (optional) receives the number of (entry, level) perturbations evaluated.
+int lw_spatial_winds(LinWinds* lw, const Geom& g, int i0, int j0, const LtFields& f, const LtOptions& o, float* u3d,
+                     float* v3d, const float* global_z_interface, const float* global_dz_interface,
+                     const float* layer_height, const float* dz_levels, long long* entries_computed,
+                     long long* launches, std::string* err);
+
 }  // namespace icar

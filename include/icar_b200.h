@@ -255,6 +255,39 @@ int icar_linear_perturb(icar_ctx* ctx, float U, float V, float Nsq, const float*
                         const float* global_dz_interface, const float* layer_height, const float* dz_levels,
                         float minimum_layer_size, float linear_contribution, float linear_update_fraction);
 
+/* lt_parameters as spatial_winds reads them (options_obj.f90:1401-1530); defaults: icar_default_lt_options(). */
+typedef struct icar_lt_options {
+    int variable_N;               /* N^2 from the state (calc_stability) instead of N_squared, default 1          */
+    int smooth_nsq;               /* vertical running mean + smooth_array of log N^2, default 1                     */
+    int vert_smooth;              /* vsmooth, default 10                                                            */
+    int stability_window_size;    /* winsz, default 10                                                              */
+    float max_stability, min_stability;   /* 6e-4, 1e-7                                                             */
+    float N_squared;              /* 3e-5 (used when variable_N = 0)                                                */
+    float linear_contribution, linear_update_fraction;   /* 1, 0.2                                                  */
+    float dirmax, dirmin, spdmax, spdmin; /* table axes: 2 pi, 0, 30, 0 (the N^2 axis spans log(min..max_stability)) */
+    int n_dir_values, n_nsq_values, n_spd_values;        /* 24, 5, 6                                                */
+    float minimum_layer_size;     /* 100                                                                            */
+} icar_lt_options;
+void icar_default_lt_options(icar_lt_options* opt);
+
+/* domain%z%data_3d of this image's tile (host, (ims:ime, kms:kme, jms:jme)): calc_stability reads it when variable_N. */
+int icar_linear_winds_set_z(icar_ctx* ctx, const float* z);
+
+/* linear_perturb -> spatial_winds(domain, reverse = .False., vsmooth, winsz, update) (linear_winds.f90:840-1127) on
+ * the resident state of the tile, with the reference's own semantics: per-cell log N^2 (calc_stability, or
+ * N_squared), its vertical and horizontal smoothing, the column-mean background wind of every (i, j) column, each
+ * cell's position in the (speed, direction, log N^2) table, trilinear interpolation between the eight entries
+ * around it, relaxation of the stored perturbation and the update of u, v.  What differs is WHEN a table entry is
+ * computed: the reference fills the whole table at start-up (initialize_spatial_winds :596-830; n_spd x n_dir x n_nsq
+ * x nx x nz x ny x 2 REALs, 720 entries by default -- 1.4 TB at 2048 x 2048 x 60); here the entries a level needs
+ * are evaluated when that level is processed (same routines, same values) and dropped afterwards.  A uniform flow
+ * needs 8 of the 720.  Layer bounds as in icar_linear_perturb.  *entries_computed (may be NULL) receives the number
+ * of (entry, level) evaluations.  Reads potential_temperature, exner, water_vapor and whichever of cloud_water,
+ * cloud_ice, rain_in_air, snow_in_air the scheme allocates; follow with icar_balance_uvw. */
+int icar_linear_perturb_spatial(icar_ctx* ctx, const icar_lt_options* opt, const float* global_z_interface,
+                                const float* global_dz_interface, const float* layer_height, const float* dz_levels,
+                                long long* entries_computed);
+
 /* ---- restart / output files ("next" rank 4).  The reference writes one NetCDF file per image (output_t%save_file,
  * src/io/output_obj.f90:41-80, 404-458) and reads it back in restart_model (src/io/restart.f90:11-90); there is no
  * NetCDF library here, so the file is a self-describing little-endian binary (layout: icar_b200/restart.py, which

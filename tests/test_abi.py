@@ -196,6 +196,11 @@ def test_ctypes_structs_match_the_header_member_order():
     assert [n for n, _ in icar_b200.Options._fields_] == c_members("icar_options")
     assert [n for n, _ in icar_b200.MpOptions._fields_] == c_members("icar_mp_options")
     assert [n for n, _ in icar_b200.HostDomain._fields_] == c_members("icar_host_domain")
+    assert [n for n, _ in icar_b200.LtOptions._fields_] == c_members("icar_lt_options")
+    lt = icar_b200.LtOptions()                         # lt_parameters defaults, options_obj.f90:1448-1479
+    assert (lt.variable_N, lt.smooth_nsq, lt.vert_smooth, lt.stability_window_size) == (1, 1, 10, 10)
+    assert (lt.n_dir_values, lt.n_nsq_values, lt.n_spd_values, lt.minimum_layer_size) == (24, 5, 6, 100.0)
+    assert abs(lt.N_squared - 3e-5) < 1e-12 and abs(lt.linear_update_fraction - 0.2) < 1e-7 and abs(lt.dirmax - 2 * 3.1415927) < 1e-6
     enum = dict((k, int(v)) for k, v in re.findall(r"(ICAR_VAR_[A-Z_]+)\s*=\s*(\d+)", hdr))
     for name, idx in icar_b200.VAR.items():
         assert enum["ICAR_VAR_" + name.upper()] == idx, name

@@ -137,3 +137,31 @@ def test_full_size_plane_against_the_restatement(gpu_lib):
     assert np.abs(ur - ur[:, :1]).max() <= 1e-6 * np.abs(ur).max()
     inner = ur[total + 200:total + n - 200, total + 200:total + n - 200]
     assert 0.9 * np.sqrt(Nsq) * h0 < np.abs(inner).max() < 1.3 * np.sqrt(Nsq) * h0
+
+
+@pytest.mark.parametrize("varying,variable_N", [(False, True), (True, True), (False, False)])
+def test_spatial_winds_matches_the_restatement(gpu_lib, varying, variable_N):
+    """icar_linear_perturb_spatial (the reference's table semantics, entries on demand) against
+    oracle/spatial_winds_np.py: the state, options and bars of tests/test_spatial_winds_host.py, where the same
+    kernels run emulated on the CPU."""
+    from oracle import spatial_winds_np as SW
+    from test_spatial_winds_host import run_oracle, varied_state
+    st = varied_state()
+    o = SW.LTOptions(buffer=7, variable_N=variable_N)
+    want_u, want_v, want_nsq, cache, lh, zi = run_oracle(st, o, None, varying, calls=2)
+    dom = domain(gpu_lib, st["nx"], st["nz"], st["ny"], dx=st["dx"])
+    dom.upload_state(st)
+    dom.linear_winds_init(st["terrain"], buffer=7)
+    dom.linear_winds_set_z(st["z"])
+    opt = gpu_lib.LtOptions(variable_N=int(variable_N))
+    total = 0
+    for _ in range(2):
+        if varying:
+            total += dom.linear_perturb_spatial(opt, global_z_interface=zi, global_dz_interface=st["dz_interface"])
+        else:
+            total += dom.linear_perturb_spatial(opt, layer_height=lh, dz_levels=st["dz_levels"])
+    du, dv = dom.download("u") - st["u"], dom.download("v") - st["v"]
+    wu, wv = want_u - st["u"], want_v - st["v"]
+    assert max(np.abs(wu).max(), np.abs(wv).max()) > 0.05
+    assert np.abs(du - wu).max() <= 2e-5 and np.abs(dv - wv).max() <= 2e-5       # m/s, on winds of ~10 m/s
+    assert 8 * st["nz"] * 2 <= total <= 720 * st["nz"] * 4 * 0.4
