@@ -346,16 +346,26 @@ def run_b200(args, rank, world, local_rank):
             zi[:, k, :] = zi[:, k - 1, :] + st["dz_interface"][:, k - 1, :]
         dom.linear_winds_init(st["terrain"], buffer=50)     # lt_parameters default (options_obj.f90:1452)
         dom.synchronize()
+        entries = None
+        if args.linear_winds == "spatial":
+            dom.linear_winds_set_z(local["z"])
         dom.timer_start()
-        dom.linear_perturb(10.0, 5.0, 3e-5, global_z_interface=zi, global_dz_interface=st["dz_interface"],
-                           linear_update_fraction=1.0)
+        if args.linear_winds == "spatial":                  # the reference's per-cell table semantics, entries on demand
+            entries = dom.linear_perturb_spatial(icar_b200.LtOptions(linear_update_fraction=1.0), global_z_interface=zi,
+                                                 global_dz_interface=st["dz_interface"])
+        else:                                               # one background state, evaluated directly
+            dom.linear_perturb(10.0, 5.0, 3e-5, global_z_interface=zi, global_dz_interface=st["dz_interface"],
+                               linear_update_fraction=1.0)
         dom.balance_uvw()
         lw_ms = max_over_ranks(dom.timer_stop())
         dt = float(dom.compute_dt(st["dz_levels"]))          # the winds changed: update_dt (time_step.f90:375-423)
         fnx, fny, _ = dom.linear_winds_dims()
         linear_winds = {"ms": lw_ms, "fft_grid": [fnx, fny], "levels": nz, "dt_s_after": dt,
-                        "api": "icar_linear_perturb (space_varying_dz, N^2 = 3e-5, direct evaluation, cuFFT Z2Z) + icar_balance_uvw; "
-                               "once per forcing interval, not inside the timed steps"}
+                        "table_entries_evaluated": entries,
+                        "api": ("icar_linear_perturb_spatial (spatial_winds: variable N, table look-up per cell, entries on demand)"
+                                if args.linear_winds == "spatial" else
+                                "icar_linear_perturb (space_varying_dz, N^2 = 3e-5, direct evaluation)") +
+                               ", cuFFT Z2Z, + icar_balance_uvw; once per forcing interval, not inside the timed steps"}
 
     # ---------------- device-resident timing
     for _ in range(max(args.warmup, 3)):
@@ -539,7 +549,7 @@ def main():
                          "(diagnostic_update), as step()'s loop does before the physics")
     ap.add_argument("--e2e-bands", type=int, default=1,
                     help="e2e pipelined over this many bands of rows (icar_b200/pipeline.py); 1 = the plain host step")
-    ap.add_argument("--linear-winds", action="store_true",
+    ap.add_argument("--linear-winds", nargs="?", const="direct", default=None, choices=["direct", "spatial"],
                     help="before the steps, run the once-per-forcing-interval wind update (icar_linear_perturb + "
                          "icar_balance_uvw) and report its time under `linear_winds` (not yet run on hardware)")
     ap.add_argument("--graph", action="store_true",

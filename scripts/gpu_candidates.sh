@@ -30,6 +30,7 @@ run e2e_bands4 -- --e2e-bands 4
 run e2e_bands8 -- --e2e-bands 8
 run e2e_bands8_derive -- --e2e-bands 8 --derive-diagnostics
 run linear_winds -- --linear-winds                 # look at linear_winds.ms in gpurun_out/cand_linear_winds.json
+run linear_winds_spatial -- --linear-winds spatial
 run nz50_default -- --nz 50
 run nz50_two_stages ICAR_FUSED_NZP52=1 -- --nz 50
 run nz50_packed ICAR_CORR_V2=1 -- --nz 50
