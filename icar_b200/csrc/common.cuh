@@ -1,6 +1,10 @@
 // Shared device helpers for the icar_b200 kernels (sm_100a).
 #pragma once
+#if defined(__CUDACC__)
 #include <cuda_runtime.h>
+#else
+#include "host_emu.h"   // host-only test harnesses (tests/cpp/)
+#endif
 #include <cstddef>
 #include <cstdint>
 

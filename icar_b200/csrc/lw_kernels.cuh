@@ -8,14 +8,8 @@
 
 #include "lw_math.cuh"
 
-#if !defined(__CUDACC__)                         // host emulation (tests only)
-struct double2 { double x, y; };
-inline double2 make_double2(double x, double y) { return {x, y}; }
-struct lw_emu_idx { unsigned x, y, z; };
-extern thread_local lw_emu_idx blockIdx, threadIdx;
-inline unsigned atomicOr(unsigned* p, unsigned v) { const unsigned old = *p; *p = old | v; return old; }
-#define __global__
-#define __launch_bounds__(n)
+#if !defined(__CUDACC__)
+#include "host_emu.h"   // host emulation (tests only)
 #endif
 
 namespace icar {
