@@ -37,6 +37,9 @@ __device__ __forceinline__ f2 rcp2(f2 a) {
 }
 __device__ __forceinline__ f2 div2(f2 a, f2 b) { return a * rcp2(b); }
 
+#else
+inline f2 rcp2(f2 a) { return f2{1.0f / a.x, 1.0f / a.y}; }      // rcp.approx is within 1 ulp of this
+inline f2 div2(f2 a, f2 b) { return a * rcp2(b); }
 #endif
 
 }  // namespace icar

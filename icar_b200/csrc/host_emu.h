@@ -15,7 +15,7 @@ inline float4 make_float4(float x, float y, float z, float w) { return {x, y, z,
 struct double2 { double x, y; };
 inline double2 make_double2(double x, double y) { return {x, y}; }
 struct icar_emu_idx { unsigned x, y, z; };
-extern thread_local icar_emu_idx blockIdx, threadIdx;
+extern thread_local icar_emu_idx blockIdx, threadIdx, blockDim;
 inline unsigned atomicOr(unsigned* p, unsigned v) { const unsigned old = *p; *p = old | v; return old; }
 inline float __frcp_rn(float x) { return 1.0f / x; }           // correctly rounded reciprocal == IEEE 1/x
 typedef void* cudaStream_t;

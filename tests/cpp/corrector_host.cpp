@@ -1,0 +1,174 @@
+// TEST INFRASTRUCTURE.  Runs the kernels of the fused MPDATA path (icar_b200/csrc/corrector_fused.inc:
+// k_face_coefficients(_v4), k_corrector_fused, k_corrector_fused_p2, k_corrector_fused_pk) on the CPU.
+//
+// A CTA is emulated with ONE OS THREAD PER CUDA THREAD: __syncthreads is a pthread barrier over the CTA, a warp
+// shuffle is an exchange through a per-warp buffer between two barriers over the warp, an mbarrier is a phase
+// counter + outstanding byte count in the shared-memory word the kernel gave it, and a TMA box load is a copy with
+// zero fill outside the field done by the issuing thread (the kernel's waiters spin on the phase like on hardware).
+// Shared memory is one heap block per CTA; CTAs run one after the other.  rcp.approx is 1.0f / x and the f32x2
+// operations are done one IEEE half at a time (f32x2.cuh), so results agree with the device to the tolerance of
+// the "fast" mode, not bit for bit.  Built with -ffp-contract=off -pthread.
+#include <pthread.h>
+#include <sched.h>
+
+#include <algorithm>
+#include <atomic>
+#include <cstdlib>
+#include <cstring>
+#include <thread>
+#include <vector>
+
+#include "../../icar_b200/csrc/common.cuh"
+#include "../../icar_b200/csrc/f32x2.cuh"
+#include "../../icar_b200/csrc/mpdata.cuh"
+
+thread_local icar_emu_idx blockIdx, threadIdx, blockDim;
+
+// ---- what the kernels need from the "hardware"
+struct CUtensorMap { const float* base; int nx, nz, ny, ld; };     // the kernels only pass its address on
+static unsigned char* icar_emu_smem = nullptr;
+static pthread_barrier_t cta_barrier;
+static std::vector<pthread_barrier_t> warp_barrier;
+static std::vector<float> warp_buffer;                              // [warp][32]
+
+static inline void __syncthreads() { pthread_barrier_wait(&cta_barrier); }
+static inline float icar_emu_shfl(float v, int delta) {            // delta = -1: value of lane - 1 (shfl.up), +1: lane + 1
+    const int tid = threadIdx.y * 32 + threadIdx.x, w = tid / 32, lane = tid % 32;
+    warp_buffer[w * 32 + lane] = v;
+    pthread_barrier_wait(&warp_barrier[w]);
+    const int src = lane + delta;
+    const float r = (src < 0 || src > 31) ? v : warp_buffer[w * 32 + src];
+    pthread_barrier_wait(&warp_barrier[w]);
+    return r;
+}
+struct EmuMbar { std::atomic<uint32_t> phase; std::atomic<int32_t> pending; };
+static_assert(sizeof(EmuMbar) == sizeof(uint64_t), "an mbarrier is one 64-bit shared-memory word");
+static inline void icar_emu_mbar_init(uint64_t* b) { auto* m = reinterpret_cast<EmuMbar*>(b); m->phase.store(0); m->pending.store(0); }
+static inline void icar_emu_mbar_expect(uint64_t* b, uint32_t bytes) { reinterpret_cast<EmuMbar*>(b)->pending.fetch_add((int32_t)bytes); }
+static inline bool icar_emu_mbar_try_wait(uint64_t* b, uint32_t parity) {
+    const bool ok = (reinterpret_cast<EmuMbar*>(b)->phase.load(std::memory_order_acquire) & 1u) != parity;
+    if (!ok) sched_yield();
+    return ok;
+}
+static inline void icar_emu_tma_load_box(void* dst, const CUtensorMap* m, uint64_t* bar, int x, int z, int y) {
+    float* d = static_cast<float*>(dst);
+    for (int zz = 0; zz < m->nz; ++zz)
+        for (int xx = 0; xx < 32; ++xx) {
+            const int gi = x + xx, gk = z + zz;
+            const bool in = gi >= 0 && gi < m->nx && gk >= 0 && gk < m->nz && y >= 0 && y < m->ny;
+            d[zz * 32 + xx] = in ? m->base[(size_t)gi + (size_t)m->ld * ((size_t)gk + (size_t)m->nz * (size_t)y)] : 0.f;
+        }
+    auto* mb = reinterpret_cast<EmuMbar*>(bar);
+    const int32_t bytes = m->nz * 32 * (int32_t)sizeof(float);
+    if (mb->pending.fetch_sub(bytes) - bytes == 0) mb->phase.fetch_add(1, std::memory_order_release);
+}
+using std::max;
+using std::min;
+#define __grid_constant__
+#define ICAR_DYNAMIC_SMEM(name) unsigned char* name = icar_emu_smem
+
+namespace icar {
+namespace {
+#include "../../icar_b200/csrc/corrector_fused.inc"
+
+// one CTA of `threads` = 32 x nzt CUDA threads
+template <class Kernel>
+void run_cta(unsigned bx, unsigned by, int nzt, size_t smem_bytes, Kernel kernel) {
+    const int threads = 32 * nzt;
+    std::vector<unsigned char> smem(smem_bytes + 128, 0xA5);          // shared memory starts uninitialised
+    icar_emu_smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem.data()) + 127) & ~uintptr_t(127));
+    pthread_barrier_init(&cta_barrier, nullptr, threads);
+    warp_barrier.assign(nzt, pthread_barrier_t{});
+    for (auto& b : warp_barrier) pthread_barrier_init(&b, nullptr, 32);
+    warp_buffer.assign((size_t)nzt * 32, 0.f);
+    std::vector<std::thread> pool;
+    pool.reserve(threads);
+    for (int t = 0; t < threads; ++t)
+        pool.emplace_back([=] {
+            blockIdx = {bx, by, 0};
+            threadIdx = {(unsigned)(t % 32), (unsigned)(t / 32), 0};
+            blockDim = {32, (unsigned)nzt, 1};
+            kernel();
+        });
+    for (auto& th : pool) th.join();
+    for (auto& b : warp_barrier) pthread_barrier_destroy(&b);
+    pthread_barrier_destroy(&cta_barrier);
+}
+
+template <class Kernel>
+void run_grid(unsigned gx, unsigned gy, int nzt, size_t smem, Kernel kernel) {
+    for (unsigned by = 0; by < gy; ++by)
+        for (unsigned bx = 0; bx < gx; ++bx) run_cta(bx, by, nzt, smem, kernel);
+}
+
+}  // namespace
+}  // namespace icar
+
+using namespace icar;
+
+extern "C" {
+
+// k_face_coefficients_v4 (v4 != 0; grid ((ld/4+127)/128, nz, ny) x 128) or k_face_coefficients (grid of 32 x 4 x 4 blocks)
+void emu_face_coefficients(int v4, int nx, int nz, int ny, int ld, const float* U, const float* V, const float* Wn,
+                           const float* G, const float* dz, float* const* coef11) {
+    Geom g{nx, nz, ny, ld, ld};
+    FusedCoef co{coef11[0], coef11[1], coef11[2], coef11[3], coef11[4], coef11[5], coef11[6], coef11[7], coef11[8], coef11[9], coef11[10]};
+    if (v4) {
+        blockDim = {128, 1, 1};
+        for (unsigned j = 0; j < (unsigned)ny; ++j)
+            for (unsigned k = 0; k < (unsigned)nz; ++k)
+                for (unsigned bx = 0; bx < (unsigned)((ld / 4 + 127) / 128); ++bx)
+                    for (unsigned t = 0; t < 128; ++t) { blockIdx = {bx, k, j}; threadIdx = {t, 0, 0}; k_face_coefficients_v4(g, U, V, Wn, G, dz, co); }
+        return;
+    }
+    blockDim = {32, 4, 4};
+    for (unsigned bz = 0; bz < (unsigned)((ny + 3) / 4); ++bz)
+        for (unsigned by = 0; by < (unsigned)((nz + 3) / 4); ++by)
+            for (unsigned bx = 0; bx < (unsigned)((nx + 31) / 32); ++bx)
+                for (unsigned tz = 0; tz < 4; ++tz)
+                    for (unsigned ty = 0; ty < 4; ++ty)
+                        for (unsigned tx = 0; tx < 32; ++tx) {
+                            blockIdx = {bx, by, bz}; threadIdx = {tx, ty, tz};
+                            k_face_coefficients(g, U, V, Wn, G, dz, co);
+                        }
+}
+
+// the corrector as fused_advect_all launches it: grid (xtiles * n, chunks), block (32, nzp / cpt), dynamic shared memory
+// of fused_plan.  kind 0: k_corrector_fused<cpt, nzp, stages>; 1: k_corrector_fused_p2<nzp>; 2: k_corrector_fused_pk<cpt / 2, nzp, stages>
+int emu_corrector(int kind, int cpt, int nzp, int stages, int nx, int nz, int ny, int ld, int n, const float* const* q2,
+                  const float* const* l, float* const* out, const float* const* coef11, int chunk) {
+    Geom g{nx, nz, ny, ld, ld};
+    FusedMaps maps{};
+    OutSet outs{};
+    outs.n = n;
+    for (int s = 0; s < n; ++s) {
+        outs.out[s] = out[s];
+        maps.q2[s] = CUtensorMap{q2[s], nx, nz, ny, ld};
+        maps.l[s] = CUtensorMap{l[s], nx, nz, ny, ld};
+    }
+    // coef11 is in FusedCoef's member order (ax bx cx ay by cy az bz cz rj rjz); the maps are in stage order
+    // (ay by cy ax bx cx az bz cz rj rjz), as fused_advect_all builds them
+    const int order[11] = {3, 4, 5, 0, 1, 2, 6, 7, 8, 9, 10};
+    for (int f = 0; f < 11; ++f) maps.coef[f] = CUtensorMap{coef11[order[f]], nx, nz, ny, ld};
+    const int nzt = nzp / cpt;
+    const size_t smem = (size_t)(2 * 10 * (nzt + 2) * TW + stages * NF * nzp * TW) * sizeof(float) + 16;
+    const int xtiles = nx / TOUT + 1, planes = ny - 2;
+    const unsigned gx = (unsigned)(xtiles * n), gy = (unsigned)((planes + chunk - 1) / chunk);
+#define CASE(K, C, Z, S, CALL) if (kind == K && cpt == C && nzp == Z && stages == S) { run_grid(gx, gy, nzt, smem, [&] { CALL; }); return 0; }
+    CASE(0, 2, 20, 2, (k_corrector_fused<2, 20, 2>(g, outs, maps, chunk)))
+    CASE(0, 2, 40, 2, (k_corrector_fused<2, 40, 2>(g, outs, maps, chunk)))
+    CASE(0, 4, 48, 2, (k_corrector_fused<4, 48, 2>(g, outs, maps, chunk)))
+    CASE(0, 4, 52, 2, (k_corrector_fused<4, 52, 2>(g, outs, maps, chunk)))
+    CASE(0, 4, 64, 1, (k_corrector_fused<4, 64, 1>(g, outs, maps, chunk)))
+    CASE(1, 2, 20, 2, (k_corrector_fused_p2<20>(g, outs, maps, chunk)))
+    CASE(1, 2, 40, 2, (k_corrector_fused_p2<40>(g, outs, maps, chunk)))
+    CASE(2, 2, 20, 2, (k_corrector_fused_pk<1, 20, 2>(g, outs, maps, chunk)))
+    CASE(2, 2, 40, 2, (k_corrector_fused_pk<1, 40, 2>(g, outs, maps, chunk)))
+    CASE(2, 4, 48, 2, (k_corrector_fused_pk<2, 48, 2>(g, outs, maps, chunk)))
+    CASE(2, 4, 52, 2, (k_corrector_fused_pk<2, 52, 2>(g, outs, maps, chunk)))
+    CASE(2, 4, 64, 1, (k_corrector_fused_pk<2, 64, 1>(g, outs, maps, chunk)))
+#undef CASE
+    return 1;
+}
+
+}

@@ -3,7 +3,7 @@
 // thread.  tests/test_linear_winds_host.py puts NumPy transforms where the product calls cuFFT.
 #include "../../icar_b200/csrc/lw_kernels.cuh"
 
-thread_local icar_emu_idx blockIdx, threadIdx;
+thread_local icar_emu_idx blockIdx, threadIdx, blockDim;
 
 using namespace icar::lwk;
 

@@ -4,7 +4,7 @@
 // operation rounds as the packed instruction's half does.
 #include "../../icar_b200/csrc/upwind_p2.cuh"
 
-thread_local icar_emu_idx blockIdx, threadIdx;
+thread_local icar_emu_idx blockIdx, threadIdx, blockDim;
 
 using namespace icar;
 
