@@ -107,6 +107,7 @@ FusedPlan fused_plan(const Geom& g) {
     FusedPlan p{};
     if (g.nz < 2 || g.nz > 64 || g.nx < 3 || g.ny < 3) return p;
     p.stages = 2;
+    p.rowbufs = 2;
     if (g.nz <= 20) { p.cpt = 2; p.nzp = 20; }
     else if (g.nz <= 40) { p.cpt = 2; p.nzp = 40; }
     else if (g.nz <= 48) { p.cpt = 4; p.nzp = 48; }
@@ -115,8 +116,14 @@ FusedPlan fused_plan(const Geom& g) {
     // opt-in until it has run on hardware: 49..52 levels (BASELINE configs[3] has 50) still fit TWO stages
     // (2 x 13 x 52 x 128 B + rows = 211 KB), so the TMA loads stay one plane ahead instead of being exposed
     if (env_int("ICAR_FUSED_NZP52", 0) == 1 && g.nz > 48 && g.nz <= 52) { p.cpt = 4; p.nzp = 52; p.stages = 2; }
+    // opt-in, not yet run on hardware (emulated on the CPU, tests/test_corrector_host.py): 53..60 levels (BASELINE
+    // configs[4] has 60) with TWO stages and ONE set of exchange rows, packed kernel only (needs ICAR_CORR_V2=1):
+    // 2 x 13 x 60 x 128 B + 10 x 17 x 128 B = 221 KB
+    if (env_int("ICAR_FUSED_NZP60", 0) == 1 && env_int("ICAR_CORR_V2", 0) == 1 && g.nz > 52 && g.nz <= 60) {
+        p.cpt = 4; p.nzp = 60; p.stages = 2; p.rowbufs = 1;
+    }
     const int nzt = p.nzp / p.cpt;
-    p.smem = (size_t)(2 * 10 * (nzt + 2) * TW + p.stages * NF * p.nzp * TW) * sizeof(float) + 16;
+    p.smem = (size_t)(p.rowbufs * 10 * (nzt + 2) * TW + p.stages * NF * p.nzp * TW) * sizeof(float) + 16;
     int dev = 0, max_optin = 0;
     if (cudaGetDevice(&dev) != cudaSuccess ||
         cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess) {
@@ -194,9 +201,9 @@ int fused_advect_all(const Geom& g, const ScalarSet& s, const float* U, const fl
     }
     // candidate form of the packed kernel, opt-in until it has been validated on hardware
     const bool v2 = env_int("ICAR_CORR_V2", 0) == 1;
-#define LAUNCH_PK(NPAIRS, Z, S)                                                                               \
+#define LAUNCH_PK(NPAIRS, Z, S, ...)                                                                          \
     {                                                                                                         \
-        auto kern = k_corrector_fused_pk<NPAIRS, Z, S>;                                                       \
+        auto kern = k_corrector_fused_pk<NPAIRS, Z, S, ##__VA_ARGS__>;                                                     \
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem) !=        \
             cudaSuccess) { (void)cudaGetLastError(); return -1; }                                             \
         kern<<<grid, block, plan.smem, st>>>(g, outs, maps, chunk);                                           \
@@ -205,6 +212,7 @@ int fused_advect_all(const Geom& g, const ScalarSet& s, const float* U, const fl
     else if (v2 && plan.cpt == 2 && plan.nzp == 40) LAUNCH_PK(1, 40, 2)
     else if (v2 && plan.nzp == 48) LAUNCH_PK(2, 48, 2)
     else if (v2 && plan.nzp == 52) LAUNCH_PK(2, 52, 2)
+    else if (v2 && plan.nzp == 60 && plan.rowbufs == 1) LAUNCH_PK(2, 60, 2, 1)
     else if (v2 && plan.nzp == 64) LAUNCH_PK(2, 64, 1)
     else if (packed && plan.nzp == 20) LAUNCH_PACKED(20)
     else if (packed && plan.nzp == 40) LAUNCH_PACKED(40)

@@ -37,3 +37,4 @@ run nz50_packed ICAR_CORR_V2=1 -- --nz 50
 run nz50_packed_two_stages ICAR_CORR_V2=1 ICAR_FUSED_NZP52=1 -- --nz 50
 run nz60_default -- --nz 60
 run nz60_packed ICAR_CORR_V2=1 -- --nz 60
+run nz60_packed_two_stages ICAR_CORR_V2=1 ICAR_FUSED_NZP60=1 -- --nz 60

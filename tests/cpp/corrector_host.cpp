@@ -134,8 +134,8 @@ void emu_face_coefficients(int v4, int nx, int nz, int ny, int ld, const float* 
 }
 
 // the corrector as fused_advect_all launches it: grid (xtiles * n, chunks), block (32, nzp / cpt), dynamic shared memory
-// of fused_plan.  kind 0: k_corrector_fused<cpt, nzp, stages>; 1: k_corrector_fused_p2<nzp>; 2: k_corrector_fused_pk<cpt / 2, nzp, stages>
-int emu_corrector(int kind, int cpt, int nzp, int stages, int nx, int nz, int ny, int ld, int n, const float* const* q2,
+// of fused_plan (rowbufs sets of exchange rows).  kind 0: k_corrector_fused<cpt, nzp, stages>; 1: k_corrector_fused_p2<nzp>; 2: k_corrector_fused_pk<cpt / 2, nzp, stages>
+int emu_corrector(int kind, int cpt, int nzp, int stages, int rowbufs, int nx, int nz, int ny, int ld, int n, const float* const* q2,
                   const float* const* l, float* const* out, const float* const* coef11, int chunk) {
     Geom g{nx, nz, ny, ld, ld};
     FusedMaps maps{};
@@ -151,10 +151,11 @@ int emu_corrector(int kind, int cpt, int nzp, int stages, int nx, int nz, int ny
     const int order[11] = {3, 4, 5, 0, 1, 2, 6, 7, 8, 9, 10};
     for (int f = 0; f < 11; ++f) maps.coef[f] = CUtensorMap{coef11[order[f]], nx, nz, ny, ld};
     const int nzt = nzp / cpt;
-    const size_t smem = (size_t)(2 * 10 * (nzt + 2) * TW + stages * NF * nzp * TW) * sizeof(float) + 16;
+    const size_t smem = (size_t)(rowbufs * 10 * (nzt + 2) * TW + stages * NF * nzp * TW) * sizeof(float) + 16;
+    if (smem > 232448) return 2;                                      // 227 KB of shared memory per CTA
     const int xtiles = nx / TOUT + 1, planes = ny - 2;
     const unsigned gx = (unsigned)(xtiles * n), gy = (unsigned)((planes + chunk - 1) / chunk);
-#define CASE(K, C, Z, S, CALL) if (kind == K && cpt == C && nzp == Z && stages == S) { run_grid(gx, gy, nzt, smem, [&] { CALL; }); return 0; }
+#define CASE(K, C, Z, S, CALL) if (rowbufs == 2 && kind == K && cpt == C && nzp == Z && stages == S) { run_grid(gx, gy, nzt, smem, [&] { CALL; }); return 0; }
     CASE(0, 2, 20, 2, (k_corrector_fused<2, 20, 2>(g, outs, maps, chunk)))
     CASE(0, 2, 40, 2, (k_corrector_fused<2, 40, 2>(g, outs, maps, chunk)))
     CASE(0, 4, 48, 2, (k_corrector_fused<4, 48, 2>(g, outs, maps, chunk)))
@@ -167,6 +168,10 @@ int emu_corrector(int kind, int cpt, int nzp, int stages, int nx, int nz, int ny
     CASE(2, 4, 48, 2, (k_corrector_fused_pk<2, 48, 2>(g, outs, maps, chunk)))
     CASE(2, 4, 52, 2, (k_corrector_fused_pk<2, 52, 2>(g, outs, maps, chunk)))
     CASE(2, 4, 64, 1, (k_corrector_fused_pk<2, 64, 1>(g, outs, maps, chunk)))
+    if (rowbufs == 1 && kind == 2 && cpt == 4 && nzp == 60 && stages == 2) {
+        run_grid(gx, gy, nzt, smem, [&] { k_corrector_fused_pk<2, 60, 2, 1>(g, outs, maps, chunk); });
+        return 0;
+    }
 #undef CASE
     return 1;
 }

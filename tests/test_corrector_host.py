@@ -57,7 +57,7 @@ def case(nx, nz, ny):
     return st
 
 
-def emulated_advect(emu, oracle, st, dt, kind, cpt, nzp, stages, chunk=None, v4=1, names=("th", "qv", "qc", "qr", "qs")):
+def emulated_advect(emu, oracle, st, dt, kind, cpt, nzp, stages, chunk=None, v4=1, names=("th", "qv", "qc", "qr", "qs"), rowbufs=2):
     """fused_advect_all: face coefficients (emulated kernel), pass 1 (the oracle's: bit-identical to the device's),
     corrector (emulated kernel).  Returns {name: field after one advect call}."""
     nx, nz, ny = st["nx"], st["nz"], st["ny"]
@@ -76,16 +76,16 @@ def emulated_advect(emu, oracle, st, dt, kind, cpt, nzp, stages, chunk=None, v4=
     out = [image(st[k], ld, rows_y=ny + 1) for k in names]               # staged_upwind_all copies the ring into `out`
     for o, k in zip(out, names):
         o[1:ny - 1, :, 1:nx - 1] = f(-7e7)                                 # the interior must come from the corrector
-    rc = emu.emu_corrector(kind, cpt, nzp, stages, nx, nz, ny, ld, len(names), P(q2), P(q), P(out), P(coef), chunk or (ny - 2))
+    rc = emu.emu_corrector(kind, cpt, nzp, stages, rowbufs, nx, nz, ny, ld, len(names), P(q2), P(q), P(out), P(coef), chunk or (ny - 2))
     assert rc == 0, "no such instantiation"
     return {k: o[:ny, :, :nx] for k, o in zip(names, out)}
 
 
-def check(emu, oracle, dims, kind, cpt, nzp, stages, chunk=None, v4=1):
+def check(emu, oracle, dims, kind, cpt, nzp, stages, chunk=None, v4=1, rowbufs=2):
     nx, nz, ny = dims
     st = case(nx, nz, ny)
     dt = float(st["dt"]) * 0.8
-    got = emulated_advect(emu, oracle, st, dt, kind, cpt, nzp, stages, chunk, v4)
+    got = emulated_advect(emu, oracle, st, dt, kind, cpt, nzp, stages, chunk, v4, rowbufs=rowbufs)
     U, V, W = oracle.wind_normalise(st["u"], st["v"], st["w"], st["jacobian_u"], st["jacobian_v"], st["jacobian_w"], None, f(dt), st["dx"])
     bar = RTOL_FUSED * max(1.0, float(1.0 / st["jacobian"].min()))
     worst = 0.0
@@ -129,3 +129,23 @@ def test_packed_forms_agree_bit_for_bit_and_y_chunks_do_not_matter(emu, oracle):
         assert np.array_equal(a[k], b[k]), k
         assert np.array_equal(a[k], c[k]), k
         assert np.array_equal(a[k], d[k]), k
+
+
+@pytest.mark.parametrize("dims,chunk", [((33, 60, 7), None), ((30, 55, 8), 3)])
+def test_two_stage_candidate_for_53_to_60_levels(emu, oracle, dims, chunk):
+    """ICAR_FUSED_NZP60=1 + ICAR_CORR_V2=1: k_corrector_fused_pk<2, 60, 2, ROWBUFS = 1> -- BASELINE configs[4] has 60
+    levels.  One set of exchange rows makes room for the second TMA stage (221 KB); the warm-up planes take one extra
+    barrier.  The OS threads of the emulation really race, so a missing barrier shows up as a wrong or varying
+    result: the kernel is run twice and must give the same bits, which must be those of the single-stage kernel."""
+    a, worst = check(emu, oracle, dims, 2, 4, 60, 2, chunk=chunk, rowbufs=1)
+    b, _ = check(emu, oracle, dims, 2, 4, 60, 2, chunk=chunk, rowbufs=1) if chunk else (a, 0)
+    c, _ = check(emu, oracle, dims, 2, 4, 64, 1, chunk=chunk)
+    for k in a:
+        assert np.array_equal(a[k], b[k]), k
+        assert np.array_equal(a[k], c[k]), k
+
+
+def test_more_shared_memory_than_a_cta_has_is_refused(emu, oracle):
+    st = case(30, 64, 6)
+    with pytest.raises(AssertionError, match="no such instantiation"):
+        emulated_advect(emu, oracle, st, float(st["dt"]) * 0.8, 2, 4, 64, 2)          # two stages of 64 levels: 236 KB
