@@ -17,6 +17,14 @@ inline double2 make_double2(double x, double y) { return {x, y}; }
 struct icar_emu_idx { unsigned x, y, z; };
 extern thread_local icar_emu_idx blockIdx, threadIdx, blockDim;
 inline unsigned atomicOr(unsigned* p, unsigned v) { const unsigned old = *p; *p = old | v; return old; }
+inline unsigned long long atomicAdd(unsigned long long* p, unsigned long long v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
+inline int atomicMax(int* p, int v) {
+    int old = __atomic_load_n(p, __ATOMIC_RELAXED);
+    while (old < v && !__atomic_compare_exchange_n(p, &old, v, true, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {}
+    return old;
+}
+inline unsigned __float_as_uint(float x) { unsigned u; __builtin_memcpy(&u, &x, 4); return u; }
+inline float __uint_as_float(unsigned u) { float x; __builtin_memcpy(&x, &u, 4); return x; }
 inline float __frcp_rn(float x) { return 1.0f / x; }           // correctly rounded reciprocal == IEEE 1/x
 typedef void* cudaStream_t;
 typedef void* cudaEvent_t;
@@ -24,4 +32,5 @@ typedef void* cudaEvent_t;
 #define __device__
 #define __host__
 #define __forceinline__ inline
+#define __noinline__ __attribute__((noinline))
 #define __launch_bounds__(...)
