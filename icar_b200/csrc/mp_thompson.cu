@@ -67,7 +67,8 @@ int th_driver_launch(const Geom& g, const ThConst& c, const ThTables& tb, float*
     dim3 block(TX, nkt), grid(gx, gy, tiles.n);
     const size_t smem = (size_t)nk * TX * sizeof(double) + (size_t)7 * (nk + 1) * TX * sizeof(float) + (size_t)10 * TX * sizeof(int);
     const int nthreads = TX * nkt;
-    static const bool math2 = [] { const char* v = std::getenv("ICAR_TH_MATH2"); return v && std::atoi(v) == 1; }();
+    const char* m2 = std::getenv("ICAR_TH_MATH2");           // read at every launch: the tests switch it
+    const bool math2 = m2 && std::atoi(m2) == 1;
     th_math2::Args A2;
     static_assert(sizeof(A2) == sizeof(A), "the two instantiations take the same arguments");
     std::memcpy(&A2, &A, sizeof(A));

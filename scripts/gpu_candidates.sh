@@ -10,6 +10,7 @@ ICAR_TEST_UNVALIDATED=1 timeout 300 python -m pytest tests/test_gpu_parity.py -m
 ICAR_TEST_UNVALIDATED=1 timeout 120 python -m pytest tests/test_gpu_step_loop.py -m gpu -q -k "step_host or host_pipeline" >> gpurun_out/candidates_tests.log 2>&1
 ICAR_TEST_UNVALIDATED=1 timeout 300 python -m pytest tests/test_cpp_host.py tests/test_gpu_step_graph.py -m gpu -q >> gpurun_out/candidates_tests.log 2>&1
 ICAR_TEST_UNVALIDATED=1 timeout 400 python -m pytest tests/test_gpu_linear_winds.py tests/test_gpu_restart.py -m gpu -q >> gpurun_out/candidates_tests.log 2>&1
+ICAR_TEST_UNVALIDATED=1 timeout 400 python -m pytest tests/test_gpu_thompson.py -m gpu -q -k math2 >> gpurun_out/candidates_tests.log 2>&1
 tail -15 gpurun_out/candidates_tests.log
 P='import sys,json; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print(sys.argv[1], "ms/step", round(d["ms_per_step"],4), "e2e ms", round(d["e2e"]["ms_per_step"],2), {k:round(v["ms_per_step"],4) for k,v in d["kernels"].items()})'
 run() {  # name, env assignments..., then -- bench arguments
@@ -31,6 +32,8 @@ run e2e_bands8 -- --e2e-bands 8
 run e2e_bands8_derive -- --e2e-bands 8 --derive-diagnostics
 run linear_winds -- --linear-winds                 # look at linear_winds.ms in gpurun_out/cand_linear_winds.json
 run linear_winds_spatial -- --linear-winds spatial
+run thompson_default -- --mp thompson --steps 20
+run thompson_math2 ICAR_TH_MATH2=1 -- --mp thompson --steps 20
 run nz50_default -- --nz 50
 run nz50_two_stages ICAR_FUSED_NZP52=1 -- --nz 50
 run nz50_packed ICAR_CORR_V2=1 -- --nz 50
