@@ -25,6 +25,10 @@ inline int atomicMax(int* p, int v) {
 }
 inline unsigned __float_as_uint(float x) { unsigned u; __builtin_memcpy(&u, &x, 4); return u; }
 inline float __uint_as_float(unsigned u) { float x; __builtin_memcpy(&x, &u, 4); return x; }
+inline int __float_as_int(float x) { int u; __builtin_memcpy(&u, &x, 4); return u; }
+inline float __int_as_float(int u) { float x; __builtin_memcpy(&x, &u, 4); return x; }
+inline long long __double_as_longlong(double x) { long long u; __builtin_memcpy(&u, &x, 8); return u; }
+inline double __longlong_as_double(long long u) { double x; __builtin_memcpy(&x, &u, 8); return x; }
 inline float __frcp_rn(float x) { return 1.0f / x; }           // correctly rounded reciprocal == IEEE 1/x
 typedef void* cudaStream_t;
 typedef void* cudaEvent_t;
