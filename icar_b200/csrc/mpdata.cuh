@@ -27,6 +27,7 @@ struct FusedPlan {
     bool ok;
     int cpt, nzp, stages;
     int rowbufs;     // sets of z-exchange rows in shared memory: 2, or 1 for the 53..60-level candidate
+    int nsync;       // 1: neighbour-only synchronisation in the plane loop (candidate)
     size_t smem;
 };
 FusedPlan fused_plan(const Geom& g);

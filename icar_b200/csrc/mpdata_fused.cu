@@ -108,6 +108,7 @@ FusedPlan fused_plan(const Geom& g) {
     if (g.nz < 2 || g.nz > 64 || g.nx < 3 || g.ny < 3) return p;
     p.stages = 2;
     p.rowbufs = 2;
+    p.nsync = 0;
     if (g.nz <= 20) { p.cpt = 2; p.nzp = 20; }
     else if (g.nz <= 40) { p.cpt = 2; p.nzp = 40; }
     else if (g.nz <= 48) { p.cpt = 4; p.nzp = 48; }
@@ -123,7 +124,11 @@ FusedPlan fused_plan(const Geom& g) {
         p.cpt = 4; p.nzp = 60; p.stages = 2; p.rowbufs = 1;
     }
     const int nzt = p.nzp / p.cpt;
-    p.smem = (size_t)(p.rowbufs * 10 * (nzt + 2) * TW + p.stages * NF * p.nzp * TW) * sizeof(float) + 16;
+    // opt-in, not yet run on hardware (emulated on the CPU): the packed kernel without CTA-wide barriers in its plane loop
+    // (a warp synchronises with the warps tz - 1 and tz + 1 only), for the two-stage, two-row-set instantiations
+    if (env_int("ICAR_CORR_NSYNC", 0) == 1 && env_int("ICAR_CORR_V2", 0) == 1 && p.stages == 2 && p.rowbufs == 2) p.nsync = 1;
+    p.smem = (size_t)(p.rowbufs * 10 * (nzt + 2) * TW + p.stages * NF * p.nzp * TW) * sizeof(float) + 16 +
+             (p.nsync ? (size_t)(2 + 3 * nzt) * 8 : 0);
     int dev = 0, max_optin = 0;
     if (cudaGetDevice(&dev) != cudaSuccess ||
         cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess) {
@@ -208,7 +213,11 @@ int fused_advect_all(const Geom& g, const ScalarSet& s, const float* U, const fl
             cudaSuccess) { (void)cudaGetLastError(); return -1; }                                             \
         kern<<<grid, block, plan.smem, st>>>(g, outs, maps, chunk);                                           \
     }
-    if (v2 && plan.cpt == 2 && plan.nzp == 20) LAUNCH_PK(1, 20, 2)
+    if (v2 && plan.nsync && plan.cpt == 2 && plan.nzp == 20) LAUNCH_PK(1, 20, 2, 2, 1)
+    else if (v2 && plan.nsync && plan.cpt == 2 && plan.nzp == 40) LAUNCH_PK(1, 40, 2, 2, 1)
+    else if (v2 && plan.nsync && plan.nzp == 48) LAUNCH_PK(2, 48, 2, 2, 1)
+    else if (v2 && plan.nsync && plan.nzp == 52) LAUNCH_PK(2, 52, 2, 2, 1)
+    else if (v2 && plan.cpt == 2 && plan.nzp == 20) LAUNCH_PK(1, 20, 2)
     else if (v2 && plan.cpt == 2 && plan.nzp == 40) LAUNCH_PK(1, 40, 2)
     else if (v2 && plan.nzp == 48) LAUNCH_PK(2, 48, 2)
     else if (v2 && plan.nzp == 52) LAUNCH_PK(2, 52, 2)

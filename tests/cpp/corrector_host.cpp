@@ -41,14 +41,38 @@ static inline float icar_emu_shfl(float v, int delta) {            // delta = -1
     pthread_barrier_wait(&warp_barrier[w]);
     return r;
 }
+// an mbarrier: phase counter + what is still outstanding in the current phase (arrivals and TMA bytes); the arrival
+// count it was initialised with lives beside it (the word itself has no room), written once before the CTA starts
 struct EmuMbar { std::atomic<uint32_t> phase; std::atomic<int32_t> pending; };
 static_assert(sizeof(EmuMbar) == sizeof(uint64_t), "an mbarrier is one 64-bit shared-memory word");
-static inline void icar_emu_mbar_init(uint64_t* b) { auto* m = reinterpret_cast<EmuMbar*>(b); m->phase.store(0); m->pending.store(0); }
-static inline void icar_emu_mbar_expect(uint64_t* b, uint32_t bytes) { reinterpret_cast<EmuMbar*>(b)->pending.fetch_add((int32_t)bytes); }
+static int32_t emu_mbar_count[256];
+static inline int32_t& emu_count_of(uint64_t* b) { return emu_mbar_count[(reinterpret_cast<uintptr_t>(b) >> 3) & 255]; }
+static inline void emu_mbar_complete_one(uint64_t* b, int32_t units) {
+    auto* m = reinterpret_cast<EmuMbar*>(b);
+    if (m->pending.fetch_sub(units) - units == 0) {
+        m->pending.store(emu_count_of(b));
+        m->phase.fetch_add(1, std::memory_order_release);
+    }
+}
+static inline void icar_emu_mbar_init(uint64_t* b, uint32_t count) {
+    auto* m = reinterpret_cast<EmuMbar*>(b);
+    emu_count_of(b) = (int32_t)count;
+    m->phase.store(0);
+    m->pending.store((int32_t)count);
+}
+static inline void icar_emu_mbar_arrive(uint64_t* b) { emu_mbar_complete_one(b, 1); }
+static inline void icar_emu_mbar_expect(uint64_t* b, uint32_t bytes) {      // arrive.expect_tx: one arrival, `bytes` more to come
+    reinterpret_cast<EmuMbar*>(b)->pending.fetch_add((int32_t)bytes - 1);
+}
 static inline bool icar_emu_mbar_try_wait(uint64_t* b, uint32_t parity) {
     const bool ok = (reinterpret_cast<EmuMbar*>(b)->phase.load(std::memory_order_acquire) & 1u) != parity;
     if (!ok) sched_yield();
     return ok;
+}
+static inline void icar_emu_yield() { sched_yield(); }
+static inline void icar_emu_syncwarp() {
+    const int w = (threadIdx.y * 32 + threadIdx.x) / 32;
+    pthread_barrier_wait(&warp_barrier[w]);
 }
 static inline void icar_emu_tma_load_box(void* dst, const CUtensorMap* m, uint64_t* bar, int x, int z, int y) {
     float* d = static_cast<float*>(dst);
@@ -58,9 +82,7 @@ static inline void icar_emu_tma_load_box(void* dst, const CUtensorMap* m, uint64
             const bool in = gi >= 0 && gi < m->nx && gk >= 0 && gk < m->nz && y >= 0 && y < m->ny;
             d[zz * 32 + xx] = in ? m->base[(size_t)gi + (size_t)m->ld * ((size_t)gk + (size_t)m->nz * (size_t)y)] : 0.f;
         }
-    auto* mb = reinterpret_cast<EmuMbar*>(bar);
-    const int32_t bytes = m->nz * 32 * (int32_t)sizeof(float);
-    if (mb->pending.fetch_sub(bytes) - bytes == 0) mb->phase.fetch_add(1, std::memory_order_release);
+    emu_mbar_complete_one(bar, m->nz * 32 * (int32_t)sizeof(float));
 }
 using std::max;
 using std::min;
@@ -135,7 +157,7 @@ void emu_face_coefficients(int v4, int nx, int nz, int ny, int ld, const float* 
 
 // the corrector as fused_advect_all launches it: grid (xtiles * n, chunks), block (32, nzp / cpt), dynamic shared memory
 // of fused_plan (rowbufs sets of exchange rows).  kind 0: k_corrector_fused<cpt, nzp, stages>; 1: k_corrector_fused_p2<nzp>; 2: k_corrector_fused_pk<cpt / 2, nzp, stages>
-int emu_corrector(int kind, int cpt, int nzp, int stages, int rowbufs, int nx, int nz, int ny, int ld, int n, const float* const* q2,
+int emu_corrector(int kind, int cpt, int nzp, int stages, int rowbufs, int nsync, int nx, int nz, int ny, int ld, int n, const float* const* q2,
                   const float* const* l, float* const* out, const float* const* coef11, int chunk) {
     Geom g{nx, nz, ny, ld, ld};
     FusedMaps maps{};
@@ -151,11 +173,12 @@ int emu_corrector(int kind, int cpt, int nzp, int stages, int rowbufs, int nx, i
     const int order[11] = {3, 4, 5, 0, 1, 2, 6, 7, 8, 9, 10};
     for (int f = 0; f < 11; ++f) maps.coef[f] = CUtensorMap{coef11[order[f]], nx, nz, ny, ld};
     const int nzt = nzp / cpt;
-    const size_t smem = (size_t)(rowbufs * 10 * (nzt + 2) * TW + stages * NF * nzp * TW) * sizeof(float) + 16;
+    const size_t smem = (size_t)(rowbufs * 10 * (nzt + 2) * TW + stages * NF * nzp * TW) * sizeof(float) + 16 +
+                        (nsync ? (size_t)(2 + 3 * nzt) * 8 : 0);
     if (smem > 232448) return 2;                                      // 227 KB of shared memory per CTA
     const int xtiles = nx / TOUT + 1, planes = ny - 2;
     const unsigned gx = (unsigned)(xtiles * n), gy = (unsigned)((planes + chunk - 1) / chunk);
-#define CASE(K, C, Z, S, CALL) if (rowbufs == 2 && kind == K && cpt == C && nzp == Z && stages == S) { run_grid(gx, gy, nzt, smem, [&] { CALL; }); return 0; }
+#define CASE(K, C, Z, S, CALL) if (!nsync && rowbufs == 2 && kind == K && cpt == C && nzp == Z && stages == S) { run_grid(gx, gy, nzt, smem, [&] { CALL; }); return 0; }
     CASE(0, 2, 20, 2, (k_corrector_fused<2, 20, 2>(g, outs, maps, chunk)))
     CASE(0, 2, 40, 2, (k_corrector_fused<2, 40, 2>(g, outs, maps, chunk)))
     CASE(0, 4, 48, 2, (k_corrector_fused<4, 48, 2>(g, outs, maps, chunk)))
@@ -168,7 +191,13 @@ int emu_corrector(int kind, int cpt, int nzp, int stages, int rowbufs, int nx, i
     CASE(2, 4, 48, 2, (k_corrector_fused_pk<2, 48, 2>(g, outs, maps, chunk)))
     CASE(2, 4, 52, 2, (k_corrector_fused_pk<2, 52, 2>(g, outs, maps, chunk)))
     CASE(2, 4, 64, 1, (k_corrector_fused_pk<2, 64, 1>(g, outs, maps, chunk)))
-    if (rowbufs == 1 && kind == 2 && cpt == 4 && nzp == 60 && stages == 2) {
+#define NCASE(C, Z, CALL) if (nsync && rowbufs == 2 && kind == 2 && stages == 2 && cpt == C && nzp == Z) { run_grid(gx, gy, nzt, smem, [&] { CALL; }); return 0; }
+    NCASE(2, 20, (k_corrector_fused_pk<1, 20, 2, 2, 1>(g, outs, maps, chunk)))
+    NCASE(2, 40, (k_corrector_fused_pk<1, 40, 2, 2, 1>(g, outs, maps, chunk)))
+    NCASE(4, 48, (k_corrector_fused_pk<2, 48, 2, 2, 1>(g, outs, maps, chunk)))
+    NCASE(4, 52, (k_corrector_fused_pk<2, 52, 2, 2, 1>(g, outs, maps, chunk)))
+#undef NCASE
+    if (!nsync && rowbufs == 1 && kind == 2 && cpt == 4 && nzp == 60 && stages == 2) {
         run_grid(gx, gy, nzt, smem, [&] { k_corrector_fused_pk<2, 60, 2, 1>(g, outs, maps, chunk); });
         return 0;
     }

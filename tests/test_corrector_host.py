@@ -57,7 +57,7 @@ def case(nx, nz, ny):
     return st
 
 
-def emulated_advect(emu, oracle, st, dt, kind, cpt, nzp, stages, chunk=None, v4=1, names=("th", "qv", "qc", "qr", "qs"), rowbufs=2):
+def emulated_advect(emu, oracle, st, dt, kind, cpt, nzp, stages, chunk=None, v4=1, names=("th", "qv", "qc", "qr", "qs"), rowbufs=2, nsync=0):
     """fused_advect_all: face coefficients (emulated kernel), pass 1 (the oracle's: bit-identical to the device's),
     corrector (emulated kernel).  Returns {name: field after one advect call}."""
     nx, nz, ny = st["nx"], st["nz"], st["ny"]
@@ -76,16 +76,16 @@ def emulated_advect(emu, oracle, st, dt, kind, cpt, nzp, stages, chunk=None, v4=
     out = [image(st[k], ld, rows_y=ny + 1) for k in names]               # staged_upwind_all copies the ring into `out`
     for o, k in zip(out, names):
         o[1:ny - 1, :, 1:nx - 1] = f(-7e7)                                 # the interior must come from the corrector
-    rc = emu.emu_corrector(kind, cpt, nzp, stages, rowbufs, nx, nz, ny, ld, len(names), P(q2), P(q), P(out), P(coef), chunk or (ny - 2))
+    rc = emu.emu_corrector(kind, cpt, nzp, stages, rowbufs, nsync, nx, nz, ny, ld, len(names), P(q2), P(q), P(out), P(coef), chunk or (ny - 2))
     assert rc == 0, "no such instantiation"
     return {k: o[:ny, :, :nx] for k, o in zip(names, out)}
 
 
-def check(emu, oracle, dims, kind, cpt, nzp, stages, chunk=None, v4=1, rowbufs=2):
+def check(emu, oracle, dims, kind, cpt, nzp, stages, chunk=None, v4=1, rowbufs=2, nsync=0):
     nx, nz, ny = dims
     st = case(nx, nz, ny)
     dt = float(st["dt"]) * 0.8
-    got = emulated_advect(emu, oracle, st, dt, kind, cpt, nzp, stages, chunk, v4, rowbufs=rowbufs)
+    got = emulated_advect(emu, oracle, st, dt, kind, cpt, nzp, stages, chunk, v4, rowbufs=rowbufs, nsync=nsync)
     U, V, W = oracle.wind_normalise(st["u"], st["v"], st["w"], st["jacobian_u"], st["jacobian_v"], st["jacobian_w"], None, f(dt), st["dx"])
     bar = RTOL_FUSED * max(1.0, float(1.0 / st["jacobian"].min()))
     worst = 0.0
@@ -149,3 +149,20 @@ def test_more_shared_memory_than_a_cta_has_is_refused(emu, oracle):
     st = case(30, 64, 6)
     with pytest.raises(AssertionError, match="no such instantiation"):
         emulated_advect(emu, oracle, st, float(st["dt"]) * 0.8, 2, 4, 64, 2)          # two stages of 64 levels: 236 KB
+
+
+def test_neighbour_only_synchronisation_experiment(emu, oracle):
+    """ICAR_CORR_NSYNC=1 (with ICAR_CORR_V2=1): k_corrector_fused_pk<.., NSYNC = 1> has no CTA-wide barrier in its plane
+    loop -- a warp synchronises with the warps tz - 1 and tz + 1 only, through monotonically increasing flags in shared
+    memory, and a TMA stage is released through an "empty" mbarrier.  The first version used one mbarrier per warp and
+    exchange and DEADLOCKED here (a warp publishes plane P + 1 before it waits, so a neighbour still waiting for plane P
+    sees the parity it started with) -- on the CPU, not on a GPU box.  Same bits as the barrier version, with the OS
+    threads of the emulation really drifting apart.  Statically the variant is 5688 SASS instructions against 3016
+    (warp-level reconvergence around the polls), so it is an experiment to be timed, not a candidate default."""
+    dims = (40, 20, 10)
+    a, _ = check(emu, oracle, dims, 2, 2, 20, 2)
+    b, _ = check(emu, oracle, dims, 2, 2, 20, 2, nsync=1)
+    c, _ = check(emu, oracle, dims, 2, 2, 20, 2, nsync=1, chunk=3)
+    for k in a:
+        assert np.array_equal(a[k], b[k]), k
+        assert np.array_equal(a[k], c[k]), k
