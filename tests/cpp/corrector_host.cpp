@@ -10,6 +10,7 @@
 // the "fast" mode, not bit for bit.  Built with -ffp-contract=off -pthread.
 #include <pthread.h>
 #include <sched.h>
+#include <time.h>
 
 #include <algorithm>
 #include <atomic>
@@ -43,6 +44,9 @@ static inline float icar_emu_shfl(float v, int delta) {            // delta = -1
 }
 // an mbarrier: phase counter + what is still outstanding in the current phase (arrivals and TMA bytes); the arrival
 // count it was initialised with lives beside it (the word itself has no room), written once before the CTA starts
+// a waiter that finds nothing sleeps a little instead of spinning: hundreds of OS threads yielding in a loop spend
+// their time in the scheduler
+static inline void emu_pause() { timespec t{0, 20000}; nanosleep(&t, nullptr); }
 struct EmuMbar { std::atomic<uint32_t> phase; std::atomic<int32_t> pending; };
 static_assert(sizeof(EmuMbar) == sizeof(uint64_t), "an mbarrier is one 64-bit shared-memory word");
 static int32_t emu_mbar_count[256];
@@ -66,10 +70,10 @@ static inline void icar_emu_mbar_expect(uint64_t* b, uint32_t bytes) {      // a
 }
 static inline bool icar_emu_mbar_try_wait(uint64_t* b, uint32_t parity) {
     const bool ok = (reinterpret_cast<EmuMbar*>(b)->phase.load(std::memory_order_acquire) & 1u) != parity;
-    if (!ok) sched_yield();
+    if (!ok) emu_pause();
     return ok;
 }
-static inline void icar_emu_yield() { sched_yield(); }
+static inline void icar_emu_yield() { emu_pause(); }
 static inline void icar_emu_syncwarp() {
     const int w = (threadIdx.y * 32 + threadIdx.x) / 32;
     pthread_barrier_wait(&warp_barrier[w]);

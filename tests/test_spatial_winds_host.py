@@ -185,7 +185,7 @@ def padded(a, pitch, fill=1e30):
 def test_spatial_winds_with_emulated_kernels(emu, varying, tile, variable_N):
     st = varied_state()
     o = SW.LTOptions(buffer=7, variable_N=variable_N)
-    calls = 2
+    calls = 1 if varying else 2            # (terrain-following bounds: many heights per entry; the relaxation memory is exercised by the others)
     want_u, want_v, want_nsq, cache, lh, zi = run_oracle(st, o, None, varying, calls=calls, tile=tile)
     nxg, nyg, nz = st["nx"], st["ny"], st["nz"]
     i0, j0, nx, ny = tile or (0, 0, nxg, nyg)
@@ -211,4 +211,4 @@ def test_spatial_winds_with_emulated_kernels(emu, varying, tile, variable_N):
     assert max(np.abs(wu).max(), np.abs(wv).max()) > 0.05                        # the hill perturbs the flow
     assert np.abs(du - wu).max() <= 2e-5 and np.abs(dv - wv).max() <= 2e-5       # m/s, on winds of ~10 m/s
     # several table entries per level were needed, far fewer than the 720 of the full table
-    assert 8 * nz <= lw.evaluated <= 720 * nz * 2 * 0.4
+    assert 8 * nz <= lw.evaluated <= 720 * nz * 2 * 0.4       # (per call; the counter restarts with every call)
