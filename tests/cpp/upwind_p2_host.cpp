@@ -2,6 +2,7 @@
 // ICAR_UPWIND_PACKED=1 candidate) on the CPU, one loop iteration per thread over the grid staged_upwind_all
 // launches: dim3((ld / 4 + 127) / 128, nz, ny) blocks of 128 threads.  Built with -ffp-contract=off, so every
 // operation rounds as the packed instruction's half does.
+#include "../../icar_b200/csrc/upwind_all.cuh"
 #include "../../icar_b200/csrc/upwind_p2.cuh"
 
 thread_local icar_emu_idx blockIdx, threadIdx, blockDim;
@@ -35,6 +36,40 @@ extern "C" int emu_upwind_all_p2(int nx, int nz, int ny, int ld, int n, const fl
         case 3: run<3>(g, s, U, V, W, dz, jaco); break;
         case 2: run<2>(g, s, U, V, W, dz, jaco); break;
         case 1: run<1>(g, s, U, V, W, dz, jaco); break;
+        default: return 1;
+    }
+    return 0;
+}
+
+// the default pass 1: k_upwind_all_v4<N, true> (grid as above) or, v4 == 0, k_upwind_all<N, markstein> on the cell grid
+// dim3((nx + 127) / 128, nz, ny) of 128-thread blocks
+template <int N>
+static void run_default(const Geom& g, const ScalarSet& s, const float* U, const float* V, const float* W, const float* dz,
+                        const float* jaco, int v4, int markstein) {
+    const unsigned gx = v4 ? (unsigned)((g.ld / 4 + 127) / 128) : (unsigned)((g.nx + 127) / 128);
+    blockDim = {128, 1, 1};
+    for (unsigned j = 0; j < (unsigned)g.ny; ++j)
+        for (unsigned k = 0; k < (unsigned)g.nz; ++k)
+            for (unsigned bx = 0; bx < gx; ++bx)
+                for (unsigned t = 0; t < 128; ++t) {
+                    blockIdx = {bx, k, j};
+                    threadIdx = {t, 0, 0};
+                    if (v4) k_upwind_all_v4<N, true>(g, s, U, V, W, dz, jaco);
+                    else if (markstein) k_upwind_all<N, true>(g, s, U, V, W, dz, jaco);
+                    else k_upwind_all<N, false>(g, s, U, V, W, dz, jaco);
+                }
+}
+
+extern "C" int emu_upwind_all(int nx, int nz, int ny, int ld, int n, const float* const* q, float* const* q2,
+                              float* const* out, const float* U, const float* V, const float* W, const float* dz,
+                              const float* jaco, int v4, int markstein) {
+    Geom g{nx, nz, ny, ld, ld};
+    ScalarSet s{};
+    s.n = n;
+    for (int i = 0; i < n; ++i) { s.q[i] = q[i]; s.q2[i] = q2[i]; s.out[i] = out[i]; }
+    switch (n) {
+        case 5: run_default<5>(g, s, U, V, W, dz, jaco, v4, markstein); break;
+        case 2: run_default<2>(g, s, U, V, W, dz, jaco, v4, markstein); break;
         default: return 1;
     }
     return 0;

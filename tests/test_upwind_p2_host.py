@@ -1,4 +1,8 @@
-"""The packed pass-1 candidate (k_upwind_all_p2, ICAR_UPWIND_PACKED=1: MPDATA's donor-cell pass on f32x2 pairs with
+"""(Also here, since the harness is the same: the pass-1 kernels that HAVE run on hardware -- k_upwind_all_v4, the default,
+and k_upwind_all with and without the shared-reciprocal quotient -- pass the same bit-for-bit check, which validates the
+emulation.)
+
+The packed pass-1 candidate (k_upwind_all_p2, ICAR_UPWIND_PACKED=1: MPDATA's donor-cell pass on f32x2 pairs with
 the donor flux in the Fortran's own form U+ l + U- r) has not run on hardware yet; its kernel body runs here on the
 CPU (tests/cpp/upwind_p2_host.cpp over icar_b200/csrc/upwind_p2.cuh and host_emu.h) against the oracle's pass 1,
 upwind_advection (adv_mpdata.f90:44-105), BIT FOR BIT -- bottom / top levels, a one-level grid, the boundary ring,
@@ -68,12 +72,18 @@ def test_packed_pass1_equals_the_oracle_bit_for_bit(emu, oracle, dims):
     out = [np.full((ny + 1, nz, ld), f(7e7)) for _ in names]
     P = lambda arrs: (C.c_void_p * len(arrs))(*[a.ctypes.data for a in arrs])
     fp = lambda a: a.ctypes.data_as(C.c_void_p)
-    for n in (5, 2):                                                             # the 5-scalar and a shorter instantiation
-        rc = emu.emu_upwind_all_p2(nx, nz, ny, ld, n, P(qin[:n]), P(q2[:n]), P(out[:n]), fp(Ud), fp(Vd), fp(Wd), fp(dz), fp(jaco))
-        assert rc == 0
+    runs = [("p2", n, None) for n in (5, 2)] + [("v4", 5, (1, 1)), ("one cell", 5, (0, 1)), ("one cell, IEEE division", 2, (0, 0))]
+    for what, n, form in runs:        # the candidate (5 scalars and a shorter instantiation), then the kernels that HAVE run on hardware
+        for a in q2 + out:
+            a[...] = f(7e7)
+        if form is None:
+            rc = emu.emu_upwind_all_p2(nx, nz, ny, ld, n, P(qin[:n]), P(q2[:n]), P(out[:n]), fp(Ud), fp(Vd), fp(Wd), fp(dz), fp(jaco))
+        else:
+            rc = emu.emu_upwind_all(nx, nz, ny, ld, n, P(qin[:n]), P(q2[:n]), P(out[:n]), fp(Ud), fp(Vd), fp(Wd), fp(dz), fp(jaco), *form)
+        assert rc == 0, what
         for s in range(n):
             got = q2[s][:ny, :, :nx]
-            assert np.array_equal(got, want[names[s]]), (names[s], np.abs(got - want[names[s]]).max())
+            assert np.array_equal(got, want[names[s]]), (what, names[s], np.abs(got - want[names[s]]).max())
             # the boundary ring also goes to `out` (it is never touched by the corrector)
             ring = np.ones((ny, nz, nx), bool); ring[1:-1, :, 1:-1] = False
             assert np.array_equal(out[s][:ny, :, :nx][ring], st[names[s]][ring])
