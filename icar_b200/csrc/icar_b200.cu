@@ -104,6 +104,7 @@ struct icar_ctx {
     float *qa = nullptr, *qb = nullptr, *u2 = nullptr, *v2 = nullptr, *w2 = nullptr;
     // fused path (mpdata_fused.cu): coefficient fields, per-scalar pass-1 scratch and output buffers
     bool fused = false;
+    bool fused_fast = false;         // TEMPORARY A/B hook: the round-1 "fast arithmetic" corrector
     FusedCoef coef{};
     float* fq2[ICAR_MAX_SCALARS] = {};
     float* fout[ICAR_MAX_SCALARS] = {};
@@ -476,7 +477,8 @@ extern "C" int icar_create(int device, const icar_grid* grid, const icar_options
         if (alloc_cells(ctx, p) != ICAR_OK) return bail(ICAR_ERR_CUDA);
     if (opt->advect_density && alloc_cells(ctx, &ctx->G) != ICAR_OK) return bail(ICAR_ERR_CUDA);
     ctx->fused = (opt->advection == 2 && opt->mpdata_order == 2 && opt->flux_corrected_transport &&
-                  !opt->advect_density && !opt->exact_arithmetic && fused_plan(ctx->g).ok);
+                  !opt->advect_density && !opt->exact_arithmetic && exact_plan(ctx->g).ok);
+    ctx->fused_fast = ctx->fused && std::getenv("ICAR_CORR_FAST") != nullptr && fused_plan(ctx->g).ok;
     if (opt->microphysics == 1) {
         ctx->nadv = 9; std::copy(kAdvectedThompson, kAdvectedThompson + 9, ctx->adv);
         ctx->nexch = 9; std::copy(kExchangedThompson, kExchangedThompson + 9, ctx->exch);
@@ -627,6 +629,26 @@ extern "C" int icar_mp_diagnostics(icar_ctx* ctx, long long out[3]) {
 
 extern "C" long long icar_kernel_launches(const icar_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
+extern "C" int icar_selftest_division(icar_ctx* ctx, const float* a, const float* b, float* packed, float* ieee, long long n) {
+    if (!ctx || !a || !b || !packed || !ieee || n <= 0 || (n & 1)) return ICAR_ERR_INVALID;
+    CU(cudaSetDevice(ctx->device));
+    float* d = nullptr;
+    const size_t bytes = (size_t)n * sizeof(float);
+    CU(cudaMalloc((void**)&d, 4 * bytes));
+    cudaError_t e = cudaMemcpyAsync(d, a, bytes, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d + n, b, bytes, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) {
+        ctx->launches += selftest_division(d, d + n, d + 2 * n, d + 3 * n, n, ctx->stream);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(packed, d + 2 * n, bytes, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(ieee, d + 3 * n, bytes, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(d);
+    CU(e);
+    return ICAR_OK;
+}
+
 extern "C" int icar_timer_start(icar_ctx* ctx) {
     if (!ctx) return ICAR_ERR_INVALID;
     CU(cudaSetDevice(ctx->device));
@@ -689,8 +711,8 @@ int advect_impl(icar_ctx* ctx, float dt, int part) {
         }
         cudaEvent_t marks[4];
         if (ctx->prof_on) for (cudaEvent_t& m : marks) m = prof_event(ctx);
-        const int nl = fused_advect_all(g, ss, ctx->U, ctx->V, ctx->W, ctx->Wn, jaco, dz, ctx->coef, ctx->stream,
-                                        ctx->prof_on ? marks : nullptr, part);
+        const int nl = (ctx->fused_fast ? fused_advect_all : exact_advect_all)(
+            g, ss, ctx->U, ctx->V, ctx->W, ctx->Wn, jaco, dz, ctx->coef, ctx->stream, ctx->prof_on ? marks : nullptr, part);
         if (ctx->prof_on) {      // consecutive marks delimit the three kernels
             if (part == 1) {
                 ctx->prof_pending.push_back({K_FACE_COEF, marks[0], marks[1]});

@@ -43,6 +43,16 @@ int fused_advect_all(const Geom& g, const ScalarSet& s, const float* U, const fl
 // part: 0 = everything; 1 = k_face_coefficients only (depends on the winds, not on the scalars); 2 = pass 1 +
 // corrector only.  A multi-image step queues part 1 before it waits for the halo exchange.
 
+// the same call with the bit-exact corrector (mpdata_exact.cu: the reference's arithmetic operation for operation); `co`
+// lends its buffers to the exact coefficient set
+FusedPlan exact_plan(const Geom& g);
+int exact_advect_all(const Geom& g, const ScalarSet& s, const float* U, const float* V, const float* W,
+                     const float* Wn, const float* jaco, const float* dz, const FusedCoef& co,
+                     cudaStream_t st, cudaEvent_t* marks = nullptr, int part = 0);
+
+// div2x of mpdata_exact.cu (what the corrector divides with) and the compiler's a / b on n device floats (n even)
+int selftest_division(const float* a, const float* b, float* packed, float* ieee, long long n, cudaStream_t st);
+
 // pass 1 (adv_mpdata.f90:44-105) of every scalar in one launch; also copies the boundary ring to out
 int staged_upwind_all(const Geom& g, const ScalarSet& s, const float* U, const float* V, const float* W,
                       const float* dz, const float* jaco, cudaStream_t st);

@@ -321,6 +321,12 @@ int icar_mp_diagnostics(icar_ctx* ctx, long long out[3]);
 /* Number of CUDA kernels this context has launched since creation. */
 long long icar_kernel_launches(const icar_ctx* ctx);
 
+/* Self-test of the division the fused MPDATA corrector uses (csrc/corrector_prims.inc: div2x, the fast path of the
+ * compiler's own div.rn.f32 on f32x2 pairs): packed[i] = div2x(a[i], b[i]) and ieee[i] = a[i] / b[i] for n (even) host
+ * floats.  The reference divides with the Fortran `/` (adv_mpdata.f90:129-251, adv_mpdata_FCT_core.f90:103-114); the
+ * two outputs must be equal bit for bit for normal operands (tests/test_gpu_parity.py). */
+int icar_selftest_division(icar_ctx* ctx, const float* a, const float* b, float* packed, float* ieee, long long n);
+
 /* Device-side stopwatch on the context's compute stream (CUDA events): icar_timer_start queues
  * the start mark, icar_timer_stop queues the stop mark, waits for it and returns the elapsed
  * device time in milliseconds between the two marks.  Replaces timer_t (timer_obj.f90:13-60),

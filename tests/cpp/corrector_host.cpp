@@ -95,7 +95,9 @@ using std::min;
 
 namespace icar {
 namespace {
+#include "../../icar_b200/csrc/corrector_prims.inc"
 #include "../../icar_b200/csrc/corrector_fused.inc"
+#include "../../icar_b200/csrc/corrector_exact.inc"
 
 // one CTA of `threads` = 32 x nzt CUDA threads
 template <class Kernel>
@@ -206,6 +208,53 @@ int emu_corrector(int kind, int cpt, int nzp, int stages, int rowbufs, int nsync
         return 0;
     }
 #undef CASE
+    return 1;
+}
+
+
+// k_face_coefficients_exact (grid ((ld/4+127)/128, nz, ny) x 128); coef10 in ExactCoef's member order
+void emu_face_coefficients_exact(int nx, int nz, int ny, int ld, const float* U, const float* V, const float* Wn,
+                                 const float* G, float* const* coef10) {
+    Geom g{nx, nz, ny, ld, ld};
+    ExactCoef co{coef10[0], coef10[1], coef10[2], coef10[3], coef10[4], coef10[5], coef10[6], coef10[7], coef10[8], coef10[9]};
+    blockDim = {128, 1, 1};
+    for (unsigned j = 0; j < (unsigned)ny; ++j)
+        for (unsigned k = 0; k < (unsigned)nz; ++k)
+            for (unsigned bx = 0; bx < (unsigned)((ld / 4 + 127) / 128); ++bx)
+                for (unsigned t = 0; t < 128; ++t) { blockIdx = {bx, k, j}; threadIdx = {t, 0, 0}; k_face_coefficients_exact(g, U, V, Wn, G, co); }
+}
+
+// the bit-exact corrector as exact_advect_all launches it: grid (xtiles * n, chunks), block (32, nzp / (2 np))
+int emu_corrector_exact(int np, int nzp, int stages, int nx, int nz, int ny, int ld, int n, const float* const* q2,
+                        const float* const* l, float* const* out, const float* const* coef10, const float* jaco, const float* dz,
+                        int chunk) {
+    Geom g{nx, nz, ny, ld, ld};
+    ExactMaps maps{};
+    OutSet outs{};
+    outs.n = n;
+    for (int s = 0; s < n; ++s) {
+        outs.out[s] = out[s];
+        maps.q2[s] = CUtensorMap{q2[s], nx, nz, ny, ld};
+        maps.l[s] = CUtensorMap{l[s], nx, nz, ny, ld};
+    }
+    // coef10 is in ExactCoef's member order (t0x cbx ccx t0y cby ccy ggy t0z cbz ccz); the maps are in stage order
+    const int order[10] = {3, 4, 5, 6, 0, 1, 2, 7, 8, 9};
+    for (int f = 0; f < 10; ++f) maps.coef[f] = CUtensorMap{coef10[order[f]], nx, nz, ny, ld};
+    maps.coef[10] = CUtensorMap{jaco, nx, nz, ny, ld};
+    maps.coef[11] = CUtensorMap{dz, nx, nz, ny, ld};
+    const int nzt = nzp / (2 * np);
+    const size_t smem = (size_t)(8 * (nzt + 1) * TW + stages * NFE * nzp * TW) * sizeof(float) + 16;
+    if (smem > 232448) return 2;                                      // 227 KB of shared memory per CTA
+    const int xtiles = nx / TOUT + 1, planes = ny - 2;
+    const unsigned gx = (unsigned)(xtiles * n), gy = (unsigned)((planes + chunk - 1) / chunk);
+#define ECASE(N, Z, S) if (np == N && nzp == Z && stages == S) { run_grid(gx, gy, nzt, smem, [&] { k_corrector_exact<N, Z, S>(g, outs, maps, chunk); }); return 0; }
+    ECASE(1, 20, 2)
+    ECASE(1, 40, 2)
+    ECASE(2, 48, 2)
+    ECASE(2, 52, 2)
+    ECASE(2, 60, 2)
+    ECASE(2, 64, 1)
+#undef ECASE
     return 1;
 }
 
