@@ -104,7 +104,6 @@ struct icar_ctx {
     float *qa = nullptr, *qb = nullptr, *u2 = nullptr, *v2 = nullptr, *w2 = nullptr;
     // fused path (mpdata_fused.cu): coefficient fields, per-scalar pass-1 scratch and output buffers
     bool fused = false;
-    bool fused_fast = false;         // TEMPORARY A/B hook: the round-1 "fast arithmetic" corrector
     FusedCoef coef{};
     float* fq2[ICAR_MAX_SCALARS] = {};
     float* fout[ICAR_MAX_SCALARS] = {};
@@ -477,8 +476,7 @@ extern "C" int icar_create(int device, const icar_grid* grid, const icar_options
         if (alloc_cells(ctx, p) != ICAR_OK) return bail(ICAR_ERR_CUDA);
     if (opt->advect_density && alloc_cells(ctx, &ctx->G) != ICAR_OK) return bail(ICAR_ERR_CUDA);
     ctx->fused = (opt->advection == 2 && opt->mpdata_order == 2 && opt->flux_corrected_transport &&
-                  !opt->advect_density && !opt->exact_arithmetic && exact_plan(ctx->g).ok);
-    ctx->fused_fast = ctx->fused && std::getenv("ICAR_CORR_FAST") != nullptr && fused_plan(ctx->g).ok;
+                  !opt->advect_density && !opt->exact_arithmetic && fused_plan(ctx->g).ok);
     if (opt->microphysics == 1) {
         ctx->nadv = 9; std::copy(kAdvectedThompson, kAdvectedThompson + 9, ctx->adv);
         ctx->nexch = 9; std::copy(kExchangedThompson, kExchangedThompson + 9, ctx->exch);
@@ -487,8 +485,8 @@ extern "C" int icar_create(int device, const icar_grid* grid, const icar_options
         ctx->nexch = 5; std::copy(kExchangedSimple, kExchangedSimple + 5, ctx->exch);
     }
     if (ctx->fused) {
-        float** cf[] = {&ctx->coef.ax, &ctx->coef.bx, &ctx->coef.cx, &ctx->coef.ay, &ctx->coef.by, &ctx->coef.cy,
-                        &ctx->coef.az, &ctx->coef.bz, &ctx->coef.cz, &ctx->coef.rj, &ctx->coef.rjz};
+        float** cf[] = {&ctx->coef.t0x, &ctx->coef.cbx, &ctx->coef.ccx, &ctx->coef.t0y, &ctx->coef.cby, &ctx->coef.ccy,
+                        &ctx->coef.ggy, &ctx->coef.t0z, &ctx->coef.cbz, &ctx->coef.ccz};
         for (float** p : cf)
             if (alloc_cells(ctx, p) != ICAR_OK) return bail(ICAR_ERR_CUDA);
         for (int n = 0; n < ctx->nadv; ++n)
@@ -534,8 +532,8 @@ extern "C" int icar_destroy(icar_ctx* ctx) {
     if (ctx->cfl_dt) cudaFree(ctx->cfl_dt);
     if (ctx->cfl_dz) cudaFree(ctx->cfl_dz);
     {
-        float* cf[] = {ctx->coef.ax, ctx->coef.bx, ctx->coef.cx, ctx->coef.ay, ctx->coef.by, ctx->coef.cy,
-                       ctx->coef.az, ctx->coef.bz, ctx->coef.cz, ctx->coef.rj, ctx->coef.rjz};
+        float* cf[] = {ctx->coef.t0x, ctx->coef.cbx, ctx->coef.ccx, ctx->coef.t0y, ctx->coef.cby, ctx->coef.ccy,
+                       ctx->coef.ggy, ctx->coef.t0z, ctx->coef.cbz, ctx->coef.ccz};
         for (float* p : cf) if (p) cudaFree(p);
         for (int n = 0; n < ICAR_MAX_SCALARS; ++n) { if (ctx->fq2[n]) cudaFree(ctx->fq2[n]); if (ctx->fout[n]) cudaFree(ctx->fout[n]); }
     }
@@ -711,8 +709,8 @@ int advect_impl(icar_ctx* ctx, float dt, int part) {
         }
         cudaEvent_t marks[4];
         if (ctx->prof_on) for (cudaEvent_t& m : marks) m = prof_event(ctx);
-        const int nl = (ctx->fused_fast ? fused_advect_all : exact_advect_all)(
-            g, ss, ctx->U, ctx->V, ctx->W, ctx->Wn, jaco, dz, ctx->coef, ctx->stream, ctx->prof_on ? marks : nullptr, part);
+        const int nl = fused_advect_all(g, ss, ctx->U, ctx->V, ctx->W, ctx->Wn, jaco, dz, ctx->coef, ctx->stream,
+                                        ctx->prof_on ? marks : nullptr, part);
         if (ctx->prof_on) {      // consecutive marks delimit the three kernels
             if (part == 1) {
                 ctx->prof_pending.push_back({K_FACE_COEF, marks[0], marks[1]});

@@ -48,7 +48,6 @@ int mp_simple_launch(const Geom& g, const float* p, float* th, const float* pii,
     }
     if (gx == 0 || gy == 0) return 0;
     int cpt = (g.nz + 9) / 10;                              // cells per thread: ~10 z-threads per CTA
-    if (const char* e = std::getenv("ICAR_MP_CPT")) { int v = std::atoi(e); if (v >= 1 && v <= 8 && v * 10 >= g.nz) cpt = v; }
     if (cpt > 8) return -1;                                 // nz > 80 is not built
     const int nzt = (g.nz + cpt - 1) / cpt;
     dim3 block(TX, nzt);

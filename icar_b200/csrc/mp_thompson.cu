@@ -16,7 +16,8 @@
 // within the tile, threadIdx.y = level): the cell's state and its ~55 REAL*8 process rates live in
 // registers, the couplings above go through a few shared-memory rows, and each field is read once and
 // written once.  Levels are processed in the Fortran's statement order within a cell, so the result
-// differs from the CPU restatement only through the device's powf/expf/log10f/pow/exp.
+// differs from the CPU restatement only through the device's powf/expf/log10f/pow/exp (and the three cheaper forms of
+// x**y described in the fragment).
 //
 // Typing follows the Fortran: REAL -> float, DOUBLE PRECISION -> double, mixed expressions promote
 // where the Fortran's do.  -fmad=false (see Makefile): no contraction.
@@ -33,15 +34,6 @@ namespace {
 
 #define ICAR_DYNAMIC_SMEM_D(name) extern __shared__ double name[]
 #include "mp_thompson_kernel.inc"
-
-// The same kernel with three shapes of x**y evaluated by cheaper routines of the same accuracy (see the fragment):
-// ICAR_TH_MATH2=1 selects it.  Opt-in until it has run on hardware; on the CPU emulation it is bit-identical to the
-// default in most fields and within 4e-8 (relative L2) of it in the others (tests/test_thompson_host.py).
-namespace th_math2 {
-#define ICAR_TH_MATH2 1
-#include "mp_thompson_kernel.inc"
-#undef ICAR_TH_MATH2
-}  // namespace th_math2
 
 }  // namespace
 
@@ -67,14 +59,7 @@ int th_driver_launch(const Geom& g, const ThConst& c, const ThTables& tb, float*
     dim3 block(TX, nkt), grid(gx, gy, tiles.n);
     const size_t smem = (size_t)nk * TX * sizeof(double) + (size_t)7 * (nk + 1) * TX * sizeof(float) + (size_t)10 * TX * sizeof(int);
     const int nthreads = TX * nkt;
-    const char* m2 = std::getenv("ICAR_TH_MATH2");           // read at every launch: the tests switch it
-    const bool math2 = m2 && std::atoi(m2) == 1;
-    th_math2::Args A2;
-    static_assert(sizeof(A2) == sizeof(A), "the two instantiations take the same arguments");
-    std::memcpy(&A2, &A, sizeof(A));
-#define TH_LAUNCH(MAXT, MINB)                                                                                         \
-    if (math2) th_math2::k_mp_thompson<MAXT, MINB><<<grid, block, smem, st>>>(g, c, tb, A2, ld2, dt, tiles, kts, kte, diag); \
-    else k_mp_thompson<MAXT, MINB><<<grid, block, smem, st>>>(g, c, tb, A, ld2, dt, tiles, kts, kte, diag)
+#define TH_LAUNCH(MAXT, MINB) k_mp_thompson<MAXT, MINB><<<grid, block, smem, st>>>(g, c, tb, A, ld2, dt, tiles, kts, kte, diag)
     if (nthreads <= 320) { TH_LAUNCH(320, 2); }
     else if (nthreads <= 640) { TH_LAUNCH(640, 1); }
     else { TH_LAUNCH(1024, 1); }

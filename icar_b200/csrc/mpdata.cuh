@@ -16,41 +16,32 @@ struct ScalarSet {
     float* out[ICAR_MAX_SCALARS];
 };
 
-// per-face scalar-independent coefficients of the fused corrector (mpdata_fused.cu)
+// per-face scalar-independent coefficients of the fused corrector (corrector_fused.inc: k_face_coefficients)
 struct FusedCoef {
-    float *ax, *bx, *cx, *ay, *by, *cy, *az, *bz, *cz, *rj, *rjz;
+    float *t0x, *cbx, *ccx, *t0y, *cby, *ccy, *ggy, *t0z, *cbz, *ccz;
 };
 
 // launch plan of the fused corrector for a tile; ok == false when it cannot serve this geometry
-// (more than 64 levels, or not enough opt-in shared memory): the caller then uses the staged path
+// (fewer than 3 or more than 64 levels, or not enough opt-in shared memory): the caller then uses the staged path
 struct FusedPlan {
     bool ok;
     int cpt, nzp, stages;
-    int rowbufs;     // sets of z-exchange rows in shared memory: 2, or 1 for the 53..60-level candidate
-    int nsync;       // 1: neighbour-only synchronisation in the plane loop (candidate)
     size_t smem;
 };
 FusedPlan fused_plan(const Geom& g);
 
-// order 2 + FCT, rho == 1, fp32: coefficients, pass 1 for all scalars, fused corrector.
-// U,V,W,Wn from staged_wind_normalise / staged_wn_G.  nz <= 64.  Returns < 0 when the TMA
+// order 2 + FCT, rho == 1, fp32 (mpdata_fused.cu): face coefficients, pass 1 for all scalars, fused corrector -- the
+// reference's arithmetic operation for operation.  U, V, W, Wn from staged_wind_normalise.  Returns < 0 when the TMA
 // tensor maps cannot be built (driver without cuTensorMapEncodeTiled).
 // marks (optional): 4 events recorded on `st` before the coefficient kernel and after each of the three
 // kernels, for the per-kernel profile (icar_profile_read).
+// part: 0 = everything; 1 = k_face_coefficients only (depends on the winds, not on the scalars); 2 = pass 1 +
+// corrector only.  A multi-image step queues part 1 before it waits for the halo exchange.
 int fused_advect_all(const Geom& g, const ScalarSet& s, const float* U, const float* V, const float* W,
                      const float* Wn, const float* jaco, const float* dz, const FusedCoef& co,
                      cudaStream_t st, cudaEvent_t* marks = nullptr, int part = 0);
-// part: 0 = everything; 1 = k_face_coefficients only (depends on the winds, not on the scalars); 2 = pass 1 +
-// corrector only.  A multi-image step queues part 1 before it waits for the halo exchange.
 
-// the same call with the bit-exact corrector (mpdata_exact.cu: the reference's arithmetic operation for operation); `co`
-// lends its buffers to the exact coefficient set
-FusedPlan exact_plan(const Geom& g);
-int exact_advect_all(const Geom& g, const ScalarSet& s, const float* U, const float* V, const float* W,
-                     const float* Wn, const float* jaco, const float* dz, const FusedCoef& co,
-                     cudaStream_t st, cudaEvent_t* marks = nullptr, int part = 0);
-
-// div2x of mpdata_exact.cu (what the corrector divides with) and the compiler's a / b on n device floats (n even)
+// div2x of corrector_prims.inc (what the corrector divides with) and the compiler's a / b on n device floats (n even)
 int selftest_division(const float* a, const float* b, float* packed, float* ieee, long long n, cudaStream_t st);
 
 // pass 1 (adv_mpdata.f90:44-105) of every scalar in one launch; also copies the boundary ring to out

@@ -335,8 +335,7 @@ __global__ void k_corrector(Geom g, const R* __restrict__ l, const R* __restrict
 }
 
 }  // namespace icar
-#include "upwind_all.cuh"  // k_upwind_all, k_upwind_all_v4: pass 1 for all scalars (default), emulatable on the CPU
-#include "upwind_p2.cuh"   // k_upwind_all_p2: pass 1 on f32x2 pairs (candidate), emulatable on the CPU
+#include "upwind_all.cuh"  // k_upwind_all_v4: pass 1 for all scalars, emulatable on the CPU
 namespace icar {
 
 // ---------------------------------------------------------------------------
@@ -352,20 +351,12 @@ static inline dim3 cell_grid(const Geom& g) {
 
 int staged_upwind_all(const Geom& g, const ScalarSet& s, const float* U, const float* V, const float* W,
                       const float* dz, const float* jaco, cudaStream_t st) {
-    const bool ieee = std::getenv("ICAR_UPWIND_IEEE_DIV") != nullptr;     // test hook, see div_shared
-    const bool scalar_form = std::getenv("ICAR_UPWIND_SCALAR") != nullptr || g.ld % 4 != 0;   // test hook: one cell per thread
-    const bool packed_form = std::getenv("ICAR_UPWIND_PACKED") != nullptr && !ieee && !scalar_form;   // opt-in candidate
-    dim3 grid = cell_grid(g);
     int done = 0, launches = 0;
     while (done < s.n) {                 // batches of up to 5 scalars share the wind / metric loads
         ScalarSet b;
         b.n = (s.n - done >= 5) ? 5 : (s.n - done);
         for (int n = 0; n < b.n; ++n) { b.q[n] = s.q[done + n]; b.q2[n] = s.q2[done + n]; b.out[n] = s.out[done + n]; }
-#define UPWIND_ALL(NN)                                                                                     \
-    if (packed_form) k_upwind_all_p2<NN><<<dim3((g.ld / 4 + 127) / 128, g.nz, g.ny), 128, 0, st>>>(g, b, U, V, W, dz, jaco); \
-    else if (ieee) k_upwind_all<NN, false><<<grid, cell_block(), 0, st>>>(g, b, U, V, W, dz, jaco);        \
-    else if (scalar_form) k_upwind_all<NN, true><<<grid, cell_block(), 0, st>>>(g, b, U, V, W, dz, jaco);  \
-    else k_upwind_all_v4<NN, true><<<dim3((g.ld / 4 + 127) / 128, g.nz, g.ny), 128, 0, st>>>(g, b, U, V, W, dz, jaco)
+#define UPWIND_ALL(NN) k_upwind_all_v4<NN><<<dim3((g.ld / 4 + 127) / 128, g.nz, g.ny), 128, 0, st>>>(g, b, U, V, W, dz, jaco)
         switch (b.n) {
             case 5: UPWIND_ALL(5); break;
             case 4: UPWIND_ALL(4); break;
@@ -385,7 +376,7 @@ int staged_wind_normalise(const Geom& g, const R* u, const R* v, const R* w, con
                           const R* jv, const R* jw, const R* rho, R dt, R dx, int scheme, R* U,
                           R* V, R* W, cudaStream_t st, const R* dz, R* Wn) {
     if constexpr (sizeof(R) == 4) {
-        if (!rho && scheme == 2 && Wn && dz && g.ld % 4 == 0 && !std::getenv("ICAR_WIND_SCALAR")) {
+        if (!rho && scheme == 2 && Wn && dz && g.ld % 4 == 0) {
             k_wind_normalise_v4<<<dim3((g.ld / 4 + 127) / 128, g.nz, g.ny), 128, 0, st>>>(
                 g, (const float*)u, (const float*)v, (const float*)w, (const float*)ju, (const float*)jv,
                 (const float*)jw, (float)dt, (float)dx, (float*)U, (float*)V, (float*)W, (const float*)dz, (float*)Wn);

@@ -1,7 +1,6 @@
-// Pass 1 of MPDATA for all scalars in one launch -- k_upwind_all (one cell per thread) and k_upwind_all_v4 (four cells
-// per thread, the default) -- in a header of their own so that tests/cpp/upwind_p2_host.cpp can run these very kernel
-// bodies on the CPU (host_emu.h) against the oracle's pass 1.  Included by mpdata_staged.cu; the SASS of the kernels
-// is byte-identical to what it was before the move (scripts/sass_same_as.py).
+// Pass 1 of MPDATA for all scalars in one launch -- k_upwind_all_v4, four cells per thread -- in a header of its own so
+// that tests/cpp/upwind_host.cpp can run this very kernel body on the CPU (host_emu.h) against the oracle's pass 1.
+// Included by mpdata_staged.cu.
 #pragma once
 #include "common.cuh"
 #include "mpdata.cuh"
@@ -9,79 +8,30 @@
 namespace icar {
 
 // ---------------------------------------------------------------------------------------------
-// Pass 1 for all scalars (same arithmetic, bit for bit, as k_upwind above; this file is built with -fmad=false).
+// Pass 1 for all scalars (same arithmetic, bit for bit, as k_upwind of mpdata_staged.cu, built with -fmad=false).
 // ---------------------------------------------------------------------------------------------
 // Both divisors of a cell (J and dz*J) are shared by all N scalars, so each quotient is formed from ONE
 // correctly rounded reciprocal per divisor, y = RN(1/b), as  q0 = RN(a*y), r = a - b*q0 (exact, FMA),
 // q = RN(q0 + r*y)  -- Markstein's correction: q is the IEEE quotient RN(a/b), bit for bit (outside the
 // subnormal range), for 3 instructions instead of the ~10 of a full division with its slow-path check.
-// MARKSTEIN = false keeps the plain `/` (test hook: tests/test_gpu_parity.py compares the two bitwise).
-template <bool MARKSTEIN>
+// (tests/test_fp_identities.py checks the identity in exact rational arithmetic.)
 __device__ __forceinline__ float div_shared(float a, float b, float y) {
-    if (!MARKSTEIN) return a / b;
     const float q0 = a * y;
     const float r = fmaf(-b, q0, a);
     return fmaf(r, y, q0);
 }
 
-template <int N, bool MARKSTEIN>
-__global__ void __launch_bounds__(128)
-k_upwind_all(Geom g, ScalarSet s, const float* __restrict__ U, const float* __restrict__ V,
-             const float* __restrict__ W, const float* __restrict__ dz, const float* __restrict__ jaco) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    const int k = blockIdx.y * blockDim.y + threadIdx.y, j = blockIdx.z * blockDim.z + threadIdx.z;
-    if (i >= g.nx || k >= g.nz || j >= g.ny) return;
-    const size_t c = g.at(i, k, j);
-    if (i == 0 || i == g.nx - 1 || j == 0 || j == g.ny - 1) {
-#pragma unroll
-        for (int n = 0; n < N; ++n) { const float v = s.q[n][c]; s.q2[n][c] = v; s.out[n][c] = v; }
-        return;
-    }
-    const size_t ps = g.ps();
-    const int ld = g.ld;
-    const bool bottom = (k == 0), top = (k == g.nz - 1), flat = (g.nz == 1);
-    // all loads of all scalars are issued before the first use (35 independent loads in flight)
-    float qc[N], qxm[N], qxp[N], qym[N], qyp[N], qzm[N], qzp[N];
-#pragma unroll
-    for (int n = 0; n < N; ++n) {
-        const float* __restrict__ qin = s.q[n];
-        qc[n] = qin[c]; qxm[n] = qin[c - 1]; qxp[n] = qin[c + 1];
-        qym[n] = qin[c - ps]; qyp[n] = qin[c + ps];
-        qzm[n] = bottom ? 0.f : qin[c - ld];
-        qzp[n] = top ? 0.f : qin[c + ld];
-    }
-    const float uxm = U[c], uxp = U[c + 1], vym = V[c], vyp = V[c + ps];
-    const float wzp = W[c], wzm = bottom ? 0.f : W[c - ld];
-    const float jc = jaco[c];
-    const float den = dz[c] * jc;
-    const float rj = MARKSTEIN ? __frcp_rn(jc) : 0.f, rden = MARKSTEIN ? __frcp_rn(den) : 0.f;
-#pragma unroll
-    for (int n = 0; n < N; ++n) {
-        const float fxm = donor(uxm, qxm[n], qc[n]), fxp = donor(uxp, qc[n], qxp[n]);
-        const float fym = donor(vym, qym[n], qc[n]), fyp = donor(vyp, qc[n], qyp[n]);
-        float val = qc[n] - div_shared<MARKSTEIN>((fxp - fxm) + (fyp - fym), jc, rj);
-        if (!flat) {
-            float vert;
-            if (bottom)   vert = donor(wzp, qc[n], qzp[n]);
-            else if (top) vert = qc[n] * wzp - donor(wzm, qzm[n], qc[n]);
-            else          vert = donor(wzp, qc[n], qzp[n]) - donor(wzm, qzm[n], qc[n]);
-            val = val - div_shared<MARKSTEIN>(vert, den, rden);
-        }
-        s.q2[n][c] = val;
-    }
-}
-
 // ---------------------------------------------------------------------------------------------
 // Pass 1 for all scalars, four consecutive cells per thread: every x-row of the 7-point stencil is one
 // 16-byte load (+ the i-1 / i+4 neighbours of the centre row), a quarter of the load and address
-// instructions of k_upwind_all, which was issue-bound on exactly those.  Same expressions, bit for bit.
+// instructions of a one-cell-per-thread kernel, which was issue-bound on exactly those.
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ void ld4(const float* __restrict__ p, float (&o)[4]) {
     const float4 q = *reinterpret_cast<const float4*>(p);
     o[0] = q.x; o[1] = q.y; o[2] = q.z; o[3] = q.w;
 }
 
-template <int N, bool MARKSTEIN>
+template <int N>
 __global__ void __launch_bounds__(128)
 k_upwind_all_v4(Geom g, ScalarSet s, const float* __restrict__ U, const float* __restrict__ V,
                 const float* __restrict__ W, const float* __restrict__ dz, const float* __restrict__ jaco) {
@@ -102,8 +52,8 @@ k_upwind_all_v4(Geom g, ScalarSet s, const float* __restrict__ U, const float* _
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
         den[e] = dzc[e] * jc[e];
-        rj[e] = MARKSTEIN ? __frcp_rn(jc[e]) : 0.f;
-        rden[e] = MARKSTEIN ? __frcp_rn(den[e]) : 0.f;
+        rj[e] = __frcp_rn(jc[e]);
+        rden[e] = __frcp_rn(den[e]);
     }
 #pragma unroll
     for (int n = 0; n < N; ++n) {
@@ -124,13 +74,13 @@ k_upwind_all_v4(Geom g, ScalarSet s, const float* __restrict__ U, const float* _
             const float uxp = (e == 3) ? u_hi : uc[e < 3 ? e + 1 : 3];
             const float fxm = donor(uc[e], qxm, qc[e]), fxp = donor(uxp, qc[e], qxp);
             const float fym = donor(vm[e], qym[e], qc[e]), fyp = donor(vp[e], qc[e], qyp[e]);
-            float v = qc[e] - div_shared<MARKSTEIN>((fxp - fxm) + (fyp - fym), jc[e], rj[e]);
+            float v = qc[e] - div_shared((fxp - fxm) + (fyp - fym), jc[e], rj[e]);
             if (!flat) {
                 float vert;
                 if (bottom)   vert = donor(wp[e], qc[e], qzp[e]);
                 else if (top) vert = qc[e] * wp[e] - donor(wm[e], qzm[e], qc[e]);
                 else          vert = donor(wp[e], qc[e], qzp[e]) - donor(wm[e], qzm[e], qc[e]);
-                v = v - div_shared<MARKSTEIN>(vert, den[e], rden[e]);
+                v = v - div_shared(vert, den[e], rden[e]);
             }
             val[e] = v;
         }

@@ -1,13 +1,14 @@
 // TEST INFRASTRUCTURE.  Runs the kernels of the fused MPDATA path (icar_b200/csrc/corrector_fused.inc:
-// k_face_coefficients(_v4), k_corrector_fused, k_corrector_fused_p2, k_corrector_fused_pk) on the CPU.
+// k_face_coefficients, k_corrector_fused) on the CPU.
 //
 // A CTA is emulated with ONE OS THREAD PER CUDA THREAD: __syncthreads is a pthread barrier over the CTA, a warp
 // shuffle is an exchange through a per-warp buffer between two barriers over the warp, an mbarrier is a phase
 // counter + outstanding byte count in the shared-memory word the kernel gave it, and a TMA box load is a copy with
 // zero fill outside the field done by the issuing thread (the kernel's waiters spin on the phase like on hardware).
-// Shared memory is one heap block per CTA; CTAs run one after the other.  rcp.approx is 1.0f / x and the f32x2
-// operations are done one IEEE half at a time (f32x2.cuh), so results agree with the device to the tolerance of
-// the "fast" mode, not bit for bit.  Built with -ffp-contract=off -pthread.
+// Shared memory is one heap block per CTA; CTAs run one after the other.  The f32x2 operations are done one IEEE half
+// at a time (f32x2.cuh) and the packed quotient is the IEEE `/` (corrector_prims.inc: the device sequence is the fast
+// path of div.rn.f32, checked against `/` on the device itself), so the results are the device's bit for bit.
+// Built with -ffp-contract=off -pthread.
 #include <pthread.h>
 #include <sched.h>
 #include <time.h>
@@ -97,7 +98,6 @@ namespace icar {
 namespace {
 #include "../../icar_b200/csrc/corrector_prims.inc"
 #include "../../icar_b200/csrc/corrector_fused.inc"
-#include "../../icar_b200/csrc/corrector_exact.inc"
 
 // one CTA of `threads` = 32 x nzt CUDA threads
 template <class Kernel>
@@ -136,35 +136,24 @@ using namespace icar;
 
 extern "C" {
 
-// k_face_coefficients_v4 (v4 != 0; grid ((ld/4+127)/128, nz, ny) x 128) or k_face_coefficients (grid of 32 x 4 x 4 blocks)
-void emu_face_coefficients(int v4, int nx, int nz, int ny, int ld, const float* U, const float* V, const float* Wn,
-                           const float* G, const float* dz, float* const* coef11) {
+// k_face_coefficients (grid ((ld/4+127)/128, nz, ny) x 128); coef10 in FusedCoef's member order
+void emu_face_coefficients(int nx, int nz, int ny, int ld, const float* U, const float* V, const float* Wn,
+                           const float* G, float* const* coef10) {
     Geom g{nx, nz, ny, ld, ld};
-    FusedCoef co{coef11[0], coef11[1], coef11[2], coef11[3], coef11[4], coef11[5], coef11[6], coef11[7], coef11[8], coef11[9], coef11[10]};
-    if (v4) {
-        blockDim = {128, 1, 1};
-        for (unsigned j = 0; j < (unsigned)ny; ++j)
-            for (unsigned k = 0; k < (unsigned)nz; ++k)
-                for (unsigned bx = 0; bx < (unsigned)((ld / 4 + 127) / 128); ++bx)
-                    for (unsigned t = 0; t < 128; ++t) { blockIdx = {bx, k, j}; threadIdx = {t, 0, 0}; k_face_coefficients_v4(g, U, V, Wn, G, dz, co); }
-        return;
-    }
-    blockDim = {32, 4, 4};
-    for (unsigned bz = 0; bz < (unsigned)((ny + 3) / 4); ++bz)
-        for (unsigned by = 0; by < (unsigned)((nz + 3) / 4); ++by)
-            for (unsigned bx = 0; bx < (unsigned)((nx + 31) / 32); ++bx)
-                for (unsigned tz = 0; tz < 4; ++tz)
-                    for (unsigned ty = 0; ty < 4; ++ty)
-                        for (unsigned tx = 0; tx < 32; ++tx) {
-                            blockIdx = {bx, by, bz}; threadIdx = {tx, ty, tz};
-                            k_face_coefficients(g, U, V, Wn, G, dz, co);
-                        }
+    FusedCoef co{coef10[0], coef10[1], coef10[2], coef10[3], coef10[4], coef10[5], coef10[6], coef10[7], coef10[8], coef10[9]};
+    blockDim = {128, 1, 1};
+    for (unsigned j = 0; j < (unsigned)ny; ++j)
+        for (unsigned k = 0; k < (unsigned)nz; ++k)
+            for (unsigned bx = 0; bx < (unsigned)((ld / 4 + 127) / 128); ++bx)
+                for (unsigned t = 0; t < 128; ++t) { blockIdx = {bx, k, j}; threadIdx = {t, 0, 0}; k_face_coefficients(g, U, V, Wn, G, co); }
 }
 
-// the corrector as fused_advect_all launches it: grid (xtiles * n, chunks), block (32, nzp / cpt), dynamic shared memory
-// of fused_plan (rowbufs sets of exchange rows).  kind 0: k_corrector_fused<cpt, nzp, stages>; 1: k_corrector_fused_p2<nzp>; 2: k_corrector_fused_pk<cpt / 2, nzp, stages>
-int emu_corrector(int kind, int cpt, int nzp, int stages, int rowbufs, int nsync, int nx, int nz, int ny, int ld, int n, const float* const* q2,
-                  const float* const* l, float* const* out, const float* const* coef11, int chunk) {
+// the corrector as fused_advect_all launches it: grid (xtiles * n, chunks), block (32, nzp / (2 np)), the dynamic shared
+// memory of fused_plan.  Returns 2 when the instantiation needs more shared memory than a CTA has, 1 when there is no
+// such instantiation.
+int emu_corrector(int np, int nzp, int stages, int nx, int nz, int ny, int ld, int n, const float* const* q2,
+                  const float* const* l, float* const* out, const float* const* coef10, const float* jaco, const float* dz,
+                  int chunk) {
     Geom g{nx, nz, ny, ld, ld};
     FusedMaps maps{};
     OutSet outs{};
@@ -174,70 +163,8 @@ int emu_corrector(int kind, int cpt, int nzp, int stages, int rowbufs, int nsync
         maps.q2[s] = CUtensorMap{q2[s], nx, nz, ny, ld};
         maps.l[s] = CUtensorMap{l[s], nx, nz, ny, ld};
     }
-    // coef11 is in FusedCoef's member order (ax bx cx ay by cy az bz cz rj rjz); the maps are in stage order
-    // (ay by cy ax bx cx az bz cz rj rjz), as fused_advect_all builds them
-    const int order[11] = {3, 4, 5, 0, 1, 2, 6, 7, 8, 9, 10};
-    for (int f = 0; f < 11; ++f) maps.coef[f] = CUtensorMap{coef11[order[f]], nx, nz, ny, ld};
-    const int nzt = nzp / cpt;
-    const size_t smem = (size_t)(rowbufs * 10 * (nzt + 2) * TW + stages * NF * nzp * TW) * sizeof(float) + 16 +
-                        (nsync ? (size_t)(2 + 3 * nzt) * 8 : 0);
-    if (smem > 232448) return 2;                                      // 227 KB of shared memory per CTA
-    const int xtiles = nx / TOUT + 1, planes = ny - 2;
-    const unsigned gx = (unsigned)(xtiles * n), gy = (unsigned)((planes + chunk - 1) / chunk);
-#define CASE(K, C, Z, S, CALL) if (!nsync && rowbufs == 2 && kind == K && cpt == C && nzp == Z && stages == S) { run_grid(gx, gy, nzt, smem, [&] { CALL; }); return 0; }
-    CASE(0, 2, 20, 2, (k_corrector_fused<2, 20, 2>(g, outs, maps, chunk)))
-    CASE(0, 2, 40, 2, (k_corrector_fused<2, 40, 2>(g, outs, maps, chunk)))
-    CASE(0, 4, 48, 2, (k_corrector_fused<4, 48, 2>(g, outs, maps, chunk)))
-    CASE(0, 4, 52, 2, (k_corrector_fused<4, 52, 2>(g, outs, maps, chunk)))
-    CASE(0, 4, 64, 1, (k_corrector_fused<4, 64, 1>(g, outs, maps, chunk)))
-    CASE(1, 2, 20, 2, (k_corrector_fused_p2<20>(g, outs, maps, chunk)))
-    CASE(1, 2, 40, 2, (k_corrector_fused_p2<40>(g, outs, maps, chunk)))
-    CASE(2, 2, 20, 2, (k_corrector_fused_pk<1, 20, 2>(g, outs, maps, chunk)))
-    CASE(2, 2, 40, 2, (k_corrector_fused_pk<1, 40, 2>(g, outs, maps, chunk)))
-    CASE(2, 4, 48, 2, (k_corrector_fused_pk<2, 48, 2>(g, outs, maps, chunk)))
-    CASE(2, 4, 52, 2, (k_corrector_fused_pk<2, 52, 2>(g, outs, maps, chunk)))
-    CASE(2, 4, 64, 1, (k_corrector_fused_pk<2, 64, 1>(g, outs, maps, chunk)))
-#define NCASE(C, Z, CALL) if (nsync && rowbufs == 2 && kind == 2 && stages == 2 && cpt == C && nzp == Z) { run_grid(gx, gy, nzt, smem, [&] { CALL; }); return 0; }
-    NCASE(2, 20, (k_corrector_fused_pk<1, 20, 2, 2, 1>(g, outs, maps, chunk)))
-    NCASE(2, 40, (k_corrector_fused_pk<1, 40, 2, 2, 1>(g, outs, maps, chunk)))
-    NCASE(4, 48, (k_corrector_fused_pk<2, 48, 2, 2, 1>(g, outs, maps, chunk)))
-    NCASE(4, 52, (k_corrector_fused_pk<2, 52, 2, 2, 1>(g, outs, maps, chunk)))
-#undef NCASE
-    if (!nsync && rowbufs == 1 && kind == 2 && cpt == 4 && nzp == 60 && stages == 2) {
-        run_grid(gx, gy, nzt, smem, [&] { k_corrector_fused_pk<2, 60, 2, 1>(g, outs, maps, chunk); });
-        return 0;
-    }
-#undef CASE
-    return 1;
-}
-
-
-// k_face_coefficients_exact (grid ((ld/4+127)/128, nz, ny) x 128); coef10 in ExactCoef's member order
-void emu_face_coefficients_exact(int nx, int nz, int ny, int ld, const float* U, const float* V, const float* Wn,
-                                 const float* G, float* const* coef10) {
-    Geom g{nx, nz, ny, ld, ld};
-    ExactCoef co{coef10[0], coef10[1], coef10[2], coef10[3], coef10[4], coef10[5], coef10[6], coef10[7], coef10[8], coef10[9]};
-    blockDim = {128, 1, 1};
-    for (unsigned j = 0; j < (unsigned)ny; ++j)
-        for (unsigned k = 0; k < (unsigned)nz; ++k)
-            for (unsigned bx = 0; bx < (unsigned)((ld / 4 + 127) / 128); ++bx)
-                for (unsigned t = 0; t < 128; ++t) { blockIdx = {bx, k, j}; threadIdx = {t, 0, 0}; k_face_coefficients_exact(g, U, V, Wn, G, co); }
-}
-
-// the bit-exact corrector as exact_advect_all launches it: grid (xtiles * n, chunks), block (32, nzp / (2 np))
-int emu_corrector_exact(int np, int nzp, int stages, int nx, int nz, int ny, int ld, int n, const float* const* q2,
-                        const float* const* l, float* const* out, const float* const* coef10, const float* jaco, const float* dz,
-                        int chunk) {
-    Geom g{nx, nz, ny, ld, ld};
-    ExactMaps maps{};
-    OutSet outs{};
-    outs.n = n;
-    for (int s = 0; s < n; ++s) {
-        outs.out[s] = out[s];
-        maps.q2[s] = CUtensorMap{q2[s], nx, nz, ny, ld};
-        maps.l[s] = CUtensorMap{l[s], nx, nz, ny, ld};
-    }
-    // coef10 is in ExactCoef's member order (t0x cbx ccx t0y cby ccy ggy t0z cbz ccz); the maps are in stage order
+    // coef10 is in FusedCoef's member order (t0x cbx ccx t0y cby ccy ggy t0z cbz ccz); the maps are in stage order
+    // (t0y cby ccy ggy | t0x cbx ccx t0z cbz ccz jaco dz), as fused_advect_all builds them
     const int order[10] = {3, 4, 5, 6, 0, 1, 2, 7, 8, 9};
     for (int f = 0; f < 10; ++f) maps.coef[f] = CUtensorMap{coef10[order[f]], nx, nz, ny, ld};
     maps.coef[10] = CUtensorMap{jaco, nx, nz, ny, ld};
@@ -247,14 +174,15 @@ int emu_corrector_exact(int np, int nzp, int stages, int nx, int nz, int ny, int
     if (smem > 232448) return 2;                                      // 227 KB of shared memory per CTA
     const int xtiles = nx / TOUT + 1, planes = ny - 2;
     const unsigned gx = (unsigned)(xtiles * n), gy = (unsigned)((planes + chunk - 1) / chunk);
-#define ECASE(N, Z, S) if (np == N && nzp == Z && stages == S) { run_grid(gx, gy, nzt, smem, [&] { k_corrector_exact<N, Z, S>(g, outs, maps, chunk); }); return 0; }
-    ECASE(1, 20, 2)
-    ECASE(1, 40, 2)
-    ECASE(2, 48, 2)
-    ECASE(2, 52, 2)
-    ECASE(2, 60, 2)
-    ECASE(2, 64, 1)
-#undef ECASE
+#define CASE(N, Z, S) if (np == N && nzp == Z && stages == S) { run_grid(gx, gy, nzt, smem, [&] { k_corrector_fused<N, Z, S>(g, outs, maps, chunk); }); return 0; }
+    CASE(1, 20, 2)
+    CASE(1, 40, 2)
+    CASE(2, 48, 2)
+    CASE(2, 52, 2)
+    CASE(2, 60, 2)
+    CASE(2, 64, 1)
+    CASE(2, 64, 2)          // does not fit: exercises the refusal
+#undef CASE
     return 1;
 }
 

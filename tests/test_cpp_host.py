@@ -43,8 +43,6 @@ def test_cpp_host_builds_and_fails_loudly_without_a_gpu(program):
 
 
 @pytest.mark.gpu
-@pytest.mark.skipif(os.environ.get("ICAR_TEST_UNVALIDATED") != "1",
-                    reason="not yet run on hardware (set ICAR_TEST_UNVALIDATED=1)")
 def test_reference_scenarios_from_cpp(program, golden_dir):
     r = subprocess.run([program], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stderr

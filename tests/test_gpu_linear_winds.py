@@ -16,9 +16,7 @@ from icar_b200 import ideal
 sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 from oracle import linear_winds_np as LW
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("ICAR_TEST_UNVALIDATED") != "1",
-                                 reason="not yet run on hardware (set ICAR_TEST_UNVALIDATED=1)")]
+pytestmark = [pytest.mark.gpu]
 
 RTOL = 1e-6
 

@@ -9,9 +9,7 @@ import pytest
 from icar_b200 import ideal
 from icar_b200 import restart as R
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("ICAR_TEST_UNVALIDATED") != "1",
-                                 reason="not yet run on hardware (set ICAR_TEST_UNVALIDATED=1)")]
+pytestmark = [pytest.mark.gpu]
 
 
 def make(gpu_lib, st, mp, **opt):

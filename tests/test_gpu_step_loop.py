@@ -154,8 +154,6 @@ def test_device_resident_loop_body(gpu_lib, oracle):
         assert np.abs(a - b).max() <= 1e-5 * np.abs(b).max(), k         # exner via device powf feeds mp_simple
 
 
-@pytest.mark.skipif(__import__("os").environ.get("ICAR_TEST_UNVALIDATED") != "1",
-                    reason="not yet run on hardware (set ICAR_TEST_UNVALIDATED=1)")
 def test_step_host_derives_exner_and_density_on_the_device(gpu_lib):
     """icar_step_host == upload; icar_diagnostic_update; icar_physics_step; download -- bit for bit -- and it
     refuses host exner / density."""
@@ -177,8 +175,6 @@ def test_step_host_derives_exner_and_density_on_the_device(gpu_lib):
         np.testing.assert_array_equal(host[k], ref.download(k), err_msg=k)
 
 
-@pytest.mark.skipif(__import__("os").environ.get("ICAR_TEST_UNVALIDATED") != "1",
-                    reason="not yet run on hardware (set ICAR_TEST_UNVALIDATED=1)")
 @pytest.mark.parametrize("bands,derive", [(3, False), (5, True), (1, False)])
 def test_host_pipeline_equals_the_undivided_host_step(gpu_lib, bands, derive):
     """icar_b200.pipeline.HostPipeline: bands of rows as stand-alone tiles with 4 ghost rows, stepped

@@ -1,11 +1,13 @@
 """k_mp_thompson run ON THE CPU (tests/cpp/thompson_host.cpp: one OS thread per CUDA thread of a CTA, pthread
 barriers, host atomics, the host's libm) against the oracle's mp_gt_driver, from identical inputs, call after call.
 
-The kernel HAS run on hardware (tests/test_gpu_thompson.py); this emulation exists so that the next versions of it --
+The kernel runs on hardware (tests/test_gpu_thompson.py); this emulation exists so that the next versions of it --
 it is the slowest kernel of the repository, DESIGN.md section 3.4 -- can be checked before they cost GPU time.  With
-the same libm on both sides the kernel's results are BIT-IDENTICAL to the oracle's (measured over the calls below,
-every species present): what separates the device from the oracle in the GPU test is the device's powf / expf /
-log10f (up to 2 ulp from glibc's) and nothing else.  That is the bar here: equality."""
+the same libm on both sides the kernel's statements are the oracle's: the only differences come from the three shapes
+of x**y the kernel evaluates with cheaper routines (10.**y through exp10f, x**3 by multiplication, x**(1/3 in REAL)
+through a refined cbrtf; mp_thompson_kernel.inc), and they stay far inside the parity bar -- every cell within 1e-6 of
+the field maximum, relative L2 <= 1e-7 per field, most fields of most calls unchanged in every bit (measured <= 4e-8;
+the GPU test's bars are 2e-5 and 1e-6).  With plain powf in their place the results were bit-identical (round 1)."""
 import ctypes as C
 import os
 import subprocess
@@ -36,11 +38,6 @@ def build(*defines):
 @pytest.fixture(scope="module")
 def emu():
     return build()
-
-
-@pytest.fixture(scope="module")
-def emu_math2():
-    return build("-DICAR_TH_MATH2=1")
 
 
 @pytest.fixture(scope="module")
@@ -76,9 +73,16 @@ def emulated_driver(emu, oth, st, dt, its, ite, jts, jte, kts, kte, along_y=0):
 
 
 def compare(got, ref, what):
+    """Returns the number of fields that are equal in every bit."""
+    exact = 0
     for k in FIELDS + ("rainnc", "snownc", "graupelnc", "sr"):
-        assert np.isfinite(got[k]).all(), (what, k)
-        assert np.array_equal(got[k], ref[k]), (what, k, float(np.abs(got[k].astype(np.float64) - ref[k]).max()))
+        a, b = got[k].astype(np.float64), ref[k].astype(np.float64)
+        assert np.isfinite(a).all(), (what, k)
+        scale = max(np.abs(b).max(), 1e-30)
+        assert np.abs(a - b).max() <= 1e-6 * scale, (what, k, np.abs(a - b).max() / scale)
+        assert np.sqrt(((a - b) ** 2).sum()) <= 1e-7 * max(np.sqrt((b ** 2).sum()), 1e-30), (what, k)
+        exact += int(np.array_equal(got[k], ref[k]))
+    return exact
 
 
 @pytest.mark.parametrize("dims,dt,calls", [((20, 20, 6), 60.0, 14), ((12, 40, 5), 120.0, 8)])
@@ -86,14 +90,16 @@ def test_emulated_kernel_matches_the_oracle_call_after_call(emu, oracle_thompson
     nx, nz, ny = dims
     ref = ideal.add_thompson_fields(ideal.make_ideal_case(nx=nx, nz=nz, ny=ny), moisten=3.0)
     seen = np.zeros(5)
+    exact = 0
     for call in range(calls):
         st = ideal.copy_state(ref)
         emulated_driver(emu, oracle_thompson, st, dt, 1, nx - 2, 1, ny - 2, 0, nz - 1)
         oracle_thompson.driver(ref, dt, 1, nx - 2, 1, ny - 2, 0, nz - 1)
-        compare(st, ref, f"call {call}")
+        exact += compare(st, ref, f"call {call}")
         np.testing.assert_array_equal(st["qv"][0], ref["qv"][0])               # untouched outside the tile
         np.testing.assert_array_equal(st["th"][:, :, 0], ref["th"][:, :, 0])
         seen = np.maximum(seen, [ref[k].max() for k in ("qc", "qr", "qi", "qs", "qg")])
+    assert exact >= 0.6 * calls * 13                       # most fields of most calls do not change by a bit
     if nz == 20:
         assert (seen > 1e-6).all(), f"scenario did not exercise every species: {seen}"
 
@@ -108,27 +114,3 @@ def test_lanes_along_y_and_a_sub_tile(emu, oracle_thompson):
     emulated_driver(emu, oracle_thompson, st, 60.0, 3, 4, 2, 16, 0, nz - 4, along_y=1)
     oracle_thompson.driver(ref, 60.0, 3, 4, 2, 16, 0, nz - 4)
     compare(st, ref, "strip")
-
-
-@pytest.mark.parametrize("dims,dt,calls", [((20, 20, 6), 60.0, 20), ((12, 40, 5), 120.0, 10)])
-def test_math2_candidate_stays_far_inside_the_parity_bar(emu_math2, oracle_thompson, dims, dt, calls):
-    """ICAR_TH_MATH2=1 (th_math2::k_mp_thompson, not yet run on hardware): 10.**y through exp10f, x**3 by
-    multiplication, x**(1/3 in REAL) through a refined cbrtf, Mrat**mu_s evaluated once -- 22 of the ~37 powf calls per
-    cell.  Bars: every cell within 1e-6 of the field maximum and relative L2 <= 1e-7 per field (measured: most fields
-    bit-identical, the others <= 4e-8; the GPU test's bars are 2e-5 and 1e-6).  A cbrtf WITHOUT the Newton step costs the
-    whole budget (1e-6 L2 in the rain mass: one ulp of lamr is visible), which is why it has one."""
-    nx, nz, ny = dims
-    ref = ideal.add_thompson_fields(ideal.make_ideal_case(nx=nx, nz=nz, ny=ny), moisten=3.0)
-    exact = 0
-    for call in range(calls):
-        st = ideal.copy_state(ref)
-        emulated_driver(emu_math2, oracle_thompson, st, dt, 1, nx - 2, 1, ny - 2, 0, nz - 1)
-        oracle_thompson.driver(ref, dt, 1, nx - 2, 1, ny - 2, 0, nz - 1)
-        for k in FIELDS + ("rainnc", "snownc", "graupelnc"):
-            a, b = st[k].astype(np.float64), ref[k].astype(np.float64)
-            assert np.isfinite(a).all(), (call, k)
-            scale = max(np.abs(b).max(), 1e-30)
-            assert np.abs(a - b).max() <= 1e-6 * scale, (call, k, np.abs(a - b).max() / scale)
-            assert np.sqrt(((a - b) ** 2).sum()) <= 1e-7 * max(np.sqrt((b ** 2).sum()), 1e-30), (call, k)
-            exact += int(np.array_equal(st[k], ref[k]))
-    assert exact >= 0.6 * calls * 12                       # most fields of most calls do not change by a bit

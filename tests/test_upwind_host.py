@@ -1,15 +1,12 @@
-"""(Also here, since the harness is the same: the pass-1 kernels that HAVE run on hardware -- k_upwind_all_v4, the default,
-and k_upwind_all with and without the shared-reciprocal quotient -- pass the same bit-for-bit check, which validates the
-emulation.)
-
-The packed pass-1 candidate (k_upwind_all_p2, ICAR_UPWIND_PACKED=1: MPDATA's donor-cell pass on f32x2 pairs with
-the donor flux in the Fortran's own form U+ l + U- r) has not run on hardware yet; its kernel body runs here on the
-CPU (tests/cpp/upwind_p2_host.cpp over icar_b200/csrc/upwind_p2.cuh and host_emu.h) against the oracle's pass 1,
-upwind_advection (adv_mpdata.f90:44-105), BIT FOR BIT -- bottom / top levels, a one-level grid, the boundary ring,
-a ragged last group of four cells, tiny and zero mixing ratios, both signs of every wind component."""
+"""MPDATA pass 1 as the product runs it (k_upwind_all_v4: all scalars in one launch, four cells per thread, quotients from
+one correctly rounded reciprocal per divisor) with its kernel body run ON THE CPU (tests/cpp/upwind_host.cpp over
+icar_b200/csrc/upwind_all.cuh and host_emu.h) against the oracle's upwind_advection (adv_mpdata.f90:44-105), BIT FOR BIT:
+bottom / top levels, a one-level grid, the boundary ring, a ragged last group of four cells, tiny and zero mixing
+ratios, both signs of every wind component."""
 import ctypes as C
 import os
 import subprocess
+import tempfile
 
 import numpy as np
 import pytest
@@ -22,10 +19,9 @@ f = np.float32
 
 @pytest.fixture(scope="module")
 def emu():
-    import tempfile
-    so = os.path.join(tempfile.mkdtemp(prefix="up2"), "libupwind_p2_host.so")
+    so = os.path.join(tempfile.mkdtemp(prefix="upw"), "libupwind_host.so")
     cmd = ["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-Wall", "-Werror", "-Wno-unknown-pragmas",
-           "-Wno-unused-function", os.path.join(ROOT, "tests", "cpp", "upwind_p2_host.cpp"), "-o", so]
+           "-Wno-unused-function", os.path.join(ROOT, "tests", "cpp", "upwind_host.cpp"), "-o", so]
     r = subprocess.run(cmd, capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
     return C.CDLL(so)
@@ -40,7 +36,7 @@ def device_image(a, ld, rows_y=None, fill=0.0):
 
 
 @pytest.mark.parametrize("dims", [(150, 23, 19), (64, 1, 9), (33, 2, 7), (40, 9, 12), (37, 8, 5)])
-def test_packed_pass1_equals_the_oracle_bit_for_bit(emu, oracle, dims):
+def test_pass1_equals_the_oracle_bit_for_bit(emu, oracle, dims):
     nx, nz, ny = dims
     st = ideal.make_ideal_case(nx=nx, nz=max(nz, 8), ny=ny, perturb=True)
     for k, v in list(st.items()):
@@ -49,8 +45,8 @@ def test_packed_pass1_equals_the_oracle_bit_for_bit(emu, oracle, dims):
     rng = np.random.default_rng(8)
     shape = st["qv"].shape
     st["qc"] = (rng.random(shape) ** 8 * 1e-3).astype(f)
-    st["qr"] = (10.0 ** rng.uniform(-30, -3, shape)).astype(f)                  # tiny, but fluxes stay normal numbers: the
-    #                      shared-reciprocal quotient is the IEEE one outside the subnormal range (tests/test_fp_identities.py)
+    st["qr"] = (10.0 ** rng.uniform(-30, -3, shape)).astype(f)     # tiny, but fluxes stay normal numbers: the shared-reciprocal
+    #                                   quotient is the IEEE one outside the subnormal range (tests/test_fp_identities.py)
     st["qr"][rng.random(shape) < 0.3] = 0
     st["w"] = (st["w"] + rng.uniform(-0.3, 0.3, shape)).astype(f)
     st["u"] = (st["u"] * rng.uniform(-1.2, 1.2, st["u"].shape)).astype(f)       # both signs of every wind component
@@ -72,18 +68,14 @@ def test_packed_pass1_equals_the_oracle_bit_for_bit(emu, oracle, dims):
     out = [np.full((ny + 1, nz, ld), f(7e7)) for _ in names]
     P = lambda arrs: (C.c_void_p * len(arrs))(*[a.ctypes.data for a in arrs])
     fp = lambda a: a.ctypes.data_as(C.c_void_p)
-    runs = [("p2", n, None) for n in (5, 2)] + [("v4", 5, (1, 1)), ("one cell", 5, (0, 1)), ("one cell, IEEE division", 2, (0, 0))]
-    for what, n, form in runs:        # the candidate (5 scalars and a shorter instantiation), then the kernels that HAVE run on hardware
+    for n in (5, 2):
         for a in q2 + out:
             a[...] = f(7e7)
-        if form is None:
-            rc = emu.emu_upwind_all_p2(nx, nz, ny, ld, n, P(qin[:n]), P(q2[:n]), P(out[:n]), fp(Ud), fp(Vd), fp(Wd), fp(dz), fp(jaco))
-        else:
-            rc = emu.emu_upwind_all(nx, nz, ny, ld, n, P(qin[:n]), P(q2[:n]), P(out[:n]), fp(Ud), fp(Vd), fp(Wd), fp(dz), fp(jaco), *form)
-        assert rc == 0, what
+        rc = emu.emu_upwind_all(nx, nz, ny, ld, n, P(qin[:n]), P(q2[:n]), P(out[:n]), fp(Ud), fp(Vd), fp(Wd), fp(dz), fp(jaco))
+        assert rc == 0
         for s in range(n):
             got = q2[s][:ny, :, :nx]
-            assert np.array_equal(got, want[names[s]]), (what, names[s], np.abs(got - want[names[s]]).max())
+            assert np.array_equal(got, want[names[s]]), (names[s], np.abs(got - want[names[s]]).max())
             # the boundary ring also goes to `out` (it is never touched by the corrector)
             ring = np.ones((ny, nz, nx), bool); ring[1:-1, :, 1:-1] = False
             assert np.array_equal(out[s][:ny, :, :nx][ring], st[names[s]][ring])
