@@ -164,7 +164,7 @@ SYMBOLS = (
     "icar_physics_step", "icar_physics_steps", "icar_synchronize", "icar_mp_diagnostics", "icar_kernel_launches",
     "icar_selftest_division",
     "icar_timer_start", "icar_timer_stop",
-    "icar_halo_plan", "icar_comm_unique_id", "icar_comm_init", "icar_mpdata_set_winds", "icar_mpdata_advect3d",
+    "icar_halo_plan", "icar_comm_unique_id", "icar_comm_init", "icar_comm_init_local", "icar_mpdata_set_winds", "icar_mpdata_advect3d",
     "icar_mpdata_set_winds_f64", "icar_mpdata_advect3d_f64", "icar_mp_simple_driver",
     "icar_physics_step_host", "icar_step_host", "icar_physics_step_host_io", "icar_host_register", "icar_host_unregister",
     "icar_default_mp_options", "icar_thompson_init", "icar_thompson_table", "icar_mp_gt_driver",
@@ -578,6 +578,14 @@ def halo_plan(grid: Grid, image: int, nimages: int):
         raise IcarError(rc, "icar_halo_plan: invalid arguments")
     return dict(send_lo=plan[0], send_hi=plan[1], recv_lo=plan[2], recv_hi=plan[3],
                 has_lo=bool(plan[4]), has_hi=bool(plan[5]), axis=("x", "y")[plan[6]], width=plan[7])
+
+
+def comm_init_local(domains) -> None:
+    """icar_comm_init_local: connects Domains that live in this process (image order) so that they exchange halos."""
+    arr = (C.c_void_p * len(domains))(*[d._h.value for d in domains])
+    rc = lib().icar_comm_init_local(arr, len(domains))
+    if rc:
+        raise IcarError(rc, "; ".join(lib().icar_last_error(d._h).decode() for d in domains))
 
 
 def comm_unique_id() -> bytes:

@@ -42,4 +42,16 @@ __device__ __forceinline__ R donor(R U, R l, R r) {
     return U * (U > R(0) ? l : r);
 }
 
+// Forces a kernel's code onto the device now.  CUDA loads kernels lazily, at their first launch, and that load can
+// wait for the device to go idle -- which never happens while an image's halo kernels are waiting on the device for a
+// neighbour whose own first launches are blocked behind that load.  icar_comm_init* therefore touches every kernel of
+// the multi-image step before the first exchange (each translation unit lists its own in a *_preload function).
+#if defined(__CUDACC__)
+template <class K>
+inline bool preload_kernel(K kernel) {
+    cudaFuncAttributes a;
+    return cudaFuncGetAttributes(&a, kernel) == cudaSuccess;
+}
+#endif
+
 }  // namespace icar

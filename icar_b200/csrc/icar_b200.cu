@@ -49,17 +49,16 @@ Shape var_shape(int var) {
     }
 }
 
-// dynamically bound NCCL (so the library loads on a host without NCCL / without a GPU)
+// dynamically bound NCCL (so the library loads on a host without NCCL / without a GPU).  NCCL is plumbing here:
+// the all-gather of the arena handles at icar_comm_init and the one-double co_min of update_dt.  The halo exchange
+// itself is written by kernels into peer-mapped memory (halo.cu).
 struct Nccl {
     void* h = nullptr;
     ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
     ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
     ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
-    ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
-    ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
-    ncclResult_t (*GroupStart)() = nullptr;
-    ncclResult_t (*GroupEnd)() = nullptr;
     const char* (*GetErrorString)(ncclResult_t) = nullptr;
     bool load(std::string& err) {
         if (h) return true;
@@ -75,11 +74,8 @@ struct Nccl {
         BIND(GetUniqueId, "ncclGetUniqueId")
         BIND(CommInitRank, "ncclCommInitRank")
         BIND(CommDestroy, "ncclCommDestroy")
-        BIND(Send, "ncclSend")
-        BIND(Recv, "ncclRecv")
+        BIND(AllGather, "ncclAllGather")
         BIND(AllReduce, "ncclAllReduce")
-        BIND(GroupStart, "ncclGroupStart")
-        BIND(GroupEnd, "ncclGroupEnd")
         BIND(GetErrorString, "ncclGetErrorString")
 #undef BIND
         return true;
@@ -125,7 +121,19 @@ struct icar_ctx {
     // multi-image
     ncclComm_t comm = nullptr;
     int image = 1, nimages = 1;
-    float *send_w = nullptr, *send_e = nullptr, *recv_w = nullptr, *recv_e = nullptr;
+    // The advected scalars (two buffers each: advect() writes the other one) and the exchange flags live in ONE
+    // allocation, the arena, so that a neighbouring image can map it (CUDA IPC, or the plain pointer inside one
+    // process) and store its boundary cells straight into this image's ghost cells (halo.cu).
+    void* arena = nullptr;
+    size_t slot_bytes = 0;                   // one buffer of one scalar, rounded up to 256 bytes
+    float* home[ICAR_MAX_SCALARS][2] = {};   // the two buffers of advected scalar n (adv[] order)
+    struct Peer {
+        void* base = nullptr;                // the neighbour's arena as this process sees it
+        bool ipc = false;                    // opened with cudaIpcOpenMemHandle (to be closed)
+        int nx = 0, ny = 0, ld = 0;
+        size_t slot_bytes = 0;
+    } peer[2];                               // [0] lower image (west / south), [1] upper image
+    bool linked = false;                     // icar_comm_init / icar_comm_init_local has connected the neighbours
     bool exchange_in_flight = false;
     bool winds_f64_valid = false;
     // per-kernel profile (icar_profile_enable / icar_profile_read): event pairs queued on the launching stream
@@ -171,10 +179,10 @@ int fail(icar_ctx* c, int code, const std::string& msg) {
 
 // kernel families of the per-kernel profile
 enum ProfKid { K_MP_SIMPLE = 0, K_MP_THOMPSON, K_WIND_NORMALISE, K_FACE_COEF, K_UPWIND_PASS1, K_CORRECTOR,
-               K_STAGED_ADVECT3D, K_HALO_PACK, K_HALO_UNPACK, K_COUNT };
+               K_STAGED_ADVECT3D, K_HALO_PUSH, K_HALO_WAIT, K_COUNT };
 const char* const kProfNames[K_COUNT] = {"k_mp_simple", "k_mp_thompson", "k_wind_normalise",
                                          "k_face_coefficients", "k_upwind_all", "k_corrector_fused",
-                                         "staged_advect3d", "k_halo_pack", "k_halo_unpack"};
+                                         "staged_advect3d", "k_halo_push", "k_halo_wait"};
 
 cudaEvent_t prof_event(icar_ctx* c) {
     if (!c->prof_pool.empty()) { cudaEvent_t e = c->prof_pool.back(); c->prof_pool.pop_back(); return e; }
@@ -219,6 +227,9 @@ void var_geometry(const icar_ctx* c, int var, int* width, int* pitch, size_t* ro
         case D2:    *width = g.nx;     *pitch = c->ld2; *rows = (size_t)g.ny; break;
     }
 }
+
+constexpr size_t kArenaHeader = 256;      // HF_COUNT exchange flags in front of the scalar buffers
+static_assert(kArenaHeader >= HF_COUNT * sizeof(unsigned), "flag block");
 
 size_t cell_elems(const icar_ctx* c) { return (size_t)c->g.ld * c->g.nz * (c->g.ny + 1); }
 
@@ -462,7 +473,29 @@ extern "C" int icar_create(int device, const icar_grid* grid, const icar_options
     CUB(cudaEventCreateWithFlags(&ctx->ev_comm, cudaEventDisableTiming));
     CUB(cudaEventCreate(&ctx->ev_t0));
     CUB(cudaEventCreate(&ctx->ev_t1));
+    if (opt->microphysics == 1) {
+        ctx->nadv = 9; std::copy(kAdvectedThompson, kAdvectedThompson + 9, ctx->adv);
+        ctx->nexch = 9; std::copy(kExchangedThompson, kExchangedThompson + 9, ctx->exch);
+    } else {
+        ctx->nadv = 5; std::copy(kAdvectedSimple, kAdvectedSimple + 5, ctx->adv);
+        ctx->nexch = 5; std::copy(kExchangedSimple, kExchangedSimple + 5, ctx->exch);
+    }
+    {   // the arena: exchange flags, then two buffers per advected scalar
+        ctx->slot_bytes = (cell_elems(ctx) * sizeof(float) + 255) / 256 * 256;
+        const size_t bytes = kArenaHeader + (size_t)2 * ctx->nadv * ctx->slot_bytes;
+        CUB(cudaMalloc(&ctx->arena, bytes));
+        CUB(cudaMemsetAsync(ctx->arena, 0, bytes, ctx->stream));
+        for (int n = 0; n < ctx->nadv; ++n)
+            for (int b = 0; b < 2; ++b)
+                ctx->home[n][b] = (float*)((char*)ctx->arena + kArenaHeader + (size_t)(2 * n + b) * ctx->slot_bytes);
+    }
     for (int v = 0; v < ICAR_VAR_COUNT; ++v) {
+        const int* a = std::find(ctx->adv, ctx->adv + ctx->nadv, v);
+        if (a != ctx->adv + ctx->nadv) {              // an advected scalar: lives in the arena
+            ctx->vars[v] = ctx->home[a - ctx->adv][0];
+            ctx->fout[a - ctx->adv] = ctx->home[a - ctx->adv][1];
+            continue;
+        }
         int width, pitch; size_t rows;
         var_geometry(ctx, v, &width, &pitch, &rows);
         size_t bytes = (var_shape(v) == D2) ? (size_t)pitch * rows * sizeof(double)
@@ -477,21 +510,13 @@ extern "C" int icar_create(int device, const icar_grid* grid, const icar_options
     if (opt->advect_density && alloc_cells(ctx, &ctx->G) != ICAR_OK) return bail(ICAR_ERR_CUDA);
     ctx->fused = (opt->advection == 2 && opt->mpdata_order == 2 && opt->flux_corrected_transport &&
                   !opt->advect_density && !opt->exact_arithmetic && fused_plan(ctx->g).ok);
-    if (opt->microphysics == 1) {
-        ctx->nadv = 9; std::copy(kAdvectedThompson, kAdvectedThompson + 9, ctx->adv);
-        ctx->nexch = 9; std::copy(kExchangedThompson, kExchangedThompson + 9, ctx->exch);
-    } else {
-        ctx->nadv = 5; std::copy(kAdvectedSimple, kAdvectedSimple + 5, ctx->adv);
-        ctx->nexch = 5; std::copy(kExchangedSimple, kExchangedSimple + 5, ctx->exch);
-    }
     if (ctx->fused) {
         float** cf[] = {&ctx->coef.t0x, &ctx->coef.cbx, &ctx->coef.ccx, &ctx->coef.t0y, &ctx->coef.cby, &ctx->coef.ccy,
                         &ctx->coef.ggy, &ctx->coef.t0z, &ctx->coef.cbz, &ctx->coef.ccz};
         for (float** p : cf)
             if (alloc_cells(ctx, p) != ICAR_OK) return bail(ICAR_ERR_CUDA);
         for (int n = 0; n < ctx->nadv; ++n)
-            if (alloc_cells(ctx, &ctx->fq2[n]) != ICAR_OK || alloc_cells(ctx, &ctx->fout[n]) != ICAR_OK)
-                return bail(ICAR_ERR_CUDA);
+            if (alloc_cells(ctx, &ctx->fq2[n]) != ICAR_OK) return bail(ICAR_ERR_CUDA);
     }
     CUB(cudaMalloc((void**)&ctx->sr2d, (size_t)ctx->ld2 * ny * sizeof(float)));
     CUB(cudaMemsetAsync(ctx->sr2d, 0, (size_t)ctx->ld2 * ny * sizeof(float), ctx->stream));
@@ -518,9 +543,11 @@ extern "C" int icar_destroy(icar_ctx* ctx) {
     if (ctx->aux) cudaStreamSynchronize(ctx->aux);
     if (ctx->sgraph.exec) cudaGraphExecDestroy(ctx->sgraph.exec);
     if (ctx->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(ctx->comm);
-    for (void* p : ctx->vars) if (p) cudaFree(p);
-    float* bufs[] = {ctx->U, ctx->V, ctx->W, ctx->Wn, ctx->G, ctx->qa, ctx->qb, ctx->u2, ctx->v2, ctx->w2,
-                     ctx->sr2d, ctx->send_w, ctx->send_e, ctx->recv_w, ctx->recv_e};
+    for (auto& pr : ctx->peer) if (pr.base && pr.ipc) cudaIpcCloseMemHandle(pr.base);
+    for (void* p : ctx->vars)         // (the advected scalars live in the arena)
+        if (p && !((char*)p >= (char*)ctx->arena && ctx->arena && (char*)p < (char*)ctx->arena + kArenaHeader + (size_t)2 * ctx->nadv * ctx->slot_bytes)) cudaFree(p);
+    if (ctx->arena) cudaFree(ctx->arena);
+    float* bufs[] = {ctx->U, ctx->V, ctx->W, ctx->Wn, ctx->G, ctx->qa, ctx->qb, ctx->u2, ctx->v2, ctx->w2, ctx->sr2d};
     for (float* p : bufs) if (p) cudaFree(p);
     if (ctx->diag) cudaFree(ctx->diag);
     for (double* t : ctx->th_tab) if (t) cudaFree(t);
@@ -535,7 +562,7 @@ extern "C" int icar_destroy(icar_ctx* ctx) {
         float* cf[] = {ctx->coef.t0x, ctx->coef.cbx, ctx->coef.ccx, ctx->coef.t0y, ctx->coef.cby, ctx->coef.ccy,
                        ctx->coef.ggy, ctx->coef.t0z, ctx->coef.cbz, ctx->coef.ccz};
         for (float* p : cf) if (p) cudaFree(p);
-        for (int n = 0; n < ICAR_MAX_SCALARS; ++n) { if (ctx->fq2[n]) cudaFree(ctx->fq2[n]); if (ctx->fout[n]) cudaFree(ctx->fout[n]); }
+        for (int n = 0; n < ICAR_MAX_SCALARS; ++n) if (ctx->fq2[n]) cudaFree(ctx->fq2[n]);
     }
     for (void* p : ctx->scratch) if (p) cudaFree(p);
     lw_destroy(ctx->lw);
@@ -561,6 +588,8 @@ extern "C" const char* icar_last_error(const icar_ctx* ctx) {
 // ============================================================================ resident state
 
 extern "C" int icar_upload(icar_ctx* ctx, int var, const void* host) {
+    if (ctx && ctx->exchange_in_flight)
+        return fail(ctx, ICAR_ERR_INVALID, "icar_upload between icar_halo_send and icar_halo_retrieve: the neighbours are writing this image's ghost cells");
     if (!ctx || !host || var < 0 || var >= ICAR_VAR_COUNT) return fail(ctx, ICAR_ERR_INVALID, "icar_upload: bad argument");
     CU(cudaSetDevice(ctx->device));
     { int jr = join_aux(ctx); if (jr) return jr; }
@@ -574,6 +603,8 @@ extern "C" int icar_upload(icar_ctx* ctx, int var, const void* host) {
 }
 
 extern "C" int icar_download(icar_ctx* ctx, int var, void* host) {
+    if (ctx && ctx->exchange_in_flight)
+        return fail(ctx, ICAR_ERR_INVALID, "icar_download between icar_halo_send and icar_halo_retrieve: the neighbours are writing this image's ghost cells");
     if (!ctx || !host || var < 0 || var >= ICAR_VAR_COUNT) return fail(ctx, ICAR_ERR_INVALID, "icar_download: bad argument");
     CU(cudaSetDevice(ctx->device));
     { int jr = join_aux(ctx); if (jr) return jr; }
@@ -709,8 +740,11 @@ int advect_impl(icar_ctx* ctx, float dt, int part) {
         }
         cudaEvent_t marks[4];
         if (ctx->prof_on) for (cudaEvent_t& m : marks) m = prof_event(ctx);
+        // a slab stores only the cells it owns: its ghost cells are refilled by the next exchange before anything reads them
+        const icar_grid& gr = ctx->grid;
+        const int own[4] = {gr.its - gr.ims, gr.ite - gr.ims + 1, gr.jts - gr.jms, gr.jte - gr.jms + 1};
         const int nl = fused_advect_all(g, ss, ctx->U, ctx->V, ctx->W, ctx->Wn, jaco, dz, ctx->coef, ctx->stream,
-                                        ctx->prof_on ? marks : nullptr, part);
+                                        ctx->prof_on ? marks : nullptr, part, ctx->nimages > 1 ? own : nullptr);
         if (ctx->prof_on) {      // consecutive marks delimit the three kernels
             if (part == 1) {
                 ctx->prof_pending.push_back({K_FACE_COEF, marks[0], marks[1]});
@@ -746,9 +780,8 @@ int advect_impl(icar_ctx* ctx, float dt, int part) {
         ctx->launches += staged_advect3d<float>(g, q, rho, jaco, dz, ctx->U, ctx->V, ctx->W, ctx->Wn, G, order,
                                                 ctx->opt.flux_corrected_transport != 0, ctx->qa, ctx->qb,
                                                 ctx->u2, ctx->v2, ctx->w2, &res, ctx->stream);
-        // the result buffer becomes the field; the old field buffer becomes scratch
-        if (res == ctx->qa) { ctx->qa = q; ctx->vars[var] = res; }
-        else if (res == ctx->qb) { ctx->qb = q; ctx->vars[var] = res; }
+        // the field stays where it is (its buffer is part of the peer-mapped arena): copy the result home
+        if (res != q) CU(cudaMemcpyAsync(q, res, cell_elems(ctx) * sizeof(float), cudaMemcpyDeviceToDevice, ctx->stream));
     }
     CU(cudaGetLastError());
     return ICAR_OK;
@@ -879,27 +912,165 @@ extern "C" int icar_comm_unique_id(char id[128]) {
     return ICAR_OK;
 }
 
+namespace {
+
+// what an image tells the others about its arena (all-gathered at icar_comm_init)
+struct ArenaInfo {
+    cudaIpcMemHandle_t handle;
+    unsigned long long slot_bytes;
+    int nx, nz, ny, ld, nadv, device;
+};
+
+// Advected scalar n of `ctx` lives in home[n][b] with the same b on every image: all images make the same sequence of
+// advect() calls, and only the fused advect() swaps (b flips for every scalar at once).
+int current_buffer(const icar_ctx* ctx) { return ctx->vars[ctx->adv[0]] == (void*)ctx->home[0][0] ? 0 : 1; }
+
+// The links of the exchange that starts now: this image's fields and flags, and for each neighbour its fields (in the
+// buffers that hold them now), geometry and flags.
+int halo_links(icar_ctx* ctx, HaloLinks* L) {
+    int plan[8];
+    if (icar_halo_plan(&ctx->grid, ctx->image, ctx->nimages, plan))
+        return fail(ctx, ICAR_ERR_INVALID, "halo exchange: tile narrower than two halos, or not a slab decomposition");
+    if (!ctx->linked) return fail(ctx, ICAR_ERR_COMM, "halo exchange: icar_comm_init / icar_comm_init_local was not called");
+    std::memset(L, 0, sizeof(*L));
+    L->nfields = ctx->nexch;
+    L->axis = plan[6];
+    L->h = plan[7];
+    L->flags = (unsigned*)ctx->arena;
+    const int b = current_buffer(ctx);
+    int slot_of[ICAR_MAX_EXCHANGED];
+    for (int s = 0; s < ctx->nexch; ++s) {
+        const int n = (int)(std::find(ctx->adv, ctx->adv + ctx->nadv, ctx->exch[s]) - ctx->adv);
+        if (n >= ctx->nadv || ctx->vars[ctx->exch[s]] != (void*)ctx->home[n][b])
+            return fail(ctx, ICAR_ERR_INVALID, "halo exchange: an exchanged scalar is not in its arena buffer");
+        slot_of[s] = 2 * n + b;
+        L->src[s] = ctx->home[n][b];
+    }
+    for (int side = 0; side < 2; ++side) {
+        HaloSide& S = L->side[side];
+        S.present = plan[4 + side];
+        if (!S.present) continue;
+        const icar_ctx::Peer& P = ctx->peer[side];
+        if (!P.base) return fail(ctx, ICAR_ERR_COMM, "halo exchange: neighbour not mapped");
+        const int peer_extent = L->axis ? P.ny : P.nx;
+        S.src0 = side == 0 ? plan[0] : plan[1];                  // put_west / put_south : put_east / put_north
+        S.dst0 = side == 0 ? peer_extent - L->h : 0;             // its upper ghost cells : its lower ghost cells
+        S.dst_ld = P.ld;
+        S.dst_ny = P.ny;
+        S.flags = (unsigned*)P.base;
+        for (int s = 0; s < ctx->nexch; ++s)
+            S.dst[s] = (float*)((char*)P.base + kArenaHeader + (size_t)slot_of[s] * P.slot_bytes);
+    }
+    return ICAR_OK;
+}
+
+int check_peer(icar_ctx* ctx, int side, const ArenaInfo& me, const ArenaInfo& other) {
+    const bool ycut = (ctx->grid.jms > ctx->grid.jds) || (ctx->grid.jme < ctx->grid.jde);
+    const bool ok = other.nz == me.nz && other.nadv == me.nadv && (ycut ? (other.nx == me.nx && other.ld == me.ld) : other.ny == me.ny);
+    if (!ok) return fail(ctx, ICAR_ERR_COMM, "icar_comm_init: the neighbouring image has a different cross-section or scheme");
+    ctx->peer[side].nx = other.nx; ctx->peer[side].ny = other.ny; ctx->peer[side].ld = other.ld;
+    ctx->peer[side].slot_bytes = (size_t)other.slot_bytes;
+    return ICAR_OK;
+}
+
+// every kernel of the multi-image step, loaded before the first exchange (preload_kernel, common.cuh)
+int preload_step_kernels(icar_ctx* ctx) {
+    const bool ok = halo_preload() && staged_preload() && fused_preload() && mp_simple_preload() && th_driver_preload();
+    if (!ok) { (void)cudaGetLastError(); return fail(ctx, ICAR_ERR_CUDA, "icar_comm_init: cannot load the kernels of the step"); }
+    return ICAR_OK;
+}
+
+ArenaInfo arena_info(const icar_ctx* ctx) {
+    ArenaInfo a{};
+    a.slot_bytes = ctx->slot_bytes;
+    a.nx = ctx->g.nx; a.nz = ctx->g.nz; a.ny = ctx->g.ny; a.ld = ctx->g.ld; a.nadv = ctx->nadv; a.device = ctx->device;
+    return a;
+}
+
+}  // namespace
+
+// One process per image: NCCL communicator (co_min of update_dt) + the neighbours' arenas mapped with CUDA IPC.
 extern "C" int icar_comm_init(icar_ctx* ctx, int image, int nimages, const char id[128]) {
     if (!ctx || !id || image < 1 || image > nimages) return fail(ctx, ICAR_ERR_INVALID, "icar_comm_init: bad argument");
     CU(cudaSetDevice(ctx->device));
     ctx->image = image;
     ctx->nimages = nimages;
     if (nimages == 1) return ICAR_OK;
+    { int rc = preload_step_kernels(ctx); if (rc) return rc; }
     std::string err;
     if (!g_nccl.load(err)) return fail(ctx, ICAR_ERR_COMM, err);
     ncclUniqueId uid;
     std::memcpy(&uid, id, 128);
     NC(g_nccl.CommInitRank(&ctx->comm, nimages, uid, image - 1));
-    size_t n = (size_t)ctx->nexch * ctx->g.ny * ctx->g.nz * ctx->grid.halo_size * sizeof(float);
-    CU(cudaMalloc((void**)&ctx->send_w, n));
-    CU(cudaMalloc((void**)&ctx->send_e, n));
-    CU(cudaMalloc((void**)&ctx->recv_w, n));
-    CU(cudaMalloc((void**)&ctx->recv_e, n));
+    // all-gather the arena descriptions
+    ArenaInfo mine = arena_info(ctx);
+    CU(cudaIpcGetMemHandle(&mine.handle, ctx->arena));
+    std::vector<ArenaInfo> all(nimages);
+    char* d = nullptr;
+    CU(cudaMalloc((void**)&d, sizeof(ArenaInfo) * (size_t)(nimages + 1)));
+    cudaError_t e = cudaMemcpyAsync(d, &mine, sizeof(ArenaInfo), cudaMemcpyHostToDevice, ctx->stream);
+    ncclResult_t nr = ncclSuccess;
+    if (e == cudaSuccess) nr = g_nccl.AllGather(d, d + sizeof(ArenaInfo), sizeof(ArenaInfo), ncclChar, ctx->comm, ctx->stream);
+    if (e == cudaSuccess && nr == ncclSuccess)
+        e = cudaMemcpyAsync(all.data(), d + sizeof(ArenaInfo), sizeof(ArenaInfo) * (size_t)nimages, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess && nr == ncclSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(d);
+    NC(nr);
+    CU(e);
+    for (int side = 0; side < 2; ++side) {
+        const int other = side == 0 ? image - 2 : image;          // 0-based rank of the neighbour
+        if (other < 0 || other >= nimages) continue;
+        int rc = check_peer(ctx, side, mine, all[other]);
+        if (rc) return rc;
+        void* base = nullptr;
+        const cudaError_t oe = cudaIpcOpenMemHandle(&base, all[other].handle, cudaIpcMemLazyEnablePeerAccess);
+        if (oe != cudaSuccess)
+            return fail(ctx, ICAR_ERR_COMM, std::string("icar_comm_init: cannot map the neighbouring image's memory (cudaIpcOpenMemHandle: ") +
+                                                cudaGetErrorString(oe) + "); the images of one run must be on GPUs of one box with peer access");
+        ctx->peer[side].base = base;
+        ctx->peer[side].ipc = true;
+    }
+    ctx->linked = true;
     return ICAR_OK;
 }
 
-// halo_send with the stream that produced the cells to be sent: the exchange (and, for x-slabs, the pack
-// kernel) is ordered after the work queued on `producer` only
+// All images in ONE process (a test harness, or one host thread driving several GPUs): ctxs[i] is image i + 1.  No NCCL
+// communicator: icar_compute_dt then returns the image's own time step and the caller takes the minimum (co_min).
+// The caller must queue the steps of all images before it waits for any of them (an image's kernels wait on the device
+// for its neighbours' data).
+extern "C" int icar_comm_init_local(icar_ctx** ctxs, int nimages) {
+    if (!ctxs || nimages < 1) return ICAR_ERR_INVALID;
+    for (int i = 0; i < nimages; ++i) if (!ctxs[i]) return ICAR_ERR_INVALID;
+    for (int i = 0; i < nimages; ++i) {
+        icar_ctx* ctx = ctxs[i];
+        CU(cudaSetDevice(ctx->device));
+        ctx->image = i + 1;
+        ctx->nimages = nimages;
+        if (nimages == 1) continue;
+        { int rc = preload_step_kernels(ctx); if (rc) return rc; }
+        const ArenaInfo mine = arena_info(ctx);
+        for (int side = 0; side < 2; ++side) {
+            const int other = side == 0 ? i - 1 : i + 1;
+            if (other < 0 || other >= nimages) continue;
+            int rc = check_peer(ctx, side, mine, arena_info(ctxs[other]));
+            if (rc) return rc;
+            if (ctxs[other]->device != ctx->device) {
+                const cudaError_t pe = cudaDeviceEnablePeerAccess(ctxs[other]->device, 0);
+                if (pe != cudaSuccess && pe != cudaErrorPeerAccessAlreadyEnabled)
+                    return fail(ctx, ICAR_ERR_COMM, std::string("icar_comm_init_local: cudaDeviceEnablePeerAccess: ") + cudaGetErrorString(pe));
+                (void)cudaGetLastError();
+            }
+            ctx->peer[side].base = ctxs[other]->arena;
+            ctx->peer[side].ipc = false;
+        }
+        ctx->linked = true;
+    }
+    return ICAR_OK;
+}
+
+// halo_send with the stream that produced the cells to be sent: the exchange is ordered after the work queued on
+// `producer` only.  `producer` must itself be ordered after everything that read this image's ghost cells (the previous
+// advect): the auxiliary stream forks from the compute stream, so it is.
 int halo_send_from(icar_ctx* ctx, cudaStream_t producer);
 
 extern "C" int icar_halo_send(icar_ctx* ctx) {
@@ -911,55 +1082,18 @@ extern "C" int icar_halo_send(icar_ctx* ctx) {
 }
 
 int halo_send_from(icar_ctx* ctx, cudaStream_t producer) {
-    if (!ctx->comm) return fail(ctx, ICAR_ERR_COMM, "icar_halo_send: icar_comm_init was not called");
-    int plan[8];
-    if (icar_halo_plan(&ctx->grid, ctx->image, ctx->nimages, plan)) return fail(ctx, ICAR_ERR_INVALID, "icar_halo_send: tile narrower than two halos, or not a slab decomposition");
-    const int h = plan[7];
-    const bool lower = plan[4] != 0, upper = plan[5] != 0;
-    const int nf = ctx->nexch;
-    float* fields[ICAR_MAX_EXCHANGED];
-    for (int s = 0; s < nf; ++s) fields[s] = (float*)ctx->vars[ctx->exch[s]];
-    if (plan[6] == 0) {
-        // x-slabs: faces are ny*nz runs of h floats -> gather all fields into one buffer per side
-        const size_t count = (size_t)nf * ctx->g.ny * ctx->g.nz * h;
-        int x0[2], ns = 0;
-        float* bufs[2];
-        if (lower) { x0[ns] = plan[0]; bufs[ns++] = ctx->send_w; }
-        if (upper) { x0[ns] = plan[1]; bufs[ns++] = ctx->send_e; }
-        { ProfScope ps(ctx, K_HALO_PACK, producer);
-          ctx->launches += halo_pack_launch(ctx->g, fields, nf, h, ns, x0, bufs, producer); }
-        CU(cudaGetLastError());
-        CU(cudaEventRecord(ctx->ev_packed, producer));
-        CU(cudaStreamWaitEvent(ctx->comm_stream, ctx->ev_packed, 0));
-        NC(g_nccl.GroupStart());
-        if (lower) {
-            NC(g_nccl.Send(ctx->send_w, count, ncclFloat, ctx->image - 2, ctx->comm, ctx->comm_stream));
-            NC(g_nccl.Recv(ctx->recv_w, count, ncclFloat, ctx->image - 2, ctx->comm, ctx->comm_stream));
-        }
-        if (upper) {
-            NC(g_nccl.Send(ctx->send_e, count, ncclFloat, ctx->image, ctx->comm, ctx->comm_stream));
-            NC(g_nccl.Recv(ctx->recv_e, count, ncclFloat, ctx->image, ctx->comm, ctx->comm_stream));
-        }
-        NC(g_nccl.GroupEnd());
-    } else {
-        // y-slabs: a face of one field is h contiguous planes -> send straight from the field and
-        // receive straight into the ghost planes (mp(subset) does not touch either while this runs)
-        const size_t ps = ctx->g.ps(), count = (size_t)h * ps;
-        CU(cudaEventRecord(ctx->ev_packed, producer));
-        CU(cudaStreamWaitEvent(ctx->comm_stream, ctx->ev_packed, 0));
-        NC(g_nccl.GroupStart());
-        for (int s = 0; s < nf; ++s) {
-            if (lower) {
-                NC(g_nccl.Send(fields[s] + (size_t)plan[0] * ps, count, ncclFloat, ctx->image - 2, ctx->comm, ctx->comm_stream));
-                NC(g_nccl.Recv(fields[s] + (size_t)plan[2] * ps, count, ncclFloat, ctx->image - 2, ctx->comm, ctx->comm_stream));
-            }
-            if (upper) {
-                NC(g_nccl.Send(fields[s] + (size_t)plan[1] * ps, count, ncclFloat, ctx->image, ctx->comm, ctx->comm_stream));
-                NC(g_nccl.Recv(fields[s] + (size_t)plan[3] * ps, count, ncclFloat, ctx->image, ctx->comm, ctx->comm_stream));
-            }
-        }
-        NC(g_nccl.GroupEnd());
+    if (ctx->exchange_in_flight) return fail(ctx, ICAR_ERR_INVALID, "icar_halo_send: the previous exchange has not been retrieved");
+    HaloLinks L;
+    int rc = halo_links(ctx, &L);
+    if (rc) return rc;
+    CU(cudaEventRecord(ctx->ev_packed, producer));
+    CU(cudaStreamWaitEvent(ctx->comm_stream, ctx->ev_packed, 0));
+    {
+        ProfScope ps(ctx, K_HALO_PUSH, ctx->comm_stream);
+        ctx->launches += halo_begin_launch(L, ctx->comm_stream);
+        ctx->launches += halo_push_launch(ctx->g, L, ctx->comm_stream);
     }
+    CU(cudaGetLastError());
     CU(cudaEventRecord(ctx->ev_comm, ctx->comm_stream));
     ctx->exchange_in_flight = true;
     return ICAR_OK;
@@ -970,23 +1104,15 @@ extern "C" int icar_halo_retrieve(icar_ctx* ctx) {
     if (ctx->nimages == 1) return ICAR_OK;
     if (!ctx->exchange_in_flight) return fail(ctx, ICAR_ERR_INVALID, "icar_halo_retrieve without icar_halo_send");
     CU(cudaSetDevice(ctx->device));
-    int plan[8];
-    if (icar_halo_plan(&ctx->grid, ctx->image, ctx->nimages, plan)) return fail(ctx, ICAR_ERR_INVALID, "icar_halo_retrieve: tile narrower than two halos");
-    const int h = plan[7];
-    const bool lower = plan[4] != 0, upper = plan[5] != 0;
-    CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_comm, 0));     // `sync images(neighbors)`, exchangeable_obj.f90:151
-    if (plan[6] == 0) {
-        const int nf = ctx->nexch;
-        float* fields[ICAR_MAX_EXCHANGED];
-        for (int s = 0; s < nf; ++s) fields[s] = (float*)ctx->vars[ctx->exch[s]];
-        int x0[2], ns = 0;
-        float* bufs[2];
-        if (lower) { x0[ns] = plan[2]; bufs[ns++] = ctx->recv_w; }
-        if (upper) { x0[ns] = plan[3]; bufs[ns++] = ctx->recv_e; }
-        { ProfScope ps(ctx, K_HALO_UNPACK, ctx->stream);
-          ctx->launches += halo_unpack_launch(ctx->g, fields, nf, h, ns, x0, bufs, ctx->stream); }
-        CU(cudaGetLastError());
+    HaloLinks L;
+    int rc = halo_links(ctx, &L);
+    if (rc) return rc;
+    CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_comm, 0));     // this image's own puts are out
+    {
+        ProfScope ps(ctx, K_HALO_WAIT, ctx->stream);           // `sync images(neighbors)`, exchangeable_obj.f90:151
+        ctx->launches += halo_wait_launch(L, ctx->stream);
     }
+    CU(cudaGetLastError());
     ctx->exchange_in_flight = false;
     return ICAR_OK;
 }
@@ -1645,18 +1771,22 @@ extern "C" int icar_compute_dt(icar_ctx* ctx, const float* dz_levels, float cfl,
         }
     }
     const float dt = cfl / maxwind3d;
-    if (dt < 1e-1f) {
-        char msg[200];
-        std::snprintf(msg, sizeof msg, "ERROR time step too small: dt = %g, Umax = %g, Vmax = %g, Wmax = %g", dt, m[1], m[2], m[3]);
-        return fail(ctx, ICAR_ERR_PHYSICS, msg);
-    }
     double seconds = (double)dt;
-    if (ctx->nimages > 1) {                                     // call co_min(seconds), :413
-        if (!ctx->comm) return fail(ctx, ICAR_ERR_COMM, "icar_compute_dt: icar_comm_init was not called");
+    if (ctx->nimages > 1 && ctx->comm) {                        // call co_min(seconds), :413
+        // (the collective comes BEFORE the "too small" stop: an image that returned early would leave the others
+        // blocked in it; this way every image sees the same minimum and stops, or goes on, together)
         CU(cudaMemcpyAsync(ctx->cfl_dt, &seconds, sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
         NC(g_nccl.AllReduce(ctx->cfl_dt, ctx->cfl_dt, 1, ncclDouble, ncclMin, ctx->comm, ctx->stream));
         CU(cudaMemcpyAsync(&seconds, ctx->cfl_dt, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
         CU(cudaStreamSynchronize(ctx->stream));
+    } else if (ctx->nimages > 1 && !ctx->linked) {
+        return fail(ctx, ICAR_ERR_COMM, "icar_compute_dt: icar_comm_init was not called");
+    }
+    if (seconds < 1e-1) {                                       // :322-328
+        char msg[240];
+        std::snprintf(msg, sizeof msg, "ERROR time step too small: dt = %g (this image: dt = %g, Umax = %g, Vmax = %g, Wmax = %g)",
+                      seconds, dt, m[1], m[2], m[3]);
+        return fail(ctx, ICAR_ERR_PHYSICS, msg);
     }
     *dt_seconds = std::min(seconds, 120.0);                     // :421
     return ICAR_OK;

@@ -70,4 +70,10 @@ int mp_simple_launch(const Geom& g, const float* p, float* th, const float* pii,
     return 1;
 }
 
+bool mp_simple_preload() {
+    return preload_kernel(k_mp_simple<1>) && preload_kernel(k_mp_simple<2>) && preload_kernel(k_mp_simple<3>) &&
+           preload_kernel(k_mp_simple<4>) && preload_kernel(k_mp_simple<5>) && preload_kernel(k_mp_simple<6>) &&
+           preload_kernel(k_mp_simple<7>) && preload_kernel(k_mp_simple<8>);
+}
+
 }  // namespace icar

@@ -22,4 +22,6 @@ int mp_simple_launch(const Geom& g, const float* p, float* th, const float* pii,
 // (acc_rain / acc_snow non-null: resident mode -- rain / snow are ignored and the call's precipitation is
 //  added straight to domain%accumulated_precipitation / accumulated_snowfall, REAL*8, mp_driver.f90:587-595)
 
+bool mp_simple_preload();     // see preload_kernel (common.cuh)
+
 }  // namespace icar

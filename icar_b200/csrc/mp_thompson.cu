@@ -67,4 +67,8 @@ int th_driver_launch(const Geom& g, const ThConst& c, const ThTables& tb, float*
     return 1;
 }
 
+bool th_driver_preload() {
+    return preload_kernel(k_mp_thompson<320, 2>) && preload_kernel(k_mp_thompson<640, 1>) && preload_kernel(k_mp_thompson<1024, 1>);
+}
+
 }  // namespace icar

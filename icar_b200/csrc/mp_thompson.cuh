@@ -70,4 +70,6 @@ int th_driver_launch(const Geom& g, const ThConst& c, const ThTables& tb, float*
 // (acc_* non-null: resident mode -- the call's precipitation / snowfall / graupel are added straight to the
 //  REAL*8 accumulators of domain_t, mp_driver.f90:587-595; rainnc / snownc / graupelnc are then null)
 
+bool th_driver_preload();     // see preload_kernel (common.cuh)
+
 }  // namespace icar

@@ -39,7 +39,9 @@ FusedPlan fused_plan(const Geom& g);
 // corrector only.  A multi-image step queues part 1 before it waits for the halo exchange.
 int fused_advect_all(const Geom& g, const ScalarSet& s, const float* U, const float* V, const float* W,
                      const float* Wn, const float* jaco, const float* dz, const FusedCoef& co,
-                     cudaStream_t st, cudaEvent_t* marks = nullptr, int part = 0);
+                     cudaStream_t st, cudaEvent_t* marks = nullptr, int part = 0, const int* own = nullptr);
+// own (optional): {i0, i1, j0, j1}, the half-open tile-local ranges of the cells whose result is stored (a slab stores
+// only the cells it owns); default: the tile without its boundary ring.
 
 // div2x of corrector_prims.inc (what the corrector divides with) and the compiler's a / b on n device floats (n even)
 int selftest_division(const float* a, const float* b, float* packed, float* ieee, long long n, cudaStream_t st);
@@ -61,5 +63,8 @@ template <class R>
 int staged_advect3d(const Geom& g, R* q, const R* rho, const R* jaco, const R* dz, const R* U,
                     const R* V, const R* W, const R* Wn, const R* G, int order, bool fct, R* qa,
                     R* qb, R* u2, R* v2, R* w2, R** result, cudaStream_t st);
+
+bool fused_preload();         // see preload_kernel (common.cuh)
+bool staged_preload();
 
 }  // namespace icar

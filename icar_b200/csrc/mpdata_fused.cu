@@ -15,6 +15,7 @@
 // This TU is compiled with -fmad=false: the only fused multiply-adds are the explicit ones of the division sequence.
 #include <cuda.h>
 
+#include <algorithm>
 #include <cstring>
 
 #include "common.cuh"
@@ -73,7 +74,7 @@ FusedPlan fused_plan(const Geom& g) {
 
 int fused_advect_all(const Geom& g, const ScalarSet& s, const float* U, const float* V, const float* W,
                      const float* Wn, const float* jaco, const float* dz, const FusedCoef& co,
-                     cudaStream_t st, cudaEvent_t* marks, int part) {
+                     cudaStream_t st, cudaEvent_t* marks, int part, const int* own) {
     int launches = 0;
     if (s.n > FUSED_MAX_SCALARS) return -1;
     if (marks) cudaEventRecord(marks[0], st);
@@ -104,7 +105,11 @@ int fused_advect_all(const Geom& g, const ScalarSet& s, const float* U, const fl
     // re-reads); one CTA per SM is resident (shared-memory bound)
     int dev = 0, sms = 148;
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const int per_row = xtiles * s.n, planes = g.ny - 2;
+    // cells whose result is stored: own = {i0, i1, j0, j1} (half-open, tile-local), default the tile without its ring
+    OutRange range{1, g.nx - 1, 1, g.ny - 1};
+    if (own) range = OutRange{std::max(own[0], 1), std::min(own[1], g.nx - 1), std::max(own[2], 1), std::min(own[3], g.ny - 1)};
+    if (range.i1 <= range.i0 || range.j1 <= range.j0) return launches;
+    const int per_row = xtiles * s.n, planes = range.j1 - range.j0;
     int best = 1;
     double best_cost = 1e30;
     for (int cand = 1; cand <= 64 && cand <= planes; ++cand) {
@@ -123,7 +128,7 @@ int fused_advect_all(const Geom& g, const ScalarSet& s, const float* U, const fl
         auto kern = k_corrector_fused<NPAIRS, Z, S>;                                                          \
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem) !=        \
             cudaSuccess) { (void)cudaGetLastError(); return -1; }                                             \
-        kern<<<grid, block, plan.smem, st>>>(g, outs, maps, chunk);                                           \
+        kern<<<grid, block, plan.smem, st>>>(g, outs, maps, chunk, range);                                          \
     }
     if (plan.nzp == 20) LAUNCH_FUSED(1, 20, 2)
     else if (plan.nzp == 40) LAUNCH_FUSED(1, 40, 2)
@@ -135,6 +140,13 @@ int fused_advect_all(const Geom& g, const ScalarSet& s, const float* U, const fl
     ++launches;
     if (marks) cudaEventRecord(marks[3], st);
     return launches;
+}
+
+bool fused_preload() {
+    return preload_kernel(k_face_coefficients) && preload_kernel(k_corrector_fused<1, 20, 2>) &&
+           preload_kernel(k_corrector_fused<1, 40, 2>) && preload_kernel(k_corrector_fused<2, 48, 2>) &&
+           preload_kernel(k_corrector_fused<2, 52, 2>) && preload_kernel(k_corrector_fused<2, 60, 2>) &&
+           preload_kernel(k_corrector_fused<2, 64, 1>);
 }
 
 }  // namespace icar

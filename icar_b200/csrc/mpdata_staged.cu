@@ -441,4 +441,12 @@ int staged_advect3d(const Geom& g, R* q, const R* rho, const R* jaco, const R* d
 INSTANTIATE(float)
 INSTANTIATE(double)
 
+bool staged_preload() {
+    return preload_kernel(k_wind_normalise<float>) && preload_kernel(k_wind_normalise_v4) && preload_kernel(k_wn_G<float>) &&
+           preload_kernel(k_upwind<float>) && preload_kernel(k_pseudo_velocities<float>) &&
+           preload_kernel(k_corrector<float, true>) && preload_kernel(k_corrector<float, false>) &&
+           preload_kernel(k_upwind_all_v4<1>) && preload_kernel(k_upwind_all_v4<2>) && preload_kernel(k_upwind_all_v4<3>) &&
+           preload_kernel(k_upwind_all_v4<4>) && preload_kernel(k_upwind_all_v4<5>);
+}
+
 }  // namespace icar

@@ -377,9 +377,8 @@ int icar_mp_gt_driver(icar_ctx* ctx, float* qv, float* qc, float* qr, float* qi,
 /* ------------------------------------------------- multi-image (one process per GPU) */
 
 /* Same for a y-slab decomposition (ximages = 1, yimages = nimages): every image keeps full x-rows,
- * which keeps all kernels at full SIMD width and makes the exchanged faces contiguous planes (no
- * pack / unpack kernels: ncclSend / ncclRecv go straight from / into the fields).  This is what
- * bench.py uses for N > 1; x-slabs remain supported. */
+ * which keeps all kernels at full SIMD width and makes the exchanged faces contiguous planes.  This is what
+ * bench.py uses for N > 1 by default; x-slabs (the reference's first axis) work the same way. */
 int icar_grid_yslab(int nx_global, int nz, int ny_global, int nimages, int image, int halo_size,
                     icar_grid* out);
 
@@ -397,12 +396,27 @@ int icar_grid_yslab(int nx_global, int nz, int ny_global, int nimages, int image
  * Pure host function (no GPU needed); icar_halo_send / icar_halo_retrieve use the same plan. */
 int icar_halo_plan(const icar_grid* grid, int image, int nimages, int plan[8]);
 
-/* ncclUniqueId bootstrap: image 1 calls icar_comm_unique_id and broadcasts the 128 bytes with
- * whatever the host program already has (coarray co_broadcast, MPI, torch.distributed); then
- * every image calls icar_comm_init.  Replaces exchangeable_t%set_neighbors
- * (exchangeable_obj.f90:68-118): neighbours are image-1 (west) and image+1 (east). */
+/* Connecting the images.  Replaces exchangeable_t%set_neighbors (exchangeable_obj.f90:68-118): neighbours are
+ * image-1 (west / south) and image+1 (east / north).
+ *
+ * The exchange is the reference's own pattern (exchangeable_obj.f90:249-356: coarray PUTs into the neighbour's
+ * halo buffers + `sync images`): icar_halo_send stores this image's boundary cells straight into the neighbours'
+ * ghost cells (peer-mapped device memory over NVLink, one kernel for all exchanged scalars and both sides) and raises
+ * a flag there; icar_halo_retrieve waits for the neighbours' flags.  No message layer is on that path.
+ *
+ * One process per image (one GPU each, all on one box): image 1 calls icar_comm_unique_id and broadcasts the 128
+ * bytes with whatever the host program already has (coarray co_broadcast, MPI, torch.distributed); then every image
+ * calls icar_comm_init, which builds the NCCL communicator (used for the co_min of update_dt, icar_compute_dt) and
+ * maps the neighbours' memory with CUDA IPC.
+ *
+ * All images in one process (one host thread driving several contexts, on one or several GPUs): icar_comm_init_local
+ * with the contexts in image order.  There is no communicator then: icar_compute_dt returns the image's own time step
+ * and the caller takes the minimum.  The caller must queue the step of every image before it waits for any of them;
+ * with several images on ONE device, CUDA_DEVICE_MAX_CONNECTIONS must be at least 3 x the number of contexts on it
+ * (an image's kernels wait on the device for its neighbours', so their streams must not share a hardware queue). */
 int icar_comm_unique_id(char id[128]);
 int icar_comm_init(icar_ctx* ctx, int image, int nimages, const char id[128]);
+int icar_comm_init_local(icar_ctx** ctxs, int nimages);
 
 /* ------------------------------------------------- host-pointer leaf calls (stateless) */
 

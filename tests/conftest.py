@@ -3,6 +3,11 @@ import sys
 
 import pytest
 
+# tests/test_gpu_local_images.py runs several images of a decomposition as contexts of ONE process on ONE device; an
+# image's kernels wait on the device for its neighbours', so their streams must not share a hardware work queue (the
+# default of 8 connections is fewer than the 3 streams x 3 contexts of those tests).  Read when CUDA initialises.
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)

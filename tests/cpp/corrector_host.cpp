@@ -174,7 +174,7 @@ int emu_corrector(int np, int nzp, int stages, int nx, int nz, int ny, int ld, i
     if (smem > 232448) return 2;                                      // 227 KB of shared memory per CTA
     const int xtiles = nx / TOUT + 1, planes = ny - 2;
     const unsigned gx = (unsigned)(xtiles * n), gy = (unsigned)((planes + chunk - 1) / chunk);
-#define CASE(N, Z, S) if (np == N && nzp == Z && stages == S) { run_grid(gx, gy, nzt, smem, [&] { k_corrector_fused<N, Z, S>(g, outs, maps, chunk); }); return 0; }
+#define CASE(N, Z, S) if (np == N && nzp == Z && stages == S) { run_grid(gx, gy, nzt, smem, [&] { k_corrector_fused<N, Z, S>(g, outs, maps, chunk, OutRange{1, nx - 1, 1, ny - 1}); }); return 0; }
     CASE(1, 20, 2)
     CASE(1, 40, 2)
     CASE(2, 48, 2)
