@@ -15,8 +15,11 @@ cell advanced one step through the microphysics and the MPDATA of all 5 advected
            out, H2D/D2H inside the timed region.
   roofline ALGORITHMIC bytes (128 B per cell-update for mp_simple +
            MPDATA x 5 scalars) / measured time, against the measured HBM copy peak.
-  cpu_baseline  the oracle (CPU restatement of the reference Fortran, "port") timed on this
-           box's host cores on a bounded sample (rank 0, N=1 only).
+  cpu_baseline  the oracle (CPU restatement of the reference Fortran, "port"), rebuilt on this box with the
+           reference's own compiler flags, timed on the host cores on a bounded sample (rank 0, N=1 only).
+  parity   (N=1) the product against the strict oracle, in this process, outside the timed region: BASELINE config 1
+           (100x100x20, 20 steps) and two steps of the benchmark state itself, per field.
+  decomposition_check  (N>1) every rank re-runs two steps on the undivided domain and compares the cells it owns.
 
 --impl reference times that CPU restatement with all host threads instead (the reference
 Fortran itself cannot be built: no Fortran compiler in the image).
@@ -31,6 +34,10 @@ import sys
 import threading
 import time
 
+# torchrun exports OMP_NUM_THREADS=1; the CPU legs set their own thread count.  Read by CUDA when it initialises: the
+# e2e pipeline drives several contexts from one process.
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -41,17 +48,15 @@ METRIC = "grid_cell_updates_per_s"
 UNIT = "cell-updates/s"
 # bytes per cell-update, SURVEY.md section 8d: mp_simple 56 B + MPDATA S=5 72 B; Thompson 84 B + MPDATA S=9 104 B
 # Algorithmic bytes per cell and launch of each kernel family (distinct fields read + written
-# once, 4 B each; S = advected scalars) and the DRAM traffic one launch moved at 512x512x40 in the committed
-# `ncu --set full` captures (profiles/r1_v11_top_kernels.txt, profiles/r1_thompson_v3.txt), in bytes.
+# once, 4 B each; S = advected scalars).
 KERNEL_BYTES = {
     "k_mp_simple": lambda S: 56.0, "k_mp_thompson": lambda S: 84.0, "k_wind_normalise": lambda S: 44.0,
-    "k_face_coefficients": lambda S: 64.0, "k_upwind_all": lambda S: 20.0 + 8.0 * S,
-    "k_corrector_fused": lambda S: 44.0 + 12.0 * S,
+    "k_face_coefficients": lambda S: 56.0, "k_upwind_all": lambda S: 20.0 + 8.0 * S,
+    "k_corrector_fused": lambda S: 48.0 + 12.0 * S,
 }
-NCU_TRAFFIC_512 = {("k_corrector_fused", 5): 1142.5e6, ("k_mp_simple", 5): 620.0e6, ("k_upwind_all", 5): 620.0e6,
-                   # Thompson: 0.68 GB of field reads + 11.4 GB of writes, almost all of it register spills around
-                   # the out-of-line math calls (profiles/r1_thompson_v3.txt)
-                   ("k_mp_thompson", 9): 12056.0e6}
+# DRAM bytes and executed instructions of one launch of each kernel SYMBOL, from the committed `ncu --set full`
+# captures (scripts/ncu_kernels_json.py); used only when the symbol and the tile are the ones timed here
+NCU_KERNELS = os.path.join(ROOT, "profiles", "ncu_kernels.json")
 SCHEMES = {
     "simple": dict(mp=2, b_alg=128.0, scalars=("th", "qv", "qc", "qr", "qs"), acc=("precipitation", "snowfall"),
                    workload="ideal hill {nx}x{ny}x{nz}, MPDATA order2+FCT, mp_simple (BASELINE configs[1])"),
@@ -239,6 +244,8 @@ def run_reference(args, rank, world):
     # bounded sample: a y-band of the workload sized so that K+W steps end within minutes
     st = make_state(args)
     dt = float(st["dt"])
+    from oracle import oracle as O0
+    flags = O0.use_fast_build()                 # the restatement rebuilt on this host with the reference's own flags
     O, step = oracle_stepper(args)
     # all the host threads this process may use: torchrun exports OMP_NUM_THREADS=1 to its ranks, which would
     # time the reference on one core
@@ -281,7 +288,7 @@ def run_reference(args, rank, world):
         "config": {"workload": SCHEMES[args.mp]["workload"].format(nx=nx, ny=ny, nz=nz), "grid": [nx, nz, ny], "sample": sample,
                    "note": "CPU restatement (oracle port) of the reference Fortran; the Fortran itself "
                            "cannot be compiled in this image (no gfortran)"},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": thr, "kind": "port", "sample": sample,
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": thr, "kind": "port", "sample": sample, "flags": flags,
                          "cpu_model": host_cpu()[0], "host_logical_cores": host_cpu()[1]},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -290,6 +297,49 @@ def run_reference(args, rank, world):
 
 
 # --------------------------------------------------------------------------------------------
+def rel_to_max(a, b):
+    return float(np.abs(a.astype(np.float64) - b.astype(np.float64)).max() / max(float(np.abs(b).max()), 1e-30))
+
+
+def parity_record(args, icar_b200, ideal, st, dt, local_rank):
+    """The product against the STRICT oracle (the checker), in this process, outside the timed region."""
+    from oracle import oracle as O
+    O.build()
+    scheme = SCHEMES[args.mp]
+    rec = {"oracle": "oracle/ (C++ restatement of the reference Fortran, " + O.STRICT_FLAGS + "); unpinned: the reference "
+                     "ships no vectors for this path and cannot be compiled here"}
+    if args.mp == "simple":
+        # BASELINE config 1: the ideal hill case 100x100x20, 20 coupled steps
+        c1 = ideal.make_ideal_case(nx=100, nz=20, ny=100)
+        ref = ideal.copy_state(c1)
+        d1 = icar_b200.Domain(icar_b200.Grid.single_image(100, 20, 100), icar_b200.Options(dx=c1["dx"]), device=local_rank)
+        d1.upload_state(c1)
+        for _ in range(20):
+            d1.physics_step(float(c1["dt"]))
+            O.step_simple(ref, np.float32(c1["dt"]), np.float32(c1["dt"]), 2, True)
+        err = {k: rel_to_max(d1.download(k), ref[k]) for k in scheme["scalars"]}
+        same = {k: bool(np.array_equal(d1.download(k), ref[k])) for k in scheme["scalars"]}
+        d1.close()
+        rec["config1_100x100x20_20_steps"] = {"max_rel_err": err, "bitwise_equal": same, "tolerance": 1e-6,
+                                              "within_tolerance": bool(max(err.values()) <= 1e-6)}
+    # the benchmark state itself: two steps from the initial state
+    _, step = oracle_stepper(args)
+    ref = {k: (v.copy() if isinstance(v, np.ndarray) else v) for k, v in st.items()}
+    d2 = icar_b200.Domain(icar_b200.Grid.single_image(args.nx, args.nz, args.ny),
+                          icar_b200.Options(dx=st["dx"], microphysics=scheme["mp"]), device=local_rank)
+    d2.upload_state(st)
+    ny, nz, nx = ref["th"].shape
+    scratch = (np.empty((ny, nz, nx - 1), np.float32), np.empty((ny - 1, nz, nx), np.float32), np.empty((ny, nz, nx), np.float32))
+    for _ in range(2):
+        d2.physics_step(dt)
+        step(ref, dt, scratch)
+    err = {k: rel_to_max(d2.download(k), ref[k]) for k in scheme["scalars"]}
+    same = {k: bool(np.array_equal(d2.download(k), ref[k])) for k in scheme["scalars"]}
+    d2.close()
+    rec[f"workload_{nx}x{nz}x{ny}_2_steps"] = {"max_rel_err": err, "bitwise_equal": same}
+    return rec
+
+
 def run_b200(args, rank, world, local_rank):
     import torch
     import torch.distributed as dist
@@ -308,21 +358,27 @@ def run_b200(args, rank, world, local_rank):
     scheme = SCHEMES[args.mp]
     st = make_state(args)
     dt = float(st["dt"])
-    if distributed:
-        grid = (icar_b200.Grid.xslab if args.slabs == "x" else icar_b200.Grid.yslab)(nx, nz, ny, world, rank + 1, halo)
-        local = ideal.slab_of(st, grid)
-    else:
-        grid = icar_b200.Grid.single_image(nx, nz, ny, halo_size=1)
-        local = st
-    dom = icar_b200.Domain(grid, icar_b200.Options(dx=st["dx"], microphysics=scheme["mp"]), device=local_rank)
-    dom.upload_state(local)
-    if distributed:
-        ids = [icar_b200.comm_unique_id() if rank == 0 else None]
-        dist.broadcast_object_list(ids, src=0)
-        dom.comm_init(rank + 1, world, ids[0])
+    options = icar_b200.Options(dx=st["dx"], microphysics=scheme["mp"])
 
-    def barrier():
-        dom.synchronize()
+    def make_domain(slabs):
+        if distributed:
+            grid = (icar_b200.Grid.xslab if slabs == "x" else icar_b200.Grid.yslab)(nx, nz, ny, world, rank + 1, halo)
+            local = ideal.slab_of(st, grid)
+        else:
+            grid = icar_b200.Grid.single_image(nx, nz, ny, halo_size=1)
+            local = st
+        dom = icar_b200.Domain(grid, options, device=local_rank)
+        dom.upload_state(local)
+        if distributed:
+            ids = [icar_b200.comm_unique_id() if rank == 0 else None]
+            dist.broadcast_object_list(ids, src=0)
+            dom.comm_init(rank + 1, world, ids[0])
+        return dom, grid, local
+
+    dom, grid, local = make_domain(args.slabs)
+
+    def barrier(d=None):
+        (d or dom).synchronize()
         if distributed:
             dist.barrier()
         torch.cuda.synchronize()
@@ -335,6 +391,53 @@ def run_b200(args, rank, world, local_rank):
         return float(t.item())
 
     cells_global = nx * nz * ny
+
+    def timed_steps(d, steps, graph):
+        """W untimed steps, then `steps` timed ones: CUDA events on the library's compute stream, max over ranks."""
+        for _ in range(max(args.warmup, 3)):
+            d.physics_step(dt)
+        if graph:
+            d.physics_steps(dt, 2, graph=True)             # capture outside the timed region
+        barrier(d)
+        l0 = d.kernel_launches
+        d.timer_start()
+        if graph:
+            d.physics_steps(dt, steps, graph=True)         # pairs of steps replayed from a CUDA graph
+        else:
+            for _ in range(steps):
+                d.physics_step(dt)
+        ms = d.timer_stop()
+        barrier(d)
+        return max_over_ranks(ms) / steps, d.kernel_launches - l0
+
+    def decomposition_check(d, g, slabs, local_state):
+        """Two steps from the initial state on this rank's slab (with its neighbours) and on the undivided domain (alone,
+        on this rank's GPU): the cells the rank owns must be equal bit for bit."""
+        one = icar_b200.Domain(icar_b200.Grid.single_image(nx, nz, ny), options, device=local_rank)
+        one.upload_state(st)
+        d.upload_state(local_state)
+        for _ in range(2):
+            one.physics_step(dt)
+            d.physics_step(dt)
+        d.synchronize()
+        if slabs == "x":
+            lo = 0 if rank == 0 else g.its - g.ims
+            hi = g.nx if rank == world - 1 else g.ite - g.ims + 1
+            g0 = g.ims - 1 + lo
+            own, ref = (lambda a: a[..., lo:hi]), (lambda a: a[..., g0:g0 + (hi - lo)])
+        else:
+            lo = 0 if rank == 0 else g.jts - g.jms
+            hi = g.ny if rank == world - 1 else g.jte - g.jms + 1
+            g0 = g.jms - 1 + lo
+            own, ref = (lambda a: a[lo:hi]), (lambda a: a[g0:g0 + (hi - lo)])
+        fields = scheme["scalars"] + scheme["acc"]
+        bad = [k for k in fields if not np.array_equal(own(d.download(k)), ref(one.download(k)))]
+        one.close()
+        t = torch.tensor([len(bad)], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t)
+        return {"bitwise_equal": bool(t.item() == 0), "fields": len(fields), "steps": 2, "ranks": world,
+                "mismatching_field_comparisons": int(t.item()),
+                "what": "cells each rank owns vs. the same steps on the undivided domain"}
 
     # ---------------- optional: what update_winds does once per forcing interval (BASELINE configs[4]: "full step incl.
     # linear_winds"): linear-theory perturbation of u, v for the background flow, then balance_uvw; timed on its own
@@ -368,26 +471,10 @@ def run_b200(args, rank, world, local_rank):
                                ", cuFFT Z2Z, + icar_balance_uvw; once per forcing interval, not inside the timed steps"}
 
     # ---------------- device-resident timing
-    for _ in range(max(args.warmup, 3)):
-        dom.physics_step(dt)
-    if args.graph:
-        dom.physics_steps(dt, 2, graph=True)               # capture outside the timed region
-    barrier()
     sampler = ClockSampler(physical_device(local_rank))
-    launches0 = dom.kernel_launches
     sampler.start()
-    dom.timer_start()
-    if args.graph:
-        dom.physics_steps(dt, args.steps, graph=True)      # pairs of steps replayed from a CUDA graph
-    else:
-        for _ in range(args.steps):
-            dom.physics_step(dt)
-    ms = dom.timer_stop()
-    barrier()
+    ms_per_step, launches = timed_steps(dom, args.steps, args.graph)
     clocks = sampler.stop()
-    launches = dom.kernel_launches - launches0
-    ms = max_over_ranks(ms)
-    ms_per_step = ms / args.steps
     value = cells_global / (ms_per_step * 1e-3)
 
     # ---------------- per-kernel timing (CUDA events around every launch, on the launching stream) for the
@@ -399,18 +486,20 @@ def run_b200(args, rank, world, local_rank):
     prof = dom.profile_read()
     dom.profile_enable(False)
     barrier()
+    fused_symbol = dom.fused_kernel_name
 
     # ---------------- end-to-end timing: host arrays in, host arrays out
+    derive = not args.upload_diagnostics
     host = {k: (np.ascontiguousarray(v) if isinstance(v, np.ndarray) else v) for k, v in local.items()}
     for k in scheme["scalars"] + scheme["acc"]:
         host[k] = dom.download(k)
-    if args.derive_diagnostics:
+    if derive:
         # exner and density are taken on the device from pressure and potential temperature (icar_step_host)
         host = {k: v for k, v in host.items() if k not in ("pii", "rho")}
     hd = dom.host_domain(host)
     dom.host_register(hd)
-    host_step = dom.step_host if args.derive_diagnostics else dom.physics_step_host
-    in_keys = ("u", "v", "w", "pressure") + (() if args.derive_diagnostics else ("pii", "rho")) + scheme["scalars"] + scheme["acc"]
+    host_step = dom.step_host if derive else dom.physics_step_host
+    in_keys = ("u", "v", "w", "pressure") + (() if derive else ("pii", "rho")) + scheme["scalars"] + scheme["acc"]
     out_keys = scheme["scalars"] + scheme["acc"]
     h2d = int(sum(host[k].nbytes for k in in_keys))
     d2h = int(sum(host[k].nbytes for k in out_keys))
@@ -420,8 +509,7 @@ def run_b200(args, rank, world, local_rank):
         # the same step pipelined over bands of rows (icar_b200/pipeline.py): upload of the next band, kernels
         # of this one and download of the previous one overlap.  Inputs and outputs are different host arrays.
         from icar_b200.pipeline import HostPipeline
-        pipe = HostPipeline(local, icar_b200.Options(dx=st["dx"], microphysics=scheme["mp"]),
-                            bands=args.e2e_bands, device=local_rank, derive_diagnostics=args.derive_diagnostics)
+        pipe = HostPipeline(local, options, bands=args.e2e_bands, device=local_rank, derive_diagnostics=derive)
         other = {k: np.ascontiguousarray(host[k].copy()) for k in out_keys}
         hd_other = dom.host_domain(other)
         dom.host_register(hd_other)
@@ -434,8 +522,9 @@ def run_b200(args, rank, world, local_rank):
             src, dst = sets[_n[0] % 2], sets[(_n[0] + 1) % 2]
             pipe.step(dt_, src, {k: dst[k] for k in out_keys})
             _n[0] += 1
-        e2e_api = (f"icar_physics_step_host_io over {n_bands} bands of rows, 4 ghost rows, one context and host thread "
-                   "per band (icar_b200.pipeline.HostPipeline; pinned host arrays, inputs and outputs swapped every step)")
+        e2e_api = (f"icar_b200.pipeline.HostPipeline: icar_physics_step_host_io over {n_bands} bands of rows, 4 ghost rows, one "
+                   "context and host thread per band (pinned host arrays, inputs and outputs swapped every step"
+                   + ("; exner / density derived on the device)" if derive else ")"))
     for _ in range(2):
         host_step(dt, hd)
     barrier()
@@ -456,11 +545,28 @@ def run_b200(args, rank, world, local_rank):
         h2d, d2h = int(t[0].item()), int(t[1].item())
     diag = dom.mp_diagnostics()
 
-    # ---------------- CPU baseline (rank 0, N=1 only)
+    # ---------------- correctness inside the driver-run artefact
+    parity = decomp = other_axis = None
+    if distributed:
+        decomp = decomposition_check(dom, grid, args.slabs, local)
+        if not args.no_other_axis:
+            # the other decomposition axis once (north_star prescribes x; y keeps full-width rows and contiguous planes)
+            oax = "x" if args.slabs == "y" else "y"
+            dom.close()
+            dom, grid, local = make_domain(oax)
+            oms, _ = timed_steps(dom, max(10, args.steps // 2), args.graph)
+            other_axis = {"slabs": oax, "ms_per_step": oms, "value": cells_global / (oms * 1e-3),
+                          "decomposition_check": decomposition_check(dom, grid, oax, local)}
+    elif rank == 0 and not args.no_parity:
+        parity = parity_record(args, icar_b200, ideal, st, dt, local_rank)
+
+    # ---------------- CPU baseline (rank 0, N=1 only): the restatement built with the reference's own flags
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from oracle import oracle as O
+        flags = O.use_fast_build()
         rate, csteps, csec, thr = cpu_oracle_rate(args, st, dt, min_seconds=10.0, max_steps=5)
-        cpu = {"value": rate, "unit": UNIT, "cores": thr, "kind": "port",
+        cpu = {"value": rate, "unit": UNIT, "cores": thr, "kind": "port", "flags": flags,
                "sample": f"{csteps} full step(s) of the same {nx}x{nz}x{ny} workload, {csec:.1f} s, "
                          f"OpenMP over j with {thr} threads (oracle/: C++ restatement of the Fortran)"}
         cpu["cpu_model"], cpu["host_logical_cores"] = host_cpu()
@@ -484,6 +590,51 @@ def run_b200(args, rank, world, local_rank):
             e["achieved_gbs"] = per_step_bytes / (kms / args.steps * 1e-3) / 1e9
         kernels[name] = e
     dominant = max(kernels, key=lambda k: kernels[k]["ms_per_step"]) if kernels else None
+
+    # ---------------- what the committed ncu captures say about the kernels timed here: DRAM traffic of the dominant
+    # kernel (only if the capture is of the SAME symbol on the same tile) and the issue ceiling of the step
+    try:
+        with open(NCU_KERNELS) as f:
+            ncu = json.load(f)
+    except Exception:
+        ncu = {}
+
+    def captured(family):
+        want = fused_symbol if family == "k_corrector_fused" else None
+        for sym, rec in ncu.items():
+            if rec.get("tile_cells") != cells_local or not sym.startswith(family):
+                continue
+            if want is None or sym == want:
+                return sym, rec
+        return None, None
+
+    traffic = traffic_src = None
+    if dominant and not distributed:
+        sym, rec = captured(dominant)
+        if rec:
+            traffic = rec["dram_bytes_per_launch"]
+            traffic_src = {"capture": "profiles/" + rec["capture"], "symbol": sym,
+                           "timed_symbol": fused_symbol if dominant == "k_corrector_fused" else dominant}
+    alu = None
+    if not distributed:
+        per_cell, missing = {}, []
+        for fam in kernels:
+            sym, rec = captured(fam)
+            if rec:
+                per_cell[sym] = rec["lane_instructions_per_cell"]
+            else:
+                missing.append(fam)
+        if per_cell:
+            sms = torch.cuda.get_device_properties(local_rank).multi_processor_count
+            mhz = clocks.get("sm_mhz") or clocks.get("sm_max_mhz") or 1965
+            rate = sms * 128 * mhz * 1e6
+            total = sum(per_cell.values())
+            alu = {"lane_instructions_per_cell": per_cell, "total_per_cell_update": total,
+                   "issue_rate_lane_instructions_per_s": rate, "floor_ms_per_step": total * cells_local / rate * 1e3,
+                   "frac_of_issue_ceiling": (total * cells_local / rate * 1e3) / ms_per_step,
+                   "not_captured": missing,
+                   "note": "executed warp instructions x 32 / cells from the committed ncu captures; 128 lanes x SMs x "
+                           "SM clock.  f32x2 instructions count once here but occupy the FMA pipe for two cycles."}
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -491,7 +642,10 @@ def run_b200(args, rank, world, local_rank):
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": scheme["workload"].format(nx=nx, ny=ny, nz=nz), "grid": [nx, nz, ny], "dt_s": dt,
                        "advected_scalars": len(scheme["scalars"]),
-                       "decomposition": (f"{args.slabs}-slabs over {world} GPUs, halo {halo}, NCCL send/recv" if distributed
+                       "arithmetic": "the reference's IEEE binary32 operations in the reference's order (advection and "
+                                     "mp_simple bit-identical to the oracle); there is no other mode",
+                       "decomposition": (f"{args.slabs}-slabs over {world} GPUs, halo {halo}, boundary cells stored into the "
+                                         "neighbours' ghost cells over NVLink (CUDA IPC), no message layer" if distributed
                                          else "single image"),
                        "l2": "resident working set ~1.1 GB per step > 126 MB L2, no explicit flush",
                        "mp_diagnostics": list(diag),
@@ -500,19 +654,20 @@ def run_b200(args, rank, world, local_rank):
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": e2e_steps, "ms_per_step": e2e_s / e2e_steps * 1e3,
                     "api": e2e_api or ("icar_step_host (pinned host arrays; exner / density derived on the device)"
-                                       if args.derive_diagnostics else "icar_physics_step_host (pinned host arrays)")},
+                                       if derive else "icar_physics_step_host (pinned host arrays)")},
             "gpu_launches": int(launches),
-            # the dominant kernel, timed live with CUDA events (rank 0's tile); `traffic` = DRAM bytes of one
-            # launch from the committed ncu --set full capture (only known for the default 512x512x40 tile)
-            "roofline": ({"bound": "hbm", "kernel": dominant, "achieved": kernels[dominant].get("achieved_gbs"),
+            # the dominant kernel, timed live with CUDA events (rank 0's tile); `traffic` = DRAM bytes of one launch
+            # from the committed ncu --set full capture of the same symbol on the same tile, else null
+            "roofline": ({"bound": "hbm", "kernel": dominant, "symbol": fused_symbol if dominant == "k_corrector_fused" else dominant,
+                          "achieved": kernels[dominant].get("achieved_gbs"),
                           "peak": peak, "unit": "GB/s",
                           "frac": (kernels[dominant]["achieved_gbs"] / peak) if "achieved_gbs" in kernels[dominant] else None,
-                          "traffic": (NCU_TRAFFIC_512.get((dominant, S)) if (grid.nx, grid.nz, grid.ny) == (512, 40, 512) else None),
+                          "traffic": traffic, "traffic_source": traffic_src,
                           "algorithmic_bytes_per_launch": kernels[dominant].get("algorithmic_bytes_per_cell", 0) * cells_local,
                           "avg_launch_us": kernels[dominant]["ms_per_step"] * 1e3,
                           "share_of_step": kernels[dominant]["ms_per_step"] / sum(k["ms_per_step"] for k in kernels.values()),
                           "peak_source": peak_src,
-                          "note": "issue-bound, not HBM-bound: see DESIGN.md section 3 (instruction counts per cell)"}
+                          "note": "issue-bound, not HBM-bound: see alu_ceiling and DESIGN.md section 3"}
                          if dominant else None),
             # the BASELINE metric's own figure: whole step on the algorithmic bytes of SURVEY.md section 8d
             "step_roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
@@ -520,6 +675,14 @@ def run_b200(args, rank, world, local_rank):
                               "algorithmic_bytes_per_cell_update": B_ALG},
             "kernels": kernels,
         }
+        if alu:
+            line["alu_ceiling"] = alu
+        if parity:
+            line["parity"] = parity
+        if decomp:
+            line["decomposition_check"] = decomp
+        if other_axis:
+            line["xslab" if other_axis["slabs"] == "x" else "yslab"] = other_axis
         if cpu:
             line["cpu_baseline"] = cpu
         if linear_winds:
@@ -544,14 +707,17 @@ def main():
     ap.add_argument("--slabs", default="y", choices=["x", "y"],
                     help="decomposition axis for N>1 (y keeps full-width rows and contiguous halo planes)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--derive-diagnostics", action="store_true",
-                    help="e2e through icar_step_host: exner and density are not uploaded but derived on the device "
-                         "(diagnostic_update), as step()'s loop does before the physics")
-    ap.add_argument("--e2e-bands", type=int, default=1,
-                    help="e2e pipelined over this many bands of rows (icar_b200/pipeline.py); 1 = the plain host step")
+    ap.add_argument("--upload-diagnostics", action="store_true",
+                    help="e2e: upload exner and density with the other host arrays (icar_physics_step_host) instead of "
+                         "deriving them on the device from pressure and potential temperature (diagnostic_update, what "
+                         "step()'s loop does before the physics; the default)")
+    ap.add_argument("--e2e-bands", type=int, default=8,
+                    help="e2e pipelined over this many bands of rows (icar_b200/pipeline.py; N=1 only); 1 = the plain host step")
+    ap.add_argument("--no-parity", action="store_true", help="skip the oracle comparison (N=1) after the timed region")
+    ap.add_argument("--no-other-axis", action="store_true", help="N>1: do not also time the other decomposition axis")
     ap.add_argument("--linear-winds", nargs="?", const="direct", default=None, choices=["direct", "spatial"],
                     help="before the steps, run the once-per-forcing-interval wind update (icar_linear_perturb + "
-                         "icar_balance_uvw) and report its time under `linear_winds` (not yet run on hardware)")
+                         "icar_balance_uvw) and report its time under `linear_winds`")
     ap.add_argument("--graph", action="store_true",
                     help="run the timed steps through icar_physics_steps (CUDA-graph replay) instead of one "
                          "icar_physics_step call per step")

@@ -162,7 +162,7 @@ SYMBOLS = (
     "icar_upload", "icar_download", "icar_device_ptr", "icar_set_model_time", "icar_get_model_time",
     "icar_advect", "icar_mp", "icar_halo_send", "icar_halo_retrieve", "icar_halo_exchange",
     "icar_physics_step", "icar_physics_steps", "icar_synchronize", "icar_mp_diagnostics", "icar_kernel_launches",
-    "icar_selftest_division",
+    "icar_selftest_division", "icar_fused_kernel_name",
     "icar_timer_start", "icar_timer_stop",
     "icar_halo_plan", "icar_comm_unique_id", "icar_comm_init", "icar_comm_init_local", "icar_mpdata_set_winds", "icar_mpdata_advect3d",
     "icar_mpdata_set_winds_f64", "icar_mpdata_advect3d_f64", "icar_mp_simple_driver",
@@ -434,6 +434,12 @@ class Domain:
     @property
     def kernel_launches(self):
         return int(lib().icar_kernel_launches(self._h))
+
+    @property
+    def fused_kernel_name(self) -> str:
+        buf = C.create_string_buffer(64)
+        self._check(lib().icar_fused_kernel_name(self._h, buf))
+        return buf.value.decode()
 
     def selftest_division(self, a, b):
         """(div2x(a, b), a / b) evaluated on the device for two float32 arrays of the same even size."""

@@ -658,6 +658,16 @@ extern "C" int icar_mp_diagnostics(icar_ctx* ctx, long long out[3]) {
 
 extern "C" long long icar_kernel_launches(const icar_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
+extern "C" int icar_fused_kernel_name(icar_ctx* ctx, char name[64]) {
+    if (!ctx || !name) return ICAR_ERR_INVALID;
+    name[0] = 0;
+    if (!ctx->fused) return ICAR_OK;                       // the staged kernels serve this configuration
+    CU(cudaSetDevice(ctx->device));
+    const FusedPlan p = fused_plan(ctx->g);
+    std::snprintf(name, 64, "k_corrector_fused<%d, %d, %d>", p.cpt / 2, p.nzp, p.stages);
+    return ICAR_OK;
+}
+
 extern "C" int icar_selftest_division(icar_ctx* ctx, const float* a, const float* b, float* packed, float* ieee, long long n) {
     if (!ctx || !a || !b || !packed || !ieee || n <= 0 || (n & 1)) return ICAR_ERR_INVALID;
     CU(cudaSetDevice(ctx->device));

@@ -321,6 +321,12 @@ int icar_mp_diagnostics(icar_ctx* ctx, long long out[3]);
 /* Number of CUDA kernels this context has launched since creation. */
 long long icar_kernel_launches(const icar_ctx* ctx);
 
+/* The instantiation of the fused MPDATA corrector that serves this context's tile, as ncu prints it
+ * ("k_corrector_fused<1, 40, 2>": pairs of levels per thread, level slots, TMA stages), or "" when the staged
+ * kernels do (mpdata_order != 2, FCT off, advect_density, exact_arithmetic, more than 64 levels).  bench.py uses it to
+ * match its roofline line with the committed ncu capture of the same symbol. */
+int icar_fused_kernel_name(icar_ctx* ctx, char name[64]);
+
 /* Self-test of the division the fused MPDATA corrector uses (csrc/corrector_prims.inc: div2x, the fast path of the
  * compiler's own div.rn.f32 on f32x2 pairs): packed[i] = div2x(a[i], b[i]) and ieee[i] = a[i] / b[i] for n (even) host
  * floats.  The reference divides with the Fortran `/` (adv_mpdata.f90:129-251, adv_mpdata_FCT_core.f90:103-114); the

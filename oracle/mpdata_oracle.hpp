@@ -111,10 +111,13 @@ void upwind_advection(const R* qin, const R* u, const R* v, const R* w, const R*
                       const R* dz, int nx, int nz, int ny, const R* jaco) {
     Dims<R> d{nx, nz, ny};
     std::memcpy(q, qin, d.cells() * sizeof(R));                       // :63-65
-#pragma omp parallel for schedule(static)
+#pragma omp parallel
+    {
+    // the per-plane temporaries f1, f3, f4, f5 of the Fortran (:54-57), one set per thread
+    std::vector<R> f1((size_t)(nx - 1) * nz), f3((size_t)(nx - 2) * nz),
+        f4((size_t)(nx - 2) * nz), f5((size_t)(nx - 2) * (nz > 1 ? nz - 1 : 0));
+#pragma omp for schedule(static)
     for (int j = 1; j < ny - 1; ++j) {                                  // :70
-        std::vector<R> f1((size_t)(nx - 1) * nz), f3((size_t)(nx - 2) * nz),
-            f4((size_t)(nx - 2) * nz), f5((size_t)(nx - 2) * (nz > 1 ? nz - 1 : 0));
         for (int k = 0; k < nz; ++k) {
             for (int f = 0; f < nx - 1; ++f)                            // :74-75
                 f1[f + (size_t)(nx - 1) * k] =
@@ -148,6 +151,7 @@ void upwind_advection(const R* qin, const R* u, const R* v, const R* w, const R*
                 }
                 q[c] = val;
             }
+    }
     }
 }
 

@@ -34,6 +34,20 @@ def build(force: bool = False) -> str:
 
 
 _lib = None
+FAST_FLAGS = "-O2 -mfma -ftree-vectorize -funroll-loops -march=native (the reference's own, src/makefile:159), OpenMP"
+STRICT_FLAGS = "-O2 -ffp-contract=off -fno-fast-math, OpenMP"
+
+
+def use_fast_build() -> str:
+    """FOR TIMING ONLY (bench.py's cpu_baseline / --impl reference legs): rebuilds the restatement on THIS host with the
+    flags the reference builds itself with (oracle/Makefile, target `fast`) and routes every later call of this module
+    through it.  Results are then no longer bit-identical to the strict build, which is the checker."""
+    global _lib, _SO
+    fast = os.path.join(_HERE, "_build", "libicar_oracle_fast.so")
+    subprocess.check_call(["make", "-C", _HERE, "-B", "fast"], stdout=subprocess.DEVNULL)
+    _SO = fast
+    _lib = None
+    return FAST_FLAGS
 
 
 def lib() -> C.CDLL:
