@@ -110,8 +110,9 @@ struct icar_ctx {
     // Thompson's module array SR (mp_driver.f90:440)
     float* sr2d = nullptr;
     cudaStream_t aux = nullptr;      // the ring strips of mp(halo) run here, next to mp(subset)
-    cudaEvent_t ev_fork = nullptr, ev_aux = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_aux = nullptr, ev_winds = nullptr;
     bool aux_pending = false;        // ring strips still running on the aux stream
+    bool winds_pending = false;      // the wind-only part of advect() still running on the aux stream (next to mp())
     unsigned long long* diag = nullptr;
     std::vector<void*> scratch;      // leaf-call staging buffers (float or double cells)
     std::vector<size_t> scratch_bytes;
@@ -370,6 +371,17 @@ int join_aux(icar_ctx* ctx) {
     return ICAR_OK;
 }
 
+// The wind-only part of advect() (wind normalisation, face coefficients) reads u, v, w and the metric and writes the
+// module arrays U_m, V_m, W_m and the coefficient planes: nothing mp() touches.  icar_physics_step queues it on the
+// auxiliary stream, where these HBM-bound kernels run next to the issue-bound microphysics kernel, and joins it here
+// before the scalars are advected.
+int join_winds(icar_ctx* ctx) {
+    if (!ctx->winds_pending) return ICAR_OK;
+    CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_winds, 0));
+    ctx->winds_pending = false;
+    return ICAR_OK;
+}
+
 }  // namespace
 
 // ============================================================================ lifecycle
@@ -523,6 +535,7 @@ extern "C" int icar_create(int device, const icar_grid* grid, const icar_options
     CUB(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
     CUB(cudaStreamCreateWithPriority(&ctx->aux, cudaStreamNonBlocking, prio_hi));
     CUB(cudaEventCreateWithFlags(&ctx->ev_aux, cudaEventDisableTiming));
+    CUB(cudaEventCreateWithFlags(&ctx->ev_winds, cudaEventDisableTiming));
     CUB(cudaMalloc((void**)&ctx->diag, 3 * sizeof(unsigned long long)));
     CUB(cudaMemsetAsync(ctx->diag, 0, 3 * sizeof(unsigned long long), ctx->stream));
     CUB(cudaStreamSynchronize(ctx->stream));
@@ -570,6 +583,7 @@ extern "C" int icar_destroy(icar_ctx* ctx) {
     for (cudaEvent_t e : ctx->prof_pool) cudaEventDestroy(e);
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
     if (ctx->ev_aux) cudaEventDestroy(ctx->ev_aux);
+    if (ctx->ev_winds) cudaEventDestroy(ctx->ev_winds);
     if (ctx->aux) cudaStreamDestroy(ctx->aux);
     if (ctx->ev_packed) cudaEventDestroy(ctx->ev_packed);
     if (ctx->ev_comm) cudaEventDestroy(ctx->ev_comm);
@@ -592,7 +606,7 @@ extern "C" int icar_upload(icar_ctx* ctx, int var, const void* host) {
         return fail(ctx, ICAR_ERR_INVALID, "icar_upload between icar_halo_send and icar_halo_retrieve: the neighbours are writing this image's ghost cells");
     if (!ctx || !host || var < 0 || var >= ICAR_VAR_COUNT) return fail(ctx, ICAR_ERR_INVALID, "icar_upload: bad argument");
     CU(cudaSetDevice(ctx->device));
-    { int jr = join_aux(ctx); if (jr) return jr; }
+    { int jr = join_aux(ctx); if (jr) return jr; jr = join_winds(ctx); if (jr) return jr; }
     int width, pitch; size_t rows;
     var_geometry(ctx, var, &width, &pitch, &rows);
     int rc = copy_in(ctx, ctx->vars[var], host, width, pitch, rows, elem_size(var));
@@ -607,7 +621,7 @@ extern "C" int icar_download(icar_ctx* ctx, int var, void* host) {
         return fail(ctx, ICAR_ERR_INVALID, "icar_download between icar_halo_send and icar_halo_retrieve: the neighbours are writing this image's ghost cells");
     if (!ctx || !host || var < 0 || var >= ICAR_VAR_COUNT) return fail(ctx, ICAR_ERR_INVALID, "icar_download: bad argument");
     CU(cudaSetDevice(ctx->device));
-    { int jr = join_aux(ctx); if (jr) return jr; }
+    { int jr = join_aux(ctx); if (jr) return jr; jr = join_winds(ctx); if (jr) return jr; }
     int width, pitch; size_t rows;
     var_geometry(ctx, var, &width, &pitch, &rows);
     int rc = copy_out(ctx, host, ctx->vars[var], width, pitch, rows, elem_size(var));
@@ -639,7 +653,7 @@ extern "C" int icar_get_model_time(icar_ctx* ctx, double* seconds) {
 extern "C" int icar_synchronize(icar_ctx* ctx) {
     if (!ctx) return ICAR_ERR_INVALID;
     CU(cudaSetDevice(ctx->device));
-    { int jr = join_aux(ctx); if (jr) return jr; }
+    { int jr = join_aux(ctx); if (jr) return jr; jr = join_winds(ctx); if (jr) return jr; }
     CU(cudaStreamSynchronize(ctx->stream));
     CU(cudaStreamSynchronize(ctx->comm_stream));
     return ICAR_OK;
@@ -648,7 +662,7 @@ extern "C" int icar_synchronize(icar_ctx* ctx) {
 extern "C" int icar_mp_diagnostics(icar_ctx* ctx, long long out[3]) {
     if (!ctx || !out) return ICAR_ERR_INVALID;
     CU(cudaSetDevice(ctx->device));
-    { int jr = join_aux(ctx); if (jr) return jr; }
+    { int jr = join_aux(ctx); if (jr) return jr; jr = join_winds(ctx); if (jr) return jr; }
     unsigned long long h[3];
     CU(cudaMemcpyAsync(h, ctx->diag, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
@@ -698,7 +712,7 @@ extern "C" int icar_timer_start(icar_ctx* ctx) {
 extern "C" int icar_timer_stop(icar_ctx* ctx, float* elapsed_ms) {
     if (!ctx || !elapsed_ms) return ICAR_ERR_INVALID;
     CU(cudaSetDevice(ctx->device));
-    { int jr = join_aux(ctx); if (jr) return jr; }
+    { int jr = join_aux(ctx); if (jr) return jr; jr = join_winds(ctx); if (jr) return jr; }
     CU(cudaEventRecord(ctx->ev_t1, ctx->stream));
     CU(cudaEventSynchronize(ctx->ev_t1));
     CU(cudaEventElapsedTime(elapsed_ms, ctx->ev_t0, ctx->ev_t1));
@@ -709,10 +723,12 @@ extern "C" int icar_timer_stop(icar_ctx* ctx, float* elapsed_ms) {
 
 // part 0: the whole advect(); part 1: what depends on the winds only (wind normalisation, face
 // coefficients) -- a multi-image step queues it before it waits for the halo exchange; part 2: the scalars.
-int advect_impl(icar_ctx* ctx, float dt, int part) {
+int advect_impl(icar_ctx* ctx, float dt, int part, cudaStream_t winds_stream) {
     if (!ctx) return ICAR_ERR_INVALID;
     CU(cudaSetDevice(ctx->device));
-    if (part != 1) { int jr = join_aux(ctx); if (jr) return jr; }
+    if (part != 1) { int jr = join_aux(ctx); if (jr) return jr; jr = join_winds(ctx); if (jr) return jr; }
+    // part 1 may run on another stream (icar_physics_step: next to mp()); parts 0 and 2 run on the compute stream
+    cudaStream_t ws = (part == 1 && winds_stream) ? winds_stream : ctx->stream;
     if (ctx->opt.advection != 1 && ctx->opt.advection != 2)
         return ICAR_OK;   // advect() does nothing for other values (advection_driver.f90:67-71)
     int rc = need_uploaded(ctx, {ICAR_VAR_U, ICAR_VAR_V, ICAR_VAR_W, ICAR_VAR_JACOBIAN, ICAR_VAR_JACOBIAN_U,
@@ -726,18 +742,18 @@ int advect_impl(icar_ctx* ctx, float dt, int part) {
     const bool mpdata = (ctx->opt.advection == 2);
     // adv_mpdata.f90:500-506 / advect.f90:344-347
     if (part != 2) {
-        ProfScope ps(ctx, K_WIND_NORMALISE, ctx->stream);
+        ProfScope ps(ctx, K_WIND_NORMALISE, ws);
         ctx->launches += staged_wind_normalise<float>(
             g, (const float*)ctx->vars[ICAR_VAR_U], (const float*)ctx->vars[ICAR_VAR_V],
             (const float*)ctx->vars[ICAR_VAR_W], (const float*)ctx->vars[ICAR_VAR_JACOBIAN_U],
             (const float*)ctx->vars[ICAR_VAR_JACOBIAN_V], (const float*)ctx->vars[ICAR_VAR_JACOBIAN_W], rho, dt,
-            ctx->opt.dx, mpdata ? 2 : 1, ctx->U, ctx->V, ctx->W, ctx->stream, ctx->fused ? dz : nullptr,
+            ctx->opt.dx, mpdata ? 2 : 1, ctx->U, ctx->V, ctx->W, ws, ctx->fused ? dz : nullptr,
             ctx->fused ? ctx->Wn : nullptr);
     }
     const int order = mpdata ? ctx->opt.mpdata_order : 1;
     const float* G = jaco;          // jaco*rho with rho == 1 is jaco itself
     if (order > 1 && !ctx->fused) {
-        if (part != 2) ctx->launches += staged_wn_G<float>(g, ctx->W, dz, jaco, rho, ctx->Wn, rho ? ctx->G : nullptr, ctx->stream);
+        if (part != 2) ctx->launches += staged_wn_G<float>(g, ctx->W, dz, jaco, rho, ctx->Wn, rho ? ctx->G : nullptr, ws);
         if (rho) G = ctx->G;
     }
     if (ctx->fused) {
@@ -753,7 +769,7 @@ int advect_impl(icar_ctx* ctx, float dt, int part) {
         // a slab stores only the cells it owns: its ghost cells are refilled by the next exchange before anything reads them
         const icar_grid& gr = ctx->grid;
         const int own[4] = {gr.its - gr.ims, gr.ite - gr.ims + 1, gr.jts - gr.jms, gr.jte - gr.jms + 1};
-        const int nl = fused_advect_all(g, ss, ctx->U, ctx->V, ctx->W, ctx->Wn, jaco, dz, ctx->coef, ctx->stream,
+        const int nl = fused_advect_all(g, ss, ctx->U, ctx->V, ctx->W, ctx->Wn, jaco, dz, ctx->coef, ws,
                                         ctx->prof_on ? marks : nullptr, part, ctx->nimages > 1 ? own : nullptr);
         if (ctx->prof_on) {      // consecutive marks delimit the three kernels
             if (part == 1) {
@@ -772,7 +788,10 @@ int advect_impl(icar_ctx* ctx, float dt, int part) {
         if (nl < 0) return fail(ctx, ICAR_ERR_CUDA, "icar_advect: cannot set up the TMA tensor maps / shared memory of the fused MPDATA kernel");
         ctx->launches += nl;
         CU(cudaGetLastError());
-        if (part == 1) return ICAR_OK;
+        if (part == 1) {
+            if (ws != ctx->stream) { CU(cudaEventRecord(ctx->ev_winds, ws)); ctx->winds_pending = true; }
+            return ICAR_OK;
+        }
         for (int n = 0; n < ctx->nadv; ++n) {      // the output buffer becomes the field, the old field the next output
             float* old_field = (float*)ctx->vars[ctx->adv[n]];
             ctx->vars[ctx->adv[n]] = ctx->fout[n];
@@ -780,7 +799,10 @@ int advect_impl(icar_ctx* ctx, float dt, int part) {
         }
         return ICAR_OK;
     }
-    if (part == 1) return ICAR_OK;
+    if (part == 1) {
+        if (ws != ctx->stream) { CU(cudaEventRecord(ctx->ev_winds, ws)); ctx->winds_pending = true; }
+        return ICAR_OK;
+    }
     // adv_mpdata.f90:512-522: every scalar with vars_to_advect > 0 (mp_simple.f90:116-118)
     ProfScope ps_staged(ctx, K_STAGED_ADVECT3D, ctx->stream);
     for (int s = 0; s < ctx->nadv; ++s) {
@@ -797,7 +819,7 @@ int advect_impl(icar_ctx* ctx, float dt, int part) {
     return ICAR_OK;
 }
 
-extern "C" int icar_advect(icar_ctx* ctx, float dt) { return advect_impl(ctx, dt, 0); }
+extern "C" int icar_advect(icar_ctx* ctx, float dt) { return advect_impl(ctx, dt, 0, nullptr); }
 
 // ============================================================================ mp
 
@@ -809,7 +831,7 @@ extern "C" int icar_advect(icar_ctx* ctx, float dt) { return advect_impl(ctx, dt
 // Both phases together cover the tile exactly once, like process_halo + process_subdomain(subset).
 int mp_phase(icar_ctx* ctx, float dt_in, int phase, int axis, int h);
 int halo_send_from(icar_ctx* ctx, cudaStream_t producer);
-int advect_impl(icar_ctx* ctx, float dt, int part);
+int advect_impl(icar_ctx* ctx, float dt, int part, cudaStream_t winds_stream);
 
 extern "C" int icar_mp(icar_ctx* ctx, float dt_in, int halo, int subset) {
     if (!ctx) return ICAR_ERR_INVALID;
@@ -1087,7 +1109,7 @@ extern "C" int icar_halo_send(icar_ctx* ctx) {
     if (!ctx) return ICAR_ERR_INVALID;
     if (ctx->nimages == 1) return ICAR_OK;
     CU(cudaSetDevice(ctx->device));
-    { int jr = join_aux(ctx); if (jr) return jr; }
+    { int jr = join_aux(ctx); if (jr) return jr; jr = join_winds(ctx); if (jr) return jr; }
     return halo_send_from(ctx, ctx->stream);
 }
 
@@ -1140,8 +1162,18 @@ extern "C" int icar_physics_step(icar_ctx* ctx, float dt) {
     const int h = ctx->grid.halo_size;
     if (dt > 1e-3f) {                                             // time_step.f90:484
         if (ctx->nimages == 1) {
+            // the wind-only part of advect() goes to the auxiliary stream first: HBM-bound kernels next to the
+            // issue-bound microphysics kernel (they share no data)
+            if ((rc = join_aux(ctx))) return rc;
+            CU(cudaEventRecord(ctx->ev_fork, ctx->stream));
+            CU(cudaStreamWaitEvent(ctx->aux, ctx->ev_fork, 0));
+            if ((rc = advect_impl(ctx, dt, 1, ctx->aux))) return rc;
             // nothing to exchange: mp(halo=1) + mp(subset=1) of :512,:523 is one whole-tile call
             if ((rc = icar_mp(ctx, dt, -1, -1))) return rc;
+            if ((rc = advect_impl(ctx, dt, 2, nullptr))) return rc;   // :529
+            ctx->model_time += (double)dt;                            // :547
+            ++ctx->eager_steps;
+            return ICAR_OK;
         } else {
             int plan[8];
             if (icar_halo_plan(&ctx->grid, ctx->image, ctx->nimages, plan)) return fail(ctx, ICAR_ERR_INVALID, "icar_physics_step: not a slab decomposition");
@@ -1160,10 +1192,10 @@ extern "C" int icar_physics_step(icar_ctx* ctx, float dt) {
             }
             if ((rc = mp_phase(ctx, dt, 0, plan[6], h))) return rc;   // :512  the cells the neighbours need (aux stream)
             if ((rc = halo_send_from(ctx, ctx->aux))) return rc;      // :515  ordered after the strips only
+            if ((rc = advect_impl(ctx, dt, 1, ctx->aux))) return rc;  // the wind-only part of advect() needs no halo: behind the strips
             if ((rc = mp_phase(ctx, dt, 1, plan[6], h))) return rc;   // :523  everything else, overlapping the exchange
-            if ((rc = advect_impl(ctx, dt, 1))) return rc;            // the wind-only part of advect() needs no halo
             if ((rc = icar_halo_retrieve(ctx))) return rc;            // :526
-            if ((rc = advect_impl(ctx, dt, 2))) return rc;            // :529
+            if ((rc = advect_impl(ctx, dt, 2, nullptr))) return rc;   // :529
             ctx->model_time += (double)dt;                            // :547
             ++ctx->eager_steps;
             return ICAR_OK;
@@ -1201,7 +1233,7 @@ int graph_pair(icar_ctx* ctx, float dt, bool* ran) {
     icar_ctx::StepGraph& sg = ctx->sgraph;
     // the eager path has to have run first: it does the lazy allocations and sets the mp_dt lag up
     if (sg.unsupported || ctx->prof_on || ctx->eager_steps < 2 || ctx->last_model_time == -999.0 ||
-        ctx->aux_pending || ctx->exchange_in_flight)
+        ctx->aux_pending || ctx->winds_pending || ctx->exchange_in_flight)
         return ICAR_OK;
     bool runs[2]; float mp_dt[2]; double last = ctx->last_model_time, t = ctx->model_time;
     mp_schedule(ctx, t, last, dt, &runs[0], &mp_dt[0], &last);
@@ -1222,6 +1254,7 @@ int graph_pair(icar_ctx* ctx, float dt, bool* ran) {
         int rc = icar_physics_step(ctx, dt);
         if (!rc) rc = icar_physics_step(ctx, dt);
         if (!rc) rc = join_aux(ctx);
+        if (!rc) rc = join_winds(ctx);
         cudaGraph_t graph = nullptr;
         const cudaError_t ce = cudaStreamEndCapture(ctx->stream, &graph);      // always: leaves capture mode
         const long long pair_launches = ctx->launches - launches0;
@@ -1230,7 +1263,7 @@ int graph_pair(icar_ctx* ctx, float dt, bool* ran) {
         ctx->model_time = t0; ctx->last_model_time = last0; ctx->launches = launches0; ctx->eager_steps = eager0;
         std::memcpy(ctx->vars, vars0, sizeof(vars0)); std::memcpy(ctx->fout, fout0, sizeof(fout0));
         ctx->qa = qa0; ctx->qb = qb0;
-        ctx->aux_pending = false; ctx->exchange_in_flight = false;
+        ctx->aux_pending = false; ctx->winds_pending = false; ctx->exchange_in_flight = false;
         if (rc || ce != cudaSuccess || !graph) {
             if (graph) cudaGraphDestroy(graph);
             cudaGetLastError();
@@ -1683,7 +1716,7 @@ extern "C" int icar_mp_gt_driver(icar_ctx* ctx, float* qv, float* qc, float* qr,
 extern "C" int icar_profile_enable(icar_ctx* ctx, int on) {
     if (!ctx) return ICAR_ERR_INVALID;
     CU(cudaSetDevice(ctx->device));
-    { int jr = join_aux(ctx); if (jr) return jr; }
+    { int jr = join_aux(ctx); if (jr) return jr; jr = join_winds(ctx); if (jr) return jr; }
     CU(cudaStreamSynchronize(ctx->stream));
     CU(cudaStreamSynchronize(ctx->aux));
     for (auto& r : ctx->prof_pending) { if (r.kid >= 0) ctx->prof_pool.push_back(r.a); ctx->prof_pool.push_back(r.b); }
@@ -1697,7 +1730,7 @@ extern "C" int icar_profile_read(icar_ctx* ctx, int max_entries, char (*names)[3
                                  int* n_out) {
     if (!ctx || !names || !ms || !launches || !n_out) return fail(ctx, ICAR_ERR_INVALID, "icar_profile_read: null argument");
     CU(cudaSetDevice(ctx->device));
-    { int jr = join_aux(ctx); if (jr) return jr; }
+    { int jr = join_aux(ctx); if (jr) return jr; jr = join_winds(ctx); if (jr) return jr; }
     CU(cudaStreamSynchronize(ctx->stream));
     CU(cudaStreamSynchronize(ctx->aux));
     for (auto& r : ctx->prof_pending) {
@@ -1728,7 +1761,7 @@ extern "C" int icar_diagnostic_update(icar_ctx* ctx) {
     CU(cudaSetDevice(ctx->device));
     int rc = need_uploaded(ctx, {ICAR_VAR_PRESSURE, ICAR_VAR_POTENTIAL_TEMPERATURE}, "icar_diagnostic_update");
     if (rc) return rc;
-    { int jr = join_aux(ctx); if (jr) return jr; }
+    { int jr = join_aux(ctx); if (jr) return jr; jr = join_winds(ctx); if (jr) return jr; }
     ctx->launches += diagnostic_update_launch(ctx->g, (const float*)ctx->vars[ICAR_VAR_PRESSURE],
                                               (const float*)ctx->vars[ICAR_VAR_POTENTIAL_TEMPERATURE],
                                               (float*)ctx->vars[ICAR_VAR_EXNER], (float*)ctx->vars[ICAR_VAR_DENSITY],
@@ -1805,7 +1838,7 @@ extern "C" int icar_compute_dt(icar_ctx* ctx, const float* dz_levels, float cfl,
 extern "C" int icar_enforce_limits(icar_ctx* ctx) {
     if (!ctx) return ICAR_ERR_INVALID;
     CU(cudaSetDevice(ctx->device));
-    { int jr = join_aux(ctx); if (jr) return jr; }
+    { int jr = join_aux(ctx); if (jr) return jr; jr = join_winds(ctx); if (jr) return jr; }
     float* fields[ICAR_MAX_EXCHANGED];
     for (int s = 0; s < ctx->nexch; ++s) fields[s] = (float*)ctx->vars[ctx->exch[s]];
     ctx->launches += enforce_limits_launch(ctx->g, fields, ctx->nexch, ctx->stream);
@@ -1834,7 +1867,7 @@ extern "C" int icar_upload_tendency(icar_ctx* ctx, int var, const float* host) {
 extern "C" int icar_apply_forcing(icar_ctx* ctx, double dt_seconds) {
     if (!ctx) return ICAR_ERR_INVALID;
     CU(cudaSetDevice(ctx->device));
-    { int jr = join_aux(ctx); if (jr) return jr; }
+    { int jr = join_aux(ctx); if (jr) return jr; jr = join_winds(ctx); if (jr) return jr; }
     const icar_grid& gr = ctx->grid;
     // this%west_boundary = (ximg == 1) ... (domain_obj.f90:2211-2214): the tile touches that domain edge
     const bool edges[4] = {gr.ims == gr.ids, gr.ime == gr.ide, gr.jms == gr.jds, gr.jme == gr.jde};
@@ -1932,7 +1965,7 @@ extern "C" int icar_linear_perturb(icar_ctx* ctx, float U, float V, float Nsq, c
     CU(cudaSetDevice(ctx->device));
     int rc = need_uploaded(ctx, {ICAR_VAR_U, ICAR_VAR_V}, "icar_linear_perturb");
     if (rc) return rc;
-    { int jr = join_aux(ctx); if (jr) return jr; }
+    { int jr = join_aux(ctx); if (jr) return jr; jr = join_winds(ctx); if (jr) return jr; }
     const icar_grid& gr = ctx->grid;
     const Geom& g = ctx->g;
     int gnx = 0, gny = 0;
@@ -1993,7 +2026,7 @@ extern "C" int icar_linear_perturb_spatial(icar_ctx* ctx, const icar_lt_options*
     int rc = need_uploaded(ctx, {ICAR_VAR_U, ICAR_VAR_V, ICAR_VAR_POTENTIAL_TEMPERATURE, ICAR_VAR_EXNER, ICAR_VAR_WATER_VAPOR},
                            "icar_linear_perturb_spatial");
     if (rc) return rc;
-    { int jr = join_aux(ctx); if (jr) return jr; }
+    { int jr = join_aux(ctx); if (jr) return jr; jr = join_winds(ctx); if (jr) return jr; }
     icar_lt_options d;
     icar_default_lt_options(&d);
     if (opt) d = *opt;
@@ -2098,7 +2131,7 @@ extern "C" int icar_write_restart(icar_ctx* ctx, const char* path) {
     if (!ctx || !path) return fail(ctx, ICAR_ERR_INVALID, "icar_write_restart: bad argument");
     static_assert(sizeof(icar_grid) == 19 * sizeof(int), "icar_grid is 19 ints");
     CU(cudaSetDevice(ctx->device));
-    { int jr = join_aux(ctx); if (jr) return jr; }
+    { int jr = join_aux(ctx); if (jr) return jr; jr = join_winds(ctx); if (jr) return jr; }
     FILE* f = std::fopen(path, "wb");
     if (!f) return fail(ctx, ICAR_ERR_INVALID, std::string("icar_write_restart: cannot create ") + path);
     // the precipitation accumulators start at zero and are only ever written by the mp kernels: always saved
@@ -2147,7 +2180,7 @@ extern "C" int icar_write_restart(icar_ctx* ctx, const char* path) {
 extern "C" int icar_read_restart(icar_ctx* ctx, const char* path) {
     if (!ctx || !path) return fail(ctx, ICAR_ERR_INVALID, "icar_read_restart: bad argument");
     CU(cudaSetDevice(ctx->device));
-    { int jr = join_aux(ctx); if (jr) return jr; }
+    { int jr = join_aux(ctx); if (jr) return jr; jr = join_winds(ctx); if (jr) return jr; }
     FILE* f = std::fopen(path, "rb");
     if (!f) return fail(ctx, ICAR_ERR_INVALID, std::string("icar_read_restart: cannot open ") + path);
     RestartHeader h;

@@ -47,9 +47,6 @@ def source_mix(rep, kernel_id, cells):
     tot = sum(ops.values())
     if not tot:
         return
-    print(f"SASS warp-instructions executed: {tot}")
-    if cells:
-        print(f"lane-instructions per cell: {tot * 32 / cells:.1f}")
     print("opcode mix:")
     for op, n in ops.most_common(16):
         print(f"  {op:10s} {n / tot * 100:5.1f}%")
@@ -76,6 +73,9 @@ def main():
         print("top warp stall reasons (warps per issue-active cycle):")
         for v, k in stalls[:6]:
             print(f"  {k.split('issue_stalled_')[1].split('_per_issue')[0]:28s} {v:6.2f}")
+        if cells and "smsp__inst_executed.sum" in d:
+            inst = float(d["smsp__inst_executed.sum"][0].replace(",", ""))
+            print(f"warp instructions executed: {inst:.0f}   lane-instructions per cell: {inst * 32 / cells:.1f}")
         source_mix(rep, n, cells)
 
 

@@ -92,6 +92,7 @@ static inline void icar_emu_tma_load_box(void* dst, const CUtensorMap* m, uint64
 using std::max;
 using std::min;
 #define __grid_constant__
+#define __maxnreg__(n)
 #define ICAR_DYNAMIC_SMEM(name) unsigned char* name = icar_emu_smem
 
 namespace icar {
