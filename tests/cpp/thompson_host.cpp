@@ -36,6 +36,7 @@ using std::min;
 
 namespace icar {
 namespace {
+#define __grid_constant__
 #include "../../icar_b200/csrc/mp_thompson_kernel.inc"
 }  // namespace
 }  // namespace icar
