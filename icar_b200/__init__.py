@@ -158,7 +158,7 @@ _lib = None
 
 # every symbol include/icar_b200.h declares
 SYMBOLS = (
-    "icar_default_options", "icar_grid_xslab", "icar_grid_yslab", "icar_create", "icar_destroy", "icar_last_error",
+    "icar_default_options", "icar_device_count", "icar_grid_xslab", "icar_grid_yslab", "icar_create", "icar_destroy", "icar_last_error",
     "icar_upload", "icar_download", "icar_device_ptr", "icar_set_model_time", "icar_get_model_time",
     "icar_advect", "icar_mp", "icar_halo_send", "icar_halo_retrieve", "icar_halo_exchange",
     "icar_physics_step", "icar_physics_steps", "icar_synchronize", "icar_mp_diagnostics", "icar_kernel_launches",

@@ -595,6 +595,14 @@ extern "C" int icar_destroy(icar_ctx* ctx) {
     return ICAR_OK;
 }
 
+extern "C" int icar_device_count(int* n) {
+    if (!n) return ICAR_ERR_INVALID;
+    int c = 0;
+    if (cudaGetDeviceCount(&c) != cudaSuccess) { (void)cudaGetLastError(); c = 0; }
+    *n = c;
+    return ICAR_OK;
+}
+
 extern "C" const char* icar_last_error(const icar_ctx* ctx) {
     return ctx ? ctx->err.c_str() : g_create_error.c_str();
 }

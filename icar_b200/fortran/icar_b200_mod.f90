@@ -32,6 +32,7 @@ module icar_b200_mod
     public :: adv_init, adv_var_request, advect
     public :: mp_init, mp_var_request, mp
     public :: b200_halo_send, b200_halo_retrieve, b200_sync_to_host, b200_finalize, b200_physics_steps
+    public :: b200_diagnostic_update, b200_update_forcing, b200_apply_forcing, b200_enforce_limits, b200_upload_winds
     public :: b200_linear_perturb, b200_write_restart, b200_read_restart
 
     ! enum icar_var
@@ -154,6 +155,29 @@ module icar_b200_mod
             type(c_ptr), value :: ctx
             character(kind=c_char), intent(in) :: path(*)
         end function
+        integer(c_int) function icar_device_count(n) bind(c)
+            import :: c_int
+            integer(c_int), intent(out) :: n
+        end function
+        integer(c_int) function icar_diagnostic_update(ctx) bind(c)
+            import :: c_int, c_ptr
+            type(c_ptr), value :: ctx
+        end function
+        integer(c_int) function icar_enforce_limits(ctx) bind(c)
+            import :: c_int, c_ptr
+            type(c_ptr), value :: ctx
+        end function
+        integer(c_int) function icar_upload_tendency(ctx, var, host) bind(c)
+            import :: c_int, c_ptr
+            type(c_ptr), value :: ctx
+            integer(c_int), value :: var
+            type(c_ptr), value :: host
+        end function
+        integer(c_int) function icar_apply_forcing(ctx, dt_seconds) bind(c)
+            import :: c_int, c_ptr, c_double
+            type(c_ptr), value :: ctx
+            real(c_double), value :: dt_seconds
+        end function
         integer(c_int) function icar_halo_send(ctx) bind(c)
             import :: c_int, c_ptr
             type(c_ptr), value :: ctx
@@ -216,6 +240,7 @@ contains
         type(icar_grid)    :: g
         type(icar_options) :: o
         character(kind=c_char) :: id(128)
+        integer(c_int) :: ndev
 
         g%ims = domain%grid%ims; g%ime = domain%grid%ime; g%kms = domain%grid%kms; g%kme = domain%grid%kme
         g%jms = domain%grid%jms; g%jme = domain%grid%jme
@@ -235,8 +260,9 @@ contains
         o%top_mp_level    = options%mp_options%top_mp_level
         o%dx = domain%dx
 
-        ! one image = one GPU of the node
-        call check(icar_create(mod(this_image()-1, 8), g, o, ctx), "icar_create")
+        ! one image = one GPU of the node (images are placed on the node's devices round robin)
+        call check(icar_device_count(ndev), "icar_device_count")
+        call check(icar_create(mod(this_image()-1, max(ndev, 1_c_int)), g, o, ctx), "icar_create")
 
         if (num_images() > 1) then          ! x-slab decompositions only (yimages == 1)
             if (this_image() == 1) call check(icar_comm_unique_id(id), "icar_comm_unique_id")
@@ -284,14 +310,20 @@ contains
         if (c_associated(ctx)) call check(icar_thompson_init(ctx, mpo), "icar_thompson_init")
     end subroutine
 
-    !> uploads the fields the host side changes between steps (diagnostic_update, apply_forcing)
+    !> Resident mode.  The state (winds, pressure, scalars) is uploaded once, at the first mp() call; after that the
+    !! whole loop body of step() that touches it runs on the device, and the call sites of the reference that would
+    !! otherwise change the HOST copies are rerouted (INTEGRATION.md section 1):
+    !!     diagnostic_update(domain, options)  ->  b200_diagnostic_update()      (time_step.f90:474)
+    !!     domain%apply_forcing(dt)            ->  b200_apply_forcing(dt)        (time_step.f90:537)
+    !!     domain%enforce_limits()             ->  b200_enforce_limits()         (time_step.f90:541)
+    !!     after every forcing update          ->  b200_update_forcing(domain)   (driver.f90:134-151: the new dqdt_3d)
+    !!     after update_winds on the host      ->  b200_upload_winds(domain)
+    !! Without these the lateral boundary tendencies of th / qv / u / v / p never reach the device copies.
     subroutine sync_to_device(domain)
         type(domain_t), intent(inout) :: domain
-        call up3(VAR_U, domain%u%data_3d);  call up3(VAR_V, domain%v%data_3d);  call up3(VAR_W, domain%w%data_3d)
-        call up3(VAR_PRESSURE, domain%pressure%data_3d)
-        call up3(VAR_EXNER,    domain%exner%data_3d)
-        call up3(VAR_DENSITY,  domain%density%data_3d)
         if (.not. state_on_device) then
+            call b200_upload_winds(domain)
+            call up3(VAR_PRESSURE, domain%pressure%data_3d)
             call up3(VAR_TH, domain%potential_temperature%data_3d)
             call up3(VAR_QV, domain%water_vapor%data_3d)
             call up3(VAR_QC, domain%cloud_water_mass%data_3d)
@@ -301,9 +333,48 @@ contains
                 call up3(VAR_QI, domain%cloud_ice_mass%data_3d);  call up3(VAR_NI, domain%cloud_ice_number%data_3d)
                 call up3(VAR_NR, domain%rain_number%data_3d);     call up3(VAR_QG, domain%graupel_mass%data_3d)
             endif
+            call check(icar_diagnostic_update(ctx), "icar_diagnostic_update")     ! exner, density from p and th
             state_on_device = .true.
         endif
         call check(icar_set_model_time(ctx, domain%model_time%seconds()), "icar_set_model_time")
+    end subroutine
+
+    !> u, v, w as the host has them (after update_winds / balance_uvw on the host)
+    subroutine b200_upload_winds(domain)
+        type(domain_t), intent(inout) :: domain
+        call up3(VAR_U, domain%u%data_3d);  call up3(VAR_V, domain%v%data_3d);  call up3(VAR_W, domain%w%data_3d)
+    end subroutine
+
+    !> diagnostic_update(domain, options), time_step.f90:49-198, for what mp / advect read: exner and density
+    subroutine b200_diagnostic_update()
+        if (state_on_device) call check(icar_diagnostic_update(ctx), "icar_diagnostic_update")
+    end subroutine
+
+    !> after the boundary object has new tendencies (update_delta_fields, domain_obj.f90:2318-2381): var%dqdt_3d of the
+    !! forced variables goes to the device
+    subroutine b200_update_forcing(domain)
+        type(domain_t), intent(inout), target :: domain
+        call tend(VAR_U, domain%u%dqdt_3d);   call tend(VAR_V, domain%v%dqdt_3d)
+        call tend(VAR_PRESSURE, domain%pressure%dqdt_3d)
+        call tend(VAR_TH, domain%potential_temperature%dqdt_3d)
+        call tend(VAR_QV, domain%water_vapor%dqdt_3d)
+    contains
+        subroutine tend(var, a)
+            integer(c_int), intent(in) :: var
+            real, intent(in), pointer :: a(:,:,:)
+            if (associated(a)) call check(icar_upload_tendency(ctx, var, c_loc(a)), "icar_upload_tendency")
+        end subroutine
+    end subroutine
+
+    !> domain%apply_forcing(dt), domain_obj.f90:2383-2448, on the device copies
+    subroutine b200_apply_forcing(dt_seconds)
+        double precision, intent(in) :: dt_seconds
+        call check(icar_apply_forcing(ctx, real(dt_seconds, c_double)), "icar_apply_forcing")
+    end subroutine
+
+    !> domain%enforce_limits(), domain_obj.f90:2228-2243, on the device copies
+    subroutine b200_enforce_limits()
+        call check(icar_enforce_limits(ctx), "icar_enforce_limits")
     end subroutine
 
     !> mp(domain, options, dt_in, halo, subset) -- mp_driver.f90:673

@@ -132,6 +132,10 @@ int icar_grid_xslab(int nx_global, int nz, int ny_global, int nimages, int image
  * device / the CUDA build is unusable: there is no CPU fallback. */
 int icar_create(int device, const icar_grid* grid, const icar_options* opt, icar_ctx** ctx);
 int icar_destroy(icar_ctx* ctx);
+
+/* Number of CUDA devices this process sees (0 without a GPU): the Fortran shim places image i on device
+ * mod(i - 1, count), one image per GPU of the node. */
+int icar_device_count(int* count);
 const char* icar_last_error(const icar_ctx* ctx); /* ctx may be NULL: last creation error */
 
 /* ------------------------------------------------------- resident domain state */

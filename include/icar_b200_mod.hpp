@@ -109,14 +109,19 @@ inline void adv_init(const domain_t& domain, const options_t& options, int devic
     mp_init(options);
 }
 
-// what the host side changes between steps (diagnostic_update, apply_forcing) goes up; the scalars only once
-inline void sync_to_device(const domain_t& domain) {
+// Resident mode: the state goes up once, at the first mp() call; after that the loop body of step() that touches it
+// runs on the device, and the reference call sites that would change the HOST copies are rerouted:
+// diagnostic_update -> b200_diagnostic_update, domain%apply_forcing -> b200_apply_forcing, domain%enforce_limits ->
+// b200_enforce_limits, new forcing tendencies -> b200_update_forcing, update_winds on the host -> b200_upload_winds.
+inline void b200_upload_winds(const domain_t& domain) {
     using namespace detail;
     up3(ICAR_VAR_U, domain.u.data_3d); up3(ICAR_VAR_V, domain.v.data_3d); up3(ICAR_VAR_W, domain.w.data_3d);
-    up3(ICAR_VAR_PRESSURE, domain.pressure.data_3d);
-    up3(ICAR_VAR_EXNER, domain.exner.data_3d);
-    up3(ICAR_VAR_DENSITY, domain.density.data_3d);
+}
+inline void sync_to_device(const domain_t& domain) {
+    using namespace detail;
     if (!state_on_device()) {
+        b200_upload_winds(domain);
+        up3(ICAR_VAR_PRESSURE, domain.pressure.data_3d);
         up3(ICAR_VAR_POTENTIAL_TEMPERATURE, domain.potential_temperature.data_3d);
         up3(ICAR_VAR_WATER_VAPOR, domain.water_vapor.data_3d);
         up3(ICAR_VAR_CLOUD_WATER, domain.cloud_water_mass.data_3d);
@@ -126,10 +131,27 @@ inline void sync_to_device(const domain_t& domain) {
             up3(ICAR_VAR_CLOUD_ICE, domain.cloud_ice_mass.data_3d); up3(ICAR_VAR_ICE_NUMBER, domain.cloud_ice_number.data_3d);
             up3(ICAR_VAR_RAIN_NUMBER, domain.rain_number.data_3d); up3(ICAR_VAR_GRAUPEL_IN_AIR, domain.graupel_mass.data_3d);
         }
+        if (domain.exner.data_3d.empty() || domain.density.data_3d.empty()) {
+            check(icar_diagnostic_update(ctx()), "icar_diagnostic_update");       // exner, density from p and th
+        } else {            // a caller that brings its own diagnosed fields (the reference scenarios do)
+            up3(ICAR_VAR_EXNER, domain.exner.data_3d);
+            up3(ICAR_VAR_DENSITY, domain.density.data_3d);
+        }
         state_on_device() = true;
     }
     check(icar_set_model_time(ctx(), domain.model_time), "icar_set_model_time");
 }
+// diagnostic_update(domain, options), time_step.f90:49-198, for what mp / advect read
+inline void b200_diagnostic_update() {
+    if (detail::state_on_device()) detail::check(icar_diagnostic_update(detail::ctx()), "icar_diagnostic_update");
+}
+// var%dqdt_3d of a forced variable (update_delta_fields, domain_obj.f90:2318-2381) goes to the device
+inline void b200_update_forcing(int var, const std::vector<float>& dqdt_3d) {
+    if (!dqdt_3d.empty()) detail::check(icar_upload_tendency(detail::ctx(), var, dqdt_3d.data()), "icar_upload_tendency");
+}
+// domain%apply_forcing(dt), domain_obj.f90:2383-2448; domain%enforce_limits(), :2228-2243
+inline void b200_apply_forcing(double dt_seconds) { detail::check(icar_apply_forcing(detail::ctx(), dt_seconds), "icar_apply_forcing"); }
+inline void b200_enforce_limits() { detail::check(icar_enforce_limits(detail::ctx()), "icar_enforce_limits"); }
 
 // mp(domain, options, dt_in, halo, subset) -- mp_driver.f90:673; halo / subset < 0 == "not present"
 inline void mp(domain_t& domain, const options_t&, float dt_in, int halo = -1, int subset = -1) {
