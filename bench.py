@@ -62,17 +62,19 @@ SCHEMES = {
                    workload="ideal hill {nx}x{ny}x{nz}, MPDATA order2+FCT, mp_simple (BASELINE configs[1])"),
     "thompson": dict(mp=1, b_alg=188.0, scalars=("th", "qv", "qc", "qr", "qs", "qi", "qg", "ni", "nr"),
                      acc=("precipitation", "snowfall", "graupel"),
-                     workload="ideal hill {nx}x{ny}x{nz}, MPDATA order2+FCT, Thompson microphysics (BASELINE configs[2])"),
+                     workload="ideal hill {nx}x{ny}x{nz}, MPDATA order2+FCT, Thompson microphysics (BASELINE {cfg})"),
 }
+BASELINE_CONFIGS = {(512, 512, 40): "configs[2]", (1024, 1024, 50): "configs[3]", (2048, 2048, 60): "configs[4]"}
 
 
-def make_state(args):
+def make_state(args, rows=None):
+    """The synthetic state of the workload; rows=(j0, j1): only that band of rows (a rank of a large y-slab run)."""
     from icar_b200 import ideal
-    st = ideal.make_ideal_case(nx=args.nx, nz=args.nz, ny=args.ny, perturb=True)
+    st = ideal.make_ideal_case(nx=args.nx, nz=args.nz, ny=args.ny, perturb=True, rows=rows)
     if args.mp == "thompson":
         ideal.add_thompson_fields(st)
     for k in SCHEMES[args.mp]["acc"]:
-        st[k] = np.zeros((args.ny, args.nx), np.float64)
+        st[k] = np.zeros((st["ny"], args.nx), np.float64)
     return st
 
 
@@ -285,7 +287,7 @@ def run_reference(args, rank, world):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": el / args.steps * 1e3,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
-        "config": {"workload": SCHEMES[args.mp]["workload"].format(nx=nx, ny=ny, nz=nz), "grid": [nx, nz, ny], "sample": sample,
+        "config": {"workload": SCHEMES[args.mp]["workload"].format(nx=nx, ny=ny, nz=nz, cfg=BASELINE_CONFIGS.get((nx, ny, nz), "grid, not one of its configs")), "grid": [nx, nz, ny], "sample": sample,
                    "note": "CPU restatement (oracle port) of the reference Fortran; the Fortran itself "
                            "cannot be compiled in this image (no gfortran)"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": thr, "kind": "port", "sample": sample, "flags": flags,
@@ -356,14 +358,22 @@ def run_b200(args, rank, world, local_rank):
     nx, nz, ny = args.nx, args.nz, args.ny
     halo = args.halo
     scheme = SCHEMES[args.mp]
-    st = make_state(args)
+    band = bool(args.band_state and distributed and args.slabs == "y")
+    if band:
+        # a rank builds only the rows it holds (ghost rows included): the global state of BASELINE configs[4] would be
+        # 25 GB of host memory per rank.  No undivided domain exists then, so no decomposition check and no other axis.
+        g0 = icar_b200.Grid.yslab(nx, nz, ny, world, rank + 1, halo)
+        st = make_state(args, rows=(g0.jms - 1, g0.jme))
+        args.no_other_axis = True
+    else:
+        st = make_state(args)
     dt = float(st["dt"])
     options = icar_b200.Options(dx=st["dx"], microphysics=scheme["mp"])
 
     def make_domain(slabs):
         if distributed:
             grid = (icar_b200.Grid.xslab if slabs == "x" else icar_b200.Grid.yslab)(nx, nz, ny, world, rank + 1, halo)
-            local = ideal.slab_of(st, grid)
+            local = st if band else ideal.slab_of(st, grid)
         else:
             grid = icar_b200.Grid.single_image(nx, nz, ny, halo_size=1)
             local = st
@@ -443,11 +453,14 @@ def run_b200(args, rank, world, local_rank):
     # linear_winds"): linear-theory perturbation of u, v for the background flow, then balance_uvw; timed on its own
     linear_winds = None
     if args.linear_winds:
-        zi = np.empty_like(st["dz_interface"])             # global z_interface = terrain + the layers below
-        zi[:, 0, :] = st["terrain"]
+        # global terrain and layer geometry (the case is uniform in y: a band's first row stands for every row)
+        g_terrain = np.broadcast_to(st["terrain"][:1], (ny, nx)) if band else st["terrain"]
+        g_dzi = np.broadcast_to(st["dz_interface"][:1], (ny, nz, nx)) if band else st["dz_interface"]
+        zi = np.empty((ny, nz, nx), np.float32)            # global z_interface = terrain + the layers below
+        zi[:, 0, :] = g_terrain
         for k in range(1, nz):
-            zi[:, k, :] = zi[:, k - 1, :] + st["dz_interface"][:, k - 1, :]
-        dom.linear_winds_init(st["terrain"], buffer=50)     # lt_parameters default (options_obj.f90:1452)
+            zi[:, k, :] = zi[:, k - 1, :] + g_dzi[:, k - 1, :]
+        dom.linear_winds_init(np.ascontiguousarray(g_terrain), buffer=50)     # lt_parameters default (options_obj.f90:1452)
         dom.synchronize()
         entries = None
         if args.linear_winds == "spatial":
@@ -455,9 +468,9 @@ def run_b200(args, rank, world, local_rank):
         dom.timer_start()
         if args.linear_winds == "spatial":                  # the reference's per-cell table semantics, entries on demand
             entries = dom.linear_perturb_spatial(icar_b200.LtOptions(linear_update_fraction=1.0), global_z_interface=zi,
-                                                 global_dz_interface=st["dz_interface"])
+                                                 global_dz_interface=g_dzi)
         else:                                               # one background state, evaluated directly
-            dom.linear_perturb(10.0, 5.0, 3e-5, global_z_interface=zi, global_dz_interface=st["dz_interface"],
+            dom.linear_perturb(10.0, 5.0, 3e-5, global_z_interface=zi, global_dz_interface=g_dzi,
                                linear_update_fraction=1.0)
         dom.balance_uvw()
         lw_ms = max_over_ranks(dom.timer_stop())
@@ -547,7 +560,10 @@ def run_b200(args, rank, world, local_rank):
 
     # ---------------- correctness inside the driver-run artefact
     parity = decomp = other_axis = None
-    if distributed:
+    if distributed and band:
+        decomp = {"skipped": "--band-state: no rank holds the undivided domain at this size; the same kernels and schedule "
+                             "are checked bit for bit at 512x512x40 and 1024x1024x50"}
+    elif distributed:
         decomp = decomposition_check(dom, grid, args.slabs, local)
         if not args.no_other_axis:
             # the other decomposition axis once (north_star prescribes x; y keeps full-width rows and contiguous planes)
@@ -640,7 +656,7 @@ def run_b200(args, rank, world, local_rank):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": scheme["workload"].format(nx=nx, ny=ny, nz=nz), "grid": [nx, nz, ny], "dt_s": dt,
+            "config": {"workload": scheme["workload"].format(nx=nx, ny=ny, nz=nz, cfg=BASELINE_CONFIGS.get((nx, ny, nz), "grid, not one of its configs")), "grid": [nx, nz, ny], "dt_s": dt,
                        "advected_scalars": len(scheme["scalars"]),
                        "arithmetic": "the reference's IEEE binary32 operations in the reference's order (advection and "
                                      "mp_simple bit-identical to the oracle); there is no other mode",
@@ -715,6 +731,9 @@ def main():
                     help="e2e pipelined over this many bands of rows (icar_b200/pipeline.py; N=1 only); 1 = the plain host step")
     ap.add_argument("--no-parity", action="store_true", help="skip the oracle comparison (N=1) after the timed region")
     ap.add_argument("--no-other-axis", action="store_true", help="N>1: do not also time the other decomposition axis")
+    ap.add_argument("--band-state", action="store_true",
+                    help="N>1, y-slabs: every rank builds only its own rows of the synthetic state (BASELINE configs[4], "
+                         "2048x2048x60: the global state would be 25 GB of host memory per rank); skips the decomposition check")
     ap.add_argument("--linear-winds", nargs="?", const="direct", default=None, choices=["direct", "spatial"],
                     help="before the steps, run the once-per-forcing-interval wind update (icar_linear_perturb + "
                          "icar_balance_uvw) and report its time under `linear_winds`")

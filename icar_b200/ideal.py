@@ -50,13 +50,21 @@ def compute_dt(u, v, w, dx, dz_levels, cfl=0.9, cap=120.0):
 
 
 def make_ideal_case(nx=100, nz=20, ny=100, dx=4000.0, dz_level=400.0, terrain=True,
-                    u0=10.0, v0=0.0, perturb=False, seed=1234):
+                    u0=10.0, v0=0.0, perturb=False, seed=1234, rows=None):
     """Returns a dict of float32 arrays + scalars describing one ICAR domain state.
 
     terrain=False is "Set A" (flat metric, jacobians == 1, space_varying_dz=.false.);
     terrain=True is "Set B" (the hill, space_varying_dz=.true., flat_z_height=-1).
     perturb=True adds the reproducible noise + v wind used for the throughput runs
-    (SURVEY.md section 8d)."""
+    (SURVEY.md section 8d).
+    rows=(j0, j1): only rows j0..j1-1 of the (ny-row) domain are built -- the same values the whole state has there
+    (the case is uniform in y except for the noise, whose random stream is advanced to the band) -- so that a rank of a
+    large decomposed run never holds the global state (2048 x 2048 x 60: 1 GB per field)."""
+    ny_global = ny
+    j0, j1 = (0, ny) if rows is None else rows
+    if not (0 <= j0 < j1 <= ny_global):
+        raise ValueError("rows outside the domain")
+    ny = j1 - j0
     dzl = np.full(nz, dz_level, np.float32)
     i = np.arange(nx, dtype=np.float64)
     hgt1 = (1000.0 * (np.cos(i / nx * 2 * np.pi + np.pi) + 1)).astype(np.float32)
@@ -106,7 +114,10 @@ def make_ideal_case(nx=100, nz=20, ny=100, dx=4000.0, dz_level=400.0, terrain=Tr
     v = np.full((ny + 1, nz, nx), v0, np.float32)
     if perturb:
         rng = np.random.default_rng(seed)
+        row, cells = nz * nx, ny_global * nz * nx            # one 64-bit draw per uniform double
+        rng.bit_generator.advance(j0 * row)
         qv *= (1 + 0.1 * rng.uniform(-1, 1, qv.shape)).astype(np.float32)
+        rng.bit_generator.advance(cells - j1 * row + j0 * row)
         th += (0.5 * rng.uniform(-1, 1, th.shape)).astype(np.float32)
         v[:] = F(5.0)
     w = balance_uvw(u, v, jac_u, jac_v, jac_w, advection_dz, dx)
@@ -117,7 +128,7 @@ def make_ideal_case(nx=100, nz=20, ny=100, dx=4000.0, dz_level=400.0, terrain=Tr
 
     zeros = lambda: np.zeros((ny, nz, nx), np.float32)
     st = dict(
-        nx=nx, nz=nz, ny=ny, dx=float(dx), dz_levels=dzl,
+        nx=nx, nz=nz, ny=ny, dx=float(dx), dz_levels=dzl, rows=(j0, j1), ny_global=ny_global,
         jacobian=jac, jacobian_u=jac_u, jacobian_v=jac_v, jacobian_w=jac_w,
         advection_dz=advection_dz, dz_mass=dz_mass, dz_interface=dz_interface, z=z, terrain=hgt,
         pressure=p, th=th, pii=pii, rho=rho, qv=qv, qc=zeros(), qr=zeros(), qs=zeros(),
