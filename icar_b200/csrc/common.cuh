@@ -1,9 +1,7 @@
 // Shared device helpers for the icar_b200 kernels (sm_100a).
 #pragma once
-#if defined(__CUDACC__)
+#ifndef ICAR_HOST_EMULATION   // (defined by tests/cpp/host_emu.h, which the CPU harnesses of the tests include first)
 #include <cuda_runtime.h>
-#else
-#include "host_emu.h"   // host-only test harnesses (tests/cpp/)
 #endif
 #include <cstddef>
 #include <cstdint>
@@ -46,7 +44,7 @@ __device__ __forceinline__ R donor(R U, R l, R r) {
 // wait for the device to go idle -- which never happens while an image's halo kernels are waiting on the device for a
 // neighbour whose own first launches are blocked behind that load.  icar_comm_init* therefore touches every kernel of
 // the multi-image step before the first exchange (each translation unit lists its own in a *_preload function).
-#if defined(__CUDACC__)
+#ifndef ICAR_HOST_EMULATION
 template <class K>
 inline bool preload_kernel(K kernel) {
     cudaFuncAttributes a;

@@ -3,16 +3,12 @@
 // aligned register pair; mov.b64 packs / unpacks cost nothing.  Everything else (compare, select, min / max,
 // MUFU, shuffles) stays per component.
 #pragma once
-#if defined(__CUDACC__)
-#include <cuda_runtime.h>
-#else
-#include "host_emu.h"   // host-only test harnesses (tests/cpp/)
-#endif
+#include "common.cuh"
 
 namespace icar {
 
+#ifndef ICAR_HOST_EMULATION      // (the CPU harnesses of the tests bring the same operations one IEEE half at a time)
 struct f2 { float x, y; };
-#if defined(__CUDACC__)
 typedef unsigned long long u64;
 __device__ __forceinline__ u64 pk(f2 a) { u64 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a.x), "f"(a.y)); return r; }
 __device__ __forceinline__ f2 up(u64 v) { f2 r; asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v)); return r; }
@@ -20,26 +16,15 @@ __device__ __forceinline__ f2 operator+(f2 a, f2 b) { u64 r; asm("add.rn.f32x2 %
 __device__ __forceinline__ f2 operator-(f2 a, f2 b) { u64 r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(pk(a)), "l"(pk(b))); return up(r); }
 __device__ __forceinline__ f2 operator*(f2 a, f2 b) { u64 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(pk(a)), "l"(pk(b))); return up(r); }
 __device__ __forceinline__ f2 fma2(f2 a, f2 b, f2 c) { u64 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(pk(a)), "l"(pk(b)), "l"(pk(c))); return up(r); }
-#else   // the same IEEE roundings, one half at a time (tests/cpp/upwind_p2_host.cpp, built with -ffp-contract=off)
-inline f2 operator+(f2 a, f2 b) { return f2{a.x + b.x, a.y + b.y}; }
-inline f2 operator-(f2 a, f2 b) { return f2{a.x - b.x, a.y - b.y}; }
-inline f2 operator*(f2 a, f2 b) { return f2{a.x * b.x, a.y * b.y}; }
-inline f2 fma2(f2 a, f2 b, f2 c) { return f2{fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y)}; }
-#endif
-__device__ __forceinline__ f2 neg2(f2 a) { return f2{-a.x, -a.y}; }
-__device__ __forceinline__ f2 splat(float v) { return f2{v, v}; }
-#if defined(__CUDACC__)
+// MUFU.RCP of both halves
 __device__ __forceinline__ f2 rcp2(f2 a) {
     f2 r;
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r.x) : "f"(a.x));
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r.y) : "f"(a.y));
     return r;
 }
-__device__ __forceinline__ f2 div2(f2 a, f2 b) { return a * rcp2(b); }
-
-#else
-inline f2 rcp2(f2 a) { return f2{1.0f / a.x, 1.0f / a.y}; }      // rcp.approx is within 1 ulp of this
-inline f2 div2(f2 a, f2 b) { return a * rcp2(b); }
 #endif
+__device__ __forceinline__ f2 neg2(f2 a) { return f2{-a.x, -a.y}; }
+__device__ __forceinline__ f2 splat(float v) { return f2{v, v}; }
 
 }  // namespace icar

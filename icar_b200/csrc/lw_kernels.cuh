@@ -1,16 +1,12 @@
 // The kernels of the linear-theory wind perturbation (see linear_winds.cu for the routine-by-routine map to
 // src/physics/linear_winds.f90).  They use nothing but lw_math.cuh, plain pointers and blockIdx / threadIdx, so that
-// tests/cpp/lw_kernels_host.cpp can run these very bodies on the CPU (one loop iteration per thread, stubs for the
-// built-ins) between NumPy transforms and compare a whole icar_linear_perturb with the restatement without a GPU.
+// tests/cpp/lw_kernels_host.cpp can run these very bodies on the CPU (one loop iteration per thread; tests/cpp/host_emu.h
+// supplies the built-ins) between NumPy transforms and compare a whole icar_linear_perturb with the restatement without a GPU.
 // The product includes this file only from linear_winds.cu.
 #pragma once
 #include <cstddef>
 
 #include "lw_math.cuh"
-
-#if !defined(__CUDACC__)
-#include "host_emu.h"   // host emulation (tests only)
-#endif
 
 namespace icar {
 namespace lwk {

@@ -20,6 +20,7 @@
 #include <thread>
 #include <vector>
 
+#include "host_emu.h"
 #include "../../icar_b200/csrc/common.cuh"
 #include "../../icar_b200/csrc/f32x2.cuh"
 #include "../../icar_b200/csrc/mpdata.cuh"
@@ -91,12 +92,20 @@ static inline void icar_emu_tma_load_box(void* dst, const CUtensorMap* m, uint64
 }
 using std::max;
 using std::min;
-#define __grid_constant__
-#define __maxnreg__(n)
 #define ICAR_DYNAMIC_SMEM(name) unsigned char* name = icar_emu_smem
 
 namespace icar {
 namespace {
+// the hardware primitives of corrector_prims.inc, emulated (one OS thread per CUDA thread of a CTA)
+inline float lane_lo(float v) { return icar_emu_shfl(v, -1); }
+inline float lane_hi(float v) { return icar_emu_shfl(v, +1); }
+inline void mbar_init(uint64_t* b, uint32_t count) { icar_emu_mbar_init(b, count); }
+inline void fence_barrier_init() {}
+inline void mbar_arrive_expect_tx(uint64_t* b, uint32_t bytes) { icar_emu_mbar_expect(b, bytes); }
+inline bool mbar_try_wait(uint64_t* b, uint32_t parity) { return icar_emu_mbar_try_wait(b, parity); }
+inline void tma_load_box(void* dst, const CUtensorMap* map, uint64_t* bar, int x, int z, int y) {
+    icar_emu_tma_load_box(dst, map, bar, x, z, y);
+}
 #include "../../icar_b200/csrc/corrector_prims.inc"
 #include "../../icar_b200/csrc/corrector_fused.inc"
 

@@ -1,6 +1,7 @@
 // TEST INFRASTRUCTURE.  Runs the kernel bodies of icar_b200/csrc/lw_kernels.cuh on the CPU: every "launch" is a loop
 // over the grid the product uses in linear_winds.cu (128 threads per block, blockIdx.y = row), one iteration per
 // thread.  tests/test_linear_winds_host.py puts NumPy transforms where the product calls cuFFT.
+#include "host_emu.h"
 #include "../../icar_b200/csrc/lw_kernels.cuh"
 
 thread_local icar_emu_idx blockIdx, threadIdx, blockDim;

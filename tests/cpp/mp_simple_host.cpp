@@ -8,6 +8,7 @@
 #include <thread>
 #include <vector>
 
+#include "host_emu.h"
 #include "../../icar_b200/csrc/common.cuh"
 #include "../../icar_b200/csrc/mp_simple.cuh"
 

@@ -11,6 +11,7 @@
 #include <thread>
 #include <vector>
 
+#include "host_emu.h"
 #include "../../icar_b200/csrc/common.cuh"
 #include "../../icar_b200/csrc/mp_thompson.cuh"
 
@@ -36,7 +37,6 @@ using std::min;
 
 namespace icar {
 namespace {
-#define __grid_constant__
 #include "../../icar_b200/csrc/mp_thompson_kernel.inc"
 }  // namespace
 }  // namespace icar

@@ -1,6 +1,7 @@
 // TEST INFRASTRUCTURE.  Runs k_upwind_all_v4 (icar_b200/csrc/upwind_all.cuh: MPDATA pass 1 for all scalars, four cells
 // per thread) on the CPU, one loop iteration per thread over the grid staged_upwind_all launches:
 // dim3((ld / 4 + 127) / 128, nz, ny) blocks of 128 threads.  Built with -ffp-contract=off.
+#include "host_emu.h"
 #include "../../icar_b200/csrc/upwind_all.cuh"
 
 thread_local icar_emu_idx blockIdx, threadIdx, blockDim;
