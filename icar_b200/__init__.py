@@ -168,7 +168,7 @@ SYMBOLS = (
     "icar_mpdata_set_winds_f64", "icar_mpdata_advect3d_f64", "icar_mp_simple_driver",
     "icar_physics_step_host", "icar_step_host", "icar_physics_step_host_io", "icar_host_register", "icar_host_unregister",
     "icar_default_mp_options", "icar_thompson_init", "icar_thompson_table", "icar_mp_gt_driver",
-    "icar_profile_enable", "icar_profile_read", "icar_diagnostic_update", "icar_compute_dt", "icar_enforce_limits",
+    "icar_profile_enable", "icar_profile_read", "icar_diagnostic_update", "icar_diagnostic_output", "icar_compute_dt", "icar_enforce_limits",
     "icar_upload_tendency", "icar_apply_forcing", "icar_balance_uvw",
     "icar_add_buffer_topo", "icar_linear_winds_init", "icar_linear_winds_dims", "icar_linear_winds_terrain_frequency",
     "icar_linear_perturbation", "icar_linear_perturb", "icar_default_lt_options", "icar_linear_winds_set_z",
@@ -313,6 +313,21 @@ class Domain:
     def diagnostic_update(self):
         """exner and density from pressure and potential temperature (time_step.f90:85-101)."""
         self._check(lib().icar_diagnostic_update(self._h))
+
+    def diagnostic_output(self, dzdx=None, dzdy=None, want=("temperature", "pressure_interface", "temperature_interface",
+                                                            "surface_pressure", "u_mass", "v_mass", "w_real")):
+        """The output-only fields of diagnostic_update (time_step.f90:88-108, 165-194) as host arrays
+        (ny, nz, nx) / (ny, nx); dzdx (ny, nz, nx+1) and dzdy (ny+1, nz, nx) are needed for w_real."""
+        g = self.grid
+        names = ("temperature", "pressure_interface", "temperature_interface", "surface_pressure", "u_mass", "v_mass", "w_real")
+        out = {n: np.zeros((g.ny, g.nx) if n == "surface_pressure" else (g.ny, g.nz, g.nx), np.float32)
+               for n in names if n in want}
+        sx = _f32(dzdx, (g.ny, g.nz, g.nx + 1), "dzdx") if dzdx is not None else None
+        sy = _f32(dzdy, (g.ny + 1, g.nz, g.nx), "dzdy") if dzdy is not None else None
+        self._check(lib().icar_diagnostic_output(self._h, _ptr(sx) if sx is not None else None,
+                                                 _ptr(sy) if sy is not None else None,
+                                                 *[_ptr(out[n]) if n in out else None for n in names]))
+        return out
 
     def compute_dt(self, dz_levels, cfl_reduction_factor=0.9, cfl_strictness=3):
         """update_dt (time_step.f90:375-423): CFL time step, min over images, capped at 120 s."""

@@ -1780,6 +1780,70 @@ extern "C" int icar_diagnostic_update(icar_ctx* ctx) {
     return ICAR_OK;
 }
 
+extern "C" int icar_diagnostic_output(icar_ctx* ctx, const float* dzdx, const float* dzdy, float* temperature,
+                                      float* pressure_interface, float* temperature_interface, float* surface_pressure,
+                                      float* u_mass, float* v_mass, float* w_real) {
+    if (!ctx) return ICAR_ERR_INVALID;
+    if (ctx->exchange_in_flight)
+        return fail(ctx, ICAR_ERR_INVALID, "icar_diagnostic_output between icar_halo_send and icar_halo_retrieve");
+    if (w_real && (!dzdx || !dzdy)) return fail(ctx, ICAR_ERR_INVALID, "icar_diagnostic_output: w_real needs dzdx and dzdy");
+    CU(cudaSetDevice(ctx->device));
+    const Geom& g = ctx->g;
+    { int jr = join_aux(ctx); if (jr) return jr; jr = join_winds(ctx); if (jr) return jr; }
+    // results are staged in three cell-shaped scratch fields at a time and copied out in the reference's dense layout
+    constexpr size_t kSlot = 24;                   // above the slots of the leaf calls
+    float* st[3] = {nullptr, nullptr, nullptr};
+    for (int n = 0; n < 3; ++n) {
+        void* p = nullptr;
+        int rc = get_scratch(ctx, kSlot + n, sizeof(float), &p);
+        if (rc) return rc;
+        st[n] = (float*)p;
+    }
+    const size_t rows = (size_t)g.nz * g.ny;
+    if (temperature || pressure_interface || temperature_interface || surface_pressure) {
+        int rc = need_uploaded(ctx, {ICAR_VAR_PRESSURE, ICAR_VAR_POTENTIAL_TEMPERATURE, ICAR_VAR_EXNER}, "icar_diagnostic_output");
+        if (rc) return rc;
+        float* pi_dev = (pressure_interface || surface_pressure) ? st[1] : nullptr;
+        ctx->launches += diagnostic_thermo_launch(g, (const float*)ctx->vars[ICAR_VAR_PRESSURE],
+                                                  (const float*)ctx->vars[ICAR_VAR_POTENTIAL_TEMPERATURE],
+                                                  (const float*)ctx->vars[ICAR_VAR_EXNER], temperature ? st[0] : nullptr,
+                                                  pi_dev, temperature_interface ? st[2] : nullptr, ctx->stream);
+        CU(cudaGetLastError());
+        if (temperature && (rc = copy_out(ctx, temperature, st[0], g.nx, g.ld, rows, sizeof(float)))) return rc;
+        if (pressure_interface && (rc = copy_out(ctx, pressure_interface, st[1], g.nx, g.ld, rows, sizeof(float)))) return rc;
+        if (temperature_interface && (rc = copy_out(ctx, temperature_interface, st[2], g.nx, g.ld, rows, sizeof(float)))) return rc;
+        if (surface_pressure)           // psfc = pressure_i(:, kms, :): one x-line per y index (time_step.f90:93)
+            CU(cudaMemcpy2DAsync(surface_pressure, (size_t)g.nx * sizeof(float), st[1], g.ps() * sizeof(float),
+                                 (size_t)g.nx * sizeof(float), (size_t)g.ny, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+    }
+    if (u_mass || v_mass || w_real) {
+        int rc = need_uploaded(ctx, {ICAR_VAR_U, ICAR_VAR_V}, "icar_diagnostic_output");
+        if (rc) return rc;
+        float *sx = nullptr, *sy = nullptr;
+        if (w_real) {
+            if ((rc = need_uploaded(ctx, {ICAR_VAR_W, ICAR_VAR_JACOBIAN}, "icar_diagnostic_output"))) return rc;
+            void* p = nullptr;
+            if ((rc = get_scratch(ctx, kSlot + 3, sizeof(float), &p))) return rc;
+            sx = (float*)p;
+            if ((rc = get_scratch(ctx, kSlot + 4, sizeof(float), &p))) return rc;
+            sy = (float*)p;
+            if ((rc = copy_in(ctx, sx, dzdx, g.nx + 1, g.ldu, rows, sizeof(float)))) return rc;
+            if ((rc = copy_in(ctx, sy, dzdy, g.nx, g.ld, (size_t)g.nz * (g.ny + 1), sizeof(float)))) return rc;
+        }
+        ctx->launches += diagnostic_winds_launch(g, (const float*)ctx->vars[ICAR_VAR_U], (const float*)ctx->vars[ICAR_VAR_V],
+                                                 (const float*)ctx->vars[ICAR_VAR_W], sx, sy,
+                                                 (const float*)ctx->vars[ICAR_VAR_JACOBIAN], u_mass ? st[0] : nullptr,
+                                                 v_mass ? st[1] : nullptr, w_real ? st[2] : nullptr, ctx->stream);
+        CU(cudaGetLastError());
+        if (u_mass && (rc = copy_out(ctx, u_mass, st[0], g.nx, g.ld, rows, sizeof(float)))) return rc;
+        if (v_mass && (rc = copy_out(ctx, v_mass, st[1], g.nx, g.ld, rows, sizeof(float)))) return rc;
+        if (w_real && (rc = copy_out(ctx, w_real, st[2], g.nx, g.ld, rows, sizeof(float)))) return rc;
+        CU(cudaStreamSynchronize(ctx->stream));
+    }
+    return ICAR_OK;
+}
+
 extern "C" int icar_compute_dt(icar_ctx* ctx, const float* dz_levels, float cfl, int strictness, double* dt_seconds) {
     if (!ctx || !dz_levels || !dt_seconds) return fail(ctx, ICAR_ERR_INVALID, "icar_compute_dt: null argument");
     if (strictness < 1 || strictness > 5) return fail(ctx, ICAR_ERR_INVALID, "icar_compute_dt: cfl_strictness must be 1..5");

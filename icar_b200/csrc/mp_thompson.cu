@@ -12,7 +12,7 @@
 //   * fall speeds         -- levels without a species inherit the speed above   (:2544-2545 ...)
 //   * nstep / ksed1       -- column maxima per species                          (:2548-2555 ...)
 //   * sedimentation       -- flux divergence needs sed(k+1), per sub-step       (:2660-2770)
-// So, as for mp_simple, a CTA owns TX columns x all levels with ONE THREAD PER CELL (threadIdx.x = column
+// So, as for mp_simple, a CTA owns TX (16 or 8) columns x all levels with ONE THREAD PER CELL (threadIdx.x = column
 // within the tile, threadIdx.y = level): the cell's state and its ~55 REAL*8 process rates live in
 // registers, the couplings above go through a few shared-memory rows, and each field is read once and
 // written once.  Levels are processed in the Fortran's statement order within a cell, so the result
@@ -43,6 +43,8 @@ int th_driver_launch(const Geom& g, const ThConst& c, const ThTables& tb, float*
                      float* graupelnc, float* graupelncv, float* sr, int ld2, const MpTiles& tiles, int kts, int kte,
                      unsigned long long* diag, cudaStream_t st, double* acc_precip, double* acc_snow,
                      double* acc_graupel) {
+    const int nk = kte - kts + 1;
+    const int TX = th_columns_per_cta(nk);
     int gx = 0, gy = 0;
     for (int t = 0; t < tiles.n; ++t) {
         if (tiles.ite[t] < tiles.its[t] || tiles.jte[t] < tiles.jts[t]) continue;
@@ -51,7 +53,6 @@ int th_driver_launch(const Geom& g, const ThConst& c, const ThTables& tb, float*
         gy = std::max(gy, tiles.along_y[t] ? w : h);
     }
     if (gx == 0 || gy == 0) return 0;
-    const int nk = kte - kts + 1;
     if (nk < 1 || nk * TX > 1024) return -1;                // one thread per level
     const int nkt = (nk * TX + 31) / 32 * 32 / TX;          // whole warps
     Args A{qv, qc, qr, qi, qs, qg, ni, nr, th, pii, p, dz, rainnc, snownc, snowncv, graupelnc, graupelncv, sr, rainncv,
@@ -59,16 +60,27 @@ int th_driver_launch(const Geom& g, const ThConst& c, const ThTables& tb, float*
     dim3 block(TX, nkt), grid(gx, gy, tiles.n);
     const size_t smem = (size_t)nk * TX * sizeof(double) + (size_t)7 * (nk + 1) * TX * sizeof(float) + (size_t)10 * TX * sizeof(int);
     const int nthreads = TX * nkt;
-#define TH_LAUNCH(MAXT, MINB) k_mp_thompson<MAXT, MINB><<<grid, block, smem, st>>>(g, c, tb, A, ld2, dt, tiles, kts, kte, diag)
-    if (nthreads <= 320) { TH_LAUNCH(320, 2); }     // two CTAs per SM: 7.8 ms per step against 10.7 ms with one (168 registers, no spills)
-    else if (nthreads <= 640) { TH_LAUNCH(640, 1); }
-    else { TH_LAUNCH(1024, 1); }
+#define TH_LAUNCH(TXC, MAXT, MINB) k_mp_thompson<TXC, MAXT, MINB><<<grid, block, smem, st>>>(g, c, tb, A, ld2, dt, tiles, kts, kte, diag)
+    // 96 registers: two CTAs of <= 320 threads or one of <= 640 per SM (one CTA per SM with 168 registers and no spills
+    // was measured at 10.7 ms per step against 7.8: occupancy matters more than the spills)
+#ifdef ICAR_TH_TX16HI
+    if (TX == 16) { if (nthreads <= 320) { TH_LAUNCH(16, 320, 2); } else if (nthreads <= 640) { TH_LAUNCH(16, 640, 1); } else { TH_LAUNCH(16, 1024, 1); } }
+#else
+    if (TX == 16) { if (nthreads <= 320) { TH_LAUNCH(16, 320, 2); } else { TH_LAUNCH(16, 640, 1); } }
+#endif
+#ifdef ICAR_TH_HI2
+    else if (nthreads <= 416) { TH_LAUNCH(8, 416, 2); }
+    else if (nthreads <= 480) { TH_LAUNCH(8, 480, 2); }
+#endif
+    else if (nthreads <= 640) { TH_LAUNCH(8, 640, 1); }
+    else { TH_LAUNCH(8, 1024, 1); }
 #undef TH_LAUNCH
     return 1;
 }
 
 bool th_driver_preload() {
-    return preload_kernel(k_mp_thompson<320, 2>) && preload_kernel(k_mp_thompson<640, 1>) && preload_kernel(k_mp_thompson<1024, 1>);
+    return preload_kernel(k_mp_thompson<16, 320, 2>) && preload_kernel(k_mp_thompson<16, 640, 1>) &&
+           preload_kernel(k_mp_thompson<8, 640, 1>) && preload_kernel(k_mp_thompson<8, 1024, 1>);
 }
 
 }  // namespace icar

@@ -20,6 +20,46 @@ k_diagnostic_update(Geom g, const float* __restrict__ p, const float* __restrict
     rho[c] = pr / (Rd * t);                                   // time_step.f90:101
 }
 
+// diagnostic_update's interface fields (time_step.f90:88-99): temperature = th * exner; pressure_i / temperature_i are
+// the level means ((k-1) + k) / 2 above the ground and a half-difference extrapolation at kms
+__global__ void __launch_bounds__(128)
+k_diagnostic_thermo(Geom g, const float* __restrict__ p, const float* __restrict__ th, const float* __restrict__ exner,
+                    float* __restrict__ temperature, float* __restrict__ p_i, float* __restrict__ t_i) {
+    const int i = blockIdx.x * 128 + threadIdx.x, k = blockIdx.y, j = blockIdx.z;
+    if (i >= g.nx) return;
+    const size_t c = g.at(i, k, j);
+    // the neighbour level: k-1 above the ground, kms+1 at the ground (a one-level model has no interface rule: copy)
+    const size_t o = (k > 0) ? c - g.ld : ((g.nz > 1) ? c + g.ld : c);
+    const float pc = p[c], po = p[o];
+    const float tc = th[c] * exner[c], to = th[o] * exner[o];
+    if (temperature) temperature[c] = tc;
+    if (p_i) p_i[c] = (k > 0) ? (po + pc) / 2.f : pc + (pc - po) / 2.f;
+    if (t_i) t_i[c] = (k > 0) ? (to + tc) / 2.f : tc + (tc - to) / 2.f;
+}
+
+// u_mass, v_mass (time_step.f90:103-108) and the real vertical motion w_real (:165-194) on the mass grid
+__global__ void __launch_bounds__(128)
+k_diagnostic_winds(Geom g, const float* __restrict__ u, const float* __restrict__ v, const float* __restrict__ w,
+                   const float* __restrict__ dzdx, const float* __restrict__ dzdy, const float* __restrict__ jaco,
+                   float* __restrict__ u_mass, float* __restrict__ v_mass, float* __restrict__ w_real) {
+    const int i = blockIdx.x * 128 + threadIdx.x, k = blockIdx.y, j = blockIdx.z;
+    if (i >= g.nx) return;
+    const size_t c = g.at(i, k, j), cu = g.atu(i, k, j), ps = g.ps();
+    const float u0 = u[cu], u1 = u[cu + 1], v0 = v[c], v1 = v[c + ps];
+    if (u_mass) u_mass[c] = (u1 + u0) / 2.f;
+    if (v_mass) v_mass[c] = (v1 + v0) / 2.f;
+    if (w_real) {
+        float r = 0.f;                                    // the boundary ring is never written by the reference: stays 0
+        if (i > 0 && i < g.nx - 1 && j > 0 && j < g.ny - 1) {
+            const float uw0 = u0 * dzdx[cu], uw1 = u1 * dzdx[cu + 1];
+            const float vw0 = v0 * dzdy[c], vw1 = v1 * dzdy[c + ps];
+            const float currw = w[c], lastw = (k > 0) ? w[c - g.ld] : 0.f;
+            r = ((uw0 + uw1) * 0.5f + (vw0 + vw1) * 0.5f) + jaco[c] * (lastw + currw) * 0.5f;
+        }
+        w_real[c] = r;
+    }
+}
+
 __global__ void __launch_bounds__(128)
 k_cfl_maxima(Geom g, const float* __restrict__ u, const float* __restrict__ v, const float* __restrict__ w,
              const float* __restrict__ dzl, float dx, unsigned* __restrict__ out) {
@@ -114,6 +154,19 @@ k_output_reorder(float* __restrict__ field, float* __restrict__ dense, int width
 int diagnostic_update_launch(const Geom& g, const float* pressure, const float* th, float* exner, float* density,
                              cudaStream_t st) {
     k_diagnostic_update<<<row_grid(g), 128, 0, st>>>(g, pressure, th, exner, density);
+    return 1;
+}
+
+int diagnostic_thermo_launch(const Geom& g, const float* pressure, const float* th, const float* exner,
+                             float* temperature, float* p_i, float* t_i, cudaStream_t st) {
+    k_diagnostic_thermo<<<row_grid(g), 128, 0, st>>>(g, pressure, th, exner, temperature, p_i, t_i);
+    return 1;
+}
+
+int diagnostic_winds_launch(const Geom& g, const float* u, const float* v, const float* w, const float* dzdx,
+                            const float* dzdy, const float* jaco, float* u_mass, float* v_mass, float* w_real,
+                            cudaStream_t st) {
+    k_diagnostic_winds<<<row_grid(g), 128, 0, st>>>(g, u, v, w, dzdx, dzdy, jaco, u_mass, v_mass, w_real);
     return 1;
 }
 

@@ -11,6 +11,18 @@ namespace icar {
 int diagnostic_update_launch(const Geom& g, const float* pressure, const float* th, float* exner, float* density,
                              cudaStream_t st);
 
+// The rest of diagnostic_update, the fields only output / other physics read (time_step.f90:88-108, 165-194):
+//   temperature = th * exner; pressure_i / temperature_i(k > kms) = (x(k-1) + x(k)) / 2, (kms) = x(kms) + (x(kms) - x(kms+1)) / 2
+//   u_mass = (u(i+1) + u(i)) / 2; v_mass = (v(j+1) + v(j)) / 2
+//   w_real(ims+1:ime-1, k, jms+1:jme-1) = (uw(i) + uw(i+1)) * 0.5 + (vw(j) + vw(j+1)) * 0.5 + jacobian * (w(k-1) + w(k)) * 0.5
+//       with uw = u * dzdx, vw = v * dzdy, w(kms-1) = 0; the boundary ring of w_real is never written (stays 0)
+// Any output pointer may be null.  dzdx is u-shaped, dzdy v-shaped (domain_obj.f90:893-900).
+int diagnostic_thermo_launch(const Geom& g, const float* pressure, const float* th, const float* exner,
+                             float* temperature, float* p_i, float* t_i, cudaStream_t st);
+int diagnostic_winds_launch(const Geom& g, const float* u, const float* v, const float* w, const float* dzdx,
+                            const float* dzdy, const float* jaco, float* u_mass, float* v_mass, float* w_real,
+                            cudaStream_t st);
+
 // compute_dt's four maxima over this image's tile (time_step.f90:234-289, use_density = .false.):
 //   out[0] = max over cells of  max|u|/dx + max|v|/dx + max|w|/dz(k)   (the strictness 2/3/4 loop)
 //   out[1..3] = maxval(abs(u)), maxval(abs(v)), maxval(abs(w))

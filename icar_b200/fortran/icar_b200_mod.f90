@@ -32,7 +32,7 @@ module icar_b200_mod
     public :: adv_init, adv_var_request, advect
     public :: mp_init, mp_var_request, mp
     public :: b200_halo_send, b200_halo_retrieve, b200_sync_to_host, b200_finalize, b200_physics_steps
-    public :: b200_diagnostic_update, b200_update_forcing, b200_apply_forcing, b200_enforce_limits, b200_upload_winds
+    public :: b200_diagnostic_update, b200_diagnostic_output, b200_update_forcing, b200_apply_forcing, b200_enforce_limits, b200_upload_winds
     public :: b200_linear_perturb, b200_write_restart, b200_read_restart
 
     ! enum icar_var
@@ -162,6 +162,11 @@ module icar_b200_mod
         integer(c_int) function icar_diagnostic_update(ctx) bind(c)
             import :: c_int, c_ptr
             type(c_ptr), value :: ctx
+        end function
+        integer(c_int) function icar_diagnostic_output(ctx, dzdx, dzdy, temperature, pressure_i, temperature_i, psfc, &
+                                                       u_mass, v_mass, w_real) bind(c)
+            import :: c_int, c_ptr
+            type(c_ptr), value :: ctx, dzdx, dzdy, temperature, pressure_i, temperature_i, psfc, u_mass, v_mass, w_real
         end function
         integer(c_int) function icar_enforce_limits(ctx) bind(c)
             import :: c_int, c_ptr
@@ -348,6 +353,28 @@ contains
     !> diagnostic_update(domain, options), time_step.f90:49-198, for what mp / advect read: exner and density
     subroutine b200_diagnostic_update()
         if (state_on_device) call check(icar_diagnostic_update(ctx), "icar_diagnostic_update")
+    end subroutine
+
+    !> the output-only fields of diagnostic_update (time_step.f90:88-108, 165-194) from the device state, into the host
+    !! arrays of `domain` that are associated: call before output instead of syncing u, v, w, p, th to the host
+    subroutine b200_diagnostic_output(domain)
+        type(domain_t), intent(inout), target :: domain
+        call check(icar_diagnostic_output(ctx, c_loc(domain%dzdx), c_loc(domain%dzdy),                              &
+                   loc3(domain%temperature%data_3d), loc3(domain%pressure_interface%data_3d),                        &
+                   loc3(domain%temperature_interface%data_3d), loc2(domain%surface_pressure%data_2d),               &
+                   loc3(domain%u_mass%data_3d), loc3(domain%v_mass%data_3d), loc3(domain%w_real%data_3d)),           &
+                   "icar_diagnostic_output")
+    contains
+        type(c_ptr) function loc3(a)
+            real, intent(in), pointer :: a(:,:,:)
+            loc3 = c_null_ptr
+            if (associated(a)) loc3 = c_loc(a)
+        end function
+        type(c_ptr) function loc2(a)
+            real, intent(in), pointer :: a(:,:)
+            loc2 = c_null_ptr
+            if (associated(a)) loc2 = c_loc(a)
+        end function
     end subroutine
 
     !> after the boundary object has new tendencies (update_delta_fields, domain_obj.f90:2318-2381): var%dqdt_3d of the

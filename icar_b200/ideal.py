@@ -174,3 +174,16 @@ def slab_of(st, grid):
         else:
             out[k] = np.ascontiguousarray(v[jlo:jhi, :, ilo:ihi])
     return out
+
+
+def terrain_slopes(st):
+    """domain%dzdx (ny, nz, nx+1) and domain%dzdy (ny+1, nz, nx) of setup_dzdxy (domain_obj.f90:1417-1451):
+    differences of the mass-level heights over dx on the interior faces, 0 on the outermost faces."""
+    z, dx = st["z"], np.float32(st["dx"])
+    ny, nz, nx = z.shape
+    dzdx = np.zeros((ny, nz, nx + 1), np.float32)
+    dzdy = np.zeros((ny + 1, nz, nx), np.float32)
+    dzdx[:, :, 1:nx] = (z[:, :, 1:] - z[:, :, :-1]) / dx
+    dzdy[1:ny, :, :] = (z[1:, :, :] - z[:-1, :, :]) / dx
+    return dzdx, dzdy
+

@@ -193,6 +193,22 @@ int icar_physics_steps(icar_ctx* ctx, float dt, int nsteps, int use_graph);
  * density = pressure / (Rd * potential_temperature * exner) (:96,:101), on the device copies. */
 int icar_diagnostic_update(icar_ctx* ctx);
 
+/* The rest of diagnostic_update (src/main/time_step.f90:88-108, 165-194): the fields that output and the other
+ * physics read, computed on the device from the resident state and written to HOST arrays in the reference's
+ * layout (any output may be NULL):
+ *   temperature (nx,nz,ny) = potential_temperature * exner                                            (:96)
+ *   pressure_interface, temperature_interface (nx,nz,ny): level means above kms, half-difference at kms (:88-90, :97-98)
+ *   surface_pressure (nx,ny) = pressure_interface(:, kms, :)                                          (:93)
+ *   u_mass, v_mass (nx,nz,ny) = means of the two faces of a cell                                      (:103-108)
+ *   w_real (nx,nz,ny): the real vertical motion, u * dzdx and v * dzdy averaged to the mass grid plus
+ *       jacobian * (w(k-1) + w(k)) / 2, on ims+1:ime-1, jms+1:jme-1; the boundary ring, which the reference never
+ *       writes, comes back 0                                                                          (:165-194)
+ * dzdx (nx+1,nz,ny) and dzdy (nx,nz,ny+1) are domain%dzdx / domain%dzdy (domain_obj.f90:893-900, 1417-1451), host
+ * arrays, needed for w_real only.  exner must be current (icar_diagnostic_update).  Synchronous. */
+int icar_diagnostic_output(icar_ctx* ctx, const float* dzdx, const float* dzdy, float* temperature,
+                           float* pressure_interface, float* temperature_interface, float* surface_pressure,
+                           float* u_mass, float* v_mass, float* w_real);
+
 /* update_dt / compute_dt (src/main/time_step.f90:217-330, 375-423) on the device-resident winds:
  * the CFL maxima for cfl_strictness 1..5 (use_density = .false.), dt = cfl_reduction_factor / maxwind,
  * `co_min` over the images of the communicator (:413; ncclAllReduce(min) of one double) and the

@@ -145,6 +145,13 @@ inline void sync_to_device(const domain_t& domain) {
 inline void b200_diagnostic_update() {
     if (detail::state_on_device()) detail::check(icar_diagnostic_update(detail::ctx()), "icar_diagnostic_update");
 }
+// the output-only fields of diagnostic_update (time_step.f90:88-108, 165-194) from the device state; any pointer may be null
+inline void b200_diagnostic_output(const float* dzdx, const float* dzdy, float* temperature, float* pressure_interface,
+                                   float* temperature_interface, float* surface_pressure, float* u_mass, float* v_mass,
+                                   float* w_real) {
+    detail::check(icar_diagnostic_output(detail::ctx(), dzdx, dzdy, temperature, pressure_interface, temperature_interface,
+                                         surface_pressure, u_mass, v_mass, w_real), "icar_diagnostic_output");
+}
 // var%dqdt_3d of a forced variable (update_delta_fields, domain_obj.f90:2318-2381) goes to the device
 inline void b200_update_forcing(int var, const std::vector<float>& dqdt_3d) {
     if (!dqdt_3d.empty()) detail::check(icar_upload_tendency(detail::ctx(), var, dqdt_3d.data()), "icar_upload_tendency");

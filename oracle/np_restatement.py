@@ -218,6 +218,39 @@ def diagnostic_update_np(pressure, th):
     return exner.astype(np.float32), density.astype(np.float32)
 
 
+def diagnostic_output_np(pressure, th, u, v, w, jacobian, dzdx, dzdy):
+    """The rest of diagnostic_update (src/main/time_step.f90:88-108, 165-194), array expressions as written there.
+    Arrays are (y, z, x): u (ny,nz,nx+1), v (ny+1,nz,nx), dzdx like u, dzdy like v.  float32 throughout."""
+    f = np.float32
+    exner = ((pressure / f(100000)) ** (RD / CP)).astype(f)
+    o = {}
+    pi = np.empty_like(pressure)
+    pi[:, 1:, :] = (pressure[:, :-1, :] + pressure[:, 1:, :]) / f(2)                          # :88
+    pi[:, 0, :] = pressure[:, 0, :] + (pressure[:, 0, :] - pressure[:, 1, :]) / f(2)           # :89
+    o["pressure_interface"] = pi
+    o["surface_pressure"] = pi[:, 0, :].copy()                                                 # :93
+    t = th * exner                                                                             # :96
+    o["temperature"] = t
+    ti = np.empty_like(t)
+    ti[:, 1:, :] = (t[:, :-1, :] + t[:, 1:, :]) / f(2)                                         # :97
+    ti[:, 0, :] = t[:, 0, :] + (t[:, 0, :] - t[:, 1, :]) / f(2)                                # :98
+    o["temperature_interface"] = ti
+    o["u_mass"] = (u[:, :, 1:] + u[:, :, :-1]) / f(2)                                          # :104
+    o["v_mass"] = (v[1:, :, :] + v[:-1, :, :]) / f(2)                                          # :107
+    ny, nz, nx = w.shape
+    wr = np.zeros_like(w)
+    lastw = np.zeros((ny - 2, nx - 2), f)
+    for z in range(nz):                                                                        # :165-194
+        uw = u[1:-1, z, 1:nx] * dzdx[1:-1, z, 1:nx]            # u(ims+1:ime, z, jms+1:jme-1) * dzdx(...)
+        vw = v[1:ny, z, 1:-1] * dzdy[1:ny, z, 1:-1]            # v(ims+1:ime-1, z, jms+1:jme) * dzdy(...)
+        currw = w[1:-1, z, 1:-1]
+        wr[1:-1, z, 1:-1] = ((uw[:, :-1] + uw[:, 1:]) * f(0.5) + (vw[:-1, :] + vw[1:, :]) * f(0.5)
+                             + jacobian[1:-1, z, 1:-1] * (lastw + currw) * f(0.5))
+        lastw = currw
+    o["w_real"] = wr
+    return o
+
+
 def compute_dt_np(dx, u, v, w, dz_levels, cfl, cfl_strictness):
     """compute_dt (src/main/time_step.f90:217-330) with use_density = .false., then update_dt's 120 s cap
     (:421).  u (ny,nz,nx+1), v (ny+1,nz,nx), w (ny,nz,nx); REAL arithmetic.  Raises where the reference

@@ -58,8 +58,9 @@ extern "C" int emu_thompson_driver(int nx, int nz, int ny, int ld, int ld2, cons
     tiles.n = 1;
     tiles.its[0] = its; tiles.ite[0] = ite; tiles.jts[0] = jts; tiles.jte[0] = jte; tiles.along_y[0] = along_y;
     const int w = ite - its + 1, h = jte - jts + 1;
-    const int gx = ((along_y ? h : w) + TX - 1) / TX, gy = along_y ? w : h;
     const int nk = kte - kts + 1;
+    const int TX = th_columns_per_cta(nk);
+    const int gx = ((along_y ? h : w) + TX - 1) / TX, gy = along_y ? w : h;
     if (nk < 1 || nk * TX > 1024) return -1;
     const int nkt = (nk * TX + 31) / 32 * 32 / TX;
     Args A{qv, qc, qr, qi, qs, qg, ni, nr, th, pii, p, dz, rainnc, snownc, nullptr, graupelnc, nullptr, sr, nullptr,
@@ -81,9 +82,11 @@ extern "C" int emu_thompson_driver(int nx, int nz, int ny, int ld, int ld2, cons
                     blockIdx = {(unsigned)bx, (unsigned)by, 0};
                     threadIdx = {(unsigned)(t % TX), (unsigned)(t / TX), 0};
                     blockDim = {(unsigned)TX, (unsigned)nkt, 1};
-                    if (nthreads <= 320) k_mp_thompson<320, 2>(g, c, tb, A, ld2, dt, tiles, kts, kte, diag);
-                    else if (nthreads <= 640) k_mp_thompson<640, 1>(g, c, tb, A, ld2, dt, tiles, kts, kte, diag);
-                    else k_mp_thompson<1024, 1>(g, c, tb, A, ld2, dt, tiles, kts, kte, diag);
+                    if (TX == 16) {
+                        if (nthreads <= 320) k_mp_thompson<16, 320, 2>(g, c, tb, A, ld2, dt, tiles, kts, kte, diag);
+                        else k_mp_thompson<16, 640, 1>(g, c, tb, A, ld2, dt, tiles, kts, kte, diag);
+                    } else if (nthreads <= 640) k_mp_thompson<8, 640, 1>(g, c, tb, A, ld2, dt, tiles, kts, kte, diag);
+                    else k_mp_thompson<8, 1024, 1>(g, c, tb, A, ld2, dt, tiles, kts, kte, diag);
                 });
             for (auto& th_ : pool) th_.join();
             pthread_barrier_destroy(&cta_barrier);

@@ -30,6 +30,37 @@ def test_diagnostic_update_matches_time_step_f90(gpu_lib):
     np.testing.assert_allclose(ex, st["pii"], rtol=3e-7)
 
 
+def test_diagnostic_output_matches_time_step_f90(gpu_lib):
+    """The output-only fields of diagnostic_update (time_step.f90:88-108, 165-194): temperature, the interface fields,
+    psfc, u_mass, v_mass, w_real -- the same REAL operations in the same order, so equal bit for bit given exner."""
+    st = ideal.make_ideal_case(nx=70, nz=15, ny=11, perturb=True)
+    rng = np.random.default_rng(5)
+    st["v"] = (st["v"] + rng.uniform(-3, 3, st["v"].shape)).astype(np.float32)
+    dzdx, dzdy = ideal.terrain_slopes(st)
+    dzdy = (dzdy + rng.uniform(-0.05, 0.05, dzdy.shape)).astype(np.float32)        # the hill is uniform in y
+    dom = make(gpu_lib, st)
+    dom.diagnostic_update()
+    got = dom.diagnostic_output(dzdx, dzdy)
+    want = NP.diagnostic_output_np(st["pressure"], st["th"], st["u"], st["v"], st["w"], st["jacobian"], dzdx, dzdy)
+    for k in ("pressure_interface", "surface_pressure", "u_mass", "v_mass", "w_real"):
+        assert np.array_equal(got[k], want[k]), k
+    assert np.abs(want["w_real"]).max() > 0.1
+    # temperature goes through the device's powf (exner): <= 2 ulp; from the device's own exner it is exact
+    ex = dom.download("exner")
+    t = st["th"] * ex
+    assert np.array_equal(got["temperature"], t)
+    ti = np.empty_like(t)
+    ti[:, 1:, :] = (t[:, :-1, :] + t[:, 1:, :]) / np.float32(2)
+    ti[:, 0, :] = t[:, 0, :] + (t[:, 0, :] - t[:, 1, :]) / np.float32(2)
+    assert np.array_equal(got["temperature_interface"], ti)
+    np.testing.assert_allclose(got["temperature"], want["temperature"], rtol=3e-7)
+    # a subset of the outputs, and w_real without the slopes is refused
+    only = dom.diagnostic_output(want=("u_mass",))
+    assert list(only) == ["u_mass"] and np.array_equal(only["u_mass"], want["u_mass"])
+    with pytest.raises(gpu_lib.IcarError):
+        dom.diagnostic_output(want=("w_real",))
+
+
 @pytest.mark.parametrize("strictness", [1, 2, 3, 4, 5])
 @pytest.mark.parametrize("scale", [1.0, 0.01])
 def test_compute_dt_all_strictness_levels(gpu_lib, strictness, scale):
