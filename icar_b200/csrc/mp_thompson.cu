@@ -61,17 +61,15 @@ int th_driver_launch(const Geom& g, const ThConst& c, const ThTables& tb, float*
     const size_t smem = (size_t)nk * TX * sizeof(double) + (size_t)7 * (nk + 1) * TX * sizeof(float) + (size_t)10 * TX * sizeof(int);
     const int nthreads = TX * nkt;
 #define TH_LAUNCH(TXC, MAXT, MINB) k_mp_thompson<TXC, MAXT, MINB><<<grid, block, smem, st>>>(g, c, tb, A, ld2, dt, tiles, kts, kte, diag)
-    // 96 registers: two CTAs of <= 320 threads or one of <= 640 per SM (one CTA per SM with 168 registers and no spills
-    // was measured at 10.7 ms per step against 7.8: occupancy matters more than the spills)
-#ifdef ICAR_TH_TX16HI
-    if (TX == 16) { if (nthreads <= 320) { TH_LAUNCH(16, 320, 2); } else if (nthreads <= 640) { TH_LAUNCH(16, 640, 1); } else { TH_LAUNCH(16, 1024, 1); } }
-#else
-    if (TX == 16) { if (nthreads <= 320) { TH_LAUNCH(16, 320, 2); } else { TH_LAUNCH(16, 640, 1); } }
-#endif
-#ifdef ICAR_TH_HI2
-    else if (nthreads <= 416) { TH_LAUNCH(8, 416, 2); }
-    else if (nthreads <= 480) { TH_LAUNCH(8, 480, 2); }
-#endif
+    // registers: what the register file gives the resident CTAs -- 96 for two CTAs of <= 320 threads or one of <= 640,
+    // 80 up to 800 threads, 64 above.  Occupancy matters more than the spills: at 40 levels one CTA per SM with 168
+    // registers and no spills ran at 10.7 ms per step against 7.8; at 50 levels 25 warps with 64 registers beat 13 with 96.
+    if (TX == 16) {
+        if (nthreads <= 320) { TH_LAUNCH(16, 320, 2); }
+        else if (nthreads <= 640) { TH_LAUNCH(16, 640, 1); }
+        else if (nthreads <= 800) { TH_LAUNCH(16, 800, 1); }
+        else { TH_LAUNCH(16, 1024, 1); }
+    }
     else if (nthreads <= 640) { TH_LAUNCH(8, 640, 1); }
     else { TH_LAUNCH(8, 1024, 1); }
 #undef TH_LAUNCH
@@ -80,6 +78,7 @@ int th_driver_launch(const Geom& g, const ThConst& c, const ThTables& tb, float*
 
 bool th_driver_preload() {
     return preload_kernel(k_mp_thompson<16, 320, 2>) && preload_kernel(k_mp_thompson<16, 640, 1>) &&
+           preload_kernel(k_mp_thompson<16, 800, 1>) && preload_kernel(k_mp_thompson<16, 1024, 1>) &&
            preload_kernel(k_mp_thompson<8, 640, 1>) && preload_kernel(k_mp_thompson<8, 1024, 1>);
 }
 

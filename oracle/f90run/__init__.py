@@ -1,0 +1,118 @@
+"""TEST INFRASTRUCTURE -- the reference's own Fortran, executed.
+
+    from oracle import f90run
+    ref = f90run.Reference("/root/reference")          # translates src/physics/adv_mpdata.f90 and mp_simple.f90 in place
+    ref.advect3d(q, U_m, V_m, W_m, jaco, dz, mpdata_order=2, fct=True)          # adv_mpdata.f90:356 on (ny, nz, nx) arrays
+    ref.mp_simple_driver(p, th, pii, rho, qv, qc, qr, qs, rain, snow, dt, dz)  # mp_simple.f90:595
+
+Nothing under /root/reference is copied: the source files are read where they lie, translated statement by statement
+(translate.py) and run on runtime.py (IEEE binary32, glibc expf).  Only tests/ and scripts that make golden vectors
+import this package; it exists so that the hand-written restatements in oracle/ are pinned to outputs of the
+reference's own source text (tests/test_reference_source.py, tests/golden/reference_source_*.npz).
+"""
+import os
+import types
+
+import numpy as np
+
+from .runtime import FArr, f32, f_exp
+from .translate import Module, TranslateError  # noqa: F401
+
+
+def _f(a):
+    """(ny, nz, nx) C-ordered float32 -> the Fortran array (nx, nz, ny) over the SAME memory"""
+    a = np.ascontiguousarray(a, np.float32)
+    return a, a.T
+
+
+class Reference:
+    def __init__(self, root="/root/reference"):
+        phys = os.path.join(root, "src", "physics")
+        self.adv_path = os.path.join(phys, "adv_mpdata.f90")
+        self.mp_path = os.path.join(phys, "mp_simple.f90")
+        for p in (self.adv_path, self.mp_path, os.path.join(phys, "adv_mpdata_FCT_core.f90")):
+            if not os.path.exists(p):
+                raise FileNotFoundError(p)
+        # kVARS (src/constants/icar_constants.f90): only the identity of an index matters to mpdata's scalar list
+        self.kvars = types.SimpleNamespace(**{n: k + 1 for k, n in enumerate(self.ADVECTED)})
+        self.adv = Module(self.adv_path, names={"kvars": self.kvars}).build(["advect3d", "upwind_advection", "mpdata_fluxes", "flux_limiter", "flux1", "mpdata"])
+        self.mp = Module(self.mp_path).build(["mp_simple_driver"])
+
+    exp4 = staticmethod(f_exp)          # exp of a REAL as the translated code evaluates it (glibc expf)
+
+    # the order of mpdata's advect3d calls (adv_mpdata.f90:512-522): kVARS name -> domain component
+    ADVECTED = ("water_vapor", "cloud_water", "rain_in_air", "snow_in_air", "potential_temperature", "cloud_ice",
+                "graupel_in_air", "ice_number_concentration", "rain_number_concentration", "snow_number_concentration",
+                "graupel_number_concentration")
+    COMPONENT = {"water_vapor": "water_vapor", "cloud_water": "cloud_water_mass", "rain_in_air": "rain_mass",
+                 "snow_in_air": "snow_mass", "potential_temperature": "potential_temperature",
+                 "cloud_ice": "cloud_ice_mass", "graupel_in_air": "graupel_mass",
+                 "ice_number_concentration": "cloud_ice_number", "rain_number_concentration": "rain_number",
+                 "snow_number_concentration": "snow_number", "graupel_number_concentration": "graupel_number"}
+
+    def mpdata(self, fields, u, v, w, jacobian_u, jacobian_v, jacobian_w, jacobian, advection_dz, dt, dx,
+               mpdata_order=2, fct=True):
+        """mpdata(domain, options, dt), adv_mpdata.f90:463-524, on a mock domain: `fields` maps kVARS names
+        (ADVECTED) to (ny, nz, nx) float32 arrays, advected in place in the reference's order; u (ny, nz, nx+1),
+        v (ny+1, nz, nx).  The module arrays U_m, V_m, W_m are (re)allocated by the routine itself."""
+        ns = types.SimpleNamespace
+        ny, nz, nx = w.shape
+        fa = lambda a: FArr(_f(a)[1], (1, 1, 1))          # noqa: E731
+        dom = ns(grid=ns(ims=1, ime=nx, kms=1, kme=nz, jms=1, jme=ny), ims=1, ime=nx, kms=1, kme=nz, jms=1, jme=ny,
+                 dx=f32(dx), advection_dz=fa(advection_dz), density=ns(data_3d=None),
+                 u=ns(data_3d=fa(u)), v=ns(data_3d=fa(v)), w=ns(data_3d=fa(w)), jacobian_u=fa(jacobian_u),
+                 jacobian_v=fa(jacobian_v), jacobian_w=fa(jacobian_w), jacobian=fa(jacobian))
+        flags = {}
+        for name in self.ADVECTED:
+            arr = fields.get(name)
+            flags[getattr(self.kvars, name)] = 1 if arr is not None else 0
+            if arr is not None:
+                if not (arr.flags.c_contiguous and arr.dtype == np.float32):
+                    raise ValueError("fields must be C-contiguous float32 (advected in place)")
+                setattr(dom, self.COMPONENT[name], ns(data_3d=FArr(arr.T, (1, 1, 1))))
+        opts = ns(parameters=ns(advect_density=False, debug=False, dz_levels=None), vars_to_advect=flags,
+                  adv_options=ns(mpdata_order=int(mpdata_order), flux_corrected_transport=bool(fct)))
+        M = self.adv.M
+        for n in ("u_m", "v_m", "w_m"):                  # `if (.not.allocated(U_m))`: a new grid needs new module arrays
+            getattr(M, n).a = None
+        self.adv.mpdata(dom, opts, f32(dt))
+
+    def set_winds(self, U_m, V_m, W_m):
+        """the module arrays U_m (ims+1:ime, :, :), V_m (:, :, jms+1:jme), W_m, given as (ny, nz, nx-1), (ny-1, nz, nx),
+        (ny, nz, nx) arrays (adv_mpdata.f90:492-495 bounds, ims = kms = jms = 1)"""
+        M = self.adv.M
+        M.u_m = FArr(np.asfortranarray(np.asarray(U_m, np.float32).T), (2, 1, 1))
+        M.v_m = FArr(np.asfortranarray(np.asarray(V_m, np.float32).T), (1, 1, 2))
+        M.w_m = FArr(np.asfortranarray(np.asarray(W_m, np.float32).T), (1, 1, 1))
+
+    def advect3d(self, q, jaco, dz, mpdata_order=2, fct=True, rho=None):
+        """advect3d(q, rho, ims, ime, kms, kme, jms, jme, jaco, dz, options), adv_mpdata.f90:356; q (ny, nz, nx) is
+        updated in place and returned"""
+        qc, qf = _f(q)
+        ny, nz, nx = qc.shape
+        rho = np.ones_like(qc) if rho is None else rho
+        opts = types.SimpleNamespace(adv_options=types.SimpleNamespace(mpdata_order=int(mpdata_order),
+                                                                       flux_corrected_transport=bool(fct)))
+        self.adv.advect3d(qf, _f(rho)[1], 1, nx, 1, nz, 1, ny, _f(jaco)[1], _f(dz)[1], opts)
+        return qc
+
+    def upwind_advection(self, qin, u, v, w, rho, dz, jaco):
+        """upwind_advection (adv_mpdata.f90:44): returns q; u (ny, nz, nx-1), v (ny-1, nz, nx), w (ny, nz, nx)"""
+        qc, qf = _f(qin)
+        ny, nz, nx = qc.shape
+        out = np.zeros_like(qc)
+        self.adv.upwind_advection(qf, _f(u)[1], _f(v)[1], _f(w)[1], _f(rho)[1], out.T, _f(dz)[1], 1, nx, 1, nz, 1, ny, _f(jaco)[1])
+        return out
+
+    # ---- mp_simple.f90
+    def mp_simple_driver(self, pressure, th, pii, rho, qv, qc, qr, qs, rain, snow, dt, dz, tile=None):
+        """mp_simple_driver (mp_simple.f90:595) on (ny, nz, nx) / (ny, nx) float32 arrays, updated in place.
+        tile = (its, ite, jts, jte, kts, kte), 1-based inclusive; default the whole memory tile."""
+        arrs = [np.ascontiguousarray(a, np.float32) for a in (pressure, th, pii, rho, qv, qc, qr, qs)]
+        for a, b in zip(arrs, (pressure, th, pii, rho, qv, qc, qr, qs)):
+            if a is not b:
+                raise ValueError("mp_simple_driver needs C-contiguous float32 arrays (updated in place)")
+        ny, nz, nx = arrs[0].shape
+        its, ite, jts, jte, kts, kte = tile or (1, nx, 1, ny, 1, nz)
+        self.mp.mp_simple_driver(*[a.T for a in arrs], rain.T, snow.T, f32(dt), _f(dz)[1],
+                                 1, nx, 1, ny, 1, nz, its, ite, jts, jte, kts, kte)

@@ -1,0 +1,1021 @@
+"""TEST INFRASTRUCTURE -- a mechanical translator from a subset of Fortran 90 to Python/NumPy.
+
+Purpose: the reference (NCAR/icar) is Fortran and no Fortran compiler exists in this image, so its own source files
+cannot be compiled here.  This module EXECUTES them instead: it reads a module source file where it lies (never copied
+into this repository), translates every statement one to one -- same operations, same order, same types -- and the
+result runs on oracle/f90run/runtime.py, whose REAL arithmetic is IEEE binary32 with glibc's expf/powf.  The outputs pin
+the hand-written restatements (oracle/*.hpp, oracle/np_restatement.py) to the reference's own text.
+
+The subset is what src/physics/adv_mpdata.f90 (+ the included adv_mpdata_FCT_core.f90) and src/physics/mp_simple.f90 use:
+modules with parameters / module variables / contained subroutines and functions; INTEGER, REAL, DOUBLE PRECISION,
+LOGICAL; explicit-shape, assumed-shape, automatic, allocatable and pointer arrays with arbitrary lower bounds; array
+sections and whole-array expressions; IF / ELSE IF / DO / DO WHILE / EXIT / CYCLE / CALL / ALLOCATE / INCLUDE /
+ASSOCIATE; derived-type components (read through Python attributes).  Anything else raises TranslateError: nothing
+is skipped silently inside a routine that is asked for (PRINT is a no-op, STOP raises).
+"""
+import os
+import re
+import types
+
+from . import runtime as R
+
+
+class TranslateError(Exception):
+    pass
+
+
+PY_KEYWORDS = {"in", "is", "lambda", "from", "pass", "del", "not", "and", "or", "if", "else", "elif", "for", "while", "def",
+               "class", "return", "global", "import", "as", "with", "try", "except", "raise", "yield", "assert", "None",
+               "True", "False", "print", "exec", "nonlocal", "finally", "break", "continue", "async", "await"}
+
+
+def py_name(n):
+    return n + "_" if n in PY_KEYWORDS else n
+
+
+# ============================================================================================ source -> statements
+def _strip_comment(line):
+    out, q = [], None
+    for ch in line:
+        if q:
+            out.append(ch)
+            if ch == q:
+                q = None
+        elif ch in "'\"":
+            q = ch
+            out.append(ch)
+        elif ch == "!":
+            break
+        else:
+            out.append(ch)
+    return "".join(out).rstrip()
+
+
+def _lower_outside_strings(s):
+    out, q = [], None
+    for ch in s:
+        if q:
+            out.append(ch)
+            if ch == q:
+                q = None
+        else:
+            if ch in "'\"":
+                q = ch
+            out.append(ch.lower())
+    return "".join(out)
+
+
+def read_statements(path, _depth=0):
+    """[(file, first line number, statement text)]: comments stripped, continuations joined, INCLUDEs inlined."""
+    if _depth > 5:
+        raise TranslateError("include depth")
+    stmts = []
+    with open(path) as f:
+        lines = f.read().split("\n")
+    cur, cur_no = "", 0
+    for no, raw in enumerate(lines, 1):
+        line = _strip_comment(raw)
+        if not line.strip():
+            continue
+        text = line.strip()
+        if cur:
+            if text.startswith("&"):
+                text = text[1:].lstrip()
+            cur += " " + text
+        else:
+            cur, cur_no = text, no
+        if cur.endswith("&"):
+            cur = cur[:-1].rstrip()
+            continue
+        for piece in _split_semicolons(cur):
+            piece = _lower_outside_strings(piece.strip())
+            if not piece:
+                continue
+            m = re.match(r"include\s+['\"]([^'\"]+)['\"]$", piece)
+            if m:
+                inc = os.path.join(os.path.dirname(path), m.group(1))
+                stmts.extend(read_statements(inc, _depth + 1))
+            else:
+                stmts.append((os.path.basename(path), cur_no, piece))
+        cur = ""
+    return stmts
+
+
+def _split_semicolons(s):
+    out, cur, q = [], [], None
+    for ch in s:
+        if q:
+            cur.append(ch)
+            if ch == q:
+                q = None
+        elif ch in "'\"":
+            q = ch
+            cur.append(ch)
+        elif ch == ";":
+            out.append("".join(cur))
+            cur = []
+        else:
+            cur.append(ch)
+    out.append("".join(cur))
+    return out
+
+
+# ============================================================================================ tokens
+TOKEN_RE = re.compile(r"""
+    (?P<str>'(?:[^']|'')*'|"(?:[^"]|"")*")
+  | (?P<num>(?:\d+\.(?![a-z]+\.)\d*|\.\d+|\d+)(?:[ed][+-]?\d+)?(?:_\w+)?)
+  | (?P<dot>\.(?:and|or|not|eqv|neqv|eq|ne|lt|le|gt|ge|true|false)\.)
+  | (?P<name>[a-z]\w*)
+  | (?P<op>\*\*|//|==|/=|<=|>=|=>|[-+*/<>=(),:%\[\]])
+  | (?P<ws>\s+)
+""", re.X)
+
+
+def tokenize(s):
+    toks, pos = [], 0
+    while pos < len(s):
+        m = TOKEN_RE.match(s, pos)
+        if not m:
+            raise TranslateError(f"cannot tokenize {s[pos:pos + 20]!r} in {s!r}")
+        pos = m.end()
+        kind = m.lastgroup
+        if kind == "ws":
+            continue
+        toks.append((kind, m.group()))
+    toks.append(("end", ""))
+    return toks
+
+
+REL = {"==": "==", "/=": "!=", "<": "<", "<=": "<=", ">": ">", ">=": ">=",
+       ".eq.": "==", ".ne.": "!=", ".lt.": "<", ".le.": "<=", ".gt.": ">", ".ge.": ">="}
+
+INTRINSICS = {"abs", "max", "min", "amax1", "amin1", "maxval", "minval", "sum", "size", "exp", "log", "alog", "log10",
+              "alog10", "sqrt", "ceiling", "floor", "nint", "int", "real", "float", "dble", "mod", "sign", "merge",
+              "this_image", "num_images", "allocated", "associated"}
+INT_RESULT = {"size", "ceiling", "floor", "nint", "int", "this_image", "num_images"}
+
+
+class Var:
+    def __init__(self, name, kind, dims=None, intent=None, parameter=False, allocatable=False, pointer=False,
+                 init=None, dummy=False, module=False, derived=False):
+        self.name, self.kind, self.dims = name, kind, dims
+        self.intent, self.parameter, self.allocatable, self.pointer = intent, parameter, allocatable, pointer
+        self.init, self.dummy, self.module, self.derived = init, dummy, module, derived
+
+    @property
+    def is_array(self):
+        return self.dims is not None
+
+
+DTYPE = {"r": "_f32", "d": "_f64", "i": "_i32", "l": "bool"}
+
+
+class Scope:
+    """Names visible in one routine: its own declarations over the module's."""
+
+    def __init__(self, module, routine=None):
+        self.module, self.routine = module, routine
+        self.locals = {}
+        self.aliases = {}          # associate names -> python expression
+
+    def lookup(self, name):
+        if name in self.locals:
+            return self.locals[name]
+        return self.module.vars.get(name)
+
+    def ref(self, name):
+        """python expression of a variable reference"""
+        if name in self.aliases:
+            return self.aliases[name]
+        if name in self.locals:
+            return py_name(name)
+        if name in self.module.vars:
+            return "_M." + py_name(name)
+        raise TranslateError(f"undeclared name {name!r} in {self.routine}")
+
+
+class ExprParser:
+    """Recursive descent over Fortran's operator precedence; emits a python expression and a kind tag
+    ('i' integer, 'r' real, 'd' double, 'l' logical, '?' unknown / derived component)."""
+
+    def __init__(self, toks, scope, consts):
+        self.t, self.p, self.scope, self.consts = toks, 0, scope, consts
+
+    def peek(self):
+        return self.t[self.p]
+
+    def next(self):
+        tok = self.t[self.p]
+        self.p += 1
+        return tok
+
+    def accept(self, kind, val=None):
+        k, v = self.t[self.p]
+        if k == kind and (val is None or v == val):
+            self.p += 1
+            return True
+        return False
+
+    def expect(self, kind, val=None):
+        if not self.accept(kind, val):
+            raise TranslateError(f"expected {val or kind}, got {self.t[self.p]} in {' '.join(v for _, v in self.t)}")
+
+    # ---- precedence levels
+    def expr(self):
+        return self.or_()
+
+    def or_(self):
+        c, k = self.and_()
+        while self.peek() == ("dot", ".or."):
+            self.next()
+            c2, _ = self.and_()
+            c, k = f"({c} or {c2})", "l"
+        return c, k
+
+    def and_(self):
+        c, k = self.not_()
+        while self.peek() == ("dot", ".and."):
+            self.next()
+            c2, _ = self.not_()
+            c, k = f"({c} and {c2})", "l"
+        return c, k
+
+    def not_(self):
+        if self.peek() == ("dot", ".not."):
+            self.next()
+            c, _ = self.not_()
+            return f"(not {c})", "l"
+        return self.rel()
+
+    def rel(self):
+        c, k = self.add()
+        kind, v = self.peek()
+        if (kind == "op" and v in REL) or (kind == "dot" and v in REL):
+            self.next()
+            c2, _ = self.add()
+            return f"({c} {REL[v]} {c2})", "l"
+        return c, k
+
+    @staticmethod
+    def _join(k1, k2):
+        if "?" in (k1, k2):
+            return "?"
+        if "d" in (k1, k2):
+            return "d"
+        if "r" in (k1, k2):
+            return "r"
+        return "i"
+
+    def add(self):
+        kind, v = self.peek()
+        if kind == "op" and v in "+-":
+            self.next()
+            c, k = self.mul()
+            c = f"(-{c})" if v == "-" else c
+        else:
+            c, k = self.mul()
+        while True:
+            kind, v = self.peek()
+            if kind == "op" and v in ("+", "-"):
+                self.next()
+                c2, k2 = self.mul()
+                c, k = f"({c} {v} {c2})", self._join(k, k2)
+            else:
+                return c, k
+
+    def mul(self):
+        c, k = self.pow_()
+        while True:
+            kind, v = self.peek()
+            if kind == "op" and v == "*":
+                self.next()
+                c2, k2 = self.pow_()
+                c, k = f"({c} * {c2})", self._join(k, k2)
+            elif kind == "op" and v == "/":
+                self.next()
+                c2, k2 = self.pow_()
+                kk = self._join(k, k2)
+                # integer / integer truncates; decided at run time unless an operand is known to be real
+                c = f"({c} / {c2})" if kk in ("r", "d") else f"_div({c}, {c2})"
+                k = kk
+            else:
+                return c, k
+
+    def pow_(self):
+        c, k = self.primary()
+        if self.peek() == ("op", "**"):
+            self.next()
+            # right associative; a unary minus in the exponent is allowed
+            kind, v = self.peek()
+            if kind == "op" and v in "+-":
+                self.next()
+                c2, k2 = self.pow_()
+                c2 = f"(-{c2})" if v == "-" else c2
+            else:
+                c2, k2 = self.pow_()
+            return f"_pow({c}, {c2})", (k if k2 == "i" else self._join(k, k2))
+        return c, k
+
+    def literal(self, text):
+        t = text
+        kindsuffix = None
+        if "_" in t:
+            t, kindsuffix = t.split("_", 1)
+        if re.fullmatch(r"\d+", t):
+            return t.lstrip("0") or "0", "i"
+        if "d" in t or kindsuffix in ("dp", "8", "real64", "r8"):
+            return f"_f64({float(t.replace('d', 'e'))!r})", "d"
+        idx = self.consts.setdefault(t, len(self.consts))
+        return f"_C[{idx}]", "r"
+
+    def args(self):
+        """after '(' : list of ('expr', code, kind) | ('sec', lo, hi, step) up to ')'"""
+        out = []
+        if self.accept("op", ")"):
+            return out
+        while True:
+            out.append(self.arg())
+            if self.accept("op", ","):
+                continue
+            self.expect("op", ")")
+            return out
+
+    def arg(self):
+        lo = hi = st = None
+        if self.peek() != ("op", ":"):
+            # keyword argument name=expr (only for intrinsics like real(x, kind=...)): not needed in the subset
+            lo = self.expr()
+            if self.peek() != ("op", ":"):
+                return ("expr", lo[0], lo[1])
+        self.expect("op", ":")
+        if self.peek()[1] not in (",", ")", ":"):
+            hi = self.expr()
+        if self.accept("op", ":"):
+            st = self.expr()
+        return ("sec", lo[0] if lo else None, hi[0] if hi else None, st[0] if st else None)
+
+    @staticmethod
+    def subscript(args):
+        parts = []
+        for a in args:
+            if a[0] == "expr":
+                parts.append(a[1])
+            elif a[1] is None and a[2] is None and a[3] is None:
+                parts.append("_ALL")
+            else:
+                parts.append(f"_Sl({a[1]}, {a[2]}, {a[3]})")
+        return ", ".join(parts)
+
+    def primary(self):
+        kind, v = self.next()
+        if kind == "num":
+            return self.literal(v)
+        if kind == "dot" and v in (".true.", ".false."):
+            return ("True" if v == ".true." else "False"), "l"
+        if kind == "str":
+            return repr(v[1:-1]), "?"
+        if kind == "op" and v == "(":
+            c, k = self.expr()
+            self.expect("op", ")")
+            return f"({c})", k
+        if kind == "op" and v == "[":
+            raise TranslateError("array constructors are outside the subset")
+        if kind != "name":
+            raise TranslateError(f"unexpected token {v!r} in {' '.join(x for _, x in self.t)}")
+        name = v
+        # ---- derived-type component chain: read through python attributes
+        if self.peek() == ("op", "%"):
+            code = self.scope.ref(name) if (name in self.scope.locals or name in self.scope.module.vars or
+                                             name in self.scope.aliases) else py_name(name)
+            while self.accept("op", "%"):
+                _, comp = self.next()
+                code += "." + py_name(comp)
+                if self.peek() == ("op", "("):
+                    self.next()
+                    a = self.args()
+                    code += f"[{self.subscript(a)}]"
+                    if self.peek() != ("op", "%"):
+                        return code, "?"
+            return f"_A({code})", "?"
+        var = self.scope.lookup(name) if name not in self.scope.aliases else None
+        if name in self.scope.aliases:
+            code = self.scope.aliases[name]
+            if self.accept("op", "("):
+                a = self.args()
+                return f"{code}[{self.subscript(a)}]", "?"
+            return f"_A({code})", "?"
+        if self.peek() == ("op", "("):
+            self.next()
+            if var is not None and var.is_array:
+                a = self.args()
+                return f"{self.scope.ref(name)}[{self.subscript(a)}]", var.kind
+            if var is not None and not var.is_array and self.scope.routine and name == self.scope.routine.result:
+                pass        # fall through: a recursive call is outside the subset, handled as a function below
+            a = self.args()
+            if any(x[0] != "expr" for x in a):
+                raise TranslateError(f"{name}(...) with a section but {name} is not an array")
+            argc = ", ".join(x[1] for x in a)
+            if name in self.scope.module.routines:
+                r = self.scope.module.routines[name]
+                if not r.is_function:
+                    raise TranslateError(f"subroutine {name} used as a function")
+                self.scope.module.need(name)
+                return f"_F_{name}({argc})", r.result_kind
+            if name in INTRINSICS:
+                if name in INT_RESULT:
+                    k = "i"
+                elif name in ("real", "float"):
+                    k = "r"
+                elif name == "dble":
+                    k = "d"
+                elif name in ("allocated", "associated"):
+                    k = "l"
+                else:
+                    ks = [x[2] for x in a]
+                    k = ks[0] if ks else "?"
+                    for kk in ks[1:]:
+                        k = self._join(k, kk)
+                return f"_fn_{name}({argc})", k
+            raise TranslateError(f"unknown function or array {name!r}")
+        if var is None:
+            if name in INTRINSICS:
+                raise TranslateError(f"intrinsic {name} without arguments")
+            raise TranslateError(f"undeclared name {name!r} in {self.scope.routine.name if self.scope.routine else 'module'}")
+        if var.is_array:
+            return f"{self.scope.ref(name)}.a", var.kind
+        return self.scope.ref(name), var.kind
+
+
+# ============================================================================================ declarations
+DECL_RE = re.compile(r"^(real|integer|logical|double\s+precision|character|type\s*\(|class\s*\()")
+
+
+def split_top(s, sep=","):
+    out, cur, depth, q = [], [], 0, None
+    for ch in s:
+        if q:
+            cur.append(ch)
+            if ch == q:
+                q = None
+            continue
+        if ch in "'\"":
+            q = ch
+        elif ch in "([":
+            depth += 1
+        elif ch in ")]":
+            depth -= 1
+        if ch == sep and depth == 0:
+            out.append("".join(cur).strip())
+            cur = []
+        else:
+            cur.append(ch)
+    out.append("".join(cur).strip())
+    return out
+
+
+def parse_declaration(stmt):
+    """-> (kind, attrs dict, [(name, dims or None, init or None)]) or None if not a declaration"""
+    if not DECL_RE.match(stmt) or re.match(r"^(real|integer|logical|double\s+precision)\s+function\b", stmt):
+        return None
+    if "::" in stmt:
+        left, right = stmt.split("::", 1)
+    else:
+        m = re.match(r"^(real|integer|logical|double\s+precision)\s*(\([^)]*\)|\*\s*\d+)?\s+(.*)$", stmt)
+        if not m:
+            return None
+        left, right = m.group(1) + (m.group(2) or ""), m.group(3)
+    parts = split_top(left.strip())
+    spec = parts[0].replace(" ", "")
+    derived = False
+    if spec.startswith("doubleprecision") or spec in ("real(8)", "real*8", "real(kind=8)", "real(dp)", "real(real64)"):
+        kind = "d"
+    elif spec.startswith("real"):
+        kind = "r"
+    elif spec.startswith("integer"):
+        kind = "i"
+    elif spec.startswith("logical"):
+        kind = "l"
+    elif spec.startswith("type(") or spec.startswith("class("):
+        kind, derived = "?", True
+    else:
+        kind = "?"
+    attrs = {"derived": derived}
+    for a in parts[1:]:
+        a = a.strip()
+        al = a.replace(" ", "")
+        if al.startswith("dimension("):
+            attrs["dims"] = a[a.index("(") + 1:a.rindex(")")]
+        elif al.startswith("intent("):
+            attrs["intent"] = al[7:-1]
+        elif al in ("parameter", "allocatable", "pointer", "target", "optional", "save", "private", "public", "value"):
+            attrs[al] = True
+        else:
+            raise TranslateError(f"declaration attribute {a!r} outside the subset: {stmt}")
+    ents = []
+    for e in split_top(right.strip()):
+        init = None
+        m = re.match(r"^(\w+)\s*(\((.*)\))?\s*(=\s*(.*))?$", e)
+        if not m:
+            raise TranslateError(f"cannot parse entity {e!r} in {stmt}")
+        if "=>" in e:
+            raise TranslateError(f"pointer initialisation outside the subset: {stmt}")
+        name, dims, init = m.group(1), m.group(3), m.group(5)
+        ents.append((name, dims if dims is not None else attrs.get("dims"), init))
+    return kind, attrs, ents
+
+
+# ============================================================================================ module / routine model
+class Routine:
+    def __init__(self, name, is_function, args, result, prefix_kind):
+        self.name, self.is_function, self.args = name, is_function, args
+        self.result = result or (name if is_function else None)
+        self.result_kind = prefix_kind
+        self.body = []                      # [(file, line, text)]
+        self.decls = {}                     # name -> Var
+        self.decl_order = []
+        self.exec_start = 0
+        self.py = None
+
+    def out_positions(self):
+        """positions of scalar dummies a call has to copy back (anything not intent(in))"""
+        out = []
+        for n, a in enumerate(self.args):
+            v = self.decls.get(a)
+            if v is None:
+                raise TranslateError(f"dummy argument {a} of {self.name} is not declared")
+            if not v.is_array and not v.derived and v.intent != "in":
+                out.append(n)
+        return out
+
+
+class Module:
+    """One Fortran module file, translated lazily routine by routine."""
+
+    def __init__(self, path, externals=None, names=None):
+        self.path = path
+        self.names = names or {}             # entities of other modules the source refers to (e.g. kVARS)
+        self.stmts = read_statements(path)
+        self.vars = {}
+        self.var_order = []
+        self.routines = {}
+        self.consts = {}
+        self.needed, self.done = [], set()
+        self.externals = externals or {}     # routine name -> python callable (routines of other modules)
+        self._split()
+        self._parse_module_decls()
+        for r in self.routines.values():
+            self._parse_routine_decls(r)
+
+    # ---- structure
+    def _split(self):
+        cur, in_contains, self.spec = None, False, []
+        for st in self.stmts:
+            _, _, t = st
+            m = re.match(r"^(?:(real|integer|logical|double\s+precision)\s+)?(?:(?:pure|elemental|recursive)\s+)*"
+                         r"(subroutine|function)\s+(\w+)\s*(?:\((.*?)\))?\s*(?:result\s*\(\s*(\w+)\s*\))?$", t)
+            if m and cur is None and in_contains:
+                pk = {"real": "r", "integer": "i", "logical": "l"}.get((m.group(1) or "").split()[0] if m.group(1) else "", None)
+                if m.group(1) and m.group(1).startswith("double"):
+                    pk = "d"
+                args = [a.strip() for a in (m.group(4) or "").split(",") if a.strip()]
+                cur = Routine(m.group(3), m.group(2) == "function", args, m.group(5), pk)
+                continue
+            if cur is not None:
+                if re.match(r"^end\s*(subroutine|function)?(\s+\w+)?$", t) and not re.match(r"^end\s*(if|do|associate|where)", t):
+                    self.routines[cur.name] = cur
+                    cur = None
+                else:
+                    cur.body.append(st)
+                continue
+            if t == "contains":
+                in_contains = True
+                continue
+            if not in_contains:
+                self.spec.append(st)
+
+    def _parse_module_decls(self):
+        for f, no, t in self.spec:
+            d = parse_declaration(t)
+            if d is None:
+                continue
+            kind, attrs, ents = d
+            for name, dims, init in ents:
+                self.vars[name] = Var(name, kind, dims, None, attrs.get("parameter", False), attrs.get("allocatable", False),
+                                      attrs.get("pointer", False), init, module=True, derived=attrs["derived"])
+                self.var_order.append(name)
+
+    def _parse_routine_decls(self, r):
+        n = 0
+        for n, (f, no, t) in enumerate(r.body):
+            if t.startswith("use ") or t.startswith("implicit ") or t.startswith("!$"):
+                continue
+            d = parse_declaration(t)
+            if d is None:
+                break
+            kind, attrs, ents = d
+            for name, dims, init in ents:
+                r.decls[name] = Var(name, kind, dims, attrs.get("intent"), attrs.get("parameter", False),
+                                    attrs.get("allocatable", False), attrs.get("pointer", False), init,
+                                    dummy=name in r.args, derived=attrs["derived"])
+                r.decl_order.append(name)
+        else:
+            n = len(r.body)
+        r.exec_start = n
+        if r.is_function:
+            if r.result in r.decls:
+                r.result_kind = r.decls[r.result].kind
+            elif r.result_kind is None:
+                raise TranslateError(f"function {r.name}: result type unknown")
+            else:
+                r.decls[r.result] = Var(r.result, r.result_kind)
+                r.decl_order.append(r.result)
+
+    def need(self, name):
+        if name not in self.done and name not in self.needed:
+            self.needed.append(name)
+
+    # ---- expressions
+    def expr(self, text, scope):
+        p = ExprParser(tokenize(text), scope, self.consts)
+        c, k = p.expr()
+        if p.peek()[0] != "end":
+            raise TranslateError(f"trailing tokens in expression {text!r}")
+        return c, k
+
+    def bounds(self, dims, scope):
+        """'ims:ime, kms:kme' -> python list literal of (lo, hi); ':' -> (1, None)"""
+        out, deferred = [], False
+        for d in split_top(dims):
+            d = d.strip()
+            if d == ":":
+                out.append("(1, None)")
+                deferred = True
+                continue
+            if ":" in d:
+                lo, hi = split_top(d, ":")
+                lo = lo.strip() or "1"
+                if hi.strip() in ("", "*"):
+                    out.append(f"({self.expr(lo, scope)[0]}, None)")
+                    deferred = True
+                else:
+                    out.append(f"({self.expr(lo, scope)[0]}, {self.expr(hi, scope)[0]})")
+            else:
+                out.append(f"(1, {self.expr(d, scope)[0]})")
+        return "[" + ", ".join(out) + "]", deferred, len(out)
+
+    # ---- statements
+    def translate(self, name):
+        r = self.routines[name]
+        scope = Scope(self, r)
+        scope.locals = dict(r.decls)
+        L = []                                             # python lines
+        ind = 1
+
+        def emit(s, at=None):
+            L.append("    " * (ind if at is None else at) + s)
+
+        emit(f"def _F_{name}({', '.join(py_name(a) for a in r.args)}):", 0)
+        # prologue: dummies under their declared bounds, locals allocated / initialised
+        for vn in r.decl_order:
+            v = r.decls[vn]
+            pn = py_name(vn)
+            if v.derived:
+                continue
+            if v.parameter:
+                emit(f"{pn} = {self.convert(self.expr(v.init, scope)[0], v.kind)}")
+                continue
+            if v.dummy:
+                if v.is_array:
+                    b, _, _ = self.bounds(v.dims, scope)
+                    emit(f"{pn} = _wrap({pn}, {b}, {DTYPE[v.kind]})")
+                elif v.intent == "in" or True:
+                    emit(f"{pn} = {self.convert(pn, v.kind)}")
+                continue
+            if v.is_array:
+                b, deferred, rank = self.bounds(v.dims, scope)
+                if v.pointer:
+                    emit(f"{pn} = None")
+                elif v.allocatable or deferred:
+                    emit(f"{pn} = _unallocated({DTYPE[v.kind]}, {rank})")
+                else:
+                    emit(f"{pn} = _alloc({DTYPE[v.kind]}, {b})")
+            else:
+                if v.init is not None:
+                    raise TranslateError(f"{name}: local {vn} has an initialiser (implies SAVE): outside the subset")
+                emit(f"{pn} = {'False' if v.kind == 'l' else self.convert('0', v.kind)}")
+        # executable part
+        block = []                                         # stack of open constructs
+        for f, no, t in r.body[r.exec_start:]:
+            try:
+                ind = self._statement(t, scope, r, emit, block, ind)
+            except TranslateError as e:
+                raise TranslateError(f"{f}:{no}: {e}\n    {t}") from None
+        if block:
+            raise TranslateError(f"{name}: unterminated {block[-1]}")
+        ind = 1
+        emit(self._return(r))
+        return "\n".join(L)
+
+    def convert(self, code, kind):
+        return {"r": f"_r4({code})", "d": f"_r8({code})", "i": f"_i4({code})", "l": f"bool({code})"}.get(kind, code)
+
+    def _return(self, r):
+        if r.is_function:
+            return f"return {self.convert(py_name(r.result), r.result_kind)}"
+        outs = r.out_positions()
+        if not outs:
+            return "return ()"
+        return "return (" + ", ".join(py_name(r.args[n]) for n in outs) + ",)"
+
+    def _lvalue(self, text, scope):
+        """-> (kind of target, python target or None, var, is_whole_array, python object expr)"""
+        text = text.strip()
+        m = re.match(r"^(\w+)\s*(\(.*\))?$", text)
+        if m and "%" not in text:
+            name = m.group(1)
+            if name in scope.aliases:
+                obj = scope.aliases[name]
+                if m.group(2):
+                    p = ExprParser(tokenize(m.group(2)), scope, self.consts)
+                    p.expect("op", "(")
+                    return "elem", f"{obj}[{ExprParser.subscript(p.args())}]", None, False, obj
+                return "whole?", None, None, True, obj
+            v = scope.lookup(name)
+            if v is None:
+                raise TranslateError(f"assignment to undeclared {name!r}")
+            ref = scope.ref(name)
+            if m.group(2):
+                if not v.is_array:
+                    raise TranslateError(f"{name} is not an array")
+                p = ExprParser(tokenize(m.group(2)), scope, self.consts)
+                p.expect("op", "(")
+                return "elem", f"{ref}[{ExprParser.subscript(p.args())}]", v, False, ref
+            if v.is_array:
+                return "whole", None, v, True, ref
+            return "scalar", ref, v, False, ref
+        # component chain
+        p = ExprParser(tokenize(text), scope, self.consts)
+        kind, v0 = p.next()
+        code = scope.ref(v0) if (v0 in scope.locals or v0 in self.vars or v0 in scope.aliases) else py_name(v0)
+        last_sub = False
+        while p.accept("op", "%"):
+            _, comp = p.next()
+            code += "." + py_name(comp)
+            last_sub = False
+            if p.peek() == ("op", "("):
+                p.next()
+                code += f"[{ExprParser.subscript(p.args())}]"
+                last_sub = True
+        if p.peek()[0] != "end":
+            raise TranslateError(f"cannot parse assignment target {text!r}")
+        if last_sub:
+            return "elem", code, None, False, code
+        return "whole?", None, None, True, code
+
+    def _assign(self, lhs, rhs, scope, emit):
+        kind, target, v, whole, obj = self._lvalue(lhs, scope)
+        c, _ = self.expr(rhs, scope)
+        if kind == "scalar":
+            emit(f"{target} = {self.convert(c, v.kind)}")
+        elif kind == "elem":
+            emit(f"{target} = {c}")
+        elif kind == "whole":
+            emit(f"{obj}.assign({c})")
+        else:       # a derived-type component or an associate name without subscripts: array or scalar, known at run time
+            emit(f"_t = {c}")
+            emit(f"if isinstance({obj}, _FArr): {obj}.assign(_t)")
+            emit(f"else: {obj} = _t")
+
+    def _call(self, t, scope, emit):
+        m = re.match(r"^call\s+(\w+)\s*(\((.*)\))?$", t)
+        if not m:
+            raise TranslateError("cannot parse call")
+        name, argtext = m.group(1), m.group(3) or ""
+        actuals = split_top(argtext) if argtext.strip() else []
+        codes = [self.expr(a, scope)[0] for a in actuals]
+        if name in self.routines:
+            r = self.routines[name]
+            if r.is_function:
+                raise TranslateError(f"function {name} called as a subroutine")
+            self.need(name)
+            outs = r.out_positions()
+            if len(actuals) != len(r.args):
+                raise TranslateError(f"call {name}: {len(actuals)} actual arguments for {len(r.args)} dummies (optional arguments are outside the subset)")
+            emit(f"_ret = _F_{name}({', '.join(codes)})")
+            for k, pos in enumerate(outs):
+                a = actuals[pos].strip()
+                if re.match(r"^\w+\s*(\(.*\))?$", a) or "%" in a:
+                    try:
+                        kind, target, v, whole, obj = self._lvalue(a, scope)
+                    except TranslateError:
+                        continue
+                    if kind == "scalar":
+                        emit(f"{target} = {self.convert(f'_ret[{k}]', v.kind)}")
+                    elif kind == "elem":
+                        emit(f"{target} = _ret[{k}]")
+            return
+        if name in self.externals:
+            emit(f"_X_{name}({', '.join(codes)})")
+            return
+        raise TranslateError(f"call to {name!r}: not a routine of this module")
+
+    def _statement(self, t, scope, r, emit_at, block, ind):
+        def emit(s):
+            emit_at(s, ind)
+
+        if t.startswith("!$") or t.startswith("use ") or t.startswith("implicit "):
+            return ind
+        # ---- block ends / middles
+        if re.match(r"^end\s*if$", t):
+            if not block or block.pop() != "if":
+                raise TranslateError("endif without if")
+            return ind - 1
+        if re.match(r"^end\s*do$", t):
+            if not block or block.pop() != "do":
+                raise TranslateError("enddo without do")
+            return ind - 1
+        if re.match(r"^end\s*associate$", t):
+            if not block or block.pop() != "associate":
+                raise TranslateError("end associate without associate")
+            return ind
+        m = re.match(r"^else\s*if\s*\((.*)\)\s*then$", t)
+        if m:
+            emit_at(f"elif {self.expr(m.group(1), scope)[0]}:", ind - 1)
+            emit("pass")
+            return ind
+        if t == "else":
+            emit_at("else:", ind - 1)
+            emit("pass")
+            return ind
+        # ---- block starts
+        m = re.match(r"^if\s*\((.*)\)\s*then$", t)
+        if m:
+            emit(f"if {self.expr(m.group(1), scope)[0]}:")
+            block.append("if")
+            emit_at("pass", ind + 1)
+            return ind + 1
+        m = re.match(r"^do\s+while\s*\((.*)\)$", t)
+        if m:
+            emit(f"while {self.expr(m.group(1), scope)[0]}:")
+            block.append("do")
+            emit_at("pass", ind + 1)
+            return ind + 1
+        m = re.match(r"^do\s+(\w+)\s*=\s*(.*)$", t)
+        if m:
+            var = m.group(1)
+            parts = [self.expr(x, scope)[0] for x in split_top(m.group(2))]
+            emit(f"for {scope.ref(var)} in _do({', '.join(parts)}):")
+            block.append("do")
+            emit_at("pass", ind + 1)
+            return ind + 1
+        if t == "do":
+            emit("while True:")
+            block.append("do")
+            emit_at("pass", ind + 1)
+            return ind + 1
+        m = re.match(r"^associate\s*\((.*)\)$", t)
+        if m:
+            for item in split_top(m.group(1)):
+                an, ex = item.split("=>", 1)
+                p = ExprParser(tokenize(ex.strip()), scope, self.consts)
+                c, _ = p.expr()
+                if c.startswith("_A(") and c.endswith(")"):
+                    c = c[3:-1]                     # the object itself, not its array: the alias may be indexed / assigned
+                scope.aliases[an.strip()] = c
+            block.append("associate")
+            return ind
+        # ---- one-line if
+        if re.match(r"^if\s*\(", t):
+            depth, k = 0, t.index("(")
+            for k in range(t.index("("), len(t)):
+                depth += t[k] == "("
+                depth -= t[k] == ")"
+                if depth == 0:
+                    break
+            cond, rest = t[t.index("(") + 1:k], t[k + 1:].strip()
+            emit(f"if {self.expr(cond, scope)[0]}:")
+            return self._statement(rest, scope, r, emit_at, block, ind + 1) - 1
+        # ---- simple statements
+        if t in ("exit",):
+            emit("break")
+            return ind
+        if t in ("cycle",):
+            emit("continue")
+            return ind
+        if t == "return":
+            emit(self._return(r))
+            return ind
+        if t.startswith("print") or t.startswith("write") or t.startswith("flush"):
+            emit("pass")
+            return ind
+        if t == "stop" or t.startswith("stop ") or t.startswith("error stop"):
+            emit(f"raise _Stop({t!r})")
+            return ind
+        if t.startswith("call "):
+            self._call(t, scope, emit)
+            return ind
+        m = re.match(r"^allocate\s*\((.*)\)$", t)
+        if m:
+            for item in split_top(m.group(1)):
+                mm = re.match(r"^(.*?)\((.*)\)$", item.strip())
+                if not mm:
+                    raise TranslateError("allocate without bounds")
+                target, dims = mm.group(1).strip(), mm.group(2)
+                b, _, _ = self.bounds(dims, scope)
+                if "%" in target:
+                    _, _, _, _, obj = self._lvalue(target, scope)
+                    emit(f"{obj} = _alloc(_f32, {b}, True)")
+                else:
+                    v = scope.lookup(target)
+                    emit(f"{scope.ref(target)} = _alloc({DTYPE[v.kind]}, {b}, True)")
+            return ind
+        m = re.match(r"^deallocate\s*\((.*)\)$", t)
+        if m:
+            for item in split_top(m.group(1)):
+                v = scope.lookup(item.strip())
+                emit(f"{scope.ref(item.strip())} = _unallocated({DTYPE[v.kind]}, {len(split_top(v.dims))})")
+            return ind
+        # ---- assignments
+        depth, q = 0, None
+        for k, ch in enumerate(t):
+            if q:
+                if ch == q:
+                    q = None
+                continue
+            if ch in "'\"":
+                q = ch
+            elif ch == "(":
+                depth += 1
+            elif ch == ")":
+                depth -= 1
+            elif ch == "=" and depth == 0:
+                if t[k:k + 2] == "=>":
+                    lhs, rhs = t[:k].strip(), t[k + 2:].strip()
+                    kind, target, v, whole, obj = self._lvalue(lhs, scope)
+                    rv = scope.lookup(rhs)
+                    if not (whole and rv is not None and rv.is_array):
+                        raise TranslateError("pointer assignment other than `pointer => whole array`")
+                    emit(f"{obj} = {scope.ref(rhs)}")
+                    return ind
+                if t[k:k + 2] == "==" or (k > 0 and t[k - 1] in "<>/="):
+                    continue
+                self._assign(t[:k], t[k + 1:], scope, emit)
+                return ind
+        raise TranslateError("statement outside the subset")
+
+    # ---- build
+    def build(self, entry_points):
+        """Translate the entry points and everything they call; returns a namespace object with the python callables
+        (attribute = routine name), `M` (module variables and parameters) and `source` (the generated python)."""
+        for e in entry_points:
+            self.need(e)
+        chunks = []
+        while self.needed:
+            n = self.needed.pop(0)
+            if n in self.done:
+                continue
+            self.done.add(n)
+            chunks.append(self.translate(n))
+        # module variables and parameters
+        mscope = Scope(self, None)
+        init = ["def _init_module(_M):"]
+        for vn in self.var_order:
+            v = self.vars[vn]
+            if v.derived:
+                continue
+            pn = py_name(vn)
+            if v.is_array:
+                _, deferred, rank = self.bounds(v.dims, mscope) if v.dims else ("", True, 0)
+                if v.allocatable or v.pointer or deferred:
+                    init.append(f"    _M.{pn} = _unallocated({DTYPE.get(v.kind, '_f32')}, {rank})")
+                else:
+                    b, _, _ = self.bounds(v.dims, mscope)
+                    init.append(f"    _M.{pn} = _alloc({DTYPE[v.kind]}, {b})")
+            elif v.init is not None:
+                try:
+                    init.append(f"    _M.{pn} = {self.convert(self.expr(v.init, mscope)[0], v.kind)}")
+                except TranslateError:
+                    if v.parameter and v.kind in "rdil":
+                        raise
+            elif v.kind in "rdi":
+                init.append(f"    _M.{pn} = {self.convert('0', v.kind)}")
+            elif v.kind == "l":
+                init.append(f"    _M.{pn} = False")
+        init.append("    return _M")
+        src = "\n\n".join(["\n".join(init)] + chunks) + "\n"
+        consts = [None] * len(self.consts)
+        for text, idx in self.consts.items():
+            consts[idx] = R.lit4(text)
+        ns = dict(R.NAMES)
+        ns["_C"] = consts
+        ns["_M"] = types.SimpleNamespace()
+        for xn, fn in self.externals.items():
+            ns["_X_" + xn] = fn
+        for nn, val in self.names.items():
+            ns[py_name(nn)] = val
+        exec(compile(src, f"<f90run:{os.path.basename(self.path)}>", "exec"), ns)
+        ns["_init_module"](ns["_M"])
+        out = types.SimpleNamespace(M=ns["_M"], source=src, constants=dict(self.consts))
+        for n in self.done:
+            setattr(out, n, ns["_F_" + n])
+        return out

@@ -84,7 +84,9 @@ extern "C" int emu_thompson_driver(int nx, int nz, int ny, int ld, int ld2, cons
                     blockDim = {(unsigned)TX, (unsigned)nkt, 1};
                     if (TX == 16) {
                         if (nthreads <= 320) k_mp_thompson<16, 320, 2>(g, c, tb, A, ld2, dt, tiles, kts, kte, diag);
-                        else k_mp_thompson<16, 640, 1>(g, c, tb, A, ld2, dt, tiles, kts, kte, diag);
+                        else if (nthreads <= 640) k_mp_thompson<16, 640, 1>(g, c, tb, A, ld2, dt, tiles, kts, kte, diag);
+                        else if (nthreads <= 800) k_mp_thompson<16, 800, 1>(g, c, tb, A, ld2, dt, tiles, kts, kte, diag);
+                        else k_mp_thompson<16, 1024, 1>(g, c, tb, A, ld2, dt, tiles, kts, kte, diag);
                     } else if (nthreads <= 640) k_mp_thompson<8, 640, 1>(g, c, tb, A, ld2, dt, tiles, kts, kte, diag);
                     else k_mp_thompson<8, 1024, 1>(g, c, tb, A, ld2, dt, tiles, kts, kte, diag);
                 });

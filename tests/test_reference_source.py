@@ -1,0 +1,179 @@
+"""The oracle pinned to the REFERENCE'S OWN SOURCE TEXT.
+
+The reference is Fortran and no Fortran compiler exists in this image, so oracle/f90run executes
+src/physics/adv_mpdata.f90 (+ adv_mpdata_FCT_core.f90) and src/physics/mp_simple.f90 themselves: read where they lie,
+translated statement by statement to Python/NumPy, run with IEEE binary32 arithmetic and glibc's expf.
+
+  * test_golden_*: the committed outputs of that execution (tests/golden/reference_source_*.npz, made by
+    tests/golden/make_reference_source_golden.py) against the C++ oracle -- equal in every bit.  These run anywhere.
+  * test_live_*: the same, executed live on fresh inputs, wherever /root/reference exists (this container).
+"""
+import importlib.util
+import os
+
+import numpy as np
+import pytest
+
+from icar_b200 import ideal
+
+REF_ROOT = "/root/reference"
+needs_reference = pytest.mark.skipif(not os.path.exists(os.path.join(REF_ROOT, "src", "physics", "adv_mpdata.f90")),
+                                     reason="the reference source tree is not on this machine")
+
+
+def load(golden_dir, name):
+    return np.load(os.path.join(golden_dir, name))
+
+
+# ------------------------------------------------------------------ committed outputs of the reference source
+def test_golden_hill_case_oracle_equals_reference_source(oracle, golden_dir):
+    g = load(golden_dir, "reference_source_hill_24x10x20_3steps_f32.npz")
+    st = ideal.make_ideal_case(nx=24, nz=10, ny=20, terrain=True)
+    st["qv"] *= np.float32(3.0)
+    dt = np.float32(st["dt"])
+    assert float(dt) == float(g["dt"])
+    for _ in range(3):
+        oracle.step_simple(st, dt, dt, 2, True)
+    for k in ("th", "qv", "qc", "qr", "qs", "rain", "snow"):
+        assert np.array_equal(st[k], g[k]), k
+    assert g["qc"].max() > 1e-4 and g["rain"].max() > 0            # the microphysics was active
+    # ... and the file frozen from the oracle in round 1 holds the same numbers
+    old = load(golden_dir, "hill_24x10x20_3steps_f32.npz")
+    for k in ("th", "qv", "qc", "qr", "qs", "rain", "snow"):
+        assert np.array_equal(old[k], g[k]), k
+
+
+def test_golden_reference_test_scenarios(oracle, golden_dir):
+    """src/tests/test_mpdata.f90:51-111 and src/tests/test_mp_simple.f90:4-33, run through the reference's own
+    advect3d / mp_simple: the oracle reproduces both"""
+    spec = importlib.util.spec_from_file_location("make_golden", os.path.join(golden_dir, "make_golden.py"))
+    mg = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mg)
+    g = load(golden_dir, "reference_source_mpdata_scenario_f32.npz")
+    rows, line = mg.mpdata_scenario(nloops=2)
+    assert np.array_equal(rows, g["rows"]) and np.array_equal(line, g["final_line"])
+    assert g["rows"][:, -2].max() <= 2.0 and g["rows"][:, -1].min() >= 1.0          # FCT: no new extrema
+    t = load(golden_dir, "reference_source_mp_simple_scenario_f32.npz")["table"]
+    assert np.array_equal(mg.mp_simple_scenario(), t)
+    assert t[-1, 5] > 0.05 and t[-1, 6] > 0.01                                      # it rained and snowed
+
+
+def test_golden_random_fields(oracle, golden_dir):
+    r = load(golden_dir, "reference_source_random_f32.npz")
+    for order, fct in ((1, True), (2, True), (2, False), (3, True)):
+        q = r["q"].copy()
+        oracle.advect3d(q, None, r["jaco"], r["dz"], r["U"], r["V"], r["W"], order, fct)
+        assert np.array_equal(q, r[f"advect3d_order{order}_fct{int(fct)}"]), (order, fct)
+    mp = {k: r["mp_in_" + k].copy() for k in ("pressure", "th", "pii", "rho", "dz_mass", "qv", "qc", "qr", "qs")}
+    ny, nz, nx = mp["th"].shape
+    rain = np.zeros((ny, nx), np.float32)
+    snow = np.zeros((ny, nx), np.float32)
+    t = [int(x) - 1 for x in r["mp_tile"]]
+    for _ in range(3):
+        oracle.mp_simple_driver(mp["pressure"], mp["th"], mp["pii"], mp["rho"], mp["qv"], mp["qc"], mp["qr"], mp["qs"],
+                                rain, snow, float(r["mp_dt"]), mp["dz_mass"], *t)
+    for k in ("th", "qv", "qc", "qr", "qs"):
+        assert np.array_equal(mp[k], r["mp_out_" + k]), k
+    assert np.array_equal(rain, r["mp_out_rain"]) and np.array_equal(snow, r["mp_out_snow"])
+
+
+# ------------------------------------------------------------------ the reference source executed live
+@pytest.fixture(scope="module")
+def ref():
+    from oracle import f90run
+    return f90run.Reference(REF_ROOT)
+
+
+@needs_reference
+def test_live_translation_is_complete(ref):
+    """every routine on the path was translated from the files where they lie, nothing was skipped"""
+    for name in ("flux1", "upwind_advection", "mpdata_fluxes", "flux_limiter", "advect3d", "mpdata"):
+        assert callable(getattr(ref.adv, name))
+    for name in ("sat_mr", "cloud_conversion", "cloud2hydrometeor", "phase_change", "mp_conversions", "sediment",
+                 "mp_simple", "mp_simple_driver"):
+        assert callable(getattr(ref.mp, name))
+    assert "adv_mpdata_FCT_core" not in ref.adv.source and "beta_in_i2" in ref.adv.source       # the include was inlined
+    # constants come from the source text, not from this repository
+    assert float(ref.mp.M.lh_vapor) == 2.26e6 and float(ref.mp.M.snow_fall_rate) == 1.5
+    assert ref.mp.M.rain_formation_time_const == np.float32(1) / np.float32(500.0)
+
+
+@needs_reference
+@pytest.mark.parametrize("order,fct", [(1, True), (2, True), (2, False), (3, True)])
+def test_live_advect3d(ref, oracle, order, fct):
+    nx, nz, ny = 11, 6, 8
+    rng = np.random.default_rng(order * 10 + fct)
+    f = np.float32
+    q = rng.uniform(0, 2, (ny, nz, nx)).astype(f)
+    q[rng.random(q.shape) < 0.3] = 0
+    U = rng.uniform(-0.3, 0.3, (ny, nz, nx - 1)).astype(f)
+    V = rng.uniform(-0.3, 0.3, (ny - 1, nz, nx)).astype(f)
+    W = rng.uniform(-20, 20, (ny, nz, nx)).astype(f)
+    jaco = rng.uniform(0.7, 1.0, (ny, nz, nx)).astype(f)
+    dz = rng.uniform(300, 400, (ny, nz, nx)).astype(f)
+    rho = rng.uniform(0.6, 1.2, (ny, nz, nx)).astype(f)
+    ref.set_winds(U, V, W)
+    for density in (None, rho):
+        want = ref.advect3d(q.copy(), jaco, dz, order, fct, rho=density)
+        got = q.copy()
+        oracle.advect3d(got, density, jaco, dz, U, V, W, order, fct)
+        assert np.array_equal(got, want)
+        assert np.abs(want - q).max() > 1e-3
+
+
+@needs_reference
+def test_live_mpdata_driver(ref, oracle):
+    """mpdata(domain, options, dt) itself on a mock domain: the wind normalisation of adv_mpdata.f90:500-506 and the
+    order of the scalar list, against oracle.wind_normalise + advect3d"""
+    st = ideal.make_ideal_case(nx=14, nz=8, ny=9, terrain=True, perturb=True)
+    rng = np.random.default_rng(2)
+    st["v"] = (st["v"] + rng.uniform(-4, 4, st["v"].shape)).astype(np.float32)
+    dt = np.float32(st["dt"])
+    a = {k: st[k].copy() for k in ("qv", "th")}
+    b = {k: st[k].copy() for k in ("qv", "th")}
+    ref.mpdata({"water_vapor": b["qv"], "potential_temperature": b["th"]}, st["u"], st["v"], st["w"], st["jacobian_u"],
+               st["jacobian_v"], st["jacobian_w"], st["jacobian"], st["advection_dz"], dt, st["dx"])
+    U, V, W = oracle.wind_normalise(st["u"], st["v"], st["w"], st["jacobian_u"], st["jacobian_v"], st["jacobian_w"],
+                                    None, dt, np.float32(st["dx"]))
+    M = ref.adv.M
+    assert np.array_equal(M.u_m.a.T, U) and np.array_equal(M.v_m.a.T, V) and np.array_equal(M.w_m.a.T, W)
+    for k in ("qv", "th"):
+        oracle.advect3d(a[k], None, st["jacobian"], st["advection_dz"], U, V, W, 2, True)
+        assert np.array_equal(a[k], b[k]), k
+
+
+@needs_reference
+def test_live_mp_simple_driver(ref, oracle):
+    st = ideal.make_ideal_case(nx=10, nz=9, ny=5, terrain=True, perturb=True)
+    st["qv"] *= np.float32(3.0)
+    names = ("pressure", "th", "pii", "rho", "qv", "qc", "qr", "qs")
+    a = {k: st[k].copy() for k in names}
+    b = {k: st[k].copy() for k in names}
+    ra = np.zeros((5, 10), np.float32); sa = ra.copy(); rb = ra.copy(); sb = ra.copy()
+    for call in range(3):
+        dt = np.float32(30.0 + 10 * call)
+        oracle.mp_simple_driver(*[a[k] for k in names], ra, sa, dt, st["dz_mass"], 1, 8, 0, 3, 0, 8)
+        ref.mp_simple_driver(*[b[k] for k in names], rb, sb, dt, st["dz_mass"], tile=(2, 9, 1, 4, 1, 9))
+        for k in names:
+            assert np.array_equal(a[k], b[k]), (call, k)
+        assert np.array_equal(ra, rb) and np.array_equal(sa, sb)
+    assert ra.max() > 0 and a["qc"].max() > 1e-4
+
+
+@needs_reference
+def test_live_kts_above_kms_reallocates_temperature(ref, oracle):
+    """`temperature = th(i,:,j) * pii(i,:,j)` reallocates the kts:kte array to the whole column (mp_simple.f90:633),
+    so conversions run on kts:kte while maxval(qr) and sedimentation see the whole column: same in the oracle"""
+    st = ideal.make_ideal_case(nx=6, nz=8, ny=4, terrain=True, perturb=True)
+    st["qv"] *= np.float32(3.0)
+    rng = np.random.default_rng(4)
+    st["qr"] = rng.uniform(0, 1e-3, st["qr"].shape).astype(np.float32)
+    names = ("pressure", "th", "pii", "rho", "qv", "qc", "qr", "qs")
+    a = {k: st[k].copy() for k in names}
+    b = {k: st[k].copy() for k in names}
+    ra = np.zeros((4, 6), np.float32); sa = ra.copy(); rb = ra.copy(); sb = ra.copy()
+    oracle.mp_simple_driver(*[a[k] for k in names], ra, sa, 40.0, st["dz_mass"], 0, 5, 0, 3, 1, 6)
+    ref.mp_simple_driver(*[b[k] for k in names], rb, sb, 40.0, st["dz_mass"], tile=(1, 6, 1, 4, 2, 7))
+    for k in names:
+        assert np.array_equal(a[k], b[k]), k
+    assert np.array_equal(ra, rb)
