@@ -308,8 +308,8 @@ def parity_record(args, icar_b200, ideal, st, dt, local_rank):
     from oracle import oracle as O
     O.build()
     scheme = SCHEMES[args.mp]
-    rec = {"oracle": "oracle/ (C++ restatement of the reference Fortran, " + O.STRICT_FLAGS + "); unpinned: the reference "
-                     "ships no vectors for this path and cannot be compiled here"}
+    rec = {"oracle": "oracle/ (C++ restatement of the reference Fortran, " + O.STRICT_FLAGS + "); pinned bit for bit to the "
+                     "reference's own Fortran source executed by oracle/f90run (tests/test_reference_source.py)"}
     if args.mp == "simple":
         # BASELINE config 1: the ideal hill case 100x100x20, 20 coupled steps
         c1 = ideal.make_ideal_case(nx=100, nz=20, ny=100)

@@ -38,6 +38,94 @@ class Reference:
         self.adv = Module(self.adv_path, names={"kvars": self.kvars}).build(["advect3d", "upwind_advection", "mpdata_fluxes", "flux_limiter", "flux1", "mpdata"])
         self.mp = Module(self.mp_path).build(["mp_simple_driver"])
 
+    # ---- mp_thompson.f90
+    # thompson_init runs as written except for the two rain-collection tables, whose builders (qr_acr_qg, qr_acr_qs;
+    # 1.4e10 inner iterations) take the entries from `big_tables` -- the C++ oracle's tables, which have their own
+    # independent NumPy / SciPy check (tests/test_oracle_thompson.py).  Every scalar constant, the bin grids, the four
+    # other table builders (freezeH2O, qi_aut_qs, table_Efrw, table_Efsw), mp_gt_driver and mp_thompson are the
+    # reference's text, executed.
+    BIG_QG = ("tcg_racg", "tmr_racg", "tcr_gacr", "tmg_gacr", "tnr_racg", "tnr_gacr")
+    BIG_QS = ("tcs_racs1", "tmr_racs1", "tcs_racs2", "tmr_racs2", "tcr_sacr1", "tms_sacr1", "tcr_sacr2", "tms_sacr2",
+              "tnr_racs1", "tnr_racs2", "tnr_sacr1", "tnr_sacr2")
+    MP_OPTIONS = dict(nt_c=100.e6, tno=5.0, am_s=0.069, rho_g=500.0, av_s=40.0, bv_s=0.55, fv_s=100.0, av_i=1847.5,
+                      av_g=442.0, bv_g=0.89, ef_si=0.05, ef_rs=0.95, ef_rg=0.75, ef_ri=0.95, c_cubes=0.5, c_sqrd=0.3,
+                      mu_r=0.0, t_adjust=0.0, ef_rw_l=False, ef_sw_l=False)      # options_obj.f90:1259-1280
+
+    FREEZE = ("tpi_qcfz", "tni_qcfz", "tpi_qrfz", "tpg_qrfz", "tni_qrfz", "tnr_qrfz")
+
+    def thompson_build(self, tables, skip_freezeh2o=False):
+        """translate mp_thompson.f90; tables: name -> array in the Fortran's shape for the builders that are not run
+        (qr_acr_qg, qr_acr_qs always; freezeH2O -- 6e6 inner iterations, two minutes here -- on request)"""
+        def fill(names):
+            def f(M):
+                for n in names:
+                    getattr(M, n).a[...] = tables[n]
+            return f
+        path = os.path.join(os.path.dirname(self.mp_path), "mp_thompson.f90")
+        over = {"qr_acr_qg": fill(self.BIG_QG), "qr_acr_qs": fill(self.BIG_QS)}
+        if skip_freezeh2o:
+            over["freezeh2o"] = fill(self.FREEZE)
+        mod = Module(path, externals={"wrf_debug": None, "wrf_error_fatal": None}, overrides=over)
+        self.th = mod.build(["thompson_init", "mp_gt_driver", "mp_thompson", "rslf", "rsif", "wgamma", "gammp", "gammln"])
+        return self.th
+
+    def thompson_init(self, tables, skip_freezeh2o=False, **options):
+        """thompson_init(mp_options), mp_thompson.f90:342 (about three minutes; half a minute without freezeH2O)"""
+        self.thompson_build(tables, skip_freezeh2o)
+        o = dict(self.MP_OPTIONS)
+        o.update(options)
+        self.th.thompson_init(types.SimpleNamespace(**{k: (v if isinstance(v, bool) else f32(v)) for k, v in o.items()}))
+        return self.th
+
+    def thompson_big_slab(self, which, km):
+        """One (k, m) slab, km = (m-1)*37 + (k-1), of the rain-graupel (which = 0: qr_acr_qg) or rain-snow (1: qr_acr_qs)
+        collection tables, computed by the reference's own builder: the routine runs as written with the km range
+        [km, km] -- the range wrf_dm_decomp1d hands one rank of a distributed run (mp_thompson.f90:2903-2907, 3075-3079;
+        the serial build assigns 0 .. ntb_r*ntb_r1-1 there).  Needs thompson_init first.  Returns name -> (28, 28 | 9) slab."""
+        name = ("qr_acr_qg", "qr_acr_qs")[which]
+        path = os.path.join(os.path.dirname(self.mp_path), "mp_thompson.f90")
+        mod = Module(path, externals={"wrf_debug": None, "wrf_error_fatal": None},
+                     patches={name: [(r"^km_s\s*=", f"km_s = {int(km)}"), (r"^km_e\s*=", f"km_e = {int(km)}")]})
+        ns = mod.build([name])
+        # the module state the builder reads: everything thompson_init has set
+        for k, v in vars(self.th.M).items():
+            if isinstance(v, FArr) and k in (self.BIG_QG + self.BIG_QS):
+                setattr(ns.M, k, FArr(np.zeros_like(v.a), v.lb, v.dtype, True))
+            else:
+                setattr(ns.M, k, v)
+        getattr(ns, name)()
+        k, m = km % 37 + 1, km // 37 + 1
+        return {n: getattr(ns.M, n).a[:, :, k - 1, m - 1].copy() for n in (self.BIG_QG if which == 0 else self.BIG_QS)}
+
+    # the order of oracle.Thompson.constants()
+    def thompson_constants(self):
+        M = self.th.M
+        out = [M.mu_c, M.sc3, M.d0i, M.xm0s, M.xm0g, M.am_r, M.am_i, M.am_g]
+        for a in ("cce", "ccg", "cie", "cig", "cre", "crg", "cse", "csg", "cge", "cgg"):
+            out += list(getattr(M, a).a)
+        out += [getattr(M, n) for n in ("t1_qr_qc", "t1_qr_qi", "t2_qr_qi", "t1_qg_qc", "t1_qs_qc", "t1_qs_qi", "t1_qr_ev",
+                                        "t2_qr_ev", "t1_qs_sd", "t2_qs_sd", "t1_qg_sd", "t2_qg_sd", "t1_qs_me", "t2_qs_me",
+                                        "t1_qg_me", "t2_qg_me")]
+        return np.array(out, np.float32)
+
+    def mp_gt_driver(self, st, dt, tile=None):
+        """mp_gt_driver (mp_thompson.f90:772) on a state dict of (ny, nz, nx) float32 arrays (th, qv, qc, qr, qi, qs, qg,
+        ni, nr, pii, pressure, dz_mass) and (ny, nx) rainnc, snownc, graupelnc, sr, updated in place; tile 1-based.
+        The domain is the memory tile (ide = nx, jde = ny), so the routine's own clip to ide-1 / jde-1 (:821-822) applies."""
+        ny, nz, nx = st["th"].shape
+        its, ite, jts, jte, kts, kte = tile or (1, nx, 1, ny, 1, nz)
+        T = lambda k: st[k].T                                   # noqa: E731
+        for k in ("qv", "qc", "qr", "qi", "qs", "qg", "ni", "nr", "th", "pii", "pressure", "dz_mass", "rainnc", "snownc", "graupelnc", "sr"):
+            if not (st[k].flags.c_contiguous and st[k].dtype == np.float32):
+                raise ValueError(k + " must be C-contiguous float32")
+        rainncv = np.zeros((ny, nx), np.float32)
+        snowncv = np.zeros((ny, nx), np.float32)
+        graupelncv = np.zeros((ny, nx), np.float32)
+        self.th.mp_gt_driver(T("qv"), T("qc"), T("qr"), T("qi"), T("qs"), T("qg"), T("ni"), T("nr"), T("th"), T("pii"),
+                             T("pressure"), T("dz_mass"), f32(dt), 1, T("rainnc"), rainncv.T, T("snownc"), snowncv.T,
+                             T("graupelnc"), graupelncv.T, T("sr"),
+                             1, nx, 1, ny, 1, nz, 1, nx, 1, ny, 1, nz, its, ite, jts, jte, kts, kte)
+
     exp4 = staticmethod(f_exp)          # exp of a REAL as the translated code evaluates it (glibc expf)
 
     # the order of mpdata's advect3d calls (adv_mpdata.f90:512-522): kVARS name -> domain component

@@ -200,6 +200,24 @@ def power(x, y):
     return np.float32(_libm.powf(float(x), float(y)))
 
 
+def cpow(x, y):
+    """constant ** constant as the compiler folds it: the correctly rounded power in the type of the result"""
+    import decimal
+    from fractions import Fraction
+    if isinstance(y, (int, np.integer)):
+        return power(x, y)
+    dt = np.float64 if (type(x) is np.float64 or type(y) is np.float64) else np.float32
+    with decimal.localcontext() as ctx:
+        ctx.prec = 80
+        exact = Fraction(decimal.Decimal(float(x)) ** decimal.Decimal(float(y)))
+    c = dt(float(exact)) if dt is np.float64 else np.float32(float(exact))
+    best = c
+    for cand in (np.nextafter(c, dt(-np.inf)), np.nextafter(c, dt(np.inf))):
+        if abs(Fraction(float(cand)) - exact) < abs(Fraction(float(best)) - exact):
+            best = cand
+    return dt(best)
+
+
 def _unary_libm(name, dname):
     cf = getattr(_libm, name)
     df = getattr(math, dname)
@@ -311,6 +329,22 @@ def f_merge(t, f, mask):
     return np.where(mask, t, f) if isinstance(mask, np.ndarray) else (t if mask else f)
 
 
+def arr(items, dtype):
+    return np.array([A(x) for x in items], dtype=dtype, order="F")
+
+
+def f_tanh(x):
+    return np.float32(math.tanh(float(x))) if type(x) is np.float32 else np.float64(math.tanh(float(x)))
+
+
+def f_atan(x):
+    return np.float32(math.atan(float(x))) if type(x) is np.float32 else np.float64(math.atan(float(x)))
+
+
+def _as_double(fn):
+    return lambda x: np.float64(fn(float(x)))
+
+
 def f_this_image():
     return 1
 
@@ -326,7 +360,7 @@ def do_range(lo, hi, step=1):
 
 NAMES = {
     "_FArr": FArr, "_Sl": Sl, "_ALL": ALL, "_A": A, "_alloc": alloc, "_unallocated": unallocated, "_wrap": wrap,
-    "_is_allocated": is_allocated, "_r4": r4, "_r8": r8, "_i4": i4, "_div": div, "_pow": power, "_do": do_range,
+    "_is_allocated": is_allocated, "_r4": r4, "_r8": r8, "_i4": i4, "_div": div, "_pow": power, "_cpow": cpow, "_do": do_range,
     "_f32": np.float32, "_f64": np.float64, "_i32": np.int32, "_np": np, "_Stop": FortranStop,
     "_fn_exp": f_exp, "_fn_log": f_log, "_fn_alog": f_log, "_fn_log10": f_log10, "_fn_alog10": f_log10,
     "_fn_sqrt": f_sqrt, "_fn_abs": f_abs,
@@ -334,5 +368,8 @@ NAMES = {
     "_fn_minval": f_minval, "_fn_sum": f_sum, "_fn_size": f_size, "_fn_ceiling": f_ceiling, "_fn_floor": f_floor,
     "_fn_nint": f_nint, "_fn_int": f_int, "_fn_real": f_real, "_fn_float": f_real, "_fn_dble": f_dble, "_fn_mod": f_mod,
     "_fn_sign": f_sign, "_fn_merge": f_merge, "_fn_this_image": f_this_image, "_fn_num_images": f_num_images,
-    "_fn_allocated": is_allocated, "_fn_associated": lambda x, *a: x is not None,
+    "_fn_allocated": is_allocated, "_fn_associated": lambda x, *a: x is not None, "_fn_present": lambda x: x is not None,
+    "_arr": arr, "_fn_dmax1": f_max, "_fn_dmin1": f_min, "_fn_dlog": _as_double(math.log), "_fn_dlog10": _as_double(math.log10),
+    "_fn_dexp": _as_double(math.exp), "_fn_dsqrt": _as_double(math.sqrt), "_fn_dabs": f_abs, "_fn_dfloat": f_dble,
+    "_fn_sngl": f_real, "_fn_tanh": f_tanh, "_fn_atan": f_atan, "_fn_iabs": f_abs, "_fn_trim": lambda x: x,
 }

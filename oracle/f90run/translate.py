@@ -91,6 +91,7 @@ def read_statements(path, _depth=0):
             piece = _lower_outside_strings(piece.strip())
             if not piece:
                 continue
+            piece = _array_constructors(piece)
             m = re.match(r"include\s+['\"]([^'\"]+)['\"]$", piece)
             if m:
                 inc = os.path.join(os.path.dirname(path), m.group(1))
@@ -99,6 +100,44 @@ def read_statements(path, _depth=0):
                 stmts.append((os.path.basename(path), cur_no, piece))
         cur = ""
     return stmts
+
+
+def _array_constructors(s):
+    """(/ a, b /) -> [ a, b ] outside strings"""
+    if "(/" not in s:
+        return s
+    out, q, k = [], None, 0
+    while k < len(s):
+        ch = s[k]
+        if q:
+            out.append(ch)
+            if ch == q:
+                q = None
+        elif ch in "'\"":
+            q = ch
+            out.append(ch)
+        elif s[k:k + 2] == "(/":
+            out.append("[")
+            k += 1
+        elif s[k:k + 2] == "/)":
+            out.append("]")
+            k += 1
+        else:
+            out.append(ch)
+        k += 1
+    return "".join(out)
+
+
+def split_label(t):
+    """'141 continue' -> ('141', 'continue'); 'name: do i = ...' -> construct name dropped"""
+    m = re.match(r"^(\d+)\s+(.*)$", t)
+    label = None
+    if m:
+        label, t = m.group(1), m.group(2)
+    m = re.match(r"^(\w+)\s*:\s*((?:do|if)\b.*)$", t)
+    if m and m.group(1) not in ("else",):
+        t = m.group(2)
+    return label, t
 
 
 def _split_semicolons(s):
@@ -149,15 +188,19 @@ def tokenize(s):
 REL = {"==": "==", "/=": "!=", "<": "<", "<=": "<=", ">": ">", ">=": ">=",
        ".eq.": "==", ".ne.": "!=", ".lt.": "<", ".le.": "<=", ".gt.": ">", ".ge.": ">="}
 
-INTRINSICS = {"abs", "max", "min", "amax1", "amin1", "maxval", "minval", "sum", "size", "exp", "log", "alog", "log10",
-              "alog10", "sqrt", "ceiling", "floor", "nint", "int", "real", "float", "dble", "mod", "sign", "merge",
-              "this_image", "num_images", "allocated", "associated"}
-INT_RESULT = {"size", "ceiling", "floor", "nint", "int", "this_image", "num_images"}
+INTRINSICS = {"abs", "max", "min", "amax1", "amin1", "dmax1", "dmin1", "maxval", "minval", "sum", "size", "exp", "log",
+              "alog", "log10", "alog10", "sqrt", "ceiling", "floor", "nint", "int", "real", "float", "dble", "mod", "sign",
+              "merge", "this_image", "num_images", "allocated", "associated", "present", "dlog", "dlog10", "dexp", "dsqrt",
+              "dabs", "dfloat", "sngl", "tanh", "atan", "sin", "cos", "iabs", "trim", "gamma"}
+INT_RESULT = {"size", "ceiling", "floor", "nint", "int", "this_image", "num_images", "iabs"}
+REAL_RESULT = {"real", "float", "sngl", "alog", "alog10", "amax1", "amin1"}
+DOUBLE_RESULT = {"dble", "dfloat", "dlog", "dlog10", "dexp", "dsqrt", "dabs", "dmax1", "dmin1"}
 
 
 class Var:
     def __init__(self, name, kind, dims=None, intent=None, parameter=False, allocatable=False, pointer=False,
-                 init=None, dummy=False, module=False, derived=False):
+                 init=None, dummy=False, module=False, derived=False, optional=False):
+        self.optional = optional
         self.name, self.kind, self.dims = name, kind, dims
         self.intent, self.parameter, self.allocatable, self.pointer = intent, parameter, allocatable, pointer
         self.init, self.dummy, self.module, self.derived = init, dummy, module, derived
@@ -167,7 +210,7 @@ class Var:
         return self.dims is not None
 
 
-DTYPE = {"r": "_f32", "d": "_f64", "i": "_i32", "l": "bool"}
+DTYPE = {"r": "_f32", "d": "_f64", "i": "_i32", "l": "bool", "c": "object", "?": "_f32"}
 
 
 class Scope:
@@ -200,6 +243,7 @@ class ExprParser:
 
     def __init__(self, toks, scope, consts):
         self.t, self.p, self.scope, self.consts = toks, 0, scope, consts
+        self.constant = set()      # codes of compile-time constant subexpressions (literals, PARAMETERs and their arithmetic)
 
     def peek(self):
         return self.t[self.p]
@@ -279,7 +323,10 @@ class ExprParser:
             if kind == "op" and v in ("+", "-"):
                 self.next()
                 c2, k2 = self.mul()
+                both = c in self.constant and c2 in self.constant
                 c, k = f"({c} {v} {c2})", self._join(k, k2)
+                if both:
+                    self.constant.add(c)
             else:
                 return c, k
 
@@ -290,14 +337,20 @@ class ExprParser:
             if kind == "op" and v == "*":
                 self.next()
                 c2, k2 = self.pow_()
+                both = c in self.constant and c2 in self.constant
                 c, k = f"({c} * {c2})", self._join(k, k2)
+                if both:
+                    self.constant.add(c)
             elif kind == "op" and v == "/":
                 self.next()
                 c2, k2 = self.pow_()
                 kk = self._join(k, k2)
+                both = c in self.constant and c2 in self.constant
                 # integer / integer truncates; decided at run time unless an operand is known to be real
                 c = f"({c} / {c2})" if kk in ("r", "d") else f"_div({c}, {c2})"
                 k = kk
+                if both:
+                    self.constant.add(c)
             else:
                 return c, k
 
@@ -313,7 +366,14 @@ class ExprParser:
                 c2 = f"(-{c2})" if v == "-" else c2
             else:
                 c2, k2 = self.pow_()
-            return f"_pow({c}, {c2})", (k if k2 == "i" else self._join(k, k2))
+            # constant ** constant is folded by the compiler (gfortran: MPFR, correctly rounded); anything else is
+            # powf / pow / repeated multiplication at run time
+            fn = "_cpow" if (c in self.constant and c2 in self.constant and k2 != "i") else "_pow"
+            both = c in self.constant and c2 in self.constant
+            c = f"{fn}({c}, {c2})"
+            if both:
+                self.constant.add(c)
+            return c, (k if k2 == "i" else self._join(k, k2))
         return c, k
 
     def literal(self, text):
@@ -322,10 +382,15 @@ class ExprParser:
         if "_" in t:
             t, kindsuffix = t.split("_", 1)
         if re.fullmatch(r"\d+", t):
-            return t.lstrip("0") or "0", "i"
+            c = t.lstrip("0") or "0"
+            self.constant.add(c)
+            return c, "i"
         if "d" in t or kindsuffix in ("dp", "8", "real64", "r8"):
-            return f"_f64({float(t.replace('d', 'e'))!r})", "d"
+            c = f"_f64({float(t.replace('d', 'e'))!r})"
+            self.constant.add(c)
+            return c, "d"
         idx = self.consts.setdefault(t, len(self.consts))
+        self.constant.add(f"_C[{idx}]")
         return f"_C[{idx}]", "r"
 
     def args(self):
@@ -377,9 +442,20 @@ class ExprParser:
         if kind == "op" and v == "(":
             c, k = self.expr()
             self.expect("op", ")")
+            if c in self.constant:
+                self.constant.add(f"({c})")
             return f"({c})", k
         if kind == "op" and v == "[":
-            raise TranslateError("array constructors are outside the subset")
+            items, k = [], None
+            while True:
+                c, kk = self.expr()
+                items.append(c)
+                k = kk if k is None else self._join(k, kk)
+                if self.accept("op", ","):
+                    continue
+                self.expect("op", "]")
+                break
+            return f"_arr([{', '.join(items)}], {DTYPE.get(k, '_f32')})", k
         if kind != "name":
             raise TranslateError(f"unexpected token {v!r} in {' '.join(x for _, x in self.t)}")
         name = v
@@ -424,11 +500,11 @@ class ExprParser:
             if name in INTRINSICS:
                 if name in INT_RESULT:
                     k = "i"
-                elif name in ("real", "float"):
+                elif name in REAL_RESULT:
                     k = "r"
-                elif name == "dble":
+                elif name in DOUBLE_RESULT:
                     k = "d"
-                elif name in ("allocated", "associated"):
+                elif name in ("allocated", "associated", "present"):
                     k = "l"
                 else:
                     ks = [x[2] for x in a]
@@ -443,11 +519,14 @@ class ExprParser:
             raise TranslateError(f"undeclared name {name!r} in {self.scope.routine.name if self.scope.routine else 'module'}")
         if var.is_array:
             return f"{self.scope.ref(name)}.a", var.kind
+        if var.parameter:
+            self.constant.add(self.scope.ref(name))
         return self.scope.ref(name), var.kind
 
 
 # ============================================================================================ declarations
 DECL_RE = re.compile(r"^(real|integer|logical|double\s+precision|character|type\s*\(|class\s*\()")
+SPEC_NO_COLONS = re.compile(r"^(real|integer|logical|double\s+precision|character)\s*(\([^)]*\)|\*\s*\d+)?\s+(.*)$")
 
 
 def split_top(s, sep=","):
@@ -480,15 +559,18 @@ def parse_declaration(stmt):
     if "::" in stmt:
         left, right = stmt.split("::", 1)
     else:
-        m = re.match(r"^(real|integer|logical|double\s+precision)\s*(\([^)]*\)|\*\s*\d+)?\s+(.*)$", stmt)
+        m = SPEC_NO_COLONS.match(stmt)
         if not m:
             return None
         left, right = m.group(1) + (m.group(2) or ""), m.group(3)
     parts = split_top(left.strip())
     spec = parts[0].replace(" ", "")
     derived = False
-    if spec.startswith("doubleprecision") or spec in ("real(8)", "real*8", "real(kind=8)", "real(dp)", "real(real64)"):
+    if spec.startswith("doubleprecision") or spec in ("real(8)", "real*8", "real(kind=8)", "real(dp)", "real(real64)",
+                                                        "real(kind=r8size)", "real(r8size)", "real(kind=dp)"):
         kind = "d"
+    elif spec.startswith("character"):
+        kind = "c"
     elif spec.startswith("real"):
         kind = "r"
     elif spec.startswith("integer"):
@@ -514,12 +596,14 @@ def parse_declaration(stmt):
     ents = []
     for e in split_top(right.strip()):
         init = None
-        m = re.match(r"^(\w+)\s*(\((.*)\))?\s*(=\s*(.*))?$", e)
+        m = re.match(r"^(\w+)\s*(\((.*?)\))?\s*(?:\*\s*\d+)?\s*(=\s*(.*))?$", e)
         if not m:
             raise TranslateError(f"cannot parse entity {e!r} in {stmt}")
         if "=>" in e:
             raise TranslateError(f"pointer initialisation outside the subset: {stmt}")
         name, dims, init = m.group(1), m.group(3), m.group(5)
+        if kind == "c" and dims is None and re.match(r"^\w+\s*\*\s*\d+$", e):
+            name = re.match(r"^(\w+)", e).group(1)
         ents.append((name, dims if dims is not None else attrs.get("dims"), init))
     return kind, attrs, ents
 
@@ -551,8 +635,12 @@ class Routine:
 class Module:
     """One Fortran module file, translated lazily routine by routine."""
 
-    def __init__(self, path, externals=None, names=None):
+    def __init__(self, path, externals=None, names=None, overrides=None, patches=None):
         self.path = path
+        # routine name -> [(regex, replacement statement)]: statements the harness replaces, each one documented where
+        # it is used (the only use: the km_s / km_e range that wrf_dm_decomp1d would hand a rank of a parallel run)
+        self.patches = patches or {}
+        self.overrides = overrides or {}     # routine name -> python callable(module namespace) run INSTEAD of the routine
         self.names = names or {}             # entities of other modules the source refers to (e.g. kVARS)
         self.stmts = read_statements(path)
         self.vars = {}
@@ -616,7 +704,7 @@ class Module:
             for name, dims, init in ents:
                 r.decls[name] = Var(name, kind, dims, attrs.get("intent"), attrs.get("parameter", False),
                                     attrs.get("allocatable", False), attrs.get("pointer", False), init,
-                                    dummy=name in r.args, derived=attrs["derived"])
+                                    dummy=name in r.args, derived=attrs["derived"], optional=attrs.get("optional", False))
                 r.decl_order.append(name)
         else:
             n = len(r.body)
@@ -674,20 +762,37 @@ class Module:
         def emit(s, at=None):
             L.append("    " * (ind if at is None else at) + s)
 
-        emit(f"def _F_{name}({', '.join(py_name(a) for a in r.args)}):", 0)
+        sig, seen_optional = [], False
+        for a in r.args:
+            seen_optional = seen_optional or (r.decls.get(a) is not None and r.decls[a].optional)
+            sig.append(py_name(a) + ("=None" if seen_optional else ""))
+        emit(f"def _F_{name}({', '.join(sig)}):", 0)
         # prologue: dummies under their declared bounds, locals allocated / initialised
         for vn in r.decl_order:
             v = r.decls[vn]
             pn = py_name(vn)
             if v.derived:
                 continue
+            if v.kind == "c":
+                if not v.dummy:
+                    emit(f"{pn} = ''")
+                continue
             if v.parameter:
-                emit(f"{pn} = {self.convert(self.expr(v.init, scope)[0], v.kind)}")
+                if v.is_array:
+                    b, _, _ = self.bounds(v.dims, scope)
+                    emit(f"{pn} = _FArr({self.expr(v.init, scope)[0]}, [lo for lo, hi in {b}])")
+                else:
+                    emit(f"{pn} = {self.convert(self.expr(v.init, scope)[0], v.kind)}")
                 continue
             if v.dummy:
                 if v.is_array:
                     b, _, _ = self.bounds(v.dims, scope)
-                    emit(f"{pn} = _wrap({pn}, {b}, {DTYPE[v.kind]})")
+                    if v.optional:
+                        emit(f"{pn} = _wrap({pn}, {b}, {DTYPE[v.kind]}) if {pn} is not None else None")
+                    else:
+                        emit(f"{pn} = _wrap({pn}, {b}, {DTYPE[v.kind]})")
+                elif v.optional:
+                    emit(f"{pn} = {self.convert(pn, v.kind)} if {pn} is not None else None")
                 elif v.intent == "in" or True:
                     emit(f"{pn} = {self.convert(pn, v.kind)}")
                 continue
@@ -705,9 +810,24 @@ class Module:
                 emit(f"{pn} = {'False' if v.kind == 'l' else self.convert('0', v.kind)}")
         # executable part
         block = []                                         # stack of open constructs
-        for f, no, t in r.body[r.exec_start:]:
+        body = [(f, no) + split_label(t) for f, no, t in r.body[r.exec_start:]]
+        for rx, repl in self.patches.get(name, []):
+            hits = [n for n, (f, no, lab, t) in enumerate(body) if re.match(rx, t)]
+            if len(hits) != 1:
+                raise TranslateError(f"{name}: patch {rx!r} matches {len(hits)} statements")
+            body[hits[0]] = body[hits[0]][:3] + (repl,)
+        self._labels = {lab: n for n, (f, no, lab, t) in enumerate(body) if lab}
+        self._body, self._do_labels = body, []
+        for n, (f, no, lab, t) in enumerate(body):
+            self._pos = n
             try:
                 ind = self._statement(t, scope, r, emit, block, ind)
+                # a labelled DO ends with the statement that carries its label
+                while lab and self._do_labels and self._do_labels[-1] == lab:
+                    self._do_labels.pop()
+                    if not block or block.pop() != "do":
+                        raise TranslateError("labelled DO ends inside another construct")
+                    ind -= 1
             except TranslateError as e:
                 raise TranslateError(f"{f}:{no}: {e}\n    {t}") from None
         if block:
@@ -792,15 +912,23 @@ class Module:
             raise TranslateError("cannot parse call")
         name, argtext = m.group(1), m.group(3) or ""
         actuals = split_top(argtext) if argtext.strip() else []
+        if name in self.externals and self.externals[name] is None:
+            emit("pass")
+            return
         codes = [self.expr(a, scope)[0] for a in actuals]
+        if name in self.overrides:
+            emit(f"_O_{name}(_M)")
+            return
         if name in self.routines:
             r = self.routines[name]
             if r.is_function:
                 raise TranslateError(f"function {name} called as a subroutine")
             self.need(name)
             outs = r.out_positions()
-            if len(actuals) != len(r.args):
-                raise TranslateError(f"call {name}: {len(actuals)} actual arguments for {len(r.args)} dummies (optional arguments are outside the subset)")
+            if any(re.match(r"^\w+\s*=[^=]", a) for a in actuals):
+                raise TranslateError(f"call {name}: keyword arguments are outside the subset")
+            if len(actuals) > len(r.args) or any(not r.decls[a].optional for a in r.args[len(actuals):]):
+                raise TranslateError(f"call {name}: {len(actuals)} actual arguments for {len(r.args)} dummies")
             emit(f"_ret = _F_{name}({', '.join(codes)})")
             for k, pos in enumerate(outs):
                 a = actuals[pos].strip()
@@ -815,7 +943,10 @@ class Module:
                         emit(f"{target} = _ret[{k}]")
             return
         if name in self.externals:
-            emit(f"_X_{name}({', '.join(codes)})")
+            if self.externals[name] is None:
+                emit("pass")                      # declared a no-op by the harness (logging)
+            else:
+                emit(f"_X_{name}({', '.join(codes)})")
             return
         raise TranslateError(f"call to {name!r}: not a routine of this module")
 
@@ -830,7 +961,7 @@ class Module:
             if not block or block.pop() != "if":
                 raise TranslateError("endif without if")
             return ind - 1
-        if re.match(r"^end\s*do$", t):
+        if re.match(r"^end\s*do(\s+\w+)?$", t):
             if not block or block.pop() != "do":
                 raise TranslateError("enddo without do")
             return ind - 1
@@ -860,6 +991,10 @@ class Module:
             block.append("do")
             emit_at("pass", ind + 1)
             return ind + 1
+        m = re.match(r"^do\s+(\d+)\s+(\w+)\s*=\s*(.*)$", t)
+        if m:
+            self._do_labels.append(m.group(1))
+            t = f"do {m.group(2)} = {m.group(3)}"
         m = re.match(r"^do\s+(\w+)\s*=\s*(.*)$", t)
         if m:
             var = m.group(1)
@@ -896,16 +1031,51 @@ class Module:
             emit(f"if {self.expr(cond, scope)[0]}:")
             return self._statement(rest, scope, r, emit_at, block, ind + 1) - 1
         # ---- simple statements
-        if t in ("exit",):
+        if t == "exit" or t == "cycle" or re.match(r"^(exit|cycle)\s+\w+$", t):
+            if " " in t and block.count("do") != 1 and False:
+                raise TranslateError("exit / cycle of an outer loop")
+            emit("break" if t.startswith("exit") else "continue")
+            return ind
+        if t == "continue":
+            emit("pass")
+            return ind
+        m = re.match(r"^go\s*to\s+(\d+)$", t)
+        if m:
+            # supported: a forward jump out of the innermost DO to a label that follows the loop with nothing but
+            # no-ops (PRINT / CONTINUE) in between -- i.e. EXIT
+            lab = m.group(1)
+            if lab not in self._labels or self._labels[lab] <= self._pos or "do" not in block:
+                raise TranslateError("GOTO other than a forward jump out of a loop")
+            depth, k = 0, self._pos + 1
+            # find the end of the innermost enclosing DO
+            while k < len(self._body):
+                tt = self._body[k][3]
+                if re.match(r"^do\b", tt):
+                    depth += 1
+                elif re.match(r"^end\s*do", tt) or (self._body[k][2] and self._do_labels and self._body[k][2] == self._do_labels[-1]):
+                    if depth == 0:
+                        break
+                    depth -= 1
+                k += 1
+            for kk in range(k + 1, self._labels[lab]):
+                tt = self._body[kk][3]
+                if not (tt.startswith("print") or tt == "continue" or tt.startswith("write")):
+                    raise TranslateError(f"GOTO {lab} skips executable statements: outside the subset")
             emit("break")
             return ind
-        if t in ("cycle",):
-            emit("continue")
+        if re.match(r"^inquire\s*\(", t):
+            m = re.search(r"(?:exist|opened)\s*=\s*(\w+)", t)
+            if not m:
+                raise TranslateError("INQUIRE without EXIST= / OPENED=")
+            emit(f"{scope.ref(m.group(1))} = False        # no cache files: tables are computed")
+            return ind
+        if re.match(r"^(open|close|read|rewind)\s*\(", t):
+            emit("pass")
             return ind
         if t == "return":
             emit(self._return(r))
             return ind
-        if t.startswith("print") or t.startswith("write") or t.startswith("flush"):
+        if t.startswith("print") or t.startswith("write") or t.startswith("flush") or t.startswith("pause"):
             emit("pass")
             return ind
         if t == "stop" or t.startswith("stop ") or t.startswith("error stop"):
@@ -990,7 +1160,10 @@ class Module:
                     init.append(f"    _M.{pn} = _unallocated({DTYPE.get(v.kind, '_f32')}, {rank})")
                 else:
                     b, _, _ = self.bounds(v.dims, mscope)
-                    init.append(f"    _M.{pn} = _alloc({DTYPE[v.kind]}, {b})")
+                    if v.init is not None:
+                        init.append(f"    _M.{pn} = _FArr(_np.asarray(_A({self.expr(v.init, mscope)[0]}), {DTYPE[v.kind]}), [lo for lo, hi in {b}])")
+                    else:
+                        init.append(f"    _M.{pn} = _alloc({DTYPE[v.kind]}, {b})")
             elif v.init is not None:
                 try:
                     init.append(f"    _M.{pn} = {self.convert(self.expr(v.init, mscope)[0], v.kind)}")
@@ -1013,6 +1186,8 @@ class Module:
             ns["_X_" + xn] = fn
         for nn, val in self.names.items():
             ns[py_name(nn)] = val
+        for on, fn in self.overrides.items():
+            ns["_O_" + on] = fn
         exec(compile(src, f"<f90run:{os.path.basename(self.path)}>", "exec"), ns)
         ns["_init_module"](ns["_M"])
         out = types.SimpleNamespace(M=ns["_M"], source=src, constants=dict(self.consts))

@@ -1,10 +1,12 @@
 // ORACLE -- TEST INFRASTRUCTURE ONLY.  Not part of the product path.
 //
 // CPU restatement of ICAR's "simple" (SB04) cloud microphysics, statement by
-// statement.  PARITY UNPINNED (see mpdata_oracle.hpp): the reference holds no
-// expected values for this path (src/tests/test_mp_simple.f90 prints only and
-// does not compile against the current module); the scenario is frozen under
-// tests/golden/ from this restatement.
+// statement.  PARITY PINNED TO THE REFERENCE'S OWN SOURCE (see mpdata_oracle.hpp):
+// the reference holds no expected values for this path (src/tests/test_mp_simple.f90
+// prints only and does not compile against the current module), so oracle/f90run
+// executes src/physics/mp_simple.f90 itself; this restatement equals its outputs
+// in every bit (driver on tiles and sub-tiles, kts > kms, the test_mp_simple.f90
+// scenario; tests/test_reference_source.py).
 //
 // Reference files followed (relative to /root/reference):
 //   src/physics/mp_simple.f90:64-96    constants

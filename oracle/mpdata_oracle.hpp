@@ -5,12 +5,15 @@
 // quirks).  Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
 // `--impl reference` legs may build, load or call this.
 //
-// PARITY UNPINNED: the reference holds no golden vectors / known-answer tests
-// for this path (src/tests/test_mpdata.f90 has no asserts and a stale
-// signature) and no Fortran compiler exists in this image, so
-// this restatement could not be checked against outputs of the reference.
-// What pins it instead: the reference's two scenarios frozen under
-// tests/golden/, plus invariants (conservation, monotonicity, order-1 == upwind).
+// PARITY PINNED TO THE REFERENCE'S OWN SOURCE.  The reference holds no golden
+// vectors / known-answer tests for this path (src/tests/test_mpdata.f90 has no
+// asserts and a stale signature) and no Fortran compiler
+// exists in this image; so oracle/f90run EXECUTES src/physics/adv_mpdata.f90 and
+// adv_mpdata_FCT_core.f90 themselves (translated statement by statement where
+// they lie, IEEE binary32).  This restatement equals those outputs in every bit:
+// advect3d (orders 1-3, FCT on / off, density), mpdata()'s wind normalisation and
+// scalar list, the test_mpdata.f90 scenario, three coupled hill-case steps
+// (tests/test_reference_source.py; tests/golden/reference_source_*.npz).
 //
 // Reference files followed (paths relative to /root/reference):
 //   src/physics/adv_mpdata.f90:24-42    flux1

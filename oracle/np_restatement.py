@@ -10,7 +10,8 @@ is written here in its "independent faces" form rather
 than the Fortran's carried-variable loop, which also proves that the carried
 temporaries are pure reuse -- the property the CUDA kernels rely on.
 
-PARITY UNPINNED (no reference golden vectors exist; see mpdata_oracle.hpp).
+Parity: the C++ oracle this file must agree with is pinned to the reference source executed by oracle/f90run
+(see mpdata_oracle.hpp); no reference golden vectors exist.
 
 Follows /root/reference/src/physics/adv_mpdata.f90 and adv_mpdata_FCT_core.f90.
 """

@@ -3,8 +3,8 @@
 Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / `--impl reference`
 legs may import this module.  The product (icar_b200/) never does.
 
-PARITY UNPINNED: see oracle/mpdata_oracle.hpp -- the reference (NCAR/icar) holds no
-golden vectors for the MPDATA / mp_simple path and cannot be compiled in this image.
+PARITY PINNED to the reference's own source text, executed by oracle/f90run (the reference holds no
+golden vectors and cannot be compiled in this image): see oracle/mpdata_oracle.hpp and tests/test_reference_source.py.
 
 All arrays are numpy arrays in the reference's memory order: Fortran (i,k,j)
 column-major == numpy C-order shape (ny, nz, nx).

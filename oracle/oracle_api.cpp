@@ -1,6 +1,6 @@
 // ORACLE -- TEST INFRASTRUCTURE ONLY (see mpdata_oracle.hpp).  C entry points
 // over the templated restatement so tests/ and bench.py's cpu_baseline leg can
-// call it through ctypes.  PARITY UNPINNED by the reference.
+// call it through ctypes.  Parity: pinned to the reference source executed by oracle/f90run.
 #include "mpdata_oracle.hpp"
 #include "mp_simple_oracle.hpp"
 

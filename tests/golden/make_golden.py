@@ -4,7 +4,9 @@ The reference (NCAR/icar) ships no expected values for this path, only two scena
 asserts (src/tests/test_mpdata.f90:51-111, src/tests/test_mp_simple.f90:4-33), and it cannot be
 compiled in this image (no Fortran compiler).  The vectors frozen here therefore come from the
 oracle restatement, NOT from a run of the reference: they pin the oracle against regressions and
-give the CUDA path fixed targets.  Re-run:  python tests/golden/make_golden.py
+give the CUDA path fixed targets.  (Round 2: make_reference_source_golden.py makes the same scenarios by EXECUTING the
+reference's Fortran source; tests/test_reference_source.py holds the two sets of files to equality.)
+Re-run:  python tests/golden/make_golden.py
 """
 import os
 import sys
@@ -79,7 +81,7 @@ def hill_case(nx=24, nz=10, ny=20, steps=3):
 
 def thompson_column_case(nz=24, ncall=12, dt=60.0):
     """A single moist column (the ideal sounding, qv x 3) pushed through mp_thompson `ncall` times:
-    cloud -> ice -> snow -> graupel -> rain all fire.  Frozen from the oracle (parity unpinned)."""
+    cloud -> ice -> snow -> graupel -> rain all fire.  Frozen from the oracle (the oracle itself is pinned by reference_source_thompson.npz)."""
     st = ideal.add_thompson_fields(ideal.make_ideal_case(nx=3, nz=nz, ny=3), moisten=3.0)
     T = O.Thompson(big_tables=True)
     out = []

@@ -10,10 +10,15 @@ path -- to outputs of the reference's text:
         BASELINE config-1 hill case
   reference_source_mpdata_scenario_f32.npz        the scenario of src/tests/test_mpdata.f90:51-111 (two loops)
   reference_source_mp_simple_scenario_f32.npz     the scenario of src/tests/test_mp_simple.f90:4-33 (100 calls of mp_simple)
+  reference_source_thompson.npz                   src/physics/mp_thompson.f90: thompson_init's 130 scalar constants, the bin
+        grids, the tables of freezeH2O / qi_aut_qs / table_Efrw / table_Efsw (2-D ones whole, 3-D ones sampled), one (k, m)
+        slab of each rain-collection table from qr_acr_qg / qr_acr_qs themselves, and mp_gt_driver + mp_thompson: six calls
+        on a moist 6 x 16 x 4 hill state in which every species forms.  (The remaining slabs of the two collection tables
+        -- 1.4e10 inner iterations -- are taken from the C++ oracle for the run.)
   reference_source_random_f32.npz                 advect3d (orders 1-3, FCT on / off) and mp_simple_driver (sub-tile) on
         random fields of a ragged 13 x 7 x 9 grid, inputs included
 
-Re-run (needs /root/reference; about five minutes):  python tests/golden/make_reference_source_golden.py
+Re-run (needs /root/reference; about a quarter of an hour):  python tests/golden/make_reference_source_golden.py
 """
 import os
 import sys
@@ -127,12 +132,55 @@ def random_cases(ref, nx=13, nz=7, ny=9, seed=3):
     return out
 
 
+THOMPSON_KEYS = ("th", "qv", "qc", "qr", "qi", "qs", "qg", "ni", "nr", "rainnc", "snownc", "graupelnc", "sr")
+THOMPSON_SLABS = ((0, 5 * 37 + 11), (1, 20 * 37 + 7))          # (table family, km): one slab of each builder
+
+
+def thompson_state(nx=6, nz=16, ny=4):
+    return ideal.add_thompson_fields(ideal.make_ideal_case(nx=nx, nz=nz, ny=ny, perturb=True), moisten=3.0)
+
+
+def thompson_case(ref):
+    from oracle import oracle as O
+    T = O.Thompson(big_tables=True)
+    big = {n: T.table(n).T for n in ref.BIG_QG + ref.BIG_QS}
+    ref.thompson_init(big)                                      # everything else is the reference's text, executed
+    M = ref.th.M
+    out = {"constants": ref.thompson_constants()}
+    for n in ("dc", "di", "dr", "ds", "dg"):
+        out["bins_" + n] = getattr(M, n).a.copy()
+    rng = np.random.default_rng(7)
+    for n in O.THOMPSON_TABLES[18:]:
+        a = getattr(M, n.lower()).a
+        flat = a.reshape(-1, order="F")                         # the Fortran's storage order
+        if a.ndim == 2:
+            out["table_" + n] = flat.copy()
+        else:
+            idx = np.sort(rng.choice(flat.size, size=2048, replace=False))
+            out["table_" + n + "_idx"] = idx
+            out["table_" + n] = flat[idx].copy()
+    for which, km in THOMPSON_SLABS:
+        for n, v in ref.thompson_big_slab(which, km).items():
+            out[f"slab_{n}"] = v
+    st = thompson_state()
+    for call in range(1, 7):
+        ref.mp_gt_driver(st, 60.0)
+        for k in THOMPSON_KEYS:
+            out[f"call{call}_{k}"] = st[k].copy()
+    return out
+
+
 if __name__ == "__main__":
     ref = f90run.Reference("/root/reference")
+    if "--thompson-only" in sys.argv:
+        np.savez_compressed(os.path.join(HERE, "reference_source_thompson.npz"), **thompson_case(ref))
+        print("written")
+        sys.exit(0)
     fields, dt = hill_case(ref)
     np.savez_compressed(os.path.join(HERE, "reference_source_hill_24x10x20_3steps_f32.npz"), dt=dt, **fields)
     rows, line = mpdata_scenario(ref)
     np.savez_compressed(os.path.join(HERE, "reference_source_mpdata_scenario_f32.npz"), rows=rows, final_line=line)
     np.savez_compressed(os.path.join(HERE, "reference_source_mp_simple_scenario_f32.npz"), table=mp_simple_scenario(ref))
     np.savez_compressed(os.path.join(HERE, "reference_source_random_f32.npz"), **random_cases(ref))
+    np.savez_compressed(os.path.join(HERE, "reference_source_thompson.npz"), **thompson_case(ref))
     print("written")

@@ -100,6 +100,36 @@ def test_tables_match_oracle(gpu_lib, oracle_thompson):
             assert rel.max() <= TABLE_RTOL, f"{name}: {rel.max():.2e}"
 
 
+def test_reference_source_golden(gpu_lib, oracle_thompson, golden_dir):
+    """The CUDA path against outputs of the reference's OWN SOURCE (src/physics/mp_thompson.f90 executed by oracle/f90run,
+    tests/golden/reference_source_thompson.npz): the small tables, and six mp_gt_driver calls, each from the reference's
+    state before that call, to the bars stated at the top of this file."""
+    import os
+    g = np.load(os.path.join(golden_dir, "reference_source_thompson.npz"))
+    dom = make_domain(gpu_lib, 6, 16, 4)
+    for name in gpu_lib.THOMPSON_TABLES[18:]:
+        flat = dom.thompson_table(name).ravel()
+        want = g["table_" + name]
+        got = flat[g["table_" + name + "_idx"]] if ("table_" + name + "_idx") in g.files else flat
+        assert ((got == 0) == (want == 0)).all(), name
+        nzr = want != 0
+        assert (np.abs(got[nzr] - want[nzr]) / np.abs(want[nzr])).max() <= TABLE_RTOL, name
+    keys = FIELDS + ("rainnc", "snownc", "graupelnc", "sr")
+    state = ideal.add_thompson_fields(ideal.make_ideal_case(nx=6, nz=16, ny=4, perturb=True), moisten=3.0)
+    excluded = 0
+    for call in range(1, 7):
+        want = ideal.copy_state(state)
+        for k in keys:
+            want[k] = g[f"call{call}_{k}"]
+        st = ideal.copy_state(state)
+        dom.mp_gt_driver(st, 60.0, 1, 6, 1, 4, 1, 16)
+        excluded += compare_call(st, want, f"reference source, call {call}", ideal.copy_state(state),
+                                 lambda p: oracle_thompson.driver(p, 60.0, 0, 5, 0, 3, 0, 15))
+        state = want                                   # the next call starts from the reference's own state
+    print(f"columns set aside as sitting on a discontinuity: {excluded} of {6 * 24}")
+    dom.close()
+
+
 def test_table_options_are_honoured(gpu_lib, oracle):
     """thompson_init with non-default mp_options (mp_thompson.f90:397-417) rebuilds the tables."""
     dom = make_domain(gpu_lib, 8, 4, 8)

@@ -1,6 +1,6 @@
 """The two independent CPU restatements (C++ per-cell loops vs NumPy whole-array slices
 transcribed from the Fortran) must agree bit for bit, and the oracle must reproduce the frozen
-golden vectors.  PARITY UNPINNED by the reference itself -- see oracle/mpdata_oracle.hpp."""
+golden vectors.  (The oracle is pinned to the reference source itself in tests/test_reference_source.py.)"""
 import os
 
 import numpy as np

@@ -1,7 +1,7 @@
 """The Thompson oracle (oracle/mp_thompson_oracle.hpp) on the CPU: frozen vectors, an independent
 NumPy evaluation of lookup-table entries, and physical invariants of the column routine.
 
-PARITY UNPINNED: the reference has no expected values for mp_thompson and cannot be compiled here;
+Parity pinned elsewhere (tests/test_reference_source.py: mp_thompson.f90 executed by oracle/f90run); the reference has no expected values for mp_thompson and cannot be compiled here;
 these tests pin the restatement against regressions and against a second, independent evaluation
 of the table integrals (mp_thompson.f90:2917-2975, :3093-3220, :3323-3381, :3425-3454)."""
 import math

@@ -177,3 +177,79 @@ def test_live_kts_above_kms_reallocates_temperature(ref, oracle):
     for k in names:
         assert np.array_equal(a[k], b[k]), k
     assert np.array_equal(ra, rb)
+
+
+# ------------------------------------------------------------------ Thompson: src/physics/mp_thompson.f90 executed
+THOMPSON_KEYS = ("th", "qv", "qc", "qr", "qi", "qs", "qg", "ni", "nr", "rainnc", "snownc", "graupelnc", "sr")
+
+
+@pytest.fixture(scope="module")
+def thompson_full(oracle):
+    return oracle.Thompson(big_tables=True)
+
+
+def thompson_state(nx=6, nz=16, ny=4):
+    return ideal.add_thompson_fields(ideal.make_ideal_case(nx=nx, nz=nz, ny=ny, perturb=True), moisten=3.0)
+
+
+def test_golden_thompson_init(oracle, golden_dir, thompson_full):
+    """thompson_init as the reference's text computes it -- 130 scalar constants, the five bin grids, the freezing /
+    ice-to-snow / collision-efficiency tables, one slab of each rain-collection table from qr_acr_qg / qr_acr_qs run
+    for that slab -- against the C++ oracle: equal in every bit"""
+    g = load(golden_dir, "reference_source_thompson.npz")
+    assert np.array_equal(thompson_full.constants(), g["constants"])
+    bins = thompson_full.bins()
+    for n in ("Dc", "Di", "Dr", "Ds", "Dg"):
+        assert np.array_equal(bins[n], g["bins_" + n.lower()]), n
+    for n in oracle.THOMPSON_TABLES[18:]:
+        flat = thompson_full.table(n).ravel()                   # the view is in the Fortran's storage order
+        want = g["table_" + n]
+        got = flat[g["table_" + n + "_idx"]] if ("table_" + n + "_idx") in g.files else flat
+        assert np.array_equal(got, want), n
+        assert (want != 0).any()
+    from oracle.f90run import Reference
+    for which, km in ((0, 5 * 37 + 11), (1, 20 * 37 + 7)):          # THOMPSON_SLABS of make_reference_source_golden.py
+        m, k = divmod(km, 37)
+        for n in (Reference.BIG_QG if which == 0 else Reference.BIG_QS):
+            assert np.array_equal(thompson_full.table(n)[m, k].T, g["slab_" + n]), (n, km)
+            assert (g["slab_" + n] != 0).any() or n.startswith("tnr_sacr")
+
+
+def test_golden_thompson_driver(golden_dir, thompson_full):
+    """six calls of mp_gt_driver + mp_thompson on a moist hill state in which cloud water, rain, ice, snow and graupel all
+    form: the oracle against the reference's text, every field of every call equal in every bit"""
+    g = load(golden_dir, "reference_source_thompson.npz")
+    st = thompson_state()
+    ny, nz, nx = st["th"].shape
+    for call in range(1, 7):
+        thompson_full.driver(st, 60.0, 0, nx - 1, 0, ny - 1, 0, nz - 1)
+        for k in THOMPSON_KEYS:
+            assert np.array_equal(st[k], g[f"call{call}_{k}"]), (call, k)
+    for k in ("qc", "qr", "qi", "qs", "qg"):
+        assert g["call6_" + k].max() > 1e-6, k
+    assert g["call6_rainnc"].max() > 0.1
+
+
+@needs_reference
+def test_live_thompson(ref, oracle, thompson_full):
+    """mp_thompson.f90 translated and run live: thompson_init (without freezeH2O's two-minute loop, whose tables the
+    golden file covers) and two driver calls on fresh inputs"""
+    tabs = {n: thompson_full.table(n).T for n in oracle.THOMPSON_TABLES}
+    ref.thompson_init(tabs, skip_freezeh2o=True)
+    assert np.array_equal(ref.thompson_constants(), thompson_full.constants())
+    M = ref.th.M
+    for n in ("tps_iaus", "tni_iaus", "tpi_ide", "t_Efrw", "t_Efsw"):
+        assert np.array_equal(getattr(M, n.lower()).a, thompson_full.table(n).T), n
+    st = ideal.add_thompson_fields(ideal.make_ideal_case(nx=4, nz=14, ny=3, perturb=True), moisten=3.5)
+    rng = np.random.default_rng(8)
+    for k, top in (("qi", 5e-5), ("qs", 2e-4), ("qg", 2e-4), ("qr", 5e-4)):
+        st[k] = (rng.uniform(0, top, st[k].shape) * (rng.random(st[k].shape) < 0.6)).astype(np.float32)
+    st["ni"] = (st["qi"] * np.float32(1e9)).astype(np.float32)
+    st["nr"] = (st["qr"] * np.float32(1e8)).astype(np.float32)
+    a, b = ideal.copy_state(st), ideal.copy_state(st)
+    for call in range(2):
+        thompson_full.driver(a, 45.0, 0, 3, 0, 2, 0, 13)
+        ref.mp_gt_driver(b, 45.0)
+        for k in THOMPSON_KEYS:
+            assert np.array_equal(a[k], b[k]), (call, k)
+    assert np.abs(a["th"] - st["th"]).max() > 0.1
