@@ -37,6 +37,14 @@ class Reference:
         self.kvars = types.SimpleNamespace(**{n: k + 1 for k, n in enumerate(self.ADVECTED)})
         self.adv = Module(self.adv_path, names={"kvars": self.kvars}).build(["advect3d", "upwind_advection", "mpdata_fluxes", "flux_limiter", "flux1", "mpdata"])
         self.mp = Module(self.mp_path).build(["mp_simple_driver"])
+        self.upw = Module(os.path.join(phys, "advect.f90"), names={"kvars": self.kvars}).build(["upwind"])
+        self.wind = Module(os.path.join(phys, "wind.f90")).build(["balance_uvw", "calc_divergence"])
+        self._time_step_path = os.path.join(root, "src", "main", "time_step.f90")
+        self.time_step = Module(self._time_step_path).build(["compute_dt"])
+        # icar_constants (Rd, cp, ...) for exner_function: the values come from the source text as well
+        self.constants = Module(os.path.join(root, "src", "constants", "icar_constants.f90")).build([]).M
+        self.atm = Module(os.path.join(root, "src", "utilities", "atm_utilities.f90"),
+                          names={"rd": self.constants.rd, "cp": self.constants.cp}).build(["exner_function"])
 
     # ---- mp_thompson.f90
     # thompson_init runs as written except for the two rain-collection tables, whose builders (qr_acr_qg, qr_acr_qs;
@@ -138,16 +146,12 @@ class Reference:
                  "ice_number_concentration": "cloud_ice_number", "rain_number_concentration": "rain_number",
                  "snow_number_concentration": "snow_number", "graupel_number_concentration": "graupel_number"}
 
-    def mpdata(self, fields, u, v, w, jacobian_u, jacobian_v, jacobian_w, jacobian, advection_dz, dt, dx,
-               mpdata_order=2, fct=True):
-        """mpdata(domain, options, dt), adv_mpdata.f90:463-524, on a mock domain: `fields` maps kVARS names
-        (ADVECTED) to (ny, nz, nx) float32 arrays, advected in place in the reference's order; u (ny, nz, nx+1),
-        v (ny+1, nz, nx).  The module arrays U_m, V_m, W_m are (re)allocated by the routine itself."""
+    def _mock_domain(self, fields, u, v, w, jacobian_u, jacobian_v, jacobian_w, jacobian, advection_dz, dx, mpdata_order, fct):
         ns = types.SimpleNamespace
         ny, nz, nx = w.shape
         fa = lambda a: FArr(_f(a)[1], (1, 1, 1))          # noqa: E731
         dom = ns(grid=ns(ims=1, ime=nx, kms=1, kme=nz, jms=1, jme=ny), ims=1, ime=nx, kms=1, kme=nz, jms=1, jme=ny,
-                 dx=f32(dx), advection_dz=fa(advection_dz), density=ns(data_3d=None),
+                 dx=f32(dx), advection_dz=fa(advection_dz), density=ns(data_3d=fa(np.ones_like(w))),
                  u=ns(data_3d=fa(u)), v=ns(data_3d=fa(v)), w=ns(data_3d=fa(w)), jacobian_u=fa(jacobian_u),
                  jacobian_v=fa(jacobian_v), jacobian_w=fa(jacobian_w), jacobian=fa(jacobian))
         flags = {}
@@ -160,6 +164,72 @@ class Reference:
                 setattr(dom, self.COMPONENT[name], ns(data_3d=FArr(arr.T, (1, 1, 1))))
         opts = ns(parameters=ns(advect_density=False, debug=False, dz_levels=None), vars_to_advect=flags,
                   adv_options=ns(mpdata_order=int(mpdata_order), flux_corrected_transport=bool(fct)))
+        return dom, opts
+
+    def upwind(self, fields, u, v, w, jacobian_u, jacobian_v, jacobian_w, jacobian, advection_dz, dt, dx):
+        """upwind(domain, options, dt), advect.f90:361-388 (advection = 1): setup_module_winds :304-336 + advect3d :106-178"""
+        dom, opts = self._mock_domain(fields, u, v, w, jacobian_u, jacobian_v, jacobian_w, jacobian, advection_dz, dx, 1, False)
+        M = self.upw.M
+        for n in ("u_m", "v_m", "w_m", "lastqv_m"):
+            getattr(M, n).a = None
+        self.upw.upwind(dom, opts, f32(dt))
+
+    def balance_uvw(self, u, v, w, jacobian_u, jacobian_v, jacobian_w, dz, dx, jacobian):
+        """balance_uvw (wind.f90:81-172): w (ny, nz, nx) is overwritten in place"""
+        for a in (u, v, w):
+            if not (a.flags.c_contiguous and a.dtype == np.float32):
+                raise ValueError("u, v, w must be C-contiguous float32")
+        self.wind.balance_uvw(u.T, v.T, w.T, _f(jacobian_u)[1], _f(jacobian_v)[1], _f(jacobian_w)[1], _f(dz)[1], f32(dx),
+                              _f(jacobian)[1], None)
+
+    def compute_dt(self, dx, u, v, w, dz_levels, cfl, cfl_strictness):
+        """compute_dt (time_step.f90:217-330) with use_density = .false.; raises runtime.FortranStop where it stops"""
+        return self.time_step.compute_dt(f32(dx), _f(u)[1], _f(v)[1], _f(w)[1], _f(np.ones_like(w))[1],
+                                         np.ascontiguousarray(dz_levels, np.float32), f32(cfl), int(cfl_strictness), False)
+
+    def diagnostic_update(self, pressure, th, u, v, w, jacobian, dzdx, dzdy):
+        """diagnostic_update(domain, options), time_step.f90:49-198, on a mock domain that has the fields of this path
+        (exner, density, temperature, the interface fields, psfc, u_mass, v_mass, w_real) and none of the others
+        (ivt / iwv / roughness / 10 m winds are not associated).  Returns name -> (ny, nz, nx) / (ny, nx) arrays."""
+        ns = types.SimpleNamespace
+        ny, nz, nx = w.shape
+        if not hasattr(self, "_diag"):
+            self._diag = Module(self._time_step_path, names={"karman": self.constants.karman, "rd": self.constants.rd},
+                                externals={"exner_function": self.atm.exner_function, "compute_ivt": None,
+                                           "compute_iq": None}).build(["diagnostic_update"])
+        out = {k: np.zeros((ny, nz, nx), np.float32) for k in ("exner", "density", "temperature", "pressure_interface",
+                                                                "temperature_interface", "u_mass", "v_mass", "w_real")}
+        out["surface_pressure"] = np.zeros((ny, nx), np.float32)
+        fa = lambda a: FArr(_f(a)[1], (1,) * a.ndim)          # noqa: E731
+        var3 = lambda a: ns(data_3d=fa(a))                    # noqa: E731
+        none3, none2 = ns(data_3d=None), ns(data_2d=None)
+        dom = ns(ims=1, ime=nx, kms=1, kme=nz, jms=1, jme=ny, exner=var3(out["exner"]), pressure=var3(pressure),
+                 pressure_interface=var3(out["pressure_interface"]), dz_interface=none3,
+                 surface_pressure=ns(data_2d=FArr(out["surface_pressure"].T, (1, 1))), density=var3(out["density"]),
+                 water_vapor=none3, cloud_water_mass=none3, rain_mass=none3, cloud_ice_mass=none3, snow_mass=none3,
+                 graupel_mass=none3, temperature=var3(out["temperature"]),
+                 temperature_interface=var3(out["temperature_interface"]), u=var3(u), v=var3(v), w=var3(w),
+                 w_real=var3(out["w_real"]), u_mass=var3(out["u_mass"]), v_mass=var3(out["v_mass"]),
+                 potential_temperature=var3(th), ivt=none2, iwv=none2, iwl=none2, iwi=none2, roughness_z0=none2,
+                 u_10m=none2, v_10m=none2, ustar=None, z=none3, terrain=none2, dzdx=fa(dzdx), dzdy=fa(dzdy),
+                 jacobian=fa(jacobian))
+        M = self._diag.M
+        for n in ("lastw", "currw", "uw", "vw"):            # `if (.not.allocated(lastw))`: a new grid needs new module arrays
+            getattr(M, n).a = None
+        self._diag.diagnostic_update(dom, ns())
+        return out
+
+    def exner_function(self, pressure):
+        """exner_function (atm_utilities.f90:682-691), elemental, with Rd and cp of icar_constants.f90"""
+        return self.atm.exner_function(np.ascontiguousarray(pressure, np.float32))
+
+    def mpdata(self, fields, u, v, w, jacobian_u, jacobian_v, jacobian_w, jacobian, advection_dz, dt, dx,
+               mpdata_order=2, fct=True):
+        """mpdata(domain, options, dt), adv_mpdata.f90:463-524, on a mock domain: `fields` maps kVARS names
+        (ADVECTED) to (ny, nz, nx) float32 arrays, advected in place in the reference's order; u (ny, nz, nx+1),
+        v (ny+1, nz, nx).  The module arrays U_m, V_m, W_m are (re)allocated by the routine itself."""
+        dom, opts = self._mock_domain(fields, u, v, w, jacobian_u, jacobian_v, jacobian_w, jacobian, advection_dz, dx,
+                                      mpdata_order, fct)
         M = self.adv.M
         for n in ("u_m", "v_m", "w_m"):                  # `if (.not.allocated(U_m))`: a new grid needs new module arrays
             getattr(M, n).a = None

@@ -133,6 +133,8 @@ def is_allocated(x):
 
 # ------------------------------------------------------------------ scalar conversions (assignment to a typed variable)
 def r4(x):
+    if isinstance(x, np.ndarray):                 # an elemental procedure applied to an array
+        return x if x.dtype == np.float32 else x.astype(np.float32)
     return x if type(x) is np.float32 else np.float32(x)
 
 
@@ -286,6 +288,14 @@ def f_size(x, dim=None):
     return int(a.size) if dim is None else int(a.shape[int(dim) - 1])
 
 
+def f_lbound(x, dim):
+    return int(x.lb[int(dim) - 1]) if isinstance(x, FArr) else 1
+
+
+def f_ubound(x, dim):
+    return f_lbound(x, dim) + int(A(x).shape[int(dim) - 1]) - 1
+
+
 def f_ceiling(x):
     return int(math.ceil(float(x)))
 
@@ -369,7 +379,7 @@ NAMES = {
     "_fn_nint": f_nint, "_fn_int": f_int, "_fn_real": f_real, "_fn_float": f_real, "_fn_dble": f_dble, "_fn_mod": f_mod,
     "_fn_sign": f_sign, "_fn_merge": f_merge, "_fn_this_image": f_this_image, "_fn_num_images": f_num_images,
     "_fn_allocated": is_allocated, "_fn_associated": lambda x, *a: x is not None, "_fn_present": lambda x: x is not None,
-    "_arr": arr, "_fn_dmax1": f_max, "_fn_dmin1": f_min, "_fn_dlog": _as_double(math.log), "_fn_dlog10": _as_double(math.log10),
+    "_arr": arr, "_fn_lbound": f_lbound, "_fn_ubound": f_ubound, "_fn_dmax1": f_max, "_fn_dmin1": f_min, "_fn_dlog": _as_double(math.log), "_fn_dlog10": _as_double(math.log10),
     "_fn_dexp": _as_double(math.exp), "_fn_dsqrt": _as_double(math.sqrt), "_fn_dabs": f_abs, "_fn_dfloat": f_dble,
     "_fn_sngl": f_real, "_fn_tanh": f_tanh, "_fn_atan": f_atan, "_fn_iabs": f_abs, "_fn_trim": lambda x: x,
 }

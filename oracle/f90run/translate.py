@@ -188,11 +188,11 @@ def tokenize(s):
 REL = {"==": "==", "/=": "!=", "<": "<", "<=": "<=", ">": ">", ">=": ">=",
        ".eq.": "==", ".ne.": "!=", ".lt.": "<", ".le.": "<=", ".gt.": ">", ".ge.": ">="}
 
-INTRINSICS = {"abs", "max", "min", "amax1", "amin1", "dmax1", "dmin1", "maxval", "minval", "sum", "size", "exp", "log",
+INTRINSICS = {"lbound", "ubound", "abs", "max", "min", "amax1", "amin1", "dmax1", "dmin1", "maxval", "minval", "sum", "size", "exp", "log",
               "alog", "log10", "alog10", "sqrt", "ceiling", "floor", "nint", "int", "real", "float", "dble", "mod", "sign",
               "merge", "this_image", "num_images", "allocated", "associated", "present", "dlog", "dlog10", "dexp", "dsqrt",
               "dabs", "dfloat", "sngl", "tanh", "atan", "sin", "cos", "iabs", "trim", "gamma"}
-INT_RESULT = {"size", "ceiling", "floor", "nint", "int", "this_image", "num_images", "iabs"}
+INT_RESULT = {"lbound", "ubound", "size", "ceiling", "floor", "nint", "int", "this_image", "num_images", "iabs"}
 REAL_RESULT = {"real", "float", "sngl", "alog", "alog10", "amax1", "amin1"}
 DOUBLE_RESULT = {"dble", "dfloat", "dlog", "dlog10", "dexp", "dsqrt", "dabs", "dmax1", "dmin1"}
 
@@ -224,7 +224,16 @@ class Scope:
     def lookup(self, name):
         if name in self.locals:
             return self.locals[name]
-        return self.module.vars.get(name)
+        if name in self.module.vars:
+            return self.module.vars[name]
+        if name in self.module.names:                # an entity of another module, supplied by the harness
+            v = self.module.names[name]
+            import numpy as _np
+            kind = "r" if isinstance(v, _np.float32) else "d" if isinstance(v, (_np.float64, float)) else \
+                   "i" if isinstance(v, int) else None
+            if kind:
+                return Var(name, kind, parameter=True)
+        return None
 
     def ref(self, name):
         """python expression of a variable reference"""
@@ -234,6 +243,8 @@ class Scope:
             return py_name(name)
         if name in self.module.vars:
             return "_M." + py_name(name)
+        if name in self.module.names:
+            return py_name(name)
         raise TranslateError(f"undeclared name {name!r} in {self.routine}")
 
 
@@ -407,6 +418,11 @@ class ExprParser:
 
     def arg(self):
         lo = hi = st = None
+        if self.peek()[0] == "name" and self.t[self.p + 1] == ("op", "="):
+            kw = self.next()[1]
+            self.next()
+            c, k = self.expr()
+            return ("kw", c, k, kw)
         if self.peek() != ("op", ":"):
             # keyword argument name=expr (only for intrinsics like real(x, kind=...)): not needed in the subset
             lo = self.expr()
@@ -487,16 +503,36 @@ class ExprParser:
                 return f"{self.scope.ref(name)}[{self.subscript(a)}]", var.kind
             if var is not None and not var.is_array and self.scope.routine and name == self.scope.routine.result:
                 pass        # fall through: a recursive call is outside the subset, handled as a function below
+            if name in ("lbound", "ubound", "size") and self.peek()[0] == "name" and \
+                    self.scope.lookup(self.peek()[1]) is not None and self.scope.lookup(self.peek()[1]).is_array and \
+                    self.t[self.p + 1][1] in (",", ")"):
+                obj = self.scope.ref(self.next()[1])          # the array object itself: its bounds are asked for
+                rest = []
+                if self.accept("op", ","):
+                    rest = self.args()
+                else:
+                    self.expect("op", ")")
+                extra = "".join(", " + x[1] for x in rest)
+                return f"_fn_{name}({obj}{extra})", "i"
             a = self.args()
-            if any(x[0] != "expr" for x in a):
+            if any(x[0] not in ("expr", "kw") for x in a):
                 raise TranslateError(f"{name}(...) with a section but {name} is not an array")
-            argc = ", ".join(x[1] for x in a)
+            argc = ", ".join(x[1] for x in a if x[0] == "expr")
             if name in self.scope.module.routines:
                 r = self.scope.module.routines[name]
                 if not r.is_function:
                     raise TranslateError(f"subroutine {name} used as a function")
                 self.scope.module.need(name)
+                kws = [(x[3], x[1]) for x in a if x[0] == "kw"]
+                for kw, _ in kws:
+                    if kw not in r.args:
+                        raise TranslateError(f"{name}: no dummy argument {kw!r}")
+                argc = ", ".join([x[1] for x in a if x[0] == "expr"] + [f"{py_name(kw)}={c}" for kw, c in kws])
                 return f"_F_{name}({argc})", r.result_kind
+            if any(x[0] == "kw" for x in a):
+                raise TranslateError(f"{name}: keyword arguments of intrinsics are outside the subset")
+            if self.scope.module.externals.get(name) is not None:       # a function of another module (harness-supplied)
+                return f"_X_{name}({argc})", "?"
             if name in INTRINSICS:
                 if name in INT_RESULT:
                     k = "i"
@@ -806,8 +842,12 @@ class Module:
                     emit(f"{pn} = _alloc({DTYPE[v.kind]}, {b})")
             else:
                 if v.init is not None:
-                    raise TranslateError(f"{name}: local {vn} has an initialiser (implies SAVE): outside the subset")
-                emit(f"{pn} = {'False' if v.kind == 'l' else self.convert('0', v.kind)}")
+                    # an initialised local is SAVEd; that is indistinguishable from a constant iff it is never assigned
+                    if any(re.match(rf"^(if\s*\(.*\)\s*)?{re.escape(vn)}\s*(\(.*\))?\s*=[^=]", t) for _, _, t in r.body[r.exec_start:]):
+                        raise TranslateError(f"{name}: local {vn} has an initialiser (SAVE) and is assigned: outside the subset")
+                    emit(f"{pn} = {self.convert(self.expr(v.init, scope)[0], v.kind)}")
+                else:
+                    emit(f"{pn} = {'False' if v.kind == 'l' else self.convert('0', v.kind)}")
         # executable part
         block = []                                         # stack of open constructs
         body = [(f, no) + split_label(t) for f, no, t in r.body[r.exec_start:]]
@@ -915,6 +955,12 @@ class Module:
         if name in self.externals and self.externals[name] is None:
             emit("pass")
             return
+        kwargs = []
+        for a in list(actuals):
+            mk = re.match(r"^(\w+)\s*=(?!=)\s*(.*)$", a)
+            if mk:
+                kwargs.append((mk.group(1), self.expr(mk.group(2), scope)[0]))
+                actuals.remove(a)
         codes = [self.expr(a, scope)[0] for a in actuals]
         if name in self.overrides:
             emit(f"_O_{name}(_M)")
@@ -925,12 +971,16 @@ class Module:
                 raise TranslateError(f"function {name} called as a subroutine")
             self.need(name)
             outs = r.out_positions()
-            if any(re.match(r"^\w+\s*=[^=]", a) for a in actuals):
-                raise TranslateError(f"call {name}: keyword arguments are outside the subset")
-            if len(actuals) > len(r.args) or any(not r.decls[a].optional for a in r.args[len(actuals):]):
-                raise TranslateError(f"call {name}: {len(actuals)} actual arguments for {len(r.args)} dummies")
-            emit(f"_ret = _F_{name}({', '.join(codes)})")
+            given = set(r.args[:len(actuals)]) | {k for k, _ in kwargs}
+            if len(actuals) > len(r.args) or any(k not in r.args for k, _ in kwargs) or \
+                    any(not r.decls[a].optional for a in r.args if a not in given):
+                raise TranslateError(f"call {name}: actual arguments do not match the {len(r.args)} dummies")
+            if any(r.args.index(k) in outs for k, _ in kwargs):
+                raise TranslateError(f"call {name}: keyword argument for a scalar that is copied back")
+            emit(f"_ret = _F_{name}({', '.join(codes + [py_name(k) + '=' + c for k, c in kwargs])})")
             for k, pos in enumerate(outs):
+                if pos >= len(actuals):
+                    continue
                 a = actuals[pos].strip()
                 if re.match(r"^\w+\s*(\(.*\))?$", a) or "%" in a:
                     try:
@@ -1168,8 +1218,7 @@ class Module:
                 try:
                     init.append(f"    _M.{pn} = {self.convert(self.expr(v.init, mscope)[0], v.kind)}")
                 except TranslateError:
-                    if v.parameter and v.kind in "rdil":
-                        raise
+                    pass        # outside the subset: the name stays undefined, and any use of it fails loudly at run time
             elif v.kind in "rdi":
                 init.append(f"    _M.{pn} = {self.convert('0', v.kind)}")
             elif v.kind == "l":

@@ -210,10 +210,26 @@ RD = np.float32(287.058)     # src/constants/icar_constants.f90:391
 CP = np.float32(1012.0)      # src/constants/icar_constants.f90:393
 
 
+def powf(x, y):
+    """x ** y on REAL operands as the compiled Fortran evaluates it: glibc's powf, element by element (NumPy's own
+    vectorised float32 power differs from it in the last bit now and then)"""
+    import ctypes
+    import ctypes.util
+    lm = ctypes.CDLL(ctypes.util.find_library("m") or "libm.so.6")
+    lm.powf.argtypes = [ctypes.c_float, ctypes.c_float]
+    lm.powf.restype = ctypes.c_float
+    x = np.ascontiguousarray(x, np.float32)
+    out = np.empty_like(x)
+    fo, fx, yy = out.reshape(-1), x.reshape(-1), float(np.float32(y))
+    for n in range(fx.size):
+        fo[n] = lm.powf(float(fx[n]), yy)
+    return out
+
+
 def diagnostic_update_np(pressure, th):
     """exner and density as diagnostic_update computes them (src/main/time_step.f90:85,96,101;
     exner_function, src/utilities/atm_utilities.f90:682-691).  float32 throughout."""
-    exner = (pressure / np.float32(100000)) ** (RD / CP)
+    exner = powf(pressure / np.float32(100000), RD / CP)
     temperature = th * exner
     density = pressure / (RD * temperature)
     return exner.astype(np.float32), density.astype(np.float32)
@@ -223,7 +239,7 @@ def diagnostic_output_np(pressure, th, u, v, w, jacobian, dzdx, dzdy):
     """The rest of diagnostic_update (src/main/time_step.f90:88-108, 165-194), array expressions as written there.
     Arrays are (y, z, x): u (ny,nz,nx+1), v (ny+1,nz,nx), dzdx like u, dzdy like v.  float32 throughout."""
     f = np.float32
-    exner = ((pressure / f(100000)) ** (RD / CP)).astype(f)
+    exner = powf(pressure / f(100000), RD / CP)
     o = {}
     pi = np.empty_like(pressure)
     pi[:, 1:, :] = (pressure[:, :-1, :] + pressure[:, 1:, :]) / f(2)                          # :88
