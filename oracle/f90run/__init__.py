@@ -68,7 +68,7 @@ class Reference:
             def f(M):
                 for n in names:
                     getattr(M, n).a[...] = tables[n]
-            return f
+            return lambda M, *a, **k: f(M)
         path = os.path.join(os.path.dirname(self.mp_path), "mp_thompson.f90")
         over = {"qr_acr_qg": fill(self.BIG_QG), "qr_acr_qs": fill(self.BIG_QS)}
         if skip_freezeh2o:
@@ -218,6 +218,32 @@ class Reference:
             getattr(M, n).a = None
         self._diag.diagnostic_update(dom, ns())
         return out
+
+    def mp_schedule(self, calls, update_interval, grid):
+        """mp(domain, options, dt_in, halo, subset), mp_driver.f90:673-772, with process_subdomain / process_halo replaced
+        by recorders: for each (model_time, dt_in, halo, subset) of `calls` the list of (routine, mp_dt, its, ite, jts,
+        jte, kts, kte) it would run -- the update_interval test, the mp_dt lag and the tile arithmetic, as written.
+        grid: dict with ids..kde, ims..kme, its..kte, nx, ny, nz."""
+        ns = types.SimpleNamespace
+        log = []
+
+        def rec(name):
+            def f(M, domain, options, mp_dt, *a, **k):
+                log[-1].append((name, float(mp_dt)) + tuple(int(k[n]) for n in ("its", "ite", "jts", "jte", "kts", "kte")) +
+                               ((int(a[0]),) if a else ()))
+            return f
+        path = os.path.join(os.path.dirname(self.mp_path), "mp_driver.f90")
+        mod = Module(path, overrides={"process_subdomain": rec("process_subdomain"), "process_halo": rec("process_halo"),
+                                      "allocate_module_variables": lambda M, *a: None})
+        drv = mod.build(["mp"])
+        drv.M.update_interval = f32(update_interval) if isinstance(drv.M.update_interval, np.float32) else int(update_interval)
+        drv.M.last_model_time = type(drv.M.last_model_time)(-999)
+        opts = ns(mp_options=ns(top_mp_level=0))
+        for t, dt, halo, subset in calls:
+            log.append([])
+            dom = ns(grid=ns(**grid), model_time=ns(seconds=lambda t=t: np.float64(t)))
+            drv.mp(dom, opts, f32(dt), halo, subset)
+        return log
 
     def exner_function(self, pressure):
         """exner_function (atm_utilities.f90:682-691), elemental, with Rd and cp of icar_constants.f90"""

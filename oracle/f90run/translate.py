@@ -485,7 +485,10 @@ class ExprParser:
                 if self.peek() == ("op", "("):
                     self.next()
                     a = self.args()
-                    code += f"[{self.subscript(a)}]"
+                    if not a:
+                        code += "()"                # a type-bound function without arguments, e.g. model_time%seconds()
+                    else:
+                        code += f"[{self.subscript(a)}]"
                     if self.peek() != ("op", "%"):
                         return code, "?"
             return f"_A({code})", "?"
@@ -963,7 +966,7 @@ class Module:
                 actuals.remove(a)
         codes = [self.expr(a, scope)[0] for a in actuals]
         if name in self.overrides:
-            emit(f"_O_{name}(_M)")
+            emit(f"_O_{name}({', '.join(['_M'] + codes + [py_name(k) + '=' + c for k, c in kwargs])})")
             return
         if name in self.routines:
             r = self.routines[name]

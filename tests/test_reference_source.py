@@ -335,3 +335,19 @@ def test_live_diagnostic_update(ref):
     for k in got:
         assert np.array_equal(got[k], want[k]), k
     assert np.abs(want["w_real"]).max() > 0.1
+
+
+@needs_reference
+def test_live_mp_driver_schedule(ref):
+    """mp(domain, options, dt_in, halo, subset) of src/physics/mp_driver.f90:673-772 executed with its scheme calls
+    replaced by recorders: the update_interval rule, the mp_dt lag (mp_dt = model_time - last_model_time, first call
+    max(update_interval, dt_in)) and the halo / subset tile arithmetic are what icar_mp implements -- the schedule below
+    is the one tests/test_gpu_parity.py::test_mp_update_interval_and_dt_lag holds the device to."""
+    g = dict(ids=1, ide=20, jds=1, jde=16, kds=1, kde=10, ims=1, ime=20, jms=1, jme=16, kms=1, kme=10,
+             its=2, ite=19, jts=2, jte=15, kts=1, kte=10, nx=20, ny=16, nz=10)
+    log = ref.mp_schedule([(0.0, 30.0, None, None), (30.0, 10.0, None, None), (40.0, 30.0, None, None)], 50, g)
+    assert log == [[("process_subdomain", 50.0, 2, 19, 2, 15, 1, 10)], [], [("process_subdomain", 40.0, 2, 19, 2, 15, 1, 10)]]
+    # step(): mp(halo=1) then mp(subset=1) at the same model time: the halo call must not advance last_model_time
+    log = ref.mp_schedule([(0.0, 30.0, 1, None), (0.0, 30.0, None, 1), (30.0, 30.0, 1, None), (30.0, 30.0, None, 1)], 0, g)
+    assert log == [[("process_halo", 30.0, 2, 19, 2, 15, 1, 10, 1)], [("process_subdomain", 30.0, 3, 18, 3, 14, 1, 10)],
+                   [("process_halo", 30.0, 2, 19, 2, 15, 1, 10, 1)], [("process_subdomain", 30.0, 3, 18, 3, 14, 1, 10)]]
