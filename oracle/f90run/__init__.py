@@ -245,6 +245,27 @@ class Reference:
             drv.mp(dom, opts, f32(dt), halo, subset)
         return log
 
+    def grid_dimensions(self, nx, ny, nz, nimages, image, halo, decomposition="x"):
+        """grid_t%set_grid_dimensions (src/objects/grid_obj.f90:144-255: my_n, my_start, update_with_halos) for image
+        `image` of `nimages`.  decomposition = "x": the slabs along x that BASELINE.json prescribes (ximages = nimages,
+        yimages = 1 -- domain_decomposition's search over splits replaced by that choice), "y": slabs along y,
+        "reference": domain_decomposition as written (the most square split).  Returns the grid_t integers."""
+        ns = types.SimpleNamespace
+
+        def slabs(M, this, gnx, gny, nimg, for_image=None, ratio=None):
+            this.ximages, this.yimages = (int(nimg), 1) if decomposition == "x" else (1, int(nimg))
+            this.ximg, this.yimg = (int(for_image), 1) if decomposition == "x" else (1, int(for_image))
+        root = os.path.dirname(os.path.dirname(os.path.dirname(self.mp_path)))
+        mod = Module(os.path.join(root, "src", "objects", "grid_obj.f90"), externals={"assert": None},
+                     names={"assertions": False, "kdefault_halo_size": 1, "_fn_num_images": lambda: int(nimages),
+                            "_fn_this_image": lambda: int(image)},
+                     overrides={} if decomposition == "reference" else {"domain_decomposition": slabs})
+        mod.component_dtype = {"dimensions": "object"}
+        g = mod.build(["set_grid_dimensions"])
+        this = ns(dimensions=None)
+        g.set_grid_dimensions(this, int(nx), int(ny), int(nz), None, None, int(halo), int(image))
+        return {k: v for k, v in vars(this).items() if isinstance(v, int) and not isinstance(v, bool)}
+
     def exner_function(self, pressure):
         """exner_function (atm_utilities.f90:682-691), elemental, with Rd and cp of icar_constants.f90"""
         return self.atm.exner_function(np.ascontiguousarray(pressure, np.float32))

@@ -679,6 +679,7 @@ class Module:
         # routine name -> [(regex, replacement statement)]: statements the harness replaces, each one documented where
         # it is used (the only use: the km_s / km_e range that wrf_dm_decomp1d would hand a rank of a parallel run)
         self.patches = patches or {}
+        self.component_dtype = {}            # derived-type component -> dtype name for ALLOCATE (default REAL)
         self.overrides = overrides or {}     # routine name -> python callable(module namespace) run INSTEAD of the routine
         self.names = names or {}             # entities of other modules the source refers to (e.g. kVARS)
         self.stmts = read_statements(path)
@@ -698,7 +699,7 @@ class Module:
         cur, in_contains, self.spec = None, False, []
         for st in self.stmts:
             _, _, t = st
-            m = re.match(r"^(?:(real|integer|logical|double\s+precision)\s+)?(?:(?:pure|elemental|recursive)\s+)*"
+            m = re.match(r"^(?:(real|integer|logical|double\s+precision)\s+)?(?:(?:pure|elemental|recursive|module)\s+)*"
                          r"(subroutine|function)\s+(\w+)\s*(?:\((.*?)\))?\s*(?:result\s*\(\s*(\w+)\s*\))?$", t)
             if m and cur is None and in_contains:
                 pk = {"real": "r", "integer": "i", "logical": "l"}.get((m.group(1) or "").split()[0] if m.group(1) else "", None)
@@ -946,14 +947,23 @@ class Module:
             emit(f"{obj}.assign({c})")
         else:       # a derived-type component or an associate name without subscripts: array or scalar, known at run time
             emit(f"_t = {c}")
-            emit(f"if isinstance({obj}, _FArr): {obj}.assign(_t)")
+            if "." in obj and not obj.endswith("]"):
+                parent, attr = obj.rsplit(".", 1)
+                emit(f"if isinstance(getattr({parent}, {attr!r}, None), _FArr): {obj}.assign(_t)")
+            else:
+                emit(f"if isinstance({obj}, _FArr): {obj}.assign(_t)")
             emit(f"else: {obj} = _t")
 
     def _call(self, t, scope, emit):
         m = re.match(r"^call\s+(\w+)\s*(\((.*)\))?$", t)
-        if not m:
+        mb = re.match(r"^call\s+(\w+)\s*%\s*(\w+)\s*(\((.*)\))?$", t)
+        if mb and (mb.group(2) in self.routines or mb.group(2) in self.overrides):
+            # a type-bound procedure whose implementation is a routine of this module: the object is the first argument
+            name, argtext = mb.group(2), mb.group(1) + ("," + mb.group(4) if (mb.group(4) or "").strip() else "")
+        elif not m:
             raise TranslateError("cannot parse call")
-        name, argtext = m.group(1), m.group(3) or ""
+        else:
+            name, argtext = m.group(1), m.group(3) or ""
         actuals = split_top(argtext) if argtext.strip() else []
         if name in self.externals and self.externals[name] is None:
             emit("pass")
@@ -1147,7 +1157,8 @@ class Module:
                 b, _, _ = self.bounds(dims, scope)
                 if "%" in target:
                     _, _, _, _, obj = self._lvalue(target, scope)
-                    emit(f"{obj} = _alloc(_f32, {b}, True)")
+                    comp = target.split("%")[-1].strip()
+                    emit(f"{obj} = _alloc({self.component_dtype.get(comp, '_f32')}, {b}, True)")
                 else:
                     v = scope.lookup(target)
                     emit(f"{scope.ref(target)} = _alloc({DTYPE[v.kind]}, {b}, True)")
@@ -1155,6 +1166,10 @@ class Module:
         m = re.match(r"^deallocate\s*\((.*)\)$", t)
         if m:
             for item in split_top(m.group(1)):
+                if "%" in item:
+                    _, _, _, _, obj = self._lvalue(item.strip(), scope)
+                    emit(f"{obj} = None")
+                    continue
                 v = scope.lookup(item.strip())
                 emit(f"{scope.ref(item.strip())} = _unallocated({DTYPE[v.kind]}, {len(split_top(v.dims))})")
             return ind

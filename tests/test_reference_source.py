@@ -351,3 +351,25 @@ def test_live_mp_driver_schedule(ref):
     log = ref.mp_schedule([(0.0, 30.0, 1, None), (0.0, 30.0, None, 1), (30.0, 30.0, 1, None), (30.0, 30.0, None, 1)], 0, g)
     assert log == [[("process_halo", 30.0, 2, 19, 2, 15, 1, 10, 1)], [("process_subdomain", 30.0, 3, 18, 3, 14, 1, 10)],
                    [("process_halo", 30.0, 2, 19, 2, 15, 1, 10, 1)], [("process_subdomain", 30.0, 3, 18, 3, 14, 1, 10)]]
+
+
+@needs_reference
+@pytest.mark.parametrize("n,nimg,halo", [(512, 8, 3), (512, 8, 1), (100, 3, 1), (1024, 4, 3), (37, 5, 2)])
+def test_live_grid_bounds(ref, n, nimg, halo):
+    """grid_t%set_grid_dimensions of src/objects/grid_obj.f90:144-255 (my_n, my_start, update_with_halos) executed for every
+    image of a slab decomposition (ximages = nimages, yimages = 1 and the transpose -- the choice BASELINE.json prescribes in
+    place of domain_decomposition's most-square split) against icar_grid_xslab / icar_grid_yslab (pure host functions)"""
+    import icar_b200
+    keys = ("ims", "ime", "kms", "kme", "jms", "jme", "its", "ite", "kts", "kte", "jts", "jte", "ids", "ide", "kds", "kde",
+            "jds", "jde", "halo_size")
+    for img in range(1, nimg + 1):
+        want = ref.grid_dimensions(n, 64, 20, nimg, img, halo, "x")
+        g = icar_b200.Grid.xslab(n, 20, 64, nimg, img, halo)
+        assert {k: getattr(g, k) for k in keys} == {k: want[k] for k in keys}, ("x", img)
+        want = ref.grid_dimensions(64, n, 20, nimg, img, halo, "y")
+        g = icar_b200.Grid.yslab(64, 20, n, nimg, img, halo)
+        assert {k: getattr(g, k) for k in keys} == {k: want[k] for k in keys}, ("y", img)
+    # domain_decomposition as written picks the most square split instead: 8 images of a square domain are 2 x 4
+    if (n, nimg) == (512, 8):
+        sq = ref.grid_dimensions(512, 512, 40, 8, 3, 1, "reference")
+        assert (sq["ximages"], sq["yimages"], sq["ximg"], sq["yimg"]) == (2, 4, 1, 2)
