@@ -535,8 +535,9 @@ def run_b200(args, rank, world, local_rank):
             src, dst = sets[_n[0] % 2], sets[(_n[0] + 1) % 2]
             pipe.step(dt_, src, {k: dst[k] for k in out_keys})
             _n[0] += 1
-        e2e_api = (f"icar_b200.pipeline.HostPipeline: icar_physics_step_host_io over {n_bands} bands of rows, 4 ghost rows, one "
-                   "context and host thread per band (pinned host arrays, inputs and outputs swapped every step"
+        e2e_api = (f"icar_b200.pipeline.HostPipeline: icar_physics_step_host_io_async over {n_bands} bands of rows, 4 ghost "
+                   "rows, one context per band, queued in band order from one host thread and awaited (pinned host arrays, "
+                   "inputs and outputs swapped every step"
                    + ("; exner / density derived on the device)" if derive else ")"))
     for _ in range(2):
         host_step(dt, hd)
@@ -727,7 +728,7 @@ def main():
                     help="e2e: upload exner and density with the other host arrays (icar_physics_step_host) instead of "
                          "deriving them on the device from pressure and potential temperature (diagnostic_update, what "
                          "step()'s loop does before the physics; the default)")
-    ap.add_argument("--e2e-bands", type=int, default=8,
+    ap.add_argument("--e2e-bands", type=int, default=4,
                     help="e2e pipelined over this many bands of rows (icar_b200/pipeline.py; N=1 only); 1 = the plain host step")
     ap.add_argument("--no-parity", action="store_true", help="skip the oracle comparison (N=1) after the timed region")
     ap.add_argument("--no-other-axis", action="store_true", help="N>1: do not also time the other decomposition axis")

@@ -166,7 +166,7 @@ SYMBOLS = (
     "icar_timer_start", "icar_timer_stop",
     "icar_halo_plan", "icar_comm_unique_id", "icar_comm_init", "icar_comm_init_local", "icar_mpdata_set_winds", "icar_mpdata_advect3d",
     "icar_mpdata_set_winds_f64", "icar_mpdata_advect3d_f64", "icar_mp_simple_driver",
-    "icar_physics_step_host", "icar_step_host", "icar_physics_step_host_io", "icar_host_register", "icar_host_unregister",
+    "icar_physics_step_host", "icar_step_host", "icar_physics_step_host_io", "icar_physics_step_host_io_async", "icar_host_register", "icar_host_unregister",
     "icar_default_mp_options", "icar_thompson_init", "icar_thompson_table", "icar_mp_gt_driver",
     "icar_profile_enable", "icar_profile_read", "icar_diagnostic_update", "icar_diagnostic_output", "icar_compute_dt", "icar_enforce_limits",
     "icar_upload_tendency", "icar_apply_forcing", "icar_balance_uvw",
@@ -585,6 +585,11 @@ class Domain:
         """Host step with separate input / output arrays; only the tile's rows row0..row1 come back."""
         self._check(lib().icar_physics_step_host_io(self._h, C.c_float(dt), C.byref(hd_in), C.byref(hd_out),
                                                     int(row0), int(row1), 1 if derive_diagnostics else 0))
+
+    def physics_step_host_io_async(self, dt, hd_in, hd_out, row0, row1, derive_diagnostics=False):
+        """physics_step_host_io queued only (pinned host arrays); wait with synchronize()."""
+        self._check(lib().icar_physics_step_host_io_async(self._h, C.c_float(dt), C.byref(hd_in), C.byref(hd_out),
+                                                          int(row0), int(row1), 1 if derive_diagnostics else 0))
 
     def host_register(self, hd): self._check(lib().icar_host_register(self._h, C.byref(hd)))
     def host_unregister(self, hd): self._check(lib().icar_host_unregister(self._h, C.byref(hd)))

@@ -1553,8 +1553,24 @@ extern "C" int icar_step_host(icar_ctx* ctx, float dt, const icar_host_domain* d
 // to pipeline one model step over several contexts that each hold a band of rows (icar_b200/pipeline.py).
 // `in`: every non-NULL member is uploaded (the whole tile).  `out`: every non-NULL output member receives the
 // tile's rows row0..row1 (0-based y index, inclusive); the pointer addresses the tile's row 0.
+namespace {
+int host_io_impl(icar_ctx* ctx, float dt, const icar_host_domain* in, const icar_host_domain* out, int row0, int row1,
+                 int derive_diagnostics, bool wait);
+}
+
 extern "C" int icar_physics_step_host_io(icar_ctx* ctx, float dt, const icar_host_domain* in, const icar_host_domain* out,
                                          int row0, int row1, int derive_diagnostics) {
+    return host_io_impl(ctx, dt, in, out, row0, row1, derive_diagnostics, true);
+}
+
+extern "C" int icar_physics_step_host_io_async(icar_ctx* ctx, float dt, const icar_host_domain* in,
+                                               const icar_host_domain* out, int row0, int row1, int derive_diagnostics) {
+    return host_io_impl(ctx, dt, in, out, row0, row1, derive_diagnostics, false);
+}
+
+namespace {
+int host_io_impl(icar_ctx* ctx, float dt, const icar_host_domain* in, const icar_host_domain* out, int row0, int row1,
+                 int derive_diagnostics, bool wait) {
     if (!ctx || !in || !out) return fail(ctx, ICAR_ERR_INVALID, "icar_physics_step_host_io: null argument");
     if (row0 < 0 || row1 >= ctx->g.ny || row1 < row0) return fail(ctx, ICAR_ERR_INVALID, "icar_physics_step_host_io: bad row range");
     if (derive_diagnostics && (in->exner || in->density))
@@ -1583,9 +1599,10 @@ extern "C" int icar_physics_step_host_io(icar_ctx* ctx, float dt, const icar_hos
         if ((rc = copy_out(ctx, (char*)h.out + first * (size_t)width * es,
                            (const char*)ctx->vars[h.var] + first * (size_t)pitch * es, width, pitch, count, es))) return rc;
     }
-    CU(cudaStreamSynchronize(ctx->stream));
+    if (wait) CU(cudaStreamSynchronize(ctx->stream));
     return ICAR_OK;
 }
+}  // namespace
 
 extern "C" int icar_host_register(icar_ctx* ctx, const icar_host_domain* dom) {
     if (!ctx || !dom) return fail(ctx, ICAR_ERR_INVALID, "icar_host_register: null argument");

@@ -505,6 +505,11 @@ int icar_step_host(icar_ctx* ctx, float dt, const icar_host_domain* dom);
  * member of `in` is uploaded (whole tile); every non-NULL output member of `out` receives the tile's rows
  * row0..row1 (0-based y index, inclusive) at its place in an array whose row 0 is the tile's row 0.
  * derive_diagnostics != 0: exner / density as in icar_step_host. */
+int icar_physics_step_host_io_async(icar_ctx* ctx, float dt, const icar_host_domain* in, const icar_host_domain* out,
+                                    int row0, int row1, int derive_diagnostics);
+/* (the _async form above only QUEUES the uploads, the kernels and the downloads on the context's streams and returns:
+ * the caller queues one band after the other, so that the copy engines serve the bands in order, and waits with
+ * icar_synchronize; host arrays must be pinned, icar_host_register, and must not be touched before that.) */
 int icar_physics_step_host_io(icar_ctx* ctx, float dt, const icar_host_domain* in, const icar_host_domain* out,
                               int row0, int row1, int derive_diagnostics);
 int icar_host_register(icar_ctx* ctx, const icar_host_domain* dom);

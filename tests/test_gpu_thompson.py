@@ -168,6 +168,27 @@ def test_mp_gt_driver_per_call_parity(gpu_lib, oracle_thompson, dims, dt):
         assert (seen > 1e-6).all(), f"scenario did not exercise every species: {seen}"
 
 
+def test_mp_gt_driver_at_the_benchmark_width(gpu_lib, oracle_thompson, capsys):
+    """One mp_gt_driver call at 512 x 40 x 64 (the benchmark's rows, 40 levels, the 16-column CTA) from a spun-up state
+    with every species present, against the oracle; prints how many columns were set aside as sitting on a discontinuity."""
+    nx, nz, ny = 512, 40, 64
+    ref = ideal.add_thompson_fields(ideal.make_ideal_case(nx=nx, nz=nz, ny=ny, perturb=True), moisten=3.0)
+    dom = make_domain(gpu_lib, nx, nz, ny)
+    for _ in range(8):                                   # spin-up on the device: the comparison below starts from ITS state
+        dom.mp_gt_driver(ref, 60.0, 2, nx - 1, 2, ny - 1, 1, nz)
+    assert all(ref[k].max() > 1e-6 for k in ("qc", "qr", "qi", "qs", "qg"))
+    st, inputs = ideal.copy_state(ref), ideal.copy_state(ref)
+    dom.mp_gt_driver(st, 60.0, 2, nx - 1, 2, ny - 1, 1, nz)
+    oracle_thompson.driver(ref, 60.0, 1, nx - 2, 1, ny - 2, 0, nz - 1)
+    excluded = compare_call(st, ref, "512x40x64", inputs,
+                            lambda p: oracle_thompson.driver(p, 60.0, 1, nx - 2, 1, ny - 2, 0, nz - 1))
+    with capsys.disabled():
+        print(f"\n[thompson 512x40x64] columns set aside as sitting on a discontinuity: {excluded} of {nx * ny} "
+              f"({100.0 * excluded / (nx * ny):.3f} %)")
+    assert excluded <= 0.01 * nx * ny
+    dom.close()
+
+
 def test_mp_gt_driver_100_levels(gpu_lib, oracle_thompson):
     """More than 80 levels run the 1024-thread instantiation (8 columns x 128 level threads).  The grid is
     too small (24 columns) for the L2 bars of the per-call test to be meaningful; cells must agree to 1e-4

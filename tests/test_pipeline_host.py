@@ -28,20 +28,26 @@ class RecordingDomain:
         for k, v in hout.items():
             v[row0:row1 + 1] = hin[k][row0:row1 + 1] + 1
 
+    physics_step_host_io_async = physics_step_host_io       # the ordered mode queues the bands from one thread ...
+
+    def synchronize(self):                                  # ... and waits for each
+        pass
+
     kernel_launches = 0
 
     def close(self):
         pass
 
 
+@pytest.mark.parametrize("ordered", [True, False])
 @pytest.mark.parametrize("bands,derive", [(3, True), (4, False), (1, False)])
-def test_bands_return_exactly_their_own_rows(monkeypatch, bands, derive):
+def test_bands_return_exactly_their_own_rows(monkeypatch, bands, derive, ordered):
     monkeypatch.setattr(P, "Domain", RecordingDomain)
     RecordingDomain.calls = []
     st = ideal.make_ideal_case(nx=16, nz=8, ny=40, perturb=True)
     for k in ("precipitation", "snowfall"):
         st[k] = np.zeros((40, 16))
-    pipe = P.HostPipeline(st, None, bands=bands, derive_diagnostics=derive)
+    pipe = P.HostPipeline(st, None, bands=bands, derive_diagnostics=derive, ordered=ordered)
     assert len(pipe.domains) == bands
     for dom, (a, b, v0, v1) in zip(pipe.domains, pipe.bounds):
         rows = v1 - v0 + 1
