@@ -266,6 +266,38 @@ class Reference:
         g.set_grid_dimensions(this, int(nx), int(ny), int(nz), None, None, int(halo), int(image))
         return {k: v for k, v in vars(this).items() if isinstance(v, int) and not isinstance(v, bool)}
 
+    # ---- linear_winds.f90 (+ fftshift.f90): the per-height solution, the layer means, the buffered terrain
+    def linear_winds(self):
+        """Translates the routines of src/physics/linear_winds.f90 that the cuFFT path restates and binds FFTW's entry
+        points to numpy.fft (an unnormalised backward / forward 2-D DFT, what fftw_execute_dft computes).  Returns the
+        namespace; `lt = ref.lt_data(nx, ny, dx)` then makes a linear_theory_type through initialize_linear_theory_data."""
+        if hasattr(self, "_lw"):
+            return self._lw
+        root = os.path.dirname(os.path.dirname(os.path.dirname(self.mp_path)))
+        shift = Module(os.path.join(root, "src", "utilities", "fftshift.f90")).build(["ifftshift2cc", "fftshift2cc"])
+
+        def execute_dft(plan, src, dst):
+            a = np.asarray(src)
+            dst[...] = (np.fft.ifft2(a) * a.size) if plan == "backward" else np.fft.fft2(a)
+        mod = Module(os.path.join(self.mp_path.rsplit("/", 1)[0], "linear_winds.f90"),
+                     externals={"ifftshift": shift.ifftshift2cc, "fftshift": shift.fftshift2cc, "fftw_execute_dft": execute_dft,
+                                "fftw_alloc_complex": lambda n: np.zeros(int(n), np.complex128),
+                                "fftw_plan_dft_2d": lambda n0, n1, a, b, sign, flags: "backward" if sign > 0 else "forward",
+                                "smooth_array": None, "io_write": None},
+                     names={"pi": self.constants.pi, "fftw_backward": 1, "fftw_forward": -1, "fftw_measure": 0,
+                            "fftw_estimate": 64})
+        mod.component_dtype = {k: "_np.complex128" for k in ("denom", "m", "msq", "mimag", "ineta")}
+        self._lw = mod.build(["initialize_linear_theory_data", "linear_perturbation_at_height", "linear_perturbation_constz",
+                              "linear_perturbation_varyingz", "add_buffer_topo"])
+        self._lw.shift = shift
+        return self._lw
+
+    def lt_data(self, nx, ny, dx):
+        lw = self.linear_winds()
+        lt = types.SimpleNamespace()
+        lw.initialize_linear_theory_data(lt, int(nx), int(ny), f32(dx))
+        return lt
+
     def exner_function(self, pressure):
         """exner_function (atm_utilities.f90:682-691), elemental, with Rd and cp of icar_constants.f90"""
         return self.atm.exner_function(np.ascontiguousarray(pressure, np.float32))

@@ -107,6 +107,14 @@ def alloc(dtype, bounds, allocatable=False):
     return FArr(np.zeros(shape, dtype=dtype, order="F"), [int(lo) for lo, _ in bounds], dtype, allocatable)
 
 
+def alloc_into(obj, dtype, bounds):
+    new = alloc(dtype, bounds, True)
+    if isinstance(obj, FArr):
+        obj.a, obj.lb, obj.dtype, obj.allocatable = new.a, new.lb, new.dtype, True
+        return obj
+    return new
+
+
 def unallocated(dtype, rank):
     return FArr(None, (1,) * rank, dtype, True)
 
@@ -225,6 +233,8 @@ def _unary_libm(name, dname):
     df = getattr(math, dname)
 
     def f(x):
+        if np.iscomplexobj(x):
+            return getattr(np, dname)(x)
         if isinstance(x, np.ndarray):
             if x.dtype == np.float32:
                 out = np.empty(x.shape, np.float32)
@@ -245,7 +255,7 @@ f_log10 = _unary_libm("log10f", "log10")
 
 
 def f_sqrt(x):
-    return np.sqrt(x)           # correctly rounded in every implementation
+    return np.sqrt(x)           # REAL / DOUBLE: correctly rounded in every implementation; COMPLEX: numpy's csqrt
 
 
 def f_abs(x):
@@ -315,9 +325,40 @@ def f_int(x):
 
 def f_real(x, kind=None):
     a = A(x)
+    if np.iscomplexobj(a):                        # REAL(z) has the kind of z
+        return a.real.copy() if isinstance(a, np.ndarray) else a.real
     if isinstance(a, np.ndarray):
         return a.astype(np.float32)
     return np.float32(a)
+
+
+def c64(x):
+    a = A(x)
+    return a.astype(np.complex64) if isinstance(a, np.ndarray) else np.complex64(a)
+
+
+def c128(x):
+    a = A(x)
+    return a.astype(np.complex128) if isinstance(a, np.ndarray) else np.complex128(a)
+
+
+def where_assign(obj, mask, val):
+    a = obj.a if isinstance(obj, FArr) else obj
+    mask = A(mask)
+    val = A(val)
+    a[mask] = val[mask] if isinstance(val, np.ndarray) else val
+
+
+def alloc_like(src, dtype):
+    a = A(src)
+    return FArr(np.array(a, dtype=dtype, order="F"), (1,) * a.ndim, dtype, True)
+
+
+def c_f_pointer(buffer, shape):
+    """c_f_pointer(cptr, fptr, shape): the Fortran pointer over the C buffer (here: the harness's numpy buffer)"""
+    shape = tuple(int(n) for n in A(shape))
+    n = int(np.prod(shape))
+    return FArr(buffer[:n].reshape(shape, order="F"), (1,) * len(shape), buffer.dtype)
 
 
 def f_dble(x):
@@ -369,7 +410,7 @@ def do_range(lo, hi, step=1):
 
 
 NAMES = {
-    "_FArr": FArr, "_Sl": Sl, "_ALL": ALL, "_A": A, "_alloc": alloc, "_unallocated": unallocated, "_wrap": wrap,
+    "_FArr": FArr, "_Sl": Sl, "_ALL": ALL, "_A": A, "_alloc": alloc, "_alloc_into": alloc_into, "_unallocated": unallocated, "_wrap": wrap,
     "_is_allocated": is_allocated, "_r4": r4, "_r8": r8, "_i4": i4, "_div": div, "_pow": power, "_cpow": cpow, "_do": do_range,
     "_f32": np.float32, "_f64": np.float64, "_i32": np.int32, "_np": np, "_Stop": FortranStop,
     "_fn_exp": f_exp, "_fn_log": f_log, "_fn_alog": f_log, "_fn_log10": f_log10, "_fn_alog10": f_log10,
@@ -379,6 +420,9 @@ NAMES = {
     "_fn_nint": f_nint, "_fn_int": f_int, "_fn_real": f_real, "_fn_float": f_real, "_fn_dble": f_dble, "_fn_mod": f_mod,
     "_fn_sign": f_sign, "_fn_merge": f_merge, "_fn_this_image": f_this_image, "_fn_num_images": f_num_images,
     "_fn_allocated": is_allocated, "_fn_associated": lambda x, *a: x is not None, "_fn_present": lambda x: x is not None,
+    "_c64": c64, "_c128": c128, "_where_assign": where_assign, "_alloc_like": alloc_like, "_c_f_pointer": c_f_pointer,
+    "_fn_cmplx": lambda a, b=0, kind=None: np.complex64(complex(a, b)), "_fn_aimag": lambda z: A(z).imag,
+    "_fn_conjg": lambda z: np.conj(A(z)),
     "_arr": arr, "_fn_lbound": f_lbound, "_fn_ubound": f_ubound, "_fn_dmax1": f_max, "_fn_dmin1": f_min, "_fn_dlog": _as_double(math.log), "_fn_dlog10": _as_double(math.log10),
     "_fn_dexp": _as_double(math.exp), "_fn_dsqrt": _as_double(math.sqrt), "_fn_dabs": f_abs, "_fn_dfloat": f_dble,
     "_fn_sngl": f_real, "_fn_tanh": f_tanh, "_fn_atan": f_atan, "_fn_iabs": f_abs, "_fn_trim": lambda x: x,

@@ -188,7 +188,7 @@ def tokenize(s):
 REL = {"==": "==", "/=": "!=", "<": "<", "<=": "<=", ">": ">", ">=": ">=",
        ".eq.": "==", ".ne.": "!=", ".lt.": "<", ".le.": "<=", ".gt.": ">", ".ge.": ">="}
 
-INTRINSICS = {"lbound", "ubound", "abs", "max", "min", "amax1", "amin1", "dmax1", "dmin1", "maxval", "minval", "sum", "size", "exp", "log",
+INTRINSICS = {"cmplx", "aimag", "conjg", "lbound", "ubound", "abs", "max", "min", "amax1", "amin1", "dmax1", "dmin1", "maxval", "minval", "sum", "size", "exp", "log",
               "alog", "log10", "alog10", "sqrt", "ceiling", "floor", "nint", "int", "real", "float", "dble", "mod", "sign",
               "merge", "this_image", "num_images", "allocated", "associated", "present", "dlog", "dlog10", "dexp", "dsqrt",
               "dabs", "dfloat", "sngl", "tanh", "atan", "sin", "cos", "iabs", "trim", "gamma"}
@@ -210,7 +210,7 @@ class Var:
         return self.dims is not None
 
 
-DTYPE = {"r": "_f32", "d": "_f64", "i": "_i32", "l": "bool", "c": "object", "?": "_f32"}
+DTYPE = {"r": "_f32", "d": "_f64", "i": "_i32", "l": "bool", "c": "object", "?": "_f32", "x": "_np.complex64", "z": "_np.complex128"}
 
 
 class Scope:
@@ -315,6 +315,10 @@ class ExprParser:
     def _join(k1, k2):
         if "?" in (k1, k2):
             return "?"
+        if "z" in (k1, k2) or ("x" in (k1, k2) and "d" in (k1, k2)):
+            return "z"
+        if "x" in (k1, k2):
+            return "x"
         if "d" in (k1, k2):
             return "d"
         if "r" in (k1, k2):
@@ -457,6 +461,11 @@ class ExprParser:
             return repr(v[1:-1]), "?"
         if kind == "op" and v == "(":
             c, k = self.expr()
+            if self.accept("op", ","):              # a complex literal (re, im)
+                c2, k2 = self.expr()
+                self.expect("op", ")")
+                kk = "z" if "d" in (k, k2) else "x"
+                return f"{DTYPE[kk]}(complex({c}, {c2}))", kk
             self.expect("op", ")")
             if c in self.constant:
                 self.constant.add(f"({c})")
@@ -564,8 +573,8 @@ class ExprParser:
 
 
 # ============================================================================================ declarations
-DECL_RE = re.compile(r"^(real|integer|logical|double\s+precision|character|type\s*\(|class\s*\()")
-SPEC_NO_COLONS = re.compile(r"^(real|integer|logical|double\s+precision|character)\s*(\([^)]*\)|\*\s*\d+)?\s+(.*)$")
+DECL_RE = re.compile(r"^(real|integer|logical|double\s+precision|complex|character|type\s*\(|class\s*\()")
+SPEC_NO_COLONS = re.compile(r"^(real|integer|logical|double\s+precision|complex|character)\s*(\([^)]*\)|\*\s*\d+)?\s+(.*)$")
 
 
 def split_top(s, sep=","):
@@ -610,6 +619,8 @@ def parse_declaration(stmt):
         kind = "d"
     elif spec.startswith("character"):
         kind = "c"
+    elif spec.startswith("complex"):
+        kind = "z" if ("double" in spec or "8" in spec or "16" in spec or "dp" in spec) else "x"
     elif spec.startswith("real"):
         kind = "r"
     elif spec.startswith("integer"):
@@ -692,7 +703,10 @@ class Module:
         self._split()
         self._parse_module_decls()
         for r in self.routines.values():
-            self._parse_routine_decls(r)
+            try:
+                self._parse_routine_decls(r)
+            except TranslateError as e:          # reported when (and only when) that routine is asked for
+                r.decl_error = e
 
     # ---- structure
     def _split(self):
@@ -723,7 +737,10 @@ class Module:
 
     def _parse_module_decls(self):
         for f, no, t in self.spec:
-            d = parse_declaration(t)
+            try:
+                d = parse_declaration(t)
+            except TranslateError:
+                continue        # e.g. a coarray: the entity stays undeclared, a routine that uses it does not translate
             if d is None:
                 continue
             kind, attrs, ents = d
@@ -735,7 +752,7 @@ class Module:
     def _parse_routine_decls(self, r):
         n = 0
         for n, (f, no, t) in enumerate(r.body):
-            if t.startswith("use ") or t.startswith("implicit ") or t.startswith("!$"):
+            if re.match(r"^use\b", t) or t.startswith("implicit ") or t.startswith("!$"):
                 continue
             d = parse_declaration(t)
             if d is None:
@@ -794,6 +811,8 @@ class Module:
     # ---- statements
     def translate(self, name):
         r = self.routines[name]
+        if getattr(r, "decl_error", None) is not None:
+            raise r.decl_error
         scope = Scope(self, r)
         scope.locals = dict(r.decls)
         L = []                                             # python lines
@@ -825,7 +844,9 @@ class Module:
                     emit(f"{pn} = {self.convert(self.expr(v.init, scope)[0], v.kind)}")
                 continue
             if v.dummy:
-                if v.is_array:
+                if v.is_array and v.allocatable:
+                    emit(f"assert isinstance({pn}, _FArr), 'an allocatable dummy argument needs the array object'")
+                elif v.is_array:
                     b, _, _ = self.bounds(v.dims, scope)
                     if v.optional:
                         emit(f"{pn} = _wrap({pn}, {b}, {DTYPE[v.kind]}) if {pn} is not None else None")
@@ -881,7 +902,8 @@ class Module:
         return "\n".join(L)
 
     def convert(self, code, kind):
-        return {"r": f"_r4({code})", "d": f"_r8({code})", "i": f"_i4({code})", "l": f"bool({code})"}.get(kind, code)
+        return {"r": f"_r4({code})", "d": f"_r8({code})", "i": f"_i4({code})", "l": f"bool({code})",
+                "x": f"_c64({code})", "z": f"_c128({code})"}.get(kind, code)
 
     def _return(self, r):
         if r.is_function:
@@ -1017,7 +1039,7 @@ class Module:
         def emit(s):
             emit_at(s, ind)
 
-        if t.startswith("!$") or t.startswith("use ") or t.startswith("implicit "):
+        if t.startswith("!$") or re.match(r"^use\b", t) or t.startswith("implicit "):
             return ind
         # ---- block ends / middles
         if re.match(r"^end\s*if$", t):
@@ -1081,6 +1103,29 @@ class Module:
                     c = c[3:-1]                     # the object itself, not its array: the alias may be indexed / assigned
                 scope.aliases[an.strip()] = c
             block.append("associate")
+            return ind
+        # ---- one-line where (mask) lhs = rhs
+        if re.match(r"^where\s*\(", t):
+            depth = 0
+            for k in range(t.index("("), len(t)):
+                depth += t[k] == "("
+                depth -= t[k] == ")"
+                if depth == 0:
+                    break
+            mask, rest = t[t.index("(") + 1:k], t[k + 1:].strip()
+            if not rest:
+                raise TranslateError("WHERE construct (block form) is outside the subset")
+            lhs, rhs = rest.split("=", 1)
+            kind, target, v, whole, obj = self._lvalue(lhs, scope)
+            if not whole:
+                raise TranslateError("WHERE on a section is outside the subset")
+            emit(f"_where_assign({obj}, {self.expr(mask, scope)[0]}, {self.expr(rhs, scope)[0]})")
+            return ind
+        m = re.match(r"^call\s+c_f_pointer\s*\((.*)\)$", t)
+        if m:
+            a = split_top(m.group(1))
+            _, _, _, _, obj = self._lvalue(a[1], scope)
+            emit(f"{obj} = _c_f_pointer({self.expr(a[0], scope)[0]}, {self.expr(a[2], scope)[0]})")
             return ind
         # ---- one-line if
         if re.match(r"^if\s*\(", t):
@@ -1149,10 +1194,18 @@ class Module:
             return ind
         m = re.match(r"^allocate\s*\((.*)\)$", t)
         if m:
-            for item in split_top(m.group(1)):
+            items = split_top(m.group(1))
+            source = None
+            if items and re.match(r"^source\s*=", items[-1]):
+                source = self.expr(items.pop().split("=", 1)[1], scope)[0]
+            for item in items:
                 mm = re.match(r"^(.*?)\((.*)\)$", item.strip())
                 if not mm:
-                    raise TranslateError("allocate without bounds")
+                    if source is None:
+                        raise TranslateError("allocate without bounds")
+                    v = scope.lookup(item.strip())
+                    emit(f"{scope.ref(item.strip())} = _alloc_like({source}, {DTYPE[v.kind]})")
+                    continue
                 target, dims = mm.group(1).strip(), mm.group(2)
                 b, _, _ = self.bounds(dims, scope)
                 if "%" in target:
@@ -1161,7 +1214,11 @@ class Module:
                     emit(f"{obj} = _alloc({self.component_dtype.get(comp, '_f32')}, {b}, True)")
                 else:
                     v = scope.lookup(target)
-                    emit(f"{scope.ref(target)} = _alloc({DTYPE[v.kind]}, {b}, True)")
+                    # into the SAME array object: an allocatable dummy argument must be seen allocated by the caller
+                    emit(f"{scope.ref(target)} = _alloc_into({scope.ref(target)}, {DTYPE[v.kind]}, {b})")
+                if source is not None:
+                    _, _, _, _, obj = self._lvalue(target, scope)
+                    emit(f"{obj}.assign({source})")
             return ind
         m = re.match(r"^deallocate\s*\((.*)\)$", t)
         if m:

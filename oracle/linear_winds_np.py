@@ -4,8 +4,10 @@
 PARITY: the Fortran cannot be compiled here and holds no expected values, but the reference ships a Python
 implementation of the same solution in its x-z form, helpers/ideal_linear.py:solve(); it is run in this container
 by tests/golden/make_linear_theory_golden.py and linear_perturbation_at_height reproduces its u_hat to 4.5e-8 of the
-field maximum (tests/test_oracle_linear_winds.py) -- so the per-height solution is PINNED; add_buffer_topo, the two
-shifts of fftshift.f90, the layer means and the 3-D (l /= 0) terms have no counterpart there and remain unpinned.
+field maximum (tests/test_oracle_linear_winds.py) -- so the per-height solution is PINNED; and (round 2) the Fortran itself
+is EXECUTED by oracle/f90run (FFTW's calls bound to numpy.fft): initialize_linear_theory_data, the per-height solution
+with l /= 0, both layer means, the two shifts of fftshift.f90 and add_buffer_topo equal this file's functions bit for
+bit (add_buffer_topo's smoothing sums to 1e-15), tests/test_reference_source.py::test_live_linear_winds.
 
 Follows, function by function:
     src/utilities/fftshift.f90:87-109, 217-239      fftshift2cc / ifftshift2cc (through a SINGLE precision temporary)

@@ -373,3 +373,48 @@ def test_live_grid_bounds(ref, n, nimg, halo):
     if (n, nimg) == (512, 8):
         sq = ref.grid_dimensions(512, 512, 40, 8, 3, 1, "reference")
         assert (sq["ximages"], sq["yimages"], sq["ximg"], sq["yimg"]) == (2, 4, 1, 2)
+
+
+@needs_reference
+def test_live_linear_winds(ref):
+    """src/physics/linear_winds.f90 executed (complex double arithmetic; FFTW's entry points bound to numpy.fft; the
+    reference's own fftshift.f90 with its single-precision temporary): initialize_linear_theory_data, the per-height
+    solution with l /= 0, the layer means over constant and terrain-following bounds, add_buffer_topo -- against
+    oracle/linear_winds_np.py, the restatement the cuFFT path is tested against"""
+    from oracle import linear_winds_np as LW
+    from oracle.f90run.runtime import unallocated
+    lw = ref.linear_winds()
+    nx, ny, dx = 24, 20, 2000.0
+    lt = ref.lt_data(nx, ny, dx)
+    L = LW.LinearTheoryData(nx, ny, dx)
+    assert np.array_equal(lt.k.a, L.k) and np.array_equal(lt.l.a, L.l) and np.array_equal(lt.kl.a, L.kl)
+    rng = np.random.default_rng(0)
+    f = np.float32
+    terrain = (500 * np.exp(-(((np.arange(nx)[:, None] - 12) / 4.0) ** 2 + ((np.arange(ny)[None, :] - 9) / 3.0) ** 2))).astype(f)
+    ft = np.asfortranarray(np.fft.fft2(terrain.astype(np.complex128)) / (nx * ny))
+    ft_np = LW.fftshift2cc(ft.copy())
+    lw.shift.fftshift2cc(ft)
+    assert np.array_equal(ft, ft_np)
+    for (U, V, N2, z) in ((f(10), f(3), f(1e-4), f(800)), (f(-5), f(7), f(3e-5), f(2500)), (f(0), f(0), f(1e-4), f(500))):
+        lw.linear_perturbation_at_height(U, V, N2, z, ft, lt)
+        u, v = LW.linear_perturbation_at_height(U, V, N2, z, ft_np, L)
+        assert np.array_equal(lt.u_perturb.a, u) and np.array_equal(lt.v_perturb.a, v)
+    assert np.abs(u).max() == 0                                      # calm background: no perturbation (:192-196)
+    lw.linear_perturbation_constz(f(10), f(3), f(1e-4), f(400), f(1200), f(100), ft, lt)
+    u, v = LW.linear_perturbation_constz(f(10), f(3), f(1e-4), f(400), f(1200), f(100), ft_np, L)
+    assert np.array_equal(lt.u_perturb.a, u) and np.array_equal(lt.v_perturb.a, v) and np.abs(u).max() > 0.1
+    buffer = 3
+    lw.M.buffer = buffer
+    zb = rng.uniform(300, 500, (nx - 2 * buffer, ny - 2 * buffer)).astype(f)
+    zt = (zb + rng.uniform(150, 400, zb.shape)).astype(f)
+    lw.linear_perturbation_varyingz(f(10), f(3), f(1e-4), np.asfortranarray(zb), np.asfortranarray(zt), f(100), ft, lt)
+    u, v = LW.linear_perturbation_varyingz(f(10), f(3), f(1e-4), zb, zt, f(100), ft_np, L, buffer)
+    assert np.array_equal(lt.u_perturb.a, u) and np.array_equal(lt.v_perturb.a, v)
+    for smooth_window, buf in ((5, 4), (0, 2), (2, 6)):
+        bt = unallocated(np.complex128, 2)
+        lw.add_buffer_topo(np.asfortranarray(terrain), bt, smooth_window, buf, None)
+        want = LW.add_buffer_topo(terrain, smooth_window, buf)
+        # (the smoothing window is a SUM over up to 11 x 11 cells: the Fortran adds them in array order, NumPy pairwise)
+        assert np.abs(bt.a - want).max() <= 1e-15 * np.abs(want).max()
+        if smooth_window == 0:
+            assert np.array_equal(bt.a, want)
