@@ -1,5 +1,5 @@
 # One GPU box: compute-sanitizer over the small-grid paths ("race detection / sanitizers").
-# memcheck on smoke() and on the candidates that have not run on hardware yet, racecheck + initcheck on smoke()
+# memcheck on smoke(), the step-loop kernels and the Thompson instantiations, racecheck + initcheck on smoke()
 # (shared-memory exchange rows / TMA stages of the fused corrector, the column reductions of the mp kernels).
 # Run it BEFORE timing a new kernel: an out-of-bounds store that happens to land in padding passes the parity
 # tests and corrupts a neighbouring field at another size.  ~5 minutes of box time.
@@ -16,8 +16,9 @@ run smoke_mem   memcheck  python -c "import __graft_entry__ as g; g.smoke()"
 run smoke_race  racecheck python -c "import __graft_entry__ as g; g.smoke()"
 run smoke_init  initcheck python -c "import __graft_entry__ as g; g.smoke()"
 run step_loop   memcheck  python -m pytest tests/test_gpu_step_loop.py -m gpu -q -x
-export ICAR_TEST_UNVALIDATED=1
+run thompson    memcheck  python -m pytest tests/test_gpu_thompson.py -m gpu -q -x -k "reference_source or 100_levels or tile_and_optional or clipped"
+run thompson_race racecheck python -m pytest tests/test_gpu_thompson.py -m gpu -q -x -k "reference_source"
+[ -n "$SHORT" ] && { for f in gpurun_out/sanitize_*.log; do tail -n 3 $f; done | tail -n 40; exit 0; }
 run linear_winds memcheck python -m pytest tests/test_gpu_linear_winds.py -m gpu -q -x -k "not full_size"
 run restart      memcheck python -m pytest tests/test_gpu_restart.py -m gpu -q -x
-run candidates   memcheck python -m pytest tests/test_gpu_parity.py -m gpu -q -x -k "candidate or 52_level or packed"
 tail -5 gpurun_out/sanitize_*.log | tail -60
