@@ -57,7 +57,8 @@ FusedPlan fused_plan(const Geom& g) {
     if (g.nz <= 20) { p.cpt = 2; p.nzp = 20; }
     else if (g.nz <= 40) { p.cpt = 2; p.nzp = 40; }
     else if (g.nz <= 48) { p.cpt = 4; p.nzp = 48; }
-    else if (g.nz <= 52) { p.cpt = 4; p.nzp = 52; }
+    else if (g.nz <= 52) { p.cpt = 2; p.nzp = 52; }
+    else if (g.nz <= 56) { p.cpt = 2; p.nzp = 56; }
     else if (g.nz <= 60) { p.cpt = 4; p.nzp = 60; }
     else { p.cpt = 4; p.nzp = 64; p.stages = 1; }
     const int nzt = p.nzp / p.cpt;
@@ -133,7 +134,8 @@ int fused_advect_all(const Geom& g, const ScalarSet& s, const float* U, const fl
     if (plan.nzp == 20) LAUNCH_FUSED(1, 20, 2)
     else if (plan.nzp == 40) LAUNCH_FUSED(1, 40, 2)
     else if (plan.nzp == 48) LAUNCH_FUSED(2, 48, 2)
-    else if (plan.nzp == 52) LAUNCH_FUSED(2, 52, 2)
+    else if (plan.nzp == 52) LAUNCH_FUSED(1, 52, 2)
+    else if (plan.nzp == 56) LAUNCH_FUSED(1, 56, 2)
     else if (plan.nzp == 60) LAUNCH_FUSED(2, 60, 2)
     else LAUNCH_FUSED(2, 64, 1)
 #undef LAUNCH_FUSED
@@ -145,8 +147,8 @@ int fused_advect_all(const Geom& g, const ScalarSet& s, const float* U, const fl
 bool fused_preload() {
     return preload_kernel(k_face_coefficients) && preload_kernel(k_corrector_fused<1, 20, 2>) &&
            preload_kernel(k_corrector_fused<1, 40, 2>) && preload_kernel(k_corrector_fused<2, 48, 2>) &&
-           preload_kernel(k_corrector_fused<2, 52, 2>) && preload_kernel(k_corrector_fused<2, 60, 2>) &&
-           preload_kernel(k_corrector_fused<2, 64, 1>);
+           preload_kernel(k_corrector_fused<1, 52, 2>) && preload_kernel(k_corrector_fused<1, 56, 2>) &&
+           preload_kernel(k_corrector_fused<2, 60, 2>) && preload_kernel(k_corrector_fused<2, 64, 1>);
 }
 
 }  // namespace icar

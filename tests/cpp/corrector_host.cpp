@@ -188,7 +188,8 @@ int emu_corrector(int np, int nzp, int stages, int nx, int nz, int ny, int ld, i
     CASE(1, 20, 2)
     CASE(1, 40, 2)
     CASE(2, 48, 2)
-    CASE(2, 52, 2)
+    CASE(1, 52, 2)
+    CASE(1, 56, 2)
     CASE(2, 60, 2)
     CASE(2, 64, 1)
     CASE(2, 64, 2)          // does not fit: exercises the refusal

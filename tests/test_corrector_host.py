@@ -92,7 +92,7 @@ def check(emu, oracle, dims, np_, nzp, stages, chunk=None):
 
 # (dims, pairs per thread, level slots, TMA stages): every instantiation fused_plan can choose
 INSTANTIATIONS = [((45, 7, 7), 1, 20, 2), ((40, 20, 7), 1, 20, 2), ((40, 33, 6), 1, 40, 2), ((36, 48, 7), 2, 48, 2),
-                  ((40, 50, 7), 2, 52, 2), ((33, 60, 7), 2, 60, 2), ((30, 55, 6), 2, 60, 2), ((33, 62, 6), 2, 64, 1)]
+                  ((40, 50, 7), 1, 52, 2), ((30, 55, 6), 1, 56, 2), ((33, 60, 7), 2, 60, 2), ((33, 62, 6), 2, 64, 1)]
 
 
 @pytest.mark.parametrize("dims,np_,nzp,stages", INSTANTIATIONS)
