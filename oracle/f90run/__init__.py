@@ -229,11 +229,13 @@ class Reference:
 
         def rec(name):
             def f(M, domain, options, mp_dt, *a, **k):
-                log[-1].append((name, float(mp_dt)) + tuple(int(k[n]) for n in ("its", "ite", "jts", "jte", "kts", "kte")) +
-                               ((int(a[0]),) if a else ()))
+                names = ("its", "ite", "jts", "jte", "kts", "kte")
+                b = tuple(int(k[n]) for n in names) if k else tuple(int(x) for x in a[:6])     # keyword or positional call
+                log[-1].append((name, float(mp_dt)) + b)
             return f
         path = os.path.join(os.path.dirname(self.mp_path), "mp_driver.f90")
-        mod = Module(path, overrides={"process_subdomain": rec("process_subdomain"), "process_halo": rec("process_halo"),
+        # process_halo (:609-658) runs as written: its four ring strips arrive at the process_subdomain recorder
+        mod = Module(path, overrides={"process_subdomain": rec("process_subdomain"),
                                       "allocate_module_variables": lambda M, *a: None})
         drv = mod.build(["mp"])
         drv.M.update_interval = f32(update_interval) if isinstance(drv.M.update_interval, np.float32) else int(update_interval)

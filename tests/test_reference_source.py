@@ -349,8 +349,13 @@ def test_live_mp_driver_schedule(ref):
     assert log == [[("process_subdomain", 50.0, 2, 19, 2, 15, 1, 10)], [], [("process_subdomain", 40.0, 2, 19, 2, 15, 1, 10)]]
     # step(): mp(halo=1) then mp(subset=1) at the same model time: the halo call must not advance last_model_time
     log = ref.mp_schedule([(0.0, 30.0, 1, None), (0.0, 30.0, None, 1), (30.0, 30.0, 1, None), (30.0, 30.0, None, 1)], 0, g)
-    assert log == [[("process_halo", 30.0, 2, 19, 2, 15, 1, 10, 1)], [("process_subdomain", 30.0, 3, 18, 3, 14, 1, 10)],
-                   [("process_halo", 30.0, 2, 19, 2, 15, 1, 10, 1)], [("process_subdomain", 30.0, 3, 18, 3, 14, 1, 10)]]
+    # process_halo (:609-658) itself: west and east columns over all rows, then south and north rows without the corners --
+    # the four strips icar_mp queues on its auxiliary stream (icar_b200.cu, `has_halo`)
+    ring = [("process_subdomain", 30.0, 2, 2, 2, 15, 1, 10), ("process_subdomain", 30.0, 19, 19, 2, 15, 1, 10),
+            ("process_subdomain", 30.0, 3, 18, 2, 2, 1, 10), ("process_subdomain", 30.0, 3, 18, 15, 15, 1, 10)]
+    assert log == [ring, [("process_subdomain", 30.0, 3, 18, 3, 14, 1, 10)], ring, [("process_subdomain", 30.0, 3, 18, 3, 14, 1, 10)]]
+    wide = ref.mp_schedule([(0.0, 20.0, 3, None)], 0, g)[0]
+    assert [t[2:6] for t in wide] == [(2, 4, 2, 15), (17, 19, 2, 15), (5, 16, 2, 4), (5, 16, 13, 15)]
 
 
 @needs_reference
