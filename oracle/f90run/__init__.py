@@ -300,6 +300,47 @@ class Reference:
         lw.initialize_linear_theory_data(lt, int(nx), int(ny), f32(dx))
         return lt
 
+    # ---- domain_obj.f90: apply_forcing, enforce_limits (the rest of step()'s loop body)
+    def _domain_module(self):
+        if not hasattr(self, "_dom"):
+            root = os.path.dirname(os.path.dirname(os.path.dirname(self.mp_path)))
+            self._dom = Module(os.path.join(root, "src", "objects", "domain_obj.f90")).build(["apply_forcing", "enforce_limits"])
+        return self._dom
+
+    def apply_forcing(self, variables, w, seconds, west=True, east=True, south=True, north=True):
+        """domain%apply_forcing(dt), domain_obj.f90:2383-2448.  variables: [(data (ny, nz, nx) float32, dqdt, force_boundaries)]
+        in the order of the variables_to_force dictionary; w: (data, dqdt) of this%w%meta_data; updated in place."""
+        ns = types.SimpleNamespace
+        fa = lambda a: FArr(a.T, (1, 1, 1))                    # noqa: E731
+
+        class Dictionary:
+            def __init__(self, items):
+                self.items, self.pos = items, 0
+
+            def reset_iterator(self):
+                self.pos = 0
+
+            def has_more_elements(self):
+                return self.pos < len(self.items)
+
+            def next(self):
+                self.pos += 1
+                return self.items[self.pos - 1]
+        items = [ns(two_d=False, three_d=True, force_boundaries=bool(fb), data_3d=fa(d), dqdt_3d=fa(t), data_2d=None, dqdt_2d=None)
+                 for d, t, fb in variables]
+        this = ns(variables_to_force=Dictionary(items), west_boundary=west, east_boundary=east, south_boundary=south,
+                  north_boundary=north, w=ns(meta_data=ns(data_3d=fa(w[0]), dqdt_3d=fa(w[1]))),
+                  external_precipitation=ns(data_2d=None), accumulated_precipitation=ns(data_2d=None, data_2dd=None))
+        self._domain_module().apply_forcing(this, ns(seconds=lambda: np.float64(seconds)))
+
+    def enforce_limits(self, fields):
+        """domain%enforce_limits(), domain_obj.f90:2228-2243; fields: component name -> (ny, nz, nx) float32 array, in place"""
+        ns = types.SimpleNamespace
+        names = ("water_vapor", "potential_temperature", "cloud_water_mass", "cloud_number", "cloud_ice_mass",
+                 "cloud_ice_number", "rain_mass", "rain_number", "snow_mass", "snow_number", "graupel_mass", "graupel_number")
+        this = ns(**{n: ns(data_3d=FArr(fields[n].T, (1, 1, 1)) if n in fields else None) for n in names})
+        self._domain_module().enforce_limits(this)
+
     def exner_function(self, pressure):
         """exner_function (atm_utilities.f90:682-691), elemental, with Rd and cp of icar_constants.f90"""
         return self.atm.exner_function(np.ascontiguousarray(pressure, np.float32))

@@ -983,7 +983,18 @@ class Module:
             # a type-bound procedure whose implementation is a routine of this module: the object is the first argument
             name, argtext = mb.group(2), mb.group(1) + ("," + mb.group(4) if (mb.group(4) or "").strip() else "")
         elif not m:
-            raise TranslateError("cannot parse call")
+            mm = re.match(r"^call\s+([\w%\s]+?)\s*(\((.*)\))?$", t)
+            if not mm or "%" not in mm.group(1):
+                raise TranslateError("cannot parse call")
+            # a type-bound procedure of an object the harness supplies: a method call on that object
+            p = ExprParser(tokenize(mm.group(1).strip()), scope, self.consts)
+            _, v0 = p.next()
+            code = scope.ref(v0) if (v0 in scope.locals or v0 in self.vars or v0 in scope.aliases) else py_name(v0)
+            while p.accept("op", "%"):
+                code += "." + py_name(p.next()[1])
+            args = [self.expr(a, scope)[0] for a in (split_top(mm.group(3)) if (mm.group(3) or "").strip() else [])]
+            emit(f"{code}({', '.join(args)})")
+            return
         else:
             name, argtext = m.group(1), m.group(3) or ""
         actuals = split_top(argtext) if argtext.strip() else []

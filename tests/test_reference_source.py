@@ -423,3 +423,33 @@ def test_live_linear_winds(ref):
         assert np.abs(bt.a - want).max() <= 1e-15 * np.abs(want).max()
         if smooth_window == 0:
             assert np.array_equal(bt.a, want)
+
+
+@needs_reference
+def test_live_apply_forcing_and_enforce_limits(ref):
+    """domain%apply_forcing (src/objects/domain_obj.f90:2383-2448: `data + dqdt * dt%seconds()` with a REAL*8 seconds, i.e. a
+    REAL*8 product and sum rounded once on assignment; boundary cells only for force_boundaries variables; w everywhere)
+    and domain%enforce_limits (:2228-2243) executed on a mock domain, against the restatements icar_apply_forcing /
+    icar_enforce_limits are tested against"""
+    from oracle import np_restatement as NP
+    rng = np.random.default_rng(0)
+    f = np.float32
+    mk = lambda: rng.uniform(-1, 1, (7, 5, 9)).astype(f)                # noqa: E731
+    q1, t1, q2, t2, w, tw = mk(), mk() * f(1e-3), mk(), mk() * f(1e-3), mk(), mk() * f(1e-3)
+    sec = 37.123456789
+    for edges in (dict(west=True, east=False, south=True, north=True), dict(west=False, east=True, south=False, north=False)):
+        a = [x.copy() for x in (q1, q2, w)]
+        b = [x.copy() for x in (q1, q2, w)]
+        ref.apply_forcing([(b[0], t1, True), (b[1], t2, False)], (b[2], tw), sec, **edges)
+        NP.apply_forcing_np(a[0], t1, sec, True, **edges)
+        NP.apply_forcing_np(a[1], t2, sec, False)
+        NP.apply_forcing_np(a[2], tw, sec, False)
+        for x, y, z in zip(a, b, (q1, q2, w)):
+            assert np.array_equal(x, y) and not np.array_equal(x, z)
+        # a REAL product would differ: the REAL*8 evaluation is what the source text says
+        assert not np.array_equal(b[1], q2 + t2 * f(sec))
+    fields = {"water_vapor": mk(), "rain_mass": mk(), "potential_temperature": mk() + f(300)}
+    c = {k: v.copy() for k, v in fields.items()}
+    ref.enforce_limits(fields)
+    NP.enforce_limits_np(list(c.values()))
+    assert all(np.array_equal(fields[k], c[k]) for k in c) and min(v.min() for v in fields.values()) == 0
