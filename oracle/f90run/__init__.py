@@ -341,6 +341,34 @@ class Reference:
         this = ns(**{n: ns(data_3d=FArr(fields[n].T, (1, 1, 1)) if n in fields else None) for n in names})
         self._domain_module().enforce_limits(this)
 
+    # ---- exchangeable_obj.f90: the halo exchange (coarray PUTs into the neighbours' halo buffers, then copies home)
+    def halo_exchange_x(self, tiles, halo):
+        """exchangeable_t%send then %retrieve (src/objects/exchangeable_obj.f90:138-162, 249-356) for a row of images along
+        x.  tiles: one (ny, nz, nx_local) float32 array per image, ghost columns included, updated in place.  Every image's
+        module variables (halo_size, the neighbour numbers, :4-7) are set before its calls, as each image holds its own."""
+        ns = types.SimpleNamespace
+        root = os.path.dirname(os.path.dirname(os.path.dirname(self.mp_path)))
+        n = len(tiles)
+        objs = {}
+        mod = Module(os.path.join(root, "src", "objects", "exchangeable_obj.f90"), names={"_remote": lambda this, img: objs[int(img)]})
+        ex = mod.build(["send", "retrieve"])
+        for p, a in enumerate(tiles, 1):
+            ny, nz, nxl = a.shape
+            buf = lambda shape: FArr(np.full(shape, np.nan, np.float32, order="F"), (1, 1, 1))     # noqa: E731
+            objs[p] = ns(data_3d=FArr(a.T, (1, 1, 1)), north_boundary=True, south_boundary=True, west_boundary=(p == 1),
+                         east_boundary=(p == n), halo_west_in=buf((halo + 1, nz, ny + 2 * halo)),
+                         halo_east_in=buf((halo + 1, nz, ny + 2 * halo)), halo_north_in=None, halo_south_in=None)
+
+        def as_image(p):
+            ex.M.halo_size, ex.M.west_neighbor, ex.M.east_neighbor = int(halo), p - 1, p + 1
+            ex.M.north_neighbor = ex.M.south_neighbor = 0
+        for p in range(1, n + 1):
+            as_image(p)
+            ex.send(objs[p])
+        for p in range(1, n + 1):                            # after `sync images`: every PUT has landed
+            as_image(p)
+            ex.retrieve(objs[p], None)
+
     def exner_function(self, pressure):
         """exner_function (atm_utilities.f90:682-691), elemental, with Rd and cp of icar_constants.f90"""
         return self.atm.exner_function(np.ascontiguousarray(pressure, np.float32))

@@ -959,6 +959,25 @@ class Module:
         return "whole?", None, None, True, code
 
     def _assign(self, lhs, rhs, scope, emit):
+        co = re.match(r"^(.*\))\s*\[([^\]]+)\]\s*$", lhs.strip())
+        if co:
+            # a coindexed object  x%comp(section)[image] = ... : the same component of ANOTHER image's object, which the
+            # harness hands out through _remote(object, image)  (a coarray PUT)
+            root = re.match(r"^(\w+)", co.group(1)).group(1)
+            img = self.expr(co.group(2), scope)[0]
+            saved = scope.aliases.get(root)
+            scope.aliases[root] = f"_remote({scope.ref(root)}, {img})"
+            try:
+                kind, target, v, whole, obj = self._lvalue(co.group(1), scope)
+            finally:
+                if saved is None:
+                    del scope.aliases[root]
+                else:
+                    scope.aliases[root] = saved
+            if kind != "elem":
+                raise TranslateError("coindexed assignment to a whole array is outside the subset")
+            emit(f"{target} = {self.expr(rhs, scope)[0]}")
+            return
         kind, target, v, whole, obj = self._lvalue(lhs, scope)
         c, _ = self.expr(rhs, scope)
         if kind == "scalar":
@@ -1155,7 +1174,7 @@ class Module:
                 raise TranslateError("exit / cycle of an outer loop")
             emit("break" if t.startswith("exit") else "continue")
             return ind
-        if t == "continue":
+        if t == "continue" or t.startswith("sync "):        # SYNC IMAGES / SYNC ALL: the harness runs the images in turn
             emit("pass")
             return ind
         m = re.match(r"^go\s*to\s+(\d+)$", t)

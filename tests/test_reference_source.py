@@ -453,3 +453,38 @@ def test_live_apply_forcing_and_enforce_limits(ref):
     ref.enforce_limits(fields)
     NP.enforce_limits_np(list(c.values()))
     assert all(np.array_equal(fields[k], c[k]) for k in c) and min(v.min() for v in fields.values()) == 0
+
+
+@needs_reference
+@pytest.mark.parametrize("halo", [1, 3])
+def test_live_halo_exchange(ref, halo):
+    """exchangeable_t%send / %retrieve of src/objects/exchangeable_obj.f90:138-162, 249-356 executed for three images in a
+    row along x (the coarray PUT `halo_west_in(...)[east_neighbor] = data_3d(...)` lands in the neighbour's object): every
+    ghost column ends up holding the neighbour's owned column of the global field, and the columns moved are exactly the
+    ones icar_halo_plan names (what k_halo_push stores into the neighbours' ghost cells)"""
+    import icar_b200
+    nxg, nz, ny, nimg = 37, 4, 6, 3
+    F = np.random.default_rng(0).uniform(0, 1, (ny, nz, nxg)).astype(np.float32)
+    grids = [icar_b200.Grid.xslab(nxg, nz, ny, nimg, p, halo) for p in range(1, nimg + 1)]
+    tiles = [np.ascontiguousarray(F[:, :, g.ims - 1:g.ime]) for g in grids]
+    want = [t.copy() for t in tiles]
+    for g, t in zip(grids, tiles):                         # ghost columns hold rubbish before the exchange
+        if g.ims > 1:
+            t[:, :, :halo] = -1
+        if g.ime < nxg:
+            t[:, :, -halo:] = -1
+    got = [t.copy() for t in tiles]
+    ref.halo_exchange_x(got, halo)
+    for a, b in zip(got, want):
+        assert np.array_equal(a, b)
+    mine = [t.copy() for t in tiles]
+    plans = [icar_b200.halo_plan(g, p, nimg) for p, g in enumerate(grids, 1)]
+    for p, pl in enumerate(plans):
+        w = pl["width"]
+        assert w == halo
+        if pl["has_hi"]:
+            mine[p + 1][:, :, plans[p + 1]["recv_lo"]:plans[p + 1]["recv_lo"] + w] = tiles[p][:, :, pl["send_hi"]:pl["send_hi"] + w]
+        if pl["has_lo"]:
+            mine[p - 1][:, :, plans[p - 1]["recv_hi"]:plans[p - 1]["recv_hi"] + w] = tiles[p][:, :, pl["send_lo"]:pl["send_lo"] + w]
+    for a, b in zip(mine, got):
+        assert np.array_equal(a, b)
