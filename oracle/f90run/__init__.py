@@ -369,6 +369,57 @@ class Reference:
             as_image(p)
             ex.retrieve(objs[p], None)
 
+    # ---- linear_winds.f90: spatial_winds, the routine linear_perturb runs every forcing interval (table look-up per cell)
+    def spatial_winds(self, st, lut_u, lut_v, o, u_pert, v_pert):
+        """spatial_winds(domain, reverse=.False., vsmooth, winsz, update=.False.), linear_winds.f90:840-1127, on a mock domain.
+        st: u (ny, nz, nx+1), v (ny+1, nz, nx), th, pii, z, qv [, qc, qi, qr, qs] (ny, nz, nx), updated in place (u, v).
+        lut_u (n_spd, n_dir, n_nsq, nx+1, nz, ny), lut_v (n_spd, n_dir, n_nsq, nx, nz, ny+1): hi_u_LUT / hi_v_LUT in the
+        Fortran's index order; u_pert (ny, nz, nx+1), v_pert (ny+1, nz, nx): hi_u/v_perturbation, in place.  o: the
+        lt_options (oracle.spatial_winds_np.LTOptions names).  calc_stability / calc_direction / calc_speed come from
+        atm_utilities.f90, calc_weight / smooth_array / linear_space from array_utilities.f90, translated as well.
+        Returns log N^2 -> N^2 as the routine leaves it in domain%nsquared, (ny, nz, nx)."""
+        ns = types.SimpleNamespace
+        root = os.path.dirname(os.path.dirname(os.path.dirname(self.mp_path)))
+        if not hasattr(self, "_sw"):
+            consts = {k: v for k, v in vars(self.constants).items() if isinstance(v, (np.floating, int))}
+            atm = Module(os.path.join(root, "src", "utilities", "atm_utilities.f90"), names=consts).build(
+                ["calc_stability", "calc_direction", "calc_speed", "calc_u", "calc_v"])
+            arr = Module(os.path.join(root, "src", "utilities", "array_utilities.f90")).build(
+                ["calc_weight", "smooth_array_3d", "linear_space"])
+            mod = Module(os.path.join(self.mp_path.rsplit("/", 1)[0], "linear_winds.f90"),
+                         externals={"calc_stability": atm.calc_stability, "calc_direction": atm.calc_direction,
+                                    "calc_speed": atm.calc_speed, "calc_weight": (arr.calc_weight, [2]),
+                                    "smooth_array": arr.smooth_array_3d},
+                         names={"pi": self.constants.pi})
+            self._sw = (mod.build(["spatial_winds"]), atm, arr)
+        sw, atm, arr = self._sw
+        ny, nz, nxu = st["u"].shape
+        nx, nyv = nxu - 1, ny + 1
+        fa = lambda a: FArr(a.T, (1,) * a.ndim)                # noqa: E731
+        var = lambda a: ns(data_3d=fa(a) if a is not None else None)    # noqa: E731
+        nsq = np.zeros((ny, nz, nx), np.float32)
+        dom = ns(u=ns(data_3d=fa(st["u"]), meta_data=ns(dqdt_3d=None)), v=ns(data_3d=fa(st["v"]), meta_data=ns(dqdt_3d=None)),
+                 nsquared=var(nsq), latitude=ns(data_2d=FArr(np.zeros((nx, ny), np.float32, order="F"), (1, 1))),
+                 cloud_water_mass=var(st.get("qc")), cloud_ice_mass=var(st.get("qi")), rain_mass=var(st.get("qr")),
+                 snow_mass=var(st.get("qs")), potential_temperature=var(st["th"]), exner=var(st["pii"]), z=var(st["z"]),
+                 water_vapor=var(st["qv"]))
+        M = sw.M
+        M.variable_n, M.smooth_nsq = bool(o.variable_N), bool(o.smooth_nsq)
+        M.n_squared, M.min_stability, M.max_stability = f32(o.N_squared), f32(o.min_stability), f32(o.max_stability)
+        M.linear_update_fraction, M.linear_contribution = f32(o.linear_update_fraction), f32(o.linear_contribution)
+        M.n_dir_values, M.n_nsq_values, M.n_spd_values = int(o.n_dir_values), int(o.n_nsq_values), int(o.n_spd_values)
+        for name, lo, hi, n in (("dir_values", o.dirmin, o.dirmax, o.n_dir_values), ("nsq_values", o.nsqmin, o.nsqmax, o.n_nsq_values),
+                                ("spd_values", o.spdmin, o.spdmax, o.n_spd_values)):
+            axis = FArr(None, (1,), np.float32, True)                   # an unallocated allocatable, as at :656-660
+            arr.linear_space(axis, f32(lo), f32(hi), int(n))
+            setattr(M, name, axis)
+        M.hi_u_lut = FArr(np.asfortranarray(lut_u), (1,) * 6)
+        M.hi_v_lut = FArr(np.asfortranarray(lut_v), (1,) * 6)
+        M.hi_u_perturbation, M.hi_v_perturbation = fa(u_pert), fa(v_pert)
+        M.lo_u_perturbation = M.lo_v_perturbation = None
+        sw.spatial_winds(dom, False, int(o.vert_smooth), int(o.stability_window_size), False)
+        return nsq
+
     def exner_function(self, pressure):
         """exner_function (atm_utilities.f90:682-691), elemental, with Rd and cp of icar_constants.f90"""
         return self.atm.exner_function(np.ascontiguousarray(pressure, np.float32))

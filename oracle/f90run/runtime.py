@@ -16,7 +16,7 @@ import math
 import numpy as np
 
 _libm = ctypes.CDLL(ctypes.util.find_library("m") or "libm.so.6")
-for _n in ("expf", "logf", "log10f", "sqrtf"):
+for _n in ("expf", "logf", "log10f", "sqrtf", "atanf", "tanhf", "sinf", "cosf"):
     getattr(_libm, _n).argtypes = [ctypes.c_float]
     getattr(_libm, _n).restype = ctypes.c_float
 _libm.powf.argtypes = [ctypes.c_float, ctypes.c_float]
@@ -384,12 +384,10 @@ def arr(items, dtype):
     return np.array([A(x) for x in items], dtype=dtype, order="F")
 
 
-def f_tanh(x):
-    return np.float32(math.tanh(float(x))) if type(x) is np.float32 else np.float64(math.tanh(float(x)))
-
-
-def f_atan(x):
-    return np.float32(math.atan(float(x))) if type(x) is np.float32 else np.float64(math.atan(float(x)))
+f_tanh = _unary_libm("tanhf", "tanh")
+f_atan = _unary_libm("atanf", "atan")
+f_sin = _unary_libm("sinf", "sin")
+f_cos = _unary_libm("cosf", "cos")
 
 
 def _as_double(fn):
@@ -425,5 +423,5 @@ NAMES = {
     "_fn_conjg": lambda z: np.conj(A(z)),
     "_arr": arr, "_fn_lbound": f_lbound, "_fn_ubound": f_ubound, "_fn_dmax1": f_max, "_fn_dmin1": f_min, "_fn_dlog": _as_double(math.log), "_fn_dlog10": _as_double(math.log10),
     "_fn_dexp": _as_double(math.exp), "_fn_dsqrt": _as_double(math.sqrt), "_fn_dabs": f_abs, "_fn_dfloat": f_dble,
-    "_fn_sngl": f_real, "_fn_tanh": f_tanh, "_fn_atan": f_atan, "_fn_iabs": f_abs, "_fn_trim": lambda x: x,
+    "_fn_sngl": f_real, "_fn_tanh": f_tanh, "_fn_atan": f_atan, "_fn_sin": f_sin, "_fn_cos": f_cos, "_fn_iabs": f_abs, "_fn_trim": lambda x: x,
 }

@@ -535,6 +535,8 @@ class ExprParser:
                 if not r.is_function:
                     raise TranslateError(f"subroutine {name} used as a function")
                 self.scope.module.need(name)
+                if r.out_positions():
+                    raise TranslateError(f"function {name} sets scalar arguments: only `x = {name}(...)` is in the subset")
                 kws = [(x[3], x[1]) for x in a if x[0] == "kw"]
                 for kw, _ in kws:
                     if kw not in r.args:
@@ -544,6 +546,8 @@ class ExprParser:
             if any(x[0] == "kw" for x in a):
                 raise TranslateError(f"{name}: keyword arguments of intrinsics are outside the subset")
             if self.scope.module.externals.get(name) is not None:       # a function of another module (harness-supplied)
+                if isinstance(self.scope.module.externals[name], tuple):
+                    raise TranslateError(f"function {name} sets scalar arguments: only `x = {name}(...)` is in the subset")
                 return f"_X_{name}({argc})", "?"
             if name in INTRINSICS:
                 if name in INT_RESULT:
@@ -645,6 +649,8 @@ def parse_declaration(stmt):
             raise TranslateError(f"declaration attribute {a!r} outside the subset: {stmt}")
     ents = []
     for e in split_top(right.strip()):
+        if "=" not in e:                                          # a codimension [*] / [:]: the local part is an ordinary array
+            e = re.sub(r"\[[^\]]*\]\s*$", "", e.strip())
         init = None
         m = re.match(r"^(\w+)\s*(\((.*?)\))?\s*(?:\*\s*\d+)?\s*(=\s*(.*))?$", e)
         if not m:
@@ -907,7 +913,11 @@ class Module:
 
     def _return(self, r):
         if r.is_function:
-            return f"return {self.convert(py_name(r.result), r.result_kind)}"
+            res = self.convert(py_name(r.result), r.result_kind)
+            outs = r.out_positions()
+            if outs:        # a function that also sets scalar arguments: (result, those arguments); see _function_with_outs
+                return "return (" + res + ", " + ", ".join(py_name(r.args[n]) for n in outs) + ",)"
+            return f"return {res}"
         outs = r.out_positions()
         if not outs:
             return "return ()"
@@ -995,6 +1005,37 @@ class Module:
                 emit(f"if isinstance({obj}, _FArr): {obj}.assign(_t)")
             emit(f"else: {obj} = _t")
 
+    def _function_with_outs(self, lhs, rhs, scope, emit):
+        """`x = f(a, b, c)` where f also sets some of its scalar arguments (intent(inout) / (out)): result and arguments
+        come back together and are copied into the actual arguments.  Returns False if rhs is not such a call."""
+        m = re.match(r"^\s*(\w+)\s*\((.*)\)\s*$", rhs)
+        if not m:
+            return False
+        name = m.group(1)
+        if name in self.routines and self.routines[name].is_function and name not in scope.locals:
+            outs, fn = self.routines[name].out_positions(), f"_F_{name}"
+            if outs:
+                self.need(name)
+        elif isinstance(self.externals.get(name), tuple):
+            outs, fn = list(self.externals[name][1]), f"_X_{name}"
+        else:
+            return False
+        if not outs:
+            return False
+        actuals = split_top(m.group(2))
+        emit(f"_ret = {fn}({', '.join(self.expr(a, scope)[0] for a in actuals)})")
+        kind, target, v, whole, obj = self._lvalue(lhs, scope)
+        if kind == "scalar":
+            emit(f"{target} = {self.convert('_ret[0]', v.kind)}")
+        elif kind == "elem":
+            emit(f"{target} = _ret[0]")
+        else:
+            raise TranslateError("array-valued function with scalar out arguments")
+        for k, pos in enumerate(outs, 1):
+            kind, target, v, whole, obj = self._lvalue(actuals[pos], scope)
+            emit(f"{target} = {self.convert(f'_ret[{k}]', v.kind) if kind == 'scalar' else f'_ret[{k}]'}")
+        return True
+
     def _call(self, t, scope, emit):
         m = re.match(r"^call\s+(\w+)\s*(\((.*)\))?$", t)
         mb = re.match(r"^call\s+(\w+)\s*%\s*(\w+)\s*(\((.*)\))?$", t)
@@ -1061,7 +1102,7 @@ class Module:
             if self.externals[name] is None:
                 emit("pass")                      # declared a no-op by the harness (logging)
             else:
-                emit(f"_X_{name}({', '.join(codes)})")
+                emit(f"_X_{name}({', '.join(codes + [py_name(k) + '=' + c for k, c in kwargs])})")
             return
         raise TranslateError(f"call to {name!r}: not a routine of this module")
 
@@ -1278,12 +1319,19 @@ class Module:
                     lhs, rhs = t[:k].strip(), t[k + 2:].strip()
                     kind, target, v, whole, obj = self._lvalue(lhs, scope)
                     rv = scope.lookup(rhs)
-                    if not (whole and rv is not None and rv.is_array):
-                        raise TranslateError("pointer assignment other than `pointer => whole array`")
-                    emit(f"{obj} = {scope.ref(rhs)}")
-                    return ind
+                    if whole and rv is not None and rv.is_array:
+                        emit(f"{obj} = {scope.ref(rhs)}")
+                        return ind
+                    if whole and re.fullmatch(r"[\w%\s]+", rhs) and "%" in rhs:
+                        # pointer => a whole array component of an object of the harness: the array object itself
+                        _, _, _, rwhole, robj = self._lvalue(rhs, scope)
+                        emit(f"{obj} = {robj}")
+                        return ind
+                    raise TranslateError("pointer assignment other than `pointer => whole array`")
                 if t[k:k + 2] == "==" or (k > 0 and t[k - 1] in "<>/="):
                     continue
+                if self._function_with_outs(t[:k], t[k + 1:], scope, emit):
+                    return ind
                 self._assign(t[:k], t[k + 1:], scope, emit)
                 return ind
         raise TranslateError("statement outside the subset")
@@ -1337,7 +1385,7 @@ class Module:
         ns["_C"] = consts
         ns["_M"] = types.SimpleNamespace()
         for xn, fn in self.externals.items():
-            ns["_X_" + xn] = fn
+            ns["_X_" + xn] = fn[0] if isinstance(fn, tuple) else fn
         for nn, val in self.names.items():
             ns[py_name(nn)] = val
         for on, fn in self.overrides.items():

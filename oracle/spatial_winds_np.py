@@ -8,8 +8,12 @@ The table entries are what initialize_spatial_winds (:596-830) computes -- linea
 keyed by node and level) instead of being tabulated in full: the full table is 720 x nx x nz x ny x 2 REALs with
 the namelist defaults (options_obj.f90:1469-1477).  The values are the same.
 
-PARITY UNPINNED for this routine (no expected values in the reference, Fortran not compilable here); the entries
-rest on oracle/linear_winds_np.py, whose per-height solution is pinned.
+PARITY: pinned to the reference's own source.  oracle/f90run executes spatial_winds itself (with calc_stability,
+calc_direction, calc_speed, calc_weight, smooth_array, linear_space of atm_utilities.f90 / array_utilities.f90) on a mock
+domain; given the same look-up table this file's spatial_winds returns the same u, v and stored perturbations in every
+bit (tests/test_reference_source.py::test_live_spatial_winds; REAL log / exp / atan / sin / cos are glibc's, like the
+compiled Fortran's).  The table ENTRIES rest on oracle/linear_winds_np.py, which equals the executed
+linear_perturbation routines; the loop of initialize_spatial_winds that fills the table (coarray puts) is not executed.
 
 Also restated: calc_stability / calc_dry_stability / calc_moist_stability / calc_sat_lapse_rate / calc_direction /
 calc_speed / calc_u / calc_v (src/utilities/atm_utilities.f90:334-467), calc_weight / linear_space / smooth_array_3d
@@ -23,6 +27,30 @@ from oracle import linear_winds_np as LW
 f = np.float32
 PI = f(3.1415927)
 GRAVITY, RD, RW, CP, LH_VAP = f(9.81), f(287.058), f(461.5), f(1012.0), f(2260000.0)
+
+
+def _libm1(name):
+    """A REAL elemental intrinsic as the compiled Fortran evaluates it: glibc's single-precision function, element by element
+    (NumPy's own vectorised float32 log / exp / arctan differ from glibc's in the last bit now and then)."""
+    import ctypes
+    import ctypes.util
+    fn = getattr(ctypes.CDLL(ctypes.util.find_library("m") or "libm.so.6"), name)
+    fn.argtypes, fn.restype = [ctypes.c_float], ctypes.c_float
+
+    def apply(x):
+        a = np.asarray(x, f)
+        if a.ndim == 0:
+            return f(fn(float(a)))
+        a = np.ascontiguousarray(a)
+        out = np.empty_like(a)
+        fo, fx = out.reshape(-1), a.reshape(-1)
+        for n in range(fx.size):
+            fo[n] = fn(float(fx[n]))
+        return out
+    return apply
+
+
+logf, expf, atanf, sinf, cosf = (_libm1(n) for n in ("logf", "expf", "atanf", "sinf", "cosf"))
 
 
 class LTOptions:
@@ -47,8 +75,8 @@ class LTOptions:
             if not hasattr(self, k):
                 raise TypeError(k)
             setattr(self, k, v)
-        self.nsqmax = np.log(f(self.max_stability)).astype(f)      # log(max_stability), REAL
-        self.nsqmin = np.log(f(self.min_stability)).astype(f)
+        self.nsqmax = logf(f(self.max_stability))                  # log(max_stability), REAL
+        self.nsqmin = logf(f(self.min_stability))
 
 
 def linear_space(lo, hi, n):
@@ -67,7 +95,7 @@ def calc_direction(u, v):
     """atm_utilities.f90:334-355 on arrays."""
     u, v = np.asarray(u, f), np.asarray(v, f)
     with np.errstate(divide="ignore", invalid="ignore"):
-        a = np.arctan(u / v).astype(f)
+        a = atanf((u / v).astype(f))
     out = np.where(v < 0, a + PI, np.where(u >= 0, a, a + f(2) * PI)).astype(f)
     zero = v == 0
     out = np.where(zero & (u > 0), PI / f(2), out)
@@ -81,7 +109,7 @@ def calc_speed(u, v):
 
 def calc_stability(th_top, th_bot, pii_top, pii_bot, z_top, z_bot, qv_top, qv_bot, qc):
     """atm_utilities.f90:448-467 with that module's variable_N = .True. (the branch spatial_winds reaches)."""
-    dry = (GRAVITY * (np.log(th_top) - np.log(th_bot)).astype(f) / (z_top - z_bot)).astype(f)
+    dry = (GRAVITY * (logf(th_top) - logf(th_bot)).astype(f) / (z_top - z_bot)).astype(f)
     t_top, t_bot = (th_top * pii_top).astype(f), (th_bot * pii_bot).astype(f)
     t = ((t_top + t_bot) / f(2)).astype(f)
     qv = ((qv_top + qv_bot) / f(2)).astype(f)
@@ -129,7 +157,7 @@ def nsquared_field(st, o):
             val = np.maximum(o.min_stability, np.minimum(o.max_stability, val)).astype(f)
         else:
             val = np.full((ny, nx), o.N_squared, f)
-        nsq[:, j - 1] = np.log(val).astype(f)
+        nsq[:, j - 1] = logf(val)
     if o.smooth_nsq:
         for j in range(1, nz + 1):                                       # in place: levels below j are already smoothed
             top = min(j + vs, nz)
@@ -178,9 +206,9 @@ class EntryCache:
     def get(self, spd, dr, nsq, z):
         key = (int(spd), int(dr), int(nsq), int(z))
         if key not in self.store:
-            U = (np.sin(self.dirs[dr]) * self.spds[spd]).astype(f)      # calc_u / calc_v (atm_utilities.f90:373-391)
-            V = (np.cos(self.dirs[dr]) * self.spds[spd]).astype(f)
-            N2 = np.exp(self.nsqs[nsq]).astype(f)
+            U = (sinf(self.dirs[dr]) * self.spds[spd]).astype(f)      # calc_u / calc_v (atm_utilities.f90:373-391)
+            V = (cosf(self.dirs[dr]) * self.spds[spd]).astype(f)
+            N2 = expf(self.nsqs[nsq])
             zb, zt = self.bounds(z)
             if np.ndim(zb) == 0:
                 p = LW.linear_perturbation_constz(U, V, N2, zb, zt, self.o.minimum_layer_size, self.tf, self.lt)

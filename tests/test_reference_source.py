@@ -488,3 +488,47 @@ def test_live_halo_exchange(ref, halo):
             mine[p - 1][:, :, plans[p - 1]["recv_hi"]:plans[p - 1]["recv_hi"] + w] = tiles[p][:, :, pl["send_lo"]:pl["send_lo"] + w]
     for a, b in zip(mine, got):
         assert np.array_equal(a, b)
+
+
+@needs_reference
+@pytest.mark.parametrize("smooth", [False, True])
+def test_live_spatial_winds(ref, smooth):
+    """spatial_winds of src/physics/linear_winds.f90:840-1127 executed on a mock domain, with calc_stability / calc_direction
+    / calc_speed of atm_utilities.f90 and calc_weight / smooth_array / linear_space of array_utilities.f90 executed as
+    well: per-cell stability and its two smoothings, column-mean wind, table positions and weights, the trilinear
+    interpolation between eight table entries, the relaxation -- against oracle/spatial_winds_np.py (the restatement
+    icar_linear_perturb_spatial is tested against) with a RANDOM look-up table handed to both: u, v and the stored
+    perturbations equal in every bit.  (What initialize_spatial_winds puts INTO the table -- linear_perturbation for the
+    node's wind and stability, staggered -- is covered by test_live_linear_winds, the loop around it is not executed.)"""
+    from oracle import spatial_winds_np as SW
+    nx, nz, ny = 9, 6, 7
+    st0 = ideal.make_ideal_case(nx=nx, nz=nz, ny=ny, terrain=True, perturb=True)
+    rng = np.random.default_rng(1)
+    f = np.float32
+    st0["u"] = (st0["u"] + rng.uniform(-6, 6, st0["u"].shape)).astype(f)
+    st0["v"] = (st0["v"] + rng.uniform(-6, 6, st0["v"].shape)).astype(f)
+    st0["qc"] = rng.uniform(0, 2e-7, st0["qv"].shape).astype(f)          # both branches of calc_stability (qc < 1e-7)
+    o = SW.LTOptions()
+    o.smooth_nsq, o.vert_smooth, o.stability_window_size, o.linear_update_fraction = smooth, 2, 2, f(0.6)
+    lut_u = rng.uniform(-3, 3, (o.n_spd_values, o.n_dir_values, o.n_nsq_values, nx + 1, nz, ny)).astype(f)
+    lut_v = rng.uniform(-3, 3, (o.n_spd_values, o.n_dir_values, o.n_nsq_values, nx, nz, ny + 1)).astype(f)
+
+    class Table:
+        dirs, nsqs, spds = SW.table_axes(o)
+
+        def get(self, s, d, n, z):
+            return np.ascontiguousarray(lut_u[s, d, n, :, z, :].T), np.ascontiguousarray(lut_v[s, d, n, :, z, :].T)
+    copy = lambda st: {k: (v.copy() if isinstance(v, np.ndarray) else v) for k, v in st.items()}      # noqa: E731
+    a, b = copy(st0), copy(st0)
+    up_a = rng.uniform(-1, 1, a["u"].shape).astype(f)
+    vp_a = rng.uniform(-1, 1, a["v"].shape).astype(f)
+    up_b, vp_b = up_a.copy(), vp_a.copy()
+    lognsq = SW.spatial_winds(a, Table(), o, up_a, vp_a)
+    nsq = ref.spatial_winds(b, lut_u, lut_v, o, up_b, vp_b)
+    assert np.array_equal(a["u"], b["u"]) and np.array_equal(a["v"], b["v"])
+    assert np.array_equal(up_a, up_b) and np.array_equal(vp_a, vp_b)
+    assert np.array_equal(SW.expf(lognsq), nsq)                          # the routine leaves exp(log N^2) in domain%nsquared
+    assert np.abs(b["u"] - st0["u"]).max() > 1.0
+    M = ref._sw[0].M
+    assert np.array_equal(M.dir_values.a, Table.dirs) and np.array_equal(M.nsq_values.a, Table.nsqs) and \
+        np.array_equal(M.spd_values.a, Table.spds)                       # linear_space (array_utilities.f90:233-235)
