@@ -1,6 +1,6 @@
 """Linear-theory winds on the device (icar_linear_winds_init / icar_linear_perturbation / icar_linear_perturb;
-SURVEY.md section 8f rank 3) against the NumPy restatement oracle/linear_winds_np.py.  PARITY UNPINNED (the
-reference holds no expected values for this path and cannot be compiled here).
+SURVEY.md section 8f rank 3) against the NumPy restatement oracle/linear_winds_np.py, which equals the reference's
+own linear_winds.f90 executed by oracle/f90run (tests/test_reference_source.py::test_live_linear_winds, ::test_live_spatial_winds).
 
 Tolerance: 1e-6 of the field maximum (BASELINE north_star).  The arithmetic is complex double on both sides; what
 differs is cuFFT against pocketfft (1e-15), the division formula (see tests/test_linear_winds_host.py) and, rarely,

@@ -1,6 +1,7 @@
 """oracle/linear_winds_np.py (linear-theory wind perturbation) on the CPU.
-PARITY UNPINNED (no expected values in the reference): these tests check the restatement against the
-conventions it must reproduce and against the analytic hydrostatic mountain-wave solution."""
+The restatement equals the reference's own linear_winds.f90 executed by oracle/f90run (tests/test_reference_source.py);
+these tests check it against the conventions it must reproduce, against the analytic hydrostatic mountain-wave
+solution and against the reference's Python solver (no expected values exist in the reference)."""
 import numpy as np
 import pytest
 
