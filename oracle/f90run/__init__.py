@@ -420,6 +420,70 @@ class Reference:
         sw.spatial_winds(dom, False, int(o.vert_smooth), int(o.stability_window_size), False)
         return nsq
 
+    def spatial_winds_table(self, terrain_xy, dx, o, z_interface=None, dz_interface=None, layer_height=None, dz_levels=None):
+        """initialize_spatial_winds (linear_winds.f90:596-838) on ONE image: the whole look-up table hi_u_LUT / hi_v_LUT
+        (n_spd, n_dir, n_nsq, nx+1 | nx, nz, ny | ny+1) filled by the routine's own loop -- the ijk -> (direction, stability,
+        speed) mapping, calc_u / calc_v, exp(nsq), the layer bounds (terrain-following from z_interface / dz_interface
+        (nx, nz, ny), or constant from layer_height / dz_levels), linear_perturbation, the staggering, copy_data_to_remote.
+        Replaced by the harness: setup_remote_grids (one image owns the whole domain; the grid algebra has its own test),
+        the file-name string and LUT file I/O (not taken), FFTW (numpy.fft).  terrain_xy (nx, ny); the terrain frequency is
+        the buffered, transformed terrain of setup_linwinds (:1201-1222), taken from the restatement that equals it."""
+        from oracle import linear_winds_np as LW
+        ns = types.SimpleNamespace
+        root = os.path.dirname(os.path.dirname(os.path.dirname(self.mp_path)))
+        consts = {k: v for k, v in vars(self.constants).items() if isinstance(v, (np.floating, int))}
+        atm = Module(os.path.join(root, "src", "utilities", "atm_utilities.f90"), names=consts).build(["calc_u", "calc_v"])
+        arr = Module(os.path.join(root, "src", "utilities", "array_utilities.f90")).build(["linear_space"])
+        shift = Module(os.path.join(root, "src", "utilities", "fftshift.f90")).build(["ifftshift2cc"])
+        nx, ny = terrain_xy.shape
+        varying = z_interface is not None
+        nz = z_interface.shape[1] if varying else len(dz_levels)
+        built = {}
+
+        def execute_dft(plan, src, dst):
+            a = np.asarray(src)
+            dst[...] = np.fft.ifft2(a) * a.size
+
+        def grids(M, u_grids, v_grids, terrain, nz_):
+            u_grids[1] = ns(nx=nx + 1, ny=ny, ims=1, ime=nx + 1, jms=1, jme=ny)
+            v_grids[1] = ns(nx=nx, ny=ny + 1, ims=1, ime=nx, jms=1, jme=ny + 1)
+
+        def perturbation(M, U, V, Nsq, zb, zt, step, ft, lt):           # the generic interface :71-74: by the rank of the bounds
+            fn = built["ns"].linear_perturbation_varyingz if np.ndim(zb) else built["ns"].linear_perturbation_constz
+            fn(U, V, Nsq, np.asfortranarray(zb) if np.ndim(zb) else zb, np.asfortranarray(zt) if np.ndim(zt) else zt, step, ft, lt)
+        lut = {}
+        mod = Module(os.path.join(self.mp_path.rsplit("/", 1)[0], "linear_winds.f90"),
+                     externals={"calc_u": atm.calc_u, "calc_v": atm.calc_v, "linear_space": arr.linear_space,
+                                "read_lut": lambda *a: 1, "write_lut": lambda *a: 0, "ifftshift": shift.ifftshift2cc,
+                                "fftw_execute_dft": execute_dft, "fftw_alloc_complex": lambda n: np.zeros(int(n), np.complex128),
+                                "fftw_plan_dft_2d": lambda *a: "backward"},
+                     overrides={"setup_remote_grids": grids, "linear_perturbation": perturbation,
+                                "destroy_linear_theory_data": lambda M, *a: None},
+                     names={"pi": self.constants.pi, "fftw_backward": 1, "fftw_measure": 0,
+                            "_remote": lambda table, img: table, "_fn_num_images": lambda: 1, "_fn_this_image": lambda: 1},
+                     patches={"initialize_spatial_winds": [(r"^lut_file\s*=", 'lut_file = "unused"')]})
+        mod.component_dtype = {k: "_np.complex128" for k in ("denom", "m", "msq", "mimag", "ineta")}
+        built["ns"] = sw = mod.build(["initialize_spatial_winds", "linear_perturbation_constz", "linear_perturbation_varyingz",
+                                      "initialize_linear_theory_data", "copy_data_to_remote"])
+        tf, total = LW.terrain_frequency(terrain_xy, o.buffer)
+        M = sw.M
+        M.buffer, M.lt_data_m = int(total), ns()
+        M.n_dir_values, M.n_nsq_values, M.n_spd_values = int(o.n_dir_values), int(o.n_nsq_values), int(o.n_spd_values)
+        M.dirmin, M.dirmax, M.nsqmin, M.nsqmax = f32(o.dirmin), f32(o.dirmax), f32(o.nsqmin), f32(o.nsqmax)
+        M.spdmin, M.spdmax, M.minimum_layer_size = f32(o.spdmin), f32(o.spdmax), f32(o.minimum_layer_size)
+        f3 = lambda a: FArr(np.asfortranarray(a, np.float32), (1,) * np.ndim(a))            # noqa: E731
+        dom = ns(z=ns(data_3d=f3(np.zeros((nx, nz, ny), np.float32) if layer_height is None else
+                                  np.broadcast_to((np.asarray(layer_height, np.float32))[None, :, None], (nx, nz, ny)).copy())),
+                 u=ns(data_3d=f3(np.zeros((nx + 1, nz, ny), np.float32))), global_terrain=f3(terrain_xy),
+                 terrain=ns(data_2d=f3(np.zeros((nx, ny), np.float32))), terrain_frequency=FArr(np.asfortranarray(tf), (1, 1)),
+                 dx=f32(dx), global_z_interface=f3(z_interface) if varying else None,
+                 global_dz_interface=f3(dz_interface) if varying else None)
+        opts = ns(lt_options=ns(u_lut_filename="", read_lut=False, write_lut=False),
+                  parameters=ns(space_varying_dz=bool(varying), interactive=False,
+                                dz_levels=FArr(np.asarray(dz_levels if dz_levels is not None else np.zeros(nz), np.float32), (1,))))
+        sw.initialize_spatial_winds(dom, opts, False)
+        return M.hi_u_lut.a, M.hi_v_lut.a
+
     def exner_function(self, pressure):
         """exner_function (atm_utilities.f90:682-691), elemental, with Rd and cp of icar_constants.f90"""
         return self.atm.exner_function(np.ascontiguousarray(pressure, np.float32))

@@ -380,6 +380,23 @@ def f_merge(t, f, mask):
     return np.where(mask, t, f) if isinstance(mask, np.ndarray) else (t if mask else f)
 
 
+class Obj:
+    """a local variable of derived type: components appear when they are assigned"""
+
+
+class ObjArray(dict):
+    """a local array of derived type, 1-based: a(i) is an Obj, a%comp the array of that component over the elements"""
+
+    def __missing__(self, key):
+        self[key] = Obj()
+        return self[key]
+
+    def __getattr__(self, name):
+        if name.startswith("__"):
+            raise AttributeError(name)
+        return np.array([getattr(self[k], name) for k in sorted(self)])
+
+
 def arr(items, dtype):
     return np.array([A(x) for x in items], dtype=dtype, order="F")
 
@@ -421,6 +438,7 @@ NAMES = {
     "_c64": c64, "_c128": c128, "_where_assign": where_assign, "_alloc_like": alloc_like, "_c_f_pointer": c_f_pointer,
     "_fn_cmplx": lambda a, b=0, kind=None: np.complex64(complex(a, b)), "_fn_aimag": lambda z: A(z).imag,
     "_fn_conjg": lambda z: np.conj(A(z)),
+    "_Obj": Obj, "_ObjArray": ObjArray, "_fn_product": lambda x: int(np.prod(A(x))), "_fn_shape": lambda x: np.array(A(x).shape),
     "_arr": arr, "_fn_lbound": f_lbound, "_fn_ubound": f_ubound, "_fn_dmax1": f_max, "_fn_dmin1": f_min, "_fn_dlog": _as_double(math.log), "_fn_dlog10": _as_double(math.log10),
     "_fn_dexp": _as_double(math.exp), "_fn_dsqrt": _as_double(math.sqrt), "_fn_dabs": f_abs, "_fn_dfloat": f_dble,
     "_fn_sngl": f_real, "_fn_tanh": f_tanh, "_fn_atan": f_atan, "_fn_sin": f_sin, "_fn_cos": f_cos, "_fn_iabs": f_abs, "_fn_trim": lambda x: x,

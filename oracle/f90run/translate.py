@@ -188,7 +188,7 @@ def tokenize(s):
 REL = {"==": "==", "/=": "!=", "<": "<", "<=": "<=", ">": ">", ">=": ">=",
        ".eq.": "==", ".ne.": "!=", ".lt.": "<", ".le.": "<=", ".gt.": ">", ".ge.": ">="}
 
-INTRINSICS = {"cmplx", "aimag", "conjg", "lbound", "ubound", "abs", "max", "min", "amax1", "amin1", "dmax1", "dmin1", "maxval", "minval", "sum", "size", "exp", "log",
+INTRINSICS = {"product", "shape", "cmplx", "aimag", "conjg", "lbound", "ubound", "abs", "max", "min", "amax1", "amin1", "dmax1", "dmin1", "maxval", "minval", "sum", "size", "exp", "log",
               "alog", "log10", "alog10", "sqrt", "ceiling", "floor", "nint", "int", "real", "float", "dble", "mod", "sign",
               "merge", "this_image", "num_images", "allocated", "associated", "present", "dlog", "dlog10", "dexp", "dsqrt",
               "dabs", "dfloat", "sngl", "tanh", "atan", "sin", "cos", "iabs", "trim", "gamma"}
@@ -512,7 +512,16 @@ class ExprParser:
             self.next()
             if var is not None and var.is_array:
                 a = self.args()
-                return f"{self.scope.ref(name)}[{self.subscript(a)}]", var.kind
+                code = f"{self.scope.ref(name)}[{self.subscript(a)}]"
+                if var.derived and self.peek() == ("op", "%"):
+                    while self.accept("op", "%"):
+                        code += "." + py_name(self.next()[1])
+                        if self.peek() == ("op", "("):
+                            self.next()
+                            aa = self.args()
+                            code += "()" if not aa else f"[{self.subscript(aa)}]"
+                    return f"_A({code})", "?"
+                return code, var.kind
             if var is not None and not var.is_array and self.scope.routine and name == self.scope.routine.result:
                 pass        # fall through: a recursive call is outside the subset, handled as a function below
             if name in ("lbound", "ubound", "size") and self.peek()[0] == "name" and \
@@ -570,6 +579,8 @@ class ExprParser:
                 raise TranslateError(f"intrinsic {name} without arguments")
             raise TranslateError(f"undeclared name {name!r} in {self.scope.routine.name if self.scope.routine else 'module'}")
         if var.is_array:
+            if var.derived:
+                return self.scope.ref(name), "?"                # an array of objects is its own container
             return f"{self.scope.ref(name)}.a", var.kind
         if var.parameter:
             self.constant.add(self.scope.ref(name))
@@ -837,6 +848,8 @@ class Module:
             v = r.decls[vn]
             pn = py_name(vn)
             if v.derived:
+                if not v.dummy:          # a local object / array of objects: components are created by assignment
+                    emit(f"{pn} = {'_ObjArray()' if v.is_array else '_Obj()'}")
                 continue
             if v.kind == "c":
                 if not v.dummy:
@@ -1068,6 +1081,11 @@ class Module:
                 kwargs.append((mk.group(1), self.expr(mk.group(2), scope)[0]))
                 actuals.remove(a)
         codes = [self.expr(a, scope)[0] for a in actuals]
+        if name in self.overrides or name in self.externals:
+            for n, a in enumerate(actuals):
+                v = scope.lookup(a.strip()) if re.fullmatch(r"\w+", a.strip()) else None
+                if v is not None and v.is_array and v.allocatable and not v.derived:
+                    codes[n] = scope.ref(a.strip())          # an allocatable array goes as the array OBJECT (it may be allocated there)
         if name in self.overrides:
             emit(f"_O_{name}({', '.join(['_M'] + codes + [py_name(k) + '=' + c for k, c in kwargs])})")
             return
@@ -1270,6 +1288,7 @@ class Module:
             if items and re.match(r"^source\s*=", items[-1]):
                 source = self.expr(items.pop().split("=", 1)[1], scope)[0]
             for item in items:
+                item = re.sub(r"\[[^\]]*\]\s*$", "", item.strip())      # allocate(x(...)[*]): the local part
                 mm = re.match(r"^(.*?)\((.*)\)$", item.strip())
                 if not mm:
                     if source is None:

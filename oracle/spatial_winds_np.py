@@ -12,8 +12,9 @@ PARITY: pinned to the reference's own source.  oracle/f90run executes spatial_wi
 calc_direction, calc_speed, calc_weight, smooth_array, linear_space of atm_utilities.f90 / array_utilities.f90) on a mock
 domain; given the same look-up table this file's spatial_winds returns the same u, v and stored perturbations in every
 bit (tests/test_reference_source.py::test_live_spatial_winds; REAL log / exp / atan / sin / cos are glibc's, like the
-compiled Fortran's).  The table ENTRIES rest on oracle/linear_winds_np.py, which equals the executed
-linear_perturbation routines; the loop of initialize_spatial_winds that fills the table (coarray puts) is not executed.
+compiled Fortran's).  The table ENTRIES: initialize_spatial_winds is executed too (one image, its own loop over the
+nodes, the coarray PUT of copy_data_to_remote) and every entry of its table equals EntryCache.get
+(::test_live_spatial_winds_table).
 
 Also restated: calc_stability / calc_dry_stability / calc_moist_stability / calc_sat_lapse_rate / calc_direction /
 calc_speed / calc_u / calc_v (src/utilities/atm_utilities.f90:334-467), calc_weight / linear_space / smooth_array_3d

@@ -532,3 +532,48 @@ def test_live_spatial_winds(ref, smooth):
     M = ref._sw[0].M
     assert np.array_equal(M.dir_values.a, Table.dirs) and np.array_equal(M.nsq_values.a, Table.nsqs) and \
         np.array_equal(M.spd_values.a, Table.spds)                       # linear_space (array_utilities.f90:233-235)
+
+
+@needs_reference
+@pytest.mark.parametrize("varying", [True, False])
+def test_live_spatial_winds_table(ref, varying):
+    """initialize_spatial_winds (src/physics/linear_winds.f90:596-838) executed on one image: its own loop over the table
+    nodes -- the ijk -> (direction, stability, speed) mapping, calc_u / calc_v, exp(nsq), the layer bounds, the generic
+    linear_perturbation, the staggering, copy_data_to_remote (a coarray PUT) -- fills the whole look-up table; every entry
+    equals what oracle/spatial_winds_np.py's EntryCache computes on demand (which is what icar_linear_perturb_spatial
+    evaluates on the device), terrain-following and constant layer bounds"""
+    from oracle import spatial_winds_np as SW
+    f = np.float32
+    nx, ny, nz = 7, 6, 2
+    o = SW.LTOptions()
+    o.buffer, o.n_dir_values, o.n_spd_values, o.n_nsq_values = 3, 5, 3, 3
+    terrain = (400 * np.exp(-(((np.arange(nx)[:, None] - 3) / 2.0) ** 2 + ((np.arange(ny)[None, :] - 2) / 1.5) ** 2))).astype(f)
+    rng = np.random.default_rng(2)
+    if varying:
+        zi = np.zeros((nx, nz, ny), f)
+        dzi = np.zeros((nx, nz, ny), f)
+        zi[:, 0, :] = terrain
+        dzi[:, 0, :] = rng.uniform(250, 350, (nx, ny))
+        zi[:, 1, :] = zi[:, 0, :] + dzi[:, 0, :]
+        dzi[:, 1, :] = rng.uniform(400, 600, (nx, ny))
+        lu, lv = ref.spatial_winds_table(terrain, 2000.0, o, z_interface=zi, dz_interface=dzi)
+
+        def bounds(z):
+            zb = zi[:, z, :] - terrain
+            return zb, zb + dzi[:, z, :]
+    else:
+        dzl = np.array([300, 500], f)
+        lh = np.array([150, 550], f)                                  # mid-level heights above the terrain: sum(dz) - dz/2
+        lu, lv = ref.spatial_winds_table(terrain, 2000.0, o, layer_height=lh, dz_levels=dzl)
+
+        def bounds(z):
+            return lh[z] - dzl[z] / f(2), lh[z] + dzl[z] / f(2)
+    cache = SW.EntryCache(terrain, 2000.0, o, bounds)
+    assert lu.shape == (3, 5, 3, nx + 1, nz, ny) and lv.shape == (3, 5, 3, nx, nz, ny + 1)
+    for s_ in range(3):
+        for d in range(5):
+            for n in range(3):
+                for z in range(nz):
+                    tu, tv = cache.get(s_, d, n, z)
+                    assert np.array_equal(tu.T, lu[s_, d, n, :, z, :]) and np.array_equal(tv.T, lv[s_, d, n, :, z, :]), (s_, d, n, z)
+    assert np.abs(lu).max() > 1.0 and (lu[0] == 0).all()             # speed node 0 is calm: no perturbation
