@@ -6,9 +6,9 @@
 // PARITY PINNED TO THE REFERENCE'S OWN SOURCE: the reference holds no expected values for this path and
 // cannot be compiled here (no Fortran compiler), so oracle/f90run executes src/physics/mp_thompson.f90 itself.
 // Equal in every bit to its outputs: thompson_init's 130 scalar constants and bin grids, the tables of freezeH2O /
-// qi_aut_qs / table_Efrw / table_Efsw, one (k, m) slab of each rain-collection table from qr_acr_qg / qr_acr_qs,
+// qi_aut_qs / table_Efrw / table_Efsw, three (k, m) slabs of each rain-collection table from qr_acr_qg / qr_acr_qs,
 // and mp_gt_driver + mp_thompson over six calls with every species present (tests/test_reference_source.py,
-// tests/golden/reference_source_thompson.npz).  Not executed: the other 1368 slabs of the two collection tables
+// tests/golden/reference_source_thompson.npz).  Not executed: the other 1366 slabs of each of the two collection tables
 // (1.4e10 inner iterations); those have an independent NumPy / SciPy check.  DESIGN.md section 5.
 //
 // Reference files followed (relative to /root/reference):

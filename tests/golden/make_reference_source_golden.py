@@ -11,8 +11,8 @@ path -- to outputs of the reference's text:
   reference_source_mpdata_scenario_f32.npz        the scenario of src/tests/test_mpdata.f90:51-111 (two loops)
   reference_source_mp_simple_scenario_f32.npz     the scenario of src/tests/test_mp_simple.f90:4-33 (100 calls of mp_simple)
   reference_source_thompson.npz                   src/physics/mp_thompson.f90: thompson_init's 130 scalar constants, the bin
-        grids, the tables of freezeH2O / qi_aut_qs / table_Efrw / table_Efsw (2-D ones whole, 3-D ones sampled), one (k, m)
-        slab of each rain-collection table from qr_acr_qg / qr_acr_qs themselves, and mp_gt_driver + mp_thompson: six calls
+        grids, the tables of freezeH2O / qi_aut_qs / table_Efrw / table_Efsw (2-D ones whole, 3-D ones sampled), three (k, m)
+        slabs of each rain-collection table from qr_acr_qg / qr_acr_qs themselves, and mp_gt_driver + mp_thompson: six calls
         on a moist 6 x 16 x 4 hill state in which every species forms.  (The remaining slabs of the two collection tables
         -- 1.4e10 inner iterations -- are taken from the C++ oracle for the run.)
   reference_source_random_f32.npz                 advect3d (orders 1-3, FCT on / off) and mp_simple_driver (sub-tile) on
@@ -133,7 +133,8 @@ def random_cases(ref, nx=13, nz=7, ny=9, seed=3):
 
 
 THOMPSON_KEYS = ("th", "qv", "qc", "qr", "qi", "qs", "qg", "ni", "nr", "rainnc", "snownc", "graupelnc", "sr")
-THOMPSON_SLABS = ((0, 5 * 37 + 11), (1, 20 * 37 + 7))          # (table family, km): one slab of each builder
+# (table family, km): first, an inner and the last (k, m) slab of each builder
+THOMPSON_SLABS = ((0, 0), (0, 5 * 37 + 11), (0, 36 * 37 + 36), (1, 0), (1, 20 * 37 + 7), (1, 36 * 37 + 36))
 
 
 def thompson_state(nx=6, nz=16, ny=4):
@@ -161,7 +162,7 @@ def thompson_case(ref):
             out["table_" + n] = flat[idx].copy()
     for which, km in THOMPSON_SLABS:
         for n, v in ref.thompson_big_slab(which, km).items():
-            out[f"slab_{n}"] = v
+            out[f"slab{km}_{n}"] = v
     st = thompson_state()
     for call in range(1, 7):
         ref.mp_gt_driver(st, 60.0)

@@ -194,8 +194,8 @@ def thompson_state(nx=6, nz=16, ny=4):
 
 def test_golden_thompson_init(oracle, golden_dir, thompson_full):
     """thompson_init as the reference's text computes it -- 130 scalar constants, the five bin grids, the freezing /
-    ice-to-snow / collision-efficiency tables, one slab of each rain-collection table from qr_acr_qg / qr_acr_qs run
-    for that slab -- against the C++ oracle: equal in every bit"""
+    ice-to-snow / collision-efficiency tables, three slabs of each rain-collection table from qr_acr_qg / qr_acr_qs run
+    for those slabs -- against the C++ oracle: equal in every bit"""
     g = load(golden_dir, "reference_source_thompson.npz")
     assert np.array_equal(thompson_full.constants(), g["constants"])
     bins = thompson_full.bins()
@@ -208,12 +208,14 @@ def test_golden_thompson_init(oracle, golden_dir, thompson_full):
         assert np.array_equal(got, want), n
         assert (want != 0).any()
     from oracle.f90run import Reference
-    for which, km in ((0, 5 * 37 + 11), (1, 20 * 37 + 7)):          # THOMPSON_SLABS of make_reference_source_golden.py
+    # THOMPSON_SLABS of make_reference_source_golden.py: the first, an inner and the last (k, m) slab of each builder
+    for which, km in ((0, 0), (0, 5 * 37 + 11), (0, 36 * 37 + 36), (1, 0), (1, 20 * 37 + 7), (1, 36 * 37 + 36)):
         m, k = divmod(km, 37)
-        for n in (Reference.BIG_QG if which == 0 else Reference.BIG_QS):
-            assert np.array_equal(thompson_full.table(n)[m, k].T, g["slab_" + n]), (n, km)
-        # (in the rain-snow slab the three `sacr1` tables are zero: that branch of the collection is not taken there)
-        assert sum(int((g["slab_" + n] != 0).sum()) for n in (Reference.BIG_QG if which == 0 else Reference.BIG_QS)) >= 2000
+        names = Reference.BIG_QG if which == 0 else Reference.BIG_QS
+        for n in names:
+            assert np.array_equal(thompson_full.table(n)[m, k].T, g[f"slab{km}_{n}"]), (n, km)
+        # (in some rain-snow slabs the `sacr1` / `racs2` tables are zero: that branch of the collection is not taken there)
+        assert sum(int((g[f"slab{km}_{n}"] != 0).sum()) for n in names) >= 1000, km
 
 
 def test_golden_thompson_driver(golden_dir, thompson_full):
