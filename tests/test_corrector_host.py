@@ -111,6 +111,39 @@ def test_y_chunks_and_repeated_runs_do_not_change_a_bit(emu, oracle):
         assert np.array_equal(a[k], b[k]) and np.array_equal(a[k], c[k]), k
 
 
+def blob_case(nx, nz, ny):
+    """Fields that are zero over most of the domain: blocks of zero and non-zero cells meet inside a warp's columns, between
+    the level groups of neighbouring warps, between x tiles and from one plane to the next."""
+    st = ideal.make_ideal_case(nx=nx, nz=nz, ny=ny, perturb=True)
+    rng = np.random.default_rng(11)
+    st["w"] = (st["w"] + rng.uniform(-0.3, 0.3, st["w"].shape)).astype(f)
+    z = lambda: np.zeros((ny, nz, nx), f)
+    qc, qr, qs = z(), z(), z()
+    qc[4:9, 3:9, 20:50] = rng.uniform(1e-5, 1e-3, (5, 6, 30))          # one block in the middle, crossing two x tiles
+    qr[:, 0:2, :] = rng.uniform(1e-5, 1e-3, (ny, 2, nx))                # the lowest two levels only
+    qr[10:, 12:, 60:] = rng.uniform(1e-5, 1e-3, qr[10:, 12:, 60:].shape)   # and a corner up to the last plane / level / column
+    qs[7, 10, 33] = f(1e-3)                                             # a single cell
+    st["qc"], st["qr"], st["qs"] = qc, qr, qs
+    return st
+
+
+@pytest.mark.parametrize("np_,nzp,nz,chunk", [(1, 20, 20, None), (1, 20, 17, 5), (2, 48, 44, None)])
+def test_fields_that_are_mostly_zero(emu, oracle, np_, nzp, nz, chunk):
+    """Hydrometeor fields as a model run has them -- zero almost everywhere, with sharp edges: the result must be the
+    oracle's bit for bit where zero and non-zero blocks meet (0 / (0 + 1e-10) quotients, limiter factors of 0 / 1e-15)."""
+    nx, ny = 72, 14
+    st = blob_case(nx, nz, ny)
+    dt = float(st["dt"]) * 0.8
+    names = ("qc", "qr", "qs", "th")
+    got = emulated_advect(emu, oracle, st, dt, np_, nzp, 2, chunk, names=names)
+    U, V, W = oracle.wind_normalise(st["u"], st["v"], st["w"], st["jacobian_u"], st["jacobian_v"], st["jacobian_w"], None, f(dt), st["dx"])
+    for k in names:
+        want = st[k].copy()
+        oracle.advect3d(want, None, st["jacobian"], st["advection_dz"], U, V, W, 2, True)
+        assert np.array_equal(got[k], want), (k, int((got[k] != want).sum()), float(np.abs(got[k] - want).max()))
+    assert (got["qs"] != 0).sum() > 1 and (got["qc"] == 0).mean() > 0.5
+
+
 def test_more_shared_memory_than_a_cta_has_is_refused(emu, oracle):
     st = case(30, 64, 6)
     with pytest.raises(AssertionError, match="more shared memory"):
