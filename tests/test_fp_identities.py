@@ -3,8 +3,8 @@
 
 * div_shared: with y = RN(1/b) the Markstein sequence q0 = RN(a*y), r = a - b*q0 (exact in an FMA),
   q = RN(q0 + r*y) is the IEEE quotient RN(a/b);
-* k_upwind_all_p2's donor flux U+ * l + U- * r, U+- = (U +- |U|) / 2, evaluated as fma(U-, r, RN(U+ * l)),
-  equals the select form U * (U > 0 ? l : r) of common.cuh (adv_mpdata.f90:41 is the former).
+* the reference's donor flux U+ * l + U- * r with U+- = (U +- |U|) / 2 (adv_mpdata.f90:41), one of whose two products
+  is always an exact zero, equals the select form U * (U > 0 ? l : r) every kernel uses (donor() in common.cuh).
 
 fp32 operations are emulated with rational arithmetic and one correct rounding per operation."""
 from fractions import Fraction
