@@ -630,7 +630,7 @@ def run_b200(args, rank, world, local_rank):
         sym, rec = captured(dominant)
         if rec:
             traffic = rec["dram_bytes_per_launch"]
-            traffic_src = {"capture": "profiles/" + rec["capture"], "symbol": sym,
+            traffic_src = {"capture": rec["capture"], "summary": rec.get("summary"), "symbol": sym,
                            "timed_symbol": fused_symbol if dominant == "k_corrector_fused" else dominant}
     alu = None
     if not distributed:

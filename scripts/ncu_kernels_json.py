@@ -34,6 +34,9 @@ for rep in sys.argv[2:]:
         dur_unit = rows[1][col["gpu__time_duration.sum"]]
         out[sym] = {
             "capture": os.path.basename(rep),
+            # the committed text summary of that capture (scripts/ncu_summary.py): <tag>_top_<what>.ncu-rep ->
+            # profiles/<tag>_top_kernels_<what>.txt
+            "summary": "profiles/" + re.sub(r"_top_(\w+?)(_v\d+)?\.ncu-rep$", r"_top_kernels_\1.txt", os.path.basename(rep)),
             "grid_size": r[col["Grid Size"]] if "Grid Size" in col else None,
             "block_size": r[col["Block Size"]] if "Block Size" in col else None,
             "tile_cells": cells,
