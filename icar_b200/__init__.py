@@ -168,7 +168,7 @@ SYMBOLS = (
     "icar_mpdata_set_winds_f64", "icar_mpdata_advect3d_f64", "icar_mp_simple_driver",
     "icar_physics_step_host", "icar_step_host", "icar_physics_step_host_io", "icar_physics_step_host_io_async", "icar_host_register", "icar_host_unregister",
     "icar_default_mp_options", "icar_thompson_init", "icar_thompson_table", "icar_mp_gt_driver",
-    "icar_profile_enable", "icar_profile_read", "icar_diagnostic_update", "icar_diagnostic_output", "icar_compute_dt", "icar_enforce_limits",
+    "icar_profile_enable", "icar_profile_read", "icar_diagnostic_update", "icar_diagnostic_output", "icar_compute_dt", "icar_enforce_limits", "icar_step",
     "icar_upload_tendency", "icar_apply_forcing", "icar_balance_uvw",
     "icar_add_buffer_topo", "icar_linear_winds_init", "icar_linear_winds_dims", "icar_linear_winds_terrain_frequency",
     "icar_linear_perturbation", "icar_linear_perturb", "icar_default_lt_options", "icar_linear_winds_set_z",
@@ -437,6 +437,15 @@ class Domain:
     def enforce_limits(self):
         """domain%enforce_limits (domain_obj.f90:2228-2243)."""
         self._check(lib().icar_enforce_limits(self._h))
+
+    def step(self, end_time, dz_levels, cfl_reduction_factor=0.9, cfl_strictness=3):
+        """step(domain, end_time, options) (time_step.f90:438-549): internal time steps until model_time reaches
+        end_time (seconds); returns how many were taken."""
+        dz = _f32(dz_levels, (self.grid.nz,), "dz_levels")
+        n = C.c_int()
+        self._check(lib().icar_step(self._h, C.c_double(end_time), _ptr(dz), C.c_float(cfl_reduction_factor),
+                                    int(cfl_strictness), C.byref(n)))
+        return n.value
 
     def synchronize(self):
         self._check(lib().icar_synchronize(self._h))

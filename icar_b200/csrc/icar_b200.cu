@@ -1972,6 +1972,35 @@ extern "C" int icar_apply_forcing(icar_ctx* ctx, double dt_seconds) {
     return ICAR_OK;
 }
 
+// step(domain, end_time, options), src/main/time_step.f90:438-549: the loop over internal time steps up to `end_time`
+// with everything on the device.  Model time is REAL*8 seconds here (the reference's Time_type holds a modified Julian
+// day and adds dt%days(); the two round differently below a microsecond, which is what the dt > 1e-3 test of :484 is
+// there to absorb).
+extern "C" int icar_step(icar_ctx* ctx, double end_time, const float* dz_levels, float cfl_reduction_factor,
+                         int cfl_strictness, int* steps_taken) {
+    if (!ctx) return ICAR_ERR_INVALID;
+    if (steps_taken) *steps_taken = 0;
+    int rc;
+    while (ctx->model_time < end_time) {                                                  // :464
+        double dt = 0.0;
+        if ((rc = icar_compute_dt(ctx, dz_levels, cfl_reduction_factor, cfl_strictness, &dt))) return rc;   // update_dt, :466
+        if (ctx->model_time + dt > end_time) dt = end_time - ctx->model_time;             // :469-471
+        if ((rc = icar_diagnostic_update(ctx))) return rc;                                // :474
+        const double t0 = ctx->model_time;
+        if (dt > 1e-3) {                                                                  // :484
+            // rad / lsm / pbl / convect (:489-509) are 0 in every configuration of this path
+            if ((rc = icar_physics_step(ctx, (float)dt))) return rc;                      // :512-529, real(dt%seconds())
+            ctx->model_time = t0;          // icar_physics_step advanced it by the REAL*4 dt; the loop keeps REAL*8 (:547)
+            if ((rc = icar_apply_forcing(ctx, dt))) return rc;                            // :537
+            if ((end_time - t0) < dt * 2.0)                                               // :540-542
+                if ((rc = icar_enforce_limits(ctx))) return rc;
+        }
+        ctx->model_time = t0 + dt;                                                        // :547
+        if (steps_taken) ++*steps_taken;
+    }
+    return ICAR_OK;
+}
+
 extern "C" int icar_balance_uvw(icar_ctx* ctx) {
     if (!ctx) return ICAR_ERR_INVALID;
     CU(cudaSetDevice(ctx->device));

@@ -31,7 +31,7 @@ module icar_b200_mod
     private
     public :: adv_init, adv_var_request, advect
     public :: mp_init, mp_var_request, mp
-    public :: b200_halo_send, b200_halo_retrieve, b200_sync_to_host, b200_finalize, b200_physics_steps
+    public :: b200_halo_send, b200_halo_retrieve, b200_sync_to_host, b200_finalize, b200_physics_steps, b200_step
     public :: b200_diagnostic_update, b200_diagnostic_output, b200_update_forcing, b200_apply_forcing, b200_enforce_limits, b200_upload_winds
     public :: b200_linear_perturb, b200_write_restart, b200_read_restart
 
@@ -171,6 +171,15 @@ module icar_b200_mod
         integer(c_int) function icar_enforce_limits(ctx) bind(c)
             import :: c_int, c_ptr
             type(c_ptr), value :: ctx
+        end function
+        integer(c_int) function icar_step(ctx, end_time, dz_levels, cfl_reduction_factor, cfl_strictness, steps_taken) bind(c)
+            import :: c_int, c_ptr, c_double, c_float
+            type(c_ptr), value :: ctx
+            real(c_double), value :: end_time
+            type(c_ptr), value :: dz_levels
+            real(c_float), value :: cfl_reduction_factor
+            integer(c_int), value :: cfl_strictness
+            type(c_ptr), value :: steps_taken
         end function
         integer(c_int) function icar_upload_tendency(ctx, var, host) bind(c)
             import :: c_int, c_ptr
@@ -433,6 +442,20 @@ contains
         real,    intent(in) :: dt
         integer, intent(in) :: n
         call check(icar_physics_steps(ctx, dt, int(n, c_int), 1_c_int), "icar_physics_steps")
+    end subroutine
+
+    !> step(domain, end_time, options) -- time_step.f90:438-549 -- with the whole loop on the device: update_dt,
+    !> diagnostic_update, mp / halo exchange / advect, apply_forcing and enforce_limits of every internal time step.
+    !> end_time_seconds is on the clock the context was given (icar_set_model_time); the host copies are stale
+    !> afterwards until b200_sync_to_host.
+    subroutine b200_step(end_time_seconds, options)
+        double precision, intent(in) :: end_time_seconds
+        type(options_t),  intent(in) :: options
+        real(c_float), allocatable, target :: dz(:)
+        dz = options%parameters%dz_levels(1:options%parameters%nz)
+        call check(icar_step(ctx, real(end_time_seconds, c_double), c_loc(dz),                        &
+                             real(options%parameters%cfl_reduction_factor, c_float),                  &
+                             int(options%parameters%cfl_strictness, c_int), c_null_ptr), "icar_step")
     end subroutine
 
     !> advect(domain, options, dt) -- advection_driver.f90:51

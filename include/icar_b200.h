@@ -330,6 +330,17 @@ int icar_restart_info(const char* path, icar_grid* grid, int* microphysics, doub
  * microphysics scheme allocates. */
 int icar_enforce_limits(icar_ctx* ctx);
 
+/* step(domain, end_time, options) (src/main/time_step.f90:438-549): internal time steps until the model time reaches
+ * end_time (seconds, same clock as icar_set_model_time), each one
+ *     update_dt (:466, icar_compute_dt) -> clip to end_time (:469-471) -> diagnostic_update (:474) ->
+ *     if dt > 1e-3: mp(halo) / halo_send / mp(subset) / halo_retrieve / advect (:512-529, icar_physics_step with
+ *     real(dt)), apply_forcing(dt) (:537), enforce_limits in the last two updates (:540-542) -> model_time += dt (:547)
+ * with no host round trip other than the one double of update_dt.  rad / lsm / pbl / convect (:489-509) are not part
+ * of this path (0 in every BASELINE configuration).  steps_taken (may be NULL) receives the number of passes.
+ * Errors are those of the calls it is made of ("time step too small" included, on every image together). */
+int icar_step(icar_ctx* ctx, double end_time, const float* dz_levels, float cfl_reduction_factor, int cfl_strictness,
+              int* steps_taken);
+
 /* Blocks until all work queued by the calls above has finished on the device. */
 int icar_synchronize(icar_ctx* ctx);
 

@@ -160,6 +160,13 @@ inline void b200_update_forcing(int var, const std::vector<float>& dqdt_3d) {
 inline void b200_apply_forcing(double dt_seconds) { detail::check(icar_apply_forcing(detail::ctx(), dt_seconds), "icar_apply_forcing"); }
 inline void b200_enforce_limits() { detail::check(icar_enforce_limits(detail::ctx()), "icar_enforce_limits"); }
 
+// step(domain, end_time, options), time_step.f90:438-549, with the whole loop on the device; returns the passes taken
+inline int b200_step(double end_time_seconds, const float* dz_levels, float cfl_reduction_factor, int cfl_strictness) {
+    int n = 0;
+    detail::check(icar_step(detail::ctx(), end_time_seconds, dz_levels, cfl_reduction_factor, cfl_strictness, &n), "icar_step");
+    return n;
+}
+
 // mp(domain, options, dt_in, halo, subset) -- mp_driver.f90:673; halo / subset < 0 == "not present"
 inline void mp(domain_t& domain, const options_t&, float dt_in, int halo = -1, int subset = -1) {
     if (halo >= 0 || subset < 0) sync_to_device(domain);          // first mp call of the step

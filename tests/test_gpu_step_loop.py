@@ -185,6 +185,69 @@ def test_device_resident_loop_body(gpu_lib, oracle):
         assert np.abs(a - b).max() <= 1e-5 * np.abs(b).max(), k         # exner via device powf feeds mp_simple
 
 
+def test_step_is_the_loop_of_time_step_f90(gpu_lib):
+    """icar_step == the do-while loop of step() (time_step.f90:464-549) written out with the calls it is made of: update_dt,
+    the clip to end_time, diagnostic_update, the physics of the step with real(dt), apply_forcing(dt), enforce_limits in
+    the last two updates, model_time += dt in REAL*8 -- bit for bit and in the same number of passes; a pass whose dt
+    is below 1e-3 s only advances the clock (:484)."""
+    st = ideal.make_ideal_case(nx=48, nz=16, ny=20, perturb=True)
+    st["qv"] *= np.float32(3.0)
+    st["qc"][:, 10:, :] = np.float32(-1e-5)             # something for enforce_limits to clamp
+    rng = np.random.default_rng(11)
+    tend = {"u": (rng.normal(0, 2e-3, st["u"].shape)).astype(np.float32),
+            "pressure": (rng.normal(0, 1e-2, st["pressure"].shape)).astype(np.float32),
+            "th": (rng.normal(0, 1e-4, st["th"].shape)).astype(np.float32)}
+    a, b = make(gpu_lib, st), make(gpu_lib, st)
+    for d in (a, b):
+        for k, v in tend.items():
+            d.upload_tendency(k, v)
+        d.model_time = 1000.0
+    passes = []                                          # (dt, physics ran, enforce_limits ran) of the loop written out
+
+    def by_hand(d, end):
+        n = 0
+        while d.model_time < end:
+            dt = d.compute_dt(st["dz_levels"])
+            if d.model_time + dt > end:
+                dt = end - d.model_time
+            d.diagnostic_update()
+            t0 = d.model_time
+            physics = limits = False
+            if dt > 1e-3:
+                d.physics_step(dt)                       # real(dt%seconds())
+                d.model_time = t0
+                d.apply_forcing(dt)
+                physics = True
+                if (end - t0) < dt * 2:
+                    d.enforce_limits()
+                    limits = True
+            d.model_time = t0 + dt
+            passes.append((dt, physics, limits))
+            n += 1
+        return n
+
+    def same_state():
+        assert a.model_time == b.model_time
+        for k in ("th", "qv", "qc", "qr", "qs", "u", "pressure", "exner", "density"):
+            np.testing.assert_array_equal(a.download(k), b.download(k), err_msg=k)
+
+    dt0 = b.compute_dt(st["dz_levels"])
+    end = 1000.0 + 2.4 * dt0                             # two full steps and a clipped one
+    n = a.step(end, st["dz_levels"])
+    assert n == by_hand(b, end) and n >= 3
+    assert abs(a.model_time - end) < 1e-9
+    same_state()
+    assert sum(p[2] for p in passes) >= 2 and not passes[0][2]      # enforce_limits: only in the last updates
+    assert (a.download("qc") >= 0).all()
+    # one more full step and half a millisecond: the last pass must not run any physics
+    end = a.model_time + b.compute_dt(st["dz_levels"]) + 0.0005
+    first = len(passes)
+    n = a.step(end, st["dz_levels"])
+    assert n == by_hand(b, end) and n == 2
+    same_state()
+    assert passes[first][1] and not passes[-1][1] and passes[-1][0] < 1e-3
+
+
 def test_step_host_derives_exner_and_density_on_the_device(gpu_lib):
     """icar_step_host == upload; icar_diagnostic_update; icar_physics_step; download -- bit for bit -- and it
     refuses host exner / density."""
