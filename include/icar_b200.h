@@ -337,7 +337,11 @@ int icar_enforce_limits(icar_ctx* ctx);
  *     real(dt)), apply_forcing(dt) (:537), enforce_limits in the last two updates (:540-542) -> model_time += dt (:547)
  * with no host round trip other than the one double of update_dt.  rad / lsm / pbl / convect (:489-509) are not part
  * of this path (0 in every BASELINE configuration).  steps_taken (may be NULL) receives the number of passes.
- * Errors are those of the calls it is made of ("time step too small" included, on every image together). */
+ * Errors are those of the calls it is made of ("time step too small" included, on every image together).
+ * The clock is REAL*8 seconds; the reference's Time_type counts days in REAL*8, so (i) it may take one more pass whose dt
+ * is a rounding leftover below 1e-3 s, in which nothing runs, and (ii) where `end_time - model_time` EQUALS 2 dt in
+ * seconds the rounding of its day count decides the `<` of :540 (enforce_limits one update earlier); here equal is not
+ * less.  oracle/f90run executes step() itself against this control flow (tests/test_reference_source.py::test_live_step_loop). */
 int icar_step(icar_ctx* ctx, double end_time, const float* dz_levels, float cfl_reduction_factor, int cfl_strictness,
               int* steps_taken);
 

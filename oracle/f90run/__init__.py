@@ -219,6 +219,67 @@ class Reference:
         self._diag.diagnostic_update(dom, ns())
         return out
 
+    def step_loop(self, start_seconds, end_seconds, dts):
+        """step(domain, end_time, options), time_step.f90:438-549, executed as written on a mock domain whose physics are
+        recorders: update_dt hands out the scripted `dts` (seconds) in turn; rad / lsm / pbl / convect / mp / advect,
+        domain%halo_send / halo_retrieve / apply_forcing / enforce_limits and diagnostic_update append to the log.
+        Model time is the reference's: a Time_type holds days in REAL*8 (time_obj.f90: `addition` :892-902 adds dt%days(),
+        `difference` :861-884 multiplies the day difference by 86400, the comparisons :656-831 compare days) and a
+        time_delta_t holds days too (time_delta_obj.f90: set :28-44 divides seconds by 86400, seconds() multiplies).
+        The debug / interactive branches (domain_check, print_progress) are patched to .false..
+        Returns (log, final model time in seconds); log entries are (name, *arguments)."""
+        ns = types.SimpleNamespace
+        log = []
+
+        class Delta:                                     # time_delta_t
+            def __init__(self, seconds=0.0): self.delta = np.float64(seconds) / np.float64(86400.0)
+            def set(self, seconds): self.delta = np.float64(seconds) / np.float64(86400.0)
+            def days(self): return self.delta
+            def seconds(self): return self.delta * np.float64(86400.0)
+            def __mul__(self, k): d = Delta(); d.delta = self.delta * np.float64(k); return d
+
+        class Time:                                      # Time_type, same calendar and reference date on both sides
+            def __init__(self, days): self.current_date_time = np.float64(days)
+            def mjd(self): return np.longdouble(self.current_date_time)
+            def seconds(self): return np.longdouble(self.current_date_time) * np.float64(86400.0)
+            def __add__(self, dt): return Time(np.float64(self.mjd() + dt.days()))
+            def __sub__(self, other):
+                d = Delta(); d.set(np.float64(self.mjd() - other.mjd()) * np.float64(86400.0)); return d
+            def __lt__(self, o): return not (self.current_date_time >= o.current_date_time)
+            def __gt__(self, o): return self.current_date_time > o.current_date_time
+
+        script = list(dts)
+
+        def update_dt(M, dt, options, domain, end_time):
+            log.append(("update_dt",))
+            # dt%set(seconds=...), time_step.f90:421; `dt` is the caller's local (a plain record until step() assigns a
+            # difference of two times to it), so it is given time_delta_t's state and accessors here
+            dt.delta = np.float64(script.pop(0)) / np.float64(86400.0)
+            dt.days = lambda d=dt: d.delta
+            dt.seconds = lambda d=dt: d.delta * np.float64(86400.0)
+
+        def recorder(name):
+            def f(domain, options, dt, halo=None, subset=None, **k):
+                log.append((name, float(dt)) + ((("halo", int(halo)),) if halo is not None else ())
+                           + ((("subset", int(subset)),) if subset is not None else ()))
+            return f
+
+        dom = ns(grid=ns(ims=1, jms=1, kms=1), model_time=Time(np.float64(start_seconds) / np.float64(86400.0)))
+        dom.halo_send = lambda: log.append(("halo_send",))
+        dom.halo_retrieve = lambda: log.append(("halo_retrieve",))
+        dom.apply_forcing = lambda dt: log.append(("apply_forcing", float(dt.seconds())))
+        dom.enforce_limits = lambda: log.append(("enforce_limits",))
+        false_if = [(r"^if\s*\(options%parameters%interactive.*then$", "if (.false.) then")]
+        mod = Module(self._time_step_path,
+                     overrides={"update_dt": update_dt,
+                                "diagnostic_update": lambda M, domain, options: log.append(("diagnostic_update",)),
+                                "print_progress": lambda M, *a: None},
+                     externals=dict({n: recorder(n) for n in ("rad", "lsm", "pbl", "convect", "mp", "advect")},
+                                    domain_check=None, str=lambda *a, **k: ""),
+                     patches={"step": false_if}).build(["step"])
+        mod.step(dom, Time(np.float64(end_seconds) / np.float64(86400.0)), ns(parameters=ns(interactive=False, debug=False)))
+        return log, float(dom.model_time.seconds())
+
     def mp_schedule(self, calls, update_interval, grid):
         """mp(domain, options, dt_in, halo, subset), mp_driver.f90:673-772, with process_subdomain / process_halo replaced
         by recorders: for each (model_time, dt_in, halo, subset) of `calls` the list of (routine, mp_dt, its, ite, jts,

@@ -268,6 +268,35 @@ def diagnostic_output_np(pressure, th, u, v, w, jacobian, dzdx, dzdy):
     return o
 
 
+def step_loop_np(start_seconds, end_seconds, dts):
+    """The control flow of icar_step (icar_b200/csrc/icar_b200.cu) = step(), time_step.f90:438-549, with the model time
+    in REAL*8 seconds: update_dt hands out the scripted `dts`; returns (log, final time) in the format of
+    oracle.f90run.Reference.step_loop -- the same routine names in the same order -- so that the two can be compared."""
+    log, script = [], list(dts)
+    t = float(start_seconds)
+    end = float(end_seconds)
+    while t < end:                                                       # :464
+        log.append(("update_dt",))                                       # :466
+        dt = float(script.pop(0))
+        if t + dt > end:                                                 # :469-471
+            dt = end - t
+        log.append(("diagnostic_update",))                               # :474
+        if dt > 1e-3:                                                    # :484
+            r = float(np.float32(dt))                                    # real(dt%seconds())
+            for name in ("rad", "lsm", "pbl", "convect"):                # :489-509 (0 on this path; the order is the source's)
+                log.append((name, r))
+            log.append(("mp", r, ("halo", 1)))                           # :512
+            log.append(("halo_send",))                                   # :515
+            log.append(("mp", r, ("subset", 1)))                         # :523
+            log.append(("halo_retrieve",))                               # :526
+            log.append(("advect", r))                                    # :529
+            log.append(("apply_forcing", dt))                            # :537
+            if (end - t) < dt * 2:                                       # :540-542
+                log.append(("enforce_limits",))
+        t = t + dt                                                       # :547
+    return log, t
+
+
 def compute_dt_np(dx, u, v, w, dz_levels, cfl, cfl_strictness):
     """compute_dt (src/main/time_step.f90:217-330) with use_density = .false., then update_dt's 120 s cap
     (:421).  u (ny,nz,nx+1), v (ny+1,nz,nx), w (ny,nz,nx); REAL arithmetic.  Raises where the reference

@@ -319,6 +319,71 @@ def test_live_compute_dt(ref, strictness):
         assert got == want, (strictness, scale)
 
 
+def _passes(log):
+    """The log of a step loop cut into passes: (dt handed to the physics or None, dt of apply_forcing, enforce_limits ran),
+    after checking that every pass is exactly the source's sequence of calls."""
+    full = ["update_dt", "diagnostic_update", "rad", "lsm", "pbl", "convect", "mp", "halo_send", "mp", "halo_retrieve",
+            "advect", "apply_forcing"]
+    out, i = [], 0
+    while i < len(log):
+        assert log[i] == ("update_dt",) and log[i + 1] == ("diagnostic_update",)
+        j = i + 2
+        while j < len(log) and log[j][0] != "update_dt":
+            j += 1
+        names = [e[0] for e in log[i:j]]
+        if names == ["update_dt", "diagnostic_update"]:
+            out.append((None, None, False))                             # a pass that only advances the clock
+        else:
+            limits = names[-1] == "enforce_limits"
+            assert names[:len(names) - limits] == full, names
+            body = log[i + 2:j - limits]
+            assert body[4][2] == ("halo", 1) and body[6][2] == ("subset", 1)
+            rdt = {e[1] for e in body[:-1] if len(e) > 1}
+            assert len(rdt) == 1                                          # every physics call gets the same real(dt)
+            out.append((rdt.pop(), body[-1][1], limits))
+        i = j
+    return out
+
+
+@needs_reference
+@pytest.mark.parametrize("start,end,dts", [
+    (1000.0, 1290.0, [120.0] * 4),                       # two full steps and a clipped one
+    (0.0, 240.0005, [120.0] * 4),                        # the remainder is half a millisecond: no physics for it (:484)
+    (3600.0, 3960.0, [120.0] * 5),                       # dt divides the interval
+    (86400.0 * 400, 86400.0 * 400 + 3600.0, [37.3] * 120),   # many steps, a dt that no binary fraction of a day holds
+    (50.0, 60.0, [120.0] * 2),                           # one clipped step
+    (0.0, 600.0, [120.0, 80.0, 33.25, 120.0, 120.0, 120.0, 120.0, 120.0]),    # dt changes from step to step
+])
+def test_live_step_loop(ref, start, end, dts):
+    """step(domain, end_time, options) of src/main/time_step.f90:438-549 executed as written (physics replaced by recorders,
+    model time in the reference's REAL*8 days) against the control flow of icar_step: the same calls in the same order in
+    every pass, the same real(dt) for the physics, apply_forcing's dt and the final time equal to within the rounding of
+    a day count (1e-6 s), enforce_limits in the same passes.  Passes that only advance the clock (dt <= 1e-3 s: what a
+    clock in days leaves over, :484) may differ in number; nothing runs in them."""
+    got_log, got_t = ref.step_loop(start, end, dts)
+    from oracle import np_restatement as NP
+    want_log, want_t = NP.step_loop_np(start, end, dts)
+    got, want = _passes(got_log), _passes(want_log)
+    physics = lambda ps: [p for p in ps if p[0] is not None]            # noqa: E731
+    assert len(physics(got)) == len(physics(want)) >= 1
+    t0, ties = start, 0
+    for g, w in zip(physics(got), physics(want)):
+        assert abs(g[0] - w[0]) <= 1e-5 and abs(g[1] - w[1]) <= 1e-5, (g, w)
+        # `(end_time - model_time) < 2 dt` (:540): where the two sides are EQUAL in seconds the reference's clock in days
+        # decides by its rounding (3600 s -> 3960 s in steps of 120 s: it clamps one update earlier); a clock in
+        # seconds has no such rounding and says "not less"
+        if abs((end - t0) - 2 * w[1]) <= 1e-5:
+            ties += 1
+            assert not w[2]
+        else:
+            assert g[2] == w[2], (g, w)
+        t0 += w[1]
+    assert ties == (1 if (start, end) == (3600.0, 3960.0) else 0)
+    assert abs(got_t - want_t) <= 1e-5 and abs(want_t - end) <= 1e-9
+    if end == 240.0005:
+        assert got[-1][0] is None and want[-1][0] is None and len(physics(want)) == 2
+
+
 @needs_reference
 def test_live_diagnostic_update(ref):
     """diagnostic_update of src/main/time_step.f90:49-198 on a mock domain (exner through exner_function of
