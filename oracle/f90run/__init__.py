@@ -219,6 +219,20 @@ class Reference:
         self._diag.diagnostic_update(dom, ns())
         return out
 
+    def advect_dispatch(self, advection):
+        """advect(domain, options, dt), src/physics/advection_driver.f90:51-66, with upwind / mpdata replaced by recorders
+        and kADV_* read from icar_constants.f90: returns the list of schemes it called for options%physics%advection."""
+        ns = types.SimpleNamespace
+        called = []
+        if not hasattr(self, "_adv_driver"):
+            root = os.path.dirname(os.path.dirname(os.path.dirname(self.mp_path)))
+            self._adv_driver = Module(os.path.join(root, "src", "physics", "advection_driver.f90"),
+                                      names={"kadv_upwind": self.constants.kadv_upwind, "kadv_mpdata": self.constants.kadv_mpdata},
+                                      externals={"upwind": lambda d, o, dt: d.append(("upwind", float(dt))),
+                                                 "mpdata": lambda d, o, dt: d.append(("mpdata", float(dt)))}).build(["advect"])
+        self._adv_driver.advect(called, ns(physics=ns(advection=int(advection))), f32(120.0))
+        return called
+
     def step_loop(self, start_seconds, end_seconds, dts):
         """step(domain, end_time, options), time_step.f90:438-549, executed as written on a mock domain whose physics are
         recorders: update_dt hands out the scripted `dts` (seconds) in turn; rad / lsm / pbl / convect / mp / advect,

@@ -319,6 +319,20 @@ def test_live_compute_dt(ref, strictness):
         assert got == want, (strictness, scale)
 
 
+@needs_reference
+def test_live_advect_dispatch(ref):
+    """advect() of advection_driver.f90:51-66 and the scheme numbers of icar_constants.f90:347-372, executed: which
+    scheme runs for which options%physics%advection -- the numbering icar_options uses (include/icar_b200.h) and the
+    "nothing for any other value" that icar_advect keeps."""
+    assert ref.advect_dispatch(1) == [("upwind", 120.0)]
+    assert ref.advect_dispatch(2) == [("mpdata", 120.0)]
+    assert ref.advect_dispatch(0) == [] and ref.advect_dispatch(3) == []
+    c = ref.constants
+    assert (int(c.kadv_upwind), int(c.kadv_mpdata), int(c.kmp_thompson), int(c.kmp_sb04)) == (1, 2, 1, 2)
+    hdr = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include", "icar_b200.h")).read()
+    assert "1 kADV_UPWIND, 2 kADV_MPDATA" in hdr and "1 kMP_THOMPSON" in hdr
+
+
 def _passes(log):
     """The log of a step loop cut into passes: (dt handed to the physics or None, dt of apply_forcing, enforce_limits ran),
     after checking that every pass is exactly the source's sequence of calls."""
