@@ -187,6 +187,28 @@ class Reference:
         return self.time_step.compute_dt(f32(dx), _f(u)[1], _f(v)[1], _f(w)[1], _f(np.ones_like(w))[1],
                                          np.ascontiguousarray(dz_levels, np.float32), f32(cfl), int(cfl_strictness), False)
 
+    def update_dt(self, dx, u, v, w, dz_levels, cfl, cfl_strictness, other_images=()):
+        """update_dt(dt, options, domain, end_time), time_step.f90:375-423, as written (a build without __INTEL_COMPILER):
+        compute_dt on the domain's winds with use_density = .false., `co_min` over this image's value and those of
+        `other_images`, and dt%set(seconds = min(seconds, 120)).  Returns the seconds dt was set to."""
+        ns = types.SimpleNamespace
+        if not hasattr(self, "_update_dt"):
+            self._co_min_others = []
+            self._update_dt = Module(self._time_step_path,
+                                     externals={"co_min": (lambda x: min([x] + list(self._co_min_others)), [0])}
+                                     ).build(["update_dt"])
+        self._co_min_others = [np.float64(x) for x in other_images]
+        fa = lambda a: FArr(_f(a)[1], (1,) * a.ndim)          # noqa: E731
+        dom = ns(dx=f32(dx), u=ns(data_3d=fa(u)), v=ns(data_3d=fa(v)), w=ns(data_3d=fa(w)),
+                 density=ns(data_3d=fa(np.ones_like(w))))
+        opts = ns(parameters=ns(dz_levels=np.ascontiguousarray(dz_levels, np.float32), cfl_reduction_factor=f32(cfl),
+                                cfl_strictness=int(cfl_strictness)))
+        got = []
+        dt = ns(set=lambda seconds: got.append(seconds))
+        self._update_dt.update_dt(dt, opts, dom, None)
+        assert len(got) == 1
+        return got[0]
+
     def diagnostic_update(self, pressure, th, u, v, w, jacobian, dzdx, dzdy):
         """diagnostic_update(domain, options), time_step.f90:49-198, on a mock domain that has the fields of this path
         (exner, density, temperature, the interface fields, psfc, u_mass, v_mass, w_real) and none of the others

@@ -65,15 +65,34 @@ def _lower_outside_strings(s):
     return "".join(out)
 
 
-def read_statements(path, _depth=0):
-    """[(file, first line number, statement text)]: comments stripped, continuations joined, INCLUDEs inlined."""
+def read_statements(path, _depth=0, defined=()):
+    """[(file, first line number, statement text)]: comments stripped, continuations joined, INCLUDEs inlined, and the
+    conditional-compilation lines of the C preprocessor (#ifdef / #ifndef / #else / #endif on a macro name) resolved with
+    the macros in `defined` -- none by default, i.e. a build with neither __INTEL_COMPILER nor any -D switch."""
     if _depth > 5:
         raise TranslateError("include depth")
     stmts = []
     with open(path) as f:
         lines = f.read().split("\n")
     cur, cur_no = "", 0
+    active = []                                            # one entry per open #if: is its current branch taken?
     for no, raw in enumerate(lines, 1):
+        if raw.lstrip().startswith("#"):
+            d = raw.strip()[1:].split()
+            if d and d[0] in ("ifdef", "ifndef") and len(d) == 2:
+                active.append((d[1] in defined) == (d[0] == "ifdef"))
+            elif d and d[0] == "else" and active:
+                active[-1] = not active[-1]
+            elif d and d[0] == "endif" and active:
+                active.pop()
+            elif d and d[0] in ("define", "undef", "include"):
+                if all(active):
+                    raise TranslateError(f"{os.path.basename(path)}:{no}: preprocessor directive outside the subset: {raw.strip()}")
+            else:
+                raise TranslateError(f"{os.path.basename(path)}:{no}: preprocessor directive outside the subset: {raw.strip()}")
+            continue
+        if not all(active):
+            continue
         line = _strip_comment(raw)
         if not line.strip():
             continue
@@ -95,7 +114,7 @@ def read_statements(path, _depth=0):
             m = re.match(r"include\s+['\"]([^'\"]+)['\"]$", piece)
             if m:
                 inc = os.path.join(os.path.dirname(path), m.group(1))
-                stmts.extend(read_statements(inc, _depth + 1))
+                stmts.extend(read_statements(inc, _depth + 1, defined))
             else:
                 stmts.append((os.path.basename(path), cur_no, piece))
         cur = ""
@@ -1065,7 +1084,10 @@ class Module:
             code = scope.ref(v0) if (v0 in scope.locals or v0 in self.vars or v0 in scope.aliases) else py_name(v0)
             while p.accept("op", "%"):
                 code += "." + py_name(p.next()[1])
-            args = [self.expr(a, scope)[0] for a in (split_top(mm.group(3)) if (mm.group(3) or "").strip() else [])]
+            args = []
+            for a in (split_top(mm.group(3)) if (mm.group(3) or "").strip() else []):
+                mk = re.match(r"^(\w+)\s*=(?!=)\s*(.*)$", a.strip())              # keyword = value
+                args.append(f"{py_name(mk.group(1))}={self.expr(mk.group(2), scope)[0]}" if mk else self.expr(a, scope)[0])
             emit(f"{code}({', '.join(args)})")
             return
         else:
@@ -1119,6 +1141,14 @@ class Module:
         if name in self.externals:
             if self.externals[name] is None:
                 emit("pass")                      # declared a no-op by the harness (logging)
+            elif isinstance(self.externals[name], tuple):
+                # (function, positions of the scalar arguments it sets): it returns their new values, in that order
+                emit(f"_ret = _X_{name}({', '.join(codes + [py_name(k) + '=' + c for k, c in kwargs])})")
+                outs = list(self.externals[name][1])
+                for k, pos in enumerate(outs):
+                    kind, target, v, whole, obj = self._lvalue(actuals[pos].strip(), scope)
+                    val = "_ret" if len(outs) == 1 else f"_ret[{k}]"
+                    emit(f"{target} = {self.convert(val, v.kind) if kind == 'scalar' else val}")
             else:
                 emit(f"_X_{name}({', '.join(codes + [py_name(k) + '=' + c for k, c in kwargs])})")
             return

@@ -209,3 +209,34 @@ def test_unsupported_statements_are_errors_not_silence(tmp_path):
     with pytest.raises(TranslateError):
         build(str(tmp_path), bad, ["s"])
     assert unallocated(np.float32, 2).a is None
+
+
+def test_conditional_compilation_harness_methods_with_keywords_and_external_out_arguments(tmp_path):
+    """#ifdef / #ifndef / #else / #endif resolve as in a build without -D switches; CALL obj%method(key = value) reaches a
+    harness object with the keyword; an external subroutine declared as (function, [positions]) sets its scalar argument."""
+    src = """
+module m
+contains
+    subroutine s(obj, x)
+        type(clock_t), intent(inout) :: obj
+        double precision, intent(inout) :: x
+#ifndef __INTEL_COMPILER
+        call shrink(x)
+#endif
+#ifdef __INTEL_COMPILER
+        x = -1
+#else
+        x = x + 1
+#endif
+        call obj%set(seconds=min(x, 120.0D0))
+    end subroutine
+end module
+"""
+    got = []
+    obj = type("O", (), {"set": lambda self, seconds: got.append(seconds)})()
+    mod = build(str(tmp_path), src, ["s"], externals={"shrink": (lambda x: x / 2, [0])})
+    assert mod.s(obj, np.float64(10.0))[0] == 6.0 and got == [6.0]
+    mod.s(obj, np.float64(1000.0))
+    assert got[-1] == 120.0
+    with pytest.raises(TranslateError, match="preprocessor"):
+        build(str(tmp_path), "#if defined(X)\nmodule m\nend module\n#endif\n", [])

@@ -320,6 +320,29 @@ def test_live_compute_dt(ref, strictness):
 
 
 @needs_reference
+@pytest.mark.parametrize("strictness", [1, 2, 3, 4, 5])
+def test_live_update_dt(ref, strictness):
+    """update_dt of src/main/time_step.f90:375-423 executed as written (the branch a build without __INTEL_COMPILER takes):
+    compute_dt with use_density = .false. on the domain's winds, co_min over the images, then the 120 s cap -- the order
+    icar_compute_dt keeps (minimum first, cap after) and the value its restatement gives."""
+    from oracle import np_restatement as NP
+    st = ideal.make_ideal_case(nx=24, nz=8, ny=10, perturb=True)
+    for scale in (0.5, 1.0, 3.0):
+        u = (st["u"] * np.float32(scale)).astype(np.float32)
+        try:
+            own = NP.compute_dt_np(st["dx"], u, st["v"], st["w"], st["dz_levels"], 0.9, strictness)      # capped at 120
+        except FloatingPointError:           # levels 1, 2 and 5 take the winds in m/s: "time step too small", both must stop
+            from oracle.f90run.runtime import FortranStop
+            with pytest.raises(FortranStop):
+                ref.update_dt(st["dx"], u, st["v"], st["w"], st["dz_levels"], 0.9, strictness)
+            continue
+        assert float(ref.update_dt(st["dx"], u, st["v"], st["w"], st["dz_levels"], 0.9, strictness)) == own
+        for others in ((300.0, 7.5), (500.0,), (119.0, 121.0)):
+            got = float(ref.update_dt(st["dx"], u, st["v"], st["w"], st["dz_levels"], 0.9, strictness, other_images=others))
+            assert got == min(own, min(others), 120.0), (scale, others)
+
+
+@needs_reference
 def test_live_advect_dispatch(ref):
     """advect() of advection_driver.f90:51-66 and the scheme numbers of icar_constants.f90:347-372, executed: which
     scheme runs for which options%physics%advection -- the numbering icar_options uses (include/icar_b200.h) and the
