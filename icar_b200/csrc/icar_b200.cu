@@ -281,7 +281,8 @@ const int kAdvectedSimple[5] = {ICAR_VAR_WATER_VAPOR, ICAR_VAR_CLOUD_WATER, ICAR
 const int kAdvectedThompson[9] = {ICAR_VAR_WATER_VAPOR, ICAR_VAR_CLOUD_WATER, ICAR_VAR_RAIN_IN_AIR,
                                   ICAR_VAR_SNOW_IN_AIR, ICAR_VAR_POTENTIAL_TEMPERATURE, ICAR_VAR_CLOUD_ICE,
                                   ICAR_VAR_GRAUPEL_IN_AIR, ICAR_VAR_ICE_NUMBER, ICAR_VAR_RAIN_NUMBER};
-// order of domain%halo_send (domain_obj.f90:106-119) restricted to the allocated scalars
+// order of domain%halo_send (domain_obj.f90:109-124) restricted to the allocated scalars
+// (tests/test_reference_source.py::test_live_domain_halo_calls executes that routine against these lists)
 const int kExchangedSimple[5] = {ICAR_VAR_WATER_VAPOR, ICAR_VAR_POTENTIAL_TEMPERATURE,
                                  ICAR_VAR_CLOUD_WATER, ICAR_VAR_RAIN_IN_AIR, ICAR_VAR_SNOW_IN_AIR};
 const int kExchangedThompson[9] = {ICAR_VAR_WATER_VAPOR, ICAR_VAR_POTENTIAL_TEMPERATURE, ICAR_VAR_CLOUD_WATER,

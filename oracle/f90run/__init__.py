@@ -401,7 +401,8 @@ class Reference:
     def _domain_module(self):
         if not hasattr(self, "_dom"):
             root = os.path.dirname(os.path.dirname(os.path.dirname(self.mp_path)))
-            self._dom = Module(os.path.join(root, "src", "objects", "domain_obj.f90")).build(["apply_forcing", "enforce_limits"])
+            self._dom = Module(os.path.join(root, "src", "objects", "domain_obj.f90")).build(
+                ["apply_forcing", "enforce_limits", "halo_send", "halo_retrieve", "halo_exchange"])
         return self._dom
 
     def apply_forcing(self, variables, w, seconds, west=True, east=True, south=True, north=True):
@@ -437,6 +438,26 @@ class Reference:
                  "cloud_ice_number", "rain_mass", "rain_number", "snow_mass", "snow_number", "graupel_mass", "graupel_number")
         this = ns(**{n: ns(data_3d=FArr(fields[n].T, (1, 1, 1)) if n in fields else None) for n in names})
         self._domain_module().enforce_limits(this)
+
+    def domain_halo_calls(self, allocated, routine="halo_exchange"):
+        """domain%halo_send / halo_retrieve / halo_exchange, domain_obj.f90:109-155, on a mock domain whose members in
+        `allocated` have their data_3d associated and record what is called on them: [(member, "send" | "retrieve",
+        no_sync)] in the order of the calls."""
+        ns = types.SimpleNamespace
+        names = ("water_vapor", "potential_temperature", "cloud_water_mass", "cloud_number", "cloud_ice_mass",
+                 "cloud_ice_number", "rain_mass", "rain_number", "snow_mass", "snow_number", "graupel_mass", "graupel_number")
+        unknown = set(allocated) - set(names)
+        if unknown:
+            raise KeyError(f"not an exchanged member of domain_t: {sorted(unknown)}")
+        log = []
+
+        def member(n):
+            return ns(data_3d=FArr(np.zeros((1, 1, 1), np.float32), (1, 1, 1)) if n in allocated else None,
+                      send=lambda: log.append((n, "send", False)),
+                      retrieve=lambda no_sync=False: log.append((n, "retrieve", bool(no_sync))))
+        this = ns(**{n: member(n) for n in names})
+        getattr(self._domain_module(), routine)(this)
+        return log
 
     # ---- exchangeable_obj.f90: the halo exchange (coarray PUTs into the neighbours' halo buffers, then copies home)
     def halo_exchange_x(self, tiles, halo):

@@ -10,6 +10,7 @@ translated statement by statement to Python/NumPy, run with IEEE binary32 arithm
 """
 import importlib.util
 import os
+import re
 
 import numpy as np
 import pytest
@@ -340,6 +341,31 @@ def test_live_update_dt(ref, strictness):
         for others in ((300.0, 7.5), (500.0,), (119.0, 121.0)):
             got = float(ref.update_dt(st["dx"], u, st["v"], st["w"], st["dz_levels"], 0.9, strictness, other_images=others))
             assert got == min(own, min(others), 120.0), (scale, others)
+
+
+@needs_reference
+def test_live_domain_halo_calls(ref):
+    """domain%halo_send / halo_retrieve / halo_exchange of domain_obj.f90:109-155 executed on a domain that has the scalars
+    of each scheme: every one of them is sent once and retrieved once, potential_temperature's retrieve is the one that
+    synchronises (the others pass no_sync), and the order of the sends is the order of the product's exchange lists
+    (kExchangedSimple / kExchangedThompson in icar_b200.cu, which icar_halo_send packs in)."""
+    member = {"WATER_VAPOR": "water_vapor", "POTENTIAL_TEMPERATURE": "potential_temperature", "CLOUD_WATER": "cloud_water_mass",
+              "CLOUD_ICE": "cloud_ice_mass", "ICE_NUMBER": "cloud_ice_number", "RAIN_IN_AIR": "rain_mass",
+              "RAIN_NUMBER": "rain_number", "SNOW_IN_AIR": "snow_mass", "GRAUPEL_IN_AIR": "graupel_mass"}
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = open(os.path.join(root, "icar_b200", "csrc", "icar_b200.cu")).read()
+    for table, count in (("kExchangedSimple", 5), ("kExchangedThompson", 9)):
+        m = re.search(table + r"\[\d+\]\s*=\s*\{([^}]*)\}", src)
+        ours = [member[v.strip().replace("ICAR_VAR_", "")] for v in m.group(1).split(",")]
+        assert len(ours) == count
+        log = ref.domain_halo_calls(set(ours))
+        sends = [n for n, what, _ in log if what == "send"]
+        assert sends == ours                                                    # same variables, same order
+        retrieves = [(n, no_sync) for n, what, no_sync in log if what == "retrieve"]
+        assert sorted(n for n, _ in retrieves) == sorted(ours)
+        assert retrieves[0] == ("potential_temperature", False) and all(ns for _, ns in retrieves[1:])
+        assert log == ref.domain_halo_calls(set(ours), "halo_send") + ref.domain_halo_calls(set(ours), "halo_retrieve")
+    assert ref.domain_halo_calls(set()) == []
 
 
 @needs_reference
