@@ -15,7 +15,7 @@ import types
 
 import numpy as np
 
-from .runtime import FArr, f32, f_exp
+from .runtime import FArr, f32, f_exp, unallocated
 from .translate import Module, TranslateError  # noqa: F401
 
 
@@ -38,7 +38,8 @@ class Reference:
         self.adv = Module(self.adv_path, names={"kvars": self.kvars}).build(["advect3d", "upwind_advection", "mpdata_fluxes", "flux_limiter", "flux1", "mpdata"])
         self.mp = Module(self.mp_path).build(["mp_simple_driver"])
         self.upw = Module(os.path.join(phys, "advect.f90"), names={"kvars": self.kvars}).build(["upwind"])
-        self.wind = Module(os.path.join(phys, "wind.f90")).build(["balance_uvw", "calc_divergence"])
+        self.wind_path = os.path.join(phys, "wind.f90")
+        self.wind = Module(self.wind_path).build(["balance_uvw", "calc_divergence"])
         self._time_step_path = os.path.join(root, "src", "main", "time_step.f90")
         self.time_step = Module(self._time_step_path).build(["compute_dt"])
         # icar_constants (Rd, cp, ...) for exner_function: the values come from the source text as well
@@ -254,6 +255,50 @@ class Reference:
                                                  "mpdata": lambda d, o, dt: d.append(("mpdata", float(dt)))}).build(["advect"])
         self._adv_driver.advect(called, ns(physics=ns(advection=int(advection))), f32(120.0))
         return called
+
+    def update_winds_calls(self, windtype, first):
+        """update_winds(domain, options), src/physics/wind.f90:289-369, with every routine it calls replaced by a recorder.
+        first: the call at start-up (domain%sintheta not allocated yet: works on u / v / w themselves) or a later one (works on
+        the next forcing step's winds held in %meta_data%dqdt_3d, update = .True.).  windtype: the name of the constant in
+        icar_constants.f90 ("kwind_linear", ...) or an integer.  Returns [(routine, which arrays, update flag or None)]."""
+        ns = types.SimpleNamespace
+        log = []
+        tags = ["?"]
+
+        def arrays(name):                                   # a one-cell array whose value says which array it is
+            tags.append(name)
+            return FArr(np.full((1, 1, 1), len(tags) - 1, np.float32), (1, 1, 1))
+
+        def which(a):
+            a = getattr(a, "a", a)
+            return tags[int(np.asarray(a).reshape(-1)[0])]
+        u, v, w = (ns(data_3d=arrays(n), meta_data=ns(dqdt_3d=arrays(n + " of the next forcing step"))) for n in "uvw")
+        dom = ns(sintheta=unallocated(np.float32, 2) if first else arrays("sintheta"), costheta=arrays("costheta"), u=u, v=v, w=w,
+                 jacobian_u=arrays("jacobian_u"), jacobian_v=arrays("jacobian_v"), jacobian_w=arrays("jacobian_w"),
+                 advection_dz=arrays("advection_dz"), dx=f32(4000.0), jacobian=arrays("jacobian"),
+                 zfr_u=arrays("zfr_u"), zfr_v=arrays("zfr_v"), zr_u=arrays("zr_u"), zr_v=arrays("zr_v"))
+        c = self.constants
+        wt = int(getattr(c, windtype)) if isinstance(windtype, str) else int(windtype)
+        opts = ns(physics=ns(windtype=wt), lt_options=ns(vert_smooth=2),
+                  parameters=ns(advect_density=False, use_terrain_difference=False))
+        if not hasattr(self, "_update_winds"):
+            self._update_winds = Module(
+                self.wind_path, names={n: int(getattr(c, n)) for n in ("kwind_linear", "kconserve_mass", "kiterative_winds",
+                                                                         "klinear_iterative_winds")},
+                overrides={
+                    "init_winds": lambda M, d, o: self._uw_log.append(("init_winds", None, None)),
+                    "make_winds_grid_relative": lambda M, uu, vv, ww, st, ct: self._uw_log.append(
+                        ("make_winds_grid_relative", self._uw_which(uu), None)),
+                    "mass_conservative_acceleration": lambda M, uu, vv, zu, zv: self._uw_log.append(
+                        ("mass_conservative_acceleration", self._uw_which(uu), None)),
+                    "iterative_winds": lambda M, d, o, update_in=False: self._uw_log.append(("iterative_winds", None, bool(update_in))),
+                    "balance_uvw": lambda M, uu, vv, ww, ju, jv, jw, dz, dx, jaco, o: self._uw_log.append(
+                        ("balance_uvw", self._uw_which(uu), None))},
+                externals={"linear_perturb": lambda d, o, vsmooth, reverse, use_density, update=False: self._uw_log.append(
+                    ("linear_perturb", "reverse" if reverse else None, bool(update)))}).build(["update_winds"])
+        self._uw_log, self._uw_which = log, which
+        self._update_winds.update_winds(dom, opts)
+        return log
 
     def step_loop(self, start_seconds, end_seconds, dts):
         """step(domain, end_time, options), time_step.f90:438-549, executed as written on a mock domain whose physics are

@@ -369,6 +369,28 @@ def test_live_domain_halo_calls(ref):
 
 
 @needs_reference
+def test_live_update_winds_order(ref):
+    """update_winds of src/physics/wind.f90:289-369 executed with its callees recorded: for windtype = kWIND_LINEAR the
+    once-per-forcing-interval wind update is  rotate to the grid -> linear_perturb(reverse = .False.) -> balance_uvw,
+    on u / v / w at start-up (update = .False.) and on the next forcing step's winds afterwards (update = .True.) --
+    the order `bench.py --linear-winds` and the shim's b200_linear_perturb keep (icar_linear_perturb, then
+    icar_balance_uvw; the rotation is the identity on the ideal grids and stays on the host)."""
+    first = ref.update_winds_calls("kwind_linear", True)
+    assert first == [("init_winds", None, None), ("make_winds_grid_relative", "u", None), ("linear_perturb", None, False),
+                     ("balance_uvw", "u", None)]
+    later = ref.update_winds_calls("kwind_linear", False)
+    nxt = "u of the next forcing step"
+    assert later == [("make_winds_grid_relative", nxt, None), ("linear_perturb", None, True), ("balance_uvw", nxt, None)]
+    # without a wind scheme only the balance remains; every variant ends with it
+    assert [c[0] for c in ref.update_winds_calls(0, True)] == ["init_winds", "make_winds_grid_relative", "balance_uvw"]
+    for wt in ("kconserve_mass", "kiterative_winds", "klinear_iterative_winds"):
+        for f in (True, False):
+            assert ref.update_winds_calls(wt, f)[-1][0] == "balance_uvw"
+    bench = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "bench.py")).read()
+    assert bench.index("dom.linear_perturb(") < bench.index("dom.balance_uvw()")
+
+
+@needs_reference
 def test_live_advect_dispatch(ref):
     """advect() of advection_driver.f90:51-66 and the scheme numbers of icar_constants.f90:347-372, executed: which
     scheme runs for which options%physics%advection -- the numbering icar_options uses (include/icar_b200.h) and the
